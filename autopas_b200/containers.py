@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference's container / traversal / functor interface on top of the C ABI.
+
+Names, argument meaning and error behaviour follow the reference so that the parity tests read like the reference's:
+  * GpuParticleContainer  <-> autopas::ParticleContainerInterface (src/autopas/containers/ParticleContainerInterface.h)
+  * GpuTraversal          <-> autopas::TraversalInterface (src/autopas/containers/TraversalInterface.h:18-84)
+  * LJFunctor             <-> mdLib::LJFunctor (applicationLibrary/molecularDynamics/molecularDynamicsLibrary/LJFunctor.h)
+  * ParticlePropertiesLibrary <-> ParticlePropertiesLibrary.h
+The C++ drop-in (autopas_b200/shim/GpuContainers.h) is the same layer for a C++ host. All numerics happen in the CUDA
+library; this module only marshals numpy arrays.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from .capi import ApbError
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class ParticlePropertiesLibrary:
+    """Per-type epsilon / sigma / mass and the mixing table (ParticlePropertiesLibrary.h:34-99, 444-473)."""
+
+    def __init__(self, cutoff):
+        self._cutoff = float(cutoff)
+        self._eps, self._sigma, self._mass, self._nu = [], [], [], []
+        self._table = None
+
+    def addSiteType(self, siteId, mass):
+        if siteId != len(self._mass):
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "site types must be registered with consecutive ids")
+        self._mass.append(float(mass))
+        self._eps.append(0.0)
+        self._sigma.append(0.0)
+        self._nu.append(0.0)
+
+    def addLJParametersToSite(self, siteId, epsilon, sigma):
+        self._eps[siteId] = float(epsilon)
+        self._sigma[siteId] = float(sigma)
+
+    def addATMParametersToSite(self, siteId, nu):
+        self._nu[siteId] = float(nu)
+
+    def getNumberRegisteredSiteTypes(self):
+        return len(self._mass)
+
+    def calculateMixingCoefficients(self):
+        T = len(self._mass)
+        if T == 0:
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "calculateMixingCoefficients without registered site types")
+        out = np.zeros(T * T * 3)
+        rc = capi.load().apb_make_lj_mixing_table(T, _ptr(_f64(self._eps)), _ptr(_f64(self._sigma)), self._cutoff,
+                                                  _ptr(out))
+        if rc != 0:
+            raise ApbError(rc, "apb_make_lj_mixing_table failed")
+        self._table = out
+
+    def getMixingTable(self):
+        if self._table is None:
+            self.calculateMixingCoefficients()
+        return self._table
+
+    def getMixing24Epsilon(self, i, j):
+        return self.getMixingTable()[3 * (i * len(self._mass) + j)]
+
+    def getMixingSigmaSquared(self, i, j):
+        return self.getMixingTable()[3 * (i * len(self._mass) + j) + 1]
+
+    def getMixingShift6(self, i, j):
+        return self.getMixingTable()[3 * (i * len(self._mass) + j) + 2]
+
+
+class LJFunctor:
+    """mdLib::LJFunctor: template flags become constructor arguments (LJFunctor.h:39-41)."""
+
+    def __init__(self, cutoff, particlePropertiesLibrary=None, applyShift=False, useMixing=False,
+                 calculateGlobals=False, countFLOPs=False):
+        if useMixing and particlePropertiesLibrary is None:
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "Mixing without a ParticlePropertiesLibrary is not possible")
+        if particlePropertiesLibrary is not None and not useMixing:
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "Not using Mixing but using a ParticlePropertiesLibrary is not allowed")
+        self._cutoff = float(cutoff)
+        self._ppl = particlePropertiesLibrary
+        self.applyShift, self.useMixing = bool(applyShift), bool(useMixing)
+        self.calculateGlobals, self.countFLOPs = bool(calculateGlobals), bool(countFLOPs)
+        self._epsilon24, self._sigmaSquared = 0.0, 0.0
+        self._raw = capi.TraversalResult()
+        self._postProcessed = False
+        self._upot = 0.0
+        self._virial = 0.0
+
+    # --- Functor interface
+    def getName(self):
+        return "LJFunctorB200"
+
+    def isRelevantForTuning(self):
+        return True
+
+    def allowsNewton3(self):
+        return True
+
+    def allowsNonNewton3(self):
+        return True
+
+    def getCutoff(self):
+        return self._cutoff
+
+    def setParticleProperties(self, epsilon24, sigmaSquared):
+        self._epsilon24, self._sigmaSquared = float(epsilon24), float(sigmaSquared)
+
+    def initTraversal(self):
+        self._raw = capi.TraversalResult()
+        self._postProcessed = False
+        self._upot = 0.0
+        self._virial = 0.0
+
+    def _deposit(self, raw):
+        """Called by the GPU traversal: adds the device accumulators, like a thread's _aosThreadData entry."""
+        self._raw.upot_sum += raw.upot_sum
+        for d in range(3):
+            self._raw.virial_sum[d] += raw.virial_sum[d]
+        for name in ("num_dist_calls", "num_kernel_calls_n3", "num_kernel_calls_no_n3", "num_global_calcs_n3",
+                     "num_global_calcs_no_n3"):
+            setattr(self._raw, name, getattr(self._raw, name) + getattr(raw, name))
+
+    def endTraversal(self, newton3):
+        if self._postProcessed:
+            raise ApbError(capi.ERR_STATE, "Already postprocessed, endTraversal(bool newton3) was called twice without "
+                                           "calling initTraversal().")
+        if self.calculateGlobals:
+            u, v = ctypes.c_double(), ctypes.c_double()
+            capi.load().apb_lj_end_traversal(ctypes.byref(self._raw), ctypes.byref(u), ctypes.byref(v))
+            self._upot, self._virial = u.value, v.value
+            self._postProcessed = True
+
+    def getPotentialEnergy(self):
+        if not self.calculateGlobals:
+            raise ApbError(capi.ERR_STATE, "Trying to get potential energy even though calculateGlobals is false.")
+        if not self._postProcessed:
+            raise ApbError(capi.ERR_STATE, "Cannot get potential energy, because endTraversal was not called.")
+        return self._upot
+
+    def getVirial(self):
+        if not self.calculateGlobals:
+            raise ApbError(capi.ERR_STATE, "Trying to get virial even though calculateGlobals is false.")
+        if not self._postProcessed:
+            raise ApbError(capi.ERR_STATE, "Cannot get virial, because endTraversal was not called.")
+        return self._virial
+
+    def getNumFLOPs(self):
+        if not self.countFLOPs:
+            return 2 ** 64 - 1  # std::numeric_limits<size_t>::max() (LJFunctor.h:786-788)
+        return capi.load().apb_lj_num_flops(ctypes.byref(self._raw), 1 if self.applyShift else 0)
+
+    def getHitRate(self):
+        if not self.countFLOPs or self._raw.num_dist_calls == 0:
+            return float("nan")
+        return (self._raw.num_kernel_calls_no_n3 + self._raw.num_kernel_calls_n3) / self._raw.num_dist_calls
+
+    # --- marshalling
+    def _c_functor(self):
+        f = capi.Functor()
+        f.kind = capi.FUNCTOR_LJ
+        f.flags = ((capi.FLAG_APPLY_SHIFT if self.applyShift else 0) | (capi.FLAG_USE_MIXING if self.useMixing else 0) |
+                   (capi.FLAG_CALC_GLOBALS if self.calculateGlobals else 0) |
+                   (capi.FLAG_COUNT_FLOPS if self.countFLOPs else 0))
+        f.cutoff = self._cutoff
+        f.epsilon24 = self._epsilon24
+        f.sigma_squared = self._sigmaSquared
+        if self.useMixing:
+            self._table_keepalive = _f64(self._ppl.getMixingTable())
+            f.num_types = self._ppl.getNumberRegisteredSiteTypes()
+            f.mixing_table = self._table_keepalive.ctypes.data
+        return f
+
+
+class GpuTraversal:
+    """TraversalInterface: (traversal option, functor, newton3). Data layout is SoA only."""
+
+    def __init__(self, traversalOption, functor, useNewton3):
+        if traversalOption not in capi.TRAVERSAL_NAMES:
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, f"unknown traversal option {traversalOption}")
+        self.option = traversalOption
+        self.functor = functor
+        self.useNewton3 = bool(useNewton3)
+
+    def getTraversalType(self):
+        return self.option
+
+    def getUseNewton3(self):
+        return self.useNewton3
+
+    def getDataLayout(self):
+        return "soa"
+
+
+class GpuParticleContainer:
+    """gpuLinkedCells / gpuVerletClusterLists behind ParticleContainerInterface's method names."""
+
+    def __init__(self, containerOption, boxMin, boxMax, cutoff, skin, cellSizeFactor=1.0, clusterSize=4,
+                 particleKind=capi.PARTICLE_LJ, device=0):
+        if containerOption not in capi.CONTAINER_NAMES:
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, f"unknown container option {containerOption}")
+        self._lib = capi.load()
+        cfg = capi.Config()
+        for d in range(3):
+            cfg.box_min[d] = float(boxMin[d])
+            cfg.box_max[d] = float(boxMax[d])
+        cfg.cutoff, cfg.skin = float(cutoff), float(skin)
+        cfg.cell_size_factor = float(cellSizeFactor)
+        cfg.cluster_size = int(clusterSize)
+        cfg.container = capi.CONTAINER_NAMES[containerOption]
+        cfg.particle_kind = int(particleKind)
+        cfg.device = int(device)
+        self._cfg = cfg
+        self.containerOption = containerOption
+        self._h = capi._H()
+        rc = self._lib.apb_create(ctypes.byref(cfg), ctypes.byref(self._h))
+        if rc != 0:
+            raise ApbError(rc, self._lib.apb_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.apb_destroy(self._h)
+            self._h = capi._H()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ApbError(rc, self._lib.apb_last_error(self._h).decode())
+
+    # --- getters
+    def getContainerType(self):
+        return self.containerOption
+
+    def getBoxMin(self):
+        return tuple(self._cfg.box_min)
+
+    def getBoxMax(self):
+        return tuple(self._cfg.box_max)
+
+    def getCutoff(self):
+        return self._cfg.cutoff
+
+    def getVerletSkin(self):
+        return self._cfg.skin
+
+    def getInteractionLength(self):
+        return self._cfg.cutoff + self._cfg.skin
+
+    def getTraversalSelectorInfo(self):
+        g = capi.Geometry()
+        self._check(self._lib.apb_get_geometry(self._h, ctypes.byref(g)))
+        return g
+
+    # --- storage
+    def addParticles(self, x, y, z, ids=None, types=None, checkInBox=True):
+        self._add(x, y, z, ids, types, capi.OWN_OWNED, checkInBox)
+
+    def addHaloParticles(self, x, y, z, ids=None, types=None):
+        self._add(x, y, z, ids, types, capi.OWN_HALO, False)
+
+    def _add(self, x, y, z, ids, types, own, check):
+        x, y, z = _f64(x), _f64(y), _f64(z)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+        types = None if types is None else np.ascontiguousarray(types, dtype=np.int32)
+        self._check(self._lib.apb_add_particles(self._h, len(x), _ptr(x), _ptr(y), _ptr(z), _ptr(ids), _ptr(types), own,
+                                                1 if check else 0))
+
+    def updateHaloParticles(self, ids, x, y, z):
+        """Bulk ParticleContainerInterface::updateHaloParticle; returns the number of ids without a halo slot."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        x, y, z = _f64(x), _f64(y), _f64(z)
+        nf = ctypes.c_int64()
+        self._check(self._lib.apb_update_halo_particles(self._h, len(ids), _ptr(ids), _ptr(x), _ptr(y), _ptr(z),
+                                                        ctypes.byref(nf)))
+        return nf.value
+
+    def deleteHaloParticles(self):
+        self._check(self._lib.apb_delete_halo_particles(self._h))
+
+    def deleteAllParticles(self):
+        self._check(self._lib.apb_delete_all_particles(self._h))
+
+    def getNumberOfParticles(self, behavior="owned"):
+        o, h = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.apb_get_num_particles(self._h, ctypes.byref(o), ctypes.byref(h)))
+        return {"owned": o.value, "halo": h.value, "ownedOrHalo": o.value + h.value}[behavior]
+
+    def size(self):
+        return self.getNumberOfParticles("ownedOrHalo")
+
+    def numSlots(self):
+        n = ctypes.c_int64()
+        self._check(self._lib.apb_get_num_slots(self._h, ctypes.byref(n)))
+        return n.value
+
+    # --- host mirror (what the iterators expose), storage order
+    def downloadColumn(self, name):
+        out = np.zeros(self.numSlots())
+        self._check(self._lib.apb_download_column(self._h, capi.COL[name], _ptr(out)))
+        return out
+
+    def uploadColumn(self, name, values):
+        values = _f64(values)
+        if len(values) != self.numSlots():
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "column length must equal the number of slots")
+        self._check(self._lib.apb_upload_column(self._h, capi.COL[name], _ptr(values)))
+
+    def downloadIds(self):
+        n = self.numSlots()
+        ids = np.zeros(n, dtype=np.int64)
+        types = np.zeros(n, dtype=np.int32)
+        own = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.apb_download_ids(self._h, _ptr(ids), _ptr(types), _ptr(own)))
+        return ids, types, own
+
+    def uploadOwnership(self, own):
+        own = np.ascontiguousarray(own, dtype=np.int32)
+        self._check(self._lib.apb_upload_ownership(self._h, _ptr(own)))
+
+    def uploadPositions(self, x, y, z):
+        self._check(self._lib.apb_upload_positions(self._h, _ptr(x), _ptr(y), _ptr(z)))
+
+    def downloadForces(self, fx, fy, fz):
+        self._check(self._lib.apb_download_forces(self._h, _ptr(fx), _ptr(fy), _ptr(fz)))
+
+    def resetForces(self, fx=0.0, fy=0.0, fz=0.0):
+        self._check(self._lib.apb_reset_forces(self._h, fx, fy, fz))
+
+    def forcesById(self, n):
+        """Forces of the non-dummy particles scattered to an (n, 3) array indexed by particle id (test helper)."""
+        ids, _, own = self.downloadIds()
+        out = np.zeros((n, 3))
+        m = (own != capi.OWN_DUMMY) & (ids >= 0) & (ids < n)
+        for d, name in enumerate(("FX", "FY", "FZ")):
+            out[ids[m], d] = self.downloadColumn(name)[m]
+        return out
+
+    # --- maintenance and the hot path
+    def updateContainer(self, keepNeighborListsValid):
+        nl = ctypes.c_int64()
+        self._check(self._lib.apb_update_container(self._h, 1 if keepNeighborListsValid else 0, ctypes.byref(nl)))
+        n = nl.value
+        cols = [np.zeros(n) for _ in range(6)]
+        ids = np.zeros(n, dtype=np.int64)
+        types = np.zeros(n, dtype=np.int32)
+        if n:
+            self._check(self._lib.apb_get_leavers(self._h, *[_ptr(c) for c in cols], _ptr(ids), _ptr(types)))
+        return {"x": cols[0], "y": cols[1], "z": cols[2], "vx": cols[3], "vy": cols[4], "vz": cols[5], "id": ids,
+                "type": types}
+
+    def rebuildNeighborLists(self, traversal):
+        self._check(self._lib.apb_rebuild_neighbor_lists(self._h, capi.TRAVERSAL_NAMES[traversal.option],
+                                                         1 if traversal.useNewton3 else 0))
+
+    def computeInteractions(self, traversal):
+        """ParticleContainerInterface::computeInteractions: runs the traversal and deposits the device accumulators
+        into the functor; the caller brackets it with functor.initTraversal() / endTraversal(newton3)."""
+        functor = traversal.functor
+        cf = functor._c_functor()
+        raw = capi.TraversalResult()
+        self._check(self._lib.apb_compute_interactions(self._h, capi.TRAVERSAL_NAMES[traversal.option], ctypes.byref(cf),
+                                                       1 if traversal.useNewton3 else 0, ctypes.byref(raw)))
+        functor._deposit(raw)
+        return raw
+
+    # --- parity artefacts
+    def debugCellOfSlot(self):
+        out = np.zeros(self.numSlots(), dtype=np.int64)
+        self._check(self._lib.apb_debug_cell_of_slot(self._h, _ptr(out)))
+        return out
+
+    def debugClusterPairs(self):
+        g = self.getTraversalSelectorInfo()
+        out = np.zeros((max(g.num_cluster_pairs, 1), 2), dtype=np.int64)
+        self._check(self._lib.apb_debug_cluster_pairs(self._h, _ptr(out)))
+        return out[:g.num_cluster_pairs]

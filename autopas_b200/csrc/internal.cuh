@@ -1,0 +1,218 @@
+// Internal state of one container handle and helpers shared by the translation units of libautopas_b200.so.
+// Nothing here is visible through the C ABI (include/autopas_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "autopas_b200.h"
+
+#define APB_OWN_DUMMY 0
+#define APB_OWN_OWNED 1
+#define APB_OWN_HALO 2
+
+#define APB_MAX_STENCIL 512
+
+// ---- geometry passed to kernels by value -----------------------------------------------------------------------
+// LinkedCells grid: restates CellBlock3D::rebuild (containers/CellBlock3D.h:360-426); filled on the host.
+struct LCGeom {
+  double boxMin[3], boxMax[3];
+  double haloBoxMin[3], haloBoxMax[3];
+  double cellLength[3], cellLengthReciprocal[3];
+  int cellsPerDim[3];  // incl. halo
+  int cellsPerInteractionLength;
+  int numCells;
+};
+
+// VerletClusterLists tower grid: restates ClusterTowerBlock2D::estimateOptimalGridSideLength / resize
+// (containers/verletClusterLists/ClusterTowerBlock2D.h:89-114, 140-168); filled on the host (uses std::cbrt).
+struct VCLGeom {
+  double boxMin[3], boxMax[3];
+  double haloBoxMin[3], haloBoxMax[3];
+  double side[2], sideReciprocal[2];
+  double interactionLength, interactionLengthSqr;
+  int towersPerDim[2];
+  int numTowersPerInteractionLength;
+  int numTowers;
+  int clusterSize;
+};
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct apb_handle_s {
+  apb_config cfg{};
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // copy stream for overlapped transfers
+  std::string err;
+  bool poisoned = false;
+
+  // ---- SoA particle storage (slots [0, nslots)), double-buffered for the sort ----
+  int64_t nslots = 0;
+  int64_t cap = 0;
+  bool active[APB_NUM_COLUMNS]{};
+  double *col[APB_NUM_COLUMNS]{};
+  double *colTmp[APB_NUM_COLUMNS]{};
+  int64_t *id = nullptr, *idTmp = nullptr;
+  int32_t *type = nullptr, *typeTmp = nullptr;
+  int32_t *own = nullptr, *ownTmp = nullptr;
+
+  // ---- structure ----
+  bool structureValid = false;  // cells / towers+lists match the storage order
+  int builtNewton3 = -1;        // VCL lists: which newton3 mode they were built for
+  LCGeom lc{};
+  VCLGeom vcl{};
+  int64_t numCells = 0;  // cells or towers
+  DevBuf key, rank, count, start, perm, slotCell, scanTmp, sortK1, sortK2, sortV;
+  int stencilN = 0;  // LC neighbour-cell offsets (incl. self at index 0)
+  int stencil[APB_MAX_STENCIL][3];
+  DevBuf stencilDev;
+
+  // VCL
+  int64_t numClusters = 0;
+  int64_t numPairs = 0;
+  DevBuf clBoxMin, clBoxMax;  // 3 doubles per cluster each (SoA: [3][numClusters])
+  DevBuf clHasOwned, clIsHalo, clTower;
+  DevBuf twFirstCluster, twNumClusters, twFirstOwned, twFirstTailHalo;
+  DevBuf nbrCount, nbrStart, nbrList;
+  // per-particle lists for APB_TRAVERSAL_GPUVCL_PRUNED (pruned.cu)
+  bool prunedValid = false;
+  int prunedTiles = 0;
+  int prunedMaxStaged = 0;  // clusters
+  long long prunedRows = 0; // list rows of 32 entries
+  DevBuf prNumStaged, prStagedStart, prStaged, prWarpLen, prWarpStart, prLists;
+
+  // ---- reductions / results ----
+  DevBuf partials;
+  DevBuf result;  // apb_traversal_result on device
+  DevBuf mixDev;
+  std::vector<double> mixHostCache;
+
+  // ---- leavers (library-owned, valid until the next update_container) ----
+  int64_t numLeavers = 0;
+  DevBuf leaverIdx;
+  std::vector<double> leaverCols[6];
+  std::vector<int64_t> leaverIds;
+  std::vector<int32_t> leaverTypes;
+
+  // pinned staging for host transfers
+  void *pinned = nullptr;
+  size_t pinnedCap = 0;
+
+  int64_t numOwned = 0, numHalo = 0;  // refreshed lazily
+  bool countsValid = false;
+
+  int fail(int code, const std::string &msg) {
+    err = msg;
+    return code;
+  }
+  int failCuda(cudaError_t e, const char *what, const char *file, int line) {
+    poisoned = true;
+    err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " at " + file + ":" +
+          std::to_string(line);
+    return APB_ERR_CUDA;
+  }
+};
+
+#define APB_CUDA(call)                                                      \
+  do {                                                                      \
+    cudaError_t e_ = (call);                                                \
+    if (e_ != cudaSuccess) return h->failCuda(e_, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define APB_CHECK(expr)              \
+  do {                               \
+    int rc_ = (expr);                \
+    if (rc_ != APB_OK) return rc_;   \
+  } while (0)
+
+#define APB_ENTRY(h)                                                                       \
+  if (!(h)) return APB_ERR_INVALID_ARGUMENT;                                               \
+  if ((h)->poisoned) return APB_ERR_CUDA;                                                  \
+  {                                                                                        \
+    cudaError_t e_ = cudaSetDevice((h)->cfg.device);                                       \
+    if (e_ != cudaSuccess) return (h)->failCuda(e_, "cudaSetDevice", __FILE__, __LINE__);  \
+  }
+
+// grow-only device buffer
+int apbEnsure(apb_handle h, DevBuf &b, size_t bytes);
+// grow particle storage to at least `slots` slots, preserving [0, nslots)
+int apbReserveSlots(apb_handle h, int64_t slots);
+int apbEnsurePinned(apb_handle h, size_t bytes);
+// permute the whole storage: slot q of the new order takes old slot perm[q] (perm < 0: dummy); swaps double buffers
+int apbPermuteStorage(apb_handle h, const int *perm, int64_t newSlots);
+
+// exclusive scan of n int32 (device), returns total through *totalDev (device int64) if non-null
+int apbExclusiveScan(apb_handle h, const int *in, int *out, int64_t n, long long *totalDev);
+
+// build.cu
+int apbRebuildLinkedCells(apb_handle h);
+int apbRebuildVCL(apb_handle h, int newton3);
+int apbBuildPruned(apb_handle h);
+void apbComputeLCGeom(const apb_config &cfg, LCGeom &g);
+int apbComputeStencil(apb_handle h);
+
+// lj.cu
+int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3, apb_traversal_result *out);
+
+static inline int apbDivUp(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+// ---- device helpers ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// CellBlock3D::get3DIndexOfPosition (containers/CellBlock3D.h:321-349) + threeToOneD
+// (utils/ThreeDimensionalMapping.h:29-32). No product-sum appears, so no FMA contraction can change the result.
+__host__ __device__ inline int apbCellIndexLC(const LCGeom &g, double px, double py, double pz) {
+  const double pos[3] = {px, py, pz};
+  int idx[3];
+  for (int d = 0; d < 3; ++d) {
+    const long long value =
+        static_cast<long long>(floor((pos[d] - g.boxMin[d]) * g.cellLengthReciprocal[d])) + g.cellsPerInteractionLength;
+    long long v = value < 0 ? 0 : value;
+    if (v > g.cellsPerDim[d] - 1) v = g.cellsPerDim[d] - 1;
+    int c = static_cast<int>(v);
+    if (pos[d] >= g.boxMax[d]) {
+      const int firstUpperHalo = g.cellsPerDim[d] - g.cellsPerInteractionLength;
+      c = c > firstUpperHalo ? c : firstUpperHalo;
+    } else if (pos[d] < g.boxMin[d] && c == g.cellsPerInteractionLength) {
+      --c;
+    } else if (pos[d] < g.boxMax[d] && c == g.cellsPerDim[d] - g.cellsPerInteractionLength) {
+      --c;
+    }
+    idx[d] = c;
+  }
+  return (idx[2] * g.cellsPerDim[1] + idx[1]) * g.cellsPerDim[0] + idx[0];
+}
+
+// ClusterTowerBlock2D::getTowerIndex2DAtPosition (ClusterTowerBlock2D.h:220-245), 1-D = x + y*nx (:258-262)
+__host__ __device__ inline int apbTowerIndex(const VCLGeom &g, double px, double py) {
+  const double pos[2] = {px, py};
+  int idx[2];
+  for (int d = 0; d < 2; ++d) {
+    const long long value = static_cast<long long>(floor((pos[d] - g.boxMin[d]) * g.sideReciprocal[d])) +
+                            g.numTowersPerInteractionLength;
+    long long v = value < 0 ? 0 : value;
+    if (v > g.towersPerDim[d] - 1) v = g.towersPerDim[d] - 1;
+    int c = static_cast<int>(v);
+    if (pos[d] >= g.haloBoxMax[d]) {
+      c = g.towersPerDim[d] - 1;
+    } else if (pos[d] < g.haloBoxMin[d]) {
+      c = 0;
+    }
+    idx[d] = c;
+  }
+  return idx[0] + idx[1] * g.towersPerDim[0];
+}
+
+// a cell can hold owned particles iff it lies in the non-halo block (CellBlock3D::cellCanContainOwnedParticles)
+__host__ __device__ inline bool apbCellCanOwn(const LCGeom &g, int cx, int cy, int cz) {
+  const int o = g.cellsPerInteractionLength;
+  return cx >= o && cx < g.cellsPerDim[0] - o && cy >= o && cy < g.cellsPerDim[1] - o && cz >= o &&
+         cz < g.cellsPerDim[2] - o;
+}
+#endif

@@ -1,0 +1,416 @@
+// Lennard-Jones 12-6 force kernels (fp64) for the gpuLinkedCells and gpuVerletClusterLists containers.
+// Arithmetic restated from mdLib::LJFunctor (applicationLibrary/molecularDynamics/molecularDynamicsLibrary/LJFunctor.h):
+//   pair kernel :146-159 (AoS, canonical) / :480-499 (SoA), globals :518-531, counters :510-516, 533-539,
+//   SoAFunctorSingle is always newton3 (:200-203, :345), N3-off cell pairs are evaluated in both directions
+//   (baseFunctors/CellFunctor.h:266-274), halo-only cell pairs are skipped (:173-184),
+//   VCL cluster traversal: traversals/VCLClusterFunctor.h:38-96.
+// The kernels are FP64-pipe bound (no tensor cores: not a contraction). One thread owns one particle i and keeps its
+// force in registers; with newton3 the reaction on j goes through fp64 atomics (RED.ADD.F64).
+#include "internal.cuh"
+#include "lj_device.cuh"
+
+// ------------------------------------------------------------------------------------------------------------------
+// block reduction of per-thread statistics into one partial per block; final pass sums partials in fixed order
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void kReducePartials(const LJStats *__restrict__ partials, int numBlocks, apb_traversal_result *out) {
+  __shared__ LJStats sh[32];
+  LJStats s;
+  ljStatsZero(s);
+  for (int b = threadIdx.x; b < numBlocks; b += blockDim.x) ljStatsAdd(s, partials[b]);
+  ljStatsWarpReduce(s);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    LJStats t;
+    ljStatsZero(t);
+    if (lane < (blockDim.x >> 5)) t = sh[lane];
+    ljStatsWarpReduce(t);
+    if (lane == 0) {
+      out->upot_sum = t.upot;
+      out->virial_sum[0] = t.vir[0];
+      out->virial_sum[1] = t.vir[1];
+      out->virial_sum[2] = t.vir[2];
+      out->num_dist_calls = t.dist;
+      out->num_kernel_calls_n3 = t.kN3;
+      out->num_kernel_calls_no_n3 = t.kNoN3;
+      out->num_global_calcs_n3 = t.gN3;
+      out->num_global_calcs_no_n3 = t.gNoN3;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LinkedCells: one thread per particle slot (slots are sorted by cell), neighbour cells from the stencil
+// ------------------------------------------------------------------------------------------------------------------
+struct LCArgs {
+  LCGeom g;
+  int64_t n;
+  const double *x, *y, *z;
+  double *fx, *fy, *fz;
+  const int32_t *type, *own;
+  const int *slotCell, *cellStart;
+  const int *stencil;  // 3 ints per entry, entry 0 = self
+  int stencilN;
+  int processHaloCells;  // also compute (discarded) forces on particles of halo cells, like the reference does
+  LJParams p;
+  LJStats *partials;
+};
+
+template <bool MIX, bool STATS, bool N3>
+__global__ void __launch_bounds__(128) kLJLinkedCells(LCArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  LJStats st;
+  ljStatsZero(st);
+  const bool inRange = i < a.n;
+  const int ownI = inRange ? a.own[i] : APB_OWN_DUMMY;
+  if (ownI != APB_OWN_DUMMY) {
+    const LCGeom &g = a.g;
+    const int c = a.slotCell[i];
+    const int cx = c % g.cellsPerDim[0], cy = (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+              cz = c / (g.cellsPerDim[0] * g.cellsPerDim[1]);
+    const bool canOwnI = apbCellCanOwn(g, cx, cy, cz);
+    if (canOwnI || N3 || a.processHaloCells) {
+      const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+      const int ti = MIX ? a.type[i] : 0;
+      const double wI = ownI == APB_OWN_OWNED ? 1. : 0.;
+      double fxa = 0., fya = 0., fza = 0.;
+      for (int s = 0; s < a.stencilN; ++s) {
+        const int ox = a.stencil[3 * s], oy = a.stencil[3 * s + 1], oz = a.stencil[3 * s + 2];
+        const int lin = (oz * g.cellsPerDim[1] + oy) * g.cellsPerDim[0] + ox;
+        if (N3 && lin < 0) continue;  // forward neighbours only: each cell pair once
+        const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
+        if (nx < 0 || ny < 0 || nz < 0 || nx >= g.cellsPerDim[0] || ny >= g.cellsPerDim[1] || nz >= g.cellsPerDim[2])
+          continue;
+        const bool canOwnJ = apbCellCanOwn(g, nx, ny, nz);
+        if (!canOwnI && !canOwnJ) continue;  // CellFunctor.h:173-184
+        const int c2 = c + lin;
+        const int j0 = a.cellStart[c2], j1 = a.cellStart[c2 + 1];
+        const bool self = s == 0;
+        for (int j = j0; j < j1; ++j) {
+          if (self && (N3 ? j <= i : j == i)) continue;
+          const int ownJ = a.own[j];
+          if (ownJ == APB_OWN_DUMMY) continue;
+          const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+          const double dr2 = ljDist2(drx, dry, drz);
+          const bool hit = dr2 <= a.p.cutoff2;
+          // counters: a same-cell pair is one newton3 evaluation in the reference, whatever the newton3 flag
+          const bool countThis = STATS && (!self || N3 || j > i);
+          if (countThis) ++st.dist;
+          if (hit) {
+            double upot6;
+            const double fac = ljEval<MIX>(a.p, dr2, ti, MIX ? a.type[j] : 0, upot6);
+            const double fx = drx * fac, fy = dry * fac, fz = drz * fac;
+            fxa += fx;
+            fya += fy;
+            fza += fz;
+            if (N3) {
+              atomicAdd(&a.fx[j], -fx);
+              atomicAdd(&a.fy[j], -fy);
+              atomicAdd(&a.fz[j], -fz);
+            }
+            if (STATS) {
+              const double wJ = ownJ == APB_OWN_OWNED ? 1. : 0.;
+              // globals: every evaluated direction adds upot6 * [i owned] (+ [j owned] with newton3)
+              const double w = N3 ? wI + wJ : wI;
+              st.upot += upot6 * w;
+              st.vir[0] += drx * fx * w;
+              st.vir[1] += dry * fy * w;
+              st.vir[2] += drz * fz * w;
+              if (countThis) {
+                if (N3 || self) {
+                  ++st.kN3;
+                  ++st.gN3;
+                } else {
+                  ++st.kNoN3;
+                  ++st.gNoN3;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (N3) {
+        atomicAdd(&a.fx[i], fxa);
+        atomicAdd(&a.fy[i], fya);
+        atomicAdd(&a.fz[i], fza);
+      } else {
+        a.fx[i] += fxa;
+        a.fy[i] += fya;
+        a.fz[i] += fza;
+      }
+    }
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// VerletClusterLists, list-faithful traversal: every listed cluster pair costs M x M distance evaluations
+// (VCLClusterFunctor.h:38-96). One thread per slot; the M lanes of a cluster walk the cluster's list together and read
+// the neighbour cluster's particles through broadcast loads.
+// ------------------------------------------------------------------------------------------------------------------
+struct VCLArgs {
+  int64_t n;
+  int M;
+  const double *x, *y, *z;
+  double *fx, *fy, *fz;
+  const int32_t *type, *own;
+  const int *clIsHalo, *nbrStart, *nbrList;
+  LJParams p;
+  LJStats *partials;
+};
+
+template <bool MIX, bool STATS, bool N3>
+__global__ void __launch_bounds__(128) kLJClusterPairs(VCLArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  LJStats st;
+  ljStatsZero(st);
+  const bool inRange = i < a.n;
+  const int ownI = inRange ? a.own[i] : APB_OWN_DUMMY;
+  if (ownI != APB_OWN_DUMMY) {
+    const int M = a.M;
+    const int64_t A = i / M;
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+    const int ti = MIX ? a.type[i] : 0;
+    const double wI = ownI == APB_OWN_OWNED ? 1. : 0.;
+    double fxa = 0., fya = 0., fza = 0.;
+    // (1) inside the cluster: SoAFunctorSingle, skipped for halo clusters (VCLClusterFunctor.h:39-41).
+    //     Both directions are evaluated (f_ji = -f_ij bit for bit), counted once as the reference's newton3 pair.
+    if (!a.clIsHalo[A]) {
+      const int64_t s0 = A * M;
+      for (int k = 0; k < M; ++k) {
+        const int64_t j = s0 + k;
+        if (j == i) continue;
+        const int ownJ = a.own[j];
+        if (ownJ == APB_OWN_DUMMY) continue;
+        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+        const double dr2 = ljDist2(drx, dry, drz);
+        const bool hit = dr2 <= a.p.cutoff2;
+        const bool countThis = STATS && j > i;
+        if (countThis) ++st.dist;
+        if (hit) {
+          double upot6;
+          const double fac = ljEval<MIX>(a.p, dr2, ti, MIX ? a.type[j] : 0, upot6);
+          const double fx = drx * fac, fy = dry * fac, fz = drz * fac;
+          fxa += fx;
+          fya += fy;
+          fza += fz;
+          if (STATS) {
+            st.upot += upot6 * wI;
+            st.vir[0] += drx * fx * wI;
+            st.vir[1] += dry * fy * wI;
+            st.vir[2] += drz * fz * wI;
+            if (countThis) {
+              ++st.kN3;
+              ++st.gN3;
+            }
+          }
+        }
+      }
+    }
+    // (2) listed neighbour clusters: SoAFunctorPair(A, B, newton3)
+    const int e0 = a.nbrStart[A], e1 = a.nbrStart[A + 1];
+    for (int e = e0; e < e1; ++e) {
+      const int64_t s0 = static_cast<int64_t>(a.nbrList[e]) * M;
+      for (int k = 0; k < M; ++k) {
+        const int64_t j = s0 + k;
+        const int ownJ = a.own[j];
+        if (ownJ == APB_OWN_DUMMY) continue;
+        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+        const double dr2 = ljDist2(drx, dry, drz);
+        const bool hit = dr2 <= a.p.cutoff2;
+        if (STATS) ++st.dist;
+        if (hit) {
+          double upot6;
+          const double fac = ljEval<MIX>(a.p, dr2, ti, MIX ? a.type[j] : 0, upot6);
+          const double fx = drx * fac, fy = dry * fac, fz = drz * fac;
+          fxa += fx;
+          fya += fy;
+          fza += fz;
+          if (N3) {
+            atomicAdd(&a.fx[j], -fx);
+            atomicAdd(&a.fy[j], -fy);
+            atomicAdd(&a.fz[j], -fz);
+          }
+          if (STATS) {
+            const double wJ = ownJ == APB_OWN_OWNED ? 1. : 0.;
+            const double w = N3 ? wI + wJ : wI;
+            st.upot += upot6 * w;
+            st.vir[0] += drx * fx * w;
+            st.vir[1] += dry * fy * w;
+            st.vir[2] += drz * fz * w;
+            if (N3) {
+              ++st.kN3;
+              ++st.gN3;
+            } else {
+              ++st.kNoN3;
+              ++st.gNoN3;
+            }
+          }
+        }
+      }
+    }
+    if (N3) {
+      atomicAdd(&a.fx[i], fxa);
+      atomicAdd(&a.fy[i], fya);
+      atomicAdd(&a.fz[i], fza);
+    } else {
+      a.fx[i] += fxa;
+      a.fy[i] += fya;
+      a.fz[i] += fza;
+    }
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------------------------
+int apbPrepareLJParams(apb_handle h, const apb_functor *f, LJParams &p) {
+  if (!(f->cutoff > 0.)) return h->fail(APB_ERR_INVALID_ARGUMENT, "functor cutoff must be > 0");
+  // AutoPas::computeInteractions checks functor cutoff <= container cutoff (AutoPasImpl.h:118-130)
+  if (f->cutoff > h->cfg.cutoff)
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "functor cutoff exceeds the container's interaction cutoff");
+  p.cutoff2 = f->cutoff * f->cutoff;
+  p.eps24 = f->epsilon24;
+  p.sigma2 = f->sigma_squared;
+  p.shift6 = (f->flags & APB_FUNCTOR_APPLY_SHIFT) ? apb_lj_calc_shift6(f->epsilon24, f->sigma_squared, p.cutoff2) : 0.;
+  p.applyShift = (f->flags & APB_FUNCTOR_APPLY_SHIFT) ? 1 : 0;
+  p.T = 0;
+  p.mix = nullptr;
+  if (f->flags & APB_FUNCTOR_USE_MIXING) {
+    if (f->num_types <= 0 || !f->mixing_table)
+      return h->fail(APB_ERR_INVALID_ARGUMENT, "mixing functor needs num_types > 0 and a mixing table");
+    const size_t cnt = static_cast<size_t>(f->num_types) * f->num_types * 3;
+    if (h->mixHostCache.size() != cnt || std::memcmp(h->mixHostCache.data(), f->mixing_table, cnt * 8) != 0) {
+      APB_CHECK(apbEnsure(h, h->mixDev, cnt * 8));
+      APB_CUDA(cudaMemcpyAsync(h->mixDev.p, f->mixing_table, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+      APB_CUDA(cudaStreamSynchronize(h->stream));
+      h->mixHostCache.assign(f->mixing_table, f->mixing_table + cnt);
+    }
+    p.T = f->num_types;
+    p.mix = static_cast<const double *>(h->mixDev.p);
+  }
+  return APB_OK;
+}
+
+int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f, apb_traversal_result *out) {
+  apb_traversal_result host;
+  std::memset(&host, 0, sizeof(host));
+  if (stats && numBlocks > 0) {
+    kReducePartials<<<1, 256, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
+                                              static_cast<apb_traversal_result *>(h->result.p));
+    APB_CUDA(cudaGetLastError());
+    APB_CUDA(cudaMemcpyAsync(&host, h->result.p, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+  }
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (!(f->flags & APB_FUNCTOR_CALC_GLOBALS)) {
+    host.upot_sum = 0.;
+    host.virial_sum[0] = host.virial_sum[1] = host.virial_sum[2] = 0.;
+    host.num_global_calcs_n3 = host.num_global_calcs_no_n3 = 0;
+  }
+  if (!(f->flags & APB_FUNCTOR_COUNT_FLOPS)) {
+    host.num_dist_calls = host.num_kernel_calls_n3 = host.num_kernel_calls_no_n3 = 0;
+    host.num_global_calcs_n3 = host.num_global_calcs_no_n3 = 0;
+  }
+  if (out) *out = host;
+  return APB_OK;
+}
+
+#define LJ_DISPATCH(KERNEL, grid, block, args)                                                     \
+  do {                                                                                             \
+    const int sel = (mix ? 4 : 0) | (stats ? 2 : 0) | (n3 ? 1 : 0);                                \
+    switch (sel) {                                                                                 \
+      case 0: KERNEL<false, false, false><<<grid, block, 0, h->stream>>>(args); break;             \
+      case 1: KERNEL<false, false, true><<<grid, block, 0, h->stream>>>(args); break;              \
+      case 2: KERNEL<false, true, false><<<grid, block, 0, h->stream>>>(args); break;              \
+      case 3: KERNEL<false, true, true><<<grid, block, 0, h->stream>>>(args); break;               \
+      case 4: KERNEL<true, false, false><<<grid, block, 0, h->stream>>>(args); break;              \
+      case 5: KERNEL<true, false, true><<<grid, block, 0, h->stream>>>(args); break;               \
+      case 6: KERNEL<true, true, false><<<grid, block, 0, h->stream>>>(args); break;               \
+      default: KERNEL<true, true, true><<<grid, block, 0, h->stream>>>(args); break;               \
+    }                                                                                              \
+  } while (0)
+
+int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bool mix, bool stats,
+                       apb_traversal_result *out);
+
+int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3, apb_traversal_result *out) {
+  LJParams p;
+  APB_CHECK(apbPrepareLJParams(h, f, p));
+  const bool mix = f->flags & APB_FUNCTOR_USE_MIXING;
+  const bool stats = f->flags & (APB_FUNCTOR_CALC_GLOBALS | APB_FUNCTOR_COUNT_FLOPS);
+  const bool n3 = newton3 != 0;
+  const int64_t n = h->nslots;
+  if (traversal == APB_TRAVERSAL_GPUVCL_PRUNED) return apbComputeLJPruned(h, f, p, mix, stats, out);
+  const int block = 128;
+  const int grid = apbDivUp(n, block);
+  if (n == 0) return apbFinishStats(h, 0, stats, f, out);
+  APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * grid));
+  if (h->cfg.container == APB_CONTAINER_LINKED_CELLS) {
+    LCArgs a;
+    a.g = h->lc;
+    a.n = n;
+    a.x = h->col[APB_COL_X];
+    a.y = h->col[APB_COL_Y];
+    a.z = h->col[APB_COL_Z];
+    a.fx = h->col[APB_COL_FX];
+    a.fy = h->col[APB_COL_FY];
+    a.fz = h->col[APB_COL_FZ];
+    a.type = h->type;
+    a.own = h->own;
+    a.slotCell = static_cast<const int *>(h->slotCell.p);
+    a.cellStart = static_cast<const int *>(h->start.p);
+    a.stencil = static_cast<const int *>(h->stencilDev.p);
+    a.stencilN = h->stencilN;
+    // with FLOP counting requested reproduce the reference's full evaluation set (incl. forces on halo-cell
+    // particles, which are discarded); otherwise skip that wasted work
+    a.processHaloCells = (f->flags & APB_FUNCTOR_COUNT_FLOPS) ? 1 : 0;
+    a.p = p;
+    a.partials = static_cast<LJStats *>(h->partials.p);
+    LJ_DISPATCH(kLJLinkedCells, grid, block, a);
+  } else {
+    VCLArgs a;
+    a.n = n;
+    a.M = h->cfg.cluster_size;
+    a.x = h->col[APB_COL_X];
+    a.y = h->col[APB_COL_Y];
+    a.z = h->col[APB_COL_Z];
+    a.fx = h->col[APB_COL_FX];
+    a.fy = h->col[APB_COL_FY];
+    a.fz = h->col[APB_COL_FZ];
+    a.type = h->type;
+    a.own = h->own;
+    a.clIsHalo = static_cast<const int *>(h->clIsHalo.p);
+    a.nbrStart = static_cast<const int *>(h->nbrStart.p);
+    a.nbrList = static_cast<const int *>(h->nbrList.p);
+    a.p = p;
+    a.partials = static_cast<LJStats *>(h->partials.p);
+    LJ_DISPATCH(kLJClusterPairs, grid, block, a);
+  }
+  APB_CUDA(cudaGetLastError());
+  return apbFinishStats(h, grid, stats, f, out);
+}
+
+int apbCheckTraversal(apb_handle h, int traversal, int newton3);
+
+extern "C" int apb_compute_interactions(apb_handle h, int32_t traversal, const apb_functor *functor, int32_t newton3,
+                                        apb_traversal_result *out) {
+  APB_ENTRY(h);
+  if (!functor) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_compute_interactions: null functor");
+  APB_CHECK(apbCheckTraversal(h, traversal, newton3));
+  if (!h->structureValid)
+    return h->fail(APB_ERR_STATE, "apb_compute_interactions: particles were added / removed since the last "
+                                  "apb_rebuild_neighbor_lists");
+  if (h->cfg.container == APB_CONTAINER_VERLET_CLUSTER_LISTS && h->builtNewton3 != (newton3 ? 1 : 0))
+    return h->fail(APB_ERR_STATE, "apb_compute_interactions: cluster-pair lists were built for the other newton3 mode "
+                                  "(VerletClusterListsRebuilder.h:153-163: list contents depend on newton3)");
+  switch (functor->kind) {
+    case APB_FUNCTOR_LJ:
+      if (h->cfg.particle_kind != APB_PARTICLE_LJ)
+        return h->fail(APB_ERR_NOT_APPLICABLE, "LJFunctor needs MoleculeLJ particles");
+      return apbComputeLJ(h, traversal, functor, newton3, out);
+    default:
+      return h->fail(APB_ERR_NOT_APPLICABLE, "functor kind not implemented on the GPU path");
+  }
+}

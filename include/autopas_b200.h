@@ -1,0 +1,223 @@
+/*
+ * autopas_b200.h — C ABI of the B200-native short-range interaction path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `int` status codes, no exceptions and no torch / CUDA types.
+ * Each entry point names the reference interface it replaces (paths relative to the AutoPas reference tree).
+ * The C++ shim `autopas_b200/shim/GpuContainers.h` implements `autopas::ParticleContainerInterface<P>` and
+ * `autopas::TraversalInterface` on top of these calls; INTEGRATION.md shows the additive edits a maintainer makes.
+ *
+ * Conventions
+ *  - All entry points return APB_OK (0) or a negative error code; `apb_last_error` gives the message.
+ *  - Host buffers passed in are borrowed for the duration of the call only.
+ *  - Compute / rebuild / update entry points are single-caller and BLOCK until the device work has finished, because
+ *    the AutoTuner times them with host timers (src/autopas/LogicHandler.h:1083-1125).
+ *  - "storage order" = the order of particle slots in the device SoA. It changes only in apb_rebuild_neighbor_lists /
+ *    apb_update_container(keep=0) / apb_set_particles, mirroring iterator invalidation in the reference.
+ *  - Ownership encoding is the reference's: dummy 0, owned 1, halo 2 (src/autopas/particles/OwnershipState.h:20-29).
+ */
+#ifndef AUTOPAS_B200_H
+#define AUTOPAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct apb_handle_s *apb_handle;
+
+enum apb_status {
+  APB_OK = 0,
+  APB_ERR_INVALID_ARGUMENT = -1,
+  APB_ERR_CUDA = -2,              /* sticky: the handle is unusable afterwards */
+  APB_ERR_NOT_APPLICABLE = -3,    /* configuration rejected, like TraversalInterface::isApplicableToDomain()==false */
+  APB_ERR_STATE = -4,             /* e.g. compute before rebuild (VerletClusterLists.h:148-170 throws likewise) */
+  APB_ERR_PARTICLE_OUTSIDE = -5,  /* add owned particle outside the box (LogicHandler.h:343-350) */
+  APB_ERR_NCCL = -6,
+  APB_ERR_OUT_OF_MEMORY = -7
+};
+
+/* options/ContainerOption.h:23-69 — new values gpuLinkedCells / gpuVerletClusterLists */
+enum apb_container { APB_CONTAINER_LINKED_CELLS = 0, APB_CONTAINER_VERLET_CLUSTER_LISTS = 1 };
+
+/* options/TraversalOption.h:25-190 — new values with unique prefixes gpulc_ / gpuvcl_
+ * (containers/CompatibleTraversals.h:29-37 filters by name prefix). */
+enum apb_traversal {
+  APB_TRAVERSAL_GPULC_C08 = 0,                /* pair set of lc_c08 (LCC08Traversal.h:73-79) */
+  APB_TRAVERSAL_GPULC_C18 = 1,                /* pair set of lc_c18 (LCC18Traversal.h:115-211); same set as c08 */
+  APB_TRAVERSAL_GPUVCL_CLUSTER_ITERATION = 2, /* VCLClusterIterationTraversal.h:60-66, newton3 off only */
+  APB_TRAVERSAL_GPUVCL_C06 = 3,               /* VCLC06Traversal.h:86-150, newton3 on/off */
+  APB_TRAVERSAL_GPUVCL_C01_BALANCED = 4,      /* VCLC01BalancedTraversal.h:60-90, newton3 off only */
+  APB_TRAVERSAL_GPUVCL_PRUNED = 5             /* B200-native: cluster-pair list refined to per-particle masks at
+                                                 rebuild (rc+skin test), newton3 off only; same forces/globals */
+};
+
+/* Which particle class the container stores (decides the SoA columns). */
+enum apb_particle_kind {
+  APB_PARTICLE_LJ = 0,        /* mdLib::MoleculeLJ (MoleculeLJ.h:39-70) */
+  APB_PARTICLE_MULTISITE = 1, /* mdLib::MultisiteMoleculeLJ (MultisiteMoleculeLJ.h) */
+  APB_PARTICLE_SPH = 2        /* sphLib::SPHParticle (SPHParticle.h:382-425) */
+};
+
+/* double-precision SoA columns addressable through apb_upload_column / apb_download_column */
+enum apb_column {
+  APB_COL_X = 0, APB_COL_Y, APB_COL_Z,
+  APB_COL_VX, APB_COL_VY, APB_COL_VZ,
+  APB_COL_FX, APB_COL_FY, APB_COL_FZ,          /* SPH: acceleration */
+  APB_COL_OLDFX, APB_COL_OLDFY, APB_COL_OLDFZ,
+  /* multisite */
+  APB_COL_Q0, APB_COL_Q1, APB_COL_Q2, APB_COL_Q3,
+  APB_COL_TX, APB_COL_TY, APB_COL_TZ,
+  /* SPH */
+  APB_COL_MASS, APB_COL_SMTH, APB_COL_DENSITY, APB_COL_PRESSURE, APB_COL_SNDSPEED,
+  APB_COL_ENGDOT, APB_COL_VSIGMAX,
+  APB_NUM_COLUMNS
+};
+
+typedef struct {
+  double box_min[3];
+  double box_max[3];
+  double cutoff;
+  double skin;
+  double cell_size_factor; /* LinkedCells only (ContainerSelectorInfo::cellSizeFactor) */
+  int32_t cluster_size;    /* VerletClusterLists only (LogicHandlerInfo.h: verletClusterSize, default 4) */
+  int32_t container;       /* enum apb_container */
+  int32_t particle_kind;   /* enum apb_particle_kind */
+  int32_t device;          /* CUDA device ordinal */
+} apb_config;
+
+enum apb_functor_kind {
+  APB_FUNCTOR_LJ = 0,          /* mdLib::LJFunctor (LJFunctor.h) */
+  APB_FUNCTOR_LJ_MULTISITE = 1,/* mdLib::LJMultisiteFunctor */
+  APB_FUNCTOR_ATM = 2,         /* mdLib::AxilrodTellerMutoFunctor (triwise) */
+  APB_FUNCTOR_SPH_DENSITY = 3, /* sphLib::SPHCalcDensityFunctor */
+  APB_FUNCTOR_SPH_HYDRO = 4    /* sphLib::SPHCalcHydroForceFunctor */
+};
+
+/* LJFunctor template flags (LJFunctor.h:39-41) become run-time bits */
+enum apb_functor_flags {
+  APB_FUNCTOR_APPLY_SHIFT = 1,
+  APB_FUNCTOR_USE_MIXING = 2,
+  APB_FUNCTOR_CALC_GLOBALS = 4,
+  APB_FUNCTOR_COUNT_FLOPS = 8
+};
+
+typedef struct {
+  int32_t kind;  /* enum apb_functor_kind */
+  int32_t flags; /* enum apb_functor_flags */
+  double cutoff; /* Functor::getCutoff() */
+  /* non-mixing parameters: LJFunctor::setParticleProperties(epsilon24, sigmaSquared) (LJFunctor.h:588-596);
+   * shift6 is derived by the library with ParticlePropertiesLibrary::calcShift6 when APPLY_SHIFT is set */
+  double epsilon24;
+  double sigma_squared;
+  /* mixing: num_types and a row-major [i*T+j] table of {epsilon24, sigmaSquared, shift6}
+   * (ParticlePropertiesLibrary.h:324-328, built by apb_make_lj_mixing_table) */
+  int32_t num_types;
+  const double *mixing_table;
+  double nu; /* ATM, non-mixing: AxilrodTellerMutoFunctor::setParticleProperties(nu) */
+} apb_functor;
+
+/* raw accumulators as the reference functor keeps them before endTraversal (LJFunctor.h:1121-1136, 1145-1195) */
+typedef struct {
+  double upot_sum;      /* LJ: sum of 6*Upot*weight ; ATM: sum of 3*Upot ... exactly the functor's _potentialEnergySum input */
+  double virial_sum[3];
+  uint64_t num_dist_calls;
+  uint64_t num_kernel_calls_n3;
+  uint64_t num_kernel_calls_no_n3;
+  uint64_t num_global_calcs_n3;
+  uint64_t num_global_calcs_no_n3;
+} apb_traversal_result;
+
+typedef struct {
+  int64_t cells_per_dim[3];   /* LinkedCells incl. halo (CellBlock3D::getCellsPerDimensionWithHalo) or towers x,y,1 */
+  double cell_length[3];      /* cell length, or tower side length x,y and 0 */
+  double interaction_length;  /* cutoff + skin */
+  int64_t cluster_size;
+  int64_t num_slots;          /* particle slots in storage order, incl. VCL padding dummies */
+  int64_t num_cells;          /* cells or towers */
+  int64_t num_clusters;       /* VCL */
+  int64_t num_cluster_pairs;  /* VCL: entries of the cluster-pair neighbour list */
+  int64_t towers_per_interaction_length; /* VCL */
+} apb_geometry;
+
+/* ---- life cycle ------------------------------------------------------------------------------------------------ */
+/* replaces ContainerSelector::generateContainer (tuning/selectors/ContainerSelector.h:44-108) */
+int apb_create(const apb_config *config, apb_handle *out_handle);
+int apb_destroy(apb_handle h);
+/* message of the last failing call on this handle (h == NULL: last failing apb_create) */
+const char *apb_last_error(apb_handle h);
+
+/* ---- particle storage ------------------------------------------------------------------------------------------ */
+/* bulk form of ParticleContainerInterface::addParticleImpl / addHaloParticleImpl
+ * (containers/ParticleContainerInterface.h:112,144). ids / types may be NULL (0..n-1 / 0). Appended particles are
+ * staged and sorted into the container at the next rebuild, like VerletClusterLists::_particlesToAdd
+ * (VerletClusterLists.h:184-192). check_box != 0: owned particles must lie in the box (half-open), else
+ * APB_ERR_PARTICLE_OUTSIDE. */
+int apb_add_particles(apb_handle h, int64_t n, const double *x, const double *y, const double *z, const int64_t *ids,
+                      const int32_t *types, int32_t ownership, int32_t check_box);
+/* ParticleContainerInterface::deleteAllParticles */
+int apb_delete_all_particles(apb_handle h);
+/* ParticleContainerInterface::deleteHaloParticles (LinkedCells.h:110): halo slots become dummies */
+int apb_delete_halo_particles(apb_handle h);
+/* bulk form of ParticleContainerInterface::updateHaloParticle (:152): positions of existing halo slots are replaced,
+ * matched by id. *out_not_found = number of ids that had no halo slot (the caller then falls back to add). */
+int apb_update_halo_particles(apb_handle h, int64_t n, const int64_t *ids, const double *x, const double *y,
+                              const double *z, int64_t *out_not_found);
+/* ParticleContainerInterface::getNumberOfParticles(behavior) */
+int apb_get_num_particles(apb_handle h, int64_t *out_owned, int64_t *out_halo);
+/* number of particle slots in storage order (incl. dummies); sizes of the column transfers below */
+int apb_get_num_slots(apb_handle h, int64_t *out_slots);
+
+/* Host mirror transfers (what ContainerIterator / getParticle hand out, iterators/ContainerIterator.h:324),
+ * whole columns in storage order. */
+int apb_download_column(apb_handle h, int32_t column, double *dst);
+int apb_upload_column(apb_handle h, int32_t column, const double *src);
+int apb_download_ids(apb_handle h, int64_t *ids, int32_t *types, int32_t *ownership);
+int apb_upload_ownership(apb_handle h, const int32_t *ownership); /* deleteParticle = mark dummy */
+/* fused transfers for the force step through host buffers: 3 columns each, pinned staging inside */
+int apb_upload_positions(apb_handle h, const double *x, const double *y, const double *z);
+int apb_download_forces(apb_handle h, double *fx, double *fy, double *fz);
+/* set force columns to a constant (TimeDiscretization.cpp:16-68 resets f to globalForce) */
+int apb_reset_forces(apb_handle h, double fx, double fy, double fz);
+
+/* ---- container maintenance ------------------------------------------------------------------------------------- */
+/* ParticleContainerInterface::updateContainer(bool keepNeighborListsValid) (:297);
+ * keep != 0: LeavingParticleCollector::collectParticlesAndMarkNonOwnedAsDummy (LeavingParticleCollector.h:85-118);
+ * keep == 0: LinkedCells.h:152-202 / VerletClusterLists.h:362-397. Leavers are kept in a library-owned buffer. */
+int apb_update_container(apb_handle h, int32_t keep_neighbor_lists_valid, int64_t *out_num_leavers);
+int apb_get_leavers(apb_handle h, double *x, double *y, double *z, double *vx, double *vy, double *vz, int64_t *ids,
+                    int32_t *types);
+/* ParticleContainerInterface::rebuildNeighborLists(TraversalInterface*) (:158): LinkedCells re-binning
+ * (counting sort) or VerletClusterLists tower/cluster/pair-list construction (VerletClusterLists.h:779-799). */
+int apb_rebuild_neighbor_lists(apb_handle h, int32_t traversal, int32_t newton3);
+/* ParticleContainerInterface::getTraversalSelectorInfo (:303) and sizes for the debug dumps */
+int apb_get_geometry(apb_handle h, apb_geometry *out);
+
+/* ---- the hot path ---------------------------------------------------------------------------------------------- */
+/* ParticleContainerInterface::computeInteractions(TraversalInterface*) (:252) with the functor's initTraversal
+ * already applied (accumulators start at zero). `out` receives the raw accumulators the shim deposits into the
+ * functor before Functor::endTraversal(newton3). May be NULL. */
+int apb_compute_interactions(apb_handle h, int32_t traversal, const apb_functor *functor, int32_t newton3,
+                             apb_traversal_result *out);
+
+/* host-side helpers restating functor post-processing, so C callers need no C++:
+ * LJFunctor::endTraversal + getPotentialEnergy/getVirial (LJFunctor.h:661-720) */
+void apb_lj_end_traversal(const apb_traversal_result *raw, double *out_upot, double *out_virial);
+/* LJFunctor::getNumFLOPs (LJFunctor.h:758-789) */
+uint64_t apb_lj_num_flops(const apb_traversal_result *raw, int32_t apply_shift);
+/* ParticlePropertiesLibrary::calculateMixingCoefficients (ParticlePropertiesLibrary.h:444-473); out: T*T*3 doubles */
+int apb_make_lj_mixing_table(int32_t num_types, const double *epsilon, const double *sigma, double cutoff,
+                             double *out_table);
+/* ParticlePropertiesLibrary::calcShift6 (:576-582) */
+double apb_lj_calc_shift6(double epsilon24, double sigma_squared, double cutoff_squared);
+
+/* ---- parity artefacts (tests only; not used by the hot path) --------------------------------------------------- */
+/* per slot: 1-D cell index (CellBlock3D::get1DIndexOfPosition) or tower index (ClusterTowerBlock2D) */
+int apb_debug_cell_of_slot(apb_handle h, int64_t *out_cell);
+/* VCL cluster-pair list as pairs of global cluster indices (cluster c covers slots [c*M, (c+1)*M)) */
+int apb_debug_cluster_pairs(apb_handle h, int64_t *out_pairs /* 2*num_cluster_pairs */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOPAS_B200_H */

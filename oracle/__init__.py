@@ -1,0 +1,231 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes access to the CPU oracle.
+
+* ``liboracle.so``            : our plain-C restatement (oracle/autopas_oracle.c, oracle/*.c), built by oracle/Makefile
+* ``_ref/libautopas_ref.so``  : the unmodified AutoPas reference compiled from /root/reference (oracle/ref_driver.cpp);
+                                present only if it was built in the development container (it travels to the GPU box
+                                as a binary; /root/reference itself does not).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+The product package ``autopas_b200`` never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle.so")
+_REF = os.path.join(_HERE, "_ref", "libautopas_ref.so")
+
+F_SHIFT, F_MIXING, F_NEWTON3, F_SOA = 1, 2, 4, 8
+OWN_DUMMY, OWN_OWNED, OWN_HALO = 0, 1, 2
+
+
+class Result(ctypes.Structure):
+    _fields_ = [
+        ("upot_sum", ctypes.c_double),
+        ("virial_sum", ctypes.c_double * 3),
+        ("num_dist_calls", ctypes.c_uint64),
+        ("num_kernel_calls_n3", ctypes.c_uint64),
+        ("num_kernel_calls_no_n3", ctypes.c_uint64),
+        ("num_global_calcs_n3", ctypes.c_uint64),
+        ("num_global_calcs_no_n3", ctypes.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {
+            "upot_sum": self.upot_sum,
+            "virial_sum": tuple(self.virial_sum),
+            "num_dist_calls": self.num_dist_calls,
+            "num_kernel_calls_n3": self.num_kernel_calls_n3,
+            "num_kernel_calls_no_n3": self.num_kernel_calls_no_n3,
+            "num_global_calcs_n3": self.num_global_calcs_n3,
+            "num_global_calcs_no_n3": self.num_global_calcs_no_n3,
+        }
+
+
+def build(with_ref=True):
+    """Compile liboracle.so (and oracle/_ref when the reference tree is present)."""
+    target = "all" if with_ref else os.path.join(_HERE, "liboracle.so")
+    subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build(with_ref=False)
+        _lib = ctypes.CDLL(_LIB)
+        _lib.orc_calc_shift6.restype = ctypes.c_double
+        _lib.orc_calc_shift6.argtypes = [ctypes.c_double] * 3
+        _lib.orc_lj_num_flops.restype = ctypes.c_uint64
+    return _lib
+
+
+def have_ref():
+    return os.path.exists(_REF)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = ctypes.CDLL(_REF)
+    return _ref
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _flags(shift, mixing, newton3, soa=False):
+    return (F_SHIFT if shift else 0) | (F_MIXING if mixing else 0) | (F_NEWTON3 if newton3 else 0) | (F_SOA if soa else 0)
+
+
+def lj_end_traversal(res):
+    """LJFunctor::endTraversal normalisation -> (upot, virial)."""
+    u, v = ctypes.c_double(), ctypes.c_double()
+    lib().orc_lj_end_traversal(ctypes.byref(res), ctypes.byref(u), ctypes.byref(v))
+    return u.value, v.value
+
+
+def lj_num_flops(res, shift):
+    return lib().orc_lj_num_flops(ctypes.byref(res), ctypes.c_int(1 if shift else 0))
+
+
+def mixing_table(eps, sigma, cutoff):
+    eps, sigma = _f64(eps), _f64(sigma)
+    T = len(eps)
+    out = np.zeros(T * T * 3)
+    lib().orc_mixing_table(ctypes.c_int(T), _p(eps), _p(sigma), ctypes.c_double(cutoff), _p(out))
+    return out
+
+
+def lc_cell_indices(box_min, box_max, il, csf, x, y, z):
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    n = len(x)
+    cell = np.zeros(n, dtype=np.int64)
+    cpd = np.zeros(3, dtype=np.int64)
+    lib().orc_lc_cell_indices(_p(_f64(box_min)), _p(_f64(box_max)), ctypes.c_double(il), ctypes.c_double(csf),
+                              ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cell), _p(cpd))
+    return cell, cpd
+
+
+def _common(x, y, z, types, own, eps, sigma):
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    n = len(x)
+    own = _i64(own if own is not None else np.ones(n))
+    types = _i64(types if types is not None else np.zeros(n))
+    eps, sigma = _f64(np.atleast_1d(eps)), _f64(np.atleast_1d(sigma))
+    return x, y, z, types, own, eps, sigma, n
+
+
+def lj_linkedcells(x, y, z, types, own, box_min, box_max, cutoff, skin, csf=1.0, shift=False, mixing=False,
+                   newton3=True, eps=1.0, sigma=1.0):
+    x, y, z, types, own, eps, sigma, n = _common(x, y, z, types, own, eps, sigma)
+    f = np.zeros((n, 3))
+    fscale = np.zeros(n)
+    res = Result()
+    cell = np.full(n, -1, dtype=np.int64)
+    lib().orc_lj_linkedcells(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(types), _p(own), _p(_f64(box_min)),
+                             _p(_f64(box_max)), ctypes.c_double(cutoff), ctypes.c_double(skin), ctypes.c_double(csf),
+                             ctypes.c_int(_flags(shift, mixing, newton3)), ctypes.c_int(len(eps)), _p(eps), _p(sigma),
+                             _p(f), _p(fscale), ctypes.byref(res), _p(cell))
+    return {"f": f, "fscale": fscale, "res": res, "cell": cell}
+
+
+def lj_bruteforce(x, y, z, types, own, cutoff, shift=False, mixing=False, eps=1.0, sigma=1.0):
+    x, y, z, types, own, eps, sigma, n = _common(x, y, z, types, own, eps, sigma)
+    f = np.zeros((n, 3))
+    fscale = np.zeros(n)
+    res = Result()
+    lib().orc_lj_bruteforce(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(types), _p(own), ctypes.c_double(cutoff),
+                            ctypes.c_int(_flags(shift, mixing, True)), ctypes.c_int(len(eps)), _p(eps), _p(sigma),
+                            _p(f), _p(fscale), ctypes.byref(res))
+    return {"f": f, "fscale": fscale, "res": res}
+
+
+def lj_vcl(x, y, z, types, own, box_min, box_max, cutoff, skin, cluster_size, shift=False, mixing=False,
+           newton3=False, eps=1.0, sigma=1.0):
+    x, y, z, types, own, eps, sigma, n = _common(x, y, z, types, own, eps, sigma)
+    f = np.zeros((n, 3))
+    fscale = np.zeros(n)
+    res = Result()
+    lib().orc_lj_vcl(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(types), _p(own), _p(_f64(box_min)), _p(_f64(box_max)),
+                     ctypes.c_double(cutoff), ctypes.c_double(skin), ctypes.c_int64(cluster_size),
+                     ctypes.c_int(_flags(shift, mixing, newton3)), ctypes.c_int(len(eps)), _p(eps), _p(sigma), _p(f),
+                     _p(fscale), ctypes.byref(res))
+    sizes = np.zeros(5, dtype=np.int64)
+    side = np.zeros(2)
+    lib().orc_vcl_dump_sizes(_p(sizes), _p(side))
+    nslots = int(sizes[0] * sizes[4])
+    slot_particle = np.zeros(max(nslots, 1), dtype=np.int64)
+    slot_tower = np.zeros(max(nslots, 1), dtype=np.int64)
+    pairs = np.zeros((max(int(sizes[1]), 1), 2), dtype=np.int64)
+    lib().orc_vcl_dump_copy(_p(slot_particle), _p(slot_tower), _p(pairs))
+    return {"f": f, "fscale": fscale, "res": res, "num_clusters": int(sizes[0]), "num_pairs": int(sizes[1]),
+            "towers_per_dim": (int(sizes[2]), int(sizes[3])), "tower_side": tuple(side),
+            "slot_particle": slot_particle[:nslots], "slot_tower": slot_tower[:nslots], "pairs": pairs[:int(sizes[1])]}
+
+
+# ---- the unmodified reference (oracle/_ref) --------------------------------------------------------------------
+def ref_lj_linkedcells(x, y, z, types, own, box_min, box_max, cutoff, skin, csf=1.0, shift=False, mixing=False,
+                       newton3=True, soa=False, traversal="lc_c08", eps=1.0, sigma=1.0):
+    x, y, z, types, own, eps, sigma, n = _common(x, y, z, types, own, eps, sigma)
+    f = np.zeros((n, 3))
+    glob = np.zeros(2)
+    flops = ctypes.c_uint64()
+    hit = ctypes.c_double()
+    cell = np.zeros(n, dtype=np.int64)
+    cpd = np.zeros(3, dtype=np.int64)
+    rc = ref().ref_lj_linkedcells(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(types), _p(own), _p(_f64(box_min)),
+                                  _p(_f64(box_max)), ctypes.c_double(cutoff), ctypes.c_double(skin),
+                                  ctypes.c_double(csf), ctypes.c_int(_flags(shift, mixing, newton3, soa)),
+                                  ctypes.c_int({"lc_c08": 0, "lc_c18": 1}[traversal]), ctypes.c_int(len(eps)), _p(eps),
+                                  _p(sigma), _p(f), _p(glob), ctypes.byref(flops), ctypes.byref(hit), _p(cell), _p(cpd))
+    if rc != 0:
+        raise RuntimeError("reference LinkedCells run failed")
+    return {"f": f, "upot": glob[0], "virial": glob[1], "flops": flops.value, "hit_rate": hit.value, "cell": cell,
+            "cells_per_dim": cpd}
+
+
+def ref_lj_vcl(x, y, z, types, own, box_min, box_max, cutoff, skin, cluster_size, shift=False, mixing=False,
+               newton3=False, soa=True, traversal="vcl_cluster_iteration", eps=1.0, sigma=1.0):
+    x, y, z, types, own, eps, sigma, n = _common(x, y, z, types, own, eps, sigma)
+    f = np.zeros((n, 3))
+    glob = np.zeros(2)
+    flops = ctypes.c_uint64()
+    hit = ctypes.c_double()
+    trav = {"vcl_cluster_iteration": 0, "vcl_c06": 1, "vcl_c01_balanced": 2}[traversal]
+    rc = ref().ref_lj_vcl(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(types), _p(own), _p(_f64(box_min)),
+                          _p(_f64(box_max)), ctypes.c_double(cutoff), ctypes.c_double(skin), ctypes.c_int64(cluster_size),
+                          ctypes.c_int(_flags(shift, mixing, newton3, soa)), ctypes.c_int(trav), ctypes.c_int(len(eps)),
+                          _p(eps), _p(sigma), _p(f), _p(glob), ctypes.byref(flops), ctypes.byref(hit))
+    if rc != 0:
+        raise RuntimeError("reference VerletClusterLists run failed")
+    sizes = np.zeros(5, dtype=np.int64)
+    side = np.zeros(2)
+    ref().ref_vcl_dump_sizes(_p(sizes), _p(side))
+    ncl, npairs, M = int(sizes[0]), int(sizes[1]), int(sizes[4])
+    tower_of_particle = np.zeros(max(n, 1), dtype=np.int64)
+    cluster_particles = np.zeros(max(ncl * M, 1), dtype=np.int64)
+    cluster_tower = np.zeros(max(ncl, 1), dtype=np.int64)
+    pairs = np.zeros((max(npairs, 1), 2), dtype=np.int64)
+    ref().ref_vcl_dump_copy(_p(tower_of_particle), _p(cluster_particles), _p(cluster_tower), _p(pairs))
+    return {"f": f, "upot": glob[0], "virial": glob[1], "flops": flops.value, "hit_rate": hit.value,
+            "num_clusters": ncl, "num_pairs": npairs, "towers_per_dim": (int(sizes[2]), int(sizes[3])),
+            "tower_side": tuple(side), "tower_of_particle": tower_of_particle[:n],
+            "cluster_particles": cluster_particles[:ncl * M].reshape(ncl, M) if ncl else np.zeros((0, M), np.int64),
+            "cluster_tower": cluster_tower[:ncl], "pairs": pairs[:npairs]}

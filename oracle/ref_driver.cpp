@@ -66,6 +66,7 @@ void fill(Container &container, int64_t n, const double *x, const double *y, con
     if (own[i] == 1) {
       container.addParticle(m);
     } else if (own[i] == 2) {
+      m.setOwnershipState(autopas::OwnershipState::halo);  // LogicHandler::addHaloParticle does this (LogicHandler.h:379-389)
       container.addHaloParticle(m);
     }
   }

@@ -1,0 +1,75 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/autopas_b200.h
+declares, and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from autopas_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "autopas_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(apb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(declared) == set(capi.SIGNATURES), "ctypes binding and header disagree"
+
+
+def test_struct_layouts_match_header():
+    # field order / count follow the header; sizes are what a C compiler gives on x86-64
+    assert ctypes.sizeof(capi.Config) == 6 * 8 + 3 * 8 + 4 * 4
+    assert ctypes.sizeof(capi.TraversalResult) == 4 * 8 + 5 * 8
+    assert ctypes.sizeof(capi.Geometry) == 3 * 8 + 3 * 8 + 8 + 6 * 8
+    assert ctypes.sizeof(capi.Functor) == 8 + 3 * 8 + 8 + 8 + 8
+
+
+def test_host_helpers_match_reference_formulas():
+    lib = capi.load()
+    # ParticlePropertiesLibrary::calcShift6 (ParticlePropertiesLibrary.h:576-582)
+    s2 = 1.0 / 6.25
+    s6 = s2 * s2 * s2
+    assert lib.apb_lj_calc_shift6(24.0, 1.0, 6.25) == 24.0 * (s6 - s6 * s6)
+    raw = capi.TraversalResult()
+    raw.upot_sum = 12.0
+    raw.virial_sum[0], raw.virial_sum[1], raw.virial_sum[2] = 2.0, 4.0, 6.0
+    raw.num_dist_calls, raw.num_kernel_calls_n3, raw.num_kernel_calls_no_n3 = 10, 3, 4
+    raw.num_global_calcs_n3, raw.num_global_calcs_no_n3 = 3, 4
+    u, v = ctypes.c_double(), ctypes.c_double()
+    lib.apb_lj_end_traversal(ctypes.byref(raw), ctypes.byref(u), ctypes.byref(v))
+    assert u.value == 12.0 * 0.5 / 6.0 and v.value == 6.0  # LJFunctor.h:661-685, :719
+    assert lib.apb_lj_num_flops(ctypes.byref(raw), 1) == 10 * 8 + 3 * 18 + 4 * 15 + 3 * 13 + 4 * 9  # :776-789
+    assert lib.apb_lj_num_flops(ctypes.byref(raw), 0) == 10 * 8 + 3 * 18 + 4 * 15 + 3 * 12 + 4 * 8
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from autopas_b200 import ApbError, GpuParticleContainer
+    with pytest.raises(ApbError) as e:
+        GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [10, 10, 10], 1.0, 0.2)
+    assert e.value.code == capi.ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_invalid_configs_are_rejected_before_touching_the_device():
+    from autopas_b200 import ApbError, GpuParticleContainer
+    with pytest.raises(ApbError) as e:
+        GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [1, 1, 1], 1.0, 0.2)  # box < cutoff + skin
+    assert e.value.code == capi.ERR_INVALID_ARGUMENT
+    with pytest.raises(ApbError) as e:
+        GpuParticleContainer("gpuVerletClusterLists", [0, 0, 0], [10, 10, 10], 1.0, 0.2, clusterSize=5)
+    assert e.value.code == capi.ERR_NOT_APPLICABLE
+    with pytest.raises(ApbError):
+        GpuParticleContainer("linkedCells", [0, 0, 0], [10, 10, 10], 1.0, 0.2)
