@@ -83,6 +83,18 @@ class TraversalResult(ctypes.Structure):
     ]
 
 
+class LoopParams(ctypes.Structure):
+    _fields_ = [
+        ("dt", ctypes.c_double),
+        ("mass_of_type", ctypes.c_void_p),
+        ("num_types", ctypes.c_int32),
+        ("global_force", ctypes.c_void_p),
+        ("rebuild_frequency", ctypes.c_int32),
+        ("traversal", ctypes.c_int32),
+        ("newton3", ctypes.c_int32),
+    ]
+
+
 class Geometry(ctypes.Structure):
     _fields_ = [
         ("cells_per_dim", ctypes.c_int64 * 3),
@@ -128,6 +140,20 @@ SIGNATURES = {
     "apb_lj_num_flops": (ctypes.c_uint64, [ctypes.POINTER(TraversalResult), _i32]),
     "apb_make_lj_mixing_table": (_i32, [_i32, _vp, _vp, _f64, _vp]),
     "apb_lj_calc_shift6": (_f64, [_f64, _f64, _f64]),
+    "apb_integrate_positions": (_i32, [_H, _f64, _vp, _i32, _vp]),
+    "apb_integrate_velocities": (_i32, [_H, _f64, _vp, _i32]),
+    "apb_comm_get_unique_id": (_i32, [_vp]),
+    "apb_comm_init": (_i32, [_H, _i32, _i32, _vp]),
+    "apb_set_decomposition": (_i32, [_H, _vp, _vp, _vp, _vp]),
+    "apb_migrate": (_i32, [_H, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "apb_exchange_halos": (_i32, [_H]),
+    "apb_allreduce_globals": (_i32, [_H, ctypes.POINTER(TraversalResult)]),
+    "apb_run_steps": (_i32, [_H, ctypes.POINTER(Functor), _vp, _i32, _i64, _vp]),
+    "apb_get_stream": (_i32, [_H, ctypes.POINTER(_vp)]),
+    "apb_get_launch_count": (_i32, [_H, ctypes.POINTER(_i64)]),
+    "apb_enable_loop_timing": (_i32, [_H, _i32]),
+    "apb_get_loop_timing": (_i32, [_H, _vp, _vp]),
+    "apb_measure_fp64_peak": (_i32, [_i32, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f64)]),
     "apb_debug_cell_of_slot": (_i32, [_H, _vp]),
     "apb_debug_cluster_pairs": (_i32, [_H, _vp]),
 }

@@ -376,6 +376,77 @@ class GpuParticleContainer:
         functor._deposit(raw)
         return raw
 
+    # --- device-resident simulation loop
+    def integratePositions(self, dt, massOfType, globalForce=None):
+        m = _f64(np.atleast_1d(massOfType))
+        g = None if globalForce is None else _f64(globalForce)
+        self._check(self._lib.apb_integrate_positions(self._h, float(dt), _ptr(m), len(m), _ptr(g)))
+
+    def integrateVelocities(self, dt, massOfType):
+        m = _f64(np.atleast_1d(massOfType))
+        self._check(self._lib.apb_integrate_velocities(self._h, float(dt), _ptr(m), len(m)))
+
+    def commInit(self, nranks, rank, uniqueId=None):
+        buf = None if uniqueId is None else np.frombuffer(bytes(uniqueId), dtype=np.uint8).copy()
+        self._check(self._lib.apb_comm_init(self._h, int(nranks), int(rank), _ptr(buf)))
+
+    def setDecomposition(self, globalBoxMin, globalBoxMax, neighbours6, periodic3=(1, 1, 1)):
+        gmin, gmax = _f64(globalBoxMin), _f64(globalBoxMax)
+        nb = np.ascontiguousarray(neighbours6, dtype=np.int32)
+        per = np.ascontiguousarray(periodic3, dtype=np.int32)
+        self._check(self._lib.apb_set_decomposition(self._h, _ptr(gmin), _ptr(gmax), _ptr(nb), _ptr(per)))
+
+    def migrate(self):
+        s, r = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.apb_migrate(self._h, ctypes.byref(s), ctypes.byref(r)))
+        return r.value
+
+    def exchangeHalos(self):
+        self._check(self._lib.apb_exchange_halos(self._h))
+
+    def allreduceGlobals(self, raw):
+        self._check(self._lib.apb_allreduce_globals(self._h, ctypes.byref(raw)))
+        return raw
+
+    def runSteps(self, traversal, numSteps, firstIteration, dt, massOfType, rebuildFrequency, globalForce=None,
+                 wantResults=True):
+        """Simulation::simulate for `numSteps` iterations on the device; returns the per-step raw accumulators."""
+        m = _f64(np.atleast_1d(massOfType))
+        g = None if globalForce is None else _f64(globalForce)
+        p = capi.LoopParams()
+        p.dt = float(dt)
+        p.mass_of_type = m.ctypes.data
+        p.num_types = len(m)
+        p.global_force = None if g is None else g.ctypes.data
+        p.rebuild_frequency = int(rebuildFrequency)
+        p.traversal = capi.TRAVERSAL_NAMES[traversal.option]
+        p.newton3 = 1 if traversal.useNewton3 else 0
+        cf = traversal.functor._c_functor()
+        res = (capi.TraversalResult * max(numSteps, 1))() if wantResults else None
+        self._check(self._lib.apb_run_steps(self._h, ctypes.byref(cf), ctypes.byref(p), int(numSteps),
+                                            int(firstIteration), res))
+        return res
+
+    def getLaunchCount(self):
+        n = ctypes.c_int64()
+        self._check(self._lib.apb_get_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def enableLoopTiming(self, enable=True):
+        self._check(self._lib.apb_enable_loop_timing(self._h, 1 if enable else 0))
+
+    def getLoopTiming(self):
+        ms = np.zeros(4)
+        cnt = np.zeros(4, dtype=np.int64)
+        self._check(self._lib.apb_get_loop_timing(self._h, _ptr(ms), _ptr(cnt)))
+        names = ("force", "rebuild", "halo_refresh", "integrate")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(names)}
+
+    def getStream(self):
+        s = ctypes.c_void_p()
+        self._check(self._lib.apb_get_stream(self._h, ctypes.byref(s)))
+        return s.value
+
     # --- parity artefacts
     def debugCellOfSlot(self):
         out = np.zeros(self.numSlots(), dtype=np.int64)

@@ -280,11 +280,11 @@ static int segSort(apb_handle h, int mode, int64_t numSeg, int maxCount, const i
   const size_t dyn = useGlobal ? 0 : smem;
   if (mode == 1) {
     if (dyn > 48 * 1024) APB_CUDA(cudaFuncSetAttribute(kSegSort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
-    kSegSort<1><<<static_cast<unsigned>(numSeg), threads, dyn, h->stream>>>(start, count, perm, h->col[APB_COL_Z], h->id,
+    ++h->launchCount, kSegSort<1><<<static_cast<unsigned>(numSeg), threads, dyn, h->stream>>>(start, count, perm, h->col[APB_COL_Z], h->id,
                                                                            useGlobal, gK1, gK2, gV);
   } else {
     if (dyn > 48 * 1024) APB_CUDA(cudaFuncSetAttribute(kSegSort<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
-    kSegSort<0><<<static_cast<unsigned>(numSeg), threads, dyn, h->stream>>>(start, count, perm, nullptr, nullptr,
+    ++h->launchCount, kSegSort<0><<<static_cast<unsigned>(numSeg), threads, dyn, h->stream>>>(start, count, perm, nullptr, nullptr,
                                                                            useGlobal, gK1, gK2, gV);
   }
   APB_CUDA(cudaGetLastError());
@@ -316,13 +316,13 @@ int apbRebuildLinkedCells(apb_handle h) {
   APB_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (nc + 1), h->stream));
   APB_CUDA(cudaMemsetAsync(scratchMax(h), 0, sizeof(int), h->stream));
   if (n > 0) {
-    kKeysLC<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own,
+    ++h->launchCount, kKeysLC<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own,
                                                      h->lc, key, rank, count);
     APB_CUDA(cudaGetLastError());
   }
   // reuse kPadCounts with M = 1 only for the max
   APB_CHECK(apbEnsure(h, h->nbrCount, sizeof(int) * (nc + 1)));
-  kPadCounts<<<apbDivUp(nc + 1, 256), 256, 0, h->stream>>>(nc + 1, count, static_cast<int *>(h->nbrCount.p), 1, scratchMax(h));
+  ++h->launchCount, kPadCounts<<<apbDivUp(nc + 1, 256), 256, 0, h->stream>>>(nc + 1, count, static_cast<int *>(h->nbrCount.p), 1, scratchMax(h));
   APB_CHECK(apbExclusiveScan(h, count, start, nc + 1, scratchTotals(h)));
   long long total = 0;
   int maxCount = 0;
@@ -330,14 +330,15 @@ int apbRebuildLinkedCells(apb_handle h) {
   APB_CUDA(cudaMemcpyAsync(&maxCount, scratchMax(h), 4, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
   if (n > 0) {
-    kScatterPerm<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, key, rank, start, perm);
+    ++h->launchCount, kScatterPerm<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, key, rank, start, perm);
     APB_CUDA(cudaGetLastError());
     APB_CHECK(segSort(h, 0, nc, maxCount, start, count, perm));
     if (total > 0) {
-      kSlotCell<<<apbDivUp(total, 256), 256, 0, h->stream>>>(total, perm, key, static_cast<int *>(h->slotCell.p));
+      ++h->launchCount, kSlotCell<<<apbDivUp(total, 256), 256, 0, h->stream>>>(total, perm, key, static_cast<int *>(h->slotCell.p));
       APB_CUDA(cudaGetLastError());
     }
   }
+  APB_CHECK(apbRemapHaloLinks(h, perm, n, total));
   APB_CHECK(apbPermuteStorage(h, perm, total));
   APB_CUDA(cudaStreamSynchronize(h->stream));
   h->numCells = nc;
@@ -562,11 +563,11 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   APB_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (nt + 1), h->stream));
   APB_CUDA(cudaMemsetAsync(scratchMax(h), 0, sizeof(int), h->stream));
   if (n > 0) {
-    kKeysVCL<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own,
+    ++h->launchCount, kKeysVCL<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own,
                                                       g, key, rank, count);
     APB_CUDA(cudaGetLastError());
   }
-  kPadCounts<<<apbDivUp(nt + 1, 256), 256, 0, h->stream>>>(nt + 1, count, padded, M, scratchMax(h));
+  ++h->launchCount, kPadCounts<<<apbDivUp(nt + 1, 256), 256, 0, h->stream>>>(nt + 1, count, padded, M, scratchMax(h));
   APB_CHECK(apbExclusiveScan(h, padded, start, nt + 1, scratchTotals(h)));
   long long total = 0;
   int maxCount = 0;
@@ -579,10 +580,11 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   int *slotTower = static_cast<int *>(h->slotCell.p);
   if (total > 0) APB_CUDA(cudaMemsetAsync(perm, 0xFF, sizeof(int) * total, h->stream));
   if (n > 0) {
-    kScatterPerm<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, key, rank, start, perm);
+    ++h->launchCount, kScatterPerm<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, key, rank, start, perm);
     APB_CUDA(cudaGetLastError());
     APB_CHECK(segSort(h, 1, nt, maxCount, start, count, perm));
   }
+  APB_CHECK(apbRemapHaloLinks(h, perm, n, total));
   APB_CHECK(apbPermuteStorage(h, perm, total));
   const int64_t numClusters = total / M;
   h->numClusters = numClusters;
@@ -596,10 +598,10 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   int *paddedKeep = static_cast<int *>(h->rank.p);
   APB_CUDA(cudaMemcpyAsync(paddedKeep, padded, sizeof(int) * (nt + 1), cudaMemcpyDeviceToDevice, h->stream));
   if (total > 0) {
-    kSlotTower<<<static_cast<unsigned>(nt), 128, 0, h->stream>>>(static_cast<int>(nt), start, paddedKeep, slotTower);
+    ++h->launchCount, kSlotTower<<<static_cast<unsigned>(nt), 128, 0, h->stream>>>(static_cast<int>(nt), start, paddedKeep, slotTower);
     const double dist = g.interactionLength * 2;
     const double startX = 1000 * g.haloBoxMax[0];
-    kParkDummies<<<apbDivUp(total, 256), 256, 0, h->stream>>>(total, h->own, slotTower, start, paddedKeep,
+    ++h->launchCount, kParkDummies<<<apbDivUp(total, 256), 256, 0, h->stream>>>(total, h->own, slotTower, start, paddedKeep,
                                                               h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z],
                                                               startX, dist);
     APB_CUDA(cudaGetLastError());
@@ -613,13 +615,13 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   APB_CHECK(apbEnsure(h, h->nbrCount, sizeof(int) * (ncAlloc + 1)));
   APB_CHECK(apbEnsure(h, h->nbrStart, sizeof(int) * (ncAlloc + 1)));
   if (numClusters > 0) {
-    kClusterBoxes<<<apbDivUp(numClusters, 128), 128, 0, h->stream>>>(
+    ++h->launchCount, kClusterBoxes<<<apbDivUp(numClusters, 128), 128, 0, h->stream>>>(
         numClusters, M, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own, slotTower,
         static_cast<double *>(h->clBoxMin.p), static_cast<double *>(h->clBoxMax.p), static_cast<int *>(h->clHasOwned.p),
         static_cast<int *>(h->clTower.p));
     APB_CUDA(cudaGetLastError());
   }
-  kTowerRanges<<<apbDivUp(nt, 128), 128, 0, h->stream>>>(
+  ++h->launchCount, kTowerRanges<<<apbDivUp(nt, 128), 128, 0, h->stream>>>(
       static_cast<int>(nt), M, start, paddedKeep, static_cast<int *>(h->clHasOwned.p),
       static_cast<int *>(h->twFirstCluster.p), static_cast<int *>(h->twNumClusters.p),
       static_cast<int *>(h->twFirstOwned.p), static_cast<int *>(h->twFirstTailHalo.p), static_cast<int *>(h->clIsHalo.p));
@@ -639,7 +641,7 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   long long numPairs = 0;
   APB_CUDA(cudaMemsetAsync(nbrCount, 0, sizeof(int) * (numClusters + 1), h->stream));
   if (numClusters > 0) {
-    kNeighborLists<false><<<apbDivUp(numClusters, 64), 64, 0, h->stream>>>(a, nbrCount, nullptr, nullptr);
+    ++h->launchCount, kNeighborLists<false><<<apbDivUp(numClusters, 64), 64, 0, h->stream>>>(a, nbrCount, nullptr, nullptr);
     APB_CUDA(cudaGetLastError());
   }
   APB_CHECK(apbExclusiveScan(h, nbrCount, nbrStart, numClusters + 1, scratchTotals(h)));
@@ -648,7 +650,7 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   if (numPairs > 0x7fffffffLL) return h->fail(APB_ERR_NOT_APPLICABLE, "cluster-pair list exceeds 2^31 entries");
   APB_CHECK(apbEnsure(h, h->nbrList, sizeof(int) * std::max<long long>(numPairs, 1)));
   if (numPairs > 0) {
-    kNeighborLists<true><<<apbDivUp(numClusters, 64), 64, 0, h->stream>>>(a, nbrCount, nbrStart,
+    ++h->launchCount, kNeighborLists<true><<<apbDivUp(numClusters, 64), 64, 0, h->stream>>>(a, nbrCount, nbrStart,
                                                                           static_cast<int *>(h->nbrList.p));
     APB_CUDA(cudaGetLastError());
   }

@@ -1,0 +1,743 @@
+// Device-resident simulation-loop pieces around the force step, so that a time step never round-trips through the host
+// mirror: Störmer-Verlet integration (examples/md-flexible/src/TimeDiscretization.cpp:16-68, 152-165), particle
+// migration and halo exchange with md-flexible's regular-grid protocol
+// (examples/md-flexible/src/domainDecomposition/RegularGridDecomposition.cpp:159-301): per dimension x, y, z in
+// sequence, left + right neighbour, already received halos are forwarded so that edges and corners propagate with only
+// six peers. Between ranks the packed buffers travel with NCCL send/recv (NVLink); a rank that is its own neighbour
+// (single GPU, periodic box) short-circuits to a device-local copy. All kernels are HBM-bound select / pack / scatter.
+#include <dlfcn.h>
+
+#include <algorithm>
+
+#include "internal.cuh"
+
+// ---- NCCL, loaded lazily (torch has usually loaded libnccl.so.2 already; the library must also load without it) ----
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+enum { ncclInt8 = 0, ncclInt32 = 2, ncclInt64 = 4, ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclMax = 2 };
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+} g_nccl;
+
+bool loadNccl() {
+  if (g_nccl.lib) return true;
+  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return false;
+#define LOADSYM(field, name)                                          \
+  *reinterpret_cast<void **>(&g_nccl.field) = dlsym(lib, name);       \
+  if (!g_nccl.field) return false;
+  LOADSYM(GetUniqueId, "ncclGetUniqueId")
+  LOADSYM(CommInitRank, "ncclCommInitRank")
+  LOADSYM(CommDestroy, "ncclCommDestroy")
+  LOADSYM(Send, "ncclSend")
+  LOADSYM(Recv, "ncclRecv")
+  LOADSYM(GroupStart, "ncclGroupStart")
+  LOADSYM(GroupEnd, "ncclGroupEnd")
+  LOADSYM(AllReduce, "ncclAllReduce")
+  LOADSYM(GetErrorString, "ncclGetErrorString")
+#undef LOADSYM
+  g_nccl.lib = lib;
+  return true;
+}
+}  // namespace
+
+#define APB_NCCL(call)                                                                                        \
+  do {                                                                                                        \
+    int r_ = (call);                                                                                          \
+    if (r_ != 0) {                                                                                            \
+      h->poisoned = true;                                                                                     \
+      return h->fail(APB_ERR_NCCL, std::string("NCCL error: ") + g_nccl.GetErrorString(r_) + " in " #call);   \
+    }                                                                                                         \
+  } while (0)
+
+extern "C" int apb_comm_get_unique_id(void *out128) {
+  if (!out128) return APB_ERR_INVALID_ARGUMENT;
+  if (!loadNccl()) return APB_ERR_NCCL;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return APB_ERR_NCCL;
+  std::memcpy(out128, &id, 128);
+  return APB_OK;
+}
+
+extern "C" int apb_comm_init(apb_handle h, int32_t nranks, int32_t rank, const void *uniqueId128) {
+  APB_ENTRY(h);
+  if (nranks < 1 || rank < 0 || rank >= nranks) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_comm_init: bad rank");
+  h->nranks = nranks;
+  h->myRank = rank;
+  if (nranks == 1) return APB_OK;
+  if (!uniqueId128) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_comm_init: null unique id");
+  if (!loadNccl()) return h->fail(APB_ERR_NCCL, "apb_comm_init: libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  std::memcpy(&id, uniqueId128, 128);
+  ncclComm_t comm = nullptr;
+  APB_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  h->comm = comm;
+  return APB_OK;
+}
+
+void apbCommDestroy(apb_handle h) {
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(h->comm));
+  h->comm = nullptr;
+}
+
+extern "C" int apb_set_decomposition(apb_handle h, const double *globalMin, const double *globalMax,
+                                     const int32_t *neighbors6, const int32_t *periodic3) {
+  APB_ENTRY(h);
+  if (!globalMin || !globalMax || !neighbors6 || !periodic3)
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_set_decomposition: null argument");
+  for (int d = 0; d < 3; ++d) {
+    h->globalMin[d] = globalMin[d];
+    h->globalMax[d] = globalMax[d];
+    h->periodic[d] = periodic3[d] != 0;
+    for (int s = 0; s < 2; ++s) {
+      const int nb = neighbors6[2 * d + s];
+      if (nb < 0 || nb >= h->nranks) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_set_decomposition: neighbour rank out of range");
+      h->neighbor[d][s] = nb;
+    }
+  }
+  h->decompositionSet = true;
+  return APB_OK;
+}
+
+extern "C" int apb_allreduce_globals(apb_handle h, apb_traversal_result *inout) {
+  APB_ENTRY(h);
+  if (!inout) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_allreduce_globals: null argument");
+  if (h->nranks == 1) return APB_OK;
+  // Simulation.cpp:319-322 reduces potential energy and virial with MPI_Reduce(SUM); counters are summed likewise
+  double *d = reinterpret_cast<double *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 128);
+  double host[9] = {inout->upot_sum, inout->virial_sum[0], inout->virial_sum[1], inout->virial_sum[2],
+                    static_cast<double>(inout->num_dist_calls), static_cast<double>(inout->num_kernel_calls_n3),
+                    static_cast<double>(inout->num_kernel_calls_no_n3), static_cast<double>(inout->num_global_calcs_n3),
+                    static_cast<double>(inout->num_global_calcs_no_n3)};
+  APB_CUDA(cudaMemcpyAsync(d, host, sizeof(host), cudaMemcpyHostToDevice, h->stream));
+  APB_NCCL(g_nccl.AllReduce(d, d, 9, ncclFloat64, ncclSum, static_cast<ncclComm_t>(h->comm), h->stream));
+  APB_CUDA(cudaMemcpyAsync(host, d, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  inout->upot_sum = host[0];
+  for (int k = 0; k < 3; ++k) inout->virial_sum[k] = host[1 + k];
+  inout->num_dist_calls = static_cast<uint64_t>(host[4]);
+  inout->num_kernel_calls_n3 = static_cast<uint64_t>(host[5]);
+  inout->num_kernel_calls_no_n3 = static_cast<uint64_t>(host[6]);
+  inout->num_global_calcs_n3 = static_cast<uint64_t>(host[7]);
+  inout->num_global_calcs_no_n3 = static_cast<uint64_t>(host[8]);
+  return APB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// time integration
+// ------------------------------------------------------------------------------------------------------------------
+// calculatePositionsAndResetForces (TimeDiscretization.cpp:16-68): oldF = f; f = globalForce;
+// r += v*dt + f*dt^2/(2m)   (owned particles only)
+__global__ void kIntegratePositions(int64_t n, const int32_t *__restrict__ own, const int32_t *__restrict__ type,
+                                    const double *__restrict__ massOfType, int numTypes, double dt, double gx, double gy,
+                                    double gz, double *x, double *y, double *z, const double *vx, const double *vy,
+                                    const double *vz, double *fx, double *fy, double *fz, double *ofx, double *ofy,
+                                    double *ofz) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || own[i] != APB_OWN_OWNED) return;
+  const int t = type[i];
+  const double m = massOfType[t < numTypes ? t : 0];
+  const double s = dt * dt / (2 * m);
+  const double Fx = fx[i], Fy = fy[i], Fz = fz[i];
+  ofx[i] = Fx;
+  ofy[i] = Fy;
+  ofz[i] = Fz;
+  fx[i] = gx;
+  fy[i] = gy;
+  fz[i] = gz;
+  x[i] += vx[i] * dt + Fx * s;
+  y[i] += vy[i] * dt + Fy * s;
+  z[i] += vz[i] * dt + Fz * s;
+}
+
+// calculateVelocities (TimeDiscretization.cpp:152-165): v += (f + oldF) * dt/(2m)
+__global__ void kIntegrateVelocities(int64_t n, const int32_t *__restrict__ own, const int32_t *__restrict__ type,
+                                     const double *__restrict__ massOfType, int numTypes, double dt, double *vx,
+                                     double *vy, double *vz, const double *fx, const double *fy, const double *fz,
+                                     const double *ofx, const double *ofy, const double *ofz) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || own[i] != APB_OWN_OWNED) return;
+  const int t = type[i];
+  const double m = massOfType[t < numTypes ? t : 0];
+  const double s = dt / (2 * m);
+  vx[i] += (fx[i] + ofx[i]) * s;
+  vy[i] += (fy[i] + ofy[i]) * s;
+  vz[i] += (fz[i] + ofz[i]) * s;
+}
+
+static int uploadMasses(apb_handle h, const double *mass, int numTypes) {
+  if (numTypes <= 0 || !mass) return h->fail(APB_ERR_INVALID_ARGUMENT, "integrate: need at least one type mass");
+  if (h->massHost.size() != static_cast<size_t>(numTypes) ||
+      std::memcmp(h->massHost.data(), mass, sizeof(double) * numTypes) != 0) {
+    APB_CHECK(apbEnsure(h, h->massDev, sizeof(double) * numTypes));
+    APB_CUDA(cudaMemcpyAsync(h->massDev.p, mass, sizeof(double) * numTypes, cudaMemcpyHostToDevice, h->stream));
+    APB_CUDA(cudaStreamSynchronize(h->stream));
+    h->massHost.assign(mass, mass + numTypes);
+  }
+  return APB_OK;
+}
+
+extern "C" int apb_integrate_positions(apb_handle h, double dt, const double *massOfType, int32_t numTypes,
+                                       const double *globalForce) {
+  APB_ENTRY(h);
+  if (!h->active[APB_COL_OLDFX]) return h->fail(APB_ERR_NOT_APPLICABLE, "particle kind has no oldF columns");
+  APB_CHECK(uploadMasses(h, massOfType, numTypes));
+  if (h->nslots == 0) return APB_OK;
+  const double g[3] = {globalForce ? globalForce[0] : 0., globalForce ? globalForce[1] : 0.,
+                       globalForce ? globalForce[2] : 0.};
+  ++h->launchCount, kIntegratePositions<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(
+      h->nslots, h->own, h->type, static_cast<const double *>(h->massDev.p), numTypes, dt, g[0], g[1], g[2],
+      h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->col[APB_COL_VX], h->col[APB_COL_VY], h->col[APB_COL_VZ],
+      h->col[APB_COL_FX], h->col[APB_COL_FY], h->col[APB_COL_FZ], h->col[APB_COL_OLDFX], h->col[APB_COL_OLDFY],
+      h->col[APB_COL_OLDFZ]);
+  APB_CUDA(cudaGetLastError());
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+extern "C" int apb_integrate_velocities(apb_handle h, double dt, const double *massOfType, int32_t numTypes) {
+  APB_ENTRY(h);
+  if (!h->active[APB_COL_OLDFX]) return h->fail(APB_ERR_NOT_APPLICABLE, "particle kind has no oldF columns");
+  APB_CHECK(uploadMasses(h, massOfType, numTypes));
+  if (h->nslots == 0) return APB_OK;
+  ++h->launchCount, kIntegrateVelocities<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(
+      h->nslots, h->own, h->type, static_cast<const double *>(h->massDev.p), numTypes, dt, h->col[APB_COL_VX],
+      h->col[APB_COL_VY], h->col[APB_COL_VZ], h->col[APB_COL_FX], h->col[APB_COL_FY], h->col[APB_COL_FZ],
+      h->col[APB_COL_OLDFX], h->col[APB_COL_OLDFY], h->col[APB_COL_OLDFZ]);
+  APB_CUDA(cudaGetLastError());
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// exchange machinery shared by halo exchange and migration
+// ------------------------------------------------------------------------------------------------------------------
+// select flags for one dimension. mode 0 = halo selection, mode 1 = migration.
+__global__ void kSelect(int64_t n, int mode, const double *__restrict__ pos, const int32_t *__restrict__ own, double lmin,
+                        double lmax, double il, double skin, int sendLeft, int sendRight, int *__restrict__ fl,
+                        int *__restrict__ fr) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int o = own[i];
+  const double p = pos[i];
+  int l = 0, r = 0;
+  if (mode == 0) {
+    if (o == APB_OWN_OWNED) {
+      // collectHaloParticlesForLeft/RightNeighbor (:509-545): owned particles in [lmin, lmin+il) / [lmax-il, lmax)
+      l = p >= lmin && p < lmin + il;
+      r = p >= lmax - il && p < lmax;
+    } else if (o == APB_OWN_HALO) {
+      // forwarding of already received halos (:204-225): [lmin-skin, lmin+il) else [lmax-il, lmax+skin)
+      if (p >= lmin - skin && p < lmin + il)
+        l = 1;
+      else if (p >= lmax - il && p < lmax + skin)
+        r = 1;
+    }
+  } else if (o == APB_OWN_OWNED) {
+    // categorizeParticlesIntoLeftAndRightNeighbor (:545-593): below the local box -> left, above or at max -> right
+    l = p < lmin;
+    r = p >= lmax;
+  }
+  fl[i] = l && sendLeft;
+  fr[i] = r && sendRight;
+}
+
+struct PackArgs {
+  int64_t n;
+  const int *flag, *pos;  // flag and exclusive scan of it
+  int ncols;
+  const double *src[APB_NUM_COLUMNS];
+  const int64_t *id;
+  const int32_t *type;
+  int shiftCol;  // index (within the packed columns) of the coordinate that gets the periodic shift
+  double shift;
+  double wrapMin, wrapMax;  // migration: clamp like the reference's nextafter guard
+  int clamp;
+  int64_t count;  // number of selected particles (row length of the packed buffer)
+  double *outCols;  // [ncols][count]
+  int64_t *outId;
+  int32_t *outType;
+  int *outIdx;  // selected slot indices (may be null)
+};
+
+__global__ void kPack(PackArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= a.n || !a.flag[i]) return;
+  const int q = a.pos[i];
+  for (int c = 0; c < a.ncols; ++c) {
+    double v = a.src[c][i];
+    if (c == a.shiftCol) {
+      v += a.shift;
+      if (a.clamp) {
+        // RegularGridDecomposition.cpp:575-590: a wrapped coordinate must end up inside [globalMin, globalMax)
+        if (v >= a.wrapMax) v = nextafter(a.wrapMax, a.wrapMin);
+        if (v < a.wrapMin) v = a.wrapMin;
+      }
+    }
+    a.outCols[static_cast<size_t>(c) * a.count + q] = v;
+  }
+  a.outId[q] = a.id[i];
+  a.outType[q] = a.type[i];
+  if (a.outIdx) a.outIdx[q] = static_cast<int>(i);
+}
+
+struct UnpackArgs {
+  int64_t count;
+  int64_t firstSlot;
+  int ncolsPacked;
+  const double *inCols;
+  const int64_t *inId;
+  const int32_t *inType;
+  int nAll;
+  double *dst[APB_NUM_COLUMNS];
+  int packedIndexOfCol[APB_NUM_COLUMNS];  // -1: zero-fill
+  int64_t *id;
+  int32_t *type, *own;
+  int ownership;
+  int *recvSlot;  // may be null
+};
+
+__global__ void kUnpackAppend(UnpackArgs a) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= a.count) return;
+  const int64_t s = a.firstSlot + q;
+  for (int c = 0; c < a.nAll; ++c) {
+    const int pc = a.packedIndexOfCol[c];
+    a.dst[c][s] = pc >= 0 ? a.inCols[static_cast<size_t>(pc) * a.count + q] : 0.;
+  }
+  a.id[s] = a.inId[q];
+  a.type[s] = a.inType[q];
+  a.own[s] = a.ownership;
+  if (a.recvSlot) a.recvSlot[q] = static_cast<int>(s);
+}
+
+__global__ void kMarkDummy(int64_t n, const int *__restrict__ fl, const int *__restrict__ fr, int32_t *own) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && (fl[i] || fr[i])) own[i] = APB_OWN_DUMMY;
+}
+
+// refresh: gather positions of the recorded send slots (+ shift), scatter into the recorded receive slots
+__global__ void kGatherPositions(int64_t m, const int *__restrict__ idx, const double *x, const double *y,
+                                 const double *z, int dim, double shift, double *out) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const int s = idx[q];
+  // a source that the rebuild dropped sends NaN: the receiver then keeps the stale copy
+  double px = nan(""), py = 0., pz = 0.;
+  if (s >= 0) {
+    px = x[s];
+    py = y[s];
+    pz = z[s];
+    if (dim == 0) px += shift;
+    if (dim == 1) py += shift;
+    if (dim == 2) pz += shift;
+  }
+  out[q] = px;
+  out[m + q] = py;
+  out[2 * m + q] = pz;
+}
+__global__ void kScatterPositions(int64_t m, const int *__restrict__ slot, const double *in, double *x, double *y,
+                                  double *z) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const int s = slot[q];
+  if (s < 0 || isnan(in[q])) return;
+  x[s] = in[q];
+  y[s] = in[m + q];
+  z[s] = in[2 * m + q];
+}
+
+__global__ void kRemap(int64_t m, int *idx, const int *__restrict__ inv, int64_t nOld) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const int s = idx[q];
+  idx[q] = (s >= 0 && s < nOld) ? inv[s] : -1;
+}
+__global__ void kInvertPerm(int64_t mNew, const int *__restrict__ perm, int *inv) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= mNew) return;
+  const int s = perm[q];
+  if (s >= 0) inv[s] = static_cast<int>(q);
+}
+
+// called by the rebuilds after the storage permutation: slot indices recorded by the halo exchange follow the sort
+int apbRemapHaloLinks(apb_handle h, const int *perm, int64_t nOld, int64_t nNew) {
+  if (!h->haloLinksValid) return APB_OK;
+  APB_CHECK(apbEnsure(h, h->invPerm, sizeof(int) * std::max<int64_t>(nOld, 1)));
+  int *inv = static_cast<int *>(h->invPerm.p);
+  APB_CUDA(cudaMemsetAsync(inv, 0xFF, sizeof(int) * std::max<int64_t>(nOld, 1), h->stream));
+  if (nNew > 0) ++h->launchCount, kInvertPerm<<<apbDivUp(nNew, 256), 256, 0, h->stream>>>(nNew, perm, inv);
+  for (int d = 0; d < 3; ++d)
+    for (int s = 0; s < 2; ++s) {
+      HaloLink &L = h->link[d][s];
+      if (L.nSend > 0) ++h->launchCount, kRemap<<<apbDivUp(L.nSend, 256), 256, 0, h->stream>>>(L.nSend, static_cast<int *>(L.sendIdx.p), inv, nOld);
+      if (L.nRecv > 0) ++h->launchCount, kRemap<<<apbDivUp(L.nRecv, 256), 256, 0, h->stream>>>(L.nRecv, static_cast<int *>(L.recvSlot.p), inv, nOld);
+    }
+  APB_CUDA(cudaGetLastError());
+  return APB_OK;
+}
+
+// exchange of counts and packed payloads with the two neighbours of one dimension.
+// sendBuf[s]: packed bytes for neighbour s (0 = left, 1 = right); what the left neighbour sends to its right arrives
+// here as "from left", so recvFrom[0] receives the left neighbour's right-going buffer.
+static int exchangeCounts(apb_handle h, int d, const long long sendCount[2], long long recvCount[2]) {
+  const int left = h->neighbor[d][0], right = h->neighbor[d][1];
+  if (h->nranks == 1 || (left == h->myRank && right == h->myRank)) {
+    recvCount[0] = sendCount[1];  // my right-going buffer re-enters from my left
+    recvCount[1] = sendCount[0];
+    return APB_OK;
+  }
+  long long *dbuf = reinterpret_cast<long long *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 64);
+  APB_CUDA(cudaMemcpyAsync(dbuf, sendCount, 16, cudaMemcpyHostToDevice, h->stream));
+  ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
+  APB_NCCL(g_nccl.GroupStart());
+  APB_NCCL(g_nccl.Send(dbuf + 0, 1, ncclInt64, left, comm, h->stream));
+  APB_NCCL(g_nccl.Send(dbuf + 1, 1, ncclInt64, right, comm, h->stream));
+  APB_NCCL(g_nccl.Recv(dbuf + 2, 1, ncclInt64, left, comm, h->stream));   // left neighbour's right-going count
+  APB_NCCL(g_nccl.Recv(dbuf + 3, 1, ncclInt64, right, comm, h->stream));  // right neighbour's left-going count
+  APB_NCCL(g_nccl.GroupEnd());
+  APB_CUDA(cudaMemcpyAsync(recvCount, dbuf + 2, 16, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+static int exchangePayload(apb_handle h, int d, void *const sendBuf[2], const size_t sendBytes[2], void *recvBuf[2],
+                           const size_t recvBytes[2]) {
+  const int left = h->neighbor[d][0], right = h->neighbor[d][1];
+  if (h->nranks == 1 || (left == h->myRank && right == h->myRank)) {
+    if (recvBytes[0]) APB_CUDA(cudaMemcpyAsync(recvBuf[0], sendBuf[1], recvBytes[0], cudaMemcpyDeviceToDevice, h->stream));
+    if (recvBytes[1]) APB_CUDA(cudaMemcpyAsync(recvBuf[1], sendBuf[0], recvBytes[1], cudaMemcpyDeviceToDevice, h->stream));
+    return APB_OK;
+  }
+  ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
+  APB_NCCL(g_nccl.GroupStart());
+  if (sendBytes[0]) APB_NCCL(g_nccl.Send(sendBuf[0], sendBytes[0], ncclInt8, left, comm, h->stream));
+  if (sendBytes[1]) APB_NCCL(g_nccl.Send(sendBuf[1], sendBytes[1], ncclInt8, right, comm, h->stream));
+  if (recvBytes[0]) APB_NCCL(g_nccl.Recv(recvBuf[0], recvBytes[0], ncclInt8, left, comm, h->stream));
+  if (recvBytes[1]) APB_NCCL(g_nccl.Recv(recvBuf[1], recvBytes[1], ncclInt8, right, comm, h->stream));
+  APB_NCCL(g_nccl.GroupEnd());
+  return APB_OK;
+}
+
+static inline size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
+static inline size_t packedBytes(int ncols, long long count) {
+  return alignUp(sizeof(double) * ncols * count) + alignUp(8 * count) + alignUp(4 * count);
+}
+
+// isNearRel (utils/Math.h) as used by the decomposition to detect global boundaries
+static bool nearRel(double a, double b) {
+  const double m = std::max(std::fabs(a), std::fabs(b));
+  return std::fabs(a - b) <= 1e-9 * (m > 0 ? m : 1.);
+}
+
+// One dimension of a generating exchange (halo generation or migration).
+// mode 0: halo generation (packed columns: x, y, z); mode 1: migration (all active columns).
+static int exchangeDim(apb_handle h, int d, int mode) {
+  const int64_t n = h->nslots;
+  const double lmin = h->cfg.box_min[d], lmax = h->cfg.box_max[d];
+  const double il = h->cfg.cutoff + h->cfg.skin;
+  const bool atMin = nearRel(lmin, h->globalMin[d]), atMax = nearRel(lmax, h->globalMax[d]);
+  const bool per = h->periodic[d];
+  if (!per && atMin && atMax) return APB_OK;
+  const int sendLeft = per || !atMin, sendRight = per || !atMax;
+  const double L = h->globalMax[d] - h->globalMin[d];
+  const int64_t nn = std::max<int64_t>(n, 1);
+  APB_CHECK(apbEnsure(h, h->key, sizeof(int) * nn));
+  APB_CHECK(apbEnsure(h, h->rank, sizeof(int) * nn));
+  APB_CHECK(apbEnsure(h, h->perm, sizeof(int) * nn));
+  APB_CHECK(apbEnsure(h, h->sortV, sizeof(int) * nn));
+  int *fl = static_cast<int *>(h->key.p), *fr = static_cast<int *>(h->rank.p);
+  int *pl = static_cast<int *>(h->perm.p), *pr = static_cast<int *>(h->sortV.p);
+  long long *totals = reinterpret_cast<long long *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result));
+  long long sendCount[2] = {0, 0}, recvCount[2] = {0, 0};
+  if (n > 0) {
+    ++h->launchCount, kSelect<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, mode, h->col[APB_COL_X + d], h->own, lmin, lmax, il, h->cfg.skin,
+                                                     sendLeft, sendRight, fl, fr);
+    APB_CUDA(cudaGetLastError());
+    APB_CHECK(apbExclusiveScan(h, fl, pl, n, totals));
+    APB_CHECK(apbExclusiveScan(h, fr, pr, n, totals + 1));
+    APB_CUDA(cudaMemcpyAsync(sendCount, totals, 16, cudaMemcpyDeviceToHost, h->stream));
+    APB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  APB_CHECK(exchangeCounts(h, d, sendCount, recvCount));
+  // packed columns
+  int ncols = 0;
+  int colIds[APB_NUM_COLUMNS];
+  if (mode == 0) {
+    ncols = 3;
+    colIds[0] = APB_COL_X;
+    colIds[1] = APB_COL_Y;
+    colIds[2] = APB_COL_Z;
+  } else {
+    for (int c = 0; c < APB_NUM_COLUMNS; ++c)
+      if (h->active[c]) colIds[ncols++] = c;
+  }
+  const size_t sb[2] = {packedBytes(ncols, sendCount[0]), packedBytes(ncols, sendCount[1])};
+  const size_t rb[2] = {packedBytes(ncols, recvCount[0]), packedBytes(ncols, recvCount[1])};
+  APB_CHECK(apbEnsure(h, h->xbuf[0], sb[0] + 256));
+  APB_CHECK(apbEnsure(h, h->xbuf[1], sb[1] + 256));
+  APB_CHECK(apbEnsure(h, h->xbuf[2], rb[0] + 256));
+  APB_CHECK(apbEnsure(h, h->xbuf[3], rb[1] + 256));
+  void *sendBuf[2] = {h->xbuf[0].p, h->xbuf[1].p}, *recvBuf[2] = {h->xbuf[2].p, h->xbuf[3].p};
+  for (int s = 0; s < 2; ++s) {
+    HaloLink &Lk = h->link[d][s];
+    if (mode == 0) {
+      APB_CHECK(apbEnsure(h, Lk.sendIdx, sizeof(int) * std::max<long long>(sendCount[s], 1)));
+      Lk.nSend = sendCount[s];
+      // shift applied by the sender at a global periodic boundary (:509-545)
+      Lk.shift = s == 0 ? (atMin ? +L : 0.) : (atMax ? -L : 0.);
+    }
+    if (sendCount[s] == 0) continue;
+    PackArgs a;
+    a.n = n;
+    a.flag = s == 0 ? fl : fr;
+    a.pos = s == 0 ? pl : pr;
+    a.ncols = ncols;
+    a.shiftCol = -1;
+    for (int c = 0; c < ncols; ++c) {
+      a.src[c] = h->col[colIds[c]];
+      if (colIds[c] == APB_COL_X + d) a.shiftCol = c;
+    }
+    a.id = h->id;
+    a.type = h->type;
+    a.shift = s == 0 ? (atMin ? +L : 0.) : (atMax ? -L : 0.);
+    a.clamp = mode == 1 && a.shift != 0.;
+    a.wrapMin = h->globalMin[d];
+    a.wrapMax = h->globalMax[d];
+    a.count = sendCount[s];
+    char *base = static_cast<char *>(sendBuf[s]);
+    a.outCols = reinterpret_cast<double *>(base);
+    a.outId = reinterpret_cast<int64_t *>(base + alignUp(sizeof(double) * ncols * sendCount[s]));
+    a.outType = reinterpret_cast<int32_t *>(base + alignUp(sizeof(double) * ncols * sendCount[s]) + alignUp(8 * sendCount[s]));
+    a.outIdx = mode == 0 ? static_cast<int *>(Lk.sendIdx.p) : nullptr;
+    ++h->launchCount, kPack<<<apbDivUp(n, 256), 256, 0, h->stream>>>(a);
+    APB_CUDA(cudaGetLastError());
+  }
+  if (mode == 1 && n > 0 && (sendCount[0] || sendCount[1])) {
+    ++h->launchCount, kMarkDummy<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, fl, fr, h->own);
+    APB_CUDA(cudaGetLastError());
+  }
+  APB_CHECK(exchangePayload(h, d, sendBuf, sb, recvBuf, rb));
+  // append what arrived: from the left neighbour first, then from the right one
+  const long long nRecvTotal = recvCount[0] + recvCount[1];
+  if (nRecvTotal > 0) APB_CHECK(apbReserveSlots(h, n + nRecvTotal));
+  int64_t first = n;
+  for (int s = 0; s < 2; ++s) {
+    HaloLink &Lk = h->link[d][s];
+    if (mode == 0) {
+      APB_CHECK(apbEnsure(h, Lk.recvSlot, sizeof(int) * std::max<long long>(recvCount[s], 1)));
+      Lk.nRecv = recvCount[s];
+    }
+    if (recvCount[s] == 0) continue;
+    UnpackArgs u;
+    u.count = recvCount[s];
+    u.firstSlot = first;
+    u.ncolsPacked = ncols;
+    char *base = static_cast<char *>(recvBuf[s]);
+    u.inCols = reinterpret_cast<const double *>(base);
+    u.inId = reinterpret_cast<const int64_t *>(base + alignUp(sizeof(double) * ncols * recvCount[s]));
+    u.inType = reinterpret_cast<const int32_t *>(base + alignUp(sizeof(double) * ncols * recvCount[s]) + alignUp(8 * recvCount[s]));
+    u.nAll = 0;
+    for (int c = 0; c < APB_NUM_COLUMNS; ++c) {
+      if (!h->active[c]) continue;
+      u.dst[u.nAll] = h->col[c];
+      int pc = -1;
+      for (int k = 0; k < ncols; ++k)
+        if (colIds[k] == c) pc = k;
+      u.packedIndexOfCol[u.nAll] = pc;
+      ++u.nAll;
+    }
+    u.id = h->id;
+    u.type = h->type;
+    u.own = h->own;
+    u.ownership = mode == 0 ? APB_OWN_HALO : APB_OWN_OWNED;
+    u.recvSlot = mode == 0 ? static_cast<int *>(Lk.recvSlot.p) : nullptr;
+    ++h->launchCount, kUnpackAppend<<<apbDivUp(recvCount[s], 256), 256, 0, h->stream>>>(u);
+    APB_CUDA(cudaGetLastError());
+    first += recvCount[s];
+  }
+  h->nslots = n + nRecvTotal;
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+static int ensureDecomposition(apb_handle h) {
+  if (h->decompositionSet) return APB_OK;
+  if (h->nranks != 1) return h->fail(APB_ERR_STATE, "apb_set_decomposition must be called on multi-rank runs");
+  for (int d = 0; d < 3; ++d) {  // single rank: fully periodic box that is its own neighbour
+    h->globalMin[d] = h->cfg.box_min[d];
+    h->globalMax[d] = h->cfg.box_max[d];
+    h->periodic[d] = true;
+    h->neighbor[d][0] = h->neighbor[d][1] = 0;
+  }
+  h->decompositionSet = true;
+  return APB_OK;
+}
+
+// RegularGridDecomposition::exchangeMigratingParticles (:238-301) fused with the container update that precedes it in
+// the simulation loop (Simulation.cpp:247-263): halos and dummies are dropped, owned particles that left the local box
+// travel to the neighbour (wrapped at periodic global boundaries), arrivals are appended as owned.
+extern "C" int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num_received) {
+  APB_ENTRY(h);
+  APB_CHECK(ensureDecomposition(h));
+  APB_CHECK(apb_delete_halo_particles(h));
+  h->haloLinksValid = false;
+  const int64_t before = h->nslots;
+  int64_t received = 0;
+  for (int d = 0; d < 3; ++d) {
+    const int64_t n0 = h->nslots;
+    APB_CHECK(exchangeDim(h, d, 1));
+    received += h->nslots - n0;
+  }
+  (void)before;
+  // compact: drop dummies (sent particles, old halos); nothing is outside the local box any more
+  int64_t nl = 0;
+  APB_CHECK(apb_update_container(h, 0, &nl));
+  if (out_num_received) *out_num_received = received;
+  if (out_num_sent) *out_num_sent = received;  // single rank: identical; multi rank: local view of arrivals
+  h->structureValid = false;
+  h->prunedValid = false;
+  h->countsValid = false;
+  return APB_OK;
+}
+
+// RegularGridDecomposition::exchangeHaloParticles (:159-236). If the container structure is invalid (rebuild step)
+// halos are selected and appended; otherwise only the positions of the existing halo copies are refreshed through the
+// recorded send / receive slots (bulk ParticleContainerInterface::updateHaloParticle, no re-selection).
+extern "C" int apb_exchange_halos(apb_handle h) {
+  APB_ENTRY(h);
+  APB_CHECK(ensureDecomposition(h));
+  if (!h->structureValid) {
+    APB_CHECK(apb_delete_halo_particles(h));
+    for (int d = 0; d < 3; ++d)
+      for (int s = 0; s < 2; ++s) h->link[d][s].nSend = h->link[d][s].nRecv = 0;
+    for (int d = 0; d < 3; ++d) APB_CHECK(exchangeDim(h, d, 0));
+    h->haloLinksValid = true;
+    h->countsValid = false;
+    return APB_OK;
+  }
+  if (!h->haloLinksValid) return h->fail(APB_ERR_STATE, "apb_exchange_halos: no halo links recorded; call it once before the rebuild");
+  for (int d = 0; d < 3; ++d) {
+    void *sendBuf[2], *recvBuf[2];
+    size_t sb[2], rb[2];
+    for (int s = 0; s < 2; ++s) {
+      HaloLink &Lk = h->link[d][s];
+      sb[s] = sizeof(double) * 3 * Lk.nSend;
+      APB_CHECK(apbEnsure(h, h->xbuf[s], sb[s] + 256));
+      sendBuf[s] = h->xbuf[s].p;
+      if (Lk.nSend > 0) {
+        ++h->launchCount, kGatherPositions<<<apbDivUp(Lk.nSend, 256), 256, 0, h->stream>>>(
+            Lk.nSend, static_cast<const int *>(Lk.sendIdx.p), h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], d,
+            Lk.shift, static_cast<double *>(sendBuf[s]));
+        APB_CUDA(cudaGetLastError());
+      }
+    }
+    for (int s = 0; s < 2; ++s) {
+      rb[s] = sizeof(double) * 3 * h->link[d][s].nRecv;
+      APB_CHECK(apbEnsure(h, h->xbuf[2 + s], rb[s] + 256));
+      recvBuf[s] = h->xbuf[2 + s].p;
+    }
+    APB_CHECK(exchangePayload(h, d, sendBuf, sb, recvBuf, rb));
+    for (int s = 0; s < 2; ++s) {
+      HaloLink &Lk = h->link[d][s];
+      if (Lk.nRecv > 0) {
+        ++h->launchCount, kScatterPositions<<<apbDivUp(Lk.nRecv, 256), 256, 0, h->stream>>>(
+            Lk.nRecv, static_cast<const int *>(Lk.recvSlot.p), static_cast<const double *>(recvBuf[s]), h->col[APB_COL_X],
+            h->col[APB_COL_Y], h->col[APB_COL_Z]);
+        APB_CUDA(cudaGetLastError());
+      }
+    }
+  }
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the simulation loop, device resident
+// ------------------------------------------------------------------------------------------------------------------
+int apbCheckTraversal(apb_handle h, int traversal, int newton3);
+
+// Simulation::simulate (examples/md-flexible/src/Simulation.cpp:230-351) for the built-in functors, without leaving the
+// device: positions -> (every rebuild_frequency steps: migrate, halo exchange, rebuild | else: halo refresh) -> forces
+// -> velocities. Work is enqueued asynchronously; the host only blocks on rebuild steps (it needs sizes) and at the end.
+extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb_loop_params *p, int32_t numSteps,
+                             int64_t firstIteration, apb_traversal_result *outPerStep) {
+  APB_ENTRY(h);
+  if (!functor || !p || numSteps < 0) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_run_steps: bad argument");
+  if (p->rebuild_frequency < 1) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_run_steps: rebuild_frequency must be >= 1");
+  APB_CHECK(apbCheckTraversal(h, p->traversal, p->newton3));
+  if (numSteps == 0) return APB_OK;
+  APB_CHECK(apbEnsure(h, h->loopResults, sizeof(apb_traversal_result) * numSteps));
+  apb_traversal_result *dres = static_cast<apb_traversal_result *>(h->loopResults.p);
+  int rc = APB_OK;
+  h->deferSync = true;
+  for (int s = 0; s < numSteps && rc == APB_OK; ++s) {
+    const int64_t it = firstIteration + s;
+    apbLoopTimingRecord(h, 3, true);
+    rc = apb_integrate_positions(h, p->dt, p->mass_of_type, p->num_types, p->global_force);
+    apbLoopTimingRecord(h, 3, false);
+    if (rc != APB_OK) break;
+    const bool rebuild = (it % p->rebuild_frequency == 0) || !h->structureValid;
+    if (rebuild) {
+      h->deferSync = false;
+      apbLoopTimingRecord(h, 1, true);
+      rc = apb_migrate(h, nullptr, nullptr);
+      if (rc == APB_OK) rc = apb_exchange_halos(h);
+      if (rc == APB_OK) rc = apb_rebuild_neighbor_lists(h, p->traversal, p->newton3);
+      apbLoopTimingRecord(h, 1, false);
+      h->deferSync = true;
+    } else {
+      apbLoopTimingRecord(h, 2, true);
+      rc = apb_exchange_halos(h);
+      apbLoopTimingRecord(h, 2, false);
+    }
+    if (rc != APB_OK) break;
+    h->asyncResultDev = dres + s;
+    apbLoopTimingRecord(h, 0, true);
+    rc = apb_compute_interactions(h, p->traversal, functor, p->newton3, nullptr);
+    apbLoopTimingRecord(h, 0, false);
+    h->asyncResultDev = nullptr;
+    if (rc != APB_OK) break;
+    apbLoopTimingRecord(h, 3, true);
+    rc = apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
+    apbLoopTimingRecord(h, 3, false);
+  }
+  h->deferSync = false;
+  h->asyncResultDev = nullptr;
+  if (rc != APB_OK) return rc;
+  if (outPerStep) {
+    APB_CUDA(cudaMemcpyAsync(outPerStep, dres, sizeof(apb_traversal_result) * numSteps, cudaMemcpyDeviceToHost, h->stream));
+  }
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (outPerStep) {
+    for (int s = 0; s < numSteps; ++s) {
+      if (!(functor->flags & APB_FUNCTOR_CALC_GLOBALS)) {
+        outPerStep[s].upot_sum = 0.;
+        outPerStep[s].virial_sum[0] = outPerStep[s].virial_sum[1] = outPerStep[s].virial_sum[2] = 0.;
+      }
+    }
+  }
+  return APB_OK;
+}
+
+// the stream all work of this handle is enqueued on (for CUDA-event timing by the caller)
+extern "C" int apb_get_stream(apb_handle h, void **outStream) {
+  APB_ENTRY(h);
+  if (!outStream) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_get_stream: null argument");
+  *outStream = h->stream;
+  return APB_OK;
+}

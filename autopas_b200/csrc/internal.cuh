@@ -46,6 +46,14 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+// slots recorded by the halo exchange of one (dimension, side): which of my slots feed the message to that neighbour
+// and where the particles received from that neighbour live
+struct HaloLink {
+  DevBuf sendIdx, recvSlot;
+  long long nSend = 0, nRecv = 0;
+  double shift = 0.;
+};
+
 struct apb_handle_s {
   apb_config cfg{};
   cudaStream_t stream = nullptr;
@@ -105,6 +113,32 @@ struct apb_handle_s {
   void *pinned = nullptr;
   size_t pinnedCap = 0;
 
+  // ---- decomposition / exchange (dynamics.cu) ----
+  int nranks = 1, myRank = 0;
+  void *comm = nullptr;  // ncclComm_t
+  bool decompositionSet = false;
+  double globalMin[3]{}, globalMax[3]{};
+  bool periodic[3]{};
+  int neighbor[3][2]{};
+  bool haloLinksValid = false;
+  HaloLink link[3][2];
+  DevBuf invPerm, xbuf[4], massDev;
+  std::vector<double> massHost;
+
+  // phase timing of apb_run_steps (perf.cu)
+  struct LoopEvent {
+    void *ev;
+    int phase;
+    bool begin;
+  };
+  bool loopTiming = false;
+  std::vector<LoopEvent> loopEvents;
+  std::vector<void *> eventPool;
+  long long launchCount = 0;                      // kernels launched through this handle
+  bool deferSync = false;                          // apb_run_steps: do not block after every call
+  apb_traversal_result *asyncResultDev = nullptr;  // apb_run_steps: where the reduced accumulators of this step go
+  DevBuf loopResults;
+
   int64_t numOwned = 0, numHalo = 0;  // refreshed lazily
   bool countsValid = false;
 
@@ -157,6 +191,13 @@ int apbRebuildVCL(apb_handle h, int newton3);
 int apbBuildPruned(apb_handle h);
 void apbComputeLCGeom(const apb_config &cfg, LCGeom &g);
 int apbComputeStencil(apb_handle h);
+
+// perf.cu
+int apbLoopTimingRecord(apb_handle h, int phase, bool begin);
+
+// dynamics.cu
+int apbRemapHaloLinks(apb_handle h, const int *perm, int64_t nOld, int64_t nNew);
+void apbCommDestroy(apb_handle h);
 
 // lj.cu
 int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3, apb_traversal_result *out);

@@ -297,8 +297,19 @@ int apbPrepareLJParams(apb_handle h, const apb_functor *f, LJParams &p) {
 int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f, apb_traversal_result *out) {
   apb_traversal_result host;
   std::memset(&host, 0, sizeof(host));
+  if (h->asyncResultDev) {
+    // device-resident loop (apb_run_steps): the reduced accumulators stay on the device, no host sync per step
+    if (stats && numBlocks > 0) {
+      ++h->launchCount, kReducePartials<<<1, 256, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
+                                                h->asyncResultDev);
+      APB_CUDA(cudaGetLastError());
+    } else {
+      APB_CUDA(cudaMemsetAsync(h->asyncResultDev, 0, sizeof(apb_traversal_result), h->stream));
+    }
+    return APB_OK;
+  }
   if (stats && numBlocks > 0) {
-    kReducePartials<<<1, 256, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
+    ++h->launchCount, kReducePartials<<<1, 256, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
                                               static_cast<apb_traversal_result *>(h->result.p));
     APB_CUDA(cudaGetLastError());
     APB_CUDA(cudaMemcpyAsync(&host, h->result.p, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
@@ -321,14 +332,14 @@ int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f
   do {                                                                                             \
     const int sel = (mix ? 4 : 0) | (stats ? 2 : 0) | (n3 ? 1 : 0);                                \
     switch (sel) {                                                                                 \
-      case 0: KERNEL<false, false, false><<<grid, block, 0, h->stream>>>(args); break;             \
-      case 1: KERNEL<false, false, true><<<grid, block, 0, h->stream>>>(args); break;              \
-      case 2: KERNEL<false, true, false><<<grid, block, 0, h->stream>>>(args); break;              \
-      case 3: KERNEL<false, true, true><<<grid, block, 0, h->stream>>>(args); break;               \
-      case 4: KERNEL<true, false, false><<<grid, block, 0, h->stream>>>(args); break;              \
-      case 5: KERNEL<true, false, true><<<grid, block, 0, h->stream>>>(args); break;               \
-      case 6: KERNEL<true, true, false><<<grid, block, 0, h->stream>>>(args); break;               \
-      default: KERNEL<true, true, true><<<grid, block, 0, h->stream>>>(args); break;               \
+      case 0: ++h->launchCount, KERNEL<false, false, false><<<grid, block, 0, h->stream>>>(args); break;             \
+      case 1: ++h->launchCount, KERNEL<false, false, true><<<grid, block, 0, h->stream>>>(args); break;              \
+      case 2: ++h->launchCount, KERNEL<false, true, false><<<grid, block, 0, h->stream>>>(args); break;              \
+      case 3: ++h->launchCount, KERNEL<false, true, true><<<grid, block, 0, h->stream>>>(args); break;               \
+      case 4: ++h->launchCount, KERNEL<true, false, false><<<grid, block, 0, h->stream>>>(args); break;              \
+      case 5: ++h->launchCount, KERNEL<true, false, true><<<grid, block, 0, h->stream>>>(args); break;               \
+      case 6: ++h->launchCount, KERNEL<true, true, false><<<grid, block, 0, h->stream>>>(args); break;               \
+      default: ++h->launchCount, KERNEL<true, true, true><<<grid, block, 0, h->stream>>>(args); break;               \
     }                                                                                              \
   } while (0)
 

@@ -214,7 +214,7 @@ int apbBuildPruned(apb_handle h) {
   int *maxStagedDev = reinterpret_cast<int *>(scratch + 32), *overflowDev = reinterpret_cast<int *>(scratch + 36);
   APB_CUDA(cudaMemsetAsync(scratch + 32, 0, 8, h->stream));
   APB_CUDA(cudaMemsetAsync(numStaged, 0, sizeof(int) * (numTiles + 1), h->stream));
-  kPrunedStage<false><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, nullptr, nullptr, maxStagedDev, overflowDev);
+  ++h->launchCount, kPrunedStage<false><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, nullptr, nullptr, maxStagedDev, overflowDev);
   APB_CUDA(cudaGetLastError());
   APB_CHECK(apbExclusiveScan(h, numStaged, stagedStart, numTiles + 1, totals));
   long long totalStaged = 0;
@@ -234,7 +234,7 @@ int apbBuildPruned(apb_handle h) {
   h->prunedMaxStaged = maxStaged;
   APB_CHECK(apbEnsure(h, h->prStaged, sizeof(int) * std::max<long long>(totalStaged, 1)));
   int *staged = static_cast<int *>(h->prStaged.p);
-  kPrunedStage<true><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, stagedStart, staged, maxStagedDev, overflowDev);
+  ++h->launchCount, kPrunedStage<true><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, stagedStart, staged, maxStagedDev, overflowDev);
   APB_CUDA(cudaGetLastError());
   const size_t smemLists = sizeof(int) * std::max(maxStaged, 1);
   if (smemLists > 48 * 1024) {
@@ -242,7 +242,7 @@ int apbBuildPruned(apb_handle h) {
     APB_CUDA(cudaFuncSetAttribute(kPrunedLists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemLists)));
   }
   APB_CUDA(cudaMemsetAsync(warpLen, 0, sizeof(int) * (numWarps + 1), h->stream));
-  kPrunedLists<false><<<numTiles, PR_TILE, smemLists, h->stream>>>(a, stagedStart, staged, warpLen, nullptr, nullptr);
+  ++h->launchCount, kPrunedLists<false><<<numTiles, PR_TILE, smemLists, h->stream>>>(a, stagedStart, staged, warpLen, nullptr, nullptr);
   APB_CUDA(cudaGetLastError());
   APB_CHECK(apbExclusiveScan(h, warpLen, warpStart, numWarps + 1, totals));
   long long totalRows = 0;
@@ -251,7 +251,7 @@ int apbBuildPruned(apb_handle h) {
   if (totalRows > 0x7fffffffLL / 32) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: lists exceed 2^31 entries");
   h->prunedRows = totalRows;
   APB_CHECK(apbEnsure(h, h->prLists, sizeof(unsigned short) * 32 * std::max<long long>(totalRows, 1)));
-  kPrunedLists<true><<<numTiles, PR_TILE, smemLists, h->stream>>>(a, stagedStart, staged, warpLen, warpStart,
+  ++h->launchCount, kPrunedLists<true><<<numTiles, PR_TILE, smemLists, h->stream>>>(a, stagedStart, staged, warpLen, warpStart,
                                                                   static_cast<unsigned short *>(h->prLists.p));
   APB_CUDA(cudaGetLastError());
   APB_CUDA(cudaStreamSynchronize(h->stream));
@@ -370,7 +370,7 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
     if (smem > 48 * 1024)                                                                                            \
       APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                     static_cast<int>(smem)));                                                       \
-    kLJPruned<MIXV, STATSV><<<numTiles, PR_TILE, smem, h->stream>>>(a);                                              \
+    ++h->launchCount, kLJPruned<MIXV, STATSV><<<numTiles, PR_TILE, smem, h->stream>>>(a);                                              \
   } while (0)
   switch (sel) {
     case 0: PR_LAUNCH(false, false); break;

@@ -123,11 +123,11 @@ __global__ void kScanTotal(const int *in, const int *out, int64_t n, long long *
 static int scanRec(apb_handle h, const int *in, int *out, int64_t n, int *scratch) {
   const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
   int *sums = scratch;
-  kScanBlock<<<static_cast<unsigned>(nb), SCAN_BLOCK, 0, h->stream>>>(in, out, sums, n);
+  ++h->launchCount, kScanBlock<<<static_cast<unsigned>(nb), SCAN_BLOCK, 0, h->stream>>>(in, out, sums, n);
   if (nb > 1) {
     int *sumsScanned = scratch + nb;
     APB_CHECK(scanRec(h, sums, sumsScanned, nb, scratch + 2 * nb));
-    kScanAddOffsets<<<static_cast<unsigned>(nb), SCAN_BLOCK, 0, h->stream>>>(out, sumsScanned, n);
+    ++h->launchCount, kScanAddOffsets<<<static_cast<unsigned>(nb), SCAN_BLOCK, 0, h->stream>>>(out, sumsScanned, n);
   }
   return APB_OK;
 }
@@ -138,7 +138,7 @@ int apbExclusiveScan(apb_handle h, const int *in, int *out, int64_t n, long long
     APB_CHECK(apbEnsure(h, h->scanTmp, sizeof(int) * (4 * nb + 64)));
     APB_CHECK(scanRec(h, in, out, n, static_cast<int *>(h->scanTmp.p)));
   }
-  if (totalDev) kScanTotal<<<1, 1, 0, h->stream>>>(in, out, n, totalDev);
+  if (totalDev) ++h->launchCount, kScanTotal<<<1, 1, 0, h->stream>>>(in, out, n, totalDev);
   APB_CUDA(cudaGetLastError());
   return APB_OK;
 }
@@ -267,6 +267,15 @@ extern "C" int apb_destroy(apb_handle h) {
                     &h->partials,     &h->result,       &h->mixDev,       &h->leaverIdx};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
+  DevBuf *more[] = {&h->loopResults, &h->invPerm, &h->xbuf[0], &h->xbuf[1], &h->xbuf[2], &h->xbuf[3], &h->massDev};
+  for (DevBuf *b : more)
+    if (b->p) cudaFree(b->p);
+  for (int d = 0; d < 3; ++d)
+    for (int s = 0; s < 2; ++s) {
+      if (h->link[d][s].sendIdx.p) cudaFree(h->link[d][s].sendIdx.p);
+      if (h->link[d][s].recvSlot.p) cudaFree(h->link[d][s].recvSlot.p);
+    }
+  apbCommDestroy(h);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -317,7 +326,7 @@ extern "C" int apb_add_particles(apb_handle h, int64_t n, const double *x, const
   }
   if (ids) APB_CUDA(cudaMemcpyAsync(h->id + first, ids, sizeof(int64_t) * n, cudaMemcpyHostToDevice, h->stream));
   if (types) APB_CUDA(cudaMemcpyAsync(h->type + first, types, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
-  kFillAppended<<<apbDivUp(n, 256), 256, 0, h->stream>>>(first, n, h->id, h->type, h->own, ownership, ids != nullptr,
+  ++h->launchCount, kFillAppended<<<apbDivUp(n, 256), 256, 0, h->stream>>>(first, n, h->id, h->type, h->own, ownership, ids != nullptr,
                                                          types != nullptr);
   APB_CUDA(cudaGetLastError());
   APB_CUDA(cudaStreamSynchronize(h->stream));
@@ -346,7 +355,7 @@ __global__ void kDeleteHalo(int64_t n, int32_t *own) {
 extern "C" int apb_delete_halo_particles(apb_handle h) {
   APB_ENTRY(h);
   if (h->nslots > 0) {
-    kDeleteHalo<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->own);
+    ++h->launchCount, kDeleteHalo<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->own);
     APB_CUDA(cudaGetLastError());
     APB_CUDA(cudaStreamSynchronize(h->stream));
   }
@@ -431,11 +440,11 @@ extern "C" int apb_update_halo_particles(apb_handle h, int64_t n, const int64_t 
   APB_CUDA(cudaMemcpyAsync(dY, y, 8 * n, cudaMemcpyHostToDevice, h->stream));
   APB_CUDA(cudaMemcpyAsync(dZ, z, 8 * n, cudaMemcpyHostToDevice, h->stream));
   if (h->nslots > 0)
-    kHashInsertHalo<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->id, h->own, keys, vals, tableSize - 1);
+    ++h->launchCount, kHashInsertHalo<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->id, h->own, keys, vals, tableSize - 1);
   // search radius: the halo copy may have moved by at most skin since the lists were built (LinkedCells.h:95-105
   // searches +-skin around the new position; VerletClusterLists.h:199 +-skin/2)
   const double r = h->cfg.skin;
-  kHashUpdateHalo<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, dIds, dX, dY, dZ, keys, vals, tableSize - 1,
+  ++h->launchCount, kHashUpdateHalo<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, dIds, dX, dY, dZ, keys, vals, tableSize - 1,
                                                            h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z],
                                                            3. * r * r, dNotFound);
   APB_CUDA(cudaGetLastError());
@@ -466,7 +475,7 @@ extern "C" int apb_get_num_particles(apb_handle h, int64_t *out_owned, int64_t *
       unsigned long long *d =
           reinterpret_cast<unsigned long long *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 64);
       APB_CUDA(cudaMemsetAsync(d, 0, 16, h->stream));
-      kCountOwnership<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->own, d);
+      ++h->launchCount, kCountOwnership<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->own, d);
       APB_CUDA(cudaGetLastError());
       APB_CUDA(cudaMemcpyAsync(counts, d, 16, cudaMemcpyDeviceToHost, h->stream));
       APB_CUDA(cudaStreamSynchronize(h->stream));
@@ -542,6 +551,24 @@ static int transfer3(apb_handle h, int firstCol, const double *const src[3], dou
   const int64_t n = h->nslots;
   if (n == 0) return APB_OK;
   const size_t bytes = sizeof(double) * n;
+  // caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister) are used for DMA directly
+  bool pinnedUser = true;
+  for (int d = 0; d < 3; ++d) {
+    cudaPointerAttributes attr;
+    const void *p = src ? static_cast<const void *>(src[d]) : static_cast<const void *>(dst[d]);
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess || attr.type != cudaMemoryTypeHost) pinnedUser = false;
+  }
+  cudaGetLastError();
+  if (pinnedUser) {
+    for (int d = 0; d < 3; ++d) {
+      if (src)
+        APB_CUDA(cudaMemcpyAsync(h->col[firstCol + d], src[d], bytes, cudaMemcpyHostToDevice, h->stream));
+      else
+        APB_CUDA(cudaMemcpyAsync(dst[d], h->col[firstCol + d], bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    APB_CUDA(cudaStreamSynchronize(h->stream));
+    return APB_OK;
+  }
   APB_CHECK(apbEnsurePinned(h, 3 * bytes));
   char *pin = static_cast<char *>(h->pinned);
   if (src) {
@@ -592,7 +619,7 @@ __global__ void kFill3(int64_t n, double *a, double *b, double *c, double va, do
 extern "C" int apb_reset_forces(apb_handle h, double fx, double fy, double fz) {
   APB_ENTRY(h);
   if (h->nslots == 0) return APB_OK;
-  kFill3<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->col[APB_COL_FX], h->col[APB_COL_FY],
+  ++h->launchCount, kFill3<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->col[APB_COL_FX], h->col[APB_COL_FY],
                                                           h->col[APB_COL_FZ], fx, fy, fz);
   APB_CUDA(cudaGetLastError());
   APB_CUDA(cudaStreamSynchronize(h->stream));
@@ -680,7 +707,7 @@ int apbPermuteStorage(apb_handle h, const int *perm, int64_t newSlots) {
     ++a.ncols;
   }
   if (newSlots > 0) {
-    kGatherAll<<<apbDivUp(newSlots, 256), 256, 0, h->stream>>>(newSlots, perm, a, h->id, h->idTmp, h->type, h->typeTmp,
+    ++h->launchCount, kGatherAll<<<apbDivUp(newSlots, 256), 256, 0, h->stream>>>(newSlots, perm, a, h->id, h->idTmp, h->type, h->typeTmp,
                                                                h->own, h->ownTmp);
     APB_CUDA(cudaGetLastError());
   }
@@ -712,7 +739,7 @@ extern "C" int apb_update_container(apb_handle h, int32_t keep, int64_t *out_num
   int *flag = static_cast<int *>(h->key.p), *keepF = static_cast<int *>(h->rank.p),
       *leavF = static_cast<int *>(h->perm.p);
   const auto &c = h->cfg;
-  kClassify<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own,
+  ++h->launchCount, kClassify<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own,
                                                      c.box_min[0], c.box_min[1], c.box_min[2], c.box_max[0],
                                                      c.box_max[1], c.box_max[2], flag, keepF, leavF);
   APB_CUDA(cudaGetLastError());
@@ -723,13 +750,13 @@ extern "C" int apb_update_container(apb_handle h, int32_t keep, int64_t *out_num
   int *leaverIdx = static_cast<int *>(h->leaverIdx.p);
   long long hostTotals[2] = {0, 0};
   if (keep) {
-    kMarkAndCollect<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, flag, leavPos, h->own, leaverIdx);
+    ++h->launchCount, kMarkAndCollect<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, flag, leavPos, h->own, leaverIdx);
     APB_CUDA(cudaGetLastError());
     APB_CUDA(cudaMemcpyAsync(hostTotals, totals, 8, cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaStreamSynchronize(h->stream));
   } else {
     // collect leavers first (own[] still intact apart from the marking, which only concerns non-kept slots)
-    kMarkAndCollect<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, flag, leavPos, h->own, leaverIdx);
+    ++h->launchCount, kMarkAndCollect<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, flag, leavPos, h->own, leaverIdx);
     APB_CUDA(cudaGetLastError());
     APB_CUDA(cudaMemcpyAsync(hostTotals, totals, 8, cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaStreamSynchronize(h->stream));
@@ -742,16 +769,16 @@ extern "C" int apb_update_container(apb_handle h, int32_t keep, int64_t *out_num
     double *tmp = static_cast<double *>(h->sortK1.p);
     for (int k = 0; k < 6; ++k) {
       h->leaverCols[k].resize(nl);
-      kGatherD<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->col[APB_COL_X + k], tmp);
+      ++h->launchCount, kGatherD<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->col[APB_COL_X + k], tmp);
       APB_CUDA(cudaMemcpyAsync(h->leaverCols[k].data(), tmp, sizeof(double) * nl, cudaMemcpyDeviceToHost, h->stream));
       APB_CUDA(cudaStreamSynchronize(h->stream));
     }
     h->leaverIds.resize(nl);
     h->leaverTypes.resize(nl);
-    kGatherI64<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->id, reinterpret_cast<int64_t *>(tmp));
+    ++h->launchCount, kGatherI64<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->id, reinterpret_cast<int64_t *>(tmp));
     APB_CUDA(cudaMemcpyAsync(h->leaverIds.data(), tmp, 8 * nl, cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaStreamSynchronize(h->stream));
-    kGatherI32<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->type, reinterpret_cast<int32_t *>(tmp));
+    ++h->launchCount, kGatherI32<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->type, reinterpret_cast<int32_t *>(tmp));
     APB_CUDA(cudaMemcpyAsync(h->leaverTypes.data(), tmp, 4 * nl, cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaStreamSynchronize(h->stream));
   }
@@ -763,12 +790,13 @@ extern "C" int apb_update_container(apb_handle h, int32_t keep, int64_t *out_num
     APB_CUDA(cudaStreamSynchronize(h->stream));
     const int64_t nk = hostTotals[1];
     int *perm = static_cast<int *>(h->perm.p);  // leaver flags no longer needed
-    kKeepPerm<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, flag, keepPos, perm);
+    ++h->launchCount, kKeepPerm<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, flag, keepPos, perm);
     APB_CUDA(cudaGetLastError());
     APB_CHECK(apbPermuteStorage(h, perm, nk));
     APB_CUDA(cudaStreamSynchronize(h->stream));
     h->structureValid = false;
     h->prunedValid = false;
+    h->haloLinksValid = false;
   }
   h->countsValid = false;
   if (out_num_leavers) *out_num_leavers = nl;

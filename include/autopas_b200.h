@@ -211,6 +211,66 @@ int apb_make_lj_mixing_table(int32_t num_types, const double *epsilon, const dou
 /* ParticlePropertiesLibrary::calcShift6 (:576-582) */
 double apb_lj_calc_shift6(double epsilon24, double sigma_squared, double cutoff_squared);
 
+/* ---- device-resident simulation loop (SURVEY §8 e, f2): no host round trip between force steps ------------------- */
+/* Störmer-Verlet halves of examples/md-flexible/src/TimeDiscretization.cpp:
+ * calculatePositionsAndResetForces (:16-68): oldF = f; f = global_force (NULL = 0); r += v dt + f dt^2 / (2 m)
+ * calculateVelocities (:152-165): v += (f + oldF) dt / (2 m). mass_of_type[typeId]; owned particles only. */
+int apb_integrate_positions(apb_handle h, double dt, const double *mass_of_type, int32_t num_types,
+                            const double *global_force);
+int apb_integrate_velocities(apb_handle h, double dt, const double *mass_of_type, int32_t num_types);
+
+/* Regular-grid spatial decomposition of examples/md-flexible/src/domainDecomposition/RegularGridDecomposition.cpp,
+ * one rank per GPU, NCCL send/recv over NVLink instead of MPI (ParticleCommunicator.cpp:38-61).
+ * apb_comm_get_unique_id: rank 0 creates the 128-byte NCCL id, the host distributes it (e.g. torch.distributed).
+ * apb_comm_init: MPI_Cart_create analogue (:106); nranks == 1 needs no id and no NCCL.
+ * apb_set_decomposition: this rank's box is apb_config.box_*; neighbours6 = {left,right} rank per dimension
+ * (:137-149), periodic3 = BoundaryTypeOption::periodic per dimension. Defaults for a single rank: global box = local
+ * box, periodic in all dimensions, own neighbour. */
+int apb_comm_get_unique_id(void *out_128_bytes);
+int apb_comm_init(apb_handle h, int32_t nranks, int32_t rank, const void *unique_id_128_bytes);
+int apb_set_decomposition(apb_handle h, const double *global_box_min, const double *global_box_max,
+                          const int32_t *neighbours6, const int32_t *periodic3);
+/* AutoPas::updateContainer + RegularGridDecomposition::exchangeMigratingParticles (:238-301) fused on the device:
+ * halos dropped, owned particles outside the local box travel to the neighbour per dimension (periodic wrap at global
+ * boundaries), arrivals become owned. Invalidates the structure (a rebuild must follow). */
+int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num_received);
+/* RegularGridDecomposition::exchangeHaloParticles (:159-236). Structure invalid (rebuild step): select + append halos,
+ * x then y then z, forwarding received halos. Structure valid: refresh the positions of the existing halo copies only
+ * (bulk updateHaloParticle), same three-phase order, fixed message sizes. */
+int apb_exchange_halos(apb_handle h);
+/* MPI_Reduce(SUM) of potential energy / virial in Simulation.cpp:319-322, as ncclAllReduce; no-op for one rank */
+int apb_allreduce_globals(apb_handle h, apb_traversal_result *inout);
+
+typedef struct {
+  double dt;                   /* deltaT */
+  const double *mass_of_type;  /* ParticlePropertiesLibrary::getMolMass(typeId) */
+  int32_t num_types;
+  const double *global_force;  /* 3 doubles or NULL */
+  int32_t rebuild_frequency;   /* AutoPas::setVerletRebuildFrequency */
+  int32_t traversal;           /* enum apb_traversal */
+  int32_t newton3;
+} apb_loop_params;
+/* Simulation::simulate (examples/md-flexible/src/Simulation.cpp:230-351) for a built-in functor, device resident:
+ * per iteration  positions -> [iteration % rebuild_frequency == 0: migrate, halo exchange, rebuild | halo refresh]
+ * -> forces -> velocities. Enqueued asynchronously; blocks on rebuild steps and at the end. out_per_step (num_steps
+ * entries or NULL) receives each step's raw accumulators (rank-local; see apb_allreduce_globals). */
+int apb_run_steps(apb_handle h, const apb_functor *functor, const apb_loop_params *params, int32_t num_steps,
+                  int64_t first_iteration, apb_traversal_result *out_per_step);
+/* the CUDA stream (cudaStream_t) all device work of this handle is enqueued on, for event timing by the caller */
+int apb_get_stream(apb_handle h, void **out_stream);
+
+/* ---- measurement ------------------------------------------------------------------------------------------------- */
+/* number of CUDA kernels launched through this handle so far (bench.py's gpu_launches) */
+int apb_get_launch_count(apb_handle h, int64_t *out_count);
+/* CUDA-event timing of the phases of apb_run_steps on the handle's stream, the analogue of the reference's
+ * rebuild / computeInteractions / remainder timers (LogicHandler.h:1083-1125).
+ * out_ms[4] / out_counts[4]: 0 force kernels, 1 rebuild (migrate + halo generation + structure build),
+ * 2 halo refresh, 3 integration. Reading resets the record. */
+int apb_enable_loop_timing(apb_handle h, int32_t enable);
+int apb_get_loop_timing(apb_handle h, double *out_ms, int64_t *out_counts);
+/* sustained DFMA rate of the device (TFLOP/s, 2 flops per FMA): the FP64 roofline denominator, measured live */
+int apb_measure_fp64_peak(int32_t device, int32_t repeats, double *out_tflops, double *out_ms);
+
 /* ---- parity artefacts (tests only; not used by the hot path) --------------------------------------------------- */
 /* per slot: 1-D cell index (CellBlock3D::get1DIndexOfPosition) or tower index (ClusterTowerBlock2D) */
 int apb_debug_cell_of_slot(apb_handle h, int64_t *out_cell);

@@ -180,6 +180,25 @@ def lj_vcl(x, y, z, types, own, box_min, box_max, cutoff, skin, cluster_size, sh
             "slot_particle": slot_particle[:nslots], "slot_tower": slot_tower[:nslots], "pairs": pairs[:int(sizes[1])]}
 
 
+def ref_bench_lj(x, y, z, own, box_min, box_max, cutoff, skin, container="VerletClusterLists", traversal="vcl_c06",
+                 cluster_size=4, newton3=True, iters=10, rebuild_freq=10):
+    """Time the unmodified reference's force step (OpenMP, all host threads). Returns a dict with the total rebuild and
+    compute seconds. Only bench.py's cpu_baseline / --impl reference legs call this."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    own = _i64(own)
+    cont = {"LinkedCells": 0, "VerletClusterLists": 1}[container]
+    trav = {"lc_c08": 0, "lc_c18": 1, "vcl_cluster_iteration": 0, "vcl_c06": 1, "vcl_c01_balanced": 2}[traversal]
+    sec = np.zeros(4)
+    rc = ref().ref_bench_lj(ctypes.c_int64(len(x)), _p(x), _p(y), _p(z), _p(own), _p(_f64(box_min)), _p(_f64(box_max)),
+                            ctypes.c_double(cutoff), ctypes.c_double(skin), ctypes.c_int(cont), ctypes.c_int(trav),
+                            ctypes.c_int64(cluster_size), ctypes.c_int(1 if newton3 else 0), ctypes.c_int(iters),
+                            ctypes.c_int(rebuild_freq), _p(sec))
+    if rc != 0:
+        raise RuntimeError("reference bench run failed")
+    return {"rebuild_s": sec[0], "compute_s": sec[1], "num_rebuilds": int(sec[2]), "upot": sec[3],
+            "threads": ref().ref_num_threads()}
+
+
 # ---- the unmodified reference (oracle/_ref) --------------------------------------------------------------------
 def ref_lj_linkedcells(x, y, z, types, own, box_min, box_max, cutoff, skin, csf=1.0, shift=False, mixing=False,
                        newton3=True, soa=False, traversal="lc_c08", eps=1.0, sigma=1.0):

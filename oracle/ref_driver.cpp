@@ -222,7 +222,54 @@ int runVCL(int64_t n, const double *x, const double *y, const double *z, const i
 }
 }  // namespace
 
-#define DISPATCH(fn, ...)                                     \
+// Timing of the reference's own force step (bench.py --impl reference / cpu_baseline): container maintenance as
+// LogicHandler does it on rebuild iterations (updateContainer(false) -> halos re-added -> rebuildNeighborLists,
+// LogicHandler.h:165-218, 1095-1108) and functor.initTraversal / computeInteractions / endTraversal every iteration
+// (:1092-1122), OpenMP over all host threads. LJFunctor with shift and globals, no FLOP counting.
+template <class Container, class MakeTraversal>
+int benchLoop(Container &container, MakeTraversal makeTraversal, int64_t n, const double *x, const double *y,
+              const double *z, const int64_t *own, bool n3, int iters, int rebuildFreq, double *seconds) {
+  using Functor = mdLib::LJFunctor<Molecule, true, false, autopas::FunctorN3Modes::Both, true, false>;
+  Functor functor(container.getCutoff());
+  functor.setParticleProperties(24., 1.);
+  std::vector<Molecule> halos;
+  for (int64_t i = 0; i < n; ++i) {
+    Molecule m({x[i], y[i], z[i]}, {0., 0., 0.}, static_cast<unsigned long>(i), 0);
+    if (own[i] == 1) {
+      container.addParticle(m);
+    } else if (own[i] == 2) {
+      m.setOwnershipState(autopas::OwnershipState::halo);
+      halos.push_back(m);
+    }
+  }
+  auto trav = makeTraversal(functor);
+  double tRebuild = 0., tCompute = 0.;
+  int nRebuild = 0;
+  for (int it = 0; it < iters; ++it) {
+    if (it % rebuildFreq == 0) {
+      autopas::utils::Timer t;
+      t.start();
+      auto leavers = container.updateContainer(false);
+      for (const auto &hp : halos) container.addHaloParticle(hp);
+      container.rebuildNeighborLists(trav.get());
+      tRebuild += static_cast<double>(t.stop()) * 1e-9;
+      ++nRebuild;
+    }
+    autopas::utils::Timer t;
+    t.start();
+    functor.initTraversal();
+    container.computeInteractions(trav.get());
+    functor.endTraversal(n3);
+    tCompute += static_cast<double>(t.stop()) * 1e-9;
+  }
+  seconds[0] = tRebuild;
+  seconds[1] = tCompute;
+  seconds[2] = nRebuild;
+  seconds[3] = functor.getPotentialEnergy();
+  return 0;
+}
+
+#define DISPATCH(fn, ...)                                    \
   do {                                                        \
     const bool s = flags & kShift, m = flags & kMixing;       \
     if (s and m) return fn<true, true>(__VA_ARGS__);          \
@@ -257,6 +304,42 @@ int ref_lj_vcl(int64_t n, const double *x, const double *y, const double *z, con
              sigma, f, globals, flops, hitRate);
   } catch (const std::exception &e) {
     fprintf(stderr, "ref_lj_vcl: %s\n", e.what());
+    return 1;
+  }
+}
+
+// container: 0 LinkedCells (traversal 0 lc_c08, 1 lc_c18), 1 VerletClusterLists (0 cluster_iteration, 1 c06, 2 c01_balanced)
+// seconds: [total rebuild s, total compute s, number of rebuilds, potential energy of the last iteration]
+int ref_bench_lj(int64_t n, const double *x, const double *y, const double *z, const int64_t *own, const double *boxMin,
+                 const double *boxMax, double cutoff, double skin, int container, int traversal, int64_t clusterSize,
+                 int newton3, int iters, int rebuildFreq, double *seconds) {
+  try {
+    using Functor = mdLib::LJFunctor<Molecule, true, false, autopas::FunctorN3Modes::Both, true, false>;
+    const std::array<double, 3> bmin{boxMin[0], boxMin[1], boxMin[2]}, bmax{boxMax[0], boxMax[1], boxMax[2]};
+    const bool n3 = newton3 != 0;
+    const auto layout = autopas::DataLayoutOption::soa;
+    if (container == 0) {
+      autopas::LinkedCells<Molecule> c(bmin, bmax, cutoff, skin, 1.0);
+      const auto info = c.getTraversalSelectorInfo();
+      auto mk = [&](Functor &f) -> std::unique_ptr<autopas::TraversalInterface> {
+        if (traversal == 0)
+          return std::make_unique<autopas::LCC08Traversal<FMCell, Functor>>(info.cellsPerDim, f, info.interactionLength,
+                                                                            info.cellLength, layout, n3);
+        return std::make_unique<autopas::LCC18Traversal<FMCell, Functor>>(info.cellsPerDim, f, info.interactionLength,
+                                                                          info.cellLength, layout, n3);
+      };
+      return benchLoop(c, mk, n, x, y, z, own, n3, iters, rebuildFreq, seconds);
+    }
+    autopas::VerletClusterLists<Molecule> c(bmin, bmax, cutoff, skin, static_cast<size_t>(clusterSize));
+    auto mk = [&](Functor &f) -> std::unique_ptr<autopas::TraversalInterface> {
+      if (traversal == 0)
+        return std::make_unique<autopas::VCLClusterIterationTraversal<FMCell, Functor>>(f, clusterSize, layout, n3);
+      if (traversal == 1) return std::make_unique<autopas::VCLC06Traversal<FMCell, Functor>>(f, clusterSize, layout, n3);
+      return std::make_unique<autopas::VCLC01BalancedTraversal<Molecule, Functor>>(f, clusterSize, layout, n3);
+    };
+    return benchLoop(c, mk, n, x, y, z, own, n3, iters, rebuildFreq, seconds);
+  } catch (const std::exception &e) {
+    fprintf(stderr, "ref_bench_lj: %s\n", e.what());
     return 1;
   }
 }
