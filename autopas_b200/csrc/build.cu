@@ -279,11 +279,11 @@ static int segSort(apb_handle h, int mode, int64_t numSeg, int maxCount, const i
   }
   const size_t dyn = useGlobal ? 0 : smem;
   if (mode == 1) {
-    if (dyn > 48 * 1024) APB_CUDA(cudaFuncSetAttribute(kSegSort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    if (dyn > 40 * 1024) APB_CUDA(cudaFuncSetAttribute(kSegSort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
     ++h->launchCount, kSegSort<1><<<static_cast<unsigned>(numSeg), threads, dyn, h->stream>>>(start, count, perm, h->col[APB_COL_Z], h->id,
                                                                            useGlobal, gK1, gK2, gV);
   } else {
-    if (dyn > 48 * 1024) APB_CUDA(cudaFuncSetAttribute(kSegSort<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
+    if (dyn > 40 * 1024) APB_CUDA(cudaFuncSetAttribute(kSegSort<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
     ++h->launchCount, kSegSort<0><<<static_cast<unsigned>(numSeg), threads, dyn, h->stream>>>(start, count, perm, nullptr, nullptr,
                                                                            useGlobal, gK1, gK2, gV);
   }

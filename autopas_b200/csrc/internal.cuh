@@ -94,7 +94,8 @@ struct apb_handle_s {
   int prunedTiles = 0;
   int prunedMaxStaged = 0;  // clusters
   long long prunedRows = 0; // list rows of 32 entries
-  DevBuf prNumStaged, prStagedStart, prStaged, prWarpLen, prWarpStart, prLists;
+  int prunedWarps = 0;
+  DevBuf prNumStaged, prStagedStart, prStaged, prWarpLen, prWarpStart, prLists, prTileFirst, prTileNum, prTileWarp;
 
   // ---- reductions / results ----
   DevBuf partials;

@@ -66,7 +66,7 @@ def test_halo_refresh_and_migration_follow_moving_particles():
     rc, skin = 2.5, 0.4
     pos, bmin, bmax = grid_lattice(12, 1.15, jitter=0.1, seed=3)
     L = bmax - bmin
-    pos = bmin + np.mod(pos - bmin, L)
+    pos = bmin + np.mod(pos + 0.52 - bmin, L)  # puts a lattice plane within reach of the box faces
     n = len(pos)
     c = GpuParticleContainer("gpuVerletClusterLists", bmin, bmax, rc, skin, clusterSize=8)
     c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(n))
