@@ -9,26 +9,26 @@
 // forces and globals equal the list-faithful traversal; only the number of distance evaluations drops (hit rate
 // ~0.7 instead of ~0.1).
 //
-// Layout for the force kernel: a CTA owns a tile of up to 256 consecutive slots of ONE tower (8 warps). The union of the
-// clusters its particles interact with is staged once in shared memory (coalesced loads), and each lane walks its
-// private list of 16-bit indices into that staged tile. Lists are stored per warp in rows of 32 lanes x 4 entries
-// (one 8-byte load per lane per 4 pairs, 256 contiguous bytes per warp); the next row is prefetched while the current
-// one is evaluated. The pair kernel is branch-free fp64; there are no atomics. Padding entries point at a sentinel slot
-// parked at 1e300, which fails the cutoff test.
+// Layout for the force kernel: a CTA owns a tile of up to 8 warp chunks (32 consecutive slots of one tower each) taken
+// from a 2 x 2 block of towers and two consecutive z chunks, i.e. a compact brick, so that the union of the clusters its
+// particles interact with is small. That union is staged once in shared memory (coalesced loads), and each lane walks
+// its private list of 16-bit indices into the staged tile. Lists are stored per warp in rows of 32 lanes x 4 entries
+// (one 8-byte load per lane per 4 pairs, 256 contiguous bytes per warp); rows are prefetched two ahead. The pair kernel
+// is branch-free fp64; there are no atomics. Padding entries point at a sentinel slot parked at 1e300, which fails the
+// cutoff test.
 #include <algorithm>
 
 #include "internal.cuh"
 #include "lj_device.cuh"
 
-#define PR_TILE 256
-#define PR_WARPS (PR_TILE / 32)
+#define PR_WARPS 8
+#define PR_TILE (PR_WARPS * 32)
 #define PR_CAND_MAX 8192  // candidate cluster ids gathered per tile before sort/unique
 
 struct PrunedArgs {
-  int64_t nslots;
   int M, logM;
   int numTiles;
-  const int *tileFirstSlot, *tileNumSlots, *tileWarpStart;
+  const int *chunkFirst, *chunkNum;  // [numTiles * PR_WARPS]: first slot and slot count of each warp chunk (-1 / 0)
   const double *x, *y, *z;
   const int32_t *own;
   const int *clIsHalo, *nbrStart, *nbrList;
@@ -45,20 +45,26 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedStage(PrunedArgs a, int *__res
   __shared__ int nCand;
   __shared__ int chunkCount[PR_TILE];
   const int tile = blockIdx.x;
-  const int s0 = a.tileFirstSlot[tile], ns = a.tileNumSlots[tile];
-  const int c0 = s0 >> a.logM, c1 = (s0 + ns + a.M - 1) >> a.logM;
   if (threadIdx.x == 0) nCand = 0;
   __syncthreads();
-  // eligible clusters of this tile: non-halo (newton3 off: halo clusters own no list and no self interaction)
+  // eligible clusters of this tile: non-halo (newton3 off: halo clusters own no list and no self interaction).
+  // thread (warp w, lane l) looks at cluster l of chunk w (a chunk holds 32 / M <= 32 clusters)
   bool any = false;
-  for (int c = c0 + threadIdx.x; c < c1; c += PR_TILE) {
-    if (a.clIsHalo[c]) continue;
-    any = true;
-    const int e0 = a.nbrStart[c], e1 = a.nbrStart[c + 1];
-    const int base = atomicAdd(&nCand, e1 - e0 + 1);
-    if (base + (e1 - e0 + 1) <= PR_CAND_MAX) {
-      cand[base] = c;
-      for (int e = e0; e < e1; ++e) cand[base + 1 + e - e0] = a.nbrList[e];
+  {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int first = a.chunkFirst[tile * PR_WARPS + w], num = a.chunkNum[tile * PR_WARPS + w];
+    const int nc = (num + a.M - 1) >> a.logM;
+    if (first >= 0 && l < nc) {
+      const int c = (first >> a.logM) + l;
+      if (!a.clIsHalo[c]) {
+        any = true;
+        const int e0 = a.nbrStart[c], e1 = a.nbrStart[c + 1];
+        const int base = atomicAdd(&nCand, e1 - e0 + 1);
+        if (base + (e1 - e0 + 1) <= PR_CAND_MAX) {
+          cand[base] = c;
+          for (int e = e0; e < e1; ++e) cand[base + 1 + e - e0] = a.nbrList[e];
+        }
+      }
     }
   }
   const int anyBlock = __syncthreads_or(any);
@@ -121,8 +127,8 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedStage(PrunedArgs a, int *__res
 }
 
 // ---- per-particle lists ----------------------------------------------------------------------------------------------
-// One CTA per tile, thread t <-> slot. FILL = false: per-warp maximum list length in rows of 4 entries.
-// FILL = true: write the lists; entry k of lane l lives at row (k / 4): rowBase + l * 4 + (k % 4).
+// One CTA per tile, thread (warp w, lane l) <-> slot l of chunk w. FILL = false: per-warp maximum list length in rows
+// of 4 entries. FILL = true: write the lists; entry k of lane l lives at row (k / 4): rowBase + l * 4 + (k % 4).
 template <bool FILL>
 __global__ void __launch_bounds__(PR_TILE) kPrunedLists(PrunedArgs a, const int *__restrict__ stagedStart,
                                                         const int *__restrict__ staged, int *__restrict__ warpRows,
@@ -133,11 +139,14 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedLists(PrunedArgs a, const int 
   const int g0 = stagedStart[tile], nS = stagedStart[tile + 1] - g0;
   for (int t = threadIdx.x; t < nS; t += PR_TILE) stg[t] = staged[g0 + t];
   __syncthreads();
-  const int ns = a.tileNumSlots[tile];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (warp * 32 >= ns) return;  // warp outside the tile (whole warp: no partial-warp exits below)
-  const int64_t i = static_cast<int64_t>(a.tileFirstSlot[tile]) + threadIdx.x;
-  const int warpGlobal = a.tileWarpStart[tile] + warp;
+  const int warpGlobal = tile * PR_WARPS + warp;
+  const int first = a.chunkFirst[warpGlobal], num = a.chunkNum[warpGlobal];
+  if (first < 0) {  // warp without a chunk (whole warp)
+    if (!FILL && lane == 0) warpRows[warpGlobal] = 0;
+    return;
+  }
+  const int64_t i = static_cast<int64_t>(first) + lane;
   const unsigned short sentinel = static_cast<unsigned short>(nS * a.M);
   int cnt = 0;
   unsigned short *out = nullptr;
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedLists(PrunedArgs a, const int 
     rows = warpRows[warpGlobal];
     out = lists + static_cast<size_t>(warpRowStart[warpGlobal]) * 128 + lane * 4;
   }
-  if (static_cast<int>(threadIdx.x) < ns && nS > 0) {
+  if (lane < num && nS > 0) {
     const int ownI = a.own[i];
     const int A = static_cast<int>(i >> a.logM);
     // forces on halo particles are never used and carry no weight in the globals: they get no list
@@ -195,44 +204,62 @@ int apbBuildPruned(apb_handle h) {
     h->prunedValid = true;
     return APB_OK;
   }
-  // tiles: up to PR_TILE consecutive slots, never across a tower boundary (towers are contiguous slot ranges)
+  // tiles: bricks of 2 x 2 towers x 2 consecutive 32-slot chunks (towers are contiguous slot ranges, z sorted)
   const int64_t nt = h->vcl.numTowers;
+  const int nx = h->vcl.towersPerDim[0], ny = h->vcl.towersPerDim[1];
   std::vector<int> towerStart(nt + 1);
   APB_CUDA(cudaMemcpy(towerStart.data(), h->start.p, sizeof(int) * (nt + 1), cudaMemcpyDeviceToHost));
-  std::vector<int> tFirst, tNum, tWarp;
-  int warps = 0;
-  for (int64_t t = 0; t < nt; ++t) {
-    for (int s = towerStart[t]; s < towerStart[t + 1]; s += PR_TILE) {
-      const int cnt = std::min(PR_TILE, towerStart[t + 1] - s);
-      tFirst.push_back(s);
-      tNum.push_back(cnt);
-      tWarp.push_back(warps);
-      warps += (cnt + 31) / 32;
+  std::vector<int> cFirst, cNum;
+  for (int by = 0; by < ny; by += 2) {
+    for (int bx = 0; bx < nx; bx += 2) {
+      int towers[4], ntw = 0, maxChunks = 0;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          if (bx + dx >= nx || by + dy >= ny) continue;
+          const int t = (bx + dx) + (by + dy) * nx;
+          towers[ntw++] = t;
+          maxChunks = std::max(maxChunks, (towerStart[t + 1] - towerStart[t] + 31) / 32);
+        }
+      for (int zc = 0; zc < maxChunks; zc += 2) {
+        int used = 0;
+        int first[PR_WARPS], num[PR_WARPS];
+        for (int q = 0; q < ntw; ++q) {
+          const int t = towers[q];
+          const int slots = towerStart[t + 1] - towerStart[t];
+          for (int k = zc; k < zc + 2; ++k) {
+            if (k * 32 >= slots) continue;
+            first[used] = towerStart[t] + k * 32;
+            num[used] = std::min(32, slots - k * 32);
+            ++used;
+          }
+        }
+        if (used == 0) continue;
+        for (int w = 0; w < PR_WARPS; ++w) {
+          cFirst.push_back(w < used ? first[w] : -1);
+          cNum.push_back(w < used ? num[w] : 0);
+        }
+      }
     }
   }
-  const int numTiles = static_cast<int>(tFirst.size());
-  const int numWarps = warps;
+  const int numTiles = static_cast<int>(cFirst.size() / PR_WARPS);
+  const int numWarps = numTiles * PR_WARPS;
   h->prunedTiles = numTiles;
   h->prunedWarps = numWarps;
   if (numTiles == 0) {
     h->prunedValid = true;
     return APB_OK;
   }
-  APB_CHECK(apbEnsure(h, h->prTileFirst, sizeof(int) * numTiles));
-  APB_CHECK(apbEnsure(h, h->prTileNum, sizeof(int) * numTiles));
-  APB_CHECK(apbEnsure(h, h->prTileWarp, sizeof(int) * numTiles));
-  APB_CUDA(cudaMemcpyAsync(h->prTileFirst.p, tFirst.data(), sizeof(int) * numTiles, cudaMemcpyHostToDevice, h->stream));
-  APB_CUDA(cudaMemcpyAsync(h->prTileNum.p, tNum.data(), sizeof(int) * numTiles, cudaMemcpyHostToDevice, h->stream));
-  APB_CUDA(cudaMemcpyAsync(h->prTileWarp.p, tWarp.data(), sizeof(int) * numTiles, cudaMemcpyHostToDevice, h->stream));
+  APB_CHECK(apbEnsure(h, h->prTileFirst, sizeof(int) * numWarps));
+  APB_CHECK(apbEnsure(h, h->prTileNum, sizeof(int) * numWarps));
+  APB_CUDA(cudaMemcpyAsync(h->prTileFirst.p, cFirst.data(), sizeof(int) * numWarps, cudaMemcpyHostToDevice, h->stream));
+  APB_CUDA(cudaMemcpyAsync(h->prTileNum.p, cNum.data(), sizeof(int) * numWarps, cudaMemcpyHostToDevice, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
   PrunedArgs a;
-  a.nslots = n;
   a.M = M;
   a.logM = logM;
   a.numTiles = numTiles;
-  a.tileFirstSlot = static_cast<const int *>(h->prTileFirst.p);
-  a.tileNumSlots = static_cast<const int *>(h->prTileNum.p);
-  a.tileWarpStart = static_cast<const int *>(h->prTileWarp.p);
+  a.chunkFirst = static_cast<const int *>(h->prTileFirst.p);
+  a.chunkNum = static_cast<const int *>(h->prTileNum.p);
   a.x = h->col[APB_COL_X];
   a.y = h->col[APB_COL_Y];
   a.z = h->col[APB_COL_Z];
@@ -266,7 +293,7 @@ int apbBuildPruned(apb_handle h) {
   const int maxStaged = hostMisc[0];
   if (static_cast<int64_t>(maxStaged) * M > 65534)
     return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile exceeds 16-bit indices");
-  const size_t smemForce = (static_cast<size_t>(maxStaged) * M + 1) * 28;
+  const size_t smemForce = (static_cast<size_t>(maxStaged) * M + 2) * 28;
   if (smemForce > 200 * 1024)
     return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile (" + std::to_string(maxStaged * M) +
                                                " particles) does not fit shared memory; use a larger cluster size");
@@ -295,13 +322,16 @@ int apbBuildPruned(apb_handle h) {
   APB_CUDA(cudaGetLastError());
   APB_CUDA(cudaStreamSynchronize(h->stream));
   h->prunedValid = true;
+  if (getenv("APB_DEBUG"))
+    fprintf(stderr, "[apb] pruned build: slots %lld tiles %d maxStagedClusters %d totalStaged %lld rows %lld (entries %lld)\n",
+            static_cast<long long>(n), numTiles, maxStaged, totalStaged, totalRows, totalRows * 128);
   return APB_OK;
 }
 
 // ---- force kernel ------------------------------------------------------------------------------------------------
 struct PrunedForceArgs {
   int M, logM;
-  const int *tileFirstSlot, *tileNumSlots, *tileWarpStart;
+  const int *chunkFirst, *chunkNum;
   const double *x, *y, *z;
   double *fx, *fy, *fz;
   const int32_t *type, *own;
@@ -381,9 +411,21 @@ __global__ void __launch_bounds__(PR_TILE) kLJPruned(PrunedForceArgs a) {
   double *sz = sy + a.stagedCapacity;
   int *stype = reinterpret_cast<int *>(sz + a.stagedCapacity);
   const int tile = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warpGlobal = tile * PR_WARPS + warp;
   const int g0 = a.stagedStart[tile], nS = a.stagedStart[tile + 1] - g0;
   const int nP = nS << a.logM;
   const int mask = a.M - 1;
+  // issue the first list rows before staging so that their latency overlaps the staging loads
+  const int first = a.chunkFirst[warpGlobal];
+  const int rows = first >= 0 ? a.warpRows[warpGlobal] : 0;
+  const unsigned sentinel = static_cast<unsigned>(nP);
+  const unsigned sent2 = sentinel | (sentinel << 16);
+  const uint2 *list = reinterpret_cast<const uint2 *>(a.lists) +
+                      (rows > 0 ? static_cast<size_t>(a.warpRowStart[warpGlobal]) * 32 + lane : 0);
+  uint2 cur = make_uint2(sent2, sent2), nxt = cur;
+  if (rows > 0) cur = __ldg(list);
+  if (rows > 1) nxt = __ldg(list + 32);
   for (int e = threadIdx.x; e < nP; e += PR_TILE) {
     const int64_t slot = (static_cast<int64_t>(a.staged[g0 + (e >> a.logM)]) << a.logM) + (e & mask);
     // particles deleted since the list build (ownership dummy) are moved out of reach
@@ -401,36 +443,26 @@ __global__ void __launch_bounds__(PR_TILE) kLJPruned(PrunedForceArgs a) {
   }
   __syncthreads();
   PairAcc<MIX, STATS> acc;
-  const int ns = a.tileNumSlots[tile];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool warpInTile = warp * 32 < ns;
-  if (warpInTile) {
-    const int warpGlobal = a.tileWarpStart[tile] + warp;
-    const int rows = a.warpRows[warpGlobal];
-    const int64_t i = static_cast<int64_t>(a.tileFirstSlot[tile]) + threadIdx.x;
-    const bool active = static_cast<int>(threadIdx.x) < ns && a.own[i] == APB_OWN_OWNED;
-    if (rows > 0) {
-      const uint2 *list = reinterpret_cast<const uint2 *>(a.lists) + static_cast<size_t>(a.warpRowStart[warpGlobal]) * 32 + lane;
-      const double xi = active ? a.x[i] : 0., yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
-      const int ti = (MIX && active) ? a.type[i] : 0;
-      const unsigned sentinel = static_cast<unsigned>(nP);
-      const unsigned sent2 = sentinel | (sentinel << 16);
-      uint2 cur = __ldg(list);
-      for (int r = 0; r < rows; ++r) {
-        uint2 nxt = make_uint2(sent2, sent2);
-        if (r + 1 < rows) nxt = __ldg(list + static_cast<size_t>(r + 1) * 32);
-        if (!active) cur = make_uint2(sent2, sent2);  // particle deleted after the list build: no interactions
-        prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.x & 0xFFFFu, sentinel, acc);
-        prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.x >> 16, sentinel, acc);
-        prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.y & 0xFFFFu, sentinel, acc);
-        prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.y >> 16, sentinel, acc);
-        cur = nxt;
-      }
-      if (active) {
-        a.fx[i] += acc.fx;
-        a.fy[i] += acc.fy;
-        a.fz[i] += acc.fz;
-      }
+  if (rows > 0) {
+    const int64_t i = static_cast<int64_t>(first) + lane;
+    const bool active = lane < a.chunkNum[warpGlobal] && a.own[i] == APB_OWN_OWNED;
+    const double xi = active ? a.x[i] : 0., yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
+    const int ti = (MIX && active) ? a.type[i] : 0;
+    for (int r = 0; r < rows; ++r) {
+      uint2 nn = make_uint2(sent2, sent2);
+      if (r + 2 < rows) nn = __ldg(list + static_cast<size_t>(r + 2) * 32);
+      if (!active) cur = make_uint2(sent2, sent2);  // particle deleted after the list build: no interactions
+      prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.x & 0xFFFFu, sentinel, acc);
+      prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.x >> 16, sentinel, acc);
+      prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.y & 0xFFFFu, sentinel, acc);
+      prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.y >> 16, sentinel, acc);
+      cur = nxt;
+      nxt = nn;
+    }
+    if (active) {
+      a.fx[i] += acc.fx;
+      a.fy[i] += acc.fy;
+      a.fz[i] += acc.fz;
     }
   }
   if (STATS) {
@@ -459,9 +491,8 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   a.M = h->cfg.cluster_size;
   a.logM = 0;
   while ((1 << a.logM) < a.M) ++a.logM;
-  a.tileFirstSlot = static_cast<const int *>(h->prTileFirst.p);
-  a.tileNumSlots = static_cast<const int *>(h->prTileNum.p);
-  a.tileWarpStart = static_cast<const int *>(h->prTileWarp.p);
+  a.chunkFirst = static_cast<const int *>(h->prTileFirst.p);
+  a.chunkNum = static_cast<const int *>(h->prTileNum.p);
   a.x = h->col[APB_COL_X];
   a.y = h->col[APB_COL_Y];
   a.z = h->col[APB_COL_Z];
