@@ -574,6 +574,7 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   APB_CUDA(cudaMemcpyAsync(&total, scratchTotals(h), 8, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaMemcpyAsync(&maxCount, scratchMax(h), 4, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
+  h->vclMaxTowerCount = maxCount;
   APB_CHECK(apbEnsure(h, h->perm, sizeof(int) * std::max<int64_t>(total, 1)));
   APB_CHECK(apbEnsure(h, h->slotCell, sizeof(int) * std::max<int64_t>(total, 1)));
   int *perm = static_cast<int *>(h->perm.p);
@@ -659,6 +660,7 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   h->numCells = nt;
   h->structureValid = true;
   h->builtNewton3 = newton3 ? 1 : 0;
+  h->ownDirty = false;
   h->prunedValid = false;
   h->countsValid = false;
   return APB_OK;

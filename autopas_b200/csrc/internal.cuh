@@ -74,6 +74,7 @@ struct apb_handle_s {
   // ---- structure ----
   bool structureValid = false;  // cells / towers+lists match the storage order
   int builtNewton3 = -1;        // VCL lists: which newton3 mode they were built for
+  bool ownDirty = false;        // ownership column modified since the structure was built (deleted particles)
   LCGeom lc{};
   VCLGeom vcl{};
   int64_t numCells = 0;  // cells or towers
@@ -93,9 +94,12 @@ struct apb_handle_s {
   bool prunedValid = false;
   int prunedTiles = 0;
   int prunedMaxStaged = 0;  // clusters
+  int prunedMaxCompact = 0; // particles staged by the force kernel (largest tile)
+  int vclMaxTowerCount = 0; // particles of the fullest tower (set by the VCL rebuild)
   long long prunedRows = 0; // list rows of 32 entries
   int prunedWarps = 0;
   DevBuf prNumStaged, prStagedStart, prStaged, prWarpLen, prWarpStart, prLists, prTileFirst, prTileNum, prTileWarp;
+  DevBuf prMasks, prUsed, prCbase, prNumCompact, prCompactSlot;
 
   // ---- reductions / results ----
   DevBuf partials;

@@ -14,7 +14,7 @@
 // particles interact with is small. That union is staged once in shared memory (coalesced loads), and each lane walks
 // its private list of 16-bit indices into the staged tile. Lists are stored per warp in rows of 32 lanes x 4 entries
 // (one 8-byte load per lane per 4 pairs, 256 contiguous bytes per warp); rows are prefetched two ahead. The pair kernel
-// is branch-free fp64; there are no atomics. Padding entries point at a sentinel slot parked at 1e300, which fails the
+// is branch-free fp64; there are no atomics. Padding entries point at a sentinel slot parked at 1e100, which fails the
 // cutoff test.
 #include <algorithm>
 
@@ -126,69 +126,274 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedStage(PrunedArgs a, int *__res
   }
 }
 
-// ---- per-particle lists ----------------------------------------------------------------------------------------------
-// One CTA per tile, thread (warp w, lane l) <-> slot l of chunk w. FILL = false: per-warp maximum list length in rows
-// of 4 entries. FILL = true: write the lists; entry k of lane l lives at row (k / 4): rowBase + l * 4 + (k % 4).
-template <bool FILL>
-__global__ void __launch_bounds__(PR_TILE) kPrunedLists(PrunedArgs a, const int *__restrict__ stagedStart,
-                                                        const int *__restrict__ staged, int *__restrict__ warpRows,
-                                                        const int *__restrict__ warpRowStart,
-                                                        unsigned short *__restrict__ lists) {
-  extern __shared__ int stg[];  // staged cluster ids of this tile (sorted)
+// ---- tile table ----------------------------------------------------------------------------------------------------
+// Tile (bx, by, zc) = towers (2bx..2bx+1, 2by..2by+1) x 32-slot chunks (2zc, 2zc+1) of each: a compact brick of up to
+// 8 warp chunks. Towers are contiguous, z-sorted slot ranges, so chunk k of tower t is slots [start[t] + 32k, +32).
+__global__ void kPrunedTiles(int numTiles, int nbx, int nzc, int nx, int ny, const int *__restrict__ towerStart,
+                             int *__restrict__ chunkFirst, int *__restrict__ chunkNum) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= numTiles * PR_WARPS) return;
+  const int tile = g / PR_WARPS, w = g % PR_WARPS;
+  const int zc = tile % nzc, b = tile / nzc;
+  const int bx = b % nbx, by = b / nbx;
+  const int tx = 2 * bx + ((w >> 1) & 1), ty = 2 * by + (w >> 2), k = 2 * zc + (w & 1);
+  int first = -1, num = 0;
+  if (tx < nx && ty < ny) {
+    const int t = tx + ty * nx;
+    const int s0 = towerStart[t], slots = towerStart[t + 1] - s0;
+    if (k * 32 < slots) {
+      first = s0 + k * 32;
+      num = min(32, slots - k * 32);
+    }
+  }
+  chunkFirst[g] = first;
+  chunkNum[g] = num;
+}
+
+// ---- partner masks -------------------------------------------------------------------------------------------------
+// One CTA per tile, thread (warp w, lane l) <-> slot l of chunk w. For every owned particle i of a non-halo cluster A and
+// every entry B of {A} U list(A): the M-bit mask of partners j in B with |ri - rj|^2 <= (cutoff + skin)^2, evaluated
+// in fp32 on tile-relative coordinates with a threshold widened by the worst-case rounding error, i.e. a (very slightly)
+// conservative superset of the fp64 decision: FP32 issues at twice the FP64 rate and the test is the hot loop of the
+// rebuild. The force kernel re-tests every pair exactly in fp64 against the cutoff, so forces do not depend on this.
+// Masks go to masks[(nbrStart[A] + A + e) * M + (i % M)], e = 0 for A itself. Also produced: rows per warp (list length
+// in rows of 4 entries), and per staged cluster the mask of particles referenced by any list of the tile together with
+// its exclusive prefix (compact index base): the force kernel stages only referenced particles.
+struct MaskOut {
+  unsigned *masks;
+  int *warpRows;
+  unsigned *used;   // [totalStaged]
+  int *cbase;       // [totalStaged]
+  int *numCompact;  // [numTiles]
+  int *maxCompact;
+};
+
+__device__ __forceinline__ int prLowerBound(const int *stg, int nS, int B) {
+  int lo = 0, hi = nS;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (stg[mid] < B) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <bool UNIFORM>
+__global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int *__restrict__ stagedStart,
+                                                        const int *__restrict__ staged, MaskOut o) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  __shared__ float sRed[PR_WARPS];
+  __shared__ int sScan[PR_TILE];
   const int tile = blockIdx.x;
   const int g0 = stagedStart[tile], nS = stagedStart[tile + 1] - g0;
-  for (int t = threadIdx.x; t < nS; t += PR_TILE) stg[t] = staged[g0 + t];
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warpGlobal = tile * PR_WARPS + warp;
-  const int first = a.chunkFirst[warpGlobal], num = a.chunkNum[warpGlobal];
-  if (first < 0) {  // warp without a chunk (whole warp)
-    if (!FILL && lane == 0) warpRows[warpGlobal] = 0;
+  if (nS == 0) {
+    if (lane == 0) o.warpRows[warpGlobal] = 0;
+    if (threadIdx.x == 0) o.numCompact[tile] = 0;
     return;
   }
-  const int64_t i = static_cast<int64_t>(first) + lane;
-  const unsigned short sentinel = static_cast<unsigned short>(nS * a.M);
-  int cnt = 0;
-  unsigned short *out = nullptr;
-  int rows = 0;
-  if (FILL) {
-    rows = warpRows[warpGlobal];
-    out = lists + static_cast<size_t>(warpRowStart[warpGlobal]) * 128 + lane * 4;
+  const int nP = nS << a.logM;
+  float4 *rel = reinterpret_cast<float4 *>(smemRaw);
+  int *stg = reinterpret_cast<int *>(rel + nP);
+  unsigned *used = reinterpret_cast<unsigned *>(stg + nS);
+  for (int t = threadIdx.x; t < nS; t += PR_TILE) {
+    stg[t] = staged[g0 + t];
+    used[t] = 0u;
   }
-  if (lane < num && nS > 0) {
-    const int ownI = a.own[i];
-    const int A = static_cast<int>(i >> a.logM);
+  __syncthreads();
+  // tile-relative fp32 coordinates; origin = first staged particle (same address for all threads: broadcast)
+  const int64_t s00 = static_cast<int64_t>(stg[0]) << a.logM;
+  const double ox = a.x[s00], oy = a.y[s00], oz = a.z[s00];
+  const int mask = a.M - 1;
+  float ext = 0.f;
+  for (int e = threadIdx.x; e < nP; e += PR_TILE) {
+    const int64_t slot = (static_cast<int64_t>(stg[e >> a.logM]) << a.logM) + (e & mask);
+    float4 r;
+    if (a.own[slot] == APB_OWN_DUMMY) {
+      r = make_float4(1e30f, 0.f, 0.f, 0.f);  // padding dummies are nobody's partner (dr2 overflows to +inf)
+    } else {
+      r = make_float4(static_cast<float>(a.x[slot] - ox), static_cast<float>(a.y[slot] - oy),
+                      static_cast<float>(a.z[slot] - oz), 0.f);
+      ext = fmaxf(ext, fmaxf(fabsf(r.x), fmaxf(fabsf(r.y), fabsf(r.z))));
+    }
+    rel[e] = r;
+  }
+  for (int s = 16; s > 0; s >>= 1) ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, s));
+  if (lane == 0) sRed[warp] = ext;
+  __syncthreads();
+  ext = sRed[0];
+#pragma unroll
+  for (int w = 1; w < PR_WARPS; ++w) ext = fmaxf(ext, sRed[w]);
+  // error budget of the fp32 test: coordinates are rounded to fp32 (<= ext 2^-24 each), the differences and the sum of
+  // squares add a few ulp: |dr2_f32 - dr2| <= 2 sqrt(3) il (3 ext 2^-24) + il^2 2^-22  ~  6.2e-7 il ext + 2.4e-7 il^2.
+  // The threshold below carries more than twice that.
+  const double il = sqrt(a.il2);
+  const float thr = __double2float_ru(a.il2 * (1.0 + 1e-6) + 1.5e-6 * il * static_cast<double>(ext));
+  const float thrBox = thr * 1.00001f;
+
+  const int first = a.chunkFirst[warpGlobal], num = a.chunkNum[warpGlobal];
+  int cnt = 0;
+  if (first >= 0) {
+    const int64_t i = static_cast<int64_t>(first) + lane;
+    const bool laneIn = lane < num;
+    const int A = static_cast<int>((laneIn ? i : static_cast<int64_t>(first)) >> a.logM);
     // forces on halo particles are never used and carry no weight in the globals: they get no list
-    if (ownI == APB_OWN_OWNED && !a.clIsHalo[A]) {
-      const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+    const bool active = laneIn && a.own[i] == APB_OWN_OWNED && !a.clIsHalo[A];
+    if (UNIFORM) {
+      // M == 32: the warp is one cluster, all lanes walk the same entries and test the same partner (smem broadcast)
+      if (!a.clIsHalo[A]) {
+        const int loA = prLowerBound(stg, nS, A);
+        const float4 ri = rel[(loA << 5) + lane];
+        // fp32 bounding box of the active particles of A
+        float bx0 = active ? ri.x : 3e38f, bx1 = active ? ri.x : -3e38f;
+        float by0 = active ? ri.y : 3e38f, by1 = active ? ri.y : -3e38f;
+        float bz0 = active ? ri.z : 3e38f, bz1 = active ? ri.z : -3e38f;
+        for (int s = 16; s > 0; s >>= 1) {
+          bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, s));
+          bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, s));
+          by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, s));
+          by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, s));
+          bz0 = fminf(bz0, __shfl_xor_sync(0xffffffffu, bz0, s));
+          bz1 = fmaxf(bz1, __shfl_xor_sync(0xffffffffu, bz1, s));
+        }
+        const int e0 = a.nbrStart[A], e1 = a.nbrStart[A + 1];
+        unsigned *mrow = o.masks + (static_cast<size_t>(e0) + A) * 32 + lane;
+        for (int e = e0 - 1; e < e1; ++e, mrow += 32) {
+          const int B = e < e0 ? A : a.nbrList[e];
+          const int lo = prLowerBound(stg, nS, B);
+          const float4 *rb = rel + (lo << 5);
+          // candidate partners: lane k tests particle k of B against the box of A
+          const float4 pk = rb[lane];
+          const float gx = fmaxf(0.f, fmaxf(bx0 - pk.x, pk.x - bx1)), gy = fmaxf(0.f, fmaxf(by0 - pk.y, pk.y - by1)),
+                      gz = fmaxf(0.f, fmaxf(bz0 - pk.z, pk.z - bz1));
+          unsigned cand = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gy, gy, gx * gx)) <= thrBox);
+          unsigned m = 0u;
+          while (cand) {
+            const int k = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float4 pj = rb[k];
+            const float dx = ri.x - pj.x, dy = ri.y - pj.y, dz = ri.z - pj.z;
+            if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) m |= 1u << k;
+          }
+          if (e < e0) m &= ~(1u << lane);
+          if (!active) m = 0u;
+          *mrow = m;
+          cnt += __popc(m);
+          const unsigned wm = __reduce_or_sync(0xffffffffu, m);
+          if (lane == 0 && wm) atomicOr(&used[lo], wm);
+        }
+      }
+    } else if (active) {
+      const int loA = prLowerBound(stg, nS, A);
+      const int li = static_cast<int>(i) & mask;
+      const float4 ri = rel[(loA << a.logM) + li];
       const int e0 = a.nbrStart[A], e1 = a.nbrStart[A + 1];
       for (int e = e0 - 1; e < e1; ++e) {
         const int B = e < e0 ? A : a.nbrList[e];
-        int lo = 0, hi = nS;  // lower_bound(B)
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (stg[mid] < B) lo = mid + 1; else hi = mid;
-        }
-        const int64_t sB = static_cast<int64_t>(B) << a.logM;
+        const int lo = prLowerBound(stg, nS, B);
+        const float4 *rb = rel + (lo << a.logM);
+        unsigned m = 0u;
         for (int k = 0; k < a.M; ++k) {
-          const int64_t j = sB + k;
-          if (j == i || a.own[j] == APB_OWN_DUMMY) continue;
-          const double dr2 = ljDist2(xi - a.x[j], yi - a.y[j], zi - a.z[j]);
-          if (dr2 <= a.il2) {
-            if (FILL) out[static_cast<size_t>(cnt >> 2) * 128 + (cnt & 3)] = static_cast<unsigned short>(lo * a.M + k);
-            ++cnt;
-          }
+          const float4 pj = rb[k];
+          const float dx = ri.x - pj.x, dy = ri.y - pj.y, dz = ri.z - pj.z;
+          if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) m |= 1u << k;
         }
+        if (e < e0) m &= ~(1u << li);
+        o.masks[(static_cast<size_t>(e) + 1 + A) * a.M + li] = m;
+        cnt += __popc(m);
+        if (m) atomicOr(&used[lo], m);
       }
     }
   }
-  if (!FILL) {
+  {
     int m = (cnt + 3) >> 2;
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) warpRows[warpGlobal] = m;
-  } else {
-    for (int k = cnt; k < rows * 4; ++k) out[static_cast<size_t>(k >> 2) * 128 + (k & 3)] = sentinel;
+    for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if (lane == 0) o.warpRows[warpGlobal] = m;
   }
+  __syncthreads();
+  // compact index base per staged cluster = exclusive prefix of popc(used) (block scan over per-thread chunks)
+  const int chunk = (nS + PR_TILE - 1) / PR_TILE;
+  const int b = min(static_cast<int>(threadIdx.x) * chunk, nS), e = min(b + chunk, nS);
+  int c = 0;
+  for (int t = b; t < e; ++t) c += __popc(used[t]);
+  sScan[threadIdx.x] = c;
+  __syncthreads();
+  for (int s = 1; s < PR_TILE; s <<= 1) {
+    const int v = threadIdx.x >= s ? sScan[threadIdx.x - s] : 0;
+    __syncthreads();
+    sScan[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = sScan[threadIdx.x] - c;
+  for (int t = b; t < e; ++t) {
+    o.used[g0 + t] = used[t];
+    o.cbase[g0 + t] = run;
+    run += __popc(used[t]);
+  }
+  if (threadIdx.x == PR_TILE - 1) {
+    o.numCompact[tile] = sScan[PR_TILE - 1];
+    atomicMax(o.maxCompact, sScan[PR_TILE - 1]);
+  }
+}
+
+// ---- lists ---------------------------------------------------------------------------------------------------------
+// Expands the masks into per-lane lists of 16-bit compact indices: entry k of lane l lives in row k / 4 at
+// rowBase + l * 4 + (k % 4). Also writes the tile's compact slot table (which slot each compact index stages).
+template <bool UNIFORM>
+__global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *__restrict__ stagedStart,
+                                                       const int *__restrict__ staged, MaskOut o,
+                                                       const int *__restrict__ warpRowStart,
+                                                       unsigned short *__restrict__ lists, int *__restrict__ compactSlot) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int tile = blockIdx.x;
+  const int g0 = stagedStart[tile], nS = stagedStart[tile + 1] - g0;
+  if (nS == 0) return;
+  int *stg = reinterpret_cast<int *>(smemRaw);
+  unsigned *used = reinterpret_cast<unsigned *>(stg + nS);
+  int *cbase = reinterpret_cast<int *>(used + nS);
+  for (int t = threadIdx.x; t < nS; t += PR_TILE) {
+    stg[t] = staged[g0 + t];
+    used[t] = o.used[g0 + t];
+    cbase[t] = o.cbase[g0 + t];
+  }
+  __syncthreads();
+  const int mask = a.M - 1;
+  int *cs = compactSlot + (static_cast<size_t>(g0) << a.logM);
+  for (int e = threadIdx.x; e < (nS << a.logM); e += PR_TILE) {
+    const int s = e >> a.logM, k = e & mask;
+    const unsigned u = used[s];
+    if ((u >> k) & 1u) cs[cbase[s] + __popc(u & ((1u << k) - 1u))] = (stg[s] << a.logM) + k;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warpGlobal = tile * PR_WARPS + warp;
+  const int first = a.chunkFirst[warpGlobal], num = a.chunkNum[warpGlobal];
+  const int rows = o.warpRows[warpGlobal];
+  if (first < 0 || rows == 0) return;
+  const unsigned short sentinel = static_cast<unsigned short>(o.numCompact[tile]);
+  unsigned short *out = lists + static_cast<size_t>(warpRowStart[warpGlobal]) * 128 + lane * 4;
+  int cnt = 0;
+  const int64_t i = static_cast<int64_t>(first) + lane;
+  const bool laneIn = lane < num;
+  const int A = static_cast<int>((laneIn ? i : static_cast<int64_t>(first)) >> a.logM);
+  const bool active = laneIn && a.own[i] == APB_OWN_OWNED && !a.clIsHalo[A];
+  if (UNIFORM ? !a.clIsHalo[A] : active) {
+    const int li = static_cast<int>(i) & mask;
+    const int e0 = a.nbrStart[A], e1 = a.nbrStart[A + 1];
+    for (int e = e0 - 1; e < e1; ++e) {
+      const int B = e < e0 ? A : a.nbrList[e];
+      const int lo = prLowerBound(stg, nS, B);
+      unsigned m = (UNIFORM || active) ? o.masks[(static_cast<size_t>(e) + 1 + A) * a.M + li] : 0u;
+      const unsigned u = used[lo];
+      const int cb = cbase[lo];
+      while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        out[static_cast<size_t>(cnt >> 2) * 128 + (cnt & 3)] = static_cast<unsigned short>(cb + __popc(u & ((1u << k) - 1u)));
+        ++cnt;
+      }
+    }
+  }
+  for (int k = cnt; k < rows * 4; ++k) out[static_cast<size_t>(k >> 2) * 128 + (k & 3)] = sentinel;
 }
 
 int apbBuildPruned(apb_handle h) {
@@ -197,63 +402,33 @@ int apbBuildPruned(apb_handle h) {
   const int M = h->cfg.cluster_size;
   int logM = 0;
   while ((1 << logM) < M) ++logM;
+  if ((1 << logM) != M || M > 32)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned needs a power-of-two cluster size <= 32");
   const int64_t n = h->nslots;
   h->prunedTiles = 0;
   h->prunedMaxStaged = 0;
+  h->prunedMaxCompact = 0;
   if (n == 0) {
     h->prunedValid = true;
     return APB_OK;
   }
-  // tiles: bricks of 2 x 2 towers x 2 consecutive 32-slot chunks (towers are contiguous slot ranges, z sorted)
-  const int64_t nt = h->vcl.numTowers;
+  // tiles: bricks of 2 x 2 towers x 2 consecutive 32-slot chunks
   const int nx = h->vcl.towersPerDim[0], ny = h->vcl.towersPerDim[1];
-  std::vector<int> towerStart(nt + 1);
-  APB_CUDA(cudaMemcpy(towerStart.data(), h->start.p, sizeof(int) * (nt + 1), cudaMemcpyDeviceToHost));
-  std::vector<int> cFirst, cNum;
-  for (int by = 0; by < ny; by += 2) {
-    for (int bx = 0; bx < nx; bx += 2) {
-      int towers[4], ntw = 0, maxChunks = 0;
-      for (int dy = 0; dy < 2; ++dy)
-        for (int dx = 0; dx < 2; ++dx) {
-          if (bx + dx >= nx || by + dy >= ny) continue;
-          const int t = (bx + dx) + (by + dy) * nx;
-          towers[ntw++] = t;
-          maxChunks = std::max(maxChunks, (towerStart[t + 1] - towerStart[t] + 31) / 32);
-        }
-      for (int zc = 0; zc < maxChunks; zc += 2) {
-        int used = 0;
-        int first[PR_WARPS], num[PR_WARPS];
-        for (int q = 0; q < ntw; ++q) {
-          const int t = towers[q];
-          const int slots = towerStart[t + 1] - towerStart[t];
-          for (int k = zc; k < zc + 2; ++k) {
-            if (k * 32 >= slots) continue;
-            first[used] = towerStart[t] + k * 32;
-            num[used] = std::min(32, slots - k * 32);
-            ++used;
-          }
-        }
-        if (used == 0) continue;
-        for (int w = 0; w < PR_WARPS; ++w) {
-          cFirst.push_back(w < used ? first[w] : -1);
-          cNum.push_back(w < used ? num[w] : 0);
-        }
-      }
-    }
-  }
-  const int numTiles = static_cast<int>(cFirst.size() / PR_WARPS);
+  const int nbx = (nx + 1) / 2, nby = (ny + 1) / 2;
+  const int maxSlots = (h->vclMaxTowerCount + M - 1) / M * M;
+  const int nzc = std::max(1, ((maxSlots + 31) / 32 + 1) / 2);
+  const int64_t numTiles64 = static_cast<int64_t>(nbx) * nby * nzc;
+  if (numTiles64 * PR_WARPS > 0x7fffffffLL) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: too many tiles");
+  const int numTiles = static_cast<int>(numTiles64);
   const int numWarps = numTiles * PR_WARPS;
   h->prunedTiles = numTiles;
   h->prunedWarps = numWarps;
-  if (numTiles == 0) {
-    h->prunedValid = true;
-    return APB_OK;
-  }
   APB_CHECK(apbEnsure(h, h->prTileFirst, sizeof(int) * numWarps));
   APB_CHECK(apbEnsure(h, h->prTileNum, sizeof(int) * numWarps));
-  APB_CUDA(cudaMemcpyAsync(h->prTileFirst.p, cFirst.data(), sizeof(int) * numWarps, cudaMemcpyHostToDevice, h->stream));
-  APB_CUDA(cudaMemcpyAsync(h->prTileNum.p, cNum.data(), sizeof(int) * numWarps, cudaMemcpyHostToDevice, h->stream));
-  APB_CUDA(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
+  ++h->launchCount, kPrunedTiles<<<apbDivUp(numWarps, 256), 256, 0, h->stream>>>(
+      numTiles, nbx, nzc, nx, ny, static_cast<const int *>(h->start.p), static_cast<int *>(h->prTileFirst.p),
+      static_cast<int *>(h->prTileNum.p));
+  APB_CUDA(cudaGetLastError());
   PrunedArgs a;
   a.M = M;
   a.logM = logM;
@@ -272,18 +447,20 @@ int apbBuildPruned(apb_handle h) {
   APB_CHECK(apbEnsure(h, h->prStagedStart, sizeof(int) * (numTiles + 1)));
   APB_CHECK(apbEnsure(h, h->prWarpLen, sizeof(int) * (numWarps + 1)));
   APB_CHECK(apbEnsure(h, h->prWarpStart, sizeof(int) * (numWarps + 1)));
+  APB_CHECK(apbEnsure(h, h->prNumCompact, sizeof(int) * (numTiles + 1)));
   int *numStaged = static_cast<int *>(h->prNumStaged.p), *stagedStart = static_cast<int *>(h->prStagedStart.p);
   int *warpRows = static_cast<int *>(h->prWarpLen.p), *warpStart = static_cast<int *>(h->prWarpStart.p);
   char *scratch = static_cast<char *>(h->result.p) + sizeof(apb_traversal_result);
   long long *totals = reinterpret_cast<long long *>(scratch);
   int *maxStagedDev = reinterpret_cast<int *>(scratch + 32), *overflowDev = reinterpret_cast<int *>(scratch + 36);
-  APB_CUDA(cudaMemsetAsync(scratch + 32, 0, 8, h->stream));
+  int *maxCompactDev = reinterpret_cast<int *>(scratch + 40);
+  APB_CUDA(cudaMemsetAsync(scratch + 32, 0, 12, h->stream));
   APB_CUDA(cudaMemsetAsync(numStaged, 0, sizeof(int) * (numTiles + 1), h->stream));
   ++h->launchCount, kPrunedStage<false><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, nullptr, nullptr, maxStagedDev, overflowDev);
   APB_CUDA(cudaGetLastError());
   APB_CHECK(apbExclusiveScan(h, numStaged, stagedStart, numTiles + 1, totals));
   long long totalStaged = 0;
-  int hostMisc[2] = {0, 0};
+  int hostMisc[3] = {0, 0, 0};
   APB_CUDA(cudaMemcpyAsync(&totalStaged, totals, 8, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaMemcpyAsync(hostMisc, scratch + 32, 8, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
@@ -291,40 +468,70 @@ int apbBuildPruned(apb_handle h) {
                                                               std::to_string(PR_CAND_MAX) +
                                                               " cluster-list entries; use a larger cluster size");
   const int maxStaged = hostMisc[0];
-  if (static_cast<int64_t>(maxStaged) * M > 65534)
-    return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile exceeds 16-bit indices");
-  const size_t smemForce = (static_cast<size_t>(maxStaged) * M + 2) * 28;
-  if (smemForce > 200 * 1024)
+  const size_t smemMasks = static_cast<size_t>(maxStaged) * M * 16 + static_cast<size_t>(maxStaged) * 8 + 16;
+  if (smemMasks > 200 * 1024)
     return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile (" + std::to_string(maxStaged * M) +
                                                " particles) does not fit shared memory; use a larger cluster size");
+  if (totalStaged * M > 0x7fffffffLL) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged sets exceed 2^31 slots");
   h->prunedMaxStaged = maxStaged;
-  APB_CHECK(apbEnsure(h, h->prStaged, sizeof(int) * std::max<long long>(totalStaged, 1)));
+  const long long stagedAlloc = std::max<long long>(totalStaged, 1);
+  APB_CHECK(apbEnsure(h, h->prStaged, sizeof(int) * stagedAlloc));
+  APB_CHECK(apbEnsure(h, h->prUsed, sizeof(int) * stagedAlloc));
+  APB_CHECK(apbEnsure(h, h->prCbase, sizeof(int) * stagedAlloc));
+  APB_CHECK(apbEnsure(h, h->prCompactSlot, sizeof(int) * stagedAlloc * M));
+  APB_CHECK(apbEnsure(h, h->prMasks, sizeof(unsigned) * static_cast<size_t>(h->numPairs + h->numClusters + 1) * M));
   int *staged = static_cast<int *>(h->prStaged.p);
   ++h->launchCount, kPrunedStage<true><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, stagedStart, staged, maxStagedDev, overflowDev);
   APB_CUDA(cudaGetLastError());
-  const size_t smemLists = sizeof(int) * std::max(maxStaged, 1);
-  if (smemLists > 40 * 1024) {
-    APB_CUDA(cudaFuncSetAttribute(kPrunedLists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemLists)));
-    APB_CUDA(cudaFuncSetAttribute(kPrunedLists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemLists)));
+  MaskOut o;
+  o.masks = static_cast<unsigned *>(h->prMasks.p);
+  o.warpRows = warpRows;
+  o.used = static_cast<unsigned *>(h->prUsed.p);
+  o.cbase = static_cast<int *>(h->prCbase.p);
+  o.numCompact = static_cast<int *>(h->prNumCompact.p);
+  o.maxCompact = maxCompactDev;
+  const bool uniform = M == 32;
+  if (smemMasks > 40 * 1024) {
+    APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemMasks)));
+    APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemMasks)));
   }
   APB_CUDA(cudaMemsetAsync(warpRows, 0, sizeof(int) * (numWarps + 1), h->stream));
-  ++h->launchCount, kPrunedLists<false><<<numTiles, PR_TILE, smemLists, h->stream>>>(a, stagedStart, staged, warpRows, nullptr, nullptr);
+  if (uniform)
+    ++h->launchCount, kPrunedMasks<true><<<numTiles, PR_TILE, smemMasks, h->stream>>>(a, stagedStart, staged, o);
+  else
+    ++h->launchCount, kPrunedMasks<false><<<numTiles, PR_TILE, smemMasks, h->stream>>>(a, stagedStart, staged, o);
   APB_CUDA(cudaGetLastError());
   APB_CHECK(apbExclusiveScan(h, warpRows, warpStart, numWarps + 1, totals));
   long long totalRows = 0;
   APB_CUDA(cudaMemcpyAsync(&totalRows, totals, 8, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaMemcpyAsync(hostMisc + 2, maxCompactDev, 4, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
   if (totalRows > 0x7fffffffLL / 128) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: lists exceed 2^31 entries");
+  const int maxCompact = hostMisc[2];
+  if (maxCompact > 65534) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile exceeds 16-bit indices");
+  if ((static_cast<size_t>(maxCompact) + 2) * 28 > 200 * 1024)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile (" + std::to_string(maxCompact) +
+                                               " particles) does not fit shared memory");
+  h->prunedMaxCompact = maxCompact;
   h->prunedRows = totalRows;
   APB_CHECK(apbEnsure(h, h->prLists, sizeof(unsigned short) * 128 * std::max<long long>(totalRows, 1)));
-  ++h->launchCount, kPrunedLists<true><<<numTiles, PR_TILE, smemLists, h->stream>>>(a, stagedStart, staged, warpRows, warpStart,
-                                                                  static_cast<unsigned short *>(h->prLists.p));
+  const size_t smemFill = static_cast<size_t>(maxStaged) * 12 + 16;
+  if (smemFill > 40 * 1024) {
+    APB_CUDA(cudaFuncSetAttribute(kPrunedFill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemFill)));
+    APB_CUDA(cudaFuncSetAttribute(kPrunedFill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemFill)));
+  }
+  if (uniform)
+    ++h->launchCount, kPrunedFill<true><<<numTiles, PR_TILE, smemFill, h->stream>>>(
+        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p));
+  else
+    ++h->launchCount, kPrunedFill<false><<<numTiles, PR_TILE, smemFill, h->stream>>>(
+        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p));
   APB_CUDA(cudaGetLastError());
-  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   h->prunedValid = true;
   if (getenv("APB_DEBUG"))
-    fprintf(stderr, "[apb] pruned build: slots %lld tiles %d maxStagedClusters %d totalStaged %lld rows %lld (entries %lld)\n",
-            static_cast<long long>(n), numTiles, maxStaged, totalStaged, totalRows, totalRows * 128);
+    fprintf(stderr, "[apb] pruned build: slots %lld tiles %d maxStagedClusters %d maxCompact %d totalStaged %lld rows %lld (entries %lld)\n",
+            static_cast<long long>(n), numTiles, maxStaged, maxCompact, totalStaged, totalRows, totalRows * 128);
   return APB_OK;
 }
 
@@ -335,41 +542,51 @@ struct PrunedForceArgs {
   const double *x, *y, *z;
   double *fx, *fy, *fz;
   const int32_t *type, *own;
-  const int *stagedStart, *staged, *warpRows, *warpRowStart;
+  const int *stagedStart, *numCompact, *compactSlot, *warpRows, *warpRowStart;
   const unsigned short *lists;
   int stagedCapacity;  // particles incl. the sentinel slot, rounded up to even
+  int checkDead;       // ownership changed since the list build: re-read it while staging
   LJParams p;
   LJStats *partials;
 };
 
-// reciprocal by Newton-Raphson on the hardware seed: MUFU.RCP64H + 4 DFMA, relative error ~1 ulp, no slow path.
-// inf / NaN inputs (sentinel distances) give garbage that the caller discards with a select.
+// reciprocal from the hardware seed: MUFU.RCP64H (relative error ~2^-20, it reads the high word only) followed by one
+// cubic step  r' = r + r (e + e^2),  e = 1 - x r  (3 DFMA, error ~e^3 = 2^-60, i.e. rounding level), no slow path.
+// inf / NaN never occur for the sentinel distance (1e200), see below.
 __device__ __forceinline__ double prRcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
 }
+
+#define PR_FAR 1e100  // x coordinate of the sentinel / of deleted partners: dr2 = 1e200 is finite and fails every cutoff
 
 template <bool MIX, bool STATS>
 struct PairAcc {
   double fx = 0., fy = 0., fz = 0.;
-  double upot = 0., vx = 0., vy = 0., vz = 0.;
+  double su2 = 0., su = 0.;  // non-mixing: sum of lj6^2 and lj6 over hits, Upot6 = eps24 (su2 - su) + hits * shift6
+  double upot = 0.;          // mixing: sum of eps24 * lj6 * (lj6 - 1) + shift6
+  double vx = 0., vy = 0., vz = 0.;
   unsigned dist = 0, hits = 0;
 };
 
-// one pair, branch-free. Same formula as LJFunctor.h:146-159 with fac regrouped as
-// (lj6 * invdr2) * (48 eps * lj6 - 24 eps) = eps24 * (lj12 + lj12m6) * invdr2; differences are at the 1e-16 level.
+// One pair, branch-free; 20 FP64-pipe instructions without and 25 with globals.
+// Same quantities as LJFunctor.h:146-159 / :174-190 regrouped:
+//   dr2 from separately rounded squares (bit-identical to the reference's dr2, so the cutoff decision is too),
+//   lj6 forced to 0 for a miss, fac = (lj6 * invdr2) * (48 eps lj6 - 24 eps) = eps24 (lj12 + lj12m6) invdr2,
+//   virial_d = dr_d^2 * fac = dr_d * f_d, Upot6 = eps24 (lj12 - lj6) + shift6. Differences are at the 1e-16 level.
+// The cutoff test compares the bit patterns as integers (both operands are non-negative doubles), which keeps the
+// FP64 pipe free of the DSETP.
 template <bool MIX, bool STATS>
 __device__ __forceinline__ void prPair(const LJParams &p, double xi, double yi, double zi, int ti, const double *sx,
                                        const double *sy, const double *sz, const int *stype, unsigned idx,
                                        unsigned sentinel, PairAcc<MIX, STATS> &acc) {
   const double drx = xi - sx[idx], dry = yi - sy[idx], drz = zi - sz[idx];
-  const double dr2 = fma(drz, drz, fma(dry, dry, drx * drx));
-  const bool hit = dr2 <= p.cutoff2;
+  const double dx2 = __dmul_rn(drx, drx), dy2 = __dmul_rn(dry, dry), dz2 = __dmul_rn(drz, drz);
+  const double dr2 = __dadd_rn(__dadd_rn(dx2, dy2), dz2);
+  const bool hit = __double_as_longlong(dr2) <= __double_as_longlong(p.cutoff2);
   double e24, s2, shift6;
   if (MIX) {
     const double *m = p.mix + 3 * (static_cast<size_t>(ti) * p.T + stype[idx]);
@@ -379,32 +596,40 @@ __device__ __forceinline__ void prPair(const LJParams &p, double xi, double yi, 
   } else {
     e24 = p.eps24;
     s2 = p.sigma2;
-    shift6 = p.shift6;
+    shift6 = 0.;
   }
   const double inv = prRcp(dr2);
   const double lj2 = s2 * inv;
-  const double lj6 = lj2 * lj2 * lj2;
-  const double t = fma(e24 + e24, lj6, -e24);
-  double fac = (lj6 * inv) * t;
-  fac = hit ? fac : 0.;
-  const double fx = drx * fac, fy = dry * fac, fz = drz * fac;
-  acc.fx += fx;
-  acc.fy += fy;
-  acc.fz += fz;
+  double u = lj2 * lj2 * lj2;
+  u = hit ? u : 0.;
+  const double t = fma(e24 + e24, u, -e24);
+  const double fac = (u * inv) * t;
+  acc.fx = fma(drx, fac, acc.fx);
+  acc.fy = fma(dry, fac, acc.fy);
+  acc.fz = fma(drz, fac, acc.fz);
   if (STATS) {
-    // potentialEnergy6 = eps24 * (lj12 - lj6) + shift6 (LJFunctor.h:174); only owned particles carry lists: weight 1
-    const double upot6 = fma(e24 * lj6, lj6 - 1.0, shift6);
-    acc.upot += hit ? upot6 : 0.;
-    acc.vx = fma(drx, fx, acc.vx);
-    acc.vy = fma(dry, fy, acc.vy);
-    acc.vz = fma(drz, fz, acc.vz);
+    if (MIX) {
+      acc.upot = fma(e24 * u, u - 1.0, acc.upot);
+      acc.upot += hit ? shift6 : 0.;
+    } else {
+      acc.su2 = fma(u, u, acc.su2);
+      acc.su += u;
+    }
+    acc.vx = fma(dx2, fac, acc.vx);
+    acc.vy = fma(dy2, fac, acc.vy);
+    acc.vz = fma(dz2, fac, acc.vz);
     acc.dist += idx != sentinel;
     acc.hits += hit;
   }
 }
 
+__device__ __forceinline__ void prCpAsync8(void *smemDst, const void *gmemSrc) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmemSrc) : "memory");
+}
+
 template <bool MIX, bool STATS>
-__global__ void __launch_bounds__(PR_TILE) kLJPruned(PrunedForceArgs a) {
+__global__ void __launch_bounds__(PR_TILE, 4) kLJPruned(PrunedForceArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   double *sx = reinterpret_cast<double *>(smemRaw);
   double *sy = sx + a.stagedCapacity;
@@ -413,51 +638,74 @@ __global__ void __launch_bounds__(PR_TILE) kLJPruned(PrunedForceArgs a) {
   const int tile = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warpGlobal = tile * PR_WARPS + warp;
-  const int g0 = a.stagedStart[tile], nS = a.stagedStart[tile + 1] - g0;
-  const int nP = nS << a.logM;
-  const int mask = a.M - 1;
-  // issue the first list rows before staging so that their latency overlaps the staging loads
+  const int nP = a.numCompact[tile];
+  if (nP == 0) {  // empty tile (block-uniform)
+    if (STATS) {
+      LJStats st;
+      ljStatsZero(st);
+      if (threadIdx.x == 0) a.partials[blockIdx.x] = st;
+    }
+    return;
+  }
+  // stage the particles referenced by this tile's lists: asynchronous 8-byte copies (LDGSTS), all in flight at once,
+  // no register round trip
+  const int *cs = a.compactSlot + (static_cast<size_t>(a.stagedStart[tile]) << a.logM);
+  for (int e = threadIdx.x; e < nP; e += PR_TILE) {
+    const int slot = __ldg(cs + e);
+    prCpAsync8(sx + e, a.x + slot);
+    prCpAsync8(sy + e, a.y + slot);
+    prCpAsync8(sz + e, a.z + slot);
+    if (MIX) stype[e] = a.type[slot];
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // while the copies fly: this lane's particle and its first list rows
   const int first = a.chunkFirst[warpGlobal];
   const int rows = first >= 0 ? a.warpRows[warpGlobal] : 0;
   const unsigned sentinel = static_cast<unsigned>(nP);
   const unsigned sent2 = sentinel | (sentinel << 16);
   const uint2 *list = reinterpret_cast<const uint2 *>(a.lists) +
                       (rows > 0 ? static_cast<size_t>(a.warpRowStart[warpGlobal]) * 32 + lane : 0);
-  uint2 cur = make_uint2(sent2, sent2), nxt = cur;
-  if (rows > 0) cur = __ldg(list);
-  if (rows > 1) nxt = __ldg(list + 32);
-  for (int e = threadIdx.x; e < nP; e += PR_TILE) {
-    const int64_t slot = (static_cast<int64_t>(a.staged[g0 + (e >> a.logM)]) << a.logM) + (e & mask);
-    // particles deleted since the list build (ownership dummy) are moved out of reach
-    const bool dead = a.own[slot] == APB_OWN_DUMMY;
-    sx[e] = dead ? 1e300 : a.x[slot];
-    sy[e] = a.y[slot];
-    sz[e] = a.z[slot];
-    if (MIX) stype[e] = a.type[slot];
-  }
+  // list rows are prefetched four ahead (register ring): with few resident warps one row of pair math is shorter than
+  // an L2 / HBM round trip
+  const uint2 sentRow = make_uint2(sent2, sent2);
+  uint2 q0 = sentRow, q1 = sentRow, q2 = sentRow, q3 = sentRow;
+  if (rows > 0) q0 = __ldg(list);
+  if (rows > 1) q1 = __ldg(list + 32);
+  if (rows > 2) q2 = __ldg(list + 64);
+  if (rows > 3) q3 = __ldg(list + 96);
+  const int64_t i = static_cast<int64_t>(first >= 0 ? first : 0) + lane;
+  const bool active = rows > 0 && lane < a.chunkNum[warpGlobal] && a.own[i] == APB_OWN_OWNED;
+  const double xi = active ? a.x[i] : 0., yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
+  const int ti = (MIX && active) ? a.type[i] : 0;
   if (threadIdx.x == 0) {  // sentinel slot for padding entries
-    sx[nP] = 1e300;
+    sx[nP] = PR_FAR;
     sy[nP] = 0.;
     sz[nP] = 0.;
     if (MIX) stype[nP] = 0;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
+  if (a.checkDead) {
+    // ownership changed since the list build (particles deleted / marked dummy): move those partners out of reach
+    for (int e = threadIdx.x; e < nP; e += PR_TILE)
+      if (a.own[cs[e]] == APB_OWN_DUMMY) sx[e] = PR_FAR;
+    __syncthreads();
+  }
   PairAcc<MIX, STATS> acc;
   if (rows > 0) {
-    const int64_t i = static_cast<int64_t>(first) + lane;
-    const bool active = lane < a.chunkNum[warpGlobal] && a.own[i] == APB_OWN_OWNED;
-    const double xi = active ? a.x[i] : 0., yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
-    const int ti = (MIX && active) ? a.type[i] : 0;
+    if (!active) q0 = q1 = q2 = q3 = sentRow;  // slot without an owned particle: no interactions
     for (int r = 0; r < rows; ++r) {
-      uint2 nn = make_uint2(sent2, sent2);
-      if (r + 2 < rows) nn = __ldg(list + static_cast<size_t>(r + 2) * 32);
-      if (!active) cur = make_uint2(sent2, sent2);  // particle deleted after the list build: no interactions
+      uint2 nn = sentRow;
+      if (active && r + 4 < rows) nn = __ldg(list + static_cast<size_t>(r + 4) * 32);
+      const uint2 cur = q0;
       prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.x & 0xFFFFu, sentinel, acc);
       prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.x >> 16, sentinel, acc);
       prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.y & 0xFFFFu, sentinel, acc);
       prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.y >> 16, sentinel, acc);
-      cur = nxt;
-      nxt = nn;
+      q0 = q1;
+      q1 = q2;
+      q2 = q3;
+      q3 = nn;
     }
     if (active) {
       a.fx[i] += acc.fx;
@@ -468,7 +716,8 @@ __global__ void __launch_bounds__(PR_TILE) kLJPruned(PrunedForceArgs a) {
   if (STATS) {
     LJStats st;
     ljStatsZero(st);
-    st.upot = acc.upot;
+    // potentialEnergy6 = eps24 * (lj12 - lj6) + shift6 (LJFunctor.h:174); only owned particles carry lists: weight 1
+    st.upot = MIX ? acc.upot : fma(a.p.eps24, acc.su2 - acc.su, static_cast<double>(acc.hits) * a.p.shift6);
     st.vir[0] = acc.vx;
     st.vir[1] = acc.vy;
     st.vir[2] = acc.vz;
@@ -502,11 +751,13 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   a.type = h->type;
   a.own = h->own;
   a.stagedStart = static_cast<const int *>(h->prStagedStart.p);
-  a.staged = static_cast<const int *>(h->prStaged.p);
+  a.numCompact = static_cast<const int *>(h->prNumCompact.p);
+  a.compactSlot = static_cast<const int *>(h->prCompactSlot.p);
   a.warpRows = static_cast<const int *>(h->prWarpLen.p);
   a.warpRowStart = static_cast<const int *>(h->prWarpStart.p);
   a.lists = static_cast<const unsigned short *>(h->prLists.p);
-  a.stagedCapacity = (h->prunedMaxStaged * a.M + 2) & ~1;
+  a.stagedCapacity = (h->prunedMaxCompact + 2) & ~1;
+  a.checkDead = h->ownDirty ? 1 : 0;
   a.p = p;
   a.partials = static_cast<LJStats *>(h->partials.p);
   const size_t smem = static_cast<size_t>(a.stagedCapacity) * (mix ? 28 : 24);
@@ -530,7 +781,7 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
       h->poisoned = true;
       return h->fail(APB_ERR_CUDA, std::string("kLJPruned launch failed: ") + cudaGetErrorString(e) + " (tiles " +
                                        std::to_string(numTiles) + ", dynamic smem " + std::to_string(smem) +
-                                       " B, staged clusters max " + std::to_string(h->prunedMaxStaged) + ")");
+                                       " B, staged particles max " + std::to_string(h->prunedMaxCompact) + ")");
     }
   }
   return apbFinishStats(h, numTiles, stats, f, out);

@@ -360,6 +360,7 @@ extern "C" int apb_delete_halo_particles(apb_handle h) {
     APB_CUDA(cudaStreamSynchronize(h->stream));
   }
   h->countsValid = false;
+  h->ownDirty = true;
   return APB_OK;
 }
 
@@ -543,6 +544,7 @@ extern "C" int apb_upload_ownership(apb_handle h, const int32_t *ownership) {
   APB_CUDA(cudaMemcpyAsync(h->own, ownership, sizeof(int32_t) * h->nslots, cudaMemcpyHostToDevice, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
   h->countsValid = false;
+  h->ownDirty = true;
   return APB_OK;
 }
 
@@ -799,6 +801,7 @@ extern "C" int apb_update_container(apb_handle h, int32_t keep, int64_t *out_num
     h->haloLinksValid = false;
   }
   h->countsValid = false;
+  h->ownDirty = true;
   if (out_num_leavers) *out_num_leavers = nl;
   return APB_OK;
 }
