@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libautopas_b200.so")
+LIB_PATH = os.environ.get("APB_LIB_PATH", os.path.join(_HERE, "libautopas_b200.so"))  # override: kernel experiments
 
 APB_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NOT_APPLICABLE, ERR_STATE, ERR_PARTICLE_OUTSIDE, ERR_NCCL, ERR_OOM = (

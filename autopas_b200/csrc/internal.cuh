@@ -97,6 +97,7 @@ struct apb_handle_s {
   int prunedMaxCompact = 0; // particles staged by the force kernel (largest tile)
   int vclMaxTowerCount = 0; // particles of the fullest tower (set by the VCL rebuild)
   long long prunedRows = 0; // list rows of 32 entries
+  unsigned long long prunedEntries = 0;  // real (non padding) list entries = distance evaluations per force call
   int prunedWarps = 0;
   DevBuf prNumStaged, prStagedStart, prStaged, prWarpLen, prWarpStart, prLists, prTileFirst, prTileNum, prTileWarp;
   DevBuf prMasks, prUsed, prCbase, prNumCompact, prCompactSlot;

@@ -21,8 +21,13 @@
 #include "internal.cuh"
 #include "lj_device.cuh"
 
-#define PR_WARPS 8
+#ifndef PR_WARPS
+#define PR_WARPS 8  // warp chunks per tile (8: 2 x 2 towers x 2 chunks, 4: 2 x 1 towers x 2 chunks)
+#endif
 #define PR_TILE (PR_WARPS * 32)
+#ifndef PR_MINBLOCKS
+#define PR_MINBLOCKS (32 / PR_WARPS)  // 32 resident warps per SM: 64 registers per thread
+#endif
 #define PR_CAND_MAX 8192  // candidate cluster ids gathered per tile before sort/unique
 
 struct PrunedArgs {
@@ -129,16 +134,18 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedStage(PrunedArgs a, int *__res
 // ---- tile table ----------------------------------------------------------------------------------------------------
 // Tile (bx, by, zc) = towers (2bx..2bx+1, 2by..2by+1) x 32-slot chunks (2zc, 2zc+1) of each: a compact brick of up to
 // 8 warp chunks. Towers are contiguous, z-sorted slot ranges, so chunk k of tower t is slots [start[t] + 32k, +32).
-__global__ void kPrunedTiles(int numTiles, int nbx, int nzc, int nx, int ny, const int *__restrict__ towerStart,
+__global__ void kPrunedTiles(int numTiles, int nbx, int nzc, int nx, int ny, int shift, const int *__restrict__ towerStart,
                              int *__restrict__ chunkFirst, int *__restrict__ chunkNum) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= numTiles * PR_WARPS) return;
   const int tile = g / PR_WARPS, w = g % PR_WARPS;
   const int zc = tile % nzc, b = tile / nzc;
   const int bx = b % nbx, by = b / nbx;
-  const int tx = 2 * bx + ((w >> 1) & 1), ty = 2 * by + (w >> 2), k = 2 * zc + (w & 1);
+  // `shift` aligns the 2 x 2 tower blocks with the first owned tower, so that halo towers (which carry no lists) do not
+  // share a tile - and a CTA's lifetime - with owned ones
+  const int tx = 2 * bx - shift + ((w >> 1) & 1), ty = PR_WARPS == 8 ? 2 * by - shift + (w >> 2) : by, k = 2 * zc + (w & 1);
   int first = -1, num = 0;
-  if (tx < nx && ty < ny) {
+  if (tx >= 0 && ty >= 0 && tx < nx && ty < ny) {
     const int t = tx + ty * nx;
     const int s0 = towerStart[t], slots = towerStart[t + 1] - s0;
     if (k * 32 < slots) {
@@ -165,7 +172,8 @@ struct MaskOut {
   unsigned *used;   // [totalStaged]
   int *cbase;       // [totalStaged]
   int *numCompact;  // [numTiles]
-  int *maxCompact;
+  int *maxCompact;  // [0] largest compact tile, [1] longest list in rows
+  unsigned long long *totalEntries;
 };
 
 __device__ __forceinline__ int prLowerBound(const int *stg, int nS, int B) {
@@ -308,7 +316,12 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
   {
     int m = (cnt + 3) >> 2;
     for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
-    if (lane == 0) o.warpRows[warpGlobal] = m;
+    if (lane == 0) {
+      o.warpRows[warpGlobal] = m;
+      if (m) atomicMax(o.maxCompact + 1, m);
+    }
+    const unsigned tot = __reduce_add_sync(0xffffffffu, static_cast<unsigned>(cnt));
+    if (lane == 0 && tot) atomicAdd(o.totalEntries, static_cast<unsigned long long>(tot));
   }
   __syncthreads();
   // compact index base per staged cluster = exclusive prefix of popc(used) (block scan over per-thread chunks)
@@ -343,7 +356,8 @@ template <bool UNIFORM>
 __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *__restrict__ stagedStart,
                                                        const int *__restrict__ staged, MaskOut o,
                                                        const int *__restrict__ warpRowStart,
-                                                       unsigned short *__restrict__ lists, int *__restrict__ compactSlot) {
+                                                       unsigned short *__restrict__ lists, int *__restrict__ compactSlot,
+                                                       int smemRowsPerWarp) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int tile = blockIdx.x;
   const int g0 = stagedStart[tile], nS = stagedStart[tile + 1] - g0;
@@ -369,31 +383,52 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   const int first = a.chunkFirst[warpGlobal], num = a.chunkNum[warpGlobal];
   const int rows = o.warpRows[warpGlobal];
   if (first < 0 || rows == 0) return;
-  const unsigned short sentinel = static_cast<unsigned short>(o.numCompact[tile]);
-  unsigned short *out = lists + static_cast<size_t>(warpRowStart[warpGlobal]) * 128 + lane * 4;
-  int cnt = 0;
+  // The warp's rows are assembled in shared memory (2-byte scattered writes) and copied out coalesced; directly in
+  // global memory only if a warp's rows exceed the shared-memory budget. Padding entries point at the sentinel slot of
+  // the lane's own bank class (16 sentinel slots follow the staged particles), so that padding causes no conflicts.
+  const int nC = o.numCompact[tile];
+  const int R = rows * 4, p = lane & 15;
+  unsigned short *gout = lists + static_cast<size_t>(warpRowStart[warpGlobal]) * 128;
+  const bool viaSmem = rows <= smemRowsPerWarp;
+  unsigned short *block = viaSmem ? reinterpret_cast<unsigned short *>(smemRaw + ((static_cast<size_t>(nS) * 12 + 15) & ~size_t(15))) +
+                                        static_cast<size_t>(warp) * smemRowsPerWarp * 128
+                                  : gout;
+  unsigned short *out = block + lane * 4;
   const int64_t i = static_cast<int64_t>(first) + lane;
   const bool laneIn = lane < num;
   const int A = static_cast<int>((laneIn ? i : static_cast<int64_t>(first)) >> a.logM);
   const bool active = laneIn && a.own[i] == APB_OWN_OWNED && !a.clIsHalo[A];
-  if (UNIFORM ? !a.clIsHalo[A] : active) {
-    const int li = static_cast<int>(i) & mask;
-    const int e0 = a.nbrStart[A], e1 = a.nbrStart[A + 1];
-    for (int e = e0 - 1; e < e1; ++e) {
-      const int B = e < e0 ? A : a.nbrList[e];
-      const int lo = prLowerBound(stg, nS, B);
-      unsigned m = (UNIFORM || active) ? o.masks[(static_cast<size_t>(e) + 1 + A) * a.M + li] : 0u;
-      const unsigned u = used[lo];
-      const int cb = cbase[lo];
-      while (m) {
-        const int k = __ffs(m) - 1;
-        m &= m - 1;
-        out[static_cast<size_t>(cnt >> 2) * 128 + (cnt & 3)] = static_cast<unsigned short>(cb + __popc(u & ((1u << k) - 1u)));
-        ++cnt;
-      }
+  const int li = static_cast<int>(i) & mask;
+  const int e0 = active ? a.nbrStart[A] : 0, e1 = active ? a.nbrStart[A + 1] : -1;
+  int cnt = 0;
+  // software pipelined: the next entry's cluster id and mask are loaded while the current one is expanded
+  int Bn = A;
+  unsigned mn = e1 >= e0 ? o.masks[(static_cast<size_t>(e0) + A) * a.M + li] : 0u;
+  for (int e = e0 - 1; e < e1; ++e) {
+    const int B = Bn;
+    unsigned m = mn;
+    if (e + 1 < e1) {
+      Bn = a.nbrList[e + 1];
+      mn = o.masks[(static_cast<size_t>(e) + 2 + A) * a.M + li];
+    }
+    const int lo = prLowerBound(stg, nS, B);
+    const unsigned u = used[lo];
+    const int cb = cbase[lo];
+    while (m) {
+      const int k = __ffs(m) - 1;
+      m &= m - 1;
+      out[static_cast<size_t>(cnt >> 2) * 128 + (cnt & 3)] = static_cast<unsigned short>((cb + __popc(u & ((1u << k) - 1u))) << 3);
+      ++cnt;
     }
   }
-  for (int k = cnt; k < rows * 4; ++k) out[static_cast<size_t>(k >> 2) * 128 + (k & 3)] = sentinel;
+  for (int t = cnt; t < R; ++t)
+    out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] = static_cast<unsigned short>((nC + ((p - nC) & 15)) << 3);
+  if (viaSmem) {
+    __syncwarp();
+    const uint4 *src = reinterpret_cast<const uint4 *>(block);
+    uint4 *dst = reinterpret_cast<uint4 *>(gout);
+    for (int q = lane; q < rows * 16; q += 32) dst[q] = src[q];
+  }
 }
 
 int apbBuildPruned(apb_handle h) {
@@ -414,7 +449,8 @@ int apbBuildPruned(apb_handle h) {
   }
   // tiles: bricks of 2 x 2 towers x 2 consecutive 32-slot chunks
   const int nx = h->vcl.towersPerDim[0], ny = h->vcl.towersPerDim[1];
-  const int nbx = (nx + 1) / 2, nby = (ny + 1) / 2;
+  const int shift = h->vcl.numTowersPerInteractionLength & 1;
+  const int nbx = (nx + shift + 1) / 2, nby = PR_WARPS == 8 ? (ny + shift + 1) / 2 : ny;
   const int maxSlots = (h->vclMaxTowerCount + M - 1) / M * M;
   const int nzc = std::max(1, ((maxSlots + 31) / 32 + 1) / 2);
   const int64_t numTiles64 = static_cast<int64_t>(nbx) * nby * nzc;
@@ -426,7 +462,7 @@ int apbBuildPruned(apb_handle h) {
   APB_CHECK(apbEnsure(h, h->prTileFirst, sizeof(int) * numWarps));
   APB_CHECK(apbEnsure(h, h->prTileNum, sizeof(int) * numWarps));
   ++h->launchCount, kPrunedTiles<<<apbDivUp(numWarps, 256), 256, 0, h->stream>>>(
-      numTiles, nbx, nzc, nx, ny, static_cast<const int *>(h->start.p), static_cast<int *>(h->prTileFirst.p),
+      numTiles, nbx, nzc, nx, ny, shift, static_cast<const int *>(h->start.p), static_cast<int *>(h->prTileFirst.p),
       static_cast<int *>(h->prTileNum.p));
   APB_CUDA(cudaGetLastError());
   PrunedArgs a;
@@ -454,13 +490,13 @@ int apbBuildPruned(apb_handle h) {
   long long *totals = reinterpret_cast<long long *>(scratch);
   int *maxStagedDev = reinterpret_cast<int *>(scratch + 32), *overflowDev = reinterpret_cast<int *>(scratch + 36);
   int *maxCompactDev = reinterpret_cast<int *>(scratch + 40);
-  APB_CUDA(cudaMemsetAsync(scratch + 32, 0, 12, h->stream));
+  APB_CUDA(cudaMemsetAsync(scratch + 32, 0, 24, h->stream));
   APB_CUDA(cudaMemsetAsync(numStaged, 0, sizeof(int) * (numTiles + 1), h->stream));
   ++h->launchCount, kPrunedStage<false><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, nullptr, nullptr, maxStagedDev, overflowDev);
   APB_CUDA(cudaGetLastError());
   APB_CHECK(apbExclusiveScan(h, numStaged, stagedStart, numTiles + 1, totals));
   long long totalStaged = 0;
-  int hostMisc[3] = {0, 0, 0};
+  int hostMisc[4] = {0, 0, 0, 0};
   APB_CUDA(cudaMemcpyAsync(&totalStaged, totals, 8, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaMemcpyAsync(hostMisc, scratch + 32, 8, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
@@ -490,6 +526,7 @@ int apbBuildPruned(apb_handle h) {
   o.cbase = static_cast<int *>(h->prCbase.p);
   o.numCompact = static_cast<int *>(h->prNumCompact.p);
   o.maxCompact = maxCompactDev;
+  o.totalEntries = reinterpret_cast<unsigned long long *>(scratch + 48);
   const bool uniform = M == 32;
   if (smemMasks > 40 * 1024) {
     APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemMasks)));
@@ -504,28 +541,35 @@ int apbBuildPruned(apb_handle h) {
   APB_CHECK(apbExclusiveScan(h, warpRows, warpStart, numWarps + 1, totals));
   long long totalRows = 0;
   APB_CUDA(cudaMemcpyAsync(&totalRows, totals, 8, cudaMemcpyDeviceToHost, h->stream));
-  APB_CUDA(cudaMemcpyAsync(hostMisc + 2, maxCompactDev, 4, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaMemcpyAsync(hostMisc + 2, maxCompactDev, 8, cudaMemcpyDeviceToHost, h->stream));  // + max rows
+  unsigned long long totalEntries = 0;
+  APB_CUDA(cudaMemcpyAsync(&totalEntries, scratch + 48, 8, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
   if (totalRows > 0x7fffffffLL / 128) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: lists exceed 2^31 entries");
   const int maxCompact = hostMisc[2];
-  if (maxCompact > 65534) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile exceeds 16-bit indices");
-  if ((static_cast<size_t>(maxCompact) + 2) * 28 > 200 * 1024)
+  if (maxCompact > 8000) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile exceeds 16-bit indices");
+  if ((static_cast<size_t>(maxCompact) + 18) * 28 > 200 * 1024)
     return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile (" + std::to_string(maxCompact) +
                                                " particles) does not fit shared memory");
   h->prunedMaxCompact = maxCompact;
   h->prunedRows = totalRows;
-  APB_CHECK(apbEnsure(h, h->prLists, sizeof(unsigned short) * 128 * std::max<long long>(totalRows, 1)));
-  const size_t smemFill = static_cast<size_t>(maxStaged) * 12 + 16;
+  h->prunedEntries = totalEntries;
+  APB_CHECK(apbEnsure(h, h->prLists, sizeof(unsigned short) * 128 * (totalRows + 8)));  // 8 rows of slack: unchecked prefetch
+  // per-warp list blocks in shared memory if the longest list fits (256 B per row)
+  const int maxRows = hostMisc[3];
+  const size_t smemFillBase = (static_cast<size_t>(maxStaged) * 12 + 15) & ~size_t(15);
+  const int smemRowsPerWarp = smemFillBase + static_cast<size_t>(PR_WARPS) * maxRows * 256 <= 150 * 1024 ? maxRows : 0;
+  const size_t smemFill = smemFillBase + static_cast<size_t>(PR_WARPS) * smemRowsPerWarp * 256 + 16;
   if (smemFill > 40 * 1024) {
     APB_CUDA(cudaFuncSetAttribute(kPrunedFill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemFill)));
     APB_CUDA(cudaFuncSetAttribute(kPrunedFill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemFill)));
   }
   if (uniform)
     ++h->launchCount, kPrunedFill<true><<<numTiles, PR_TILE, smemFill, h->stream>>>(
-        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p));
+        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp);
   else
     ++h->launchCount, kPrunedFill<false><<<numTiles, PR_TILE, smemFill, h->stream>>>(
-        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p));
+        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp);
   APB_CUDA(cudaGetLastError());
   if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   h->prunedValid = true;
@@ -544,8 +588,8 @@ struct PrunedForceArgs {
   const int32_t *type, *own;
   const int *stagedStart, *numCompact, *compactSlot, *warpRows, *warpRowStart;
   const unsigned short *lists;
-  int stagedCapacity;  // particles incl. the sentinel slot, rounded up to even
-  int checkDead;       // ownership changed since the list build: re-read it while staging
+  int stagedCapacity;  // particles incl. the 16 sentinel slots, rounded up to even
+  unsigned long long totalEntries;  // list entries written at build time = distance evaluations per call
   LJParams p;
   LJStats *partials;
 };
@@ -561,9 +605,9 @@ __device__ __forceinline__ double prRcp(double x) {
   return fma(r, t, r);
 }
 
-#define PR_FAR 1e100  // x coordinate of the sentinel / of deleted partners: dr2 = 1e200 is finite and fails every cutoff
+#define PR_FAR 1e100  // x coordinate of the sentinels / of deleted partners: dr2 ~ 1e200 is finite and fails every cutoff
 
-template <bool MIX, bool STATS>
+template <bool MIX, bool STATS, bool DEAD>
 struct PairAcc {
   double fx = 0., fy = 0., fz = 0.;
   double su2 = 0., su = 0.;  // non-mixing: sum of lj6^2 and lj6 over hits, Upot6 = eps24 (su2 - su) + hits * shift6
@@ -572,24 +616,26 @@ struct PairAcc {
   unsigned dist = 0, hits = 0;
 };
 
-// One pair, branch-free; 20 FP64-pipe instructions without and 25 with globals.
+// One pair; 20 FP64-pipe instructions without and 25 with globals, about a dozen others.
 // Same quantities as LJFunctor.h:146-159 / :174-190 regrouped:
 //   dr2 from separately rounded squares (bit-identical to the reference's dr2, so the cutoff decision is too),
-//   lj6 forced to 0 for a miss, fac = (lj6 * invdr2) * (48 eps lj6 - 24 eps) = eps24 (lj12 + lj12m6) invdr2,
+//   fac = (lj6 * invdr2) * (48 eps lj6 - 24 eps) = eps24 (lj12 + lj12m6) invdr2,
 //   virial_d = dr_d^2 * fac = dr_d * f_d, Upot6 = eps24 (lj12 - lj6) + shift6. Differences are at the 1e-16 level.
-// The cutoff test compares the bit patterns as integers (both operands are non-negative doubles), which keeps the
-// FP64 pipe free of the DSETP.
-template <bool MIX, bool STATS>
-__device__ __forceinline__ void prPair(const LJParams &p, double xi, double yi, double zi, int ti, const double *sx,
-                                       const double *sy, const double *sz, const int *stype, unsigned idx,
-                                       unsigned sentinel, PairAcc<MIX, STATS> &acc) {
-  const double drx = xi - sx[idx], dry = yi - sy[idx], drz = zi - sz[idx];
+// A miss skips the (predicated) accumulation instead of multiplying by a mask. The cutoff test compares the bit
+// patterns as integers (both operands are non-negative doubles), which keeps the DSETP off the FP64 pipe.
+// `e8` is the partner's index in the staged tile times 8; positions are staged as (x, y, z) triples.
+template <bool MIX, bool STATS, bool DEAD>
+__device__ __forceinline__ void prPair(const LJParams &p, double xi, double yi, double zi, int ti,
+                                       const unsigned char *sxyz, const int *stype, unsigned e8, unsigned sentinel8,
+                                       PairAcc<MIX, STATS, DEAD> &acc) {
+  const double *pj = reinterpret_cast<const double *>(sxyz + e8 * 3u);
+  const double drx = xi - pj[0], dry = yi - pj[1], drz = zi - pj[2];
   const double dx2 = __dmul_rn(drx, drx), dy2 = __dmul_rn(dry, dry), dz2 = __dmul_rn(drz, drz);
   const double dr2 = __dadd_rn(__dadd_rn(dx2, dy2), dz2);
   const bool hit = __double_as_longlong(dr2) <= __double_as_longlong(p.cutoff2);
   double e24, s2, shift6;
   if (MIX) {
-    const double *m = p.mix + 3 * (static_cast<size_t>(ti) * p.T + stype[idx]);
+    const double *m = p.mix + 3 * (static_cast<size_t>(ti) * p.T + stype[e8 >> 3]);
     e24 = __ldg(m);
     s2 = __ldg(m + 1);
     shift6 = p.applyShift ? __ldg(m + 2) : 0.;
@@ -600,26 +646,31 @@ __device__ __forceinline__ void prPair(const LJParams &p, double xi, double yi, 
   }
   const double inv = prRcp(dr2);
   const double lj2 = s2 * inv;
-  double u = lj2 * lj2 * lj2;
-  u = hit ? u : 0.;
+  const double u = lj2 * lj2 * lj2;
   const double t = fma(e24 + e24, u, -e24);
-  const double fac = (u * inv) * t;
-  acc.fx = fma(drx, fac, acc.fx);
-  acc.fy = fma(dry, fac, acc.fy);
-  acc.fz = fma(drz, fac, acc.fz);
-  if (STATS) {
-    if (MIX) {
-      acc.upot = fma(e24 * u, u - 1.0, acc.upot);
-      acc.upot += hit ? shift6 : 0.;
-    } else {
-      acc.su2 = fma(u, u, acc.su2);
-      acc.su += u;
+  double fac = (u * inv) * t;
+  double uu = u;
+  // keep the pair math unconditional (the four pairs of a row interleave and hide each other's FP64 latency); only the
+  // accumulation below is predicated
+  asm volatile("" : "+d"(fac), "+d"(uu));
+  if (STATS && DEAD) acc.dist += e8 < sentinel8;
+  if (hit) {
+    acc.fx = fma(drx, fac, acc.fx);
+    acc.fy = fma(dry, fac, acc.fy);
+    acc.fz = fma(drz, fac, acc.fz);
+    if (STATS) {
+      if (MIX) {
+        acc.upot = fma(e24 * uu, uu - 1.0, acc.upot);
+        acc.upot += shift6;
+      } else {
+        acc.su2 = fma(uu, uu, acc.su2);
+        acc.su += uu;
+      }
+      acc.vx = fma(dx2, fac, acc.vx);
+      acc.vy = fma(dy2, fac, acc.vy);
+      acc.vz = fma(dz2, fac, acc.vz);
+      ++acc.hits;
     }
-    acc.vx = fma(dx2, fac, acc.vx);
-    acc.vy = fma(dy2, fac, acc.vy);
-    acc.vz = fma(dz2, fac, acc.vz);
-    acc.dist += idx != sentinel;
-    acc.hits += hit;
   }
 }
 
@@ -628,90 +679,116 @@ __device__ __forceinline__ void prCpAsync8(void *smemDst, const void *gmemSrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmemSrc) : "memory");
 }
 
-template <bool MIX, bool STATS>
-__global__ void __launch_bounds__(PR_TILE, 4) kLJPruned(PrunedForceArgs a) {
+// DEAD: the ownership column changed since the list build (particles deleted / marked dummy). Those partners are moved
+// out of reach while staging and distance evaluations are counted per pair; otherwise their number is the build-time
+// entry count.
+template <bool MIX, bool STATS, bool DEAD>
+__global__ void __launch_bounds__(PR_TILE, PR_MINBLOCKS) kLJPruned(PrunedForceArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
-  double *sx = reinterpret_cast<double *>(smemRaw);
-  double *sy = sx + a.stagedCapacity;
-  double *sz = sy + a.stagedCapacity;
-  int *stype = reinterpret_cast<int *>(sz + a.stagedCapacity);
+  unsigned char *sxyz = smemRaw;  // (x, y, z) per staged particle
+  int *stype = reinterpret_cast<int *>(smemRaw + static_cast<size_t>(a.stagedCapacity) * 24);
   const int tile = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warpGlobal = tile * PR_WARPS + warp;
   const int nP = a.numCompact[tile];
+  const bool addEntries = STATS && !DEAD && blockIdx.x == 0 && threadIdx.x == 0;
   if (nP == 0) {  // empty tile (block-uniform)
-    if (STATS) {
+    if (STATS && threadIdx.x == 0) {
       LJStats st;
       ljStatsZero(st);
-      if (threadIdx.x == 0) a.partials[blockIdx.x] = st;
+      if (addEntries) st.dist = a.totalEntries;
+      a.partials[blockIdx.x] = st;
     }
     return;
   }
-  // stage the particles referenced by this tile's lists: asynchronous 8-byte copies (LDGSTS), all in flight at once,
-  // no register round trip
+  // Prologue, ordered so that independent global loads are in flight together: (1) this warp's list rows (prefetched
+  // four ahead in a register ring; the list buffer has slack behind its end, so the prefetch needs no bounds check),
+  // (2) the tile's slot table, (3) the staged positions as asynchronous 8-byte copies (LDGSTS, no register round
+  // trip), (4) this lane's own particle.
+  const int first = a.chunkFirst[warpGlobal];
+  const int rows = first >= 0 ? a.warpRows[warpGlobal] : 0;
+  const uint2 *list = reinterpret_cast<const uint2 *>(a.lists) +
+                      (rows > 0 ? static_cast<size_t>(a.warpRowStart[warpGlobal]) * 32 + lane : lane);
+  uint2 q0 = __ldg(list), q1 = __ldg(list + 32), q2 = __ldg(list + 64), q3 = __ldg(list + 96);
   const int *cs = a.compactSlot + (static_cast<size_t>(a.stagedStart[tile]) << a.logM);
-  for (int e = threadIdx.x; e < nP; e += PR_TILE) {
+  double *sd = reinterpret_cast<double *>(sxyz);
+  constexpr int PR_STAGE_UNROLL = 8;
+  int slots[PR_STAGE_UNROLL];
+#pragma unroll
+  for (int k = 0; k < PR_STAGE_UNROLL; ++k) {
+    const int e = threadIdx.x + k * PR_TILE;
+    slots[k] = e < nP ? __ldg(cs + e) : -1;
+  }
+  const int64_t i = static_cast<int64_t>(first >= 0 ? first : 0) + lane;
+  const bool active = rows > 0 && lane < a.chunkNum[warpGlobal] && a.own[i] == APB_OWN_OWNED;
+  // a slot without an owned particle (its rows hold padding only, unless it was deleted after the build) sits far away
+  const double xi = active ? a.x[i] : 0.5 * PR_FAR, yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
+  const int ti = (MIX && active) ? a.type[i] : 0;
+#pragma unroll
+  for (int k = 0; k < PR_STAGE_UNROLL; ++k) {
+    const int e = threadIdx.x + k * PR_TILE;
+    if (slots[k] >= 0) {
+      prCpAsync8(sd + 3 * e, a.x + slots[k]);
+      prCpAsync8(sd + 3 * e + 1, a.y + slots[k]);
+      prCpAsync8(sd + 3 * e + 2, a.z + slots[k]);
+      if (MIX) stype[e] = a.type[slots[k]];
+    }
+  }
+  for (int e = threadIdx.x + PR_STAGE_UNROLL * PR_TILE; e < nP; e += PR_TILE) {
     const int slot = __ldg(cs + e);
-    prCpAsync8(sx + e, a.x + slot);
-    prCpAsync8(sy + e, a.y + slot);
-    prCpAsync8(sz + e, a.z + slot);
+    prCpAsync8(sd + 3 * e, a.x + slot);
+    prCpAsync8(sd + 3 * e + 1, a.y + slot);
+    prCpAsync8(sd + 3 * e + 2, a.z + slot);
     if (MIX) stype[e] = a.type[slot];
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  // while the copies fly: this lane's particle and its first list rows
-  const int first = a.chunkFirst[warpGlobal];
-  const int rows = first >= 0 ? a.warpRows[warpGlobal] : 0;
-  const unsigned sentinel = static_cast<unsigned>(nP);
-  const unsigned sent2 = sentinel | (sentinel << 16);
-  const uint2 *list = reinterpret_cast<const uint2 *>(a.lists) +
-                      (rows > 0 ? static_cast<size_t>(a.warpRowStart[warpGlobal]) * 32 + lane : 0);
-  // list rows are prefetched four ahead (register ring): with few resident warps one row of pair math is shorter than
-  // an L2 / HBM round trip
-  const uint2 sentRow = make_uint2(sent2, sent2);
-  uint2 q0 = sentRow, q1 = sentRow, q2 = sentRow, q3 = sentRow;
-  if (rows > 0) q0 = __ldg(list);
-  if (rows > 1) q1 = __ldg(list + 32);
-  if (rows > 2) q2 = __ldg(list + 64);
-  if (rows > 3) q3 = __ldg(list + 96);
-  const int64_t i = static_cast<int64_t>(first >= 0 ? first : 0) + lane;
-  const bool active = rows > 0 && lane < a.chunkNum[warpGlobal] && a.own[i] == APB_OWN_OWNED;
-  const double xi = active ? a.x[i] : 0., yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
-  const int ti = (MIX && active) ? a.type[i] : 0;
-  if (threadIdx.x == 0) {  // sentinel slot for padding entries
-    sx[nP] = PR_FAR;
-    sy[nP] = 0.;
-    sz[nP] = 0.;
-    if (MIX) stype[nP] = 0;
+  const unsigned sentinel8 = static_cast<unsigned>(nP) << 3;
+  if (threadIdx.x < 16) {  // sentinel slots for padding entries, one per bank class
+    sd[3 * (nP + threadIdx.x)] = PR_FAR;
+    sd[3 * (nP + threadIdx.x) + 1] = 0.;
+    sd[3 * (nP + threadIdx.x) + 2] = 0.;
+    if (MIX) stype[nP + threadIdx.x] = 0;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  if (a.checkDead) {
-    // ownership changed since the list build (particles deleted / marked dummy): move those partners out of reach
+  if (DEAD) {
     for (int e = threadIdx.x; e < nP; e += PR_TILE)
-      if (a.own[cs[e]] == APB_OWN_DUMMY) sx[e] = PR_FAR;
+      if (a.own[cs[e]] == APB_OWN_DUMMY) sd[3 * e] = PR_FAR;
     __syncthreads();
   }
-  PairAcc<MIX, STATS> acc;
-  if (rows > 0) {
-    if (!active) q0 = q1 = q2 = q3 = sentRow;  // slot without an owned particle: no interactions
-    for (int r = 0; r < rows; ++r) {
-      uint2 nn = sentRow;
-      if (active && r + 4 < rows) nn = __ldg(list + static_cast<size_t>(r + 4) * 32);
-      const uint2 cur = q0;
-      prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.x & 0xFFFFu, sentinel, acc);
-      prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.x >> 16, sentinel, acc);
-      prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.y & 0xFFFFu, sentinel, acc);
-      prPair<MIX, STATS>(a.p, xi, yi, zi, ti, sx, sy, sz, stype, cur.y >> 16, sentinel, acc);
-      q0 = q1;
-      q1 = q2;
-      q2 = q3;
-      q3 = nn;
+  PairAcc<MIX, STATS, DEAD> acc;
+#define PR_ROW(Q)                                                                                       \
+  do {                                                                                                  \
+    prPair<MIX, STATS, DEAD>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).x & 0xFFFFu), sentinel8, acc);      \
+    prPair<MIX, STATS, DEAD>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).x >> 16), sentinel8, acc);          \
+    prPair<MIX, STATS, DEAD>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).y & 0xFFFFu), sentinel8, acc);      \
+    prPair<MIX, STATS, DEAD>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).y >> 16), sentinel8, acc);          \
+  } while (0)
+  int r = 0;
+  list += 128;
+  for (; r + 4 <= rows; r += 4, list += 128) {
+    PR_ROW(q0);
+    q0 = __ldg(list);
+    PR_ROW(q1);
+    q1 = __ldg(list + 32);
+    PR_ROW(q2);
+    q2 = __ldg(list + 64);
+    PR_ROW(q3);
+    q3 = __ldg(list + 96);
+  }
+  if (r < rows) {
+    PR_ROW(q0);
+    if (r + 1 < rows) {
+      PR_ROW(q1);
+      if (r + 2 < rows) PR_ROW(q2);
     }
-    if (active) {
-      a.fx[i] += acc.fx;
-      a.fy[i] += acc.fy;
-      a.fz[i] += acc.fz;
-    }
+  }
+#undef PR_ROW
+  if (active) {
+    // single writer per slot: fire-and-forget RED.ADD.F64 instead of a load / add / store round trip
+    atomicAdd(a.fx + i, acc.fx);
+    atomicAdd(a.fy + i, acc.fy);
+    atomicAdd(a.fz + i, acc.fz);
   }
   if (STATS) {
     LJStats st;
@@ -721,7 +798,7 @@ __global__ void __launch_bounds__(PR_TILE, 4) kLJPruned(PrunedForceArgs a) {
     st.vir[0] = acc.vx;
     st.vir[1] = acc.vy;
     st.vir[2] = acc.vz;
-    st.dist = acc.dist;
+    st.dist = DEAD ? acc.dist : (addEntries ? a.totalEntries : 0ULL);
     st.kNoN3 = acc.hits;
     st.gNoN3 = acc.hits;
     ljStatsBlockReduce(st, a.partials);
@@ -756,24 +833,28 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   a.warpRows = static_cast<const int *>(h->prWarpLen.p);
   a.warpRowStart = static_cast<const int *>(h->prWarpStart.p);
   a.lists = static_cast<const unsigned short *>(h->prLists.p);
-  a.stagedCapacity = (h->prunedMaxCompact + 2) & ~1;
-  a.checkDead = h->ownDirty ? 1 : 0;
+  a.stagedCapacity = (h->prunedMaxCompact + 17) & ~1;
+  a.totalEntries = h->prunedEntries;
   a.p = p;
   a.partials = static_cast<LJStats *>(h->partials.p);
   const size_t smem = static_cast<size_t>(a.stagedCapacity) * (mix ? 28 : 24);
-  const int sel = (mix ? 2 : 0) | (stats ? 1 : 0);
-#define PR_LAUNCH(MIXV, STATSV)                                                                                      \
+  const int sel = (mix ? 4 : 0) | (stats ? 2 : 0) | (h->ownDirty ? 1 : 0);
+#define PR_LAUNCH(MIXV, STATSV, DEADV)                                                                               \
   do {                                                                                                               \
     if (smem > 40 * 1024)                                                                                            \
-      APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+      APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                     static_cast<int>(smem)));                                                       \
-    ++h->launchCount, kLJPruned<MIXV, STATSV><<<numTiles, PR_TILE, smem, h->stream>>>(a);                            \
+    ++h->launchCount, kLJPruned<MIXV, STATSV, DEADV><<<numTiles, PR_TILE, smem, h->stream>>>(a);                     \
   } while (0)
   switch (sel) {
-    case 0: PR_LAUNCH(false, false); break;
-    case 1: PR_LAUNCH(false, true); break;
-    case 2: PR_LAUNCH(true, false); break;
-    default: PR_LAUNCH(true, true); break;
+    case 0: PR_LAUNCH(false, false, false); break;
+    case 1: PR_LAUNCH(false, false, true); break;
+    case 2: PR_LAUNCH(false, true, false); break;
+    case 3: PR_LAUNCH(false, true, true); break;
+    case 4: PR_LAUNCH(true, false, false); break;
+    case 5: PR_LAUNCH(true, false, true); break;
+    case 6: PR_LAUNCH(true, true, false); break;
+    default: PR_LAUNCH(true, true, true); break;
   }
   {
     const cudaError_t e = cudaGetLastError();
