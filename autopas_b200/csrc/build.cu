@@ -340,7 +340,7 @@ int apbRebuildLinkedCells(apb_handle h) {
   }
   APB_CHECK(apbRemapHaloLinks(h, perm, n, total));
   APB_CHECK(apbPermuteStorage(h, perm, total));
-  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   h->numCells = nc;
   h->structureValid = true;
   h->countsValid = false;
@@ -655,7 +655,7 @@ int apbRebuildVCL(apb_handle h, int newton3) {
                                                                           static_cast<int *>(h->nbrList.p));
     APB_CUDA(cudaGetLastError());
   }
-  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   h->numPairs = numPairs;
   h->numCells = nt;
   h->structureValid = true;

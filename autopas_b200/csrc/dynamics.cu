@@ -361,6 +361,68 @@ __global__ void kScatterPositions(int64_t m, const int *__restrict__ slot, const
   z[s] = in[2 * m + q];
 }
 
+// both sides of one dimension in one launch (the refresh is launch-latency bound: a few thousand particles per message)
+__global__ void kGatherPositions2(int64_t m0, int64_t m1, const int *__restrict__ idx0, const int *__restrict__ idx1,
+                                  const double *x, const double *y, const double *z, int dim, double shift0,
+                                  double shift1, double *out0, double *out1) {
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= m0 + m1) return;
+  const bool second = q >= m0;
+  if (second) q -= m0;
+  const int64_t m = second ? m1 : m0;
+  const int s = second ? idx1[q] : idx0[q];
+  double *out = second ? out1 : out0;
+  const double shift = second ? shift1 : shift0;
+  double px = nan(""), py = 0., pz = 0.;
+  if (s >= 0) {
+    px = x[s];
+    py = y[s];
+    pz = z[s];
+    if (dim == 0) px += shift;
+    if (dim == 1) py += shift;
+    if (dim == 2) pz += shift;
+  }
+  out[q] = px;
+  out[m + q] = py;
+  out[2 * m + q] = pz;
+}
+__global__ void kScatterPositions2(int64_t m0, int64_t m1, const int *__restrict__ slot0, const int *__restrict__ slot1,
+                                   const double *in0, const double *in1, double *x, double *y, double *z) {
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= m0 + m1) return;
+  const bool second = q >= m0;
+  if (second) q -= m0;
+  const int64_t m = second ? m1 : m0;
+  const int s = second ? slot1[q] : slot0[q];
+  const double *in = second ? in1 : in0;
+  if (s < 0 || isnan(in[q])) return;
+  x[s] = in[q];
+  y[s] = in[m + q];
+  z[s] = in[2 * m + q];
+}
+// a rank that is its own neighbour in this dimension (periodic, one rank wide): what goes out to the right re-enters from
+// the left and vice versa, so the refresh is a direct slot-to-slot copy. srcA -> dstA are the right-going particles
+// (received "from the left"), srcB -> dstB the left-going ones.
+__global__ void kRefreshSelf(int64_t mA, int64_t mB, const int *__restrict__ srcA, const int *__restrict__ dstA,
+                             const int *__restrict__ srcB, const int *__restrict__ dstB, double shiftA, double shiftB,
+                             int dim, double *x, double *y, double *z) {
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= mA + mB) return;
+  const bool second = q >= mA;
+  if (second) q -= mA;
+  const int s = second ? srcB[q] : srcA[q];
+  const int t = second ? dstB[q] : dstA[q];
+  if (s < 0 || t < 0) return;  // dropped by the rebuild: the stale copy stays
+  const double shift = second ? shiftB : shiftA;
+  double px = x[s], py = y[s], pz = z[s];
+  if (dim == 0) px += shift;
+  if (dim == 1) py += shift;
+  if (dim == 2) pz += shift;
+  x[t] = px;
+  y[t] = py;
+  z[t] = pz;
+}
+
 __global__ void kRemap(int64_t m, int *idx, const int *__restrict__ inv, int64_t nOld) {
   const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= m) return;
@@ -571,7 +633,7 @@ static int exchangeDim(apb_handle h, int d, int mode) {
     first += recvCount[s];
   }
   h->nslots = n + nRecvTotal;
-  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   return APB_OK;
 }
 
@@ -632,34 +694,46 @@ extern "C" int apb_exchange_halos(apb_handle h) {
   }
   if (!h->haloLinksValid) return h->fail(APB_ERR_STATE, "apb_exchange_halos: no halo links recorded; call it once before the rebuild");
   for (int d = 0; d < 3; ++d) {
+    HaloLink &L0 = h->link[d][0], &L1 = h->link[d][1];
+    const int left = h->neighbor[d][0], right = h->neighbor[d][1];
+    if (h->nranks == 1 || (left == h->myRank && right == h->myRank)) {
+      // my right-going particles (link 1) arrive in the slots recorded for "from the left" (link 0) and vice versa
+      if (L1.nSend != L0.nRecv || L0.nSend != L1.nRecv)
+        return h->fail(APB_ERR_STATE, "apb_exchange_halos: inconsistent self-exchange links");
+      const int64_t m = L1.nSend + L0.nSend;
+      if (m > 0) {
+        ++h->launchCount, kRefreshSelf<<<apbDivUp(m, 256), 256, 0, h->stream>>>(
+            L1.nSend, L0.nSend, static_cast<const int *>(L1.sendIdx.p), static_cast<const int *>(L0.recvSlot.p),
+            static_cast<const int *>(L0.sendIdx.p), static_cast<const int *>(L1.recvSlot.p), L1.shift, L0.shift, d,
+            h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z]);
+        APB_CUDA(cudaGetLastError());
+      }
+      continue;
+    }
     void *sendBuf[2], *recvBuf[2];
     size_t sb[2], rb[2];
     for (int s = 0; s < 2; ++s) {
-      HaloLink &Lk = h->link[d][s];
-      sb[s] = sizeof(double) * 3 * Lk.nSend;
-      APB_CHECK(apbEnsure(h, h->xbuf[s], sb[s] + 256));
-      sendBuf[s] = h->xbuf[s].p;
-      if (Lk.nSend > 0) {
-        ++h->launchCount, kGatherPositions<<<apbDivUp(Lk.nSend, 256), 256, 0, h->stream>>>(
-            Lk.nSend, static_cast<const int *>(Lk.sendIdx.p), h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], d,
-            Lk.shift, static_cast<double *>(sendBuf[s]));
-        APB_CUDA(cudaGetLastError());
-      }
-    }
-    for (int s = 0; s < 2; ++s) {
+      sb[s] = sizeof(double) * 3 * h->link[d][s].nSend;
       rb[s] = sizeof(double) * 3 * h->link[d][s].nRecv;
+      APB_CHECK(apbEnsure(h, h->xbuf[s], sb[s] + 256));
       APB_CHECK(apbEnsure(h, h->xbuf[2 + s], rb[s] + 256));
+      sendBuf[s] = h->xbuf[s].p;
       recvBuf[s] = h->xbuf[2 + s].p;
     }
+    if (L0.nSend + L1.nSend > 0) {
+      ++h->launchCount, kGatherPositions2<<<apbDivUp(L0.nSend + L1.nSend, 256), 256, 0, h->stream>>>(
+          L0.nSend, L1.nSend, static_cast<const int *>(L0.sendIdx.p), static_cast<const int *>(L1.sendIdx.p),
+          h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], d, L0.shift, L1.shift,
+          static_cast<double *>(sendBuf[0]), static_cast<double *>(sendBuf[1]));
+      APB_CUDA(cudaGetLastError());
+    }
     APB_CHECK(exchangePayload(h, d, sendBuf, sb, recvBuf, rb));
-    for (int s = 0; s < 2; ++s) {
-      HaloLink &Lk = h->link[d][s];
-      if (Lk.nRecv > 0) {
-        ++h->launchCount, kScatterPositions<<<apbDivUp(Lk.nRecv, 256), 256, 0, h->stream>>>(
-            Lk.nRecv, static_cast<const int *>(Lk.recvSlot.p), static_cast<const double *>(recvBuf[s]), h->col[APB_COL_X],
-            h->col[APB_COL_Y], h->col[APB_COL_Z]);
-        APB_CUDA(cudaGetLastError());
-      }
+    if (L0.nRecv + L1.nRecv > 0) {
+      ++h->launchCount, kScatterPositions2<<<apbDivUp(L0.nRecv + L1.nRecv, 256), 256, 0, h->stream>>>(
+          L0.nRecv, L1.nRecv, static_cast<const int *>(L0.recvSlot.p), static_cast<const int *>(L1.recvSlot.p),
+          static_cast<const double *>(recvBuf[0]), static_cast<const double *>(recvBuf[1]), h->col[APB_COL_X],
+          h->col[APB_COL_Y], h->col[APB_COL_Z]);
+      APB_CUDA(cudaGetLastError());
     }
   }
   if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
@@ -693,13 +767,11 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
     if (rc != APB_OK) break;
     const bool rebuild = (it % p->rebuild_frequency == 0) || !h->structureValid;
     if (rebuild) {
-      h->deferSync = false;
       apbLoopTimingRecord(h, 1, true);
       rc = apb_migrate(h, nullptr, nullptr);
       if (rc == APB_OK) rc = apb_exchange_halos(h);
       if (rc == APB_OK) rc = apb_rebuild_neighbor_lists(h, p->traversal, p->newton3);
       apbLoopTimingRecord(h, 1, false);
-      h->deferSync = true;
     } else {
       apbLoopTimingRecord(h, 2, true);
       rc = apb_exchange_halos(h);

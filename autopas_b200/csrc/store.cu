@@ -357,7 +357,7 @@ extern "C" int apb_delete_halo_particles(apb_handle h) {
   if (h->nslots > 0) {
     ++h->launchCount, kDeleteHalo<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->own);
     APB_CUDA(cudaGetLastError());
-    APB_CUDA(cudaStreamSynchronize(h->stream));
+    if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   }
   h->countsValid = false;
   h->ownDirty = true;
@@ -795,7 +795,7 @@ extern "C" int apb_update_container(apb_handle h, int32_t keep, int64_t *out_num
     ++h->launchCount, kKeepPerm<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, flag, keepPos, perm);
     APB_CUDA(cudaGetLastError());
     APB_CHECK(apbPermuteStorage(h, perm, nk));
-    APB_CUDA(cudaStreamSynchronize(h->stream));
+    if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
     h->structureValid = false;
     h->prunedValid = false;
     h->haloLinksValid = false;
