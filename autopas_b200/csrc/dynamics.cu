@@ -226,44 +226,147 @@ extern "C" int apb_integrate_velocities(apb_handle h, double dt, const double *m
 // ------------------------------------------------------------------------------------------------------------------
 // exchange machinery shared by halo exchange and migration
 // ------------------------------------------------------------------------------------------------------------------
-// select flags for one dimension. mode 0 = halo selection, mode 1 = migration.
-__global__ void kSelect(int64_t n, int mode, const double *__restrict__ pos, const int32_t *__restrict__ own, double lmin,
-                        double lmax, double il, double skin, int sendLeft, int sendRight, int *__restrict__ fl,
-                        int *__restrict__ fr) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int o = own[i];
-  const double p = pos[i];
-  int l = 0, r = 0;
-  if (mode == 0) {
+// Selection for one dimension. mode 0 = halo selection, mode 1 = migration. Ordered compaction without N-sized scans:
+// kSelectCount (per-block counts) -> kScanBlockCounts (one block) -> kSelectWrite (slot indices in ascending order).
+struct SelectArgs {
+  int64_t n;
+  int mode;
+  const double *pos;
+  const int32_t *own;
+  double lmin, lmax, il, skin;
+  int sendLeft, sendRight;
+};
+
+__device__ __forceinline__ void selectFlags(const SelectArgs &a, int64_t i, int &l, int &r) {
+  l = r = 0;
+  if (i >= a.n) return;
+  const int o = a.own[i];
+  const double p = a.pos[i];
+  if (a.mode == 0) {
     if (o == APB_OWN_OWNED) {
       // collectHaloParticlesForLeft/RightNeighbor (:509-545): owned particles in [lmin, lmin+il) / [lmax-il, lmax)
-      l = p >= lmin && p < lmin + il;
-      r = p >= lmax - il && p < lmax;
+      l = p >= a.lmin && p < a.lmin + a.il;
+      r = p >= a.lmax - a.il && p < a.lmax;
     } else if (o == APB_OWN_HALO) {
       // forwarding of already received halos (:204-225): [lmin-skin, lmin+il) else [lmax-il, lmax+skin)
-      if (p >= lmin - skin && p < lmin + il)
+      if (p >= a.lmin - a.skin && p < a.lmin + a.il)
         l = 1;
-      else if (p >= lmax - il && p < lmax + skin)
+      else if (p >= a.lmax - a.il && p < a.lmax + a.skin)
         r = 1;
     }
   } else if (o == APB_OWN_OWNED) {
     // categorizeParticlesIntoLeftAndRightNeighbor (:545-593): below the local box -> left, above or at max -> right
-    l = p < lmin;
-    r = p >= lmax;
+    l = p < a.lmin;
+    r = p >= a.lmax;
   }
-  fl[i] = l && sendLeft;
-  fr[i] = r && sendRight;
+  l = l && a.sendLeft;
+  r = r && a.sendRight;
+}
+
+#define SEL_BLOCK 256
+__global__ void __launch_bounds__(SEL_BLOCK) kSelectCount(SelectArgs a, int2 *__restrict__ blockCounts) {
+  __shared__ int sl[SEL_BLOCK / 32], sr[SEL_BLOCK / 32];
+  int l, r;
+  selectFlags(a, static_cast<int64_t>(blockIdx.x) * SEL_BLOCK + threadIdx.x, l, r);
+  const int cl = __popc(__ballot_sync(0xffffffffu, l)), cr = __popc(__ballot_sync(0xffffffffu, r));
+  if ((threadIdx.x & 31) == 0) {
+    sl[threadIdx.x >> 5] = cl;
+    sr[threadIdx.x >> 5] = cr;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tl = 0, tr = 0;
+    for (int w = 0; w < SEL_BLOCK / 32; ++w) {
+      tl += sl[w];
+      tr += sr[w];
+    }
+    blockCounts[blockIdx.x] = make_int2(tl, tr);
+  }
+}
+
+// exclusive scan of the per-block counts by one block; totals[0..1] = number selected for the left / right neighbour
+__global__ void __launch_bounds__(1024) kScanBlockCounts(int numBlocks, int2 *__restrict__ counts, long long *totals) {
+  __shared__ int wl[32], wr[32];
+  __shared__ int carryL, carryR;
+  if (threadIdx.x == 0) carryL = carryR = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < numBlocks; base += 1024) {
+    const int b = base + threadIdx.x;
+    const int2 c = b < numBlocks ? counts[b] : make_int2(0, 0);
+    int il = c.x, ir = c.y;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tl = __shfl_up_sync(0xffffffffu, il, o), tr = __shfl_up_sync(0xffffffffu, ir, o);
+      if (lane >= o) {
+        il += tl;
+        ir += tr;
+      }
+    }
+    if (lane == 31) {
+      wl[warp] = il;
+      wr[warp] = ir;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int vl = wl[lane], vr = wr[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int tl = __shfl_up_sync(0xffffffffu, vl, o), tr = __shfl_up_sync(0xffffffffu, vr, o);
+        if (lane >= o) {
+          vl += tl;
+          vr += tr;
+        }
+      }
+      wl[lane] = vl;
+      wr[lane] = vr;
+    }
+    __syncthreads();
+    const int offL = carryL + (warp ? wl[warp - 1] : 0), offR = carryR + (warp ? wr[warp - 1] : 0);
+    if (b < numBlocks) counts[b] = make_int2(offL + il - c.x, offR + ir - c.y);
+    __syncthreads();
+    if (threadIdx.x == 1023) {
+      carryL = offL + il;
+      carryR = offR + ir;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    totals[0] = carryL;
+    totals[1] = carryR;
+  }
+}
+
+__global__ void __launch_bounds__(SEL_BLOCK) kSelectWrite(SelectArgs a, const int2 *__restrict__ blockOffsets,
+                                                          int *__restrict__ idxL, int *__restrict__ idxR) {
+  __shared__ int sl[SEL_BLOCK / 32], sr[SEL_BLOCK / 32];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * SEL_BLOCK + threadIdx.x;
+  int l, r;
+  selectFlags(a, i, l, r);
+  const unsigned bl = __ballot_sync(0xffffffffu, l), br = __ballot_sync(0xffffffffu, r);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    sl[warp] = __popc(bl);
+    sr[warp] = __popc(br);
+  }
+  __syncthreads();
+  int offL = blockOffsets[blockIdx.x].x, offR = blockOffsets[blockIdx.x].y;
+  for (int w = 0; w < warp; ++w) {
+    offL += sl[w];
+    offR += sr[w];
+  }
+  const unsigned below = (1u << lane) - 1u;
+  if (l) idxL[offL + __popc(bl & below)] = static_cast<int>(i);
+  if (r) idxR[offR + __popc(br & below)] = static_cast<int>(i);
 }
 
 struct PackArgs {
-  int64_t n;
-  const int *flag, *pos;  // flag and exclusive scan of it
+  const int *idx;  // selected slots, ascending
   int ncols;
   const double *src[APB_NUM_COLUMNS];
   const int64_t *id;
   const int32_t *type;
-  int shiftCol;  // index (within the packed columns) of the coordinate that gets the periodic shift
+  int32_t *own;
+  int markDummy;  // migration: the packed particle leaves this rank
+  int shiftCol;   // index (within the packed columns) of the coordinate that gets the periodic shift
   double shift;
   double wrapMin, wrapMax;  // migration: clamp like the reference's nextafter guard
   int clamp;
@@ -275,9 +378,9 @@ struct PackArgs {
 };
 
 __global__ void kPack(PackArgs a) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= a.n || !a.flag[i]) return;
-  const int q = a.pos[i];
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= a.count) return;
+  const int i = a.idx[q];
   for (int c = 0; c < a.ncols; ++c) {
     double v = a.src[c][i];
     if (c == a.shiftCol) {
@@ -292,7 +395,8 @@ __global__ void kPack(PackArgs a) {
   }
   a.outId[q] = a.id[i];
   a.outType[q] = a.type[i];
-  if (a.outIdx) a.outIdx[q] = static_cast<int>(i);
+  if (a.outIdx) a.outIdx[q] = i;
+  if (a.markDummy) a.own[i] = APB_OWN_DUMMY;
 }
 
 struct UnpackArgs {
@@ -323,11 +427,6 @@ __global__ void kUnpackAppend(UnpackArgs a) {
   a.type[s] = a.inType[q];
   a.own[s] = a.ownership;
   if (a.recvSlot) a.recvSlot[q] = static_cast<int>(s);
-}
-
-__global__ void kMarkDummy(int64_t n, const int *__restrict__ fl, const int *__restrict__ fr, int32_t *own) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n && (fl[i] || fr[i])) own[i] = APB_OWN_DUMMY;
 }
 
 // refresh: gather positions of the recorded send slots (+ shift), scatter into the recorded receive slots
@@ -518,20 +617,30 @@ static int exchangeDim(apb_handle h, int d, int mode) {
   const int sendLeft = per || !atMin, sendRight = per || !atMax;
   const double L = h->globalMax[d] - h->globalMin[d];
   const int64_t nn = std::max<int64_t>(n, 1);
-  APB_CHECK(apbEnsure(h, h->key, sizeof(int) * nn));
-  APB_CHECK(apbEnsure(h, h->rank, sizeof(int) * nn));
+  const int numBlocks = apbDivUp(nn, SEL_BLOCK);
   APB_CHECK(apbEnsure(h, h->perm, sizeof(int) * nn));
   APB_CHECK(apbEnsure(h, h->sortV, sizeof(int) * nn));
-  int *fl = static_cast<int *>(h->key.p), *fr = static_cast<int *>(h->rank.p);
+  APB_CHECK(apbEnsure(h, h->key, sizeof(int2) * numBlocks));
   int *pl = static_cast<int *>(h->perm.p), *pr = static_cast<int *>(h->sortV.p);
+  int2 *blockCounts = static_cast<int2 *>(h->key.p);
   long long *totals = reinterpret_cast<long long *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result));
   long long sendCount[2] = {0, 0}, recvCount[2] = {0, 0};
   if (n > 0) {
-    ++h->launchCount, kSelect<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, mode, h->col[APB_COL_X + d], h->own, lmin, lmax, il, h->cfg.skin,
-                                                     sendLeft, sendRight, fl, fr);
+    SelectArgs sa;
+    sa.n = n;
+    sa.mode = mode;
+    sa.pos = h->col[APB_COL_X + d];
+    sa.own = h->own;
+    sa.lmin = lmin;
+    sa.lmax = lmax;
+    sa.il = il;
+    sa.skin = h->cfg.skin;
+    sa.sendLeft = sendLeft;
+    sa.sendRight = sendRight;
+    ++h->launchCount, kSelectCount<<<numBlocks, SEL_BLOCK, 0, h->stream>>>(sa, blockCounts);
+    ++h->launchCount, kScanBlockCounts<<<1, 1024, 0, h->stream>>>(numBlocks, blockCounts, totals);
+    ++h->launchCount, kSelectWrite<<<numBlocks, SEL_BLOCK, 0, h->stream>>>(sa, blockCounts, pl, pr);
     APB_CUDA(cudaGetLastError());
-    APB_CHECK(apbExclusiveScan(h, fl, pl, n, totals));
-    APB_CHECK(apbExclusiveScan(h, fr, pr, n, totals + 1));
     APB_CUDA(cudaMemcpyAsync(sendCount, totals, 16, cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaStreamSynchronize(h->stream));
   }
@@ -565,9 +674,9 @@ static int exchangeDim(apb_handle h, int d, int mode) {
     }
     if (sendCount[s] == 0) continue;
     PackArgs a;
-    a.n = n;
-    a.flag = s == 0 ? fl : fr;
-    a.pos = s == 0 ? pl : pr;
+    a.idx = s == 0 ? pl : pr;
+    a.own = h->own;
+    a.markDummy = mode == 1;
     a.ncols = ncols;
     a.shiftCol = -1;
     for (int c = 0; c < ncols; ++c) {
@@ -586,11 +695,7 @@ static int exchangeDim(apb_handle h, int d, int mode) {
     a.outId = reinterpret_cast<int64_t *>(base + alignUp(sizeof(double) * ncols * sendCount[s]));
     a.outType = reinterpret_cast<int32_t *>(base + alignUp(sizeof(double) * ncols * sendCount[s]) + alignUp(8 * sendCount[s]));
     a.outIdx = mode == 0 ? static_cast<int *>(Lk.sendIdx.p) : nullptr;
-    ++h->launchCount, kPack<<<apbDivUp(n, 256), 256, 0, h->stream>>>(a);
-    APB_CUDA(cudaGetLastError());
-  }
-  if (mode == 1 && n > 0 && (sendCount[0] || sendCount[1])) {
-    ++h->launchCount, kMarkDummy<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, fl, fr, h->own);
+    ++h->launchCount, kPack<<<apbDivUp(sendCount[s], 256), 256, 0, h->stream>>>(a);
     APB_CUDA(cudaGetLastError());
   }
   APB_CHECK(exchangePayload(h, d, sendBuf, sb, recvBuf, rb));
@@ -666,9 +771,8 @@ extern "C" int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num
     received += h->nslots - n0;
   }
   (void)before;
-  // compact: drop dummies (sent particles, old halos); nothing is outside the local box any more
-  int64_t nl = 0;
-  APB_CHECK(apb_update_container(h, 0, &nl));
+  // Sent particles and the old halos are dummies now. They are not compacted here: the rebuild that must follow drops
+  // dummies while it sorts (VerletClusterLists.h:362-397 / LinkedCells.h:152-202 likewise delete dummies on rebuild).
   if (out_num_received) *out_num_received = received;
   if (out_num_sent) *out_num_sent = received;  // single rank: identical; multi rank: local view of arrivals
   h->structureValid = false;
