@@ -291,6 +291,104 @@ static int segSort(apb_handle h, int mode, int64_t numSeg, int maxCount, const i
   return APB_OK;
 }
 
+// ---- tower sort with z bins (VerletClusterLists) --------------------------------------------------------------------
+// Sorting every tower by (z, id) is done as a counting sort on the finer key (tower, z bin) followed by an all-pairs
+// rank sort inside each bin (a dozen particles): O(N * bin size) comparisons instead of a bitonic network over the whole
+// tower. z bins are monotone in z, so bin order followed by in-bin order is the total (z, id) order the reference's
+// sorted towers have (ClusterTower.h:83-100) with the canonical tie-break.
+__global__ void kKeysVCLBins(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ z, const int32_t *__restrict__ own, VCLGeom g, int ZB,
+                             double zScale, int *__restrict__ key, int *__restrict__ rank, int *__restrict__ binCount) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int k = -1;
+  if (i < n && own[i] != APB_OWN_DUMMY) {
+    const double px = x[i], py = y[i], pz = z[i];
+    // VerletClusterListsRebuilder::sortParticlesIntoTowers (:217-232): only particles inside the halo box are kept
+    const bool in = px >= g.haloBoxMin[0] && px < g.haloBoxMax[0] && py >= g.haloBoxMin[1] && py < g.haloBoxMax[1] &&
+                    pz >= g.haloBoxMin[2] && pz < g.haloBoxMax[2];
+    if (in) {
+      int zb = static_cast<int>((pz - g.haloBoxMin[2]) * zScale);
+      zb = zb < 0 ? 0 : (zb > ZB - 1 ? ZB - 1 : zb);
+      k = apbTowerIndex(g, px, py) * ZB + zb;
+    }
+  }
+  // warp-aggregated arrival rank: storage is tower-major from the previous build, so most lanes of a warp share a key
+  // and one atomic per group replaces up to 32 colliding ones
+  const unsigned grp = __match_any_sync(0xffffffffu, k);
+  const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
+  int base = 0;
+  if (lane == leader && k >= 0) base = atomicAdd(&binCount[k], __popc(grp));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (i < n) {
+    key[i] = k;
+    if (k >= 0) rank[i] = base + __popc(grp & ((1u << lane) - 1u));
+  }
+}
+
+// one warp per tower: exclusive prefix of its bins (in place), particle count, M-padded count, global maximum
+__global__ void kTowerBins(int numTowers, int ZB, int M, int *__restrict__ binCount, int *__restrict__ binOff,
+                           int *__restrict__ count, int *__restrict__ padded, int *maxCount) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= numTowers) return;
+  int run = 0;
+  for (int b0 = 0; b0 < ZB; b0 += 32) {
+    const int b = b0 + lane;
+    const int c = b < ZB ? binCount[t * ZB + b] : 0;
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (b < ZB) binOff[t * ZB + b] = run + incl - c;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) {
+    count[t] = run;
+    padded[t] = (run + M - 1) / M * M;
+    if (run > 0) atomicMax(maxCount, run);
+  }
+}
+
+__global__ void kScatterPermBins(int64_t n, int ZB, const int *__restrict__ key, const int *__restrict__ rank,
+                                 const int *__restrict__ start, const int *__restrict__ binOff, int *__restrict__ perm) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = key[i];
+  if (k >= 0) perm[start[k / ZB] + binOff[k] + rank[i]] = static_cast<int>(i);
+}
+
+// one warp per (tower, z bin): rank of every member among the members by (z, id, slot); permOut receives the sorted bin
+__global__ void kBinSort(int numBins, int ZB, const int *__restrict__ start, const int *__restrict__ binOff,
+                         const int *__restrict__ binCount, const int *__restrict__ permIn, int *__restrict__ permOut,
+                         const double *__restrict__ z, const int64_t *__restrict__ id) {
+  const int bin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (bin >= numBins) return;
+  const int cnt = binCount[bin];
+  if (cnt == 0) return;
+  const int b0 = start[bin / ZB] + binOff[bin];
+  for (int ci = 0; ci < cnt; ci += 32) {
+    const bool mine = ci + lane < cnt;
+    const int p = mine ? permIn[b0 + ci + lane] : 0;
+    const double zi = mine ? z[p] : 0.;
+    const long long idi = mine ? id[p] : 0;
+    int r = 0;
+    for (int cj = 0; cj < cnt; cj += 32) {
+      const bool have = cj + lane < cnt;
+      const int pj = have ? (cj == ci ? p : permIn[b0 + cj + lane]) : 0;
+      const double zj = have ? (cj == ci ? zi : z[pj]) : 0.;
+      const long long idj = have ? (cj == ci ? idi : id[pj]) : 0;
+      const int m = min(32, cnt - cj);
+      for (int k = 0; k < m; ++k) {
+        const double zk = __shfl_sync(0xffffffffu, zj, k);
+        const long long idk = __shfl_sync(0xffffffffu, idj, k);
+        const int pk = __shfl_sync(0xffffffffu, pj, k);
+        r += zk < zi || (zk == zi && (idk < idi || (idk == idi && pk < p)));
+      }
+    }
+    if (mine) permOut[b0 + r] = p;
+  }
+}
+
 // scratch words behind the result struct: [0..1] scan totals (int64), [8] max count (int32)
 static long long *scratchTotals(apb_handle h) {
   return reinterpret_cast<long long *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result));
@@ -552,22 +650,34 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   const VCLGeom &g = h->vcl;
   const int64_t n = h->nslots;
   const int64_t nt = g.numTowers;
+  // z bins per tower: about a dozen particles per bin on average
+  const double avgPerTower = static_cast<double>(owned + halo) / static_cast<double>(std::max<int64_t>(nt, 1));
+  const int ZB = static_cast<int>(std::min(512.0, std::max(1.0, std::ceil(avgPerTower / 12.0))));
+  const double zScale = static_cast<double>(ZB) / (g.haloBoxMax[2] - g.haloBoxMin[2]);
+  const int64_t numBins = nt * ZB;
+  if (numBins + 1 > 0x7fffffffLL) return h->fail(APB_ERR_NOT_APPLICABLE, "too many towers");
   APB_CHECK(apbEnsure(h, h->key, sizeof(int) * std::max<int64_t>(n, 1)));
-  APB_CHECK(apbEnsure(h, h->rank, sizeof(int) * std::max<int64_t>(n, 1)));
+  APB_CHECK(apbEnsure(h, h->rank, sizeof(int) * std::max<int64_t>(std::max<int64_t>(n, nt + 1), 1)));
   APB_CHECK(apbEnsure(h, h->count, sizeof(int) * (nt + 1)));
   APB_CHECK(apbEnsure(h, h->start, sizeof(int) * (nt + 1)));
   APB_CHECK(apbEnsure(h, h->nbrCount, sizeof(int) * (nt + 1)));  // padded counts (temporarily)
+  APB_CHECK(apbEnsure(h, h->sortK1, sizeof(int) * (numBins + 1)));  // bin counts
+  APB_CHECK(apbEnsure(h, h->sortK2, sizeof(int) * (numBins + 1)));  // bin offsets inside the tower
   int *key = static_cast<int *>(h->key.p), *rank = static_cast<int *>(h->rank.p);
   int *count = static_cast<int *>(h->count.p), *start = static_cast<int *>(h->start.p);
   int *padded = static_cast<int *>(h->nbrCount.p);
+  int *binCount = static_cast<int *>(h->sortK1.p), *binOff = static_cast<int *>(h->sortK2.p);
   APB_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * (nt + 1), h->stream));
+  APB_CUDA(cudaMemsetAsync(padded, 0, sizeof(int) * (nt + 1), h->stream));
+  APB_CUDA(cudaMemsetAsync(binCount, 0, sizeof(int) * (numBins + 1), h->stream));
   APB_CUDA(cudaMemsetAsync(scratchMax(h), 0, sizeof(int), h->stream));
   if (n > 0) {
-    ++h->launchCount, kKeysVCL<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own,
-                                                      g, key, rank, count);
+    ++h->launchCount, kKeysVCLBins<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z],
+                                                          h->own, g, ZB, zScale, key, rank, binCount);
     APB_CUDA(cudaGetLastError());
   }
-  ++h->launchCount, kPadCounts<<<apbDivUp(nt + 1, 256), 256, 0, h->stream>>>(nt + 1, count, padded, M, scratchMax(h));
+  ++h->launchCount, kTowerBins<<<apbDivUp(nt * 32, 256), 256, 0, h->stream>>>(static_cast<int>(nt), ZB, M, binCount, binOff, count,
+                                                                  padded, scratchMax(h));
   APB_CHECK(apbExclusiveScan(h, padded, start, nt + 1, scratchTotals(h)));
   long long total = 0;
   int maxCount = 0;
@@ -576,14 +686,16 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   APB_CUDA(cudaStreamSynchronize(h->stream));
   h->vclMaxTowerCount = maxCount;
   APB_CHECK(apbEnsure(h, h->perm, sizeof(int) * std::max<int64_t>(total, 1)));
+  APB_CHECK(apbEnsure(h, h->sortV, sizeof(int) * std::max<int64_t>(total, 1)));
   APB_CHECK(apbEnsure(h, h->slotCell, sizeof(int) * std::max<int64_t>(total, 1)));
-  int *perm = static_cast<int *>(h->perm.p);
+  int *perm = static_cast<int *>(h->perm.p), *permUnsorted = static_cast<int *>(h->sortV.p);
   int *slotTower = static_cast<int *>(h->slotCell.p);
   if (total > 0) APB_CUDA(cudaMemsetAsync(perm, 0xFF, sizeof(int) * total, h->stream));
-  if (n > 0) {
-    ++h->launchCount, kScatterPerm<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, key, rank, start, perm);
+  if (n > 0 && total > 0) {
+    ++h->launchCount, kScatterPermBins<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, ZB, key, rank, start, binOff, permUnsorted);
+    ++h->launchCount, kBinSort<<<apbDivUp(numBins * 32, 256), 256, 0, h->stream>>>(static_cast<int>(numBins), ZB, start, binOff, binCount,
+                                                                      permUnsorted, perm, h->col[APB_COL_Z], h->id);
     APB_CUDA(cudaGetLastError());
-    APB_CHECK(segSort(h, 1, nt, maxCount, start, count, perm));
   }
   APB_CHECK(apbRemapHaloLinks(h, perm, n, total));
   APB_CHECK(apbPermuteStorage(h, perm, total));
