@@ -1,0 +1,731 @@
+/**
+ * @file GpuContainers.h
+ * Header-only C++20 drop-in classes that put the B200 library (include/autopas_b200.h) behind AutoPas' own container /
+ * traversal / functor interfaces. Compiles against the UNMODIFIED AutoPas headers; INTEGRATION.md lists the additive
+ * enum / selector edits that make the tuner generate these classes.
+ *
+ *   autopas_b200::GpuParticleContainer<Particle_T>  : autopas::ParticleContainerInterface<Particle_T>
+ *       (src/autopas/containers/ParticleContainerInterface.h:38-410). Particles live in device SoA columns; the host
+ *       sees them through a lazily synchronised AoS mirror that is downloaded when an iterator touches it and written
+ *       back before the next device operation if it was handed out mutable.
+ *   autopas_b200::GpuTraversal<Functor_T>           : autopas::TraversalInterface (containers/TraversalInterface.h:18-84)
+ *       maps the static functor type to a kernel descriptor; functors without a GPU kernel make
+ *       isApplicableToDomain() false, so the configuration is rejected instead of silently running on the CPU.
+ *   autopas_b200::GpuLJFunctor<Particle_T, ...>     : autopas::PairwiseFunctor, wraps mdLib::LJFunctor (same template
+ *       flags). CPU traversals run the wrapped reference functor unchanged; GPU traversals deposit the raw accumulators
+ *       (LJFunctor.h:1121-1195) here and endTraversal applies the reference normalisation (LJFunctor.h:661-685).
+ */
+#pragma once
+
+#include <array>
+#include <atomic>
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "autopas/baseFunctors/PairwiseFunctor.h"
+#include "autopas/containers/ParticleContainerInterface.h"
+#include "autopas/containers/TraversalInterface.h"
+#include "autopas/iterators/ContainerIterator.h"
+#include "autopas/options/DataLayoutOption.h"
+#include "autopas/particles/OwnershipState.h"
+#include "autopas/utils/ExceptionHandler.h"
+#include "autopas/utils/WrapOpenMP.h"
+#include "autopas/utils/inBox.h"
+#include "autopas/utils/markParticleAsDeleted.h"
+#include "autopas_b200.h"
+#include "molecularDynamicsLibrary/LJFunctor.h"
+#include "molecularDynamicsLibrary/ParticlePropertiesLibrary.h"
+
+namespace autopas_b200 {
+
+/// Kernel descriptor handed from a GPU-capable functor to the container.
+struct FunctorDescriptor {
+  apb_functor functor{};
+  std::vector<double> mixingTable;  // keeps functor.mixing_table alive
+};
+
+/// Interface the container sees; implemented by GpuTraversal<Functor_T>.
+class GpuTraversalInterface {
+ public:
+  virtual ~GpuTraversalInterface() = default;
+  [[nodiscard]] virtual int apbTraversal() const = 0;
+  [[nodiscard]] virtual bool functorHasGpuKernel() const = 0;
+  virtual FunctorDescriptor describeFunctor() = 0;
+  virtual void depositResult(const apb_traversal_result &raw) = 0;
+};
+
+/// Names as they would appear in TraversalOption (unique prefixes gpulc_ / gpuvcl_, CompatibleTraversals.h:29-37).
+inline const char *traversalName(int t) {
+  switch (t) {
+    case APB_TRAVERSAL_GPULC_C08: return "gpulc_c08";
+    case APB_TRAVERSAL_GPULC_C18: return "gpulc_c18";
+    case APB_TRAVERSAL_GPUVCL_CLUSTER_ITERATION: return "gpuvcl_cluster_iteration";
+    case APB_TRAVERSAL_GPUVCL_C06: return "gpuvcl_c06";
+    case APB_TRAVERSAL_GPUVCL_C01_BALANCED: return "gpuvcl_c01_balanced";
+    default: return "gpuvcl_pruned";
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GpuLJFunctor
+// ---------------------------------------------------------------------------------------------------------------------
+template <class Particle_T, bool applyShift = false, bool useMixing = false,
+          autopas::FunctorN3Modes useNewton3 = autopas::FunctorN3Modes::Both, bool calculateGlobals = false,
+          bool countFLOPs = false, bool relevantForTuning = true>
+class GpuLJFunctor
+    : public autopas::PairwiseFunctor<Particle_T, GpuLJFunctor<Particle_T, applyShift, useMixing, useNewton3,
+                                                               calculateGlobals, countFLOPs, relevantForTuning>> {
+  using Self = GpuLJFunctor<Particle_T, applyShift, useMixing, useNewton3, calculateGlobals, countFLOPs, relevantForTuning>;
+  using Cpu = mdLib::LJFunctor<Particle_T, applyShift, useMixing, useNewton3, calculateGlobals, countFLOPs, relevantForTuning>;
+  using SoAArraysType = typename Particle_T::SoAArraysType;
+
+ public:
+  static constexpr bool apbHasGpuKernel = true;
+
+  explicit GpuLJFunctor(double cutoff) requires(not useMixing)
+      : autopas::PairwiseFunctor<Particle_T, Self>(cutoff), _cpu(cutoff), _cutoff(cutoff) {}
+  GpuLJFunctor(double cutoff, ParticlePropertiesLibrary<double, size_t> &ppl) requires(useMixing)
+      : autopas::PairwiseFunctor<Particle_T, Self>(cutoff), _cpu(cutoff, ppl), _cutoff(cutoff), _ppl(&ppl) {}
+
+  std::string getName() final { return "GpuLJFunctor"; }
+  bool isRelevantForTuning() final { return relevantForTuning; }
+  bool allowsNewton3() final { return _cpu.allowsNewton3(); }
+  bool allowsNonNewton3() final { return _cpu.allowsNonNewton3(); }
+
+  // ---- CPU path: the wrapped reference functor, untouched ----
+  void AoSFunctor(Particle_T &i, Particle_T &j, bool newton3) final { _cpu.AoSFunctor(i, j, newton3); }
+  void SoAFunctorSingle(autopas::SoAView<SoAArraysType> soa, bool newton3) final { _cpu.SoAFunctorSingle(soa, newton3); }
+  void SoAFunctorPair(autopas::SoAView<SoAArraysType> soa1, autopas::SoAView<SoAArraysType> soa2, bool newton3) final {
+    _cpu.SoAFunctorPair(soa1, soa2, newton3);
+  }
+  void SoAFunctorVerlet(autopas::SoAView<SoAArraysType> soa, const size_t indexFirst,
+                        const std::vector<size_t, autopas::AlignedAllocator<size_t>> &neighborList, bool newton3) final {
+    _cpu.SoAFunctorVerlet(soa, indexFirst, neighborList, newton3);
+  }
+  constexpr static auto getNeededAttr() { return Cpu::getNeededAttr(); }
+  constexpr static auto getNeededAttr(std::false_type) { return Cpu::getNeededAttr(std::false_type()); }
+  constexpr static auto getComputedAttr() { return Cpu::getComputedAttr(); }
+  constexpr static bool getMixing() { return useMixing; }
+
+  /// LJFunctor::setParticleProperties (LJFunctor.h:588-596)
+  void setParticleProperties(double epsilon24, double sigmaSquared) {
+    _cpu.setParticleProperties(epsilon24, sigmaSquared);
+    _epsilon24 = epsilon24;
+    _sigmaSquared = sigmaSquared;
+  }
+
+  void initTraversal() final {
+    _cpu.initTraversal();
+    _gpuRaw = {};
+    _gpuUpot = _gpuVirial = 0.;
+    _postProcessed = false;
+  }
+
+  /// Reference normalisation (LJFunctor.h:661-685): Upot = sum * 0.5 / 6, virial = (vx + vy + vz) * 0.5
+  void endTraversal(bool newton3) final {
+    if (_postProcessed) {
+      autopas::utils::ExceptionHandler::exception(
+          "Already postprocessed, endTraversal(bool newton3) was called twice without calling initTraversal().");
+    }
+    _cpu.endTraversal(newton3);
+    if constexpr (calculateGlobals) {
+      apb_lj_end_traversal(&_gpuRaw, &_gpuUpot, &_gpuVirial);
+    }
+    _postProcessed = true;
+  }
+
+  double getPotentialEnergy() {
+    double cpu = 0.;
+    if constexpr (calculateGlobals) cpu = _cpu.getPotentialEnergy();  // throws like the reference if misused
+    else return _cpu.getPotentialEnergy();
+    return cpu + _gpuUpot;
+  }
+  double getVirial() {
+    double cpu = 0.;
+    if constexpr (calculateGlobals) cpu = _cpu.getVirial();
+    else return _cpu.getVirial();
+    return cpu + _gpuVirial;
+  }
+  [[nodiscard]] size_t getNumFLOPs() const override {
+    if constexpr (countFLOPs) return _cpu.getNumFLOPs() + apb_lj_num_flops(&_gpuRaw, applyShift ? 1 : 0);
+    return std::numeric_limits<size_t>::max();
+  }
+  [[nodiscard]] double getHitRate() const override {
+    if constexpr (countFLOPs) {
+      const auto kernel = _gpuRaw.num_kernel_calls_n3 + _gpuRaw.num_kernel_calls_no_n3;
+      if (_gpuRaw.num_dist_calls > 0) return static_cast<double>(kernel) / static_cast<double>(_gpuRaw.num_dist_calls);
+      return _cpu.getHitRate();
+    }
+    return std::numeric_limits<double>::quiet_NaN();
+  }
+
+  // ---- GPU path hooks used by GpuTraversal ----
+  FunctorDescriptor apbDescribe() {
+    FunctorDescriptor d;
+    d.functor.kind = APB_FUNCTOR_LJ;
+    d.functor.flags = (applyShift ? APB_FUNCTOR_APPLY_SHIFT : 0) | (useMixing ? APB_FUNCTOR_USE_MIXING : 0) |
+                      (calculateGlobals ? APB_FUNCTOR_CALC_GLOBALS : 0) | (countFLOPs ? APB_FUNCTOR_COUNT_FLOPS : 0);
+    d.functor.cutoff = _cutoff;
+    d.functor.epsilon24 = _epsilon24;
+    d.functor.sigma_squared = _sigmaSquared;
+    if constexpr (useMixing) {
+      // ParticlePropertiesLibrary stores {epsilon24, sigmaSquared, shift6} per pair (ParticlePropertiesLibrary.h:324-328)
+      const auto T = _ppl->getNumberRegisteredSiteTypes();
+      d.mixingTable.resize(T * T * 3);
+      for (size_t i = 0; i < T; ++i)
+        for (size_t j = 0; j < T; ++j) {
+          d.mixingTable[3 * (i * T + j) + 0] = _ppl->getMixing24Epsilon(i, j);
+          d.mixingTable[3 * (i * T + j) + 1] = _ppl->getMixingSigmaSquared(i, j);
+          d.mixingTable[3 * (i * T + j) + 2] = _ppl->getMixingShift6(i, j);
+        }
+      d.functor.num_types = static_cast<int32_t>(T);
+      d.functor.mixing_table = d.mixingTable.data();
+    }
+    return d;
+  }
+  void apbDeposit(const apb_traversal_result &raw) {
+    _gpuRaw.upot_sum += raw.upot_sum;
+    for (int d = 0; d < 3; ++d) _gpuRaw.virial_sum[d] += raw.virial_sum[d];
+    _gpuRaw.num_dist_calls += raw.num_dist_calls;
+    _gpuRaw.num_kernel_calls_n3 += raw.num_kernel_calls_n3;
+    _gpuRaw.num_kernel_calls_no_n3 += raw.num_kernel_calls_no_n3;
+    _gpuRaw.num_global_calcs_n3 += raw.num_global_calcs_n3;
+    _gpuRaw.num_global_calcs_no_n3 += raw.num_global_calcs_no_n3;
+  }
+
+ private:
+  Cpu _cpu;
+  double _cutoff;
+  ParticlePropertiesLibrary<double, size_t> *_ppl = nullptr;
+  double _epsilon24 = 0., _sigmaSquared = 0.;
+  apb_traversal_result _gpuRaw{};
+  double _gpuUpot = 0., _gpuVirial = 0.;
+  bool _postProcessed = false;
+};
+
+template <class F>
+concept HasGpuKernel = requires(F &f) {
+  { f.apbDescribe() } -> std::same_as<FunctorDescriptor>;
+  f.apbDeposit(std::declval<const apb_traversal_result &>());
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GpuTraversal
+// ---------------------------------------------------------------------------------------------------------------------
+template <class Functor_T>
+class GpuTraversal : public autopas::TraversalInterface, public GpuTraversalInterface {
+ public:
+  /// like the reference traversals (e.g. LCC08Traversal.h:40-43): functor by reference, newton3; the data layout is SoA
+  GpuTraversal(int apbTraversalOption, Functor_T &functor, bool useNewton3,
+               autopas::TraversalOption reportedOption = autopas::TraversalOption::vcl_cluster_iteration)
+      : autopas::TraversalInterface(autopas::DataLayoutOption::soa, useNewton3),
+        _traversal(apbTraversalOption), _functor(&functor), _reported(reportedOption) {}
+
+  /// With the additive enum edits of INTEGRATION.md this returns TraversalOption::gpulc_c08 etc.; against the
+  /// unmodified reference it reports the stock option passed to the constructor.
+  [[nodiscard]] autopas::TraversalOption getTraversalType() const override { return _reported; }
+
+  /// No CPU fallback: a functor without a GPU kernel, or newton3 on a newton3-off-only traversal
+  /// (CompatibleTraversals.h:142-151), makes the configuration inapplicable (TraversalSelector.h:353-356).
+  [[nodiscard]] bool isApplicableToDomain() const override {
+    if (not functorHasGpuKernel()) return false;
+    if (_useNewton3 and (_traversal == APB_TRAVERSAL_GPUVCL_CLUSTER_ITERATION or
+                         _traversal == APB_TRAVERSAL_GPUVCL_C01_BALANCED or _traversal == APB_TRAVERSAL_GPUVCL_PRUNED))
+      return false;
+    return true;
+  }
+  void initTraversal() override {}
+  void traverseParticles() override {
+    autopas::utils::ExceptionHandler::exception(
+        "GpuTraversal::traverseParticles(): GPU traversals run inside GpuParticleContainer::computeInteractions()");
+  }
+  void endTraversal() override {}
+
+  [[nodiscard]] int apbTraversal() const override { return _traversal; }
+  [[nodiscard]] bool functorHasGpuKernel() const override { return HasGpuKernel<Functor_T>; }
+  FunctorDescriptor describeFunctor() override {
+    if constexpr (HasGpuKernel<Functor_T>) return _functor->apbDescribe();
+    autopas::utils::ExceptionHandler::exception("GpuTraversal: functor {} has no GPU kernel", _functor->getName());
+    return {};
+  }
+  void depositResult(const apb_traversal_result &raw) override {
+    if constexpr (HasGpuKernel<Functor_T>) _functor->apbDeposit(raw);
+  }
+
+ private:
+  int _traversal;
+  Functor_T *_functor;
+  autopas::TraversalOption _reported;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GpuParticleContainer
+// ---------------------------------------------------------------------------------------------------------------------
+template <class Particle_T>
+class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle_T> {
+  using Base = autopas::ParticleContainerInterface<Particle_T>;
+  static constexpr size_t kChunk = 1024;  // mirror particles per iterator "cell" (threads stride over chunks)
+
+ public:
+  /**
+   * @param container APB_CONTAINER_LINKED_CELLS or APB_CONTAINER_VERLET_CLUSTER_LISTS
+   * Arguments as ContainerSelector::generateContainer passes them (tuning/selectors/ContainerSelector.h:57-104).
+   */
+  GpuParticleContainer(int container, const std::array<double, 3> &boxMin, const std::array<double, 3> &boxMax,
+                       double cutoff, double skin, double cellSizeFactor = 1.0, unsigned int clusterSize = 4,
+                       int device = 0)
+      : Base(skin), _boxMin(boxMin), _boxMax(boxMax), _cutoff(cutoff), _containerKind(container),
+        _pending(autopas::autopas_get_max_threads()) {
+    apb_config cfg{};
+    for (int d = 0; d < 3; ++d) {
+      cfg.box_min[d] = boxMin[d];
+      cfg.box_max[d] = boxMax[d];
+    }
+    cfg.cutoff = cutoff;
+    cfg.skin = skin;
+    cfg.cell_size_factor = cellSizeFactor;
+    cfg.cluster_size = static_cast<int32_t>(clusterSize);
+    cfg.container = container;
+    cfg.particle_kind = APB_PARTICLE_LJ;
+    cfg.device = device;
+    if (apb_create(&cfg, &_h) != APB_OK) {
+      autopas::utils::ExceptionHandler::exception("GpuParticleContainer: {}", apb_last_error(nullptr));
+    }
+  }
+  ~GpuParticleContainer() override {
+    if (_h) apb_destroy(_h);
+  }
+
+  /// With INTEGRATION.md applied: ContainerOption::gpuLinkedCells / gpuVerletClusterLists.
+  [[nodiscard]] autopas::ContainerOption getContainerType() const override {
+    return _containerKind == APB_CONTAINER_LINKED_CELLS ? autopas::ContainerOption::linkedCells
+                                                        : autopas::ContainerOption::verletClusterLists;
+  }
+  void reserve(size_t, size_t) override {}
+
+  // ---- storage ------------------------------------------------------------------------------------------------------
+ protected:
+  /// thread-safe like VerletClusterLists::addParticleImpl (VerletClusterLists.h:184-192): per-thread staging vectors
+  void addParticleImpl(const Particle_T &p) override { _pending[autopas::autopas_get_thread_num()].push_back(p); }
+  void addHaloParticleImpl(const Particle_T &haloParticle) override {
+    Particle_T copy = haloParticle;
+    copy.setOwnershipState(autopas::OwnershipState::halo);
+    _pending[autopas::autopas_get_thread_num()].push_back(copy);
+  }
+
+ public:
+  /// ParticleContainerInterface::updateHaloParticle (:152): position of the halo copy with the same id is replaced
+  bool updateHaloParticle(const Particle_T &haloParticle) override {
+    syncToDevice();
+    const int64_t id = static_cast<int64_t>(haloParticle.getID());
+    const auto &r = haloParticle.getR();
+    int64_t notFound = 0;
+    check(apb_update_halo_particles(_h, 1, &id, &r[0], &r[1], &r[2], &notFound));
+    _mirrorValid = false;
+    return notFound == 0;
+  }
+  /// bulk form (one device call for a whole halo message); returns the number of particles that were not found
+  size_t updateHaloParticles(const std::vector<Particle_T> &halos) {
+    syncToDevice();
+    std::vector<int64_t> ids(halos.size());
+    std::vector<double> x(halos.size()), y(halos.size()), z(halos.size());
+    for (size_t i = 0; i < halos.size(); ++i) {
+      ids[i] = static_cast<int64_t>(halos[i].getID());
+      x[i] = halos[i].getR()[0];
+      y[i] = halos[i].getR()[1];
+      z[i] = halos[i].getR()[2];
+    }
+    int64_t notFound = 0;
+    check(apb_update_halo_particles(_h, static_cast<int64_t>(halos.size()), ids.data(), x.data(), y.data(), z.data(),
+                                    &notFound));
+    _mirrorValid = false;
+    return static_cast<size_t>(notFound);
+  }
+
+  void deleteHaloParticles() override {
+    syncToDevice();
+    check(apb_delete_halo_particles(_h));
+    _mirrorValid = false;
+  }
+  void deleteAllParticles() override {
+    for (auto &v : _pending) v.clear();
+    check(apb_delete_all_particles(_h));
+    _mirror.clear();
+    _mirrorValid = true;
+    _mirrorDirty = false;
+  }
+
+  [[nodiscard]] size_t getNumberOfParticles(autopas::IteratorBehavior behavior = autopas::IteratorBehavior::owned) const override {
+    const_cast<GpuParticleContainer *>(this)->syncToDevice();
+    int64_t owned = 0, halo = 0;
+    check(apb_get_num_particles(_h, &owned, &halo));
+    size_t n = 0;
+    if (behavior & autopas::IteratorBehavior::owned) n += static_cast<size_t>(owned);
+    if (behavior & autopas::IteratorBehavior::halo) n += static_cast<size_t>(halo);
+    if (behavior & autopas::IteratorBehavior::dummy) {
+      int64_t slots = 0;
+      check(apb_get_num_slots(_h, &slots));
+      n += static_cast<size_t>(slots - owned - halo);
+    }
+    return n;
+  }
+  [[nodiscard]] size_t size() const override {
+    const_cast<GpuParticleContainer *>(this)->syncToDevice();
+    int64_t slots = 0;
+    check(apb_get_num_slots(_h, &slots));
+    return static_cast<size_t>(slots);
+  }
+
+  // ---- iterators: served from the host mirror -----------------------------------------------------------------------
+  [[nodiscard]] autopas::ContainerIterator<Particle_T, true, false> begin(
+      autopas::IteratorBehavior behavior = autopas::IteratorBehavior::ownedOrHalo,
+      autopas::utils::optRef<typename autopas::ContainerIterator<Particle_T, true, false>::ParticleVecType> additionalVectors =
+          std::nullopt) override {
+    acquireMirror(true);
+    return autopas::ContainerIterator<Particle_T, true, false>(*this, behavior, additionalVectors);
+  }
+  [[nodiscard]] autopas::ContainerIterator<Particle_T, false, false> begin(
+      autopas::IteratorBehavior behavior = autopas::IteratorBehavior::ownedOrHalo,
+      autopas::utils::optRef<typename autopas::ContainerIterator<Particle_T, false, false>::ParticleVecType> additionalVectors =
+          std::nullopt) const override {
+    const_cast<GpuParticleContainer *>(this)->acquireMirror(false);
+    return autopas::ContainerIterator<Particle_T, false, false>(*this, behavior, additionalVectors);
+  }
+  [[nodiscard]] autopas::ContainerIterator<Particle_T, true, true> getRegionIterator(
+      const std::array<double, 3> &lowerCorner, const std::array<double, 3> &higherCorner,
+      autopas::IteratorBehavior behavior,
+      autopas::utils::optRef<typename autopas::ContainerIterator<Particle_T, true, true>::ParticleVecType> additionalVectors =
+          std::nullopt) override {
+    acquireMirror(true);
+    return autopas::ContainerIterator<Particle_T, true, true>(*this, behavior, additionalVectors, lowerCorner, higherCorner);
+  }
+  [[nodiscard]] autopas::ContainerIterator<Particle_T, false, true> getRegionIterator(
+      const std::array<double, 3> &lowerCorner, const std::array<double, 3> &higherCorner,
+      autopas::IteratorBehavior behavior,
+      autopas::utils::optRef<typename autopas::ContainerIterator<Particle_T, false, true>::ParticleVecType> additionalVectors =
+          std::nullopt) const override {
+    const_cast<GpuParticleContainer *>(this)->acquireMirror(false);
+    return autopas::ContainerIterator<Particle_T, false, true>(*this, behavior, additionalVectors, lowerCorner, higherCorner);
+  }
+
+  /// ParticleContainerInterface::getParticle (:337-352): the mirror is cut into chunks of kChunk particles that play
+  /// the role of cells; a thread starts at chunk `thread id` and strides by the number of threads.
+  std::tuple<const Particle_T *, size_t, size_t> getParticle(size_t cellIndex, size_t particleIndex,
+                                                             autopas::IteratorBehavior behavior) const override {
+    constexpr std::array<double, 3> lo{std::numeric_limits<double>::lowest(), std::numeric_limits<double>::lowest(),
+                                       std::numeric_limits<double>::lowest()};
+    constexpr std::array<double, 3> hi{std::numeric_limits<double>::max(), std::numeric_limits<double>::max(),
+                                       std::numeric_limits<double>::max()};
+    return getParticleImpl<false>(cellIndex, particleIndex, behavior, lo, hi);
+  }
+  std::tuple<const Particle_T *, size_t, size_t> getParticle(size_t cellIndex, size_t particleIndex,
+                                                             autopas::IteratorBehavior behavior,
+                                                             const std::array<double, 3> &boxMin,
+                                                             const std::array<double, 3> &boxMax) const override {
+    return getParticleImpl<true>(cellIndex, particleIndex, behavior, boxMin, boxMax);
+  }
+
+  /// like VerletClusterLists::deleteParticle (VerletClusterLists.h:350-360): mark as dummy, storage order is kept
+  bool deleteParticle(Particle_T &particle) override {
+    autopas::internal::markParticleAsDeleted(particle);
+    _mirrorDirty = true;
+    return false;
+  }
+  bool deleteParticle(size_t cellIndex, size_t particleIndex) override {
+    autopas::internal::markParticleAsDeleted(_mirror[cellIndex * kChunk + particleIndex]);
+    _mirrorDirty = true;
+    return false;
+  }
+
+  // ---- the hot path -------------------------------------------------------------------------------------------------
+  void rebuildNeighborLists(autopas::TraversalInterface *traversal) override {
+    auto *gpu = asGpuTraversal(traversal);
+    syncToDevice();
+    check(apb_rebuild_neighbor_lists(_h, gpu->apbTraversal(), traversal->getUseNewton3() ? 1 : 0));
+    _mirrorValid = false;
+  }
+  void computeInteractions(autopas::TraversalInterface *traversal) override {
+    auto *gpu = asGpuTraversal(traversal);
+    syncToDevice();
+    FunctorDescriptor d = gpu->describeFunctor();
+    apb_traversal_result raw{};
+    check(apb_compute_interactions(_h, gpu->apbTraversal(), &d.functor, traversal->getUseNewton3() ? 1 : 0, &raw));
+    gpu->depositResult(raw);
+    _mirrorValid = false;
+  }
+  [[nodiscard]] std::vector<Particle_T> updateContainer(bool keepNeighborListsValid) override {
+    syncToDevice();
+    int64_t nl = 0;
+    check(apb_update_container(_h, keepNeighborListsValid ? 1 : 0, &nl));
+    _mirrorValid = false;
+    std::vector<Particle_T> leavers(static_cast<size_t>(nl));
+    if (nl > 0) {
+      std::vector<double> c[6];
+      for (auto &v : c) v.resize(nl);
+      std::vector<int64_t> ids(nl);
+      std::vector<int32_t> types(nl);
+      check(apb_get_leavers(_h, c[0].data(), c[1].data(), c[2].data(), c[3].data(), c[4].data(), c[5].data(), ids.data(),
+                            types.data()));
+      for (int64_t i = 0; i < nl; ++i) {
+        Particle_T p;
+        p.setR({c[0][i], c[1][i], c[2][i]});
+        p.setV({c[3][i], c[4][i], c[5][i]});
+        p.setID(static_cast<size_t>(ids[i]));
+        if constexpr (requires { p.setTypeId(size_t{}); }) p.setTypeId(static_cast<size_t>(types[i]));
+        p.setOwnershipState(autopas::OwnershipState::owned);
+        leavers[i] = p;
+      }
+    }
+    return leavers;
+  }
+  [[nodiscard]] autopas::TraversalSelectorInfo getTraversalSelectorInfo() const override {
+    apb_geometry g{};
+    check(apb_get_geometry(_h, &g));
+    return autopas::TraversalSelectorInfo(
+        {static_cast<unsigned long>(g.cells_per_dim[0]), static_cast<unsigned long>(g.cells_per_dim[1]),
+         static_cast<unsigned long>(g.cells_per_dim[2])},
+        g.interaction_length, {g.cell_length[0], g.cell_length[1], g.cell_length[2]},
+        static_cast<unsigned int>(g.cluster_size));
+  }
+
+  [[nodiscard]] const std::array<double, 3> &getBoxMax() const override { return _boxMax; }
+  [[nodiscard]] const std::array<double, 3> &getBoxMin() const override { return _boxMin; }
+  [[nodiscard]] double getCutoff() const override { return _cutoff; }
+  void setCutoff(double cutoff) override { _cutoff = cutoff; }
+  [[nodiscard]] double getVerletSkin() const override { return this->_skin; }
+  [[nodiscard]] double getInteractionLength() const override { return _cutoff + this->_skin; }
+
+  /// non-virtual helpers required by the withStaticContainerType lambdas (AutoPasDecl.h:295-545)
+  template <typename Lambda>
+  void forEach(Lambda forEachLambda, autopas::IteratorBehavior behavior = autopas::IteratorBehavior::ownedOrHalo) {
+    for (auto it = this->begin(behavior | autopas::IteratorBehavior::forceSequential); it.isValid(); ++it) forEachLambda(*it);
+  }
+  template <typename Lambda, typename A>
+  void reduce(Lambda reduceLambda, A &result, autopas::IteratorBehavior behavior = autopas::IteratorBehavior::ownedOrHalo) {
+    for (auto it = this->begin(behavior | autopas::IteratorBehavior::forceSequential); it.isValid(); ++it) reduceLambda(*it, result);
+  }
+  template <typename Lambda>
+  void forEachInRegion(Lambda forEachLambda, const std::array<double, 3> &lowerCorner,
+                       const std::array<double, 3> &higherCorner, autopas::IteratorBehavior behavior) {
+    for (auto it = this->getRegionIterator(lowerCorner, higherCorner, behavior | autopas::IteratorBehavior::forceSequential);
+         it.isValid(); ++it)
+      forEachLambda(*it);
+  }
+  template <typename Lambda, typename A>
+  void reduceInRegion(Lambda reduceLambda, A &result, const std::array<double, 3> &lowerCorner,
+                      const std::array<double, 3> &higherCorner, autopas::IteratorBehavior behavior) {
+    for (auto it = this->getRegionIterator(lowerCorner, higherCorner, behavior | autopas::IteratorBehavior::forceSequential);
+         it.isValid(); ++it)
+      reduceLambda(*it, result);
+  }
+
+  /// the C handle, for device-resident extensions (apb_run_steps, apb_exchange_halos, ...)
+  [[nodiscard]] apb_handle handle() {
+    syncToDevice();
+    _mirrorValid = false;
+    return _h;
+  }
+
+ private:
+  void check(int rc) const {
+    if (rc != APB_OK) autopas::utils::ExceptionHandler::exception("GpuParticleContainer: {}", apb_last_error(_h));
+  }
+  GpuTraversalInterface *asGpuTraversal(autopas::TraversalInterface *traversal) const {
+    // the reference containers dynamic_cast to their own traversal interface and throw on mismatch
+    // (LinkedCells.h:576-588, VerletClusterLists.h:154-162)
+    auto *gpu = dynamic_cast<GpuTraversalInterface *>(traversal);
+    if (gpu == nullptr) {
+      autopas::utils::ExceptionHandler::exception(
+          "GpuParticleContainer: trying to use a traversal of the wrong type (not a GpuTraversal)");
+    }
+    return gpu;
+  }
+
+  /// staged additions -> device (bulk apb_add_particles), mutated mirror -> device. Called before every device operation.
+  void syncToDevice() {
+    std::lock_guard<std::mutex> lock(_mutex);
+    if (_mirrorDirty) uploadMirror();
+    flushPending();
+  }
+  void flushPending() {
+    size_t total = 0;
+    for (auto &v : _pending) total += v.size();
+    if (total == 0) return;
+    for (int pass = 0; pass < 2; ++pass) {  // owned first, then halo: two bulk calls
+      const auto want = pass == 0 ? autopas::OwnershipState::owned : autopas::OwnershipState::halo;
+      std::vector<double> col[12];
+      std::vector<int64_t> ids;
+      std::vector<int32_t> types;
+      for (auto &v : _pending)
+        for (auto &p : v) {
+          if (p.getOwnershipState() != want) continue;
+          for (int d = 0; d < 3; ++d) {
+            col[d].push_back(p.getR()[d]);
+            col[3 + d].push_back(p.getV()[d]);
+            col[6 + d].push_back(p.getF()[d]);
+            if constexpr (requires { p.getOldF(); }) col[9 + d].push_back(p.getOldF()[d]);
+          }
+          ids.push_back(static_cast<int64_t>(p.getID()));
+          if constexpr (requires { p.getTypeId(); }) types.push_back(static_cast<int32_t>(p.getTypeId()));
+          else types.push_back(0);
+        }
+      if (ids.empty()) continue;
+      int64_t before = 0;
+      check(apb_get_num_slots(_h, &before));
+      check(apb_add_particles(_h, static_cast<int64_t>(ids.size()), col[0].data(), col[1].data(), col[2].data(), ids.data(),
+                              types.data(), pass == 0 ? APB_OWN_OWNED_VALUE : APB_OWN_HALO_VALUE, 0));
+      // velocities / forces of the appended slots: columns are transferred whole, so patch them through the mirror path
+      _appendedExtra.push_back({static_cast<size_t>(before), std::move(col[3]), std::move(col[4]), std::move(col[5]),
+                                std::move(col[6]), std::move(col[7]), std::move(col[8]), std::move(col[9]),
+                                std::move(col[10]), std::move(col[11])});
+    }
+    for (auto &v : _pending) v.clear();
+    patchAppendedColumns();
+    _mirrorValid = false;
+  }
+  struct Appended {
+    size_t first;
+    std::vector<double> c[9];
+    Appended(size_t f, std::vector<double> &&a0, std::vector<double> &&a1, std::vector<double> &&a2,
+             std::vector<double> &&a3, std::vector<double> &&a4, std::vector<double> &&a5, std::vector<double> &&a6,
+             std::vector<double> &&a7, std::vector<double> &&a8)
+        : first(f), c{std::move(a0), std::move(a1), std::move(a2), std::move(a3), std::move(a4),
+                      std::move(a5), std::move(a6), std::move(a7), std::move(a8)} {}
+  };
+  void patchAppendedColumns() {
+    if (_appendedExtra.empty()) return;
+    int64_t slots = 0;
+    check(apb_get_num_slots(_h, &slots));
+    static constexpr int colId[9] = {APB_COL_VX, APB_COL_VY, APB_COL_VZ, APB_COL_FX, APB_COL_FY,
+                                     APB_COL_FZ, APB_COL_OLDFX, APB_COL_OLDFY, APB_COL_OLDFZ};
+    std::vector<double> tmp(static_cast<size_t>(slots));
+    for (int k = 0; k < 9; ++k) {
+      bool any = false;
+      for (auto &a : _appendedExtra)
+        for (double v : a.c[k]) any = any or v != 0.;
+      if (not any) continue;  // appended slots are zero-initialised by the library
+      check(apb_download_column(_h, colId[k], tmp.data()));
+      for (auto &a : _appendedExtra)
+        for (size_t i = 0; i < a.c[k].size(); ++i) tmp[a.first + i] = a.c[k][i];
+      check(apb_upload_column(_h, colId[k], tmp.data()));
+    }
+    _appendedExtra.clear();
+  }
+
+  /// device -> mirror if the mirror is stale; `forWriting` marks it dirty (it is handed out through mutable iterators)
+  void acquireMirror(bool forWriting) {
+    std::lock_guard<std::mutex> lock(_mutex);
+    size_t pending = 0;
+    for (auto &v : _pending) pending += v.size();
+    if (pending > 0) {  // staged additions must become visible to iterators: push them (and a mutated mirror) first
+      if (_mirrorDirty) uploadMirror();
+      flushPending();
+    }
+    if (not _mirrorValid) downloadMirror();
+    if (forWriting) _mirrorDirty = true;
+  }
+  void downloadMirror() {
+    int64_t slots = 0;
+    check(apb_get_num_slots(_h, &slots));
+    const size_t n = static_cast<size_t>(slots);
+    std::vector<double> c[12];
+    static constexpr int colId[12] = {APB_COL_X, APB_COL_Y, APB_COL_Z, APB_COL_VX, APB_COL_VY, APB_COL_VZ,
+                                      APB_COL_FX, APB_COL_FY, APB_COL_FZ, APB_COL_OLDFX, APB_COL_OLDFY, APB_COL_OLDFZ};
+    for (int k = 0; k < 12; ++k) {
+      c[k].resize(n);
+      if (n) check(apb_download_column(_h, colId[k], c[k].data()));
+    }
+    std::vector<int64_t> ids(n);
+    std::vector<int32_t> types(n), own(n);
+    if (n) check(apb_download_ids(_h, ids.data(), types.data(), own.data()));
+    _mirror.resize(n);
+    AUTOPAS_OPENMP(parallel for schedule(static))
+    for (size_t i = 0; i < n; ++i) {
+      Particle_T &p = _mirror[i];
+      p.setR({c[0][i], c[1][i], c[2][i]});
+      p.setV({c[3][i], c[4][i], c[5][i]});
+      p.setF({c[6][i], c[7][i], c[8][i]});
+      if constexpr (requires { p.setOldF(std::array<double, 3>{}); }) p.setOldF({c[9][i], c[10][i], c[11][i]});
+      p.setID(static_cast<size_t>(ids[i]));
+      if constexpr (requires { p.setTypeId(size_t{}); }) p.setTypeId(static_cast<size_t>(types[i]));
+      p.setOwnershipState(static_cast<autopas::OwnershipState>(own[i]));
+    }
+    _mirrorValid = true;
+    _mirrorDirty = false;
+  }
+  void uploadMirror() {
+    const size_t n = _mirror.size();
+    int64_t slots = 0;
+    check(apb_get_num_slots(_h, &slots));
+    if (static_cast<size_t>(slots) != n) {
+      autopas::utils::ExceptionHandler::exception("GpuParticleContainer: host mirror and device storage diverged");
+    }
+    std::vector<double> c[12];
+    std::vector<int32_t> own(n);
+    for (auto &v : c) v.resize(n);
+    AUTOPAS_OPENMP(parallel for schedule(static))
+    for (size_t i = 0; i < n; ++i) {
+      const Particle_T &p = _mirror[i];
+      for (int d = 0; d < 3; ++d) {
+        c[d][i] = p.getR()[d];
+        c[3 + d][i] = p.getV()[d];
+        c[6 + d][i] = p.getF()[d];
+        if constexpr (requires { p.getOldF(); }) c[9 + d][i] = p.getOldF()[d];
+      }
+      own[i] = static_cast<int32_t>(p.getOwnershipState());
+    }
+    static constexpr int colId[12] = {APB_COL_X, APB_COL_Y, APB_COL_Z, APB_COL_VX, APB_COL_VY, APB_COL_VZ,
+                                      APB_COL_FX, APB_COL_FY, APB_COL_FZ, APB_COL_OLDFX, APB_COL_OLDFY, APB_COL_OLDFZ};
+    if (n) {
+      for (int k = 0; k < 12; ++k) check(apb_upload_column(_h, colId[k], c[k].data()));
+      check(apb_upload_ownership(_h, own.data()));
+    }
+    _mirrorDirty = false;
+  }
+
+  template <bool regionIter>
+  std::tuple<const Particle_T *, size_t, size_t> getParticleImpl(size_t cellIndex, size_t particleIndex,
+                                                                 autopas::IteratorBehavior behavior,
+                                                                 const std::array<double, 3> &boxMin,
+                                                                 const std::array<double, 3> &boxMax) const {
+    const size_t n = _mirror.size();
+    const size_t numChunks = (n + kChunk - 1) / kChunk;
+    const bool sequential = behavior & autopas::IteratorBehavior::forceSequential;
+    const size_t stride = sequential ? 1 : static_cast<size_t>(autopas::autopas_get_num_threads());
+    if (cellIndex == 0 and particleIndex == 0) {
+      cellIndex = sequential ? 0 : static_cast<size_t>(autopas::autopas_get_thread_num());
+    }
+    while (cellIndex < numChunks) {
+      const size_t base = cellIndex * kChunk;
+      const size_t len = std::min(kChunk, n - base);
+      for (; particleIndex < len; ++particleIndex) {
+        const Particle_T &p = _mirror[base + particleIndex];
+        if (autopas::containerIteratorUtils::particleFulfillsIteratorRequirements<regionIter>(p, behavior, boxMin, boxMax)) {
+          return {&p, cellIndex, particleIndex};
+        }
+      }
+      cellIndex += stride;
+      particleIndex = 0;
+    }
+    return {nullptr, 0, 0};
+  }
+
+  static constexpr int32_t APB_OWN_OWNED_VALUE = 1, APB_OWN_HALO_VALUE = 2;  // OwnershipState.h:20-29
+
+  apb_handle _h = nullptr;
+  std::array<double, 3> _boxMin, _boxMax;
+  double _cutoff;
+  int _containerKind;
+  std::vector<std::vector<Particle_T>> _pending;
+  std::vector<Appended> _appendedExtra;
+  mutable std::vector<Particle_T> _mirror;
+  mutable bool _mirrorValid = true;   // mirror == device (an empty container starts coherent)
+  mutable bool _mirrorDirty = false;  // mirror was handed out mutable since the last upload
+  mutable std::mutex _mutex;
+};
+
+}  // namespace autopas_b200

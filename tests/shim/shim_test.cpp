@@ -1,0 +1,204 @@
+// Drop-in check of autopas_b200/shim/GpuContainers.h against the UNMODIFIED AutoPas headers (compiled where they lie by
+// oracle/Makefile, target `shimtest`; the binary runs on the GPU box through tests/test_gpu_shim.py).
+// Same flow as the reference's own parity harness (tests/testAutopas/tests/containers/TraversalComparison.cpp:135-199):
+// container -> fill -> rebuildNeighborLists -> functor.initTraversal(); computeInteractions(traversal);
+// functor.endTraversal(n3) -> read forces through the container iterators. Reference configuration:
+// LinkedCells, csf 1, lc_c08, AoS, newton3 (:210-214).
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <random>
+#include <set>
+
+#include "GpuContainers.h"
+#include "autopas/containers/linkedCells/LinkedCells.h"
+#include "autopas/containers/linkedCells/traversals/LCC08Traversal.h"
+#include "molecularDynamicsLibrary/LJFunctor.h"
+#include "molecularDynamicsLibrary/MoleculeLJ.h"
+
+using Molecule = mdLib::MoleculeLJ;
+using FMCell = autopas::FullParticleCell<Molecule>;
+
+static int g_fail = 0;
+#define CHECK(cond, ...)                                   \
+  do {                                                     \
+    if (!(cond)) {                                         \
+      std::printf("FAIL %s:%d: ", __FILE__, __LINE__);     \
+      std::printf(__VA_ARGS__);                            \
+      std::printf("\n");                                   \
+      ++g_fail;                                            \
+    }                                                      \
+  } while (0)
+
+struct Scenario {
+  std::array<double, 3> boxMin{0., 0., 0.}, boxMax{12., 12., 12.};
+  double cutoff = 2.5, skin = 0.3;
+  std::vector<Molecule> owned, halo;
+};
+
+// jittered simple-cubic lattice (spacing 1, jitter 0.2) over the box and its halo shell: liquid-like distances, no
+// near contacts, so that the force comparison is meaningful per particle
+static Scenario makeScenario(unsigned seed) {
+  Scenario s;
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> u(-0.2, 0.2);
+  const double il = s.cutoff + s.skin;
+  size_t idOwned = 0, idHalo = 1000000;
+  for (int iz = -3; iz < 15; ++iz)
+    for (int iy = -3; iy < 15; ++iy)
+      for (int ix = -3; ix < 15; ++ix) {
+        const std::array<double, 3> r{ix + 0.5 + u(rng), iy + 0.5 + u(rng), iz + 0.5 + u(rng)};
+        const bool inHaloBox = r[0] >= -il and r[0] < 12. + il and r[1] >= -il and r[1] < 12. + il and r[2] >= -il and r[2] < 12. + il;
+        if (autopas::utils::inBox(r, s.boxMin, s.boxMax)) {
+          s.owned.emplace_back(r, std::array<double, 3>{u(rng), u(rng), u(rng)}, idOwned++, 0);
+        } else if (inHaloBox) {
+          Molecule m(r, {0., 0., 0.}, idHalo++, 0);
+          m.setOwnershipState(autopas::OwnershipState::halo);
+          s.halo.push_back(m);
+        }
+      }
+  return s;
+}
+
+template <class Container>
+static void fill(Container &c, const Scenario &s) {
+  for (const auto &p : s.owned) c.addParticle(p);
+  for (const auto &p : s.halo) c.addHaloParticle(p);
+}
+
+template <class Container>
+static std::map<size_t, std::array<double, 3>> forcesOfOwned(Container &c) {
+  std::map<size_t, std::array<double, 3>> f;
+  for (auto it = c.begin(autopas::IteratorBehavior::owned); it.isValid(); ++it) f[it->getID()] = it->getF();
+  return f;
+}
+
+template <bool n3>
+static void compare(const Scenario &s, int gpuContainer, int gpuTraversal, unsigned clusterSize, const char *name) {
+  constexpr bool shift = true, globals = true;
+  // reference
+  autopas::LinkedCells<Molecule> ref(s.boxMin, s.boxMax, s.cutoff, s.skin, 1.0);
+  fill(ref, s);
+  using RefFunctor = mdLib::LJFunctor<Molecule, shift, false, autopas::FunctorN3Modes::Both, globals, true>;
+  RefFunctor fr(s.cutoff);
+  fr.setParticleProperties(24.0, 1.0);
+  const auto info = ref.getTraversalSelectorInfo();
+  autopas::LCC08Traversal<FMCell, RefFunctor> tr(info.cellsPerDim, fr, info.interactionLength, info.cellLength,
+                                                 autopas::DataLayoutOption::aos, true);
+  ref.rebuildNeighborLists(&tr);
+  fr.initTraversal();
+  ref.computeInteractions(&tr);
+  fr.endTraversal(true);
+  // GPU behind the same interface
+  autopas_b200::GpuParticleContainer<Molecule> gpu(gpuContainer, s.boxMin, s.boxMax, s.cutoff, s.skin, 1.0, clusterSize);
+  autopas::ParticleContainerInterface<Molecule> &c = gpu;
+  fill(c, s);
+  CHECK(c.getNumberOfParticles(autopas::IteratorBehavior::owned) == s.owned.size(), "%s owned count", name);
+  CHECK(c.getNumberOfParticles(autopas::IteratorBehavior::halo) == s.halo.size(), "%s halo count", name);
+  using GpuFunctor = autopas_b200::GpuLJFunctor<Molecule, shift, false, autopas::FunctorN3Modes::Both, globals, true>;
+  GpuFunctor fg(s.cutoff);
+  fg.setParticleProperties(24.0, 1.0);
+  autopas_b200::GpuTraversal<GpuFunctor> tg(gpuTraversal, fg, n3);
+  CHECK(tg.isApplicableToDomain(), "%s applicable", name);
+  c.rebuildNeighborLists(&tg);
+  fg.initTraversal();
+  c.computeInteractions(&tg);
+  fg.endTraversal(n3);
+  const auto fRef = forcesOfOwned(ref);
+  const auto fGpu = forcesOfOwned(c);
+  CHECK(fRef.size() == fGpu.size() && fGpu.size() == s.owned.size(), "%s iterator visits %zu of %zu owned", name,
+        fGpu.size(), s.owned.size());
+  double maxRel = 0., fmax = 0.;
+  for (const auto &[id, f] : fRef) fmax = std::max({fmax, std::fabs(f[0]), std::fabs(f[1]), std::fabs(f[2])});
+  for (const auto &[id, f] : fRef) {
+    const auto it = fGpu.find(id);
+    if (it == fGpu.end()) {
+      CHECK(false, "%s id %zu missing", name, id);
+      continue;
+    }
+    for (int d = 0; d < 3; ++d) maxRel = std::max(maxRel, std::fabs(it->second[d] - f[d]) / fmax);
+  }
+  CHECK(maxRel <= 1e-12, "%s force mismatch %.3e (relative to max |F| = %.3e)", name, maxRel, fmax);
+  const double u0 = fr.getPotentialEnergy(), u1 = fg.getPotentialEnergy();
+  const double v0 = fr.getVirial(), v1 = fg.getVirial();
+  CHECK(std::fabs(u1 - u0) <= 1e-12 * std::fabs(u0), "%s Upot %.17g vs %.17g", name, u1, u0);
+  CHECK(std::fabs(v1 - v0) <= 1e-12 * std::fabs(v0), "%s virial %.17g vs %.17g", name, v1, v0);
+  std::printf("%-44s newton3=%d  max |dF|/max|F| = %.2e  Upot %.12e  virial %.12e\n", name, int(n3), maxRel, u1, v1);
+
+  // region iterator: same particle set as the reference container
+  const std::array<double, 3> lo{2., 3., 1.}, hi{7.5, 9., 12.5};
+  std::set<size_t> a, b;
+  for (auto it = ref.getRegionIterator(lo, hi, autopas::IteratorBehavior::ownedOrHalo); it.isValid(); ++it) a.insert(it->getID());
+  for (auto it = c.getRegionIterator(lo, hi, autopas::IteratorBehavior::ownedOrHalo); it.isValid(); ++it) b.insert(it->getID());
+  CHECK(a == b, "%s region iterator: %zu vs %zu particles", name, b.size(), a.size());
+
+  // mutable iterators write through: move owned particles, some of them out of the box; leavers must match
+  auto move = [&](auto &cont) {
+    for (auto it = cont.begin(autopas::IteratorBehavior::owned); it.isValid(); ++it) {
+      auto r = it->getR();
+      r[0] += (it->getID() % 7 == 0) ? 1.5 : 0.01;
+      it->setR(r);
+    }
+  };
+  move(ref);
+  move(c);
+  auto leaveRef = ref.updateContainer(false);
+  auto leaveGpu = c.updateContainer(false);
+  std::set<size_t> la, lb;
+  for (auto &p : leaveRef) la.insert(p.getID());
+  for (auto &p : leaveGpu) lb.insert(p.getID());
+  CHECK(la == lb, "%s leavers: %zu vs %zu", name, lb.size(), la.size());
+  CHECK(c.getNumberOfParticles(autopas::IteratorBehavior::halo) == 0, "%s halos dropped by updateContainer", name);
+  CHECK(c.getNumberOfParticles(autopas::IteratorBehavior::owned) == s.owned.size() - la.size(), "%s owned after update", name);
+  // deleteParticle through an iterator
+  size_t deleted = 0;
+  for (auto it = c.begin(autopas::IteratorBehavior::owned); it.isValid(); ++it)
+    if (it->getID() % 5 == 1) {
+      autopas::internal::deleteParticle(it);
+      ++deleted;
+    }
+  CHECK(c.getNumberOfParticles(autopas::IteratorBehavior::owned) == s.owned.size() - la.size() - deleted, "%s delete", name);
+}
+
+int main() {
+  autopas::utils::ExceptionHandler::setBehavior(autopas::utils::ExceptionBehavior::throwException);
+  const Scenario s = makeScenario(42);
+  try {
+    compare<true>(s, APB_CONTAINER_LINKED_CELLS, APB_TRAVERSAL_GPULC_C08, 4, "gpuLinkedCells/gpulc_c08");
+    compare<false>(s, APB_CONTAINER_LINKED_CELLS, APB_TRAVERSAL_GPULC_C18, 4, "gpuLinkedCells/gpulc_c18");
+    compare<true>(s, APB_CONTAINER_VERLET_CLUSTER_LISTS, APB_TRAVERSAL_GPUVCL_C06, 4, "gpuVerletClusterLists/gpuvcl_c06");
+    compare<false>(s, APB_CONTAINER_VERLET_CLUSTER_LISTS, APB_TRAVERSAL_GPUVCL_CLUSTER_ITERATION, 4,
+                   "gpuVerletClusterLists/gpuvcl_cluster_iteration");
+    compare<false>(s, APB_CONTAINER_VERLET_CLUSTER_LISTS, APB_TRAVERSAL_GPUVCL_PRUNED, 32, "gpuVerletClusterLists/gpuvcl_pruned");
+    // wrong traversal type is rejected like the reference containers do
+    autopas_b200::GpuParticleContainer<Molecule> gpu(APB_CONTAINER_LINKED_CELLS, s.boxMin, s.boxMax, s.cutoff, s.skin);
+    using RefFunctor = mdLib::LJFunctor<Molecule>;
+    RefFunctor fr(s.cutoff);
+    const auto info = gpu.getTraversalSelectorInfo();
+    autopas::LCC08Traversal<FMCell, RefFunctor> tr(info.cellsPerDim, fr, info.interactionLength, info.cellLength,
+                                                   autopas::DataLayoutOption::aos, true);
+    bool threw = false;
+    try {
+      gpu.computeInteractions(&tr);
+    } catch (const autopas::utils::ExceptionHandler::AutoPasException &) {
+      threw = true;
+    }
+    CHECK(threw, "CPU traversal on the GPU container must throw");
+    // a functor without a GPU kernel makes the GPU traversal inapplicable (no CPU fallback)
+    autopas_b200::GpuTraversal<RefFunctor> tn(APB_TRAVERSAL_GPULC_C08, fr, true);
+    CHECK(!tn.isApplicableToDomain(), "reference LJFunctor has no GPU kernel: configuration must be inapplicable");
+    // adding an owned particle outside the box throws (ParticleContainerInterface.h:92-105)
+    threw = false;
+    try {
+      gpu.addParticle(Molecule({-1., 0., 0.}, {0., 0., 0.}, 1, 0));
+    } catch (const autopas::utils::ExceptionHandler::AutoPasException &) {
+      threw = true;
+    }
+    CHECK(threw, "addParticle outside the box must throw");
+  } catch (const std::exception &e) {
+    std::printf("FAIL: exception %s\n", e.what());
+    ++g_fail;
+  }
+  std::printf(g_fail ? "SHIM TEST FAILED (%d)\n" : "SHIM TEST PASSED\n", g_fail);
+  return g_fail ? 1 : 0;
+}
