@@ -68,6 +68,10 @@ class Functor(ctypes.Structure):
         ("num_types", ctypes.c_int32),
         ("mixing_table", ctypes.c_void_p),
         ("nu", ctypes.c_double),
+        ("num_mol_types", ctypes.c_int32),
+        ("site_start", ctypes.c_void_p),
+        ("site_positions", ctypes.c_void_p),
+        ("site_types", ctypes.c_void_p),
     ]
 
 
@@ -140,6 +144,8 @@ SIGNATURES = {
     "apb_lj_num_flops": (ctypes.c_uint64, [ctypes.POINTER(TraversalResult), _i32]),
     "apb_make_lj_mixing_table": (_i32, [_i32, _vp, _vp, _f64, _vp]),
     "apb_lj_calc_shift6": (_f64, [_f64, _f64, _f64]),
+    "apb_atm_end_traversal": (None, [ctypes.POINTER(TraversalResult), ctypes.POINTER(_f64), ctypes.POINTER(_f64)]),
+    "apb_atm_num_flops": (ctypes.c_uint64, [ctypes.POINTER(TraversalResult)]),
     "apb_integrate_positions": (_i32, [_H, _f64, _vp, _i32, _vp]),
     "apb_integrate_velocities": (_i32, [_H, _f64, _vp, _i32]),
     "apb_comm_get_unique_id": (_i32, [_vp]),

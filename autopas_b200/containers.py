@@ -75,6 +75,30 @@ class ParticlePropertiesLibrary:
     def getMixingShift6(self, i, j):
         return self.getMixingTable()[3 * (i * len(self._mass) + j) + 2]
 
+    def getMixingNuTable(self):
+        """nu_ijk = cbrt(nu_i nu_j nu_k), row-major [T*T*T] (ParticlePropertiesLibrary.h:460-470)."""
+        nu = np.asarray(self._nu)
+        return np.cbrt(nu[:, None, None] * nu[None, :, None] * nu[None, None, :]).ravel()
+
+    def addMolType(self, molId, siteIds, relSitePos, momentOfInertia=(1.0, 1.0, 1.0)):
+        """ParticlePropertiesLibrary::addMolType: a molecule type = site types + unrotated relative site positions."""
+        if not hasattr(self, "_mols"):
+            self._mols = []
+        if molId != len(self._mols):
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "molecule types must be registered with consecutive ids")
+        pos = np.asarray(relSitePos, dtype=np.float64).reshape(-1, 3)
+        if len(siteIds) != len(pos):
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "number of site types and site positions differ")
+        self._mols.append((list(siteIds), pos, tuple(momentOfInertia)))
+
+    def getMolTables(self):
+        """(site_start[numMolTypes + 1], site_positions[numSites, 3], site_types[numSites]) for the C ABI."""
+        mols = getattr(self, "_mols", [])
+        starts = np.cumsum([0] + [len(m[0]) for m in mols])
+        pos = np.concatenate([m[1] for m in mols]) if mols else np.zeros((0, 3))
+        types = np.concatenate([np.asarray(m[0]) for m in mols]) if mols else np.zeros(0)
+        return starts, pos, types
+
 
 class LJFunctor:
     """mdLib::LJFunctor: template flags become constructor arguments (LJFunctor.h:39-41)."""
@@ -177,6 +201,193 @@ class LJFunctor:
             self._table_keepalive = _f64(self._ppl.getMixingTable())
             f.num_types = self._ppl.getNumberRegisteredSiteTypes()
             f.mixing_table = self._table_keepalive.ctypes.data
+        return f
+
+
+class _FunctorBase:
+    """Common part of the functor mirrors: accumulators deposited by the GPU traversal, initTraversal / endTraversal."""
+    calculateGlobals = False
+    countFLOPs = False
+
+    def _init_base(self, cutoff):
+        self._cutoff = float(cutoff)
+        self._raw = capi.TraversalResult()
+        self._postProcessed = False
+
+    def isRelevantForTuning(self):
+        return True
+
+    def allowsNewton3(self):
+        return True
+
+    def allowsNonNewton3(self):
+        return True
+
+    def getCutoff(self):
+        return self._cutoff
+
+    def initTraversal(self):
+        self._raw = capi.TraversalResult()
+        self._postProcessed = False
+
+    _deposit = LJFunctor._deposit
+
+    def endTraversal(self, newton3):
+        if self._postProcessed:
+            raise ApbError(capi.ERR_STATE, "Already postprocessed, endTraversal(bool newton3) was called twice without "
+                                           "calling initTraversal().")
+        self._postProcessed = True
+
+
+class SPHCalcDensityFunctor(_FunctorBase):
+    """sphLib::SPHCalcDensityFunctor (applicationLibrary/sph/SPHLibrary/SPHCalcDensityFunctor.h): functor cutoff is 0,
+    the kernel support 2.5 h is enforced inside W."""
+
+    def __init__(self):
+        self._init_base(0.0)
+
+    def getName(self):
+        return "SPHDensityFunctor"
+
+    @staticmethod
+    def getNumFlopsPerKernelCall():
+        return 3 + 2 * 19 + 2 + 2  # SPHCalcDensityFunctor.h:65-72, SPHKernels.cpp:11-21
+
+    def _c_functor(self):
+        f = capi.Functor()
+        f.kind = capi.FUNCTOR_SPH_DENSITY
+        return f
+
+
+class SPHCalcHydroForceFunctor(_FunctorBase):
+    """sphLib::SPHCalcHydroForceFunctor (applicationLibrary/sph/SPHLibrary/SPHCalcHydroForceFunctor.h)."""
+
+    def __init__(self):
+        self._init_base(0.0)
+
+    def getName(self):
+        return "SPHHydroForceFunctor"
+
+    def _c_functor(self):
+        f = capi.Functor()
+        f.kind = capi.FUNCTOR_SPH_HYDRO
+        return f
+
+
+class AxilrodTellerMutoFunctor(_FunctorBase):
+    """mdLib::AxilrodTellerMutoFunctor (AxilrodTellerMutoFunctor.h): triwise; template flags become arguments."""
+
+    def __init__(self, cutoff, particlePropertiesLibrary=None, useMixing=False, calculateGlobals=False,
+                 countFLOPs=False):
+        if useMixing and particlePropertiesLibrary is None:
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "Mixing without a ParticlePropertiesLibrary is not possible")
+        self._init_base(cutoff)
+        self._ppl = particlePropertiesLibrary
+        self.useMixing, self.calculateGlobals, self.countFLOPs = bool(useMixing), bool(calculateGlobals), bool(countFLOPs)
+        self._nu = 0.0
+        self._upot = self._virial = 0.0
+
+    def getName(self):
+        return "AxilrodTellerMutoFunctorAutoVec"
+
+    def setParticleProperties(self, nu):
+        self._nu = float(nu)
+
+    def endTraversal(self, newton3):
+        super().endTraversal(newton3)
+        if self.calculateGlobals:
+            u, v = ctypes.c_double(), ctypes.c_double()
+            capi.load().apb_atm_end_traversal(ctypes.byref(self._raw), ctypes.byref(u), ctypes.byref(v))
+            self._upot, self._virial = u.value, v.value
+
+    def getPotentialEnergy(self):
+        if not self.calculateGlobals:
+            raise ApbError(capi.ERR_STATE, "Trying to get potential energy even though calculateGlobals is false.")
+        if not self._postProcessed:
+            raise ApbError(capi.ERR_STATE, "Cannot get potential energy, because endTraversal was not called.")
+        return self._upot
+
+    def getVirial(self):
+        if not self.calculateGlobals:
+            raise ApbError(capi.ERR_STATE, "Trying to get virial even though calculateGlobals is false.")
+        if not self._postProcessed:
+            raise ApbError(capi.ERR_STATE, "Cannot get virial, because endTraversal was not called.")
+        return self._virial
+
+    def getNumFLOPs(self):
+        if not self.countFLOPs:
+            return 2 ** 64 - 1
+        return capi.load().apb_atm_num_flops(ctypes.byref(self._raw))
+
+    def _c_functor(self):
+        f = capi.Functor()
+        f.kind = capi.FUNCTOR_ATM
+        f.flags = ((capi.FLAG_USE_MIXING if self.useMixing else 0) | (capi.FLAG_CALC_GLOBALS if self.calculateGlobals else 0) |
+                   (capi.FLAG_COUNT_FLOPS if self.countFLOPs else 0))
+        f.cutoff = self._cutoff
+        f.nu = self._nu
+        if self.useMixing:
+            self._table_keepalive = _f64(self._ppl.getMixingNuTable())
+            f.num_types = self._ppl.getNumberRegisteredSiteTypes()
+            f.mixing_table = self._table_keepalive.ctypes.data
+        return f
+
+
+class LJMultisiteFunctor(_FunctorBase):
+    """mdLib::LJMultisiteFunctor (LJMultisiteFunctor.h): site geometry comes from the ParticlePropertiesLibrary
+    (addMolType) when mixing is used, else from setParticleProperties(epsilon24, sigmaSquared, sitePositions)."""
+
+    def __init__(self, cutoff, particlePropertiesLibrary=None, applyShift=False, useMixing=False, calculateGlobals=False):
+        if useMixing and particlePropertiesLibrary is None:
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "Mixing without a ParticlePropertiesLibrary is not possible")
+        self._init_base(cutoff)
+        self._ppl = particlePropertiesLibrary
+        self.applyShift, self.useMixing, self.calculateGlobals = bool(applyShift), bool(useMixing), bool(calculateGlobals)
+        self._epsilon24 = self._sigmaSquared = 0.0
+        self._sitePositions = np.zeros((0, 3))
+        self._upot = self._virial = 0.0
+
+    def getName(self):
+        return "LJMultisiteFunctor"
+
+    def setParticleProperties(self, epsilon24, sigmaSquared, sitePositionsLJ):
+        self._epsilon24, self._sigmaSquared = float(epsilon24), float(sigmaSquared)
+        self._sitePositions = np.ascontiguousarray(sitePositionsLJ, dtype=np.float64).reshape(-1, 3)
+
+    def endTraversal(self, newton3):
+        super().endTraversal(newton3)
+        if self.calculateGlobals:  # same normalisation as LJFunctor (LJMultisiteFunctor.h:725-750)
+            u, v = ctypes.c_double(), ctypes.c_double()
+            capi.load().apb_lj_end_traversal(ctypes.byref(self._raw), ctypes.byref(u), ctypes.byref(v))
+            self._upot, self._virial = u.value, v.value
+
+    getPotentialEnergy = AxilrodTellerMutoFunctor.getPotentialEnergy
+    getVirial = AxilrodTellerMutoFunctor.getVirial
+
+    def _c_functor(self):
+        f = capi.Functor()
+        f.kind = capi.FUNCTOR_LJ_MULTISITE
+        f.flags = ((capi.FLAG_APPLY_SHIFT if self.applyShift else 0) | capi.FLAG_USE_MIXING |
+                   (capi.FLAG_CALC_GLOBALS if self.calculateGlobals else 0))
+        f.cutoff = self._cutoff
+        if self.useMixing:
+            table = _f64(self._ppl.getMixingTable())
+            ntypes = self._ppl.getNumberRegisteredSiteTypes()
+            starts, pos, types = self._ppl.getMolTables()
+        else:
+            shift6 = capi.load().apb_lj_calc_shift6(self._epsilon24, self._sigmaSquared, self._cutoff ** 2)
+            table = _f64([self._epsilon24, self._sigmaSquared, shift6])
+            ntypes = 1
+            ns = len(self._sitePositions)
+            starts, pos, types = np.array([0, ns]), self._sitePositions, np.zeros(ns)
+        self._keep = (table, np.ascontiguousarray(starts, dtype=np.int32), _f64(np.asarray(pos).ravel()),
+                      np.ascontiguousarray(types, dtype=np.int32))
+        f.num_types = ntypes
+        f.mixing_table = self._keep[0].ctypes.data
+        f.num_mol_types = len(self._keep[1]) - 1
+        f.site_start = self._keep[1].ctypes.data
+        f.site_positions = self._keep[2].ctypes.data
+        f.site_types = self._keep[3].ctypes.data
         return f
 
 

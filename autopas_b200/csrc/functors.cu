@@ -1,0 +1,634 @@
+// Built-in functors other than single-site Lennard-Jones, on the gpuLinkedCells container (fp64):
+//   * sphLib::SPHCalcDensityFunctor    (applicationLibrary/sph/SPHLibrary/SPHCalcDensityFunctor.h:43-63)
+//   * sphLib::SPHCalcHydroForceFunctor (applicationLibrary/sph/SPHLibrary/SPHCalcHydroForceFunctor.h:45-108)
+//     with the kernels of SPHKernels.h:37-87
+//   * mdLib::AxilrodTellerMutoFunctor  (…/molecularDynamicsLibrary/AxilrodTellerMutoFunctor.h:186-293), triwise
+//   * mdLib::LJMultisiteFunctor        (…/molecularDynamicsLibrary/LJMultisiteFunctor.h:181-274)
+// Pair set = the reference's lc_c08 / lc_c18 cell pairs (all particle pairs of cell pairs whose border distance is at most
+// the interaction length, halo-only cell pairs skipped, CellFunctor.h:173-184); one thread owns one particle i.
+// Arithmetic follows the AoS functors expression by expression; every product and sum that feeds a comparison is rounded
+// separately (__dmul_rn / __dadd_rn), like the oracle built with -ffp-contract=off.
+#include "internal.cuh"
+#include "lj_device.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// linked-cells pair walk shared by the kernels below
+// ---------------------------------------------------------------------------------------------------------------------
+struct LCWalk {
+  LCGeom g;
+  int64_t n;
+  const int32_t *own;
+  const int *slotCell, *cellStart;
+  const int *stencil;  // 3 ints per entry, entry 0 = self
+  int stencilN;
+};
+
+// Calls f(j) for every partner slot j of slot i. N3: each pair once (same cell: j > i; other cells: forward half of the
+// stencil); otherwise every j != i of all stencil cells. Dummies are skipped, and so are cell pairs in which neither
+// cell can hold owned particles.
+template <bool N3, class F>
+__device__ __forceinline__ void lcForEachPartner(const LCWalk &a, int64_t i, F &&f) {
+  const LCGeom &g = a.g;
+  const int c = a.slotCell[i];
+  const int cx = c % g.cellsPerDim[0], cy = (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+            cz = c / (g.cellsPerDim[0] * g.cellsPerDim[1]);
+  const bool canOwnI = apbCellCanOwn(g, cx, cy, cz);
+  if (!canOwnI && !N3) return;  // forces on particles of halo cells are never used
+  for (int s = 0; s < a.stencilN; ++s) {
+    const int ox = a.stencil[3 * s], oy = a.stencil[3 * s + 1], oz = a.stencil[3 * s + 2];
+    const int lin = (oz * g.cellsPerDim[1] + oy) * g.cellsPerDim[0] + ox;
+    if (N3 && lin < 0) continue;
+    const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
+    if (nx < 0 || ny < 0 || nz < 0 || nx >= g.cellsPerDim[0] || ny >= g.cellsPerDim[1] || nz >= g.cellsPerDim[2]) continue;
+    if (!canOwnI && !apbCellCanOwn(g, nx, ny, nz)) continue;
+    const int c2 = c + lin;
+    const int j0 = a.cellStart[c2], j1 = a.cellStart[c2 + 1];
+    for (int j = j0; j < j1; ++j) {
+      if (s == 0 && (N3 ? j <= i : j == i)) continue;
+      if (a.own[j] == APB_OWN_DUMMY) continue;
+      f(j);
+    }
+  }
+}
+
+static LCWalk makeWalk(apb_handle h) {
+  LCWalk w;
+  w.g = h->lc;
+  w.n = h->nslots;
+  w.own = h->own;
+  w.slotCell = static_cast<const int *>(h->slotCell.p);
+  w.cellStart = static_cast<const int *>(h->start.p);
+  w.stencil = static_cast<const int *>(h->stencilDev.p);
+  w.stencilN = h->stencilN;
+  return w;
+}
+
+__device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SPH kernels (SPHKernels.h:37-87)
+// ---------------------------------------------------------------------------------------------------------------------
+#define SPH_SUPPORT 2.5
+#define SPH_PI 3.14159265358979323846
+
+__device__ __forceinline__ double sphW(double dr2, double h) {
+  const double H = SPH_SUPPORT * h;
+  if (dr2 < __dmul_rn(H, H)) {
+    const double s = sqrt(dr2) / H;
+    const double s1 = 1.0 - s;
+    const double s2 = fmax(0., 0.5 - s);
+    double r = __dadd_rn(__dmul_rn(__dmul_rn(s1, s1), s1), -__dmul_rn(4.0, __dmul_rn(__dmul_rn(s2, s2), s2)));
+    r = __dmul_rn(r, 16.0 / SPH_PI / __dmul_rn(__dmul_rn(H, H), H));
+    return r;
+  }
+  return 0.;
+}
+
+// gradW(dr, h) = dr * scale; returns scale
+__device__ __forceinline__ double sphGradWScale(double drabs, double h) {
+  const double H = SPH_SUPPORT * h;
+  const double s = drabs / H;
+  const double s1 = (1.0 - s < 0) ? 0 : 1.0 - s;
+  const double s2 = (0.5 - s < 0) ? 0 : 0.5 - s;
+  double r = __dadd_rn(__dmul_rn(-3.0, __dmul_rn(s1, s1)), __dmul_rn(12.0, __dmul_rn(s2, s2)));
+  r = __dmul_rn(r, 16.0 / SPH_PI / __dmul_rn(__dmul_rn(H, H), H));
+  return r / __dadd_rn(__dmul_rn(drabs, H), __dmul_rn(1.0e-6, h));
+}
+
+struct SPHArgs {
+  LCWalk w;
+  const double *x, *y, *z, *vx, *vy, *vz, *mass, *smth, *pressure, *snd;
+  double *density, *ax, *ay, *az, *engDot, *vsigmax;
+};
+
+// SPHCalcDensityFunctor::AoSFunctor (:43-63): rho_i += m_j W(dr, h_i); newton3: rho_j += m_i W(dr, h_j)
+template <bool N3>
+__global__ void __launch_bounds__(128) kSPHDensityLC(SPHArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= a.w.n || a.w.own[i] == APB_OWN_DUMMY) return;
+  const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
+  double rho = 0.;
+  lcForEachPartner<N3>(a.w, i, [&](int j) {
+    const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+    const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+    rho += __dmul_rn(a.mass[j], sphW(dr2, hi));
+    if (N3) {
+      const double d2 = __dmul_rn(mi, sphW(dr2, a.smth[j]));
+      if (d2 != 0.) atomicAdd(a.density + j, d2);
+    }
+  });
+  if (N3)
+    atomicAdd(a.density + i, rho);
+  else
+    a.density[i] += rho;
+}
+
+__device__ __forceinline__ void atomicMaxPositive(double *addr, double v) {
+  // v_sig = c_i + c_j - 3 w with w <= 0 is positive: the bit patterns of non-negative doubles order like integers
+  atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
+}
+
+// SPHCalcHydroForceFunctor::AoSFunctor (:45-108)
+template <bool N3>
+__global__ void __launch_bounds__(128) kSPHHydroLC(SPHArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= a.w.n || a.w.own[i] == APB_OWN_DUMMY) return;
+  const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
+  const double vxi = a.vx[i], vyi = a.vy[i], vzi = a.vz[i];
+  const double rhoi = a.density[i], Pi = a.pressure[i], ci = a.snd[i];
+  const double cut = hi * SPH_SUPPORT;
+  const double cut2 = __dmul_rn(cut, cut);
+  const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
+  double accx = 0., accy = 0., accz = 0., eng = 0., vmax = a.vsigmax[i];
+  lcForEachPartner<N3>(a.w, i, [&](int j) {
+    const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+    const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+    if (dr2 >= cut2) return;
+    const double dvx = vxi - a.vx[j], dvy = vyi - a.vy[j], dvz = vzi - a.vz[j];
+    const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
+    const double drabs = sqrt(dr2);
+    const double wij = (dvdr < 0) ? dvdr / drabs : 0;
+    const double vsig = __dadd_rn(__dadd_rn(ci, a.snd[j]), -__dmul_rn(3.0, wij));
+    vmax = fmax(vmax, vsig);
+    const double rhoj = a.density[j], Pj = a.pressure[j], mj = a.mass[j];
+    const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
+    // gradW_ij = (gradW(dr, h_i) + gradW(dr, h_j)) * 0.5, component by component
+    const double gi = sphGradWScale(drabs, hi), gj = sphGradWScale(drabs, a.smth[j]);
+    const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
+    const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
+    const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
+    const double PjOverRho2 = Pj / __dmul_rn(rhoj, rhoj);
+    const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
+    const double si = __dmul_rn(scale, mj);
+    accx -= __dmul_rn(gx, si);
+    accy -= __dmul_rn(gy, si);
+    accz -= __dmul_rn(gz, si);
+    const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
+    const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
+    eng += __dmul_rn(gdv, scale2i);
+    if (N3) {
+      atomicMaxPositive(a.vsigmax + j, vsig);
+      const double sj = __dmul_rn(scale, mi);
+      atomicAdd(a.ax + j, __dmul_rn(gx, sj));
+      atomicAdd(a.ay + j, __dmul_rn(gy, sj));
+      atomicAdd(a.az + j, __dmul_rn(gz, sj));
+      const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
+      atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
+    }
+  });
+  if (N3) {
+    atomicAdd(a.ax + i, accx);
+    atomicAdd(a.ay + i, accy);
+    atomicAdd(a.az + i, accz);
+    atomicAdd(a.engDot + i, eng);
+    atomicMaxPositive(a.vsigmax + i, vmax);
+  } else {
+    a.ax[i] += accx;
+    a.ay[i] += accy;
+    a.az[i] += accz;
+    a.engDot[i] += eng;
+    a.vsigmax[i] = vmax;
+  }
+}
+
+static int computeSPH(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
+  if (h->cfg.particle_kind != APB_PARTICLE_SPH) return h->fail(APB_ERR_NOT_APPLICABLE, "SPH functors need SPHParticle storage");
+  if (h->cfg.container != APB_CONTAINER_LINKED_CELLS)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "SPH functors run on gpuLinkedCells (gpulc_c08 / gpulc_c18)");
+  if (out) std::memset(out, 0, sizeof(*out));
+  const int64_t n = h->nslots;
+  if (n == 0) return APB_OK;
+  SPHArgs a;
+  a.w = makeWalk(h);
+  a.x = h->col[APB_COL_X];
+  a.y = h->col[APB_COL_Y];
+  a.z = h->col[APB_COL_Z];
+  a.vx = h->col[APB_COL_VX];
+  a.vy = h->col[APB_COL_VY];
+  a.vz = h->col[APB_COL_VZ];
+  a.mass = h->col[APB_COL_MASS];
+  a.smth = h->col[APB_COL_SMTH];
+  a.pressure = h->col[APB_COL_PRESSURE];
+  a.snd = h->col[APB_COL_SNDSPEED];
+  a.density = h->col[APB_COL_DENSITY];
+  a.ax = h->col[APB_COL_FX];
+  a.ay = h->col[APB_COL_FY];
+  a.az = h->col[APB_COL_FZ];
+  a.engDot = h->col[APB_COL_ENGDOT];
+  a.vsigmax = h->col[APB_COL_VSIGMAX];
+  const int block = 128, grid = apbDivUp(n, block);
+  ++h->launchCount;
+  if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
+    if (newton3)
+      kSPHDensityLC<true><<<grid, block, 0, h->stream>>>(a);
+    else
+      kSPHDensityLC<false><<<grid, block, 0, h->stream>>>(a);
+  } else {
+    if (newton3)
+      kSPHHydroLC<true><<<grid, block, 0, h->stream>>>(a);
+    else
+      kSPHHydroLC<false><<<grid, block, 0, h->stream>>>(a);
+  }
+  APB_CUDA(cudaGetLastError());
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Axilrod-Teller-Muto (triwise). newton3 off: every particle i evaluates the triplets (i, j, k), j < k, of its own
+// neighbourhood and receives its force (the reference's lc_c01 calls the functor three times per triplet with rotated
+// roles, CellFunctor3B.h:267-273). Three kernels: neighbours of i within the cutoff (count, fill), then the triplets.
+// ---------------------------------------------------------------------------------------------------------------------
+struct ATMArgs {
+  LCWalk w;
+  const double *x, *y, *z;
+  double *fx, *fy, *fz;
+  const int32_t *type;
+  double cutoff2, nu;
+  const double *nuMix;  // [T*T*T] or null
+  int T;
+  int *nbrCount;  // per slot
+  int *nbr;       // [cap][n] (entry-major: coalesced across threads)
+  int cap;
+  int *maxCount;
+  LJStats *partials;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) kATMNeighbors(ATMArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int cnt = 0;
+  if (i < a.w.n && a.w.own[i] != APB_OWN_DUMMY) {
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+    lcForEachPartner<false>(a.w, i, [&](int j) {
+      const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+      if (dot3(drx, dry, drz, drx, dry, drz) <= a.cutoff2) {
+        if (FILL) a.nbr[static_cast<size_t>(cnt) * a.w.n + i] = j;
+        ++cnt;
+      }
+    });
+  }
+  if (!FILL) {
+    if (i < a.w.n) a.nbrCount[i] = cnt;
+    int m = cnt;
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(a.maxCount, m);
+  }
+}
+
+template <bool MIX, bool STATS>
+__global__ void __launch_bounds__(128) kATMTriplets(ATMArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  LJStats st;
+  ljStatsZero(st);
+  if (i < a.w.n && a.w.own[i] != APB_OWN_DUMMY) {
+    const int cnt = a.nbrCount[i];
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+    const int ti = MIX ? a.type[i] : 0;
+    const bool owned = a.w.own[i] == APB_OWN_OWNED;
+    double Fx = 0., Fy = 0., Fz = 0.;
+    for (int p = 0; p < cnt; ++p) {
+      const int j = a.nbr[static_cast<size_t>(p) * a.w.n + i];
+      const double xj = a.x[j], yj = a.y[j], zj = a.z[j];
+      const double ijx = xj - xi, ijy = yj - yi, ijz = zj - zi;
+      const double d2ij = dot3(ijx, ijy, ijz, ijx, ijy, ijz);
+      for (int q = p + 1; q < cnt; ++q) {
+        const int k = a.nbr[static_cast<size_t>(q) * a.w.n + i];
+        const double xk = a.x[k], yk = a.y[k], zk = a.z[k];
+        const double jkx = xk - xj, jky = yk - yj, jkz = zk - zj;
+        const double d2jk = dot3(jkx, jky, jkz, jkx, jky, jkz);
+        if (STATS) ++st.dist;
+        if (d2jk > a.cutoff2) continue;  // d2ij and d2ki are within the cutoff by construction of the list
+        const double kix = xi - xk, kiy = yi - yk, kiz = zi - zk;
+        const double d2ki = dot3(kix, kiy, kiz, kix, kiy, kiz);
+        double nu = a.nu;
+        if (MIX) nu = __ldg(a.nuMix + (static_cast<size_t>(ti) * a.T + a.type[j]) * a.T + a.type[k]);
+        // AxilrodTellerMutoFunctor.h:217-251
+        const double all2 = d2ij * d2jk * d2ki;
+        const double all5 = all2 * all2 * sqrt(all2);
+        const double factor = 3.0 * nu / all5;
+        const double IJdKI = dot3(ijx, ijy, ijz, kix, kiy, kiz);
+        const double IJdJK = dot3(ijx, ijy, ijz, jkx, jky, jkz);
+        const double JKdKI = dot3(jkx, jky, jkz, kix, kiy, kiz);
+        const double allDots = IJdKI * IJdJK * JKdKI;
+        const double cJK = IJdKI * (IJdJK - JKdKI);
+        const double cIJ = IJdJK * JKdKI - d2jk * d2ki + 5.0 * allDots / d2ij;
+        const double cKI = -IJdJK * JKdKI + d2ij * d2jk - 5.0 * allDots / d2ki;
+        const double fx = (jkx * cJK + ijx * cIJ + kix * cKI) * factor;
+        const double fy = (jky * cJK + ijy * cIJ + kiy * cKI) * factor;
+        const double fz = (jkz * cJK + ijz * cIJ + kiz * cKI) * factor;
+        Fx += fx;
+        Fy += fy;
+        Fz += fz;
+        if (STATS) {
+          ++st.kNoN3;
+          ++st.gNoN3;
+          if (owned) {
+            // potentialEnergy3 = factor (allDistsSquared - 3 allDotProducts); virial = f_i * r_i (:269-275)
+            st.upot += factor * (all2 - 3.0 * allDots);
+            st.vir[0] += fx * xi;
+            st.vir[1] += fy * yi;
+            st.vir[2] += fz * zi;
+          }
+        }
+      }
+    }
+    a.fx[i] += Fx;
+    a.fy[i] += Fy;
+    a.fz[i] += Fz;
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
+int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f, apb_traversal_result *out);
+
+static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
+  if (h->cfg.particle_kind != APB_PARTICLE_LJ) return h->fail(APB_ERR_NOT_APPLICABLE, "AxilrodTellerMutoFunctor needs MoleculeLJ particles");
+  // the reference offers triwise traversals for LinkedCells / DirectSum only (CompatibleTraversals.h:219-231)
+  if (h->cfg.container != APB_CONTAINER_LINKED_CELLS)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "triwise functors run on gpuLinkedCells only");
+  if (newton3)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "the GPU triwise traversal evaluates every particle's own triplets (newton3 off)");
+  if (!(f->cutoff > 0.) || f->cutoff > h->cfg.cutoff)
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "functor cutoff must be in (0, container cutoff]");
+  const bool mix = f->flags & APB_FUNCTOR_USE_MIXING;
+  const bool stats = f->flags & (APB_FUNCTOR_CALC_GLOBALS | APB_FUNCTOR_COUNT_FLOPS);
+  const int64_t n = h->nslots;
+  if (n == 0) return apbFinishStats(h, 0, stats, f, out);
+  ATMArgs a;
+  a.w = makeWalk(h);
+  a.x = h->col[APB_COL_X];
+  a.y = h->col[APB_COL_Y];
+  a.z = h->col[APB_COL_Z];
+  a.fx = h->col[APB_COL_FX];
+  a.fy = h->col[APB_COL_FY];
+  a.fz = h->col[APB_COL_FZ];
+  a.type = h->type;
+  a.cutoff2 = f->cutoff * f->cutoff;
+  a.nu = f->nu;
+  a.nuMix = nullptr;
+  a.T = 0;
+  if (mix) {
+    // mixing: mixing_table holds nu_ijk = cbrt(nu_i nu_j nu_k) row-major [T*T*T] (ParticlePropertiesLibrary.h:460-470)
+    if (f->num_types <= 0 || !f->mixing_table) return h->fail(APB_ERR_INVALID_ARGUMENT, "ATM mixing needs num_types and a nu table");
+    const size_t cnt = static_cast<size_t>(f->num_types) * f->num_types * f->num_types;
+    APB_CHECK(apbEnsure(h, h->mixDev, cnt * 8));
+    APB_CUDA(cudaMemcpyAsync(h->mixDev.p, f->mixing_table, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+    APB_CUDA(cudaStreamSynchronize(h->stream));
+    h->mixHostCache.clear();
+    a.nuMix = static_cast<const double *>(h->mixDev.p);
+    a.T = f->num_types;
+  }
+  const int block = 128, grid = apbDivUp(n, block);
+  APB_CHECK(apbEnsure(h, h->nbrCount, sizeof(int) * (n + 1)));
+  a.nbrCount = static_cast<int *>(h->nbrCount.p);
+  a.nbr = nullptr;
+  a.cap = 0;
+  int *maxDev = reinterpret_cast<int *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 32);
+  a.maxCount = maxDev;
+  APB_CUDA(cudaMemsetAsync(maxDev, 0, 4, h->stream));
+  ++h->launchCount, kATMNeighbors<false><<<grid, block, 0, h->stream>>>(a);
+  APB_CUDA(cudaGetLastError());
+  int cap = 0;
+  APB_CUDA(cudaMemcpyAsync(&cap, maxDev, 4, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  a.cap = cap;
+  APB_CHECK(apbEnsure(h, h->nbrList, sizeof(int) * static_cast<size_t>(std::max(cap, 1)) * n));
+  a.nbr = static_cast<int *>(h->nbrList.p);
+  if (cap > 0) {
+    ++h->launchCount, kATMNeighbors<true><<<grid, block, 0, h->stream>>>(a);
+    APB_CUDA(cudaGetLastError());
+  }
+  APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * grid));
+  a.partials = static_cast<LJStats *>(h->partials.p);
+  ++h->launchCount;
+  const int sel = (mix ? 2 : 0) | (stats ? 1 : 0);
+  switch (sel) {
+    case 0: kATMTriplets<false, false><<<grid, block, 0, h->stream>>>(a); break;
+    case 1: kATMTriplets<false, true><<<grid, block, 0, h->stream>>>(a); break;
+    case 2: kATMTriplets<true, false><<<grid, block, 0, h->stream>>>(a); break;
+    default: kATMTriplets<true, true><<<grid, block, 0, h->stream>>>(a); break;
+  }
+  APB_CUDA(cudaGetLastError());
+  return apbFinishStats(h, grid, stats, f, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LJMultisiteFunctor::AoSFunctor (LJMultisiteFunctor.h:181-274): centre-of-mass cutoff, sites rotated by the molecule's
+// quaternion (utils/Quaternion.cpp:13-46), site-site LJ without a per-site cutoff, force on the centre of mass and
+// torque r_site x f. One thread per molecule i; newton3 off evaluates both directions (like the LJ kernels).
+// ---------------------------------------------------------------------------------------------------------------------
+#define MS_MAX_SITES 16
+struct MSArgs {
+  LCWalk w;
+  const double *x, *y, *z, *q0, *q1, *q2, *q3;
+  double *fx, *fy, *fz, *tx, *ty, *tz;
+  const int32_t *type;
+  double cutoff2;
+  const int *siteStart;
+  const double *sitePos;
+  const int *siteType;
+  const double *mix;  // [T*T][3] = {eps24, sigma2, shift6}
+  int T;
+  int applyShift;
+  LJStats *partials;
+};
+
+// autopas::utils::quaternion::rotateVectorOfPositions (Quaternion.cpp:13-46): rotation matrix from (q0..q3) applied to p
+__device__ __forceinline__ void msRotate(double q0, double q1, double q2, double q3, double px, double py, double pz,
+                                         double &rx, double &ry, double &rz) {
+  const double q00 = q0 * q0, q01 = q0 * q1, q02 = q0 * q2, q03 = q0 * q3;
+  const double q11 = q1 * q1, q12 = q1 * q2, q13 = q1 * q3, q22 = q2 * q2, q23 = q2 * q3, q33 = q3 * q3;
+  const double r00 = q00 + q11 - q22 - q33, r01 = 2. * (q12 - q03), r02 = 2. * (q13 + q02);
+  const double r10 = 2. * (q12 + q03), r11 = q00 - q11 + q22 - q33, r12 = 2. * (q23 - q01);
+  const double r20 = 2. * (q13 - q02), r21 = 2. * (q23 + q01), r22 = q00 - q11 - q22 + q33;
+  rx = r00 * px + r01 * py + r02 * pz;
+  ry = r10 * px + r11 * py + r12 * pz;
+  rz = r20 * px + r21 * py + r22 * pz;
+}
+
+template <bool STATS, bool N3>
+__global__ void __launch_bounds__(128) kLJMultisiteLC(MSArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  LJStats st;
+  ljStatsZero(st);
+  if (i < a.w.n && a.w.own[i] != APB_OWN_DUMMY) {
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+    const int mi = a.type[i];
+    const int sA0 = a.siteStart[mi], nA = a.siteStart[mi + 1] - sA0;
+    double rAx[MS_MAX_SITES], rAy[MS_MAX_SITES], rAz[MS_MAX_SITES];
+    for (int s = 0; s < nA; ++s)
+      msRotate(a.q0[i], a.q1[i], a.q2[i], a.q3[i], a.sitePos[3 * (sA0 + s)], a.sitePos[3 * (sA0 + s) + 1],
+               a.sitePos[3 * (sA0 + s) + 2], rAx[s], rAy[s], rAz[s]);
+    const double wI = a.w.own[i] == APB_OWN_OWNED ? 1. : 0.;
+    double Fx = 0., Fy = 0., Fz = 0., Tx = 0., Ty = 0., Tz = 0.;
+    lcForEachPartner<N3>(a.w, i, [&](int j) {
+      const double dcx = xi - a.x[j], dcy = yi - a.y[j], dcz = zi - a.z[j];
+      if (dot3(dcx, dcy, dcz, dcx, dcy, dcz) > a.cutoff2) return;  // centre-of-mass cutoff (:191)
+      const int mj = a.type[j];
+      const int sB0 = a.siteStart[mj], nB = a.siteStart[mj + 1] - sB0;
+      const double wJ = a.w.own[j] == APB_OWN_OWNED ? 1. : 0.;
+      double FBx = 0., FBy = 0., FBz = 0., TBx = 0., TBy = 0., TBz = 0.;
+      for (int sb = 0; sb < nB; ++sb) {
+        double rBx, rBy, rBz;
+        msRotate(a.q0[j], a.q1[j], a.q2[j], a.q3[j], a.sitePos[3 * (sB0 + sb)], a.sitePos[3 * (sB0 + sb) + 1],
+                 a.sitePos[3 * (sB0 + sb) + 2], rBx, rBy, rBz);
+        const int tb = a.siteType[sB0 + sb];
+        for (int sa = 0; sa < nA; ++sa) {
+          // displacement between the sites: dr_CoM + r_siteA - r_siteB (:218-220)
+          const double drx = (dcx - rBx) + rAx[sa], dry = (dcy - rBy) + rAy[sa], drz = (dcz - rBz) + rAz[sa];
+          const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+          const double *m = a.mix + 3 * (static_cast<size_t>(a.siteType[sA0 + sa]) * a.T + tb);
+          const double e24 = __ldg(m), s2 = __ldg(m + 1), shift6 = a.applyShift ? __ldg(m + 2) : 0.;
+          const double inv = 1. / dr2;
+          const double lj2 = s2 * inv;
+          const double lj6 = lj2 * lj2 * lj2;
+          const double lj12 = lj6 * lj6;
+          const double lj12m6 = lj12 - lj6;
+          const double fac = e24 * (lj12 + lj12m6) * inv;
+          const double fx = drx * fac, fy = dry * fac, fz = drz * fac;
+          Fx += fx;
+          Fy += fy;
+          Fz += fz;
+          // torque on A: r_siteA x f (:236-238)
+          Tx += rAy[sa] * fz - rAz[sa] * fy;
+          Ty += rAz[sa] * fx - rAx[sa] * fz;
+          Tz += rAx[sa] * fy - rAy[sa] * fx;
+          if (N3) {
+            FBx -= fx;
+            FBy -= fy;
+            FBz -= fz;
+            TBx -= rBy * fz - rBz * fy;
+            TBy -= rBz * fx - rBx * fz;
+            TBz -= rBx * fy - rBy * fx;
+          }
+          if (STATS) {
+            const double w = N3 ? wI + wJ : wI;
+            st.upot += (e24 * lj12m6 + shift6) * w;
+            st.vir[0] += drx * fx * w;
+            st.vir[1] += dry * fy * w;
+            st.vir[2] += drz * fz * w;
+          }
+        }
+      }
+      if (N3) {
+        atomicAdd(a.fx + j, FBx);
+        atomicAdd(a.fy + j, FBy);
+        atomicAdd(a.fz + j, FBz);
+        atomicAdd(a.tx + j, TBx);
+        atomicAdd(a.ty + j, TBy);
+        atomicAdd(a.tz + j, TBz);
+      }
+    });
+    if (N3) {
+      atomicAdd(a.fx + i, Fx);
+      atomicAdd(a.fy + i, Fy);
+      atomicAdd(a.fz + i, Fz);
+      atomicAdd(a.tx + i, Tx);
+      atomicAdd(a.ty + i, Ty);
+      atomicAdd(a.tz + i, Tz);
+    } else {
+      a.fx[i] += Fx;
+      a.fy[i] += Fy;
+      a.fz[i] += Fz;
+      a.tx[i] += Tx;
+      a.ty[i] += Ty;
+      a.tz[i] += Tz;
+    }
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
+static int computeMultisite(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
+  if (h->cfg.particle_kind != APB_PARTICLE_MULTISITE)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "LJMultisiteFunctor needs MultisiteMoleculeLJ storage");
+  if (h->cfg.container != APB_CONTAINER_LINKED_CELLS)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "LJMultisiteFunctor runs on gpuLinkedCells (gpulc_c08 / gpulc_c18)");
+  if (!(f->cutoff > 0.) || f->cutoff > h->cfg.cutoff)
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "functor cutoff must be in (0, container cutoff]");
+  if (f->num_mol_types <= 0 || !f->site_start || !f->site_positions || !f->site_types || f->num_types <= 0 || !f->mixing_table)
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "LJMultisiteFunctor needs the site tables and the site-type mixing table");
+  const bool stats = f->flags & APB_FUNCTOR_CALC_GLOBALS;
+  const int64_t n = h->nslots;
+  if (n == 0) return apbFinishStats(h, 0, stats, f, out);
+  const int nMol = f->num_mol_types;
+  const int nSites = f->site_start[nMol];
+  for (int m = 0; m < nMol; ++m)
+    if (f->site_start[m + 1] - f->site_start[m] > MS_MAX_SITES || f->site_start[m + 1] < f->site_start[m])
+      return h->fail(APB_ERR_NOT_APPLICABLE, "molecules with more than 16 sites are not supported");
+  // one device buffer: mixing table | site positions | site start | site types
+  const size_t mixBytes = sizeof(double) * 3 * f->num_types * f->num_types;
+  const size_t posBytes = sizeof(double) * 3 * nSites;
+  const size_t startBytes = sizeof(int) * (nMol + 1), typeBytes = sizeof(int) * nSites;
+  APB_CHECK(apbEnsure(h, h->mixDev, mixBytes + posBytes + startBytes + typeBytes + 64));
+  char *base = static_cast<char *>(h->mixDev.p);
+  APB_CUDA(cudaMemcpyAsync(base, f->mixing_table, mixBytes, cudaMemcpyHostToDevice, h->stream));
+  APB_CUDA(cudaMemcpyAsync(base + mixBytes, f->site_positions, posBytes, cudaMemcpyHostToDevice, h->stream));
+  APB_CUDA(cudaMemcpyAsync(base + mixBytes + posBytes, f->site_start, startBytes, cudaMemcpyHostToDevice, h->stream));
+  APB_CUDA(cudaMemcpyAsync(base + mixBytes + posBytes + startBytes, f->site_types, typeBytes, cudaMemcpyHostToDevice, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  h->mixHostCache.clear();
+  MSArgs a;
+  a.w = makeWalk(h);
+  a.x = h->col[APB_COL_X];
+  a.y = h->col[APB_COL_Y];
+  a.z = h->col[APB_COL_Z];
+  a.q0 = h->col[APB_COL_Q0];
+  a.q1 = h->col[APB_COL_Q1];
+  a.q2 = h->col[APB_COL_Q2];
+  a.q3 = h->col[APB_COL_Q3];
+  a.fx = h->col[APB_COL_FX];
+  a.fy = h->col[APB_COL_FY];
+  a.fz = h->col[APB_COL_FZ];
+  a.tx = h->col[APB_COL_TX];
+  a.ty = h->col[APB_COL_TY];
+  a.tz = h->col[APB_COL_TZ];
+  a.type = h->type;
+  a.cutoff2 = f->cutoff * f->cutoff;
+  a.mix = reinterpret_cast<const double *>(base);
+  a.sitePos = reinterpret_cast<const double *>(base + mixBytes);
+  a.siteStart = reinterpret_cast<const int *>(base + mixBytes + posBytes);
+  a.siteType = reinterpret_cast<const int *>(base + mixBytes + posBytes + startBytes);
+  a.T = f->num_types;
+  a.applyShift = (f->flags & APB_FUNCTOR_APPLY_SHIFT) ? 1 : 0;
+  const int block = 128, grid = apbDivUp(n, block);
+  APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * grid));
+  a.partials = static_cast<LJStats *>(h->partials.p);
+  ++h->launchCount;
+  const int sel = (stats ? 2 : 0) | (newton3 ? 1 : 0);
+  switch (sel) {
+    case 0: kLJMultisiteLC<false, false><<<grid, block, 0, h->stream>>>(a); break;
+    case 1: kLJMultisiteLC<false, true><<<grid, block, 0, h->stream>>>(a); break;
+    case 2: kLJMultisiteLC<true, false><<<grid, block, 0, h->stream>>>(a); break;
+    default: kLJMultisiteLC<true, true><<<grid, block, 0, h->stream>>>(a); break;
+  }
+  APB_CUDA(cudaGetLastError());
+  return apbFinishStats(h, grid, stats, f, out);
+}
+
+int apbComputeOtherFunctor(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
+  switch (f->kind) {
+    case APB_FUNCTOR_SPH_DENSITY:
+    case APB_FUNCTOR_SPH_HYDRO: return computeSPH(h, f, newton3, out);
+    case APB_FUNCTOR_ATM: return computeATM(h, f, newton3, out);
+    case APB_FUNCTOR_LJ_MULTISITE: return computeMultisite(h, f, newton3, out);
+    default: return h->fail(APB_ERR_NOT_APPLICABLE, "functor kind not implemented on the GPU path");
+  }
+}
+
+// AxilrodTellerMutoFunctor::endTraversal (:360-386) + getPotentialEnergy / getVirial (:392-420)
+extern "C" void apb_atm_end_traversal(const apb_traversal_result *raw, double *upot, double *virial) {
+  double u = raw->upot_sum;
+  u /= 3.;
+  u /= 3.;
+  if (upot) *upot = u;
+  if (virial) *virial = raw->virial_sum[0] + raw->virial_sum[1] + raw->virial_sum[2];
+}
+
+// AxilrodTellerMutoFunctor::getNumFLOPs (:476-486)
+extern "C" uint64_t apb_atm_num_flops(const apb_traversal_result *r) {
+  return r->num_dist_calls * 24 + r->num_kernel_calls_n3 * 100 + r->num_kernel_calls_no_n3 * 59 +
+         r->num_global_calcs_n3 * 24 + r->num_global_calcs_no_n3 * 10;
+}

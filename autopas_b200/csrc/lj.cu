@@ -404,6 +404,7 @@ int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3,
 }
 
 int apbCheckTraversal(apb_handle h, int traversal, int newton3);
+int apbComputeOtherFunctor(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out);
 
 extern "C" int apb_compute_interactions(apb_handle h, int32_t traversal, const apb_functor *functor, int32_t newton3,
                                         apb_traversal_result *out) {
@@ -422,6 +423,6 @@ extern "C" int apb_compute_interactions(apb_handle h, int32_t traversal, const a
         return h->fail(APB_ERR_NOT_APPLICABLE, "LJFunctor needs MoleculeLJ particles");
       return apbComputeLJ(h, traversal, functor, newton3, out);
     default:
-      return h->fail(APB_ERR_NOT_APPLICABLE, "functor kind not implemented on the GPU path");
+      return apbComputeOtherFunctor(h, functor, newton3, out);
   }
 }

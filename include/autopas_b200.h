@@ -115,6 +115,13 @@ typedef struct {
   int32_t num_types;
   const double *mixing_table;
   double nu; /* ATM, non-mixing: AxilrodTellerMutoFunctor::setParticleProperties(nu) */
+  /* LJMultisiteFunctor: site geometry of ParticlePropertiesLibrary::getSitePositions / getSiteTypes
+   * (ParticlePropertiesLibrary.h); molecule type m owns sites [site_start[m], site_start[m + 1]). Site types index
+   * the mixing table above (num_types = number of site types). */
+  int32_t num_mol_types;
+  const int32_t *site_start;    /* num_mol_types + 1 entries */
+  const double *site_positions; /* 3 doubles per site: unrotated position relative to the centre of mass */
+  const int32_t *site_types;    /* per site */
 } apb_functor;
 
 /* raw accumulators as the reference functor keeps them before endTraversal (LJFunctor.h:1121-1136, 1145-1195) */
@@ -210,6 +217,11 @@ int apb_make_lj_mixing_table(int32_t num_types, const double *epsilon, const dou
                              double *out_table);
 /* ParticlePropertiesLibrary::calcShift6 (:576-582) */
 double apb_lj_calc_shift6(double epsilon24, double sigma_squared, double cutoff_squared);
+/* AxilrodTellerMutoFunctor::endTraversal + getPotentialEnergy / getVirial (AxilrodTellerMutoFunctor.h:360-420):
+ * Upot = sum / 9, virial = vx + vy + vz (not scaled) */
+void apb_atm_end_traversal(const apb_traversal_result *raw, double *out_upot, double *out_virial);
+/* AxilrodTellerMutoFunctor::getNumFLOPs (:476-480): 24 D + 59 K_noN3 + 100 K_N3 + 10 G_noN3 + 24 G_N3 */
+uint64_t apb_atm_num_flops(const apb_traversal_result *raw);
 
 /* ---- device-resident simulation loop (SURVEY §8 e, f2): no host round trip between force steps ------------------- */
 /* Störmer-Verlet halves of examples/md-flexible/src/TimeDiscretization.cpp:

@@ -248,3 +248,136 @@ def ref_lj_vcl(x, y, z, types, own, box_min, box_max, cutoff, skin, cluster_size
             "tower_side": tuple(side), "tower_of_particle": tower_of_particle[:n],
             "cluster_particles": cluster_particles[:ncl * M].reshape(ncl, M) if ncl else np.zeros((0, M), np.int64),
             "cluster_tower": cluster_tower[:ncl], "pairs": pairs[:npairs]}
+
+
+# ---- functors other than single-site LJ (oracle/functors_oracle.c, oracle/ref_driver_extra.cpp, _multisite.cpp) -----
+_REF_MS = os.path.join(_HERE, "_ref", "libautopas_ref_ms.so")
+_ref_ms = None
+
+
+def have_ref_ms():
+    return os.path.exists(_REF_MS)
+
+
+def ref_ms():
+    global _ref_ms
+    if _ref_ms is None:
+        _ref_ms = ctypes.CDLL(_REF_MS)
+    return _ref_ms
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+_D = ctypes.c_double
+
+
+def sph_W(dr2, h):
+    fn = lib().orc_sph_W
+    fn.restype = _D
+    fn.argtypes = [_D, _D]
+    return fn(float(dr2), float(h))
+
+
+def sph_gradW(dr, h):
+    out = np.zeros(3)
+    lib().orc_sph_gradW(_p(_f64(dr)), _D(float(h)), _p(out))
+    return out
+
+
+def sph_density(pos, mass, smth, own):
+    n = len(pos)
+    x, y, z = (_f64(pos[:, d]) for d in range(3))
+    rho, scale = np.zeros(n), np.zeros(n)
+    lib().orc_sph_density(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(_f64(mass)), _p(_f64(smth)), _p(_i64(own)), _p(rho),
+                          _p(scale))
+    return rho, scale
+
+
+def sph_hydro(pos, vel, mass, smth, density, pressure, snd, own):
+    n = len(pos)
+    cols = [_f64(pos[:, d]) for d in range(3)] + [_f64(vel[:, d]) for d in range(3)]
+    acc, eng, vsig, scale = np.zeros(3 * n), np.zeros(n), np.zeros(n), np.zeros(n)
+    lib().orc_sph_hydro(ctypes.c_int64(n), *[_p(c) for c in cols], _p(_f64(mass)), _p(_f64(smth)), _p(_f64(density)),
+                        _p(_f64(pressure)), _p(_f64(snd)), _p(_i64(own)), None, _p(acc), _p(eng), _p(vsig), _p(scale))
+    return acc.reshape(n, 3), eng, vsig, scale
+
+
+def atm(pos, types, own, cutoff, nu=None, nu_of_type=None):
+    """Returns dict(f, scale, upot3_sum, virial_sum[3], kernel_calls); Upot = upot3_sum / 9 (ATM endTraversal)."""
+    n = len(pos)
+    x, y, z = (_f64(pos[:, d]) for d in range(3))
+    t = _i64(np.zeros(n) if types is None else types)
+    f, scale, res = np.zeros(3 * n), np.zeros(n), np.zeros(5)
+    if nu_of_type is not None:
+        v = np.asarray(nu_of_type, dtype=np.float64)
+        mix = _f64(np.cbrt(v[:, None, None] * v[None, :, None] * v[None, None, :]).ravel())
+        T, mixp, nu0 = len(v), _p(mix), 0.0
+    else:
+        T, mixp, nu0 = 0, None, float(nu)
+    lib().orc_atm(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(t), _p(_i64(own)), _D(float(cutoff)), _D(nu0),
+                  ctypes.c_int(T), mixp, _p(f), _p(scale), _p(res))
+    return {"f": f.reshape(n, 3), "scale": scale, "upot3_sum": res[0], "virial_sum": res[1:4].copy(),
+            "kernel_calls": int(res[4])}
+
+
+def multisite(pos, quat, mol_type, own, cutoff, shift, eps, sigma, site_start, site_pos, site_type):
+    n = len(pos)
+    x, y, z = (_f64(pos[:, d]) for d in range(3))
+    mix = mixing_table(eps, sigma, cutoff)
+    f, tq, scale, res = np.zeros(3 * n), np.zeros(3 * n), np.zeros(n), np.zeros(4)
+    keep = (_f64(np.asarray(quat).ravel()), _i64(mol_type), _i64(own), _f64(mix), _i32(site_start),
+            _f64(np.asarray(site_pos).ravel()), _i32(site_type))
+    lib().orc_multisite(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(keep[0]), _p(keep[1]), _p(keep[2]),
+                        _D(float(cutoff)), ctypes.c_int(1 if shift else 0), ctypes.c_int(len(eps)), _p(keep[3]),
+                        _p(keep[4]), _p(keep[5]), _p(keep[6]), _p(f), _p(tq), _p(scale), _p(res))
+    return {"f": f.reshape(n, 3), "torque": tq.reshape(n, 3), "scale": scale, "upot6_sum": res[0],
+            "virial_sum": res[1:4].copy()}
+
+
+def ref_sph(pos, vel, mass, smth, density, pressure, snd, own, box_min, box_max, cutoff, skin, which, newton3):
+    n = len(pos)
+    cols = [_f64(pos[:, d]) for d in range(3)] + [_f64(vel[:, d]) for d in range(3)]
+    rho, acc, eng, vsig = np.zeros(n), np.zeros(3 * n), np.zeros(n), np.zeros(n)
+    rc = ref().ref_sph(ctypes.c_int64(n), *[_p(c) for c in cols], _p(_f64(mass)), _p(_f64(smth)), _p(_f64(density)),
+                       _p(_f64(pressure)), _p(_f64(snd)), _p(_i64(own)), _p(_f64(box_min)), _p(_f64(box_max)),
+                       _D(float(cutoff)), _D(float(skin)), ctypes.c_int(which), ctypes.c_int(1 if newton3 else 0),
+                       _p(rho), _p(acc), _p(eng), _p(vsig))
+    if rc != 0:
+        raise RuntimeError("reference SPH run failed")
+    return {"density": rho, "acc": acc.reshape(n, 3), "engdot": eng, "vsigmax": vsig}
+
+
+def ref_atm(pos, types, own, box_min, box_max, cutoff, skin, nu=None, nu_of_type=None):
+    n = len(pos)
+    x, y, z = (_f64(pos[:, d]) for d in range(3))
+    t = _i64(np.zeros(n) if types is None else types)
+    f, g, flops = np.zeros(3 * n), np.zeros(2), ctypes.c_uint64(0)
+    nt = 0 if nu_of_type is None else len(nu_of_type)
+    nup = None if nu_of_type is None else _p(_f64(nu_of_type))
+    keep = _f64(nu_of_type) if nu_of_type is not None else None
+    nup = None if keep is None else _p(keep)
+    rc = ref().ref_atm(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(t), _p(_i64(own)), _p(_f64(box_min)),
+                       _p(_f64(box_max)), _D(float(cutoff)), _D(float(skin)), _D(0.0 if nu is None else float(nu)),
+                       ctypes.c_int(nt), nup, _p(f), _p(g), ctypes.byref(flops))
+    if rc != 0:
+        raise RuntimeError("reference ATM run failed")
+    return {"f": f.reshape(n, 3), "upot": g[0], "virial": g[1], "flops": flops.value}
+
+
+def ref_multisite(pos, quat, mol_type, own, box_min, box_max, cutoff, skin, shift, newton3, eps, sigma, site_start,
+                  site_pos, site_type):
+    n = len(pos)
+    x, y, z = (_f64(pos[:, d]) for d in range(3))
+    f, tq, g = np.zeros(3 * n), np.zeros(3 * n), np.zeros(2)
+    keep = (_f64(np.asarray(quat).ravel()), _i64(mol_type), _i64(own), _f64(eps), _f64(sigma), _i32(site_start),
+            _f64(np.asarray(site_pos).ravel()), _i32(site_type))
+    rc = ref_ms().ref_multisite(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(keep[0]), _p(keep[1]), _p(keep[2]),
+                                _p(_f64(box_min)), _p(_f64(box_max)), _D(float(cutoff)), _D(float(skin)),
+                                ctypes.c_int(1 if shift else 0), ctypes.c_int(1 if newton3 else 0),
+                                ctypes.c_int(len(eps)), _p(keep[3]), _p(keep[4]), ctypes.c_int(len(site_start) - 1),
+                                _p(keep[5]), _p(keep[6]), _p(keep[7]), _p(f), _p(tq), _p(g))
+    if rc != 0:
+        raise RuntimeError("reference multisite run failed")
+    return {"f": f.reshape(n, 3), "torque": tq.reshape(n, 3), "upot": g[0], "virial": g[1]}

@@ -31,7 +31,34 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.Config) == 6 * 8 + 3 * 8 + 4 * 4
     assert ctypes.sizeof(capi.TraversalResult) == 4 * 8 + 5 * 8
     assert ctypes.sizeof(capi.Geometry) == 3 * 8 + 3 * 8 + 8 + 6 * 8
-    assert ctypes.sizeof(capi.Functor) == 8 + 3 * 8 + 8 + 8 + 8
+    assert ctypes.sizeof(capi.Functor) == 8 + 3 * 8 + 8 + 8 + 8 + 8 + 3 * 8
+
+
+def test_struct_layouts_match_the_c_compiler(tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc lays them out from include/autopas_b200.h vs the ctypes mirror."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields = {"apb_config": ["cutoff", "cluster_size", "device"],
+              "apb_functor": ["cutoff", "num_types", "mixing_table", "nu", "num_mol_types", "site_start", "site_types"],
+              "apb_traversal_result": ["virial_sum", "num_dist_calls", "num_global_calcs_no_n3"],
+              "apb_geometry": ["cell_length", "num_slots", "towers_per_interaction_length"],
+              "apb_loop_params": ["mass_of_type", "num_types", "global_force", "rebuild_frequency", "newton3"]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "autopas_b200.h"', 'int main(void) {']
+    for st, fs in fields.items():
+        lines.append(f'printf("{st} %zu\\n", sizeof({st}));')
+        for f in fs:
+            lines.append(f'printf("{st}.{f} %zu\\n", offsetof({st}, {f}));')
+    lines += ['return 0; }']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    mirror = {"apb_config": capi.Config, "apb_functor": capi.Functor, "apb_traversal_result": capi.TraversalResult,
+              "apb_geometry": capi.Geometry, "apb_loop_params": capi.LoopParams}
+    for st, fs in fields.items():
+        assert int(out[st]) == ctypes.sizeof(mirror[st]), st
+        for f in fs:
+            assert int(out[f"{st}.{f}"]) == getattr(mirror[st], f).offset, f"{st}.{f}"
 
 
 def test_host_helpers_match_reference_formulas():

@@ -1,0 +1,216 @@
+"""GPU parity of the functors other than single-site LJ (autopas_b200/csrc/functors.cu) through the C ABI: against the
+CPU oracle on seeded scenarios and against fixtures produced by the unmodified reference (tests/golden/fn_*.npz).
+Error norm: |gpu - ref| <= 1e-12 * (sum of the magnitudes of the particle's contributions)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from autopas_b200 import (ApbError, AxilrodTellerMutoFunctor, GpuParticleContainer, GpuTraversal, LJMultisiteFunctor,
+                          ParticlePropertiesLibrary, SPHCalcDensityFunctor, SPHCalcHydroForceFunctor, capi)
+from functor_scenarios import atm_scenario, multisite_scenario, sph_scenario
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def close(a, b, scale, tol=1e-12):
+    a, b, s = np.asarray(a), np.asarray(b), np.asarray(scale)
+    if a.ndim == 2:
+        s = s[:, None]
+    return np.all(np.abs(a - b) <= tol * s + 1e-300)
+
+
+def make_container(s, kind, types=None):
+    c = GpuParticleContainer("gpuLinkedCells", s["box_min"], s["box_max"], s["cutoff"], s["skin"], particleKind=kind)
+    pos, own = s["pos"], s["own"]
+    ids = np.arange(len(pos))
+    o, h = own == 1, own == 2
+    t = None if types is None else np.asarray(types, dtype=np.int32)
+    c.addParticles(pos[o, 0], pos[o, 1], pos[o, 2], ids[o], None if t is None else t[o])
+    c.addHaloParticles(pos[h, 0], pos[h, 1], pos[h, 2], ids[h], None if t is None else t[h])
+    return c
+
+
+def upload_by_id(c, **columns):
+    ids, _, _ = c.downloadIds()
+    for name, values in columns.items():
+        c.uploadColumn(name, np.asarray(values, dtype=np.float64)[ids])
+    return ids
+
+
+def by_id(c, name, ids, n):
+    out = np.zeros(n)
+    out[ids] = c.downloadColumn(name)
+    return out
+
+
+def run(c, trav_name, functor, n3):
+    t = GpuTraversal(trav_name, functor, n3)
+    functor.initTraversal()
+    c.computeInteractions(t)
+    functor.endTraversal(n3)
+
+
+# ---- SPH ------------------------------------------------------------------------------------------------------------
+def _sph_gpu(s, n3, density_in=None):
+    n = len(s["pos"])
+    c = make_container(s, capi.PARTICLE_SPH)
+    c.rebuildNeighborLists(GpuTraversal("gpulc_c08", SPHCalcDensityFunctor(), n3))
+    ids = upload_by_id(c, VX=s["vel"][:, 0], VY=s["vel"][:, 1], VZ=s["vel"][:, 2], MASS=s["mass"], SMTH=s["smth"],
+                       PRESSURE=s["pressure"], SNDSPEED=s["snd"])
+    run(c, "gpulc_c08", SPHCalcDensityFunctor(), n3)
+    rho = by_id(c, "DENSITY", ids, n)
+    if density_in is None:
+        density_in = np.where(s["own"] == 1, rho, 1.0) + 0.5
+    upload_by_id(c, DENSITY=density_in)
+    run(c, "gpulc_c18", SPHCalcHydroForceFunctor(), n3)
+    acc = np.stack([by_id(c, k, ids, n) for k in ("FX", "FY", "FZ")], axis=1)
+    eng, vsig = by_id(c, "ENGDOT", ids, n), by_id(c, "VSIGMAX", ids, n)
+    c.close()
+    return rho, density_in, acc, eng, vsig
+
+
+@pytest.mark.parametrize("n3", [False, True])
+def test_sph_matches_oracle(n3):
+    s = sph_scenario(seed=31, vary_h=not n3)  # newton3 evaluates a pair once with the first particle's support
+    rho, dens_in, acc, eng, vsig = _sph_gpu(s, n3)
+    owned = s["own"] == 1
+    o_rho, sc = oracle.sph_density(s["pos"], s["mass"], s["smth"], s["own"])
+    assert close(rho[owned], o_rho[owned], sc[owned])
+    o_acc, o_eng, o_vsig, sc = oracle.sph_hydro(s["pos"], s["vel"], s["mass"], s["smth"], dens_in, s["pressure"],
+                                                s["snd"], s["own"])
+    assert close(acc[owned], o_acc[owned], sc[owned])
+    assert close(eng[owned], o_eng[owned], sc[owned] * 10)
+    np.testing.assert_allclose(vsig[owned], o_vsig[owned], rtol=1e-14)
+
+
+@pytest.mark.parametrize("n3", [0, 1])
+def test_sph_matches_reference_fixture(n3):
+    g = dict(np.load(os.path.join(GOLDEN, f"fn_sph_n3{n3}.npz")))
+    g["cutoff"], g["skin"] = float(g["cutoff"]), float(g["skin"])
+    rho, _, acc, eng, vsig = _sph_gpu(g, bool(n3), density_in=g["density_in"])
+    owned = g["own"] == 1
+    _, sc = oracle.sph_density(g["pos"], g["mass"], g["smth"], g["own"])
+    assert close(rho[owned], g["ref_density"][owned], sc[owned])
+    _, _, _, sc = oracle.sph_hydro(g["pos"], g["vel"], g["mass"], g["smth"], g["density_in"], g["pressure"], g["snd"], g["own"])
+    assert close(acc[owned], g["ref_acc"][owned], sc[owned])
+    assert close(eng[owned], g["ref_engdot"][owned], sc[owned] * 10)
+    np.testing.assert_allclose(vsig[owned], g["ref_vsigmax"][owned], rtol=1e-14)
+
+
+def test_sph_needs_sph_particles_and_linked_cells():
+    s = sph_scenario(seed=3)
+    c = make_container(s, capi.PARTICLE_LJ)
+    t = GpuTraversal("gpulc_c08", SPHCalcDensityFunctor(), False)
+    c.rebuildNeighborLists(t)
+    with pytest.raises(ApbError):
+        c.computeInteractions(t)
+    c.close()
+
+
+# ---- Axilrod-Teller-Muto --------------------------------------------------------------------------------------------
+def _atm_gpu(s, nu=None, nu_of_type=None):
+    n = len(s["pos"])
+    c = make_container(s, capi.PARTICLE_LJ, types=s["types"])
+    if nu_of_type is not None:
+        ppl = ParticlePropertiesLibrary(s["cutoff"])
+        for t, v in enumerate(nu_of_type):
+            ppl.addSiteType(t, 1.0)
+            ppl.addATMParametersToSite(t, v)
+        f = AxilrodTellerMutoFunctor(s["cutoff"], ppl, useMixing=True, calculateGlobals=True, countFLOPs=True)
+    else:
+        f = AxilrodTellerMutoFunctor(s["cutoff"], calculateGlobals=True, countFLOPs=True)
+        f.setParticleProperties(nu)
+    c.rebuildNeighborLists(GpuTraversal("gpulc_c08", f, False))
+    run(c, "gpulc_c08", f, False)
+    F = c.forcesById(n)
+    c.close()
+    return F, f
+
+
+def test_atm_matches_oracle():
+    s = atm_scenario(seed=41)
+    F, f = _atm_gpu(s, nu=0.073)
+    o = oracle.atm(s["pos"], s["types"], s["own"], s["cutoff"], nu=0.073)
+    owned = s["own"] == 1
+    assert close(F[owned], o["f"][owned], o["scale"][owned])
+    assert f.getPotentialEnergy() == pytest.approx(o["upot3_sum"] / 9.0, rel=1e-12)
+    assert f.getVirial() == pytest.approx(o["virial_sum"].sum(), rel=1e-11)
+    assert f._raw.num_kernel_calls_no_n3 == o["kernel_calls"]
+
+
+@pytest.mark.parametrize("name", ["fn_atm.npz", "fn_atm_mix.npz"])
+def test_atm_matches_reference_fixture(name):
+    g = dict(np.load(os.path.join(GOLDEN, name)))
+    g["cutoff"], g["skin"] = float(g["cutoff"]), float(g["skin"])
+    kw = dict(nu_of_type=g["nu_of_type"]) if "nu_of_type" in g else dict(nu=float(g["nu"]))
+    F, f = _atm_gpu(g, **kw)
+    o = oracle.atm(g["pos"], g["types"], g["own"], g["cutoff"], **kw)
+    owned = g["own"] == 1
+    assert close(F[owned], g["ref_f"][owned], o["scale"][owned])
+    assert f.getPotentialEnergy() == pytest.approx(float(g["ref_upot"]), rel=1e-12)
+    assert f.getVirial() == pytest.approx(float(g["ref_virial"]), rel=1e-11)
+
+
+def test_atm_newton3_is_rejected_not_emulated():
+    s = atm_scenario(seed=5)
+    c = make_container(s, capi.PARTICLE_LJ, types=s["types"])
+    f = AxilrodTellerMutoFunctor(s["cutoff"])
+    f.setParticleProperties(0.073)
+    t = GpuTraversal("gpulc_c08", f, True)
+    c.rebuildNeighborLists(t)
+    with pytest.raises(ApbError) as e:
+        c.computeInteractions(t)
+    assert e.value.code == capi.ERR_NOT_APPLICABLE
+    c.close()
+
+
+# ---- LJ multi-site --------------------------------------------------------------------------------------------------
+def _multisite_gpu(s, n3, shift=True):
+    n = len(s["pos"])
+    c = make_container(s, capi.PARTICLE_MULTISITE, types=s["mol_type"])
+    ppl = ParticlePropertiesLibrary(s["cutoff"])
+    for t, (e, sg) in enumerate(zip(s["eps"], s["sigma"])):
+        ppl.addSiteType(t, 1.0)
+        ppl.addLJParametersToSite(t, e, sg)
+    ss = list(s["site_start"])
+    for m in range(len(ss) - 1):
+        ppl.addMolType(m, list(np.asarray(s["site_type"])[ss[m]:ss[m + 1]]), np.asarray(s["site_pos"])[ss[m]:ss[m + 1]])
+    f = LJMultisiteFunctor(s["cutoff"], ppl, applyShift=shift, useMixing=True, calculateGlobals=True)
+    c.rebuildNeighborLists(GpuTraversal("gpulc_c08", f, n3))
+    q = np.asarray(s["quat"])
+    ids = upload_by_id(c, Q0=q[:, 0], Q1=q[:, 1], Q2=q[:, 2], Q3=q[:, 3])
+    run(c, "gpulc_c08", f, n3)
+    F = c.forcesById(n)
+    T = np.stack([by_id(c, k, ids, n) for k in ("TX", "TY", "TZ")], axis=1)
+    c.close()
+    return F, T, f
+
+
+@pytest.mark.parametrize("n3", [False, True])
+def test_multisite_matches_oracle(n3):
+    s = multisite_scenario(seed=51)
+    F, T, f = _multisite_gpu(s, n3)
+    o = oracle.multisite(s["pos"], s["quat"], s["mol_type"], s["own"], s["cutoff"], True, s["eps"], s["sigma"],
+                         s["site_start"], s["site_pos"], s["site_type"])
+    owned = s["own"] == 1
+    assert close(F[owned], o["f"][owned], o["scale"][owned])
+    assert close(T[owned], o["torque"][owned], o["scale"][owned])
+    assert f.getPotentialEnergy() == pytest.approx(o["upot6_sum"] * 0.5 / 6.0, rel=1e-12)
+    assert f.getVirial() == pytest.approx(o["virial_sum"].sum() * 0.5, rel=1e-12)
+
+
+@pytest.mark.parametrize("n3", [0, 1])
+def test_multisite_matches_reference_fixture(n3):
+    g = dict(np.load(os.path.join(GOLDEN, f"fn_multisite_n3{n3}.npz")))
+    g["cutoff"], g["skin"] = float(g["cutoff"]), float(g["skin"])
+    F, T, f = _multisite_gpu(g, bool(n3))
+    o = oracle.multisite(g["pos"], g["quat"], g["mol_type"], g["own"], g["cutoff"], True, g["eps"], g["sigma"],
+                         g["site_start"], g["site_pos"], g["site_type"])
+    owned = g["own"] == 1
+    assert close(F[owned], g["ref_f"][owned], o["scale"][owned])
+    assert close(T[owned], g["ref_torque"][owned], o["scale"][owned])
+    assert f.getPotentialEnergy() == pytest.approx(float(g["ref_upot"]), rel=1e-12)
+    assert f.getVirial() == pytest.approx(float(g["ref_virial"]), rel=1e-12)
