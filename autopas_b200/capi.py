@@ -18,7 +18,7 @@ CONTAINER_LINKED_CELLS, CONTAINER_VERLET_CLUSTER_LISTS = 0, 1
  TRAVERSAL_GPUVCL_C01_BALANCED, TRAVERSAL_GPUVCL_PRUNED) = range(6)
 PARTICLE_LJ, PARTICLE_MULTISITE, PARTICLE_SPH = 0, 1, 2
 FUNCTOR_LJ, FUNCTOR_LJ_MULTISITE, FUNCTOR_ATM, FUNCTOR_SPH_DENSITY, FUNCTOR_SPH_HYDRO = range(5)
-FLAG_APPLY_SHIFT, FLAG_USE_MIXING, FLAG_CALC_GLOBALS, FLAG_COUNT_FLOPS = 1, 2, 4, 8
+FLAG_APPLY_SHIFT, FLAG_USE_MIXING, FLAG_CALC_GLOBALS, FLAG_COUNT_FLOPS, FLAG_VIRIAL_TRACE = 1, 2, 4, 8, 16
 OWN_DUMMY, OWN_OWNED, OWN_HALO = 0, 1, 2
 
 COLUMNS = ["X", "Y", "Z", "VX", "VY", "VZ", "FX", "FY", "FZ", "OLDFX", "OLDFY", "OLDFZ", "Q0", "Q1", "Q2", "Q3", "TX",

@@ -104,7 +104,10 @@ class LJFunctor:
     """mdLib::LJFunctor: template flags become constructor arguments (LJFunctor.h:39-41)."""
 
     def __init__(self, cutoff, particlePropertiesLibrary=None, applyShift=False, useMixing=False,
-                 calculateGlobals=False, countFLOPs=False):
+                 calculateGlobals=False, countFLOPs=False, virialTraceOnly=False):
+        """virialTraceOnly: the device may accumulate only the sum of the three virial components, which is all
+        getVirial() returns (LJFunctor.h:719); the C++ shim sets it, the parity tests cover both settings."""
+        self.virialTraceOnly = bool(virialTraceOnly)
         if useMixing and particlePropertiesLibrary is None:
             raise ApbError(capi.ERR_INVALID_ARGUMENT, "Mixing without a ParticlePropertiesLibrary is not possible")
         if particlePropertiesLibrary is not None and not useMixing:
@@ -193,7 +196,8 @@ class LJFunctor:
         f.kind = capi.FUNCTOR_LJ
         f.flags = ((capi.FLAG_APPLY_SHIFT if self.applyShift else 0) | (capi.FLAG_USE_MIXING if self.useMixing else 0) |
                    (capi.FLAG_CALC_GLOBALS if self.calculateGlobals else 0) |
-                   (capi.FLAG_COUNT_FLOPS if self.countFLOPs else 0))
+                   (capi.FLAG_COUNT_FLOPS if self.countFLOPs else 0) |
+                   (capi.FLAG_VIRIAL_TRACE if self.virialTraceOnly else 0))
         f.cutoff = self._cutoff
         f.epsilon24 = self._epsilon24
         f.sigma_squared = self._sigmaSquared

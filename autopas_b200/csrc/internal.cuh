@@ -107,6 +107,7 @@ struct apb_handle_s {
   DevBuf result;  // apb_traversal_result on device
   DevBuf mixDev;
   std::vector<double> mixHostCache;
+  int mixHostShift = -1;  // APPLY_SHIFT bit the derived table was built with
 
   // ---- leavers (library-owned, valid until the next update_container) ----
   int64_t numLeavers = 0;

@@ -278,18 +278,42 @@ int apbPrepareLJParams(apb_handle h, const apb_functor *f, LJParams &p) {
   p.applyShift = (f->flags & APB_FUNCTOR_APPLY_SHIFT) ? 1 : 0;
   p.T = 0;
   p.mix = nullptr;
+  p.mix4 = nullptr;
+  {
+    const double s6 = p.sigma2 * p.sigma2 * p.sigma2;
+    p.k1 = 2. * p.eps24 * s6 * s6;
+    p.k2 = -p.eps24 * s6;
+    long long bits;
+    std::memcpy(&bits, &p.cutoff2, 8);
+    p.cutHiLo = static_cast<int>(bits >> 32) - 1;
+  }
   if (f->flags & APB_FUNCTOR_USE_MIXING) {
     if (f->num_types <= 0 || !f->mixing_table)
       return h->fail(APB_ERR_INVALID_ARGUMENT, "mixing functor needs num_types > 0 and a mixing table");
     const size_t cnt = static_cast<size_t>(f->num_types) * f->num_types * 3;
-    if (h->mixHostCache.size() != cnt || std::memcmp(h->mixHostCache.data(), f->mixing_table, cnt * 8) != 0) {
-      APB_CHECK(apbEnsure(h, h->mixDev, cnt * 8));
+    if (h->mixHostCache.size() != cnt || h->mixHostShift != (f->flags & APB_FUNCTOR_APPLY_SHIFT) ||
+        std::memcmp(h->mixHostCache.data(), f->mixing_table, cnt * 8) != 0) {
+      // device buffer: the caller's table | the derived {K1, K2, K1 / 2, shift6} table (32-byte entries)
+      const size_t pairs = cnt / 3, off4 = (cnt * 8 + 31) & ~size_t(31);
+      std::vector<double> derived(pairs * 4);
+      for (size_t k = 0; k < pairs; ++k) {
+        const double e24 = f->mixing_table[3 * k], s2 = f->mixing_table[3 * k + 1];
+        const double s6 = s2 * s2 * s2;
+        derived[4 * k] = 2. * e24 * s6 * s6;
+        derived[4 * k + 1] = -e24 * s6;
+        derived[4 * k + 2] = e24 * s6 * s6;
+        derived[4 * k + 3] = (f->flags & APB_FUNCTOR_APPLY_SHIFT) ? f->mixing_table[3 * k + 2] : 0.;
+      }
+      APB_CHECK(apbEnsure(h, h->mixDev, off4 + pairs * 32));
       APB_CUDA(cudaMemcpyAsync(h->mixDev.p, f->mixing_table, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+      APB_CUDA(cudaMemcpyAsync(static_cast<char *>(h->mixDev.p) + off4, derived.data(), pairs * 32, cudaMemcpyHostToDevice, h->stream));
       APB_CUDA(cudaStreamSynchronize(h->stream));
       h->mixHostCache.assign(f->mixing_table, f->mixing_table + cnt);
+      h->mixHostShift = f->flags & APB_FUNCTOR_APPLY_SHIFT;
     }
     p.T = f->num_types;
     p.mix = static_cast<const double *>(h->mixDev.p);
+    p.mix4 = reinterpret_cast<const double *>(static_cast<const char *>(h->mixDev.p) + ((cnt * 8 + 31) & ~size_t(31)));
   }
   return APB_OK;
 }

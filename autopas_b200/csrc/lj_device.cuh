@@ -9,6 +9,10 @@ struct LJParams {
   const double *mix;             // [T*T][3] = {eps24, sigma2, shift6} (ParticlePropertiesLibrary.h:324-328)
   int T;
   int applyShift;
+  // derived constants of the regrouped pair kernel (pruned.cu: prPair): K1 = 2 eps24 sigma^12, K2 = -eps24 sigma^6
+  double k1, k2;
+  const double *mix4;  // [T*T][4] = {K1, K2, K1 / 2, shift6}
+  int cutHiLo;         // high word of the bit pattern of cutoff^2, minus 1 (band in which dr2 is re-evaluated exactly)
 };
 
 struct LJStats {

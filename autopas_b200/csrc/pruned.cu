@@ -607,71 +607,119 @@ __device__ __forceinline__ double prRcp(double x) {
 
 #define PR_FAR 1e100  // x coordinate of the sentinels / of deleted partners: dr2 ~ 1e200 is finite and fails every cutoff
 
-template <bool MIX, bool STATS, bool DEAD>
+template <bool MIX, bool STATS, bool VIR3>
 struct PairAcc {
   double fx = 0., fy = 0., fz = 0.;
-  double su2 = 0., su = 0.;  // non-mixing: sum of lj6^2 and lj6 over hits, Upot6 = eps24 (su2 - su) + hits * shift6
-  double upot = 0.;          // mixing: sum of eps24 * lj6 * (lj6 - 1) + shift6
-  double vx = 0., vy = 0., vz = 0.;
+  double sb2 = 0., sb = 0.;  // non-mixing: sums of b^2 and b over hits, b = 1 / dr2^3 (see prPair)
+  double upot = 0., vt = 0.;  // mixing: sum of potentialEnergy6 and of the virial trace
+  double vx = 0., vy = 0., vz = 0.;  // VIR3: virial per component
   unsigned dist = 0, hits = 0;
 };
 
-// One pair; 20 FP64-pipe instructions without and 25 with globals, about a dozen others.
-// Same quantities as LJFunctor.h:146-159 / :174-190 regrouped:
-//   dr2 from separately rounded squares (bit-identical to the reference's dr2, so the cutoff decision is too),
-//   fac = (lj6 * invdr2) * (48 eps lj6 - 24 eps) = eps24 (lj12 + lj12m6) invdr2,
-//   virial_d = dr_d^2 * fac = dr_d * f_d, Upot6 = eps24 (lj12 - lj6) + shift6. Differences are at the 1e-16 level.
-// A miss skips the (predicated) accumulation instead of multiplying by a mask. The cutoff test compares the bit
-// patterns as integers (both operands are non-negative doubles), which keeps the DSETP off the FP64 pipe.
+// One pair: 17 FP64-pipe instructions without globals, 19 with (non-mixing), +5 with per-component virial.
+// Same quantities as LJFunctor.h:146-159 / :174-190, regrouped around b = invdr2^3 so that sigma and epsilon fold into
+// two constants K1 = 2 eps24 sigma^12 and K2 = -eps24 sigma^6 (per type pair when mixing):
+//   fac           = eps24 (lj12 + lj12m6) invdr2 = invdr2^4 (K1 b + K2)
+//   Upot6         = eps24 (lj12 - lj6) + shift6  = b (K1/2 b + K2) + shift6
+//   virial trace  = dr . f = dr2 fac             = b (K1 b + K2)              (dr2 invdr2^4 = b)
+// so Upot and the virial trace (what LJFunctor::getVirial returns, LJFunctor.h:719) need only sum b^2 and sum b.
+// Differences to the reference's operation order are at the 1e-16 level per pair.
+// Cutoff decision: dr2 is evaluated with two FMAs (3 instead of 5 FP64 instructions) and compared through the high
+// word of its bit pattern (non-negative doubles order like integers; off the FP64 pipe). The reference rounds every
+// product and sum separately (LJFunctor.h:484-488) and the two values can differ by a few ulp, so the fast path only
+// accepts pairs whose high word is below the one of cutoff^2 minus 1; a pair whose high word is within +-1 of it
+// (relative distance to the cutoff < 3e-6: about one row in 10^4) raises `near`, and the caller re-evaluates that row
+// the reference's way (prPairExact) - the decision stays bit-identical.
+// A miss skips the (predicated) accumulation instead of multiplying by a mask.
 // `e8` is the partner's index in the staged tile times 8; positions are staged as (x, y, z) triples.
-template <bool MIX, bool STATS, bool DEAD>
+template <bool MIX, bool STATS, bool VIR3>
+__device__ __forceinline__ void prAccumulate(const LJParams &p, int ti, const int *stype, unsigned e8, double drx,
+                                             double dry, double drz, double dx2, double b, double t, double fac,
+                                             double k2, PairAcc<MIX, STATS, VIR3> &acc) {
+  acc.fx = fma(drx, fac, acc.fx);
+  acc.fy = fma(dry, fac, acc.fy);
+  acc.fz = fma(drz, fac, acc.fz);
+  if (STATS) {
+    if (MIX) {
+      const double2 *m = reinterpret_cast<const double2 *>(p.mix4) + 2 * (static_cast<size_t>(ti) * p.T + stype[e8 >> 3]);
+      const double2 as = __ldg(m + 1);  // {K1 / 2, shift6}
+      acc.upot = fma(b, fma(as.x, b, k2), acc.upot);
+      acc.upot += as.y;
+      if (!VIR3) acc.vt = fma(b, t, acc.vt);
+    } else {
+      acc.sb2 = fma(b, b, acc.sb2);
+      acc.sb += b;
+    }
+    if (VIR3) {
+      acc.vx = fma(dx2, fac, acc.vx);
+      acc.vy = fma(dry * dry, fac, acc.vy);
+      acc.vz = fma(drz * drz, fac, acc.vz);
+    }
+    ++acc.hits;
+  }
+}
+
+template <bool MIX, bool STATS, bool DEAD, bool VIR3>
 __device__ __forceinline__ void prPair(const LJParams &p, double xi, double yi, double zi, int ti,
                                        const unsigned char *sxyz, const int *stype, unsigned e8, unsigned sentinel8,
-                                       PairAcc<MIX, STATS, DEAD> &acc) {
+                                       PairAcc<MIX, STATS, VIR3> &acc, bool &near) {
+#ifdef PR_EXP_NOCONFLICT
+  e8 = (((e8 >> 3) & ~15u) | (threadIdx.x & 15u)) << 3;  // timing experiment only: conflict-free gather
+#endif
   const double *pj = reinterpret_cast<const double *>(sxyz + e8 * 3u);
   const double drx = xi - pj[0], dry = yi - pj[1], drz = zi - pj[2];
-  const double dx2 = __dmul_rn(drx, drx), dy2 = __dmul_rn(dry, dry), dz2 = __dmul_rn(drz, drz);
-  const double dr2 = __dadd_rn(__dadd_rn(dx2, dy2), dz2);
-  const bool hit = __double_as_longlong(dr2) <= __double_as_longlong(p.cutoff2);
-  double e24, s2, shift6;
+  const double dx2 = drx * drx;
+  const double dr2 = fma(drz, drz, fma(dry, dry, dx2));
+  const int band = __double2hiint(dr2) - p.cutHiLo;  // cutHiLo = high word of cutoff^2 minus 1
+  const bool hit = band < 0;
+  near |= static_cast<unsigned>(band) <= 2u;
+  double k1, k2;
   if (MIX) {
-    const double *m = p.mix + 3 * (static_cast<size_t>(ti) * p.T + stype[e8 >> 3]);
-    e24 = __ldg(m);
-    s2 = __ldg(m + 1);
-    shift6 = p.applyShift ? __ldg(m + 2) : 0.;
+    const double2 *m = reinterpret_cast<const double2 *>(p.mix4) + 2 * (static_cast<size_t>(ti) * p.T + stype[e8 >> 3]);
+    const double2 k = __ldg(m);
+    k1 = k.x;
+    k2 = k.y;
   } else {
-    e24 = p.eps24;
-    s2 = p.sigma2;
-    shift6 = 0.;
+    k1 = p.k1;
+    k2 = p.k2;
   }
   const double inv = prRcp(dr2);
-  const double lj2 = s2 * inv;
-  const double u = lj2 * lj2 * lj2;
-  const double t = fma(e24 + e24, u, -e24);
-  double fac = (u * inv) * t;
-  double uu = u;
+  const double a2 = inv * inv;
+  double b = a2 * inv;
+  const double c = a2 * a2;
+  const double t = fma(k1, b, k2);
+  double fac = c * t;
   // keep the pair math unconditional (the four pairs of a row interleave and hide each other's FP64 latency); only the
   // accumulation below is predicated
-  asm volatile("" : "+d"(fac), "+d"(uu));
+  asm volatile("" : "+d"(fac), "+d"(b));
   if (STATS && DEAD) acc.dist += e8 < sentinel8;
-  if (hit) {
-    acc.fx = fma(drx, fac, acc.fx);
-    acc.fy = fma(dry, fac, acc.fy);
-    acc.fz = fma(drz, fac, acc.fz);
-    if (STATS) {
-      if (MIX) {
-        acc.upot = fma(e24 * uu, uu - 1.0, acc.upot);
-        acc.upot += shift6;
-      } else {
-        acc.su2 = fma(uu, uu, acc.su2);
-        acc.su += uu;
-      }
-      acc.vx = fma(dx2, fac, acc.vx);
-      acc.vy = fma(dy2, fac, acc.vy);
-      acc.vz = fma(dz2, fac, acc.vz);
-      ++acc.hits;
-    }
+  if (hit) prAccumulate<MIX, STATS, VIR3>(p, ti, stype, e8, drx, dry, drz, dx2, b, t, fac, k2, acc);
+}
+
+// the rare path: a pair inside the band around the cutoff that prPair left out, decided like the reference does
+template <bool MIX, bool STATS, bool VIR3>
+__device__ __forceinline__ void prPairExact(const LJParams &p, double xi, double yi, double zi, int ti,
+                                            const unsigned char *sxyz, const int *stype, unsigned e8,
+                                            PairAcc<MIX, STATS, VIR3> &acc) {
+  const double *pj = reinterpret_cast<const double *>(sxyz + e8 * 3u);
+  const double drx = xi - pj[0], dry = yi - pj[1], drz = zi - pj[2];
+  const double dx2 = drx * drx;
+  const double dr2 = fma(drz, drz, fma(dry, dry, dx2));
+  if (static_cast<unsigned>(__double2hiint(dr2) - p.cutHiLo) > 2u) return;  // prPair has dealt with it
+  const double dr2x = ljDist2(drx, dry, drz);
+  if (__double_as_longlong(dr2x) > __double_as_longlong(p.cutoff2)) return;
+  double k1 = p.k1, k2 = p.k2;
+  if (MIX) {
+    const double2 *m = reinterpret_cast<const double2 *>(p.mix4) + 2 * (static_cast<size_t>(ti) * p.T + stype[e8 >> 3]);
+    const double2 k = __ldg(m);
+    k1 = k.x;
+    k2 = k.y;
   }
+  const double inv = prRcp(dr2x);
+  const double a2 = inv * inv;
+  const double b = a2 * inv;
+  const double t = fma(k1, b, k2);
+  prAccumulate<MIX, STATS, VIR3>(p, ti, stype, e8, drx, dry, drz, dx2, b, t, (a2 * a2) * t, k2, acc);
 }
 
 __device__ __forceinline__ void prCpAsync8(void *smemDst, const void *gmemSrc) {
@@ -682,7 +730,7 @@ __device__ __forceinline__ void prCpAsync8(void *smemDst, const void *gmemSrc) {
 // DEAD: the ownership column changed since the list build (particles deleted / marked dummy). Those partners are moved
 // out of reach while staging and distance evaluations are counted per pair; otherwise their number is the build-time
 // entry count.
-template <bool MIX, bool STATS, bool DEAD>
+template <bool MIX, bool STATS, bool DEAD, bool VIR3>
 __global__ void __launch_bounds__(PR_TILE, PR_MINBLOCKS) kLJPruned(PrunedForceArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   unsigned char *sxyz = smemRaw;  // (x, y, z) per staged particle
@@ -756,13 +804,20 @@ __global__ void __launch_bounds__(PR_TILE, PR_MINBLOCKS) kLJPruned(PrunedForceAr
       if (a.own[cs[e]] == APB_OWN_DUMMY) sd[3 * e] = PR_FAR;
     __syncthreads();
   }
-  PairAcc<MIX, STATS, DEAD> acc;
-#define PR_ROW(Q)                                                                                       \
-  do {                                                                                                  \
-    prPair<MIX, STATS, DEAD>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).x & 0xFFFFu), sentinel8, acc);      \
-    prPair<MIX, STATS, DEAD>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).x >> 16), sentinel8, acc);          \
-    prPair<MIX, STATS, DEAD>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).y & 0xFFFFu), sentinel8, acc);      \
-    prPair<MIX, STATS, DEAD>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).y >> 16), sentinel8, acc);          \
+  PairAcc<MIX, STATS, VIR3> acc;
+#define PR_ROW(Q)                                                                                              \
+  do {                                                                                                         \
+    bool near = false;                                                                                         \
+    prPair<MIX, STATS, DEAD, VIR3>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).x & 0xFFFFu), sentinel8, acc, near); \
+    prPair<MIX, STATS, DEAD, VIR3>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).x >> 16), sentinel8, acc, near);     \
+    prPair<MIX, STATS, DEAD, VIR3>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).y & 0xFFFFu), sentinel8, acc, near); \
+    prPair<MIX, STATS, DEAD, VIR3>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).y >> 16), sentinel8, acc, near);     \
+    if (near) {                                                                                                \
+      prPairExact<MIX, STATS, VIR3>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).x & 0xFFFFu), acc);                 \
+      prPairExact<MIX, STATS, VIR3>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).x >> 16), acc);                     \
+      prPairExact<MIX, STATS, VIR3>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).y & 0xFFFFu), acc);                 \
+      prPairExact<MIX, STATS, VIR3>(a.p, xi, yi, zi, ti, sxyz, stype, ((Q).y >> 16), acc);                     \
+    }                                                                                                          \
   } while (0)
   int r = 0;
   list += 128;
@@ -794,10 +849,11 @@ __global__ void __launch_bounds__(PR_TILE, PR_MINBLOCKS) kLJPruned(PrunedForceAr
     LJStats st;
     ljStatsZero(st);
     // potentialEnergy6 = eps24 * (lj12 - lj6) + shift6 (LJFunctor.h:174); only owned particles carry lists: weight 1
-    st.upot = MIX ? acc.upot : fma(a.p.eps24, acc.su2 - acc.su, static_cast<double>(acc.hits) * a.p.shift6);
-    st.vir[0] = acc.vx;
-    st.vir[1] = acc.vy;
-    st.vir[2] = acc.vz;
+    // K1/2 sum b^2 + K2 sum b + hits shift6; the trace of the virial is K1 sum b^2 + K2 sum b
+    st.upot = MIX ? acc.upot : fma(0.5 * a.p.k1, acc.sb2, fma(a.p.k2, acc.sb, static_cast<double>(acc.hits) * a.p.shift6));
+    st.vir[0] = VIR3 ? acc.vx : (MIX ? acc.vt : fma(a.p.k1, acc.sb2, a.p.k2 * acc.sb));
+    st.vir[1] = VIR3 ? acc.vy : 0.;
+    st.vir[2] = VIR3 ? acc.vz : 0.;
     st.dist = DEAD ? acc.dist : (addEntries ? a.totalEntries : 0ULL);
     st.kNoN3 = acc.hits;
     st.gNoN3 = acc.hits;
@@ -838,23 +894,29 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   a.p = p;
   a.partials = static_cast<LJStats *>(h->partials.p);
   const size_t smem = static_cast<size_t>(a.stagedCapacity) * (mix ? 28 : 24);
-  const int sel = (mix ? 4 : 0) | (stats ? 2 : 0) | (h->ownDirty ? 1 : 0);
-#define PR_LAUNCH(MIXV, STATSV, DEADV)                                                                               \
+  // per-component virial only on request: LJFunctor exposes the sum alone (getVirial, LJFunctor.h:719)
+  const bool vir3 = stats && !(f->flags & APB_FUNCTOR_VIRIAL_TRACE);
+  const int sel = (mix ? 8 : 0) | (stats ? 4 : 0) | (h->ownDirty ? 2 : 0) | (vir3 ? 1 : 0);
+#define PR_LAUNCH(MIXV, STATSV, DEADV, VIRV)                                                                         \
   do {                                                                                                               \
     if (smem > 40 * 1024)                                                                                            \
-      APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+      APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV, VIRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                     static_cast<int>(smem)));                                                       \
-    ++h->launchCount, kLJPruned<MIXV, STATSV, DEADV><<<numTiles, PR_TILE, smem, h->stream>>>(a);                     \
+    ++h->launchCount, kLJPruned<MIXV, STATSV, DEADV, VIRV><<<numTiles, PR_TILE, smem, h->stream>>>(a);               \
   } while (0)
   switch (sel) {
-    case 0: PR_LAUNCH(false, false, false); break;
-    case 1: PR_LAUNCH(false, false, true); break;
-    case 2: PR_LAUNCH(false, true, false); break;
-    case 3: PR_LAUNCH(false, true, true); break;
-    case 4: PR_LAUNCH(true, false, false); break;
-    case 5: PR_LAUNCH(true, false, true); break;
-    case 6: PR_LAUNCH(true, true, false); break;
-    default: PR_LAUNCH(true, true, true); break;
+    case 0: PR_LAUNCH(false, false, false, false); break;
+    case 2: PR_LAUNCH(false, false, true, false); break;
+    case 4: PR_LAUNCH(false, true, false, false); break;
+    case 5: PR_LAUNCH(false, true, false, true); break;
+    case 6: PR_LAUNCH(false, true, true, false); break;
+    case 7: PR_LAUNCH(false, true, true, true); break;
+    case 8: PR_LAUNCH(true, false, false, false); break;
+    case 10: PR_LAUNCH(true, false, true, false); break;
+    case 12: PR_LAUNCH(true, true, false, false); break;
+    case 13: PR_LAUNCH(true, true, false, true); break;
+    case 14: PR_LAUNCH(true, true, true, false); break;
+    default: PR_LAUNCH(true, true, true, true); break;
   }
   {
     const cudaError_t e = cudaGetLastError();

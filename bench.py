@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--newton3", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--virial-components", action="store_true",
+                    help="accumulate the virial per component instead of its sum (LJFunctor::getVirial returns the sum)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -252,7 +254,8 @@ def main():
     c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(n) + rank * n)
     for d, name in enumerate(("VX", "VY", "VZ")):
         c.uploadColumn(name, vel[:, d])
-    functor = LJFunctor(CUTOFF, applyShift=True, calculateGlobals=True, countFLOPs=True)
+    functor = LJFunctor(CUTOFF, applyShift=True, calculateGlobals=True, countFLOPs=True,
+                       virialTraceOnly=not args.virial_components)
     functor.setParticleProperties(24.0, 1.0)
     trav = GpuTraversal(args.traversal, functor, bool(args.newton3))
     mass = [1.0]
@@ -369,7 +372,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "container": "gpuVerletClusterLists", "traversal": args.traversal,
                            "newton3": bool(args.newton3), "cluster_size": args.cluster_size,
-                           "functor": "LJFunctor shift+globals+flop counters", "decomposition": dims,
+                           "functor": "LJFunctor shift+globals+flop counters" + (", virial per component" if args.virial_components else ""), "decomposition": dims,
                            "particles_total": int(owned_total), "num_clusters": int(g.num_clusters),
                            "num_cluster_pairs": int(g.num_cluster_pairs),
                            "l2_policy": "inputs larger than L2: per-particle lists + SoA columns streamed every step "

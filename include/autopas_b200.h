@@ -99,7 +99,10 @@ enum apb_functor_flags {
   APB_FUNCTOR_APPLY_SHIFT = 1,
   APB_FUNCTOR_USE_MIXING = 2,
   APB_FUNCTOR_CALC_GLOBALS = 4,
-  APB_FUNCTOR_COUNT_FLOPS = 8
+  APB_FUNCTOR_COUNT_FLOPS = 8,
+  /* LJFunctor exposes only the sum of the three virial components (getVirial, LJFunctor.h:719). With this bit the
+   * kernels may return that sum in virial_sum[0] and zero in [1], [2]: only virial_sum[0]+[1]+[2] is meaningful. */
+  APB_FUNCTOR_VIRIAL_TRACE = 16
 };
 
 typedef struct {

@@ -365,3 +365,71 @@ def test_full_size_properties(n_per_dim, spacing, cutoff, skin):
         assert u == pytest.approx(u0, rel=1e-12), k
         assert v == pytest.approx(v0, rel=1e-12), k
     assert u0 < 0  # a liquid-density LJ lattice is bound
+
+
+# ---- gpuvcl_pruned specifics ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mixing", [False, True])
+def test_pruned_virial_trace_only(mixing):
+    """APB_FUNCTOR_VIRIAL_TRACE: only the sum of the virial components (all LJFunctor::getVirial returns,
+    LJFunctor.h:719) is accumulated; Upot, virial, forces and counters must equal the per-component run."""
+    pos, own, types = uniform_with_halo(3000, 400, [9., 9., 9.], 1.0, seed=77, ntypes=2)
+    out = []
+    for trace in (False, True):
+        c = GpuParticleContainer("gpuVerletClusterLists", [0, 0, 0], [9, 9, 9], 1.0, 0.15, clusterSize=32)
+        ids = np.arange(len(pos))
+        mo, mh = own == 1, own == 2
+        c.addParticles(pos[mo, 0], pos[mo, 1], pos[mo, 2], ids[mo], types[mo])
+        c.addHaloParticles(pos[mh, 0], pos[mh, 1], pos[mh, 2], ids[mh], types[mh])
+        f = make_functor(1.0, True, mixing, [1.0, 1.3], [1.0, 0.9])
+        f.virialTraceOnly = trace
+        t = GpuTraversal("gpuvcl_pruned", f, False)
+        c.rebuildNeighborLists(t)
+        f.initTraversal()
+        c.computeInteractions(t)
+        f.endTraversal(False)
+        out.append((c.forcesById(len(pos)), f.getPotentialEnergy(), f.getVirial(), f.getNumFLOPs()))
+        c.close()
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    assert out[0][1] == out[1][1]
+    assert out[1][2] == pytest.approx(out[0][2], rel=1e-12)
+    assert out[0][3] == out[1][3]
+    kw = dict(shift=True, mixing=mixing, eps=[1.0, 1.3], sigma=[1.0, 0.9])
+    o = oracle.lj_vcl(pos[:, 0], pos[:, 1], pos[:, 2], types if mixing else None, own, [0, 0, 0], [9, 9, 9], 1.0, 0.15, 32,
+                      newton3=False, **kw)
+    u, v = oracle.lj_end_traversal(o["res"])
+    assert out[1][1] == pytest.approx(u, rel=1e-12)
+    assert out[1][2] == pytest.approx(v, rel=1e-12)
+
+
+@pytest.mark.parametrize("cutoff", [1.0, 2.5, 1.7])
+def test_pruned_cutoff_decision_is_bit_exact(cutoff):
+    """Pairs whose squared distance lies within a few ulp of cutoff^2: the pruned kernel evaluates dr2 with FMAs and
+    re-evaluates such pairs with separately rounded products and sums, so the number of kernel calls (pairs with
+    dr2 <= cutoff^2, LJFunctor.h:149 / :494) must equal the oracle's exactly. Scenario: 8 centres, each with 500
+    particles on the sphere of radius cutoff around it (coordinates of the order of the cutoff, so dr2 scatters by a
+    few ulp around cutoff^2)."""
+    rng = np.random.default_rng(int(cutoff * 10))
+    k = np.arange(500) + 0.5
+    phi, theta = np.arccos(1 - 2 * k / 500), np.pi * (1 + 5 ** 0.5) * k
+    sphere = np.stack([np.cos(theta) * np.sin(phi), np.sin(theta) * np.sin(phi), np.cos(phi)], axis=1)
+    centres = (np.stack(np.meshgrid(*[np.arange(2)] * 3, indexing="ij"), axis=-1).reshape(-1, 3) * 4.0 + 2.0) * cutoff
+    centres = centres + rng.uniform(-0.01, 0.01, centres.shape)
+    parts, near, inside, outside = [centres], 0, 0, 0
+    for cpos in centres:
+        p = cpos + sphere * (cutoff * (1.0 + rng.integers(-3, 4, 500) * 1.1e-16))[:, None]
+        d = cpos - p
+        dr2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+        near += int((np.abs(dr2 - cutoff * cutoff) <= 4 * np.spacing(cutoff * cutoff)).sum())
+        inside += int((dr2 <= cutoff * cutoff).sum())
+        outside += int((dr2 > cutoff * cutoff).sum())
+        parts.append(p)
+    assert near > 1000 and inside > 400 and outside > 400, (near, inside, outside)
+    pos = np.vstack(parts)
+    L = 8.0 * cutoff
+    own = np.ones(len(pos), dtype=np.int64)
+    c, f = run_gpu("gpuVerletClusterLists", "gpuvcl_pruned", pos, own, None, [0, 0, 0], [L, L, L], cutoff, 0.2 * cutoff,
+                   False, shift=True, M=32)
+    bf = oracle.lj_bruteforce(pos[:, 0], pos[:, 1], pos[:, 2], None, own, cutoff, shift=True)
+    assert f._raw.num_kernel_calls_no_n3 == 2 * bf["res"].num_kernel_calls_n3  # newton3 off: both directions
+    check_forces(c.forcesById(len(pos)), bf["f"], bf["fscale"], own)
+    c.close()
