@@ -551,6 +551,13 @@ class GpuParticleContainer:
     def downloadForces(self, fx, fy, fz):
         self._check(self._lib.apb_download_forces(self._h, _ptr(fx), _ptr(fy), _ptr(fz)))
 
+    def uploadPositionsById(self, x, y, z, idBegin=0):
+        """Positions of the owned particles from host arrays indexed by particle id - idBegin."""
+        self._check(self._lib.apb_upload_positions_by_id(self._h, int(idBegin), len(x), _ptr(x), _ptr(y), _ptr(z)))
+
+    def downloadForcesById(self, fx, fy, fz, idBegin=0):
+        self._check(self._lib.apb_download_forces_by_id(self._h, int(idBegin), len(fx), _ptr(fx), _ptr(fy), _ptr(fz)))
+
     def resetForces(self, fx=0.0, fy=0.0, fz=0.0):
         self._check(self._lib.apb_reset_forces(self._h, fx, fy, fz))
 

@@ -9,6 +9,8 @@
 
 #include <algorithm>
 
+#include <chrono>
+
 #include "internal.cuh"
 
 // ---- NCCL, loaded lazily (torch has usually loaded libnccl.so.2 already; the library must also load without it) ----
@@ -90,6 +92,14 @@ extern "C" int apb_comm_init(apb_handle h, int32_t nranks, int32_t rank, const v
 }
 
 void apbCommDestroy(apb_handle h) {
+  for (auto &o : h->p2pOpened)
+    if (o.second) cudaIpcCloseMemHandle(o.second);
+  h->p2pOpened.clear();
+  if (h->p2pArena) cudaFree(h->p2pArena);
+  if (h->p2pCounters) cudaFree(h->p2pCounters);
+  h->p2pArena = nullptr;
+  h->p2pCounters = nullptr;
+  h->p2pState = 0;
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(static_cast<ncclComm_t>(h->comm));
   h->comm = nullptr;
 }
@@ -499,6 +509,142 @@ __global__ void kScatterPositions2(int64_t m0, int64_t m1, const int *__restrict
   y[s] = in[m + q];
   z[s] = in[2 * m + q];
 }
+// ---- halo refresh through peer memory ---------------------------------------------------------------------------------
+// kPushHalo: gathers the positions recorded for the two neighbours of dimension `dim` (shifted at a periodic global
+// boundary) and stores them directly into the neighbours' arenas (NVLink peer stores through the IPC mapping); the last
+// block to finish publishes the sequence number in the neighbours' flags. kPullHalo spins on the own flags until both
+// neighbours have published `seq`, then scatters the received positions into the halo slots.
+__global__ void kPushHalo(int64_t m0, int64_t m1, const int *__restrict__ idx0, const int *__restrict__ idx1,
+                          const double *x, const double *y, const double *z, int dim, double shift0, double shift1,
+                          double *out0, double *out1, unsigned long long *flag0, unsigned long long *flag1,
+                          unsigned long long seq, int *counter) {
+  __shared__ bool isLast;
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q < m0 + m1) {
+    const bool second = q >= m0;
+    if (second) q -= m0;
+    const int64_t m = second ? m1 : m0;
+    const int s = second ? idx1[q] : idx0[q];
+    double *out = second ? out1 : out0;
+    const double shift = second ? shift1 : shift0;
+    double px = nan(""), py = 0., pz = 0.;
+    if (s >= 0) {
+      px = x[s];
+      py = y[s];
+      pz = z[s];
+      if (dim == 0) px += shift;
+      if (dim == 1) py += shift;
+      if (dim == 2) pz += shift;
+    }
+    out[q] = px;
+    out[m + q] = py;
+    out[2 * m + q] = pz;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) isLast = atomicAdd(counter, 1) == static_cast<int>(gridDim.x) - 1;
+  __syncthreads();
+  if (isLast && threadIdx.x == 0) {
+    *counter = 0;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(flag0) = seq;
+    *reinterpret_cast<volatile unsigned long long *>(flag1) = seq;
+    __threadfence_system();
+  }
+}
+
+__global__ void kPullHalo(int64_t m0, int64_t m1, const int *__restrict__ slot0, const int *__restrict__ slot1,
+                          const double *in0, const double *in1, const unsigned long long *flag0,
+                          const unsigned long long *flag1, unsigned long long seq, double *x, double *y, double *z) {
+  if (threadIdx.x == 0) {
+    while (*reinterpret_cast<const volatile unsigned long long *>(flag0) < seq) {
+    }
+    while (*reinterpret_cast<const volatile unsigned long long *>(flag1) < seq) {
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= m0 + m1) return;
+  const bool second = q >= m0;
+  if (second) q -= m0;
+  const int64_t m = second ? m1 : m0;
+  const int s = second ? slot1[q] : slot0[q];
+  const double *in = second ? in1 : in0;
+  if (s < 0) return;
+  const double px = __ldcg(in + q);  // written by the peer: read through L2, not a stale L1 line
+  if (isnan(px)) return;
+  x[s] = px;
+  y[s] = __ldcg(in + m + q);
+  z[s] = __ldcg(in + 2 * m + q);
+}
+
+static inline double *p2pRegion(void *arena, size_t cap, int d, int s, int parity) {
+  return static_cast<double *>(arena) + (static_cast<size_t>((d * 2 + s) * 2 + parity)) * cap;
+}
+static inline unsigned long long *p2pFlag(void *arena, size_t cap, int d, int s) {
+  return reinterpret_cast<unsigned long long *>(static_cast<double *>(arena) + 12 * cap) + (d * 2 + s);
+}
+
+// One-time set-up: allocate the arena, trade IPC handles with the distinct neighbour ranks (NCCL send / recv) and map
+// theirs. Every rank of the decomposition reaches this at the same point (its first halo refresh), so the pairwise
+// exchange matches up. APB_NO_P2P_HALO=1 keeps the NCCL send / recv refresh (set it on all ranks).
+static int ensureP2P(apb_handle h) {
+  if (h->p2pState != 0) return APB_OK;
+  h->p2pState = -1;
+  if (h->nranks <= 1 || !h->comm || getenv("APB_NO_P2P_HALO")) return APB_OK;
+  std::vector<int> peers;
+  for (int d = 0; d < 3; ++d)
+    for (int s = 0; s < 2; ++s) {
+      const int r = h->neighbor[d][s];
+      if (r != h->myRank && std::find(peers.begin(), peers.end(), r) == peers.end()) peers.push_back(r);
+    }
+  if (peers.empty()) return APB_OK;
+  size_t mb = 24;  // per region; 12 regions
+  if (const char *e = getenv("APB_HALO_ARENA_MB")) mb = std::max<long>(1, atol(e));
+  h->p2pCap = mb * 1024 * 1024 / sizeof(double);
+  const size_t bytes = 12 * h->p2pCap * sizeof(double) + 64;
+  APB_CUDA(cudaMalloc(&h->p2pArena, bytes));
+  APB_CUDA(cudaMemsetAsync(h->p2pArena, 0, bytes, h->stream));
+  APB_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->p2pCounters), 4 * sizeof(int)));
+  APB_CUDA(cudaMemsetAsync(h->p2pCounters, 0, 4 * sizeof(int), h->stream));
+  cudaIpcMemHandle_t mine;
+  APB_CUDA(cudaIpcGetMemHandle(&mine, h->p2pArena));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  APB_CHECK(apbEnsure(h, h->xbuf[0], 64 * (peers.size() + 1) + 256));
+  char *dev = static_cast<char *>(h->xbuf[0].p);
+  APB_CUDA(cudaMemcpyAsync(dev, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+  ncclComm_t comm = static_cast<ncclComm_t>(h->comm);
+  APB_NCCL(g_nccl.GroupStart());
+  for (size_t k = 0; k < peers.size(); ++k) {
+    APB_NCCL(g_nccl.Send(dev, 64, ncclInt8, peers[k], comm, h->stream));
+    APB_NCCL(g_nccl.Recv(dev + 64 * (k + 1), 64, ncclInt8, peers[k], comm, h->stream));
+  }
+  APB_NCCL(g_nccl.GroupEnd());
+  std::vector<cudaIpcMemHandle_t> theirs(peers.size());
+  APB_CUDA(cudaMemcpyAsync(theirs.data(), dev + 64, 64 * peers.size(), cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  for (size_t k = 0; k < peers.size(); ++k) {
+    void *base = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&base, theirs[k], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return h->fail(APB_ERR_CUDA, std::string("peer-memory halo refresh: cudaIpcOpenMemHandle for rank ") +
+                                       std::to_string(peers[k]) + " failed (" + cudaGetErrorString(e) +
+                                       "); set APB_NO_P2P_HALO=1 on all ranks to use NCCL send/recv instead");
+    }
+    h->p2pOpened.emplace_back(peers[k], base);
+  }
+  for (int d = 0; d < 3; ++d)
+    for (int s = 0; s < 2; ++s) {
+      h->p2pPeer[d][s] = nullptr;
+      for (auto &o : h->p2pOpened)
+        if (o.first == h->neighbor[d][s]) h->p2pPeer[d][s] = o.second;
+    }
+  h->p2pState = 1;
+  return APB_OK;
+}
+
 // a rank that is its own neighbour in this dimension (periodic, one rank wide): what goes out to the right re-enters from
 // the left and vice versa, so the refresh is a direct slot-to-slot copy. srcA -> dstA are the right-going particles
 // (received "from the left"), srcB -> dstB the left-going ones.
@@ -797,6 +943,8 @@ extern "C" int apb_exchange_halos(apb_handle h) {
     return APB_OK;
   }
   if (!h->haloLinksValid) return h->fail(APB_ERR_STATE, "apb_exchange_halos: no halo links recorded; call it once before the rebuild");
+  APB_CHECK(ensureP2P(h));
+  ++h->p2pSeq;
   for (int d = 0; d < 3; ++d) {
     HaloLink &L0 = h->link[d][0], &L1 = h->link[d][1];
     const int left = h->neighbor[d][0], right = h->neighbor[d][1];
@@ -812,6 +960,33 @@ extern "C" int apb_exchange_halos(apb_handle h) {
             h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z]);
         APB_CUDA(cudaGetLastError());
       }
+      continue;
+    }
+    // (a non-periodic dimension has ranks without one of the neighbours: all ranks keep NCCL for it)
+    if (h->p2pState == 1 && h->periodic[d] && h->p2pPeer[d][0] && h->p2pPeer[d][1]) {
+      // my left-going particles land in the left neighbour's "from the right" region and vice versa
+      if (3 * static_cast<size_t>(std::max(std::max(L0.nSend, L1.nSend), std::max(L0.nRecv, L1.nRecv))) > h->p2pCap)
+        return h->fail(APB_ERR_NOT_APPLICABLE, "halo refresh: more halo particles per face than the peer-memory arena "
+                                               "holds; raise APB_HALO_ARENA_MB (default 24) on all ranks");
+      const int parity = static_cast<int>(h->p2pSeq & 1);
+      // Which of the neighbour's two receive regions a send list feeds follows the matching of the generating exchange
+      // (exchangePayload): with distinct neighbours my left-going particles are what the left neighbour receives "from
+      // its right" (side 1); when both neighbours are the same rank (two ranks in this dimension) NCCL pairs the sends
+      // and receives of the group in order, so send list 0 feeds its side 0 and send list 1 its side 1.
+      const int to0 = left == right ? 0 : 1, to1 = left == right ? 1 : 0;
+      const int64_t mS = L0.nSend + L1.nSend, mR = L0.nRecv + L1.nRecv;
+      ++h->launchCount, kPushHalo<<<std::max<int64_t>(1, apbDivUp(mS, 256)), 256, 0, h->stream>>>(
+          L0.nSend, L1.nSend, static_cast<const int *>(L0.sendIdx.p), static_cast<const int *>(L1.sendIdx.p),
+          h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], d, L0.shift, L1.shift,
+          p2pRegion(h->p2pPeer[d][0], h->p2pCap, d, to0, parity), p2pRegion(h->p2pPeer[d][1], h->p2pCap, d, to1, parity),
+          p2pFlag(h->p2pPeer[d][0], h->p2pCap, d, to0), p2pFlag(h->p2pPeer[d][1], h->p2pCap, d, to1), h->p2pSeq,
+          h->p2pCounters + d);
+      ++h->launchCount, kPullHalo<<<std::max<int64_t>(1, apbDivUp(mR, 256)), 256, 0, h->stream>>>(
+          L0.nRecv, L1.nRecv, static_cast<const int *>(L0.recvSlot.p), static_cast<const int *>(L1.recvSlot.p),
+          p2pRegion(h->p2pArena, h->p2pCap, d, 0, parity), p2pRegion(h->p2pArena, h->p2pCap, d, 1, parity),
+          p2pFlag(h->p2pArena, h->p2pCap, d, 0), p2pFlag(h->p2pArena, h->p2pCap, d, 1), h->p2pSeq, h->col[APB_COL_X],
+          h->col[APB_COL_Y], h->col[APB_COL_Z]);
+      APB_CUDA(cudaGetLastError());
       continue;
     }
     void *sendBuf[2], *recvBuf[2];
@@ -863,6 +1038,17 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
   apb_traversal_result *dres = static_cast<apb_traversal_result *>(h->loopResults.p);
   int rc = APB_OK;
   h->deferSync = true;
+  // APB_DEBUG_TIMING: host wall time spent inside each phase call (where the host blocks on count read-backs / peers)
+  static const bool dbgTiming = getenv("APB_DEBUG_TIMING") != nullptr;
+  // Overlapped halo refresh (interior / boundary split of the force step). The two partial force launches cost about
+  // 0.02 ms of tail effects; measured on 8 x B200 the split pays once all three dimensions exchange with remote ranks
+  // (13.5 -> 14.3 GFUPs/s), at 2 GPUs (one remote dimension) it is a wash. APB_SPLIT_STEP=0 / 1 overrides.
+  int remoteDims = 0;
+  for (int d = 0; d < 3; ++d) remoteDims += h->neighbor[d][0] != h->myRank || h->neighbor[d][1] != h->myRank;
+  const char *splitEnv = getenv("APB_SPLIT_STEP");
+  const bool noSplit = splitEnv ? atoi(splitEnv) == 0 : remoteDims < 3;
+  double hostMs[5] = {0, 0, 0, 0, 0};
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int s = 0; s < numSteps && rc == APB_OK; ++s) {
     const int64_t it = firstIteration + s;
     apbLoopTimingRecord(h, 3, true);
@@ -872,13 +1058,57 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
     const bool rebuild = (it % p->rebuild_frequency == 0) || !h->structureValid;
     if (rebuild) {
       apbLoopTimingRecord(h, 1, true);
+      const double t0 = now();
       rc = apb_migrate(h, nullptr, nullptr);
+      const double t1 = now();
       if (rc == APB_OK) rc = apb_exchange_halos(h);
+      const double t2 = now();
       if (rc == APB_OK) rc = apb_rebuild_neighbor_lists(h, p->traversal, p->newton3);
+      const double t3 = now();
+      hostMs[0] += t1 - t0, hostMs[1] += t2 - t1, hostMs[2] += t3 - t2;
       apbLoopTimingRecord(h, 1, false);
-    } else {
+    } else if (h->nranks > 1 && p->traversal == APB_TRAVERSAL_GPUVCL_PRUNED && functor->kind == APB_FUNCTOR_LJ &&
+               h->prunedValid && !noSplit) {
+      // Split step: the halo refresh (NCCL over NVLink) runs on the second stream while the interior tiles - those
+      // that stage no halo copy - are evaluated; the boundary tiles follow once the refreshed positions have landed.
+      if (!h->evSplit[0]) {
+        APB_CUDA(cudaEventCreateWithFlags(&h->evSplit[0], cudaEventDisableTiming));
+        APB_CUDA(cudaEventCreateWithFlags(&h->evSplit[1], cudaEventDisableTiming));
+      }
+      const double t0 = now();
+      APB_CUDA(cudaEventRecord(h->evSplit[0], h->stream));
+      APB_CUDA(cudaStreamWaitEvent(h->stream2, h->evSplit[0], 0));
+      cudaStream_t mainStream = h->stream;
+      h->stream = h->stream2;
       apbLoopTimingRecord(h, 2, true);
       rc = apb_exchange_halos(h);
+      apbLoopTimingRecord(h, 2, false);
+      cudaEventRecord(h->evSplit[1], h->stream2);
+      h->stream = mainStream;
+      hostMs[3] += now() - t0;
+      if (rc != APB_OK) break;
+      h->asyncResultDev = dres + s;
+      apbLoopTimingRecord(h, 0, true);
+      h->prunedPart = 1;
+      rc = apb_compute_interactions(h, p->traversal, functor, p->newton3, nullptr);
+      if (rc == APB_OK) {
+        APB_CUDA(cudaStreamWaitEvent(h->stream, h->evSplit[1], 0));
+        h->prunedPart = 2;
+        rc = apb_compute_interactions(h, p->traversal, functor, p->newton3, nullptr);
+      }
+      h->prunedPart = 0;
+      apbLoopTimingRecord(h, 0, false);
+      h->asyncResultDev = nullptr;
+      if (rc != APB_OK) break;
+      apbLoopTimingRecord(h, 3, true);
+      rc = apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
+      apbLoopTimingRecord(h, 3, false);
+      continue;
+    } else {
+      apbLoopTimingRecord(h, 2, true);
+      const double t0 = now();
+      rc = apb_exchange_halos(h);
+      hostMs[3] += now() - t0;
       apbLoopTimingRecord(h, 2, false);
     }
     if (rc != APB_OK) break;
@@ -895,6 +1125,9 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
   h->deferSync = false;
   h->asyncResultDev = nullptr;
   if (rc != APB_OK) return rc;
+  if (dbgTiming)
+    fprintf(stderr, "[apb] rank %d run_steps(%d): host ms in migrate %.3f, halo build %.3f, rebuild %.3f, halo refresh %.3f\n",
+            h->myRank, numSteps, hostMs[0], hostMs[1], hostMs[2], hostMs[3]);
   if (outPerStep) {
     APB_CUDA(cudaMemcpyAsync(outPerStep, dres, sizeof(apb_traversal_result) * numSteps, cudaMemcpyDeviceToHost, h->stream));
   }

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "autopas_b200.h"
@@ -101,6 +102,9 @@ struct apb_handle_s {
   int prunedWarps = 0;
   DevBuf prNumStaged, prStagedStart, prStaged, prWarpLen, prWarpStart, prLists, prTileFirst, prTileNum, prTileWarp;
   DevBuf prMasks, prUsed, prCbase, prNumCompact, prCompactSlot;
+  DevBuf prTileHalo, prTileOrder;  // per tile: stages a halo copy; tiles ordered interior first (+ the interior count)
+  int prunedPart = 0;              // 0: whole traversal; 1 / 2: interior / boundary half of a split step (apb_run_steps)
+  cudaEvent_t evSplit[2] = {nullptr, nullptr};
 
   // ---- reductions / results ----
   DevBuf partials;
@@ -112,6 +116,7 @@ struct apb_handle_s {
   // ---- leavers (library-owned, valid until the next update_container) ----
   int64_t numLeavers = 0;
   DevBuf leaverIdx;
+  DevBuf idStage;  // 3 x numIds doubles: staging of the by-id transfers
   std::vector<double> leaverCols[6];
   std::vector<int64_t> leaverIds;
   std::vector<int32_t> leaverTypes;
@@ -127,6 +132,16 @@ struct apb_handle_s {
   double globalMin[3]{}, globalMax[3]{};
   bool periodic[3]{};
   int neighbor[3][2]{};
+  // peer-memory halo refresh (non-rebuild steps, ranks of one node): every rank owns an arena of receive regions
+  // [3 dims][2 sides][2 parities] x p2pCap doubles followed by one 64-bit sequence flag per (dim, side); neighbours map
+  // it through CUDA IPC and write refreshed halo positions straight into it over NVLink
+  void *p2pArena = nullptr;
+  size_t p2pCap = 0;                       // doubles per region
+  void *p2pPeer[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // neighbour arenas (mapped)
+  std::vector<std::pair<int, void *>> p2pOpened;  // rank -> mapped base (one mapping per distinct neighbour)
+  unsigned long long p2pSeq = 0;
+  int p2pState = 0;                        // 0 not set up yet, 1 ready, -1 not applicable
+  int *p2pCounters = nullptr;              // 3 block counters (last-block-signals pattern)
   bool haloLinksValid = false;
   HaloLink link[3][2];
   DevBuf invPerm, xbuf[4], massDev;

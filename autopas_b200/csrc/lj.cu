@@ -12,11 +12,21 @@
 // ------------------------------------------------------------------------------------------------------------------
 // block reduction of per-thread statistics into one partial per block; final pass sums partials in fixed order
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void kReducePartials(const LJStats *__restrict__ partials, int numBlocks, apb_traversal_result *out) {
+__global__ void __launch_bounds__(1024) kReducePartials(const LJStats *__restrict__ partials, int numBlocks, apb_traversal_result *out) {
   __shared__ LJStats sh[32];
   LJStats s;
   ljStatsZero(s);
-  for (int b = threadIdx.x; b < numBlocks; b += blockDim.x) ljStatsAdd(s, partials[b]);
+  // a thread's partials are loaded four at a time (independent loads in flight), summed in index order
+  int b = threadIdx.x;
+  for (; b + 3 * static_cast<int>(blockDim.x) < numBlocks; b += 4 * blockDim.x) {
+    const LJStats p0 = partials[b], p1 = partials[b + blockDim.x], p2 = partials[b + 2 * blockDim.x],
+                  p3 = partials[b + 3 * blockDim.x];
+    ljStatsAdd(s, p0);
+    ljStatsAdd(s, p1);
+    ljStatsAdd(s, p2);
+    ljStatsAdd(s, p3);
+  }
+  for (; b < numBlocks; b += blockDim.x) ljStatsAdd(s, partials[b]);
   ljStatsWarpReduce(s);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) sh[warp] = s;
@@ -324,7 +334,7 @@ int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f
   if (h->asyncResultDev) {
     // device-resident loop (apb_run_steps): the reduced accumulators stay on the device, no host sync per step
     if (stats && numBlocks > 0) {
-      ++h->launchCount, kReducePartials<<<1, 256, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
+      ++h->launchCount, kReducePartials<<<1, 1024, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
                                                 h->asyncResultDev);
       APB_CUDA(cudaGetLastError());
     } else {
@@ -333,7 +343,7 @@ int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f
     return APB_OK;
   }
   if (stats && numBlocks > 0) {
-    ++h->launchCount, kReducePartials<<<1, 256, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
+    ++h->launchCount, kReducePartials<<<1, 1024, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
                                               static_cast<apb_traversal_result *>(h->result.p));
     APB_CUDA(cudaGetLastError());
     APB_CUDA(cudaMemcpyAsync(&host, h->result.p, sizeof(host), cudaMemcpyDeviceToHost, h->stream));

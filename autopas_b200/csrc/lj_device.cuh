@@ -51,9 +51,9 @@ __device__ __forceinline__ void ljStatsWarpReduce(LJStats &s) {
     s.gNoN3 += __shfl_xor_sync(0xffffffffu, s.gNoN3, o);
   }
 }
-// all threads of the block must call this; writes partials[blockIdx.x]. Butterfly order is fixed, so the sums are
+// all threads of the block must call this; writes partials[index] (default: blockIdx.x). Butterfly order is fixed, so the sums are
 // reproducible run to run.
-__device__ __forceinline__ void ljStatsBlockReduce(LJStats &s, LJStats *partials) {
+__device__ __forceinline__ void ljStatsBlockReduce(LJStats &s, LJStats *partials, int index = -1) {
   __shared__ LJStats sh[32];
   ljStatsWarpReduce(s);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -64,7 +64,7 @@ __device__ __forceinline__ void ljStatsBlockReduce(LJStats &s, LJStats *partials
     ljStatsZero(t);
     if (lane < ((blockDim.x + 31) >> 5)) t = sh[lane];
     ljStatsWarpReduce(t);
-    if (lane == 0) partials[blockIdx.x] = t;
+    if (lane == 0) partials[index >= 0 ? index : static_cast<int>(blockIdx.x)] = t;
   }
 }
 

@@ -22,8 +22,9 @@
 #include "lj_device.cuh"
 
 #ifndef PR_WARPS
-#define PR_WARPS 8  // warp chunks per tile (8: 2 x 2 towers x 2 chunks, 4: 2 x 1 towers x 2 chunks)
+#define PR_WARPS 8  // warp chunks per tile (8: 2 x 2 towers x 2 chunks, 16: 2 x 2 towers x 4 chunks, 4: 2 x 1 towers x 2 chunks)
 #endif
+#define PR_ZC (PR_WARPS >= 8 ? PR_WARPS / 4 : 2)  // consecutive 32-slot chunks of one tower per tile (power of two)
 #define PR_TILE (PR_WARPS * 32)
 #ifndef PR_MINBLOCKS
 #define PR_MINBLOCKS (32 / PR_WARPS)  // 32 resident warps per SM: 64 registers per thread
@@ -143,7 +144,8 @@ __global__ void kPrunedTiles(int numTiles, int nbx, int nzc, int nx, int ny, int
   const int bx = b % nbx, by = b / nbx;
   // `shift` aligns the 2 x 2 tower blocks with the first owned tower, so that halo towers (which carry no lists) do not
   // share a tile - and a CTA's lifetime - with owned ones
-  const int tx = 2 * bx - shift + ((w >> 1) & 1), ty = PR_WARPS == 8 ? 2 * by - shift + (w >> 2) : by, k = 2 * zc + (w & 1);
+  const int wz = w % PR_ZC, wt = w / PR_ZC;  // chunk within the tower, tower within the 2 x 2 (2 x 1) block
+  const int tx = 2 * bx - shift + (wt & 1), ty = PR_WARPS >= 8 ? 2 * by - shift + (wt >> 1) : by, k = PR_ZC * zc + wz;
   int first = -1, num = 0;
   if (tx >= 0 && ty >= 0 && tx < nx && ty < ny) {
     const int t = tx + ty * nx;
@@ -357,11 +359,14 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
                                                        const int *__restrict__ staged, MaskOut o,
                                                        const int *__restrict__ warpRowStart,
                                                        unsigned short *__restrict__ lists, int *__restrict__ compactSlot,
-                                                       int smemRowsPerWarp) {
+                                                       int smemRowsPerWarp, int *__restrict__ tileHalo) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int tile = blockIdx.x;
   const int g0 = stagedStart[tile], nS = stagedStart[tile + 1] - g0;
-  if (nS == 0) return;
+  if (nS == 0) {
+    if (threadIdx.x == 0) tileHalo[tile] = 0;
+    return;
+  }
   int *stg = reinterpret_cast<int *>(smemRaw);
   unsigned *used = reinterpret_cast<unsigned *>(stg + nS);
   int *cbase = reinterpret_cast<int *>(used + nS);
@@ -373,11 +378,19 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   __syncthreads();
   const int mask = a.M - 1;
   int *cs = compactSlot + (static_cast<size_t>(g0) << a.logM);
+  // a tile is a boundary tile if any particle it stages is a halo copy: its forces have to wait for the halo refresh
+  int stagesHalo = 0;
   for (int e = threadIdx.x; e < (nS << a.logM); e += PR_TILE) {
     const int s = e >> a.logM, k = e & mask;
     const unsigned u = used[s];
-    if ((u >> k) & 1u) cs[cbase[s] + __popc(u & ((1u << k) - 1u))] = (stg[s] << a.logM) + k;
+    if ((u >> k) & 1u) {
+      const int slot = (stg[s] << a.logM) + k;
+      cs[cbase[s] + __popc(u & ((1u << k) - 1u))] = slot;
+      stagesHalo |= a.own[slot] == APB_OWN_HALO;
+    }
   }
+  stagesHalo = __syncthreads_or(stagesHalo);
+  if (threadIdx.x == 0) tileHalo[tile] = stagesHalo;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warpGlobal = tile * PR_WARPS + warp;
   const int first = a.chunkFirst[warpGlobal], num = a.chunkNum[warpGlobal];
@@ -431,6 +444,31 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   }
 }
 
+// Tile order for the split force step: interior tiles (stage no halo copy) first, boundary tiles after them, each group
+// in ascending tile order (deterministic). order[pos] = tile, *numInterior = size of the first group. One block.
+__global__ void __launch_bounds__(1024) kPrunedTileOrder(int numTiles, const int *__restrict__ tileHalo,
+                                                        int *__restrict__ order, int *__restrict__ numInterior) {
+  __shared__ int sScan[1024];
+  const int chunk = (numTiles + 1023) / 1024;
+  const int b = min(static_cast<int>(threadIdx.x) * chunk, numTiles), e = min(b + chunk, numTiles);
+  int c = 0;
+  for (int t = b; t < e; ++t) c += tileHalo[t] == 0;
+  sScan[threadIdx.x] = c;
+  __syncthreads();
+  for (int s = 1; s < 1024; s <<= 1) {
+    const int v = threadIdx.x >= s ? sScan[threadIdx.x - s] : 0;
+    __syncthreads();
+    sScan[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const int total = sScan[1023];
+  int posI = sScan[threadIdx.x] - c, posB = total + (b - posI);
+  for (int t = b; t < e; ++t) {
+    if (tileHalo[t] == 0) order[posI++] = t; else order[posB++] = t;
+  }
+  if (threadIdx.x == 0) *numInterior = total;
+}
+
 int apbBuildPruned(apb_handle h) {
   if (!h->structureValid || h->builtNewton3 != 0)
     return h->fail(APB_ERR_STATE, "gpuvcl_pruned needs cluster lists built with newton3 off");
@@ -450,9 +488,9 @@ int apbBuildPruned(apb_handle h) {
   // tiles: bricks of 2 x 2 towers x 2 consecutive 32-slot chunks
   const int nx = h->vcl.towersPerDim[0], ny = h->vcl.towersPerDim[1];
   const int shift = h->vcl.numTowersPerInteractionLength & 1;
-  const int nbx = (nx + shift + 1) / 2, nby = PR_WARPS == 8 ? (ny + shift + 1) / 2 : ny;
+  const int nbx = (nx + shift + 1) / 2, nby = PR_WARPS >= 8 ? (ny + shift + 1) / 2 : ny;
   const int maxSlots = (h->vclMaxTowerCount + M - 1) / M * M;
-  const int nzc = std::max(1, ((maxSlots + 31) / 32 + 1) / 2);
+  const int nzc = std::max(1, ((maxSlots + 31) / 32 + PR_ZC - 1) / PR_ZC);
   const int64_t numTiles64 = static_cast<int64_t>(nbx) * nby * nzc;
   if (numTiles64 * PR_WARPS > 0x7fffffffLL) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: too many tiles");
   const int numTiles = static_cast<int>(numTiles64);
@@ -484,6 +522,8 @@ int apbBuildPruned(apb_handle h) {
   APB_CHECK(apbEnsure(h, h->prWarpLen, sizeof(int) * (numWarps + 1)));
   APB_CHECK(apbEnsure(h, h->prWarpStart, sizeof(int) * (numWarps + 1)));
   APB_CHECK(apbEnsure(h, h->prNumCompact, sizeof(int) * (numTiles + 1)));
+  APB_CHECK(apbEnsure(h, h->prTileHalo, sizeof(int) * (numTiles + 1)));
+  APB_CHECK(apbEnsure(h, h->prTileOrder, sizeof(int) * (numTiles + 2)));
   int *numStaged = static_cast<int *>(h->prNumStaged.p), *stagedStart = static_cast<int *>(h->prStagedStart.p);
   int *warpRows = static_cast<int *>(h->prWarpLen.p), *warpStart = static_cast<int *>(h->prWarpStart.p);
   char *scratch = static_cast<char *>(h->result.p) + sizeof(apb_traversal_result);
@@ -566,10 +606,17 @@ int apbBuildPruned(apb_handle h) {
   }
   if (uniform)
     ++h->launchCount, kPrunedFill<true><<<numTiles, PR_TILE, smemFill, h->stream>>>(
-        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp);
+        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp,
+        static_cast<int *>(h->prTileHalo.p));
   else
     ++h->launchCount, kPrunedFill<false><<<numTiles, PR_TILE, smemFill, h->stream>>>(
-        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp);
+        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp,
+        static_cast<int *>(h->prTileHalo.p));
+  APB_CUDA(cudaGetLastError());
+  // order[0 .. numTiles) and, behind it, the number of interior tiles
+  ++h->launchCount, kPrunedTileOrder<<<1, 1024, 0, h->stream>>>(numTiles, static_cast<const int *>(h->prTileHalo.p),
+                                                               static_cast<int *>(h->prTileOrder.p),
+                                                               static_cast<int *>(h->prTileOrder.p) + numTiles);
   APB_CUDA(cudaGetLastError());
   if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   h->prunedValid = true;
@@ -592,6 +639,10 @@ struct PrunedForceArgs {
   unsigned long long totalEntries;  // list entries written at build time = distance evaluations per call
   LJParams p;
   LJStats *partials;
+  // split step: part 0 = all tiles in natural order; 1 = interior tiles order[0 .. *numInterior); 2 = boundary tiles
+  // order[*numInterior .. numTiles). A CTA beyond its part's range exits at once. Partials are indexed by position.
+  const int *tileOrder, *numInterior;
+  int part, numTiles;
 };
 
 // reciprocal from the hardware seed: MUFU.RCP64H (relative error ~2^-20, it reads the high word only) followed by one
@@ -735,17 +786,22 @@ __global__ void __launch_bounds__(PR_TILE, PR_MINBLOCKS) kLJPruned(PrunedForceAr
   extern __shared__ __align__(16) unsigned char smemRaw[];
   unsigned char *sxyz = smemRaw;  // (x, y, z) per staged particle
   int *stype = reinterpret_cast<int *>(smemRaw + static_cast<size_t>(a.stagedCapacity) * 24);
-  const int tile = blockIdx.x;
+  int pos = blockIdx.x;
+  if (a.part != 0) {
+    const int nI = *a.numInterior;
+    if (a.part == 1 ? pos >= nI : (pos += nI) >= a.numTiles) return;
+  }
+  const int tile = a.part != 0 ? a.tileOrder[pos] : pos;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warpGlobal = tile * PR_WARPS + warp;
   const int nP = a.numCompact[tile];
-  const bool addEntries = STATS && !DEAD && blockIdx.x == 0 && threadIdx.x == 0;
+  const bool addEntries = STATS && !DEAD && pos == 0 && threadIdx.x == 0;
   if (nP == 0) {  // empty tile (block-uniform)
     if (STATS && threadIdx.x == 0) {
       LJStats st;
       ljStatsZero(st);
       if (addEntries) st.dist = a.totalEntries;
-      a.partials[blockIdx.x] = st;
+      a.partials[pos] = st;
     }
     return;
   }
@@ -754,7 +810,11 @@ __global__ void __launch_bounds__(PR_TILE, PR_MINBLOCKS) kLJPruned(PrunedForceAr
   // (2) the tile's slot table, (3) the staged positions as asynchronous 8-byte copies (LDGSTS, no register round
   // trip), (4) this lane's own particle.
   const int first = a.chunkFirst[warpGlobal];
+#ifdef PR_EXP_NOLOOP
+  const int rows = first >= 0 ? min(a.warpRows[warpGlobal], PR_EXP_NOLOOP) : 0;  // timing experiment only
+#else
   const int rows = first >= 0 ? a.warpRows[warpGlobal] : 0;
+#endif
   const uint2 *list = reinterpret_cast<const uint2 *>(a.lists) +
                       (rows > 0 ? static_cast<size_t>(a.warpRowStart[warpGlobal]) * 32 + lane : lane);
   uint2 q0 = __ldg(list), q1 = __ldg(list + 32), q2 = __ldg(list + 64), q3 = __ldg(list + 96);
@@ -838,7 +898,6 @@ __global__ void __launch_bounds__(PR_TILE, PR_MINBLOCKS) kLJPruned(PrunedForceAr
       if (r + 2 < rows) PR_ROW(q2);
     }
   }
-#undef PR_ROW
   if (active) {
     // single writer per slot: fire-and-forget RED.ADD.F64 instead of a load / add / store round trip
     atomicAdd(a.fx + i, acc.fx);
@@ -857,9 +916,202 @@ __global__ void __launch_bounds__(PR_TILE, PR_MINBLOCKS) kLJPruned(PrunedForceAr
     st.dist = DEAD ? acc.dist : (addEntries ? a.totalEntries : 0ULL);
     st.kNoN3 = acc.hits;
     st.gNoN3 = acc.hits;
+    ljStatsBlockReduce(st, a.partials, pos);
+  }
+}
+
+// ---- persistent variant ----------------------------------------------------------------------------------------------
+// The kernel above spends about a quarter of its time outside the pair loop: every CTA first waits for three dependent
+// global round trips (tile header -> slot table -> positions) and, because the CTAs of a wave start together and take
+// similar time, the four CTAs of an SM tend to sit in that prologue simultaneously. Here PR_PBLOCKS CTAs per SM stay
+// resident and walk tiles blockIdx.x, blockIdx.x + gridDim.x, ... (static assignment: the summation order of the
+// statistics stays fixed). Positions are double buffered in shared memory: while the warps run the pair loop of tile t,
+// the cp.async copies of tile t + grid land in the other buffer; the slot-table entries, the warp's own particle and
+// its first list rows of the next tile are prefetched into registers during the loop as well. One __syncthreads per
+// tile hands the buffers over.
+#ifndef PR_PBLOCKS
+#define PR_PBLOCKS 2
+#endif
+#define PR_PSLOTS 8  // slot-table entries per thread held in registers for the next tile
+
+template <bool MIX>
+__device__ __forceinline__ void prStageOne(const PrunedForceArgs &a, double *sd, int *stype, int e, int slot) {
+  prCpAsync8(sd + 3 * e, a.x + slot);
+  prCpAsync8(sd + 3 * e + 1, a.y + slot);
+  prCpAsync8(sd + 3 * e + 2, a.z + slot);
+  if (MIX) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(stype + e));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(a.type + slot) : "memory");
+  }
+}
+
+template <bool MIX>
+__device__ __forceinline__ void prSentinels(double *sd, int *stype, int nP) {
+  if (threadIdx.x < 16) {  // sentinel slots for padding entries, one per bank class
+    sd[3 * (nP + threadIdx.x)] = PR_FAR;
+    sd[3 * (nP + threadIdx.x) + 1] = 0.;
+    sd[3 * (nP + threadIdx.x) + 2] = 0.;
+    if (MIX) stype[nP + threadIdx.x] = 0;
+  }
+}
+
+template <bool MIX, bool STATS, bool DEAD, bool VIR3>
+__global__ void __launch_bounds__(PR_TILE, PR_PBLOCKS) kLJPrunedP(PrunedForceArgs a, int numTiles) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const size_t bufBytes = (static_cast<size_t>(a.stagedCapacity) * (MIX ? 28 : 24) + 15) & ~size_t(15);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grid = gridDim.x;
+  int t = blockIdx.x;  // the host launches at most numTiles CTAs
+  PairAcc<MIX, STATS, VIR3> acc;
+
+  // ---- first tile: staged without overlap
+  int nP = a.numCompact[t];
+  const int *cs = a.compactSlot + (static_cast<size_t>(a.stagedStart[t]) << a.logM);
+  {
+    double *sd = reinterpret_cast<double *>(smemRaw);
+    int *stype = reinterpret_cast<int *>(smemRaw + static_cast<size_t>(a.stagedCapacity) * 24);
+    for (int e = threadIdx.x; e < nP; e += PR_TILE) prStageOne<MIX>(a, sd, stype, e, __ldg(cs + e));
+    prSentinels<MIX>(sd, stype, nP);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int first, rows;
+  bool active;
+  int64_t i;
+  double xi, yi, zi;
+  int ti = 0;
+  const uint2 *list;
+  uint2 q0, q1, q2, q3;
+  {
+    const int wg = t * PR_WARPS + warp;
+    first = a.chunkFirst[wg];
+    rows = first >= 0 ? a.warpRows[wg] : 0;
+    list = reinterpret_cast<const uint2 *>(a.lists) + (rows > 0 ? static_cast<size_t>(a.warpRowStart[wg]) * 32 + lane : lane);
+    q0 = __ldg(list), q1 = __ldg(list + 32), q2 = __ldg(list + 64), q3 = __ldg(list + 96);
+    i = static_cast<int64_t>(first >= 0 ? first : 0) + lane;
+    active = rows > 0 && lane < a.chunkNum[wg] && a.own[i] == APB_OWN_OWNED;
+    xi = active ? a.x[i] : 0.5 * PR_FAR, yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
+    if (MIX) ti = active ? a.type[i] : 0;
+  }
+  // header of the next tile (consumed at the top of the loop body), and of the one after (loaded one tile ahead)
+  int tn = t + grid;
+  int nPn = tn < numTiles ? a.numCompact[tn] : 0;
+  int ssn = tn < numTiles ? a.stagedStart[tn] : 0;
+
+  for (int it = 0;; ++it) {
+    unsigned char *sxyz = smemRaw + (it & 1) * bufBytes;
+    int *stype = reinterpret_cast<int *>(sxyz + static_cast<size_t>(a.stagedCapacity) * 24);
+    unsigned char *sxyzN = smemRaw + ((it + 1) & 1) * bufBytes;
+    double *sdN = reinterpret_cast<double *>(sxyzN);
+    int *stypeN = reinterpret_cast<int *>(sxyzN + static_cast<size_t>(a.stagedCapacity) * 24);
+    const unsigned sentinel8 = static_cast<unsigned>(nP) << 3;
+    // this tile's positions have landed and every warp has left the previous tile (whose buffer is refilled below)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    if (DEAD) {
+      double *sd = reinterpret_cast<double *>(sxyz);
+      for (int e = threadIdx.x; e < nP; e += PR_TILE)
+        if (a.own[cs[e]] == APB_OWN_DUMMY) sd[3 * e] = PR_FAR;
+      __syncthreads();
+    }
+    // loads for the next tile, consumed after the first block of rows
+    const int *csn = a.compactSlot + (static_cast<size_t>(ssn) << a.logM);
+    int slots[PR_PSLOTS];
+#pragma unroll
+    for (int k = 0; k < PR_PSLOTS; ++k) {
+      const int e = threadIdx.x + k * PR_TILE;
+      slots[k] = e < nPn ? __ldg(csn + e) : -1;
+    }
+    int firstN = -1, rowsN = 0, numN = 0, rowStartN = 0;
+    if (tn < numTiles) {
+      const int wg = tn * PR_WARPS + warp;
+      firstN = a.chunkFirst[wg];
+      rowsN = a.warpRows[wg];
+      rowStartN = a.warpRowStart[wg];
+      numN = a.chunkNum[wg];
+    }
+    const int tnn = tn + grid;
+    const int nPnn = tnn < numTiles ? a.numCompact[tnn] : 0;
+    const int ssnn = tnn < numTiles ? a.stagedStart[tnn] : 0;
+
+    acc.fx = acc.fy = acc.fz = 0.;
+    int r = 0;
+    list += 128;
+    if (rows >= 4) {
+      PR_ROW(q0);
+      q0 = __ldg(list);
+      PR_ROW(q1);
+      q1 = __ldg(list + 32);
+      PR_ROW(q2);
+      q2 = __ldg(list + 64);
+      PR_ROW(q3);
+      q3 = __ldg(list + 96);
+      r = 4;
+      list += 128;
+    }
+    // ---- start the copies of the next tile into the other buffer
+#pragma unroll
+    for (int k = 0; k < PR_PSLOTS; ++k)
+      if (slots[k] >= 0) prStageOne<MIX>(a, sdN, stypeN, threadIdx.x + k * PR_TILE, slots[k]);
+    for (int e = threadIdx.x + PR_PSLOTS * PR_TILE; e < nPn; e += PR_TILE) prStageOne<MIX>(a, sdN, stypeN, e, __ldg(csn + e));
+    if (tn < numTiles) prSentinels<MIX>(sdN, stypeN, nPn);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // ---- the warp's own particle and first list rows of the next tile
+    if (firstN < 0) rowsN = 0;
+    const int64_t iN = static_cast<int64_t>(firstN >= 0 ? firstN : 0) + lane;
+    const bool activeN = rowsN > 0 && lane < numN && a.own[iN] == APB_OWN_OWNED;
+    const double xN = activeN ? a.x[iN] : 0.5 * PR_FAR, yN = activeN ? a.y[iN] : 0., zN = activeN ? a.z[iN] : 0.;
+    int tiN = 0;
+    if (MIX) tiN = activeN ? a.type[iN] : 0;
+    const uint2 *listN = reinterpret_cast<const uint2 *>(a.lists) + (rowsN > 0 ? static_cast<size_t>(rowStartN) * 32 + lane : lane);
+    const uint2 p0 = __ldg(listN), p1 = __ldg(listN + 32), p2 = __ldg(listN + 64), p3 = __ldg(listN + 96);
+
+    for (; r + 4 <= rows; r += 4, list += 128) {
+      PR_ROW(q0);
+      q0 = __ldg(list);
+      PR_ROW(q1);
+      q1 = __ldg(list + 32);
+      PR_ROW(q2);
+      q2 = __ldg(list + 64);
+      PR_ROW(q3);
+      q3 = __ldg(list + 96);
+    }
+    if (r < rows) {
+      PR_ROW(q0);
+      if (r + 1 < rows) {
+        PR_ROW(q1);
+        if (r + 2 < rows) PR_ROW(q2);
+      }
+    }
+    if (active) {
+      // single writer per slot: fire-and-forget RED.ADD.F64 instead of a load / add / store round trip
+      atomicAdd(a.fx + i, acc.fx);
+      atomicAdd(a.fy + i, acc.fy);
+      atomicAdd(a.fz + i, acc.fz);
+    }
+    if (tn >= numTiles) break;
+    t = tn, tn = tnn;
+    nP = nPn, nPn = nPnn, ssn = ssnn;
+    cs = csn;
+    first = firstN, rows = rowsN, active = activeN, i = iN;
+    xi = xN, yi = yN, zi = zN, ti = tiN;
+    list = listN;
+    q0 = p0, q1 = p1, q2 = p2, q3 = p3;
+  }
+  if (STATS) {
+    LJStats st;
+    ljStatsZero(st);
+    const bool addEntries = !DEAD && blockIdx.x == 0 && threadIdx.x == 0;
+    st.upot = MIX ? acc.upot : fma(0.5 * a.p.k1, acc.sb2, fma(a.p.k2, acc.sb, static_cast<double>(acc.hits) * a.p.shift6));
+    st.vir[0] = VIR3 ? acc.vx : (MIX ? acc.vt : fma(a.p.k1, acc.sb2, a.p.k2 * acc.sb));
+    st.vir[1] = VIR3 ? acc.vy : 0.;
+    st.vir[2] = VIR3 ? acc.vz : 0.;
+    st.dist = DEAD ? acc.dist : (addEntries ? a.totalEntries : 0ULL);
+    st.kNoN3 = acc.hits;
+    st.gNoN3 = acc.hits;
     ljStatsBlockReduce(st, a.partials);
   }
 }
+#undef PR_ROW
 
 int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f, apb_traversal_result *out);
 
@@ -868,7 +1120,6 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   if (!h->prunedValid) APB_CHECK(apbBuildPruned(h));
   const int numTiles = h->prunedTiles;
   if (numTiles == 0) return apbFinishStats(h, 0, stats, f, out);
-  APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * numTiles));
   PrunedForceArgs a;
   a.M = h->cfg.cluster_size;
   a.logM = 0;
@@ -892,17 +1143,43 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   a.stagedCapacity = (h->prunedMaxCompact + 17) & ~1;
   a.totalEntries = h->prunedEntries;
   a.p = p;
-  a.partials = static_cast<LJStats *>(h->partials.p);
   const size_t smem = static_cast<size_t>(a.stagedCapacity) * (mix ? 28 : 24);
   // per-component virial only on request: LJFunctor exposes the sum alone (getVirial, LJFunctor.h:719)
   const bool vir3 = stats && !(f->flags & APB_FUNCTOR_VIRIAL_TRACE);
   const int sel = (mix ? 8 : 0) | (stats ? 4 : 0) | (h->ownDirty ? 2 : 0) | (vir3 ? 1 : 0);
+  // persistent double-buffered kernel when two position buffers fit PR_PBLOCKS times into an SM's shared memory
+  static int numSMs = 0;
+  if (numSMs == 0) {
+    cudaDeviceProp prop;
+    APB_CUDA(cudaGetDeviceProperties(&prop, h->cfg.device));
+    numSMs = prop.multiProcessorCount;
+  }
+  const size_t smemP = 2 * ((smem + 15) & ~size_t(15));
+  // measured on B200 (C2 workload): 16 resident warps per SM hide the shared-memory gather latency worse than the 32 of
+  // the one-shot kernel, so the persistent variant is opt-in until the gather is conflict-free
+  static const bool wantPersistent = getenv("APB_PRUNED_PERSISTENT") != nullptr;
+  const int part = h->prunedPart;  // set by apb_run_steps around the two halves of a split step
+  a.part = part;
+  a.numTiles = numTiles;
+  a.tileOrder = static_cast<const int *>(h->prTileOrder.p);
+  a.numInterior = a.tileOrder + numTiles;
+  const bool persistent = part == 0 && wantPersistent && smemP * PR_PBLOCKS + 1024 * PR_PBLOCKS <= 227 * 1024 && smemP <= 200 * 1024;
+  int numBlocks = numTiles;
+  if (persistent) numBlocks = std::min(numTiles, numSMs * PR_PBLOCKS);
+  APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * numBlocks));
+  a.partials = static_cast<LJStats *>(h->partials.p);
 #define PR_LAUNCH(MIXV, STATSV, DEADV, VIRV)                                                                         \
   do {                                                                                                               \
-    if (smem > 40 * 1024)                                                                                            \
-      APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV, VIRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    static_cast<int>(smem)));                                                       \
-    ++h->launchCount, kLJPruned<MIXV, STATSV, DEADV, VIRV><<<numTiles, PR_TILE, smem, h->stream>>>(a);               \
+    if (persistent) {                                                                                                \
+      APB_CUDA(cudaFuncSetAttribute(kLJPrunedP<MIXV, STATSV, DEADV, VIRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    static_cast<int>(smemP)));                                                      \
+      ++h->launchCount, kLJPrunedP<MIXV, STATSV, DEADV, VIRV><<<numBlocks, PR_TILE, smemP, h->stream>>>(a, numTiles); \
+    } else {                                                                                                         \
+      if (smem > 40 * 1024)                                                                                          \
+        APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV, VIRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      static_cast<int>(smem)));                                                     \
+      ++h->launchCount, kLJPruned<MIXV, STATSV, DEADV, VIRV><<<numTiles, PR_TILE, smem, h->stream>>>(a);             \
+    }                                                                                                                \
   } while (0)
   switch (sel) {
     case 0: PR_LAUNCH(false, false, false, false); break;
@@ -927,5 +1204,6 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
                                        " B, staged particles max " + std::to_string(h->prunedMaxCompact) + ")");
     }
   }
-  return apbFinishStats(h, numTiles, stats, f, out);
+  if (part == 1) return APB_OK;  // the boundary half follows and finishes the statistics
+  return apbFinishStats(h, numBlocks, stats, f, out);
 }

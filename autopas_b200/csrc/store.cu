@@ -212,7 +212,13 @@ extern "C" int apb_create(const apb_config *config, apb_handle *out) {
   }
   h->cfg = c;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    // the exchange stream outranks the compute stream: its small pack / NCCL / unpack kernels must get SM slots while
+    // the interior force kernel still has blocks waiting (split step of apb_run_steps)
+    int leastPriority = 0, greatestPriority = 0;
+    cudaDeviceGetStreamPriorityRange(&leastPriority, &greatestPriority);
+    e = cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, greatestPriority);
+  }
   if (e != cudaSuccess) {
     g_createError = std::string("apb_create: cudaStreamCreate: ") + cudaGetErrorString(e);
     delete h;
@@ -264,7 +270,8 @@ extern "C" int apb_destroy(apb_handle h) {
                     &h->stencilDev,   &h->clBoxMin,     &h->clBoxMax,     &h->clHasOwned,  &h->clIsHalo,
                     &h->clTower,      &h->twFirstCluster, &h->twNumClusters, &h->twFirstOwned, &h->twFirstTailHalo,
                     &h->nbrCount,     &h->nbrStart,     &h->nbrList,      &h->prNumStaged, &h->prStagedStart, &h->prStaged, &h->prWarpLen, &h->prWarpStart, &h->prLists,
-                    &h->partials,     &h->result,       &h->mixDev,       &h->leaverIdx};
+                    &h->partials,     &h->result,       &h->mixDev,       &h->leaverIdx, &h->idStage, &h->prTileHalo, &h->prTileOrder, &h->prMasks, &h->prUsed, &h->prCbase,
+                    &h->prNumCompact, &h->prCompactSlot};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   DevBuf *more[] = {&h->prTileFirst, &h->prTileNum, &h->prTileWarp, &h->loopResults, &h->invPerm, &h->xbuf[0], &h->xbuf[1], &h->xbuf[2], &h->xbuf[3], &h->massDev};
@@ -276,6 +283,8 @@ extern "C" int apb_destroy(apb_handle h) {
       if (h->link[d][s].recvSlot.p) cudaFree(h->link[d][s].recvSlot.p);
     }
   apbCommDestroy(h);
+  for (cudaEvent_t e : h->evSplit)
+    if (e) cudaEventDestroy(e);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
@@ -607,6 +616,102 @@ extern "C" int apb_download_forces(apb_handle h, double *fx, double *fy, double 
   if (h->nslots > 0 && (!fx || !fy || !fz)) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_download_forces: null destination");
   double *dst[3] = {fx, fy, fz};
   return transfer3(h, APB_COL_FX, nullptr, dst);
+}
+
+// ---- transfers through host arrays indexed by particle id -------------------------------------------------------------
+// The host side of a force step whose particle data lives in host memory (the C++ shim's mirror, md-flexible's own
+// arrays): only owned particles travel, and the host never has to learn the storage order.
+__global__ void kScatterPositionsById(int64_t n, const int32_t *__restrict__ own, const int64_t *__restrict__ id,
+                                      int64_t idBegin, int64_t numIds, const double *__restrict__ sx,
+                                      const double *__restrict__ sy, const double *__restrict__ sz, double *x, double *y,
+                                      double *z) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || own[i] != APB_OWN_OWNED) return;
+  const int64_t k = id[i] - idBegin;
+  if (k < 0 || k >= numIds) return;
+  x[i] = sx[k];
+  y[i] = sy[k];
+  z[i] = sz[k];
+}
+
+__global__ void kGatherForcesById(int64_t n, const int32_t *__restrict__ own, const int64_t *__restrict__ id,
+                                  int64_t idBegin, int64_t numIds, const double *__restrict__ fx,
+                                  const double *__restrict__ fy, const double *__restrict__ fz, double *sx, double *sy,
+                                  double *sz) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || own[i] != APB_OWN_OWNED) return;
+  const int64_t k = id[i] - idBegin;
+  if (k < 0 || k >= numIds) return;
+  sx[k] = fx[i];
+  sy[k] = fy[i];
+  sz[k] = fz[i];
+}
+
+static bool isPinnedHost(const void *p) {
+  cudaPointerAttributes attr;
+  const bool ok = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  return ok;
+}
+
+extern "C" int apb_upload_positions_by_id(apb_handle h, int64_t idBegin, int64_t numIds, const double *x, const double *y,
+                                          const double *z) {
+  APB_ENTRY(h);
+  if (numIds < 0 || (numIds > 0 && (!x || !y || !z)))
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_upload_positions_by_id: bad argument");
+  if (numIds == 0 || h->nslots == 0) return APB_OK;
+  const size_t bytes = sizeof(double) * numIds;
+  APB_CHECK(apbEnsure(h, h->idStage, 3 * bytes));
+  char *stage = static_cast<char *>(h->idStage.p);
+  const double *src[3] = {x, y, z};
+  const bool pinnedUser = isPinnedHost(x) && isPinnedHost(y) && isPinnedHost(z);
+  if (!pinnedUser) APB_CHECK(apbEnsurePinned(h, 3 * bytes));
+  for (int d = 0; d < 3; ++d) {
+    const void *from = src[d];
+    if (!pinnedUser) {
+      std::memcpy(static_cast<char *>(h->pinned) + d * bytes, src[d], bytes);
+      from = static_cast<char *>(h->pinned) + d * bytes;
+    }
+    APB_CUDA(cudaMemcpyAsync(stage + d * bytes, from, bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  ++h->launchCount, kScatterPositionsById<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(
+      h->nslots, h->own, h->id, idBegin, numIds, reinterpret_cast<const double *>(stage),
+      reinterpret_cast<const double *>(stage + bytes), reinterpret_cast<const double *>(stage + 2 * bytes), h->col[APB_COL_X],
+      h->col[APB_COL_Y], h->col[APB_COL_Z]);
+  APB_CUDA(cudaGetLastError());
+  APB_CUDA(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffers on return
+  return APB_OK;
+}
+
+extern "C" int apb_download_forces_by_id(apb_handle h, int64_t idBegin, int64_t numIds, double *fx, double *fy, double *fz) {
+  APB_ENTRY(h);
+  if (numIds < 0 || (numIds > 0 && (!fx || !fy || !fz)))
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_download_forces_by_id: bad argument");
+  if (numIds == 0) return APB_OK;
+  const size_t bytes = sizeof(double) * numIds;
+  APB_CHECK(apbEnsure(h, h->idStage, 3 * bytes));
+  char *stage = static_cast<char *>(h->idStage.p);
+  // ids without an owned particle on this device read as zero
+  APB_CUDA(cudaMemsetAsync(stage, 0, 3 * bytes, h->stream));
+  if (h->nslots > 0) {
+    ++h->launchCount, kGatherForcesById<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(
+        h->nslots, h->own, h->id, idBegin, numIds, h->col[APB_COL_FX], h->col[APB_COL_FY], h->col[APB_COL_FZ],
+        reinterpret_cast<double *>(stage), reinterpret_cast<double *>(stage + bytes),
+        reinterpret_cast<double *>(stage + 2 * bytes));
+    APB_CUDA(cudaGetLastError());
+  }
+  double *dst[3] = {fx, fy, fz};
+  if (isPinnedHost(fx) && isPinnedHost(fy) && isPinnedHost(fz)) {
+    for (int d = 0; d < 3; ++d)
+      APB_CUDA(cudaMemcpyAsync(dst[d], stage + d * bytes, bytes, cudaMemcpyDeviceToHost, h->stream));
+    APB_CUDA(cudaStreamSynchronize(h->stream));
+    return APB_OK;
+  }
+  APB_CHECK(apbEnsurePinned(h, 3 * bytes));
+  APB_CUDA(cudaMemcpyAsync(h->pinned, stage, 3 * bytes, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int d = 0; d < 3; ++d) std::memcpy(dst[d], static_cast<char *>(h->pinned) + d * bytes, bytes);
+  return APB_OK;
 }
 
 __global__ void kFill3(int64_t n, double *a, double *b, double *c, double va, double vb, double vc) {

@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 RHO = 0.8442
 CUTOFF, SKIN, REBUILD, DT = 2.5, 0.3, 10, 0.002
 METRIC = "MFUPs/s LJ fp64 force step"
+# BASELINE.json configs[2]: spinodal-decomposition start, 252^3 simple-cubic lattice at spacing 1.5,
+# Maxwell-Boltzmann velocities at T = 1.4, skin 0.5, deltaT 0.00182367; the TOTAL is fixed (strong scaling)
+C3 = {"n_per_dim": 252, "spacing": 1.5, "skin": 0.5, "dt": 0.00182367, "temperature": 1.4}
 
 
 def decomposition(n):
@@ -55,16 +58,29 @@ def coords_rank(c, dims):
     return (c[2] % dims[2] * dims[1] + c[1] % dims[1]) * dims[0] + c[0] % dims[0]
 
 
-def make_workload(n_per_dim, rank, dims, seed=42):
-    """100^3 simple-cubic lattice at rho* = 0.8442, jittered, one sub-box per rank."""
+def make_workload(n_per_dim, rank, dims, seed=42, workload="c2"):
+    """c2: 100^3 simple-cubic lattice at rho* = 0.8442, jittered, one sub-box of n_per_dim^3 per rank
+    (weak scaling). c3: the 252^3 lattice at spacing 1.5 split over the ranks (strong scaling), Brownian velocities."""
+    c = np.array(rank_coords(rank, dims), dtype=float)
+    rng = np.random.default_rng(seed + rank)
+    if workload == "c3":
+        spacing = C3["spacing"]
+        counts = [n_per_dim // d for d in dims]
+        if any(n_per_dim % d for d in dims):
+            raise SystemExit(f"c3: {n_per_dim} lattice points per dimension do not split over {dims}")
+        Ls = np.array(counts, dtype=float) * spacing
+        lo = c * Ls
+        gs = [(np.arange(k) + 0.5) * spacing for k in counts]
+        zz, yy, xx = np.meshgrid(gs[2], gs[1], gs[0], indexing="ij")
+        pos = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1) + lo
+        vel = rng.normal(0.0, np.sqrt(C3["temperature"]), pos.shape)
+        return pos, vel, lo, lo + Ls, np.zeros(3), np.array(dims, dtype=float) * Ls
     spacing = RHO ** (-1.0 / 3.0)
     L = n_per_dim * spacing
-    c = np.array(rank_coords(rank, dims), dtype=float)
     lo = c * L
     g = (np.arange(n_per_dim) + 0.5) * spacing
     zz, yy, xx = np.meshgrid(g, g, g, indexing="ij")
     pos = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1) + lo
-    rng = np.random.default_rng(seed + rank)
     pos += rng.uniform(-0.1, 0.1, pos.shape)
     vel = rng.normal(0.0, 1.0, pos.shape)
     vel -= vel.mean(axis=0)
@@ -94,6 +110,8 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if self.index is None:
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -168,35 +186,51 @@ def main():
     ap.add_argument("--newton3", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 (default): BASELINE configs[1], 1M-particle LJ liquid per GPU, weak scaling; "
+                         "c3: configs[2], the 16M-particle spinodal box split over the GPUs, strong scaling")
     ap.add_argument("--virial-components", action="store_true",
                     help="accumulate the virial per component instead of its sum (LJFunctor::getVirial returns the sum)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, world)
     dims = decomposition(world)
-    n_local = args.n_per_dim ** 3
-    workload = (f"C2 LJ liquid rho*=0.8442, {n_local} particles per GPU (jittered 100^3 lattice), cutoff 2.5, "
-                f"skin 0.3, rebuild every 10 steps, periodic")
+    global SKIN, DT
+    if args.workload == "c3":
+        SKIN, DT = C3["skin"], C3["dt"]
+        if args.n_per_dim == 100:
+            args.n_per_dim = C3["n_per_dim"]
+        workload = (f"C3 spinodal-decomposition LJ box, {args.n_per_dim ** 3} particles in total ({args.n_per_dim}^3 "
+                    f"lattice, spacing 1.5, T=1.4), cutoff 2.5, skin 0.5, rebuild every 10 steps, periodic")
+    else:
+        n_local = args.n_per_dim ** 3
+        workload = (f"C2 LJ liquid rho*=0.8442, {n_local} particles per GPU (jittered 100^3 lattice), cutoff 2.5, "
+                    f"skin 0.3, rebuild every 10 steps, periodic")
 
     if args.impl == "reference":
         if rank != 0:
             return
-        pos, vel, bmin, bmax, gmin, gmax = make_workload(args.n_per_dim, 0, [1, 1, 1])
+        pos, vel, bmin, bmax, gmin, gmax = make_workload(args.n_per_dim, 0, [1, 1, 1], workload=args.workload)
         ref = reference_arm(args, pos, bmin, bmax)
         if ref is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libautopas_ref.so was not built"}))
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libautopas_ref.so was not built"}), file=json_out, flush=True)
             return
         line = {"impl": "reference", "metric": METRIC, "value": ref["value"], "unit": "MFUPs/s", "n_gpus": n_gpus,
                 "steps": ref["iters"], "warmup": min(args.warmup, 1), "ms_per_step": ref["seconds"] / ref["iters"] * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if args.workload == "c3" else "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "container": "VerletClusterLists", "traversal": "vcl_c06",
                            "newton3": True, "cluster_size": 4, "host_threads": ref["cores"]},
                 "cpu_baseline": {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": ref["value"], "unit": "MFUPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return
 
     import torch
@@ -229,7 +263,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    pos, vel, bmin, bmax, gmin, gmax = make_workload(args.n_per_dim, rank, dims)
+    pos, vel, bmin, bmax, gmin, gmax = make_workload(args.n_per_dim, rank, dims, workload=args.workload)
     n = len(pos)
     c = GpuParticleContainer("gpuVerletClusterLists", bmin, bmax, CUTOFF, SKIN, clusterSize=args.cluster_size,
                              device=local_rank)
@@ -269,7 +303,7 @@ def main():
     # ---- device-resident timed region ----
     c.enableLoopTiming(True)
     c.getLoopTiming()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank if rank == 0 else None)  # one nvidia-smi poller per job, not per rank
     launches0 = c.getLaunchCount()
     barrier()
     sampler.start()
@@ -313,40 +347,63 @@ def main():
         roofline["hbm_peak_gbs_measured"] = None
 
     # ---- end to end through the C ABI with host buffers ----
+    # The host owns x, y, z and fx, fy, fz indexed by particle id (pinned). Every step: positions host -> device, [every
+    # 10th: migration, halo exchange, rebuild | halo refresh], force kernel, forces device -> host, Upot / virial read back.
     e2e_steps = max(REBUILD, (args.e2e_steps // REBUILD) * REBUILD)
-    cap = int(c.numSlots() * 1.3) + 4096
-    host = {k: torch.empty(cap, dtype=torch.float64).pin_memory().numpy() for k in ("x", "y", "z", "fx", "fy", "fz")}
-
-    def pull_positions():
-        ns = c.numSlots()
-        # (the mirror refresh after a rebuild: storage order changed)
-        lib = capi.load()
-        for k, col in (("x", "X"), ("y", "Y"), ("z", "Z")):
-            lib.apb_download_column(c._h, capi.COL[col], host[k].ctypes.data)
-        return ns
-
-    ns = pull_positions()
+    host = {k: torch.empty(n, dtype=torch.float64).pin_memory().numpy() for k in ("x", "y", "z", "fx", "fy", "fz")}
+    c.migrate()  # positions back into the (periodic) box before the host takes its copy
+    c.exchangeHalos()
+    c.rebuildNeighborLists(trav)
+    ids_s, _, own_s = c.downloadIds()
+    m_owned = own_s == capi.OWN_OWNED
+    k_owned = ids_s[m_owned] - rank * n
+    if not ((k_owned >= 0) & (k_owned < n)).all():
+        k_owned = None  # particles migrated between ranks during the device-resident run: fall back to slot order
+    for d, col in enumerate(("X", "Y", "Z")):
+        colv = c.downloadColumn(col)
+        if k_owned is not None:
+            host["xyz"[d]][k_owned] = colv[m_owned]
     h2d = d2h = 0
     upot_e2e = []
+    if k_owned is None:
+        cap = int(c.numSlots() * 1.3) + 4096
+        host = {k: torch.empty(cap, dtype=torch.float64).pin_memory().numpy() for k in ("x", "y", "z", "fx", "fy", "fz")}
+
+        def pull_positions():
+            lib = capi.load()
+            for k, col in (("x", "X"), ("y", "Y"), ("z", "Z")):
+                lib.apb_download_column(c._h, capi.COL[col], host[k].ctypes.data)
+            return c.numSlots()
+
+        ns = pull_positions()
     barrier()
     t0 = time.perf_counter()
     for it in range(e2e_steps):
-        c.uploadPositions(host["x"][:ns], host["y"][:ns], host["z"][:ns])
-        h2d += 3 * 8 * ns
+        if k_owned is not None:
+            c.uploadPositionsById(host["x"], host["y"], host["z"], idBegin=rank * n)
+            h2d += 3 * 8 * n
+        else:
+            c.uploadPositions(host["x"][:ns], host["y"][:ns], host["z"][:ns])
+            h2d += 3 * 8 * ns
         if it % REBUILD == 0:
             c.migrate()
             c.exchangeHalos()
             c.rebuildNeighborLists(trav)
-            ns = pull_positions()
-            d2h += 3 * 8 * ns
+            if k_owned is None:
+                ns = pull_positions()
+                d2h += 3 * 8 * ns
         else:
             c.exchangeHalos()
         c.resetForces()
         functor.initTraversal()
         raw = c.computeInteractions(trav)
         functor.endTraversal(bool(args.newton3))
-        c.downloadForces(host["fx"][:ns], host["fy"][:ns], host["fz"][:ns])
-        d2h += 3 * 8 * ns + ctypes.sizeof(raw)
+        if k_owned is not None:
+            c.downloadForcesById(host["fx"], host["fy"], host["fz"], idBegin=rank * n)
+            d2h += 3 * 8 * n + ctypes.sizeof(raw)
+        else:
+            c.downloadForces(host["fx"][:ns], host["fy"][:ns], host["fz"][:ns])
+            d2h += 3 * 8 * ns + ctypes.sizeof(raw)
         upot_e2e.append(functor.getPotentialEnergy())
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -354,7 +411,11 @@ def main():
     e2e = {"value": owned_total * e2e_steps / e2e_s * 1e-6, "unit": "MFUPs/s",
            "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
            "ms_per_step": e2e_s / e2e_steps * 1e3,
-           "note": "positions host->device and forces device->host every step (pinned buffers), Upot/virial read back"}
+           "note": ("positions host->device and forces device->host every step, pinned host arrays indexed by particle "
+                    "id (apb_upload_positions_by_id / apb_download_forces_by_id), Upot/virial read back"
+                    if k_owned is not None else
+                    "positions host->device and forces device->host every step in storage order (pinned), Upot/virial "
+                    "read back")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -368,7 +429,7 @@ def main():
     if rank == 0:
         g = c.getTraversalSelectorInfo()
         line = {"metric": METRIC, "value": value, "unit": "MFUPs/s", "n_gpus": n_gpus, "steps": steps, "warmup": warm,
-                "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong" if args.workload == "c3" else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "container": "gpuVerletClusterLists", "traversal": args.traversal,
                            "newton3": bool(args.newton3), "cluster_size": args.cluster_size,
@@ -380,7 +441,7 @@ def main():
                            "host_wall_ms_per_step": wall / steps * 1e3},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "upot_last": res[steps - 1].upot_sum * 0.5 / 6.0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     c.close()
     if world > 1:
         dist.destroy_process_group()

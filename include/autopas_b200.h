@@ -187,6 +187,14 @@ int apb_upload_ownership(apb_handle h, const int32_t *ownership); /* deleteParti
 /* fused transfers for the force step through host buffers: 3 columns each, pinned staging inside */
 int apb_upload_positions(apb_handle h, const double *x, const double *y, const double *z);
 int apb_download_forces(apb_handle h, double *fx, double *fy, double *fz);
+/* The same through host arrays indexed by particle id: entry k belongs to id id_begin + k (0 <= k < num_ids). Only
+ * owned particles are touched: positions are scattered to their slots on the device, forces gathered from them (ids
+ * without an owned particle on this device read as zero). The host does not need to know the storage order, so
+ * nothing has to be re-read after a rebuild; halo slots are refreshed by apb_exchange_halos / apb_update_halo_particles
+ * as usual. */
+int apb_upload_positions_by_id(apb_handle h, int64_t id_begin, int64_t num_ids, const double *x, const double *y,
+                               const double *z);
+int apb_download_forces_by_id(apb_handle h, int64_t id_begin, int64_t num_ids, double *fx, double *fy, double *fz);
 /* set force columns to a constant (TimeDiscretization.cpp:16-68 resets f to globalForce) */
 int apb_reset_forces(apb_handle h, double fx, double fy, double fz);
 

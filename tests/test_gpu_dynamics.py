@@ -177,3 +177,41 @@ def test_run_steps_matches_stepwise_calls_and_conserves_energy():
     assert abs(e_end - e0) <= 5e-3 * abs(ke0)
     a.close()
     b.close()
+
+
+def test_transfers_by_particle_id():
+    """apb_upload_positions_by_id / apb_download_forces_by_id: host arrays indexed by id, only owned particles travel."""
+    rng = np.random.default_rng(5)
+    n, nh, L = 3000, 300, 9.0
+    pos = rng.uniform(0, L, (n, 3))
+    halo = rng.uniform(-0.9, L + 0.9, (nh, 3))
+    halo = halo[((halo < 0) | (halo >= L)).any(axis=1)]
+    c = GpuParticleContainer("gpuVerletClusterLists", [0, 0, 0], [L, L, L], 1.0, 0.2, clusterSize=8)
+    base = 1000
+    c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(n) + base)
+    c.addHaloParticles(halo[:, 0], halo[:, 1], halo[:, 2], np.arange(len(halo)) + base + n)
+    f = LJFunctor(1.0, applyShift=True, calculateGlobals=True)
+    f.setParticleProperties(24.0, 1.0)
+    t = GpuTraversal("gpuvcl_pruned", f, False)
+    c.rebuildNeighborLists(t)
+    moved = pos + rng.uniform(-0.04, 0.04, pos.shape)  # < skin / 2
+    moved = np.clip(moved, 0, np.nextafter(L, 0))
+    c.uploadPositionsById(np.ascontiguousarray(moved[:, 0]), np.ascontiguousarray(moved[:, 1]),
+                          np.ascontiguousarray(moved[:, 2]), idBegin=base)
+    ids, _, own = c.downloadIds()
+    m = own == 1
+    for d, name in enumerate("XYZ"):
+        col = c.downloadColumn(name)
+        np.testing.assert_array_equal(col[m], moved[ids[m] - base, d])
+        hm = own == 2
+        np.testing.assert_array_equal(np.sort(col[hm]), np.sort(halo[:, d]))  # halo slots untouched
+    f.initTraversal()
+    c.computeInteractions(t)
+    f.endTraversal(False)
+    fx, fy, fz = np.full(n + 5, 7.0), np.full(n + 5, 7.0), np.full(n + 5, 7.0)
+    c.downloadForcesById(fx, fy, fz, idBegin=base)
+    for d, (name, arr) in enumerate((("FX", fx), ("FY", fy), ("FZ", fz))):
+        col = c.downloadColumn(name)
+        np.testing.assert_array_equal(arr[ids[m] - base], col[m])
+        np.testing.assert_array_equal(arr[n:], np.zeros(5))  # ids without an owned particle read as zero
+    c.close()
