@@ -136,6 +136,7 @@ SIGNATURES = {
     "apb_download_forces": (_i32, [_H, _vp, _vp, _vp]),
     "apb_upload_positions_by_id": (_i32, [_H, _i64, _i64, _vp, _vp, _vp]),
     "apb_download_forces_by_id": (_i32, [_H, _i64, _i64, _vp, _vp, _vp]),
+    "apb_force_step_by_id": (_i32, [_H, _i32, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "apb_reset_forces": (_i32, [_H, _f64, _f64, _f64]),
     "apb_update_container": (_i32, [_H, _i32, ctypes.POINTER(_i64)]),
     "apb_get_leavers": (_i32, [_H, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

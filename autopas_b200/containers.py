@@ -598,6 +598,19 @@ class GpuParticleContainer:
         functor._deposit(raw)
         return raw
 
+    def forceStepById(self, traversal, x, y, z, fx, fy, fz, rebuild, idBegin=0):
+        """apb_force_step_by_id: one force step for host arrays indexed by particle id; deposits the accumulators into
+        the functor like computeInteractions (bracket with functor.initTraversal() / endTraversal(newton3))."""
+        functor = traversal.functor
+        cf = functor._c_functor()
+        raw = capi.TraversalResult()
+        self._check(self._lib.apb_force_step_by_id(
+            self._h, capi.TRAVERSAL_NAMES[traversal.option], ctypes.byref(cf), 1 if traversal.useNewton3 else 0,
+            1 if rebuild else 0, int(idBegin), len(x), _ptr(x), _ptr(y), _ptr(z), _ptr(fx), _ptr(fy), _ptr(fz),
+            ctypes.byref(raw)))
+        functor._deposit(raw)
+        return raw
+
     # --- device-resident simulation loop
     def integratePositions(self, dt, massOfType, globalForce=None):
         m = _f64(np.atleast_1d(massOfType))

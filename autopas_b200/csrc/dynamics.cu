@@ -1143,6 +1143,55 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
   return APB_OK;
 }
 
+// One AutoPas::computeInteractions call for a caller whose particle data lives in host memory, as one stream-ordered
+// batch with a single host synchronisation at the end (rebuild steps additionally block where sizes are read back):
+// positions by id host -> device, [rebuild != 0: migration, halo exchange, neighbour-structure rebuild | halo refresh],
+// forces = 0, traversal, forces by id device -> host, accumulators.
+extern "C" int apb_force_step_by_id(apb_handle h, int32_t traversal, const apb_functor *functor, int32_t newton3,
+                                    int32_t rebuild, int64_t idBegin, int64_t numIds, const double *x, const double *y,
+                                    const double *z, double *fx, double *fy, double *fz, apb_traversal_result *out) {
+  APB_ENTRY(h);
+  if (!functor) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_force_step_by_id: null functor");
+  APB_CHECK(apbCheckTraversal(h, traversal, newton3));
+  APB_CHECK(apbEnsure(h, h->loopResults, sizeof(apb_traversal_result)));
+  apb_traversal_result *dres = static_cast<apb_traversal_result *>(h->loopResults.p);
+  const bool lj = functor->kind == APB_FUNCTOR_LJ;
+  apb_traversal_result host;
+  std::memset(&host, 0, sizeof(host));
+  h->deferSync = true;
+  int rc = apb_upload_positions_by_id(h, idBegin, numIds, x, y, z);
+  if (rc == APB_OK && (rebuild || !h->structureValid)) {
+    rc = apb_migrate(h, nullptr, nullptr);
+    if (rc == APB_OK) rc = apb_exchange_halos(h);
+    if (rc == APB_OK) rc = apb_rebuild_neighbor_lists(h, traversal, newton3);
+  } else if (rc == APB_OK) {
+    rc = apb_exchange_halos(h);
+  }
+  if (rc == APB_OK) rc = apb_reset_forces(h, 0., 0., 0.);
+  if (rc == APB_OK) {
+    if (lj) h->asyncResultDev = dres;  // the LJ kernels leave their reduced accumulators on the device
+    rc = apb_compute_interactions(h, traversal, functor, newton3, lj ? nullptr : &host);
+    h->asyncResultDev = nullptr;
+  }
+  h->deferSync = false;
+  if (rc != APB_OK) return rc;
+  if (lj) APB_CUDA(cudaMemcpyAsync(&host, dres, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+  APB_CHECK(apb_download_forces_by_id(h, idBegin, numIds, fx, fy, fz));  // synchronises
+  if (lj) {
+    if (!(functor->flags & APB_FUNCTOR_CALC_GLOBALS)) {
+      host.upot_sum = 0.;
+      host.virial_sum[0] = host.virial_sum[1] = host.virial_sum[2] = 0.;
+      host.num_global_calcs_n3 = host.num_global_calcs_no_n3 = 0;
+    }
+    if (!(functor->flags & APB_FUNCTOR_COUNT_FLOPS)) {
+      host.num_dist_calls = host.num_kernel_calls_n3 = host.num_kernel_calls_no_n3 = 0;
+      host.num_global_calcs_n3 = host.num_global_calcs_no_n3 = 0;
+    }
+  }
+  if (out) *out = host;
+  return APB_OK;
+}
+
 // the stream all work of this handle is enqueued on (for CUDA-event timing by the caller)
 extern "C" int apb_get_stream(apb_handle h, void **outStream) {
   APB_ENTRY(h);

@@ -679,7 +679,8 @@ extern "C" int apb_upload_positions_by_id(apb_handle h, int64_t idBegin, int64_t
       reinterpret_cast<const double *>(stage + bytes), reinterpret_cast<const double *>(stage + 2 * bytes), h->col[APB_COL_X],
       h->col[APB_COL_Y], h->col[APB_COL_Z]);
   APB_CUDA(cudaGetLastError());
-  APB_CUDA(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffers on return
+  // the caller may reuse its buffers on return; inside apb_force_step_by_id the step's final synchronisation covers it
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   return APB_OK;
 }
 
@@ -729,7 +730,7 @@ extern "C" int apb_reset_forces(apb_handle h, double fx, double fy, double fz) {
   ++h->launchCount, kFill3<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->col[APB_COL_FX], h->col[APB_COL_FY],
                                                           h->col[APB_COL_FZ], fx, fy, fz);
   APB_CUDA(cudaGetLastError());
-  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   return APB_OK;
 }
 

@@ -380,30 +380,31 @@ def main():
     t0 = time.perf_counter()
     for it in range(e2e_steps):
         if k_owned is not None:
-            c.uploadPositionsById(host["x"], host["y"], host["z"], idBegin=rank * n)
+            # one C-ABI call per step: apb_force_step_by_id (upload, [rebuild chain | halo refresh], forces, download)
+            functor.initTraversal()
+            raw = c.forceStepById(trav, host["x"], host["y"], host["z"], host["fx"], host["fy"], host["fz"],
+                                  rebuild=it % REBUILD == 0, idBegin=rank * n)
+            functor.endTraversal(bool(args.newton3))
             h2d += 3 * 8 * n
-        else:
-            c.uploadPositions(host["x"][:ns], host["y"][:ns], host["z"][:ns])
-            h2d += 3 * 8 * ns
+            d2h += 3 * 8 * n + ctypes.sizeof(raw)
+            upot_e2e.append(functor.getPotentialEnergy())
+            continue
+        c.uploadPositions(host["x"][:ns], host["y"][:ns], host["z"][:ns])
+        h2d += 3 * 8 * ns
         if it % REBUILD == 0:
             c.migrate()
             c.exchangeHalos()
             c.rebuildNeighborLists(trav)
-            if k_owned is None:
-                ns = pull_positions()
-                d2h += 3 * 8 * ns
+            ns = pull_positions()
+            d2h += 3 * 8 * ns
         else:
             c.exchangeHalos()
         c.resetForces()
         functor.initTraversal()
         raw = c.computeInteractions(trav)
         functor.endTraversal(bool(args.newton3))
-        if k_owned is not None:
-            c.downloadForcesById(host["fx"], host["fy"], host["fz"], idBegin=rank * n)
-            d2h += 3 * 8 * n + ctypes.sizeof(raw)
-        else:
-            c.downloadForces(host["fx"][:ns], host["fy"][:ns], host["fz"][:ns])
-            d2h += 3 * 8 * ns + ctypes.sizeof(raw)
+        c.downloadForces(host["fx"][:ns], host["fy"][:ns], host["fz"][:ns])
+        d2h += 3 * 8 * ns + ctypes.sizeof(raw)
         upot_e2e.append(functor.getPotentialEnergy())
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -412,7 +413,7 @@ def main():
            "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps, "steps": e2e_steps,
            "ms_per_step": e2e_s / e2e_steps * 1e3,
            "note": ("positions host->device and forces device->host every step, pinned host arrays indexed by particle "
-                    "id (apb_upload_positions_by_id / apb_download_forces_by_id), Upot/virial read back"
+                    "id, one apb_force_step_by_id call per step, Upot/virial read back"
                     if k_owned is not None else
                     "positions host->device and forces device->host every step in storage order (pinned), Upot/virial "
                     "read back")}

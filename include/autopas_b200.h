@@ -195,6 +195,13 @@ int apb_download_forces(apb_handle h, double *fx, double *fy, double *fz);
 int apb_upload_positions_by_id(apb_handle h, int64_t id_begin, int64_t num_ids, const double *x, const double *y,
                                const double *z);
 int apb_download_forces_by_id(apb_handle h, int64_t id_begin, int64_t num_ids, double *fx, double *fy, double *fz);
+/* One computeInteractions call for a caller whose particle data lives in host memory (LogicHandler::computeInteractionsPipeline,
+ * LogicHandler.h:1258, seen from md-flexible's arrays): positions by id host -> device, [rebuild != 0: migration, halo
+ * exchange, apb_rebuild_neighbor_lists | halo refresh], forces = 0, traversal, forces by id device -> host. Enqueued as
+ * one stream-ordered batch with a single host synchronisation at the end. */
+int apb_force_step_by_id(apb_handle h, int32_t traversal, const apb_functor *functor, int32_t newton3, int32_t rebuild,
+                         int64_t id_begin, int64_t num_ids, const double *x, const double *y, const double *z,
+                         double *fx, double *fy, double *fz, apb_traversal_result *out_result);
 /* set force columns to a constant (TimeDiscretization.cpp:16-68 resets f to globalForce) */
 int apb_reset_forces(apb_handle h, double fx, double fy, double fz);
 

@@ -215,3 +215,45 @@ def test_transfers_by_particle_id():
         np.testing.assert_array_equal(arr[ids[m] - base], col[m])
         np.testing.assert_array_equal(arr[n:], np.zeros(5))  # ids without an owned particle read as zero
     c.close()
+
+
+def test_force_step_by_id_equals_separate_calls():
+    """apb_force_step_by_id (one stream-ordered batch) against the same step through the individual entry points."""
+    rng = np.random.default_rng(11)
+    n, L = 4000, 10.0
+    pos = rng.uniform(0, L, (n, 3))
+    out = []
+    for fused in (False, True):
+        c = GpuParticleContainer("gpuVerletClusterLists", [0, 0, 0], [L, L, L], 1.0, 0.2, clusterSize=32)
+        c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(n))
+        f = LJFunctor(1.0, applyShift=True, calculateGlobals=True, countFLOPs=True)
+        f.setParticleProperties(24.0, 1.0)
+        t = GpuTraversal("gpuvcl_pruned", f, False)
+        x, y, z = (np.ascontiguousarray(pos[:, d]) for d in range(3))
+        fx, fy, fz = np.zeros(n), np.zeros(n), np.zeros(n)
+        res = []
+        for it in range(3):
+            moved = np.clip(pos + 0.01 * it, 0, np.nextafter(L, 0))  # displacement < skin / 2
+            x, y, z = (np.ascontiguousarray(moved[:, d]) for d in range(3))
+            f.initTraversal()
+            if fused:
+                c.forceStepById(t, x, y, z, fx, fy, fz, rebuild=it == 0)
+            else:
+                c.uploadPositionsById(x, y, z) if it > 0 else None
+                if it == 0:
+                    c.migrate()
+                    c.exchangeHalos()
+                    c.rebuildNeighborLists(t)
+                else:
+                    c.exchangeHalos()
+                c.resetForces()
+                c.computeInteractions(t)
+                c.downloadForcesById(fx, fy, fz)
+            f.endTraversal(False)
+            res.append((np.stack([fx, fy, fz], 1).copy(), f.getPotentialEnergy(), f.getVirial(), f.getNumFLOPs()))
+        out.append(res)
+        c.close()
+    for a, b in zip(*out):
+        np.testing.assert_array_equal(a[0], b[0])
+        assert a[1:] == b[1:]
+    assert np.abs(out[0][-1][0]).max() > 0
