@@ -168,7 +168,8 @@ class GpuLJFunctor
     FunctorDescriptor d;
     d.functor.kind = APB_FUNCTOR_LJ;
     d.functor.flags = (applyShift ? APB_FUNCTOR_APPLY_SHIFT : 0) | (useMixing ? APB_FUNCTOR_USE_MIXING : 0) |
-                      (calculateGlobals ? APB_FUNCTOR_CALC_GLOBALS : 0) | (countFLOPs ? APB_FUNCTOR_COUNT_FLOPS : 0);
+                      (calculateGlobals ? APB_FUNCTOR_CALC_GLOBALS : 0) | (countFLOPs ? APB_FUNCTOR_COUNT_FLOPS : 0) |
+                      APB_FUNCTOR_VIRIAL_TRACE;  // getVirial() returns the sum of the components (LJFunctor.h:719)
     d.functor.cutoff = _cutoff;
     d.functor.epsilon24 = _epsilon24;
     d.functor.sigma_squared = _sigmaSquared;

@@ -340,6 +340,13 @@ def main():
                                "MEASURED_PEAKS.json holds no FP64 figure",
                 "share_of_step": force_ms / ms_total,
                 "phases_ms_per_step": {k: v[0] / steps for k, v in timing.items()}}
+    if args.workload == "c2" and args.traversal == "gpuvcl_pruned" and args.n_per_dim == 100:
+        try:  # DRAM bytes per launch of this kernel on this workload, from the committed ncu --set full capture
+            roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "kLJPruned_traffic.json")))["dram_bytes_per_launch"]
+            roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)"
+            roofline["algorithmic_bytes_per_launch"] = int(n * 48 + np.mean([r.num_dist_calls for r in res]) * 2)
+        except (OSError, ValueError, KeyError):
+            pass
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roofline["hbm_peak_gbs_measured"] = peaks.get("hbm_gbs")
