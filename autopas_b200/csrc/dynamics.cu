@@ -206,6 +206,7 @@ extern "C" int apb_integrate_positions(apb_handle h, double dt, const double *ma
   APB_ENTRY(h);
   if (!h->active[APB_COL_OLDFX]) return h->fail(APB_ERR_NOT_APPLICABLE, "particle kind has no oldF columns");
   APB_CHECK(uploadMasses(h, massOfType, numTypes));
+  h->ownedInsideBox = false;
   if (h->nslots == 0) return APB_OK;
   const double g[3] = {globalForce ? globalForce[0] : 0., globalForce ? globalForce[1] : 0.,
                        globalForce ? globalForce[2] : 0.};
@@ -688,6 +689,10 @@ int apbRemapHaloLinks(apb_handle h, const int *perm, int64_t nOld, int64_t nNew)
   int *inv = static_cast<int *>(h->invPerm.p);
   APB_CUDA(cudaMemsetAsync(inv, 0xFF, sizeof(int) * std::max<int64_t>(nOld, 1), h->stream));
   if (nNew > 0) ++h->launchCount, kInvertPerm<<<apbDivUp(nNew, 256), 256, 0, h->stream>>>(nNew, perm, inv);
+  if (h->haloAllMode && h->haloAllN > 0) {
+    ++h->launchCount, kRemap<<<apbDivUp(h->haloAllN, 256), 256, 0, h->stream>>>(h->haloAllN, static_cast<int *>(h->haloAllSrc.p), inv, nOld);
+    ++h->launchCount, kRemap<<<apbDivUp(h->haloAllN, 256), 256, 0, h->stream>>>(h->haloAllN, static_cast<int *>(h->haloAllDst.p), inv, nOld);
+  }
   for (int d = 0; d < 3; ++d)
     for (int s = 0; s < 2; ++s) {
       HaloLink &L = h->link[d][s];
@@ -888,6 +893,183 @@ static int exchangeDim(apb_handle h, int d, int mode) {
   return APB_OK;
 }
 
+// ---- single rank, fully periodic: all periodic images in one pass -----------------------------------------------------
+// With every dimension its own neighbour the three forwarding rounds of exchangeHaloParticles
+// (RegularGridDecomposition.cpp:159-236) produce exactly the images  r + (sx, sy, sz),  s_d in {0, +L_d if r_d in
+// [min, min + il), -L_d if r_d in [max - il, max)}, not all zero, of every owned particle (owned particles lie inside the
+// box after apb_migrate, so the widened forwarding ranges of halo copies never matter). One selection pass, one append,
+// one host read-back instead of three of each; the refresh is one slot-to-slot kernel.
+struct ImageArgs {
+  int64_t n;
+  const int32_t *own;
+  const double *x, *y, *z;
+  double lo[3], hi[3], il;
+};
+__device__ __forceinline__ int imageOptions(const ImageArgs &a, int64_t i, int opt[3]) {
+  opt[0] = opt[1] = opt[2] = 0;
+  if (i >= a.n || a.own[i] != APB_OWN_OWNED) return 0;
+  const double p[3] = {a.x[i], a.y[i], a.z[i]};
+  int count = 1;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int nearMin = p[d] >= a.lo[d] && p[d] < a.lo[d] + a.il, nearMax = p[d] >= a.hi[d] - a.il && p[d] < a.hi[d];
+    opt[d] = nearMin | (nearMax << 1);
+    count *= 1 + nearMin + nearMax;
+  }
+  return count - 1;
+}
+__global__ void __launch_bounds__(SEL_BLOCK) kImageCount(ImageArgs a, int *__restrict__ blockCounts) {
+  __shared__ int sw[SEL_BLOCK / 32];
+  int opt[3];
+  const int c = imageOptions(a, static_cast<int64_t>(blockIdx.x) * SEL_BLOCK + threadIdx.x, opt);
+  const int w = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < SEL_BLOCK / 32; ++k) t += sw[k];
+    blockCounts[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(SEL_BLOCK) kImageWrite(ImageArgs a, const int *__restrict__ blockOffsets, int *__restrict__ src,
+                                                        int *__restrict__ code) {
+  __shared__ int sw[SEL_BLOCK / 32];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * SEL_BLOCK + threadIdx.x;
+  int opt[3];
+  const int c = imageOptions(a, i, opt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = c;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sw[warp] = incl;
+  __syncthreads();
+  int pos = blockOffsets[blockIdx.x] + incl - c;
+  for (int k = 0; k < warp; ++k) pos += sw[k];
+  if (c == 0) return;
+  for (int cz = 0; cz < 3; ++cz)
+    for (int cy = 0; cy < 3; ++cy)
+      for (int cx = 0; cx < 3; ++cx) {
+        if (cx + cy + cz == 0) continue;
+        if ((cx && !((opt[0] >> (cx - 1)) & 1)) || (cy && !((opt[1] >> (cy - 1)) & 1)) || (cz && !((opt[2] >> (cz - 1)) & 1)))
+          continue;
+        src[pos] = static_cast<int>(i);
+        code[pos] = cx + 3 * cy + 9 * cz;
+        ++pos;
+      }
+}
+__device__ __forceinline__ double imageShift(int digit, double L) { return digit == 1 ? L : (digit == 2 ? -L : 0.); }
+
+struct ImageAppendArgs {
+  int64_t count, firstSlot;
+  const int *src, *code;
+  int *dst;
+  double L[3];
+  double *x, *y, *z;
+  int nOther;
+  double *other[APB_NUM_COLUMNS];  // active columns other than x, y, z: zero-filled like kUnpackAppend does
+  int64_t *id;
+  int32_t *type, *own;
+};
+__global__ void kImageAppend(ImageAppendArgs a) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= a.count) return;
+  const int s = a.src[q], c = a.code[q];
+  const int64_t t = a.firstSlot + q;
+  a.x[t] = a.x[s] + imageShift(c % 3, a.L[0]);
+  a.y[t] = a.y[s] + imageShift((c / 3) % 3, a.L[1]);
+  a.z[t] = a.z[s] + imageShift(c / 9, a.L[2]);
+  for (int k = 0; k < a.nOther; ++k) a.other[k][t] = 0.;
+  a.id[t] = a.id[s];
+  a.type[t] = a.type[s];
+  a.own[t] = APB_OWN_HALO;
+  a.dst[q] = static_cast<int>(t);
+}
+// refresh of the images (non-rebuild steps): a source or image slot that the rebuild dropped is skipped
+__global__ void kImageRefresh(int64_t m, const int *__restrict__ src, const int *__restrict__ dst, const int *__restrict__ code,
+                              double Lx, double Ly, double Lz, double *x, double *y, double *z) {
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const int s = src[q], t = dst[q], c = code[q];
+  if (s < 0 || t < 0) return;
+  x[t] = x[s] + imageShift(c % 3, Lx);
+  y[t] = y[s] + imageShift((c / 3) % 3, Ly);
+  z[t] = z[s] + imageShift(c / 9, Lz);
+}
+
+static bool allDimsSelf(apb_handle h) {
+  for (int d = 0; d < 3; ++d)
+    if (!h->periodic[d] || h->neighbor[d][0] != h->myRank || h->neighbor[d][1] != h->myRank ||
+        !nearRel(h->cfg.box_min[d], h->globalMin[d]) || !nearRel(h->cfg.box_max[d], h->globalMax[d]))
+      return false;
+  return true;
+}
+
+static int generateImagesAllSelf(apb_handle h) {
+  const int64_t n = h->nslots;
+  h->haloAllN = 0;
+  h->haloAllMode = true;
+  if (n == 0) return APB_OK;
+  ImageArgs a;
+  a.n = n;
+  a.own = h->own;
+  a.x = h->col[APB_COL_X];
+  a.y = h->col[APB_COL_Y];
+  a.z = h->col[APB_COL_Z];
+  for (int d = 0; d < 3; ++d) {
+    a.lo[d] = h->cfg.box_min[d];
+    a.hi[d] = h->cfg.box_max[d];
+  }
+  a.il = h->cfg.cutoff + h->cfg.skin;
+  const int numBlocks = apbDivUp(n, SEL_BLOCK);
+  APB_CHECK(apbEnsure(h, h->key, sizeof(int) * (numBlocks + 1)));
+  APB_CHECK(apbEnsure(h, h->rank, sizeof(int) * (numBlocks + 1)));
+  int *blockCounts = static_cast<int *>(h->key.p), *blockOffsets = static_cast<int *>(h->rank.p);
+  long long *totals = reinterpret_cast<long long *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result));
+  ++h->launchCount, kImageCount<<<numBlocks, SEL_BLOCK, 0, h->stream>>>(a, blockCounts);
+  APB_CUDA(cudaGetLastError());
+  APB_CUDA(cudaMemsetAsync(blockCounts + numBlocks, 0, sizeof(int), h->stream));
+  APB_CHECK(apbExclusiveScan(h, blockCounts, blockOffsets, numBlocks + 1, totals));
+  long long total = 0;
+  APB_CUDA(cudaMemcpyAsync(&total, totals, 8, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (total == 0) return APB_OK;
+  if (n + total > 0x7fffffffLL) return h->fail(APB_ERR_NOT_APPLICABLE, "halo generation exceeds 2^31 slots");
+  APB_CHECK(apbEnsure(h, h->haloAllSrc, sizeof(int) * total));
+  APB_CHECK(apbEnsure(h, h->haloAllDst, sizeof(int) * total));
+  APB_CHECK(apbEnsure(h, h->haloAllCode, sizeof(int) * total));
+  APB_CHECK(apbReserveSlots(h, n + total));
+  a.own = h->own;  // the reservation may have moved the columns
+  a.x = h->col[APB_COL_X];
+  a.y = h->col[APB_COL_Y];
+  a.z = h->col[APB_COL_Z];
+  ++h->launchCount, kImageWrite<<<numBlocks, SEL_BLOCK, 0, h->stream>>>(a, blockOffsets, static_cast<int *>(h->haloAllSrc.p),
+                                                                      static_cast<int *>(h->haloAllCode.p));
+  ImageAppendArgs u;
+  u.count = total;
+  u.firstSlot = n;
+  u.src = static_cast<const int *>(h->haloAllSrc.p);
+  u.code = static_cast<const int *>(h->haloAllCode.p);
+  u.dst = static_cast<int *>(h->haloAllDst.p);
+  for (int d = 0; d < 3; ++d) u.L[d] = h->globalMax[d] - h->globalMin[d];
+  u.x = h->col[APB_COL_X];
+  u.y = h->col[APB_COL_Y];
+  u.z = h->col[APB_COL_Z];
+  u.nOther = 0;
+  for (int c = 0; c < APB_NUM_COLUMNS; ++c)
+    if (h->active[c] && c != APB_COL_X && c != APB_COL_Y && c != APB_COL_Z) u.other[u.nOther++] = h->col[c];
+  u.id = h->id;
+  u.type = h->type;
+  u.own = h->own;
+  ++h->launchCount, kImageAppend<<<apbDivUp(total, 256), 256, 0, h->stream>>>(u);
+  APB_CUDA(cudaGetLastError());
+  h->nslots = n + total;
+  h->haloAllN = total;
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
 static int ensureDecomposition(apb_handle h) {
   if (h->decompositionSet) return APB_OK;
   if (h->nranks != 1) return h->fail(APB_ERR_STATE, "apb_set_decomposition must be called on multi-rank runs");
@@ -904,6 +1086,29 @@ static int ensureDecomposition(apb_handle h) {
 // RegularGridDecomposition::exchangeMigratingParticles (:238-301) fused with the container update that precedes it in
 // the simulation loop (Simulation.cpp:247-263): halos and dummies are dropped, owned particles that left the local box
 // travel to the neighbour (wrapped at periodic global boundaries), arrivals are appended as owned.
+// Migration in a dimension in which this rank is its own neighbour (periodic, one rank wide): the leaver re-enters
+// through the opposite face, i.e. its coordinate is wrapped in place - same arithmetic as kPack's shift + clamp
+// (RegularGridDecomposition.cpp:575-590), no selection, no compaction, no append.
+__global__ void kWrapSelf(int64_t n, const int32_t *__restrict__ own, double *x, double *y, double *z, int dimMask,
+                          double lx, double ly, double lz, double hx, double hy, double hz) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || own[i] != APB_OWN_OWNED) return;
+  double *col[3] = {x, y, z};
+  const double lo[3] = {lx, ly, lz}, hi[3] = {hx, hy, hz};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (!((dimMask >> d) & 1)) continue;
+    const double p = col[d][i];
+    const double L = hi[d] - lo[d];
+    if (p < lo[d] || p >= hi[d]) {
+      double v = p < lo[d] ? p + L : p - L;
+      if (v >= hi[d]) v = nextafter(hi[d], lo[d]);
+      if (v < lo[d]) v = lo[d];
+      col[d][i] = v;
+    }
+  }
+}
+
 extern "C" int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num_received) {
   APB_ENTRY(h);
   APB_CHECK(ensureDecomposition(h));
@@ -911,10 +1116,25 @@ extern "C" int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num
   h->haloLinksValid = false;
   const int64_t before = h->nslots;
   int64_t received = 0;
+  int selfMask = 0;
   for (int d = 0; d < 3; ++d) {
+    const bool self = h->periodic[d] && h->neighbor[d][0] == h->myRank && h->neighbor[d][1] == h->myRank &&
+                      nearRel(h->cfg.box_min[d], h->globalMin[d]) && nearRel(h->cfg.box_max[d], h->globalMax[d]);
+    if (self) {
+      selfMask |= 1 << d;
+      continue;
+    }
     const int64_t n0 = h->nslots;
     APB_CHECK(exchangeDim(h, d, 1));
     received += h->nslots - n0;
+  }
+  // self dimensions last: arrivals of the exchanged dimensions are wrapped as well (the dimensions are independent)
+  if (selfMask && h->nslots > 0) {
+    ++h->launchCount, kWrapSelf<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(
+        h->nslots, h->own, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], selfMask, h->globalMin[0],
+        h->globalMin[1], h->globalMin[2], h->globalMax[0], h->globalMax[1], h->globalMax[2]);
+    APB_CUDA(cudaGetLastError());
+    if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   }
   (void)before;
   // Sent particles and the old halos are dummies now. They are not compacted here: the rebuild that must follow drops
@@ -924,6 +1144,7 @@ extern "C" int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num
   h->structureValid = false;
   h->prunedValid = false;
   h->countsValid = false;
+  h->ownedInsideBox = true;
   return APB_OK;
 }
 
@@ -937,12 +1158,29 @@ extern "C" int apb_exchange_halos(apb_handle h) {
     APB_CHECK(apb_delete_halo_particles(h));
     for (int d = 0; d < 3; ++d)
       for (int s = 0; s < 2; ++s) h->link[d][s].nSend = h->link[d][s].nRecv = 0;
-    for (int d = 0; d < 3; ++d) APB_CHECK(exchangeDim(h, d, 0));
+    h->haloAllMode = false;
+    h->haloAllN = 0;
+    static const bool noOnePass = getenv("APB_NO_ONEPASS_HALO") != nullptr;
+    if (h->ownedInsideBox && !noOnePass && allDimsSelf(h))
+      APB_CHECK(generateImagesAllSelf(h));
+    else
+      for (int d = 0; d < 3; ++d) APB_CHECK(exchangeDim(h, d, 0));
     h->haloLinksValid = true;
     h->countsValid = false;
     return APB_OK;
   }
   if (!h->haloLinksValid) return h->fail(APB_ERR_STATE, "apb_exchange_halos: no halo links recorded; call it once before the rebuild");
+  if (h->haloAllMode) {
+    if (h->haloAllN > 0) {
+      ++h->launchCount, kImageRefresh<<<apbDivUp(h->haloAllN, 256), 256, 0, h->stream>>>(
+          h->haloAllN, static_cast<const int *>(h->haloAllSrc.p), static_cast<const int *>(h->haloAllDst.p),
+          static_cast<const int *>(h->haloAllCode.p), h->globalMax[0] - h->globalMin[0], h->globalMax[1] - h->globalMin[1],
+          h->globalMax[2] - h->globalMin[2], h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z]);
+      APB_CUDA(cudaGetLastError());
+    }
+    if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+    return APB_OK;
+  }
   APB_CHECK(ensureP2P(h));
   ++h->p2pSeq;
   for (int d = 0; d < 3; ++d) {

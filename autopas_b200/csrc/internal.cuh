@@ -143,6 +143,12 @@ struct apb_handle_s {
   int p2pState = 0;                        // 0 not set up yet, 1 ready, -1 not applicable
   int *p2pCounters = nullptr;              // 3 block counters (last-block-signals pattern)
   bool haloLinksValid = false;
+  // single rank, all dimensions periodic: every halo copy is a direct image of an owned particle (one pass instead of
+  // three forwarding rounds); haloAllSrc / Dst / Code = source slot, halo slot, shift code (base 3: 0 none, 1 +L, 2 -L)
+  DevBuf haloAllSrc, haloAllDst, haloAllCode;
+  long long haloAllN = 0;
+  bool haloAllMode = false;
+  bool ownedInsideBox = false;  // set by apb_migrate, cleared by whatever moves or adds particles
   HaloLink link[3][2];
   DevBuf invPerm, xbuf[4], massDev;
   std::vector<double> massHost;

@@ -271,7 +271,7 @@ extern "C" int apb_destroy(apb_handle h) {
                     &h->clTower,      &h->twFirstCluster, &h->twNumClusters, &h->twFirstOwned, &h->twFirstTailHalo,
                     &h->nbrCount,     &h->nbrStart,     &h->nbrList,      &h->prNumStaged, &h->prStagedStart, &h->prStaged, &h->prWarpLen, &h->prWarpStart, &h->prLists,
                     &h->partials,     &h->result,       &h->mixDev,       &h->leaverIdx, &h->idStage, &h->prTileHalo, &h->prTileOrder, &h->prMasks, &h->prUsed, &h->prCbase,
-                    &h->prNumCompact, &h->prCompactSlot};
+                    &h->prNumCompact, &h->prCompactSlot, &h->haloAllSrc, &h->haloAllDst, &h->haloAllCode};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   DevBuf *more[] = {&h->prTileFirst, &h->prTileNum, &h->prTileWarp, &h->loopResults, &h->invPerm, &h->xbuf[0], &h->xbuf[1], &h->xbuf[2], &h->xbuf[3], &h->massDev};
@@ -308,6 +308,7 @@ __global__ void kFillAppended(int64_t first, int64_t n, int64_t *id, int32_t *ty
 extern "C" int apb_add_particles(apb_handle h, int64_t n, const double *x, const double *y, const double *z,
                                  const int64_t *ids, const int32_t *types, int32_t ownership, int32_t check_box) {
   APB_ENTRY(h);
+  h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
   if (n < 0 || (n > 0 && (!x || !y || !z))) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_add_particles: null positions");
   if (ownership != APB_OWN_OWNED && ownership != APB_OWN_HALO)
     return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_add_particles: ownership must be owned (1) or halo (2)");
@@ -527,6 +528,7 @@ extern "C" int apb_download_column(apb_handle h, int32_t column, double *dst) {
 
 extern "C" int apb_upload_column(apb_handle h, int32_t column, const double *src) {
   APB_ENTRY(h);
+  h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
   APB_CHECK(checkColumn(h, column));
   if (h->nslots == 0) return APB_OK;
   if (!src) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_upload_column: null source");
@@ -548,6 +550,7 @@ extern "C" int apb_download_ids(apb_handle h, int64_t *ids, int32_t *types, int3
 
 extern "C" int apb_upload_ownership(apb_handle h, const int32_t *ownership) {
   APB_ENTRY(h);
+  h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
   if (h->nslots == 0) return APB_OK;
   if (!ownership) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_upload_ownership: null source");
   APB_CUDA(cudaMemcpyAsync(h->own, ownership, sizeof(int32_t) * h->nslots, cudaMemcpyHostToDevice, h->stream));
@@ -606,6 +609,7 @@ static int transfer3(apb_handle h, int firstCol, const double *const src[3], dou
 
 extern "C" int apb_upload_positions(apb_handle h, const double *x, const double *y, const double *z) {
   APB_ENTRY(h);
+  h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
   if (h->nslots > 0 && (!x || !y || !z)) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_upload_positions: null source");
   const double *src[3] = {x, y, z};
   return transfer3(h, APB_COL_X, src, nullptr);
@@ -657,6 +661,7 @@ static bool isPinnedHost(const void *p) {
 extern "C" int apb_upload_positions_by_id(apb_handle h, int64_t idBegin, int64_t numIds, const double *x, const double *y,
                                           const double *z) {
   APB_ENTRY(h);
+  h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
   if (numIds < 0 || (numIds > 0 && (!x || !y || !z)))
     return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_upload_positions_by_id: bad argument");
   if (numIds == 0 || h->nslots == 0) return APB_OK;
