@@ -1279,12 +1279,13 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
   // APB_DEBUG_TIMING: host wall time spent inside each phase call (where the host blocks on count read-backs / peers)
   static const bool dbgTiming = getenv("APB_DEBUG_TIMING") != nullptr;
   // Overlapped halo refresh (interior / boundary split of the force step). The two partial force launches cost about
-  // 0.02 ms of tail effects; measured on 8 x B200 the split pays once all three dimensions exchange with remote ranks
-  // (13.5 -> 14.3 GFUPs/s), at 2 GPUs (one remote dimension) it is a wash. APB_SPLIT_STEP=0 / 1 overrides.
+  // 0.02 ms of tail effects; measured on B200s the split pays from two exchanging dimensions on (4 GPUs: 7.4 -> 7.8,
+  // 8 GPUs: 13.5 -> 14.3 GFUPs/s), at 2 GPUs (one remote dimension) it is a wash. APB_SPLIT_STEP=0 / 1 overrides.
+  // (A single resident kernel for all three refresh rounds was tried as well: no gain over the per-dimension kernels.)
   int remoteDims = 0;
   for (int d = 0; d < 3; ++d) remoteDims += h->neighbor[d][0] != h->myRank || h->neighbor[d][1] != h->myRank;
   const char *splitEnv = getenv("APB_SPLIT_STEP");
-  const bool noSplit = splitEnv ? atoi(splitEnv) == 0 : remoteDims < 3;
+  const bool noSplit = splitEnv ? atoi(splitEnv) == 0 : remoteDims < 2;
   double hostMs[5] = {0, 0, 0, 0, 0};
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int s = 0; s < numSteps && rc == APB_OK; ++s) {
