@@ -189,6 +189,34 @@ __global__ void kIntegrateVelocities(int64_t n, const int32_t *__restrict__ own,
   vz[i] += (fz[i] + ofz[i]) * s;
 }
 
+// calculateVelocities of step s followed by calculatePositionsAndResetForces of step s + 1 in one pass over the
+// particles (same arithmetic, expression by expression, as the two kernels above): 24 instead of 30 column passes.
+__global__ void kIntegrateVelocitiesPositions(int64_t n, const int32_t *__restrict__ own, const int32_t *__restrict__ type,
+                                              const double *__restrict__ massOfType, int numTypes, double dt, double gx,
+                                              double gy, double gz, double *x, double *y, double *z, double *vx, double *vy,
+                                              double *vz, double *fx, double *fy, double *fz, double *ofx, double *ofy,
+                                              double *ofz) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || own[i] != APB_OWN_OWNED) return;
+  const int t = type[i];
+  const double m = massOfType[t < numTypes ? t : 0];
+  const double sv = dt / (2 * m), sx = dt * dt / (2 * m);
+  const double Fx = fx[i], Fy = fy[i], Fz = fz[i];
+  const double Vx = vx[i] + (Fx + ofx[i]) * sv, Vy = vy[i] + (Fy + ofy[i]) * sv, Vz = vz[i] + (Fz + ofz[i]) * sv;
+  vx[i] = Vx;
+  vy[i] = Vy;
+  vz[i] = Vz;
+  ofx[i] = Fx;
+  ofy[i] = Fy;
+  ofz[i] = Fz;
+  fx[i] = gx;
+  fy[i] = gy;
+  fz[i] = gz;
+  x[i] += Vx * dt + Fx * sx;
+  y[i] += Vy * dt + Fy * sx;
+  z[i] += Vz * dt + Fz * sx;
+}
+
 static int uploadMasses(apb_handle h, const double *mass, int numTypes) {
   if (numTypes <= 0 || !mass) return h->fail(APB_ERR_INVALID_ARGUMENT, "integrate: need at least one type mass");
   if (h->massHost.size() != static_cast<size_t>(numTypes) ||
@@ -217,6 +245,24 @@ extern "C" int apb_integrate_positions(apb_handle h, double dt, const double *ma
       h->col[APB_COL_OLDFZ]);
   APB_CUDA(cudaGetLastError());
   if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+// velocities of the finished step + positions of the next one (apb_run_steps between two steps)
+static int integrateVelocitiesPositions(apb_handle h, double dt, const double *massOfType, int32_t numTypes,
+                                        const double *globalForce) {
+  if (!h->active[APB_COL_OLDFX]) return h->fail(APB_ERR_NOT_APPLICABLE, "particle kind has no oldF columns");
+  APB_CHECK(uploadMasses(h, massOfType, numTypes));
+  h->ownedInsideBox = false;
+  if (h->nslots == 0) return APB_OK;
+  const double g[3] = {globalForce ? globalForce[0] : 0., globalForce ? globalForce[1] : 0.,
+                       globalForce ? globalForce[2] : 0.};
+  ++h->launchCount, kIntegrateVelocitiesPositions<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(
+      h->nslots, h->own, h->type, static_cast<const double *>(h->massDev.p), numTypes, dt, g[0], g[1], g[2],
+      h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->col[APB_COL_VX], h->col[APB_COL_VY], h->col[APB_COL_VZ],
+      h->col[APB_COL_FX], h->col[APB_COL_FY], h->col[APB_COL_FZ], h->col[APB_COL_OLDFX], h->col[APB_COL_OLDFY],
+      h->col[APB_COL_OLDFZ]);
+  APB_CUDA(cudaGetLastError());
   return APB_OK;
 }
 
@@ -1290,10 +1336,12 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int s = 0; s < numSteps && rc == APB_OK; ++s) {
     const int64_t it = firstIteration + s;
-    apbLoopTimingRecord(h, 3, true);
-    rc = apb_integrate_positions(h, p->dt, p->mass_of_type, p->num_types, p->global_force);
-    apbLoopTimingRecord(h, 3, false);
-    if (rc != APB_OK) break;
+    if (s == 0) {  // later steps: positions were advanced together with the previous step's velocities
+      apbLoopTimingRecord(h, 3, true);
+      rc = apb_integrate_positions(h, p->dt, p->mass_of_type, p->num_types, p->global_force);
+      apbLoopTimingRecord(h, 3, false);
+      if (rc != APB_OK) break;
+    }
     const bool rebuild = (it % p->rebuild_frequency == 0) || !h->structureValid;
     if (rebuild) {
       apbLoopTimingRecord(h, 1, true);
@@ -1340,7 +1388,8 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
       h->asyncResultDev = nullptr;
       if (rc != APB_OK) break;
       apbLoopTimingRecord(h, 3, true);
-      rc = apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
+      rc = s + 1 < numSteps ? integrateVelocitiesPositions(h, p->dt, p->mass_of_type, p->num_types, p->global_force)
+                            : apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
       apbLoopTimingRecord(h, 3, false);
       continue;
     } else {
@@ -1358,7 +1407,8 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
     h->asyncResultDev = nullptr;
     if (rc != APB_OK) break;
     apbLoopTimingRecord(h, 3, true);
-    rc = apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
+    rc = s + 1 < numSteps ? integrateVelocitiesPositions(h, p->dt, p->mass_of_type, p->num_types, p->global_force)
+                          : apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
     apbLoopTimingRecord(h, 3, false);
   }
   h->deferSync = false;
