@@ -102,6 +102,7 @@ struct apb_handle_s {
   int prunedWarps = 0;
   DevBuf prNumStaged, prStagedStart, prStaged, prWarpLen, prWarpStart, prLists, prTileFirst, prTileNum, prTileWarp;
   DevBuf prMasks, prUsed, prCbase, prNumCompact, prCompactSlot;
+  DevBuf prEntryLo;
   DevBuf prTileHalo, prTileOrder;  // per tile: stages a halo copy; tiles ordered interior first (+ the interior count)
   int prunedPart = 0;              // 0: whole traversal; 1 / 2: interior / boundary half of a split step (apb_run_steps)
   cudaEvent_t evSplit[2] = {nullptr, nullptr};

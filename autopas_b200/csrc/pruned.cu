@@ -170,6 +170,7 @@ __global__ void kPrunedTiles(int numTiles, int nbx, int nzc, int nx, int ny, int
 // its exclusive prefix (compact index base): the force kernel stages only referenced particles.
 struct MaskOut {
   unsigned *masks;
+  int *entryLo;  // per mask row: index of the partner cluster in the tile's staged set (saves kPrunedFill the search)
   int *warpRows;
   unsigned *used;   // [totalStaged]
   int *cbase;       // [totalStaged]
@@ -288,6 +289,7 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
           if (e < e0) m &= ~(1u << lane);
           if (!active) m = 0u;
           *mrow = m;
+          if (lane == 0) o.entryLo[static_cast<size_t>(e) + 1 + A] = lo;
           cnt += __popc(m);
           const unsigned wm = __reduce_or_sync(0xffffffffu, m);
           if (lane == 0 && wm) atomicOr(&used[lo], wm);
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
         }
         if (e < e0) m &= ~(1u << li);
         o.masks[(static_cast<size_t>(e) + 1 + A) * a.M + li] = m;
+        o.entryLo[static_cast<size_t>(e) + 1 + A] = lo;  // same value from every lane of the cluster
         cnt += __popc(m);
         if (m) atomicOr(&used[lo], m);
       }
@@ -415,16 +418,15 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   const int e0 = active ? a.nbrStart[A] : 0, e1 = active ? a.nbrStart[A + 1] : -1;
   int cnt = 0;
   // software pipelined: the next entry's cluster id and mask are loaded while the current one is expanded
-  int Bn = A;
+  int lon = e1 >= e0 ? o.entryLo[static_cast<size_t>(e0) + A] : 0;
   unsigned mn = e1 >= e0 ? o.masks[(static_cast<size_t>(e0) + A) * a.M + li] : 0u;
   for (int e = e0 - 1; e < e1; ++e) {
-    const int B = Bn;
+    const int lo = lon;
     unsigned m = mn;
     if (e + 1 < e1) {
-      Bn = a.nbrList[e + 1];
+      lon = o.entryLo[static_cast<size_t>(e) + 2 + A];
       mn = o.masks[(static_cast<size_t>(e) + 2 + A) * a.M + li];
     }
-    const int lo = prLowerBound(stg, nS, B);
     const unsigned u = used[lo];
     const int cb = cbase[lo];
     while (m) {
@@ -561,6 +563,8 @@ int apbBuildPruned(apb_handle h) {
   APB_CUDA(cudaGetLastError());
   MaskOut o;
   o.masks = static_cast<unsigned *>(h->prMasks.p);
+  APB_CHECK(apbEnsure(h, h->prEntryLo, sizeof(int) * static_cast<size_t>(h->numPairs + h->numClusters + 2)));
+  o.entryLo = static_cast<int *>(h->prEntryLo.p);
   o.warpRows = warpRows;
   o.used = static_cast<unsigned *>(h->prUsed.p);
   o.cbase = static_cast<int *>(h->prCbase.p);
