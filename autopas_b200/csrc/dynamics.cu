@@ -1213,6 +1213,7 @@ extern "C" int apb_exchange_halos(apb_handle h) {
       for (int d = 0; d < 3; ++d) APB_CHECK(exchangeDim(h, d, 0));
     h->haloLinksValid = true;
     h->countsValid = false;
+    h->noHalos = false;
     return APB_OK;
   }
   if (!h->haloLinksValid) return h->fail(APB_ERR_STATE, "apb_exchange_halos: no halo links recorded; call it once before the rebuild");

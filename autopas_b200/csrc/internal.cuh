@@ -149,6 +149,7 @@ struct apb_handle_s {
   DevBuf haloAllSrc, haloAllDst, haloAllCode;
   long long haloAllN = 0;
   bool haloAllMode = false;
+  bool noHalos = false;         // set by apb_delete_halo_particles, cleared when halo copies may exist again
   bool ownedInsideBox = false;  // set by apb_migrate, cleared by whatever moves or adds particles
   HaloLink link[3][2];
   DevBuf invPerm, xbuf[4], massDev;

@@ -280,11 +280,16 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
           unsigned cand = __ballot_sync(0xffffffffu, fmaf(gz, gz, fmaf(gy, gy, gx * gx)) <= thrBox);
           unsigned m = 0u;
           while (cand) {
-            const int k = __ffs(cand) - 1;
+            // two candidates per iteration (independent load -> distance chains); an odd last one is evaluated twice
+            const int k0 = __ffs(cand) - 1;
             cand &= cand - 1;
-            const float4 pj = rb[k];
-            const float dx = ri.x - pj.x, dy = ri.y - pj.y, dz = ri.z - pj.z;
-            if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) m |= 1u << k;
+            const int k1 = cand ? __ffs(cand) - 1 : k0;
+            cand &= cand - 1;
+            const float4 p0 = rb[k0], p1 = rb[k1];
+            const float dx0 = ri.x - p0.x, dy0 = ri.y - p0.y, dz0 = ri.z - p0.z;
+            const float dx1 = ri.x - p1.x, dy1 = ri.y - p1.y, dz1 = ri.z - p1.z;
+            if (fmaf(dz0, dz0, fmaf(dy0, dy0, dx0 * dx0)) <= thr) m |= 1u << k0;
+            if (fmaf(dz1, dz1, fmaf(dy1, dy1, dx1 * dx1)) <= thr) m |= 1u << k1;
           }
           if (e < e0) m &= ~(1u << lane);
           if (!active) m = 0u;

@@ -132,7 +132,50 @@ static int scanRec(apb_handle h, const int *in, int *out, int64_t n, int *scratc
   return APB_OK;
 }
 
+// Arrays of up to 2^18 elements (towers, tiles, warps, clusters of a 1 M-particle container) are scanned by ONE block
+// in one launch, total included: the rebuild chain is launch-latency bound on slow hosts, and the recursive version
+// costs four launches per scan.
+#define SCAN_SMALL_MAX (1 << 18)
+__global__ void __launch_bounds__(1024) kScanSmall(const int *__restrict__ in, int *__restrict__ out, int n, long long *total) {
+  __shared__ int warpSums[32];
+  const int chunk = (n + 1023) / 1024;
+  const int b = min(static_cast<int>(threadIdx.x) * chunk, n), e = min(b + chunk, n);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += in[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warpSums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warpSums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    warpSums[lane] = w;
+  }
+  __syncthreads();
+  int run = (warp == 0 ? 0 : warpSums[warp - 1]) + incl - sum;
+  for (int i = b; i < e; ++i) {
+    const int v = in[i];  // read before the write: in and out may alias
+    out[i] = run;
+    run += v;
+  }
+  if (total && threadIdx.x == 1023) *total = warpSums[31];
+}
+
 int apbExclusiveScan(apb_handle h, const int *in, int *out, int64_t n, long long *totalDev) {
+  if (n > 0 && n <= SCAN_SMALL_MAX) {
+    ++h->launchCount, kScanSmall<<<1, 1024, 0, h->stream>>>(in, out, static_cast<int>(n), totalDev);
+    APB_CUDA(cudaGetLastError());
+    return APB_OK;
+  }
   if (n > 0) {
     const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     APB_CHECK(apbEnsure(h, h->scanTmp, sizeof(int) * (4 * nb + 64)));
@@ -309,6 +352,7 @@ extern "C" int apb_add_particles(apb_handle h, int64_t n, const double *x, const
                                  const int64_t *ids, const int32_t *types, int32_t ownership, int32_t check_box) {
   APB_ENTRY(h);
   h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
+  h->noHalos = false;
   if (n < 0 || (n > 0 && (!x || !y || !z))) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_add_particles: null positions");
   if (ownership != APB_OWN_OWNED && ownership != APB_OWN_HALO)
     return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_add_particles: ownership must be owned (1) or halo (2)");
@@ -364,6 +408,8 @@ __global__ void kDeleteHalo(int64_t n, int32_t *own) {
 
 extern "C" int apb_delete_halo_particles(apb_handle h) {
   APB_ENTRY(h);
+  if (h->noHalos) return APB_OK;  // nothing was added since the last call (apb_migrate followed by apb_exchange_halos)
+  h->noHalos = true;
   if (h->nslots > 0) {
     ++h->launchCount, kDeleteHalo<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->own);
     APB_CUDA(cudaGetLastError());
@@ -466,14 +512,31 @@ extern "C" int apb_update_halo_particles(apb_handle h, int64_t n, const int64_t 
   return APB_OK;
 }
 
-__global__ void kCountOwnership(int64_t n, const int32_t *own, unsigned long long *counts) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int o = i < n ? own[i] : 0;
-  const unsigned owned = __ballot_sync(0xffffffffu, o == APB_OWN_OWNED);
-  const unsigned halo = __ballot_sync(0xffffffffu, o == APB_OWN_HALO);
+// grid-stride, one atomic pair per block: 37 k same-address atomics (one per warp) cost 28 us at 1.2 M slots
+__global__ void __launch_bounds__(256) kCountOwnership(int64_t n, const int32_t *own, unsigned long long *counts) {
+  __shared__ unsigned so[8], sh[8];
+  unsigned owned = 0, halo = 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int o = own[i];
+    owned += o == APB_OWN_OWNED;
+    halo += o == APB_OWN_HALO;
+  }
+  owned = __reduce_add_sync(0xffffffffu, owned);
+  halo = __reduce_add_sync(0xffffffffu, halo);
   if ((threadIdx.x & 31) == 0) {
-    if (owned) atomicAdd(&counts[0], static_cast<unsigned long long>(__popc(owned)));
-    if (halo) atomicAdd(&counts[1], static_cast<unsigned long long>(__popc(halo)));
+    so[threadIdx.x >> 5] = owned;
+    sh[threadIdx.x >> 5] = halo;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long to = 0, th = 0;
+    for (int w = 0; w < 8; ++w) {
+      to += so[w];
+      th += sh[w];
+    }
+    if (to) atomicAdd(&counts[0], to);
+    if (th) atomicAdd(&counts[1], th);
   }
 }
 
@@ -486,7 +549,7 @@ extern "C" int apb_get_num_particles(apb_handle h, int64_t *out_owned, int64_t *
       unsigned long long *d =
           reinterpret_cast<unsigned long long *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 64);
       APB_CUDA(cudaMemsetAsync(d, 0, 16, h->stream));
-      ++h->launchCount, kCountOwnership<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(h->nslots, h->own, d);
+      ++h->launchCount, kCountOwnership<<<static_cast<unsigned>(std::min<int64_t>(apbDivUp(h->nslots, 256), 1184)), 256, 0, h->stream>>>(h->nslots, h->own, d);
       APB_CUDA(cudaGetLastError());
       APB_CUDA(cudaMemcpyAsync(counts, d, 16, cudaMemcpyDeviceToHost, h->stream));
       APB_CUDA(cudaStreamSynchronize(h->stream));
@@ -529,6 +592,7 @@ extern "C" int apb_download_column(apb_handle h, int32_t column, double *dst) {
 extern "C" int apb_upload_column(apb_handle h, int32_t column, const double *src) {
   APB_ENTRY(h);
   h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
+  h->noHalos = false;
   APB_CHECK(checkColumn(h, column));
   if (h->nslots == 0) return APB_OK;
   if (!src) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_upload_column: null source");
@@ -551,6 +615,7 @@ extern "C" int apb_download_ids(apb_handle h, int64_t *ids, int32_t *types, int3
 extern "C" int apb_upload_ownership(apb_handle h, const int32_t *ownership) {
   APB_ENTRY(h);
   h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
+  h->noHalos = false;
   if (h->nslots == 0) return APB_OK;
   if (!ownership) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_upload_ownership: null source");
   APB_CUDA(cudaMemcpyAsync(h->own, ownership, sizeof(int32_t) * h->nslots, cudaMemcpyHostToDevice, h->stream));
@@ -610,6 +675,7 @@ static int transfer3(apb_handle h, int firstCol, const double *const src[3], dou
 extern "C" int apb_upload_positions(apb_handle h, const double *x, const double *y, const double *z) {
   APB_ENTRY(h);
   h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
+  h->noHalos = false;
   if (h->nslots > 0 && (!x || !y || !z)) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_upload_positions: null source");
   const double *src[3] = {x, y, z};
   return transfer3(h, APB_COL_X, src, nullptr);
@@ -662,6 +728,7 @@ extern "C" int apb_upload_positions_by_id(apb_handle h, int64_t idBegin, int64_t
                                           const double *z) {
   APB_ENTRY(h);
   h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
+  h->noHalos = false;
   if (numIds < 0 || (numIds > 0 && (!x || !y || !z)))
     return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_upload_positions_by_id: bad argument");
   if (numIds == 0 || h->nslots == 0) return APB_OK;
