@@ -108,7 +108,7 @@ struct apb_handle_s {
   cudaEvent_t evSplit[2] = {nullptr, nullptr};
 
   // ---- reductions / results ----
-  DevBuf partials;
+  DevBuf partials, partials2;
   DevBuf result;  // apb_traversal_result on device
   DevBuf mixDev;
   std::vector<double> mixHostCache;

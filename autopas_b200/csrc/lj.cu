@@ -50,6 +50,33 @@ __global__ void __launch_bounds__(1024) kReducePartials(const LJStats *__restric
   }
 }
 
+// first stage for many partials (16 M-particle containers have ~10^5 tiles): block b sums the contiguous slice b and
+// writes one LJStats behind the partials; the single-block kernel above then finishes. Slices and orders are fixed.
+__global__ void __launch_bounds__(256) kReducePartialsStage1(const LJStats *__restrict__ partials, int numBlocks, int slice,
+                                                             LJStats *__restrict__ out) {
+  LJStats s;
+  ljStatsZero(s);
+  const int b0 = blockIdx.x * slice, b1 = min(b0 + slice, numBlocks);
+  for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x) ljStatsAdd(s, partials[b]);
+  ljStatsBlockReduce(s, out);
+}
+
+int apbReducePartials(apb_handle h, int numBlocks, apb_traversal_result *dst) {
+  const LJStats *partials = static_cast<const LJStats *>(h->partials.p);
+  if (numBlocks > 16384) {
+    const int stage1Blocks = 128, slice = (numBlocks + stage1Blocks - 1) / stage1Blocks;
+    // room behind the partials: apbEnsure may move the buffer, so the caller's partials are re-read from the handle
+    APB_CHECK(apbEnsure(h, h->partials2, sizeof(LJStats) * stage1Blocks));
+    LJStats *mid = static_cast<LJStats *>(h->partials2.p);
+    ++h->launchCount, kReducePartialsStage1<<<stage1Blocks, 256, 0, h->stream>>>(partials, numBlocks, slice, mid);
+    ++h->launchCount, kReducePartials<<<1, 1024, 0, h->stream>>>(mid, stage1Blocks, dst);
+  } else {
+    ++h->launchCount, kReducePartials<<<1, 1024, 0, h->stream>>>(partials, numBlocks, dst);
+  }
+  APB_CUDA(cudaGetLastError());
+  return APB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // LinkedCells: one thread per particle slot (slots are sorted by cell), neighbour cells from the stencil
 // ------------------------------------------------------------------------------------------------------------------
@@ -334,18 +361,14 @@ int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f
   if (h->asyncResultDev) {
     // device-resident loop (apb_run_steps): the reduced accumulators stay on the device, no host sync per step
     if (stats && numBlocks > 0) {
-      ++h->launchCount, kReducePartials<<<1, 1024, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
-                                                h->asyncResultDev);
-      APB_CUDA(cudaGetLastError());
+      APB_CHECK(apbReducePartials(h, numBlocks, h->asyncResultDev));
     } else {
       APB_CUDA(cudaMemsetAsync(h->asyncResultDev, 0, sizeof(apb_traversal_result), h->stream));
     }
     return APB_OK;
   }
   if (stats && numBlocks > 0) {
-    ++h->launchCount, kReducePartials<<<1, 1024, 0, h->stream>>>(static_cast<const LJStats *>(h->partials.p), numBlocks,
-                                              static_cast<apb_traversal_result *>(h->result.p));
-    APB_CUDA(cudaGetLastError());
+    APB_CHECK(apbReducePartials(h, numBlocks, static_cast<apb_traversal_result *>(h->result.p)));
     APB_CUDA(cudaMemcpyAsync(&host, h->result.p, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
   }
   APB_CUDA(cudaStreamSynchronize(h->stream));

@@ -314,7 +314,7 @@ extern "C" int apb_destroy(apb_handle h) {
                     &h->clTower,      &h->twFirstCluster, &h->twNumClusters, &h->twFirstOwned, &h->twFirstTailHalo,
                     &h->nbrCount,     &h->nbrStart,     &h->nbrList,      &h->prNumStaged, &h->prStagedStart, &h->prStaged, &h->prWarpLen, &h->prWarpStart, &h->prLists,
                     &h->partials,     &h->result,       &h->mixDev,       &h->leaverIdx, &h->idStage, &h->prTileHalo, &h->prTileOrder, &h->prMasks, &h->prUsed, &h->prCbase,
-                    &h->prNumCompact, &h->prCompactSlot, &h->haloAllSrc, &h->haloAllDst, &h->haloAllCode, &h->prEntryLo};
+                    &h->prNumCompact, &h->prCompactSlot, &h->haloAllSrc, &h->haloAllDst, &h->haloAllCode, &h->prEntryLo, &h->partials2};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   DevBuf *more[] = {&h->prTileFirst, &h->prTileNum, &h->prTileWarp, &h->loopResults, &h->invPerm, &h->xbuf[0], &h->xbuf[1], &h->xbuf[2], &h->xbuf[3], &h->massDev};
