@@ -632,6 +632,29 @@ static inline double *p2pRegion(void *arena, size_t cap, int d, int s, int parit
 static inline unsigned long long *p2pFlag(void *arena, size_t cap, int d, int s) {
   return reinterpret_cast<unsigned long long *>(static_cast<double *>(arena) + 12 * cap) + (d * 2 + s);
 }
+// count slots of the generating exchange: {count, sequence number} per (dimension, side, parity)
+static inline long long *p2pCountSlot(void *arena, size_t cap, int d, int s, int parity) {
+  return reinterpret_cast<long long *>(reinterpret_cast<char *>(static_cast<double *>(arena) + 12 * cap) + 64) +
+         2 * ((d * 2 + s) * 2 + parity);
+}
+// my two send counts (device values of the selection) go straight into the neighbours' count slots
+__global__ void kPushCounts(const long long *__restrict__ counts, long long *slot0, long long *slot1, long long seq) {
+  *reinterpret_cast<volatile long long *>(slot0) = counts[0];
+  *reinterpret_cast<volatile long long *>(slot1) = counts[1];
+  __threadfence_system();
+  *reinterpret_cast<volatile long long *>(slot0 + 1) = seq;
+  *reinterpret_cast<volatile long long *>(slot1 + 1) = seq;
+  __threadfence_system();
+}
+__global__ void kPullCounts(const long long *slot0, const long long *slot1, long long seq, long long *out) {
+  while (*reinterpret_cast<const volatile long long *>(slot0 + 1) < seq) {
+  }
+  while (*reinterpret_cast<const volatile long long *>(slot1 + 1) < seq) {
+  }
+  __threadfence_system();
+  out[0] = *reinterpret_cast<const volatile long long *>(slot0);
+  out[1] = *reinterpret_cast<const volatile long long *>(slot1);
+}
 
 // One-time set-up: allocate the arena, trade IPC handles with the distinct neighbour ranks (NCCL send / recv) and map
 // theirs. Every rank of the decomposition reaches this at the same point (its first halo refresh), so the pairwise
@@ -650,7 +673,7 @@ static int ensureP2P(apb_handle h) {
   size_t mb = 24;  // per region; 12 regions
   if (const char *e = getenv("APB_HALO_ARENA_MB")) mb = std::max<long>(1, atol(e));
   h->p2pCap = mb * 1024 * 1024 / sizeof(double);
-  const size_t bytes = 12 * h->p2pCap * sizeof(double) + 64;
+  const size_t bytes = 12 * h->p2pCap * sizeof(double) + 64 + 192;  // regions | 6 flags | 12 count slots
   APB_CUDA(cudaMalloc(&h->p2pArena, bytes));
   APB_CUDA(cudaMemsetAsync(h->p2pArena, 0, bytes, h->stream));
   APB_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->p2pCounters), 4 * sizeof(int)));
@@ -805,6 +828,7 @@ static bool nearRel(double a, double b) {
 // One dimension of a generating exchange (halo generation or migration).
 // mode 0: halo generation (packed columns: x, y, z); mode 1: migration (all active columns).
 static int exchangeDim(apb_handle h, int d, int mode) {
+  if (h->nranks > 1) APB_CHECK(ensureP2P(h));  // every rank passes here in the same order: the handle trade matches up
   const int64_t n = h->nslots;
   const double lmin = h->cfg.box_min[d], lmax = h->cfg.box_max[d];
   const double il = h->cfg.cutoff + h->cfg.skin;
@@ -838,10 +862,30 @@ static int exchangeDim(apb_handle h, int d, int mode) {
     ++h->launchCount, kScanBlockCounts<<<1, 1024, 0, h->stream>>>(numBlocks, blockCounts, totals);
     ++h->launchCount, kSelectWrite<<<numBlocks, SEL_BLOCK, 0, h->stream>>>(sa, blockCounts, pl, pr);
     APB_CUDA(cudaGetLastError());
+  } else {
+    APB_CUDA(cudaMemsetAsync(totals, 0, 16, h->stream));
+  }
+  const int left = h->neighbor[d][0], right = h->neighbor[d][1];
+  const bool remote = h->nranks > 1 && !(left == h->myRank && right == h->myRank);
+  if (remote && h->p2pState == 1 && per && h->p2pPeer[d][0] && h->p2pPeer[d][1]) {
+    // counts through the peer arenas: no NCCL round and one host read-back (send and receive counts together)
+    const long long seq = static_cast<long long>(++h->p2pCountSeq);
+    const int parity = static_cast<int>(seq & 1);
+    const int to0 = left == right ? 0 : 1, to1 = left == right ? 1 : 0;  // same matching as the payload (see the refresh)
+    ++h->launchCount, kPushCounts<<<1, 1, 0, h->stream>>>(totals, p2pCountSlot(h->p2pPeer[d][0], h->p2pCap, d, to0, parity),
+                                                        p2pCountSlot(h->p2pPeer[d][1], h->p2pCap, d, to1, parity), seq);
+    ++h->launchCount, kPullCounts<<<1, 1, 0, h->stream>>>(p2pCountSlot(h->p2pArena, h->p2pCap, d, 0, parity),
+                                                        p2pCountSlot(h->p2pArena, h->p2pCap, d, 1, parity), seq, totals + 2);
+    APB_CUDA(cudaGetLastError());
+    long long both[4];
+    APB_CUDA(cudaMemcpyAsync(both, totals, 32, cudaMemcpyDeviceToHost, h->stream));
+    APB_CUDA(cudaStreamSynchronize(h->stream));
+    sendCount[0] = both[0], sendCount[1] = both[1], recvCount[0] = both[2], recvCount[1] = both[3];
+  } else {
     APB_CUDA(cudaMemcpyAsync(sendCount, totals, 16, cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaStreamSynchronize(h->stream));
+    APB_CHECK(exchangeCounts(h, d, sendCount, recvCount));
   }
-  APB_CHECK(exchangeCounts(h, d, sendCount, recvCount));
   // packed columns
   int ncols = 0;
   int colIds[APB_NUM_COLUMNS];
