@@ -125,24 +125,6 @@ __global__ void kKeysLC(int64_t n, const double *__restrict__ x, const double *_
   key[i] = k;
 }
 
-__global__ void kKeysVCL(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
-                         const double *__restrict__ z, const int32_t *__restrict__ own, VCLGeom g,
-                         int *__restrict__ key, int *__restrict__ rank, int *__restrict__ count) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int k = -1;
-  if (own[i] != APB_OWN_DUMMY) {
-    const double px = x[i], py = y[i], pz = z[i];
-    // VerletClusterListsRebuilder::sortParticlesIntoTowers (:217-232): only particles inside the halo box are kept
-    const bool in = px >= g.haloBoxMin[0] && px < g.haloBoxMax[0] && py >= g.haloBoxMin[1] && py < g.haloBoxMax[1] &&
-                    pz >= g.haloBoxMin[2] && pz < g.haloBoxMax[2];
-    if (in) {
-      k = apbTowerIndex(g, px, py);
-      rank[i] = atomicAdd(&count[k], 1);
-    }
-  }
-  key[i] = k;
-}
 
 __global__ void kPadCounts(int64_t n, const int *__restrict__ count, int *__restrict__ padded, int M, int *maxCount) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -834,10 +816,6 @@ extern "C" int apb_get_geometry(apb_handle h, apb_geometry *out) {
   return APB_OK;
 }
 
-__global__ void kWiden(int64_t n, const int *__restrict__ src, int64_t *__restrict__ dst) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[i];
-}
 
 extern "C" int apb_debug_cell_of_slot(apb_handle h, int64_t *out) {
   APB_ENTRY(h);

@@ -486,36 +486,6 @@ __global__ void kUnpackAppend(UnpackArgs a) {
   if (a.recvSlot) a.recvSlot[q] = static_cast<int>(s);
 }
 
-// refresh: gather positions of the recorded send slots (+ shift), scatter into the recorded receive slots
-__global__ void kGatherPositions(int64_t m, const int *__restrict__ idx, const double *x, const double *y,
-                                 const double *z, int dim, double shift, double *out) {
-  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q >= m) return;
-  const int s = idx[q];
-  // a source that the rebuild dropped sends NaN: the receiver then keeps the stale copy
-  double px = nan(""), py = 0., pz = 0.;
-  if (s >= 0) {
-    px = x[s];
-    py = y[s];
-    pz = z[s];
-    if (dim == 0) px += shift;
-    if (dim == 1) py += shift;
-    if (dim == 2) pz += shift;
-  }
-  out[q] = px;
-  out[m + q] = py;
-  out[2 * m + q] = pz;
-}
-__global__ void kScatterPositions(int64_t m, const int *__restrict__ slot, const double *in, double *x, double *y,
-                                  double *z) {
-  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q >= m) return;
-  const int s = slot[q];
-  if (s < 0 || isnan(in[q])) return;
-  x[s] = in[q];
-  y[s] = in[m + q];
-  z[s] = in[2 * m + q];
-}
 
 // both sides of one dimension in one launch (the refresh is launch-latency bound: a few thousand particles per message)
 __global__ void kGatherPositions2(int64_t m0, int64_t m1, const int *__restrict__ idx0, const int *__restrict__ idx1,

@@ -250,7 +250,9 @@ int apb_integrate_positions(apb_handle h, double dt, const double *mass_of_type,
 int apb_integrate_velocities(apb_handle h, double dt, const double *mass_of_type, int32_t num_types);
 
 /* Regular-grid spatial decomposition of examples/md-flexible/src/domainDecomposition/RegularGridDecomposition.cpp,
- * one rank per GPU, NCCL send/recv over NVLink instead of MPI (ParticleCommunicator.cpp:38-61).
+ * one rank per GPU, over NVLink instead of MPI (ParticleCommunicator.cpp:38-61): NCCL send/recv for the payload of the
+ * generating exchanges (rebuild steps); counts and the per-step halo refresh go through peer memory (arenas mapped with
+ * CUDA IPC among the ranks of one node; APB_NO_P2P_HALO=1 on all ranks keeps everything on NCCL).
  * apb_comm_get_unique_id: rank 0 creates the 128-byte NCCL id, the host distributes it (e.g. torch.distributed).
  * apb_comm_init: MPI_Cart_create analogue (:106); nranks == 1 needs no id and no NCCL.
  * apb_set_decomposition: this rank's box is apb_config.box_*; neighbours6 = {left,right} rank per dimension
@@ -262,11 +264,13 @@ int apb_set_decomposition(apb_handle h, const double *global_box_min, const doub
                           const int32_t *neighbours6, const int32_t *periodic3);
 /* AutoPas::updateContainer + RegularGridDecomposition::exchangeMigratingParticles (:238-301) fused on the device:
  * halos dropped, owned particles outside the local box travel to the neighbour per dimension (periodic wrap at global
- * boundaries), arrivals become owned. Invalidates the structure (a rebuild must follow). */
+ * boundaries), arrivals become owned. Invalidates the structure (a rebuild must follow). In a dimension in which the
+ * rank is its own neighbour the coordinate is wrapped in place; the out counts cover the exchanged dimensions only. */
 int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num_received);
 /* RegularGridDecomposition::exchangeHaloParticles (:159-236). Structure invalid (rebuild step): select + append halos,
  * x then y then z, forwarding received halos. Structure valid: refresh the positions of the existing halo copies only
- * (bulk updateHaloParticle), same three-phase order, fixed message sizes. */
+ * (bulk updateHaloParticle), same three-phase order, fixed message sizes. A single fully periodic rank called after
+ * apb_migrate generates (and later refreshes) all periodic images in one pass - the same set of halo copies. */
 int apb_exchange_halos(apb_handle h);
 /* MPI_Reduce(SUM) of potential energy / virial in Simulation.cpp:319-322, as ncclAllReduce; no-op for one rank */
 int apb_allreduce_globals(apb_handle h, apb_traversal_result *inout);
