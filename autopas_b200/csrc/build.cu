@@ -383,6 +383,8 @@ static int *scratchMax(apb_handle h) {
 // LinkedCells rebuild
 // ------------------------------------------------------------------------------------------------------------------
 int apbRebuildLinkedCells(apb_handle h) {
+  if (!h->ownedInsideBox) h->ownedKnown = false;  // (see apbRebuildVCL)
+  h->countsTrusted = false;
   const int64_t n = h->nslots;
   const int64_t nc = h->lc.numCells;
   APB_CHECK(apbEnsure(h, h->key, sizeof(int) * std::max<int64_t>(n, 1)));
@@ -626,7 +628,9 @@ __global__ void kNeighborLists(NbrArgs a, int *__restrict__ nbrCount, const int 
 int apbRebuildVCL(apb_handle h, int newton3) {
   const int M = h->cfg.cluster_size;
   int64_t owned = 0, halo = 0;
-  h->countsValid = false;
+  if (!h->countsTrusted) h->countsValid = false;  // trusted: set by the one-pass halo generation that just ran
+  h->countsTrusted = false;
+  if (!h->ownedInsideBox) h->ownedKnown = false;  // the sort drops particles outside the halo box, owned ones included
   APB_CHECK(apb_get_num_particles(h, &owned, &halo));
   computeVCLGeom(h->cfg, owned + halo, h->vcl);
   const VCLGeom &g = h->vcl;

@@ -798,6 +798,7 @@ static bool nearRel(double a, double b) {
 // One dimension of a generating exchange (halo generation or migration).
 // mode 0: halo generation (packed columns: x, y, z); mode 1: migration (all active columns).
 static int exchangeDim(apb_handle h, int d, int mode) {
+  if (mode == 1) h->ownedKnown = false;  // migration between ranks changes the number of owned particles
   if (h->nranks > 1) APB_CHECK(ensureP2P(h));  // every rank passes here in the same order: the handle trade matches up
   const int64_t n = h->nslots;
   const double lmin = h->cfg.box_min[d], lmax = h->cfg.box_max[d];
@@ -1221,12 +1222,19 @@ extern "C" int apb_exchange_halos(apb_handle h) {
     h->haloAllMode = false;
     h->haloAllN = 0;
     static const bool noOnePass = getenv("APB_NO_ONEPASS_HALO") != nullptr;
-    if (h->ownedInsideBox && !noOnePass && allDimsSelf(h))
-      APB_CHECK(generateImagesAllSelf(h));
-    else
-      for (int d = 0; d < 3; ++d) APB_CHECK(exchangeDim(h, d, 0));
-    h->haloLinksValid = true;
     h->countsValid = false;
+    h->countsTrusted = false;
+    if (h->ownedInsideBox && !noOnePass && allDimsSelf(h)) {
+      APB_CHECK(generateImagesAllSelf(h));
+      if (h->ownedKnown) {  // owned count unchanged since it was counted, halo count = number of images just written
+        h->numOwned = h->ownedCount;
+        h->numHalo = h->haloAllN;
+        h->countsValid = h->countsTrusted = true;
+      }
+    } else {
+      for (int d = 0; d < 3; ++d) APB_CHECK(exchangeDim(h, d, 0));
+    }
+    h->haloLinksValid = true;
     h->noHalos = false;
     return APB_OK;
   }

@@ -171,6 +171,10 @@ struct apb_handle_s {
 
   int64_t numOwned = 0, numHalo = 0;  // refreshed lazily
   bool countsValid = false;
+  // owned count as last counted; stays valid while nothing can add / remove owned particles, so that the single-rank
+  // rebuild chain (in-place wrap + one-pass halo images, whose number the host knows) needs no counting kernel
+  bool ownedKnown = false, countsTrusted = false;
+  int64_t ownedCount = 0;
 
   int fail(int code, const std::string &msg) {
     err = msg;

@@ -351,6 +351,7 @@ __global__ void kFillAppended(int64_t first, int64_t n, int64_t *id, int32_t *ty
 extern "C" int apb_add_particles(apb_handle h, int64_t n, const double *x, const double *y, const double *z,
                                  const int64_t *ids, const int32_t *types, int32_t ownership, int32_t check_box) {
   APB_ENTRY(h);
+  h->ownedKnown = false;  // the number of owned particles may change
   h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
   h->noHalos = false;
   if (n < 0 || (n > 0 && (!x || !y || !z))) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_add_particles: null positions");
@@ -393,6 +394,7 @@ extern "C" int apb_add_particles(apb_handle h, int64_t n, const double *x, const
 
 extern "C" int apb_delete_all_particles(apb_handle h) {
   APB_ENTRY(h);
+  h->ownedKnown = false;  // the number of owned particles may change
   h->nslots = 0;
   h->structureValid = false;
   h->prunedValid = false;
@@ -557,6 +559,8 @@ extern "C" int apb_get_num_particles(apb_handle h, int64_t *out_owned, int64_t *
     h->numOwned = static_cast<int64_t>(counts[0]);
     h->numHalo = static_cast<int64_t>(counts[1]);
     h->countsValid = true;
+    h->ownedKnown = true;
+    h->ownedCount = h->numOwned;
   }
   if (out_owned) *out_owned = h->numOwned;
   if (out_halo) *out_halo = h->numHalo;
@@ -614,6 +618,7 @@ extern "C" int apb_download_ids(apb_handle h, int64_t *ids, int32_t *types, int3
 
 extern "C" int apb_upload_ownership(apb_handle h, const int32_t *ownership) {
   APB_ENTRY(h);
+  h->ownedKnown = false;  // the number of owned particles may change
   h->ownedInsideBox = false;  // positions / ownership may change: the one-pass halo images need apb_migrate first
   h->noHalos = false;
   if (h->nslots == 0) return APB_OK;
@@ -901,6 +906,7 @@ int apbPermuteStorage(apb_handle h, const int *perm, int64_t newSlots) {
 
 extern "C" int apb_update_container(apb_handle h, int32_t keep, int64_t *out_num_leavers) {
   APB_ENTRY(h);
+  h->ownedKnown = false;  // the number of owned particles may change
   h->numLeavers = 0;
   for (auto &v : h->leaverCols) v.clear();
   h->leaverIds.clear();
