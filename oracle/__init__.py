@@ -146,6 +146,16 @@ def lj_linkedcells(x, y, z, types, own, box_min, box_max, cutoff, skin, csf=1.0,
     return {"f": f, "fscale": fscale, "res": res, "cell": cell}
 
 
+def lc_pair_offsets(cells_per_dim, cell_length, interaction_length):
+    """Linear offset differences of the cell pairs of one base cell (self = 0 included), ascending."""
+    cpd = np.asarray(cells_per_dim, dtype=np.int64)
+    cl = _f64(cell_length)
+    out = np.zeros(4096, dtype=np.int64)
+    lib().orc_lc_pair_offsets.restype = ctypes.c_int64
+    n = lib().orc_lc_pair_offsets(_p(cpd), _p(cl), ctypes.c_double(interaction_length), _p(out), ctypes.c_int64(len(out)))
+    return out[:n]
+
+
 def lj_bruteforce(x, y, z, types, own, cutoff, shift=False, mixing=False, eps=1.0, sigma=1.0):
     x, y, z, types, own, eps, sigma, n = _common(x, y, z, types, own, eps, sigma)
     f = np.zeros((n, 3))

@@ -268,6 +268,42 @@ static int cell_can_own(const lc_geom *g, int64_t cx, int64_t cy, int64_t cz) {
 }
 
 /*
+ * The set of relative cell offsets the LinkedCells traversals pair a base cell with, as linear offset differences
+ * (self = 0 included): every offset within the overlap whose cell-border distance is <= the interaction length
+ * (LCC08CellHandlerUtility.cpp:67-159, filter :124), each unordered pair once. This is what orc_lj_linkedcells walks and
+ * what the reference's c08 base step covers when its offset pairs are flattened to differences
+ * (LCC08CellHandlerUtilityTest.cpp:27-233 holds the expected tables). Returns the count, fills out_lin (ascending).
+ */
+int64_t orc_lc_pair_offsets(const int64_t *cpd, const double *cell_length, double il, int64_t *out_lin, int64_t max_out) {
+  int ov[3];
+  for (int d = 0; d < 3; ++d) ov[d] = (int)ceil(il / cell_length[d]);
+  const double il2 = il * il;
+  int64_t count = 0;
+  for (int oz = -ov[2]; oz <= ov[2]; ++oz)
+    for (int oy = -ov[1]; oy <= ov[1]; ++oy)
+      for (int ox = -ov[0]; ox <= ov[0]; ++ox) {
+        const int64_t lin = ((int64_t)oz * cpd[1] + oy) * cpd[0] + ox;
+        if (lin < 0) continue;
+        const double dv[3] = {(abs(ox) > 1 ? abs(ox) - 1 : 0) * cell_length[0], (abs(oy) > 1 ? abs(oy) - 1 : 0) * cell_length[1],
+                              (abs(oz) > 1 ? abs(oz) - 1 : 0) * cell_length[2]};
+        if (!(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2] <= il2)) continue;
+        if (count < max_out) out_lin[count] = lin;
+        ++count;
+      }
+  /* ascending */
+  for (int64_t i = 1; i < count && i < max_out; ++i) {
+    const int64_t v = out_lin[i];
+    int64_t j = i - 1;
+    while (j >= 0 && out_lin[j] > v) {
+      out_lin[j + 1] = out_lin[j];
+      --j;
+    }
+    out_lin[j + 1] = v;
+  }
+  return count;
+}
+
+/*
  * LinkedCells + lc_c08 (== lc_c18 pair set) + LJFunctor SoA:
  * every cell: CellFunctor::processCell (baseFunctors/CellFunctor.h:141-160) -> SoAFunctorSingle;
  * every cell pair within the overlap whose border distance <= interaction length

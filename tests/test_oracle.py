@@ -225,3 +225,80 @@ def test_oracle_matches_reference_live(container, newton3):
     assert u == pytest.approx(r["upot"], rel=1e-12)
     assert v == pytest.approx(r["virial"], rel=1e-12)
     assert oracle.lj_num_flops(o["res"], True) == r["flops"]
+
+
+# ---- cell-pair stencil against the reference's c08 offset tables (LCC08CellHandlerUtilityTest.cpp:27-233) -----------
+C08_DIFFS_OVERLAP1 = [0, 1, 11, 12, 13, 131, 132, 133, 143, 144, 145, 155, 156, 157]
+C08_DIFFS_OVERLAP2 = [
+    0, 1, 2, 10, 11, 12, 13, 14, 22, 23, 24, 25, 26, 118, 119, 120, 121, 122, 130, 131, 132,
+    133, 134, 142, 143, 144, 145, 146, 154, 155, 156, 157, 158, 166, 167, 168, 169, 170, 262, 263, 264, 265,
+    266, 274, 275, 276, 277, 278, 286, 287, 288, 289, 290, 298, 299, 300, 301, 302, 310, 311, 312, 313, 314]
+C08_DIFFS_OVERLAP3 = [
+    0, 1, 2, 3, 9, 10, 11, 12, 13, 14, 15, 21, 22, 23, 24, 25, 26, 27, 33, 34, 35,
+    36, 37, 38, 39, 105, 106, 107, 108, 109, 110, 111, 117, 118, 119, 120, 121, 122, 123, 129, 130, 131,
+    132, 133, 134, 135, 141, 142, 143, 144, 145, 146, 147, 153, 154, 155, 156, 157, 158, 159, 165, 166, 167,
+    168, 169, 170, 171, 177, 178, 179, 180, 181, 182, 183, 249, 250, 251, 252, 253, 254, 255, 261, 262, 263,
+    264, 265, 266, 267, 273, 274, 275, 276, 277, 278, 279, 285, 286, 287, 288, 289, 290, 291, 297, 298, 299,
+    300, 301, 302, 303, 309, 310, 311, 312, 313, 314, 315, 321, 322, 323, 324, 325, 326, 327, 394, 395, 396,
+    397, 398, 405, 406, 407, 408, 409, 410, 411, 417, 418, 419, 420, 421, 422, 423, 429, 430, 431, 432, 433,
+    434, 435, 441, 442, 443, 444, 445, 446, 447, 453, 454, 455, 456, 457, 458, 459, 466, 467, 468, 469, 470]
+
+
+@pytest.mark.parametrize("il,expected", [(1.0, C08_DIFFS_OVERLAP1), (2.0, C08_DIFFS_OVERLAP2), (3.0, C08_DIFFS_OVERLAP3)])
+def test_cell_pair_offsets_match_c08_tables(il, expected):
+    """The reference flattens its c08 offset pairs to sorted offset differences for 12^3 cells of length 1
+    (LCC08CellHandlerUtilityTest.h:31-40); the oracle's cell-pair stencil must produce the same tables (14 / 63 / 168
+    pairs for overlap 1 / 2 / 3, the latter without the four far corners)."""
+    got = oracle.lc_pair_offsets([12, 12, 12], [1.0, 1.0, 1.0], il)
+    assert list(got) == expected
+
+
+def test_vcl_grid_alignment_literals():
+    """VerletClusterListsTest.cpp:258-308 (testGridAlignment): box 10^3, cutoff 2, skin 0.05, cluster size 4 and 257
+    particles give 5 x 5 owned towers of side 2 with 2 halo towers on each side (9 x 9), and the four corner probes fall
+    into towers (2,2), (1,1), (6,6), (7,7)."""
+    rng = np.random.default_rng(3)
+    probes = np.array([[0., 0., 0.], [-0.1, -0.1, -0.1], [9.9, 9.9, 9.9], [10., 10., 10.]])
+    filler = 5.0 + rng.uniform(-1.5, 1.5, (253, 3))  # the reference puts them all at the centre; only the count matters
+    pos = np.vstack([probes, filler])
+    own = np.ones(len(pos), dtype=np.int64)
+    own[[1, 3]] = 2
+    o = oracle.lj_vcl(pos[:, 0], pos[:, 1], pos[:, 2], None, own, [0, 0, 0], [10, 10, 10], 2.0, 0.05, 4)
+    assert o["towers_per_dim"] == (9, 9)
+    assert o["tower_side"] == (2.0, 2.0)
+    tower_of = {int(p): int(t) for p, t in zip(o["slot_particle"], o["slot_tower"]) if p >= 0}
+    assert [tower_of[i] for i in range(4)] == [2 + 2 * 9, 1 + 1 * 9, 6 + 6 * 9, 7 + 7 * 9]
+
+
+def test_vcl_newton3_list_is_half_of_the_non_newton3_list():
+    """VerletClusterListsTest.cpp:215-256 (testNewton3NeighborList): 2431 uniform particles in a 3^3 box, cutoff 1,
+    skin 0.1, cluster size 4, no halos: the non-newton3 list has twice the entries of the newton3 list, and every
+    newton3 entry (A, B) appears in the non-newton3 list as (A, B) and as (B, A)."""
+    rng = np.random.default_rng(42)
+    pos = rng.uniform(0, 3, (2431, 3))
+    own = np.ones(len(pos), dtype=np.int64)
+    args = (pos[:, 0], pos[:, 1], pos[:, 2], None, own, [0, 0, 0], [3, 3, 3], 1.0, 0.1, 4)
+    non3 = {tuple(p) for p in oracle.lj_vcl(*args, newton3=False)["pairs"]}
+    n3 = {tuple(p) for p in oracle.lj_vcl(*args, newton3=True)["pairs"]}
+    assert len(non3) == 2 * len(n3)
+    for a, b in n3:
+        assert (a, b) in non3 and (b, a) in non3
+
+
+@pytest.mark.parametrize("newton3", [True, False])
+@pytest.mark.parametrize("shift", [True, False])
+def test_flop_counter_literals(newton3, shift):
+    """LJFunctorFlopCounterTest.cpp:35-170, LinkedCells / lc_c08 / SoA: four molecules in a 3^3 box (cutoff 1.1,
+    skin 0.2) give 6 distance calls and 2 newton3 kernel calls with newton3, and 10 distance calls, 1 newton3 (inside a
+    cell the SoA functor always uses newton3) + 2 non-newton3 kernel calls without; globals are counted per kernel call;
+    FLOPs = 8 D + 18 K_n3 + 15 K_non3 + (12 | 13 with shift) G_n3 + (8 | 9) G_non3; hit rate = kernel calls / D."""
+    pos = np.array([[0.9, 0.3, 0.9], [0.9, 0.9, 0.9], [0.9, 1.5, 0.9], [0.1, 2.4, 0.1]])
+    own = np.ones(4, dtype=np.int64)
+    o = oracle.lj_linkedcells(pos[:, 0], pos[:, 1], pos[:, 2], None, own, [0, 0, 0], [3, 3, 3], 1.1, 0.2, 1.0,
+                              shift=shift, newton3=newton3)
+    r = o["res"]
+    dist, kn3, knon3 = (6, 2, 0) if newton3 else (10, 1, 2)
+    assert (r.num_dist_calls, r.num_kernel_calls_n3, r.num_kernel_calls_no_n3) == (dist, kn3, knon3)
+    assert (r.num_global_calcs_n3, r.num_global_calcs_no_n3) == (kn3, knon3)
+    expected = 8 * dist + 18 * kn3 + 15 * knon3 + (13 if shift else 12) * kn3 + (9 if shift else 8) * knon3
+    assert oracle.lj_num_flops(r, shift) == expected

@@ -154,3 +154,14 @@ def test_atm_matches_reference_live():
     owned = s["own"] == 1
     assert close(o["f"][owned], r["f"][owned], o["scale"][owned])
     assert o["upot3_sum"] / 9.0 == pytest.approx(r["upot"], rel=1e-12)
+
+
+def test_atm_kernel_call_literal():
+    """ATMFunctorFlopCounterTest.cpp:66-100: four molecules, cutoff 1.1: only the triplet {0, 1, 2} lies inside the
+    cutoff; without newton3 the functor is called once per participant: 3 kernel calls (59 FLOPs each + 10 for globals,
+    24 per distance triple, AxilrodTellerMutoFunctor.h:476-480)."""
+    pos = np.array([[0.2, 0.2, 0.2], [1.0, 0.2, 0.2], [1.0, 0.8, 0.2], [0.2, 0.2, 2.5]])
+    o = oracle.atm(pos, None, np.ones(4, dtype=np.int64), 1.1, nu=0.073)
+    assert o["kernel_calls"] == 3
+    assert np.all(o["f"][3] == 0.0) and np.abs(o["f"][:3]).max() > 0
+    np.testing.assert_allclose(o["f"][:3].sum(axis=0), 0.0, atol=1e-15)
