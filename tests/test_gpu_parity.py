@@ -433,3 +433,19 @@ def test_pruned_cutoff_decision_is_bit_exact(cutoff):
     assert f._raw.num_kernel_calls_no_n3 == 2 * bf["res"].num_kernel_calls_n3  # newton3 off: both directions
     check_forces(c.forcesById(len(pos)), bf["f"], bf["fscale"], own)
     c.close()
+
+
+@pytest.mark.parametrize("newton3", [True, False])
+def test_gpu_flop_counter_literals(newton3):
+    """LJFunctorFlopCounterTest.cpp:35-170 through gpuLinkedCells / gpulc_c08: the counters of the four-molecule
+    scenario equal the reference's literals (6 distance calls, 2 newton3 kernel calls | 10, 1 + 2)."""
+    pos = np.array([[0.9, 0.3, 0.9], [0.9, 0.9, 0.9], [0.9, 1.5, 0.9], [0.1, 2.4, 0.1]])
+    own = np.ones(4, dtype=np.int64)
+    c, f = run_gpu("gpuLinkedCells", "gpulc_c08", pos, own, None, [0, 0, 0], [3, 3, 3], 1.1, 0.2, newton3, shift=True)
+    r = f._raw
+    dist, kn3, knon3 = (6, 2, 0) if newton3 else (10, 1, 2)
+    assert (r.num_dist_calls, r.num_kernel_calls_n3, r.num_kernel_calls_no_n3) == (dist, kn3, knon3)
+    assert (r.num_global_calcs_n3, r.num_global_calcs_no_n3) == (kn3, knon3)
+    assert f.getNumFLOPs() == 8 * dist + 18 * kn3 + 15 * knon3 + 13 * kn3 + 9 * knon3
+    assert f.getHitRate() == pytest.approx((kn3 + knon3) / dist, abs=1e-14)
+    c.close()
