@@ -100,3 +100,45 @@ def test_invalid_configs_are_rejected_before_touching_the_device():
     assert e.value.code == capi.ERR_NOT_APPLICABLE
     with pytest.raises(ApbError):
         GpuParticleContainer("linkedCells", [0, 0, 0], [10, 10, 10], 1.0, 0.2)
+
+
+def test_lj_mixing_rules_match_the_reference_test():
+    """ParticlePropertiesLibraryTest.cpp:254-342 (LennardJonesMixingTest) and :69-107 (AddingDifferentSitesTest) for the
+    host-side table builder of the product library (apb_make_lj_mixing_table) and for the oracle: eps24_ij =
+    24 sqrt(eps_i eps_j), sigma2_ij = ((sigma_i + sigma_j) / 2)^2, shift6_ij = calcShift6(eps24_ij, sigma2_ij, rc^2)."""
+    import numpy as np
+
+    import oracle
+    from autopas_b200 import ParticlePropertiesLibrary
+
+    cutoff = 1.1
+    eps, sig = [0.6, 0.7, 1.0], [1.2, 1.4, 1.0]
+    ppl = ParticlePropertiesLibrary(cutoff)
+    for t in range(3):
+        ppl.addSiteType(t, 1.0)
+        ppl.addLJParametersToSite(t, eps[t], sig[t])
+    ppl.calculateMixingCoefficients()
+    table = oracle.mixing_table(eps, sig, cutoff).reshape(3, 3, 3)
+
+    def shift6(e24, s2):
+        s6 = (s2 / (cutoff * cutoff)) ** 3
+        return e24 * (s6 - s6 * s6)
+
+    for i in range(3):
+        for j in range(3):
+            e24 = 24.0 * np.sqrt(eps[i] * eps[j])
+            s2 = ((sig[i] + sig[j]) / 2.0) ** 2
+            for got in ((ppl.getMixing24Epsilon(i, j), ppl.getMixingSigmaSquared(i, j), ppl.getMixingShift6(i, j)), table[i, j]):
+                assert got[0] == pytest.approx(e24, rel=4e-16)
+                assert got[1] == pytest.approx(s2, rel=4e-16)
+                assert got[2] == pytest.approx(shift6(e24, s2), rel=1e-14)
+    # a pure LJ site next to a pure Axilrod-Teller site (zero-initialised parameters)
+    mixed = ParticlePropertiesLibrary(0.1)
+    mixed.addSiteType(0, 1.0)
+    mixed.addLJParametersToSite(0, 1.0, 1.0)
+    mixed.addSiteType(1, 1.2)
+    mixed.addATMParametersToSite(1, 0.1)
+    mixed.calculateMixingCoefficients()
+    assert mixed.getMixing24Epsilon(0, 1) == 0.0 and mixed.getMixingSigmaSquared(1, 0) == 0.25
+    nu = mixed.getMixingNuTable().reshape(2, 2, 2)
+    assert nu[0, 0, 1] == 0.0 and nu[1, 1, 0] == 0.0 and nu[1, 1, 1] == pytest.approx(0.1, rel=1e-15)
