@@ -11,11 +11,13 @@
 //
 // Layout for the force kernel: a CTA owns a tile of up to 8 warp chunks (32 consecutive slots of one tower each) taken
 // from a 2 x 2 block of towers and two consecutive z chunks, i.e. a compact brick, so that the union of the clusters its
-// particles interact with is small. That union is staged once in shared memory (coalesced loads), and each lane walks
-// its private list of 16-bit indices into the staged tile. Lists are stored per warp in rows of 32 lanes x 4 entries
-// (one 8-byte load per lane per 4 pairs, 256 contiguous bytes per warp); rows are prefetched two ahead. The pair kernel
-// is branch-free fp64; there are no atomics. Padding entries point at a sentinel slot parked at 1e100, which fails the
-// cutoff test.
+// particles interact with is small. The particles of that union that some list of the tile refers to are staged once in
+// shared memory (asynchronous 8-byte copies; (x, y) pairs and a z array at compile-time offsets), and each lane walks
+// its private list of 16-bit entries (staged index * 16). Lists are stored per warp in rows of 32 lanes x 4 entries
+// (one 8-byte load per lane per 4 pairs, 256 contiguous bytes per warp); rows are prefetched four ahead. The pair math
+// is unconditional fp64, only the accumulation is predicated; forces leave through one RED.ADD per component and
+// particle (single writer). Padding entries point at sentinel slots parked at 1e100, which fail the cutoff test.
+// Tiles that stage no halo copy are "interior": apb_run_steps evaluates them while the halo refresh is in flight.
 #include <algorithm>
 
 #include "internal.cuh"
