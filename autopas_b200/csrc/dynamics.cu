@@ -570,14 +570,27 @@ __global__ void kPushHalo(int64_t m0, int64_t m1, const int *__restrict__ idx0, 
   }
 }
 
+// Waits until *flag >= seq. A neighbour that never publishes (it failed, or the ranks call the exchange in different
+// orders) must not hang the GPU: after about ten seconds the wait gives up and raises *timedOut, which the host turns
+// into an error at its next read-back.
+#define P2P_SPIN_LIMIT_CYCLES 20000000000LL
+__device__ __forceinline__ void p2pWait(const unsigned long long *flag, unsigned long long seq, int *timedOut) {
+  const long long t0 = clock64();
+  while (*reinterpret_cast<const volatile unsigned long long *>(flag) < seq) {
+    if (clock64() - t0 > P2P_SPIN_LIMIT_CYCLES) {
+      *reinterpret_cast<volatile int *>(timedOut) = 1;
+      break;
+    }
+  }
+}
+
 __global__ void kPullHalo(int64_t m0, int64_t m1, const int *__restrict__ slot0, const int *__restrict__ slot1,
                           const double *in0, const double *in1, const unsigned long long *flag0,
-                          const unsigned long long *flag1, unsigned long long seq, double *x, double *y, double *z) {
+                          const unsigned long long *flag1, unsigned long long seq, double *x, double *y, double *z,
+                          int *timedOut) {
   if (threadIdx.x == 0) {
-    while (*reinterpret_cast<const volatile unsigned long long *>(flag0) < seq) {
-    }
-    while (*reinterpret_cast<const volatile unsigned long long *>(flag1) < seq) {
-    }
+    p2pWait(flag0, seq, timedOut);
+    p2pWait(flag1, seq, timedOut);
     __threadfence_system();
   }
   __syncthreads();
@@ -616,14 +629,13 @@ __global__ void kPushCounts(const long long *__restrict__ counts, long long *slo
   *reinterpret_cast<volatile long long *>(slot1 + 1) = seq;
   __threadfence_system();
 }
-__global__ void kPullCounts(const long long *slot0, const long long *slot1, long long seq, long long *out) {
-  while (*reinterpret_cast<const volatile long long *>(slot0 + 1) < seq) {
-  }
-  while (*reinterpret_cast<const volatile long long *>(slot1 + 1) < seq) {
-  }
+__global__ void kPullCounts(const long long *slot0, const long long *slot1, long long seq, long long *out, int *timedOut) {
+  p2pWait(reinterpret_cast<const unsigned long long *>(slot0 + 1), static_cast<unsigned long long>(seq), timedOut);
+  p2pWait(reinterpret_cast<const unsigned long long *>(slot1 + 1), static_cast<unsigned long long>(seq), timedOut);
   __threadfence_system();
   out[0] = *reinterpret_cast<const volatile long long *>(slot0);
   out[1] = *reinterpret_cast<const volatile long long *>(slot1);
+  out[2] = *reinterpret_cast<volatile int *>(timedOut);
 }
 
 // One-time set-up: allocate the arena, trade IPC handles with the distinct neighbour ranks (NCCL send / recv) and map
@@ -846,11 +858,17 @@ static int exchangeDim(apb_handle h, int d, int mode) {
     ++h->launchCount, kPushCounts<<<1, 1, 0, h->stream>>>(totals, p2pCountSlot(h->p2pPeer[d][0], h->p2pCap, d, to0, parity),
                                                         p2pCountSlot(h->p2pPeer[d][1], h->p2pCap, d, to1, parity), seq);
     ++h->launchCount, kPullCounts<<<1, 1, 0, h->stream>>>(p2pCountSlot(h->p2pArena, h->p2pCap, d, 0, parity),
-                                                        p2pCountSlot(h->p2pArena, h->p2pCap, d, 1, parity), seq, totals + 2);
+                                                        p2pCountSlot(h->p2pArena, h->p2pCap, d, 1, parity), seq, totals + 2,
+                                                        h->p2pCounters + 3);
     APB_CUDA(cudaGetLastError());
-    long long both[4];
-    APB_CUDA(cudaMemcpyAsync(both, totals, 32, cudaMemcpyDeviceToHost, h->stream));
+    long long both[5];
+    APB_CUDA(cudaMemcpyAsync(both, totals, 40, cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaStreamSynchronize(h->stream));
+    if (both[4] != 0) {
+      h->poisoned = true;
+      return h->fail(APB_ERR_STATE, "peer-memory exchange: a neighbour rank did not publish its data within ten seconds "
+                                    "(rank failed, or the ranks call the exchange in different orders)");
+    }
     sendCount[0] = both[0], sendCount[1] = both[1], recvCount[0] = both[2], recvCount[1] = both[3];
   } else {
     APB_CUDA(cudaMemcpyAsync(sendCount, totals, 16, cudaMemcpyDeviceToHost, h->stream));
@@ -1292,7 +1310,7 @@ extern "C" int apb_exchange_halos(apb_handle h) {
           L0.nRecv, L1.nRecv, static_cast<const int *>(L0.recvSlot.p), static_cast<const int *>(L1.recvSlot.p),
           p2pRegion(h->p2pArena, h->p2pCap, d, 0, parity), p2pRegion(h->p2pArena, h->p2pCap, d, 1, parity),
           p2pFlag(h->p2pArena, h->p2pCap, d, 0), p2pFlag(h->p2pArena, h->p2pCap, d, 1), h->p2pSeq, h->col[APB_COL_X],
-          h->col[APB_COL_Y], h->col[APB_COL_Z]);
+          h->col[APB_COL_Y], h->col[APB_COL_Z], h->p2pCounters + 3);
       APB_CUDA(cudaGetLastError());
       continue;
     }
@@ -1443,7 +1461,14 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
   if (outPerStep) {
     APB_CUDA(cudaMemcpyAsync(outPerStep, dres, sizeof(apb_traversal_result) * numSteps, cudaMemcpyDeviceToHost, h->stream));
   }
+  int refreshTimedOut = 0;
+  if (h->p2pState == 1)
+    APB_CUDA(cudaMemcpyAsync(&refreshTimedOut, h->p2pCounters + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (refreshTimedOut) {
+    h->poisoned = true;
+    return h->fail(APB_ERR_STATE, "halo refresh: a neighbour rank did not publish its positions within ten seconds");
+  }
   if (outPerStep) {
     for (int s = 0; s < numSteps; ++s) {
       if (!(functor->flags & APB_FUNCTOR_CALC_GLOBALS)) {
