@@ -4,8 +4,9 @@
  * (autopas_b200/) never does.
  *
  * Parity is PINNED: tests/test_oracle.py checks this file against the reference's own golden vectors
- * (LJFunctorTestNoGlobals.h:27-31, testingHelpers/LJPotential.h, CellBlock3DTest.cpp, VerletClusterListsTest.cpp
- * properties) and, when oracle/_ref/libautopas_ref.so exists, against the unmodified reference compiled from
+ * (LJFunctorTestNoGlobals.h:27-31, testingHelpers/LJPotential.h, CellBlock3DTest.cpp, the c08 offset tables of
+ * LCC08CellHandlerUtilityTest.cpp, LJFunctorFlopCounterTest.cpp, VerletClusterListsTest.cpp: brute-force equivalence,
+ * grid alignment, newton3 list relation) and, when oracle/_ref/libautopas_ref.so exists, against the unmodified reference compiled from
  * /root/reference (oracle/ref_driver.cpp).
  *
  * Every function cites the reference file:line it follows (paths relative to the reference tree).
