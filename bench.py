@@ -332,6 +332,8 @@ def main():
     capi.load().apb_measure_fp64_peak(local_rank, 3, ctypes.byref(peak_tf), ctypes.byref(peak_ms))
     kernel_ms = force_ms / max(force_launches, 1)
     achieved_tf = flops_per_step / (kernel_ms * 1e-3) / 1e12
+    # bound: the FP64 FMA pipe (north_star asks for the fraction of the B200 FP64 peak; the kernel is neither HBM- nor
+    # tensor-bound: 268 MB of DRAM traffic per 0.19 ms launch = 1.4 TB/s, and the path is not a contraction)
     roofline = {"bound": "fp64", "kernel": "kLJPruned" if args.traversal == "gpuvcl_pruned" else "kLJClusterPairs",
                 "achieved": achieved_tf, "peak": peak_tf.value, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf.value if peak_tf.value else None, "traffic": None,
