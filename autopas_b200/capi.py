@@ -123,6 +123,7 @@ SIGNATURES = {
     "apb_destroy": (_i32, [_H]),
     "apb_last_error": (ctypes.c_char_p, [_H]),
     "apb_add_particles": (_i32, [_H, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32]),
+    "apb_reserve": (_i32, [_H, _i64, _i64]),
     "apb_delete_all_particles": (_i32, [_H]),
     "apb_delete_halo_particles": (_i32, [_H]),
     "apb_update_halo_particles": (_i32, [_H, _i64, _vp, _vp, _vp, _vp, ctypes.POINTER(_i64)]),
@@ -160,6 +161,7 @@ SIGNATURES = {
     "apb_run_steps": (_i32, [_H, ctypes.POINTER(Functor), _vp, _i32, _i64, _vp]),
     "apb_get_stream": (_i32, [_H, ctypes.POINTER(_vp)]),
     "apb_get_launch_count": (_i32, [_H, ctypes.POINTER(_i64)]),
+    "apb_get_alloc_count": (_i32, [_H, ctypes.POINTER(_i64)]),
     "apb_enable_loop_timing": (_i32, [_H, _i32]),
     "apb_get_loop_timing": (_i32, [_H, _vp, _vp]),
     "apb_measure_fp64_peak": (_i32, [_i32, _i32, ctypes.POINTER(_f64), ctypes.POINTER(_f64)]),

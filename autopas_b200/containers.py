@@ -505,6 +505,10 @@ class GpuParticleContainer:
     def deleteHaloParticles(self):
         self._check(self._lib.apb_delete_halo_particles(self._h))
 
+    def reserve(self, numParticles, numParticlesHaloEstimate=0):
+        """ParticleContainerInterface::reserve (containers/ParticleContainerInterface.h:95)."""
+        self._check(self._lib.apb_reserve(self._h, int(numParticles), int(numParticlesHaloEstimate)))
+
     def deleteAllParticles(self):
         self._check(self._lib.apb_delete_all_particles(self._h))
 
@@ -665,6 +669,11 @@ class GpuParticleContainer:
     def getLaunchCount(self):
         n = ctypes.c_int64()
         self._check(self._lib.apb_get_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def getAllocCount(self):
+        n = ctypes.c_int64()
+        self._check(self._lib.apb_get_alloc_count(self._h, ctypes.byref(n)))
         return n.value
 
     def enableLoopTiming(self, enable=True):

@@ -237,13 +237,20 @@ __global__ void kSlotCell(int64_t m, const int *__restrict__ perm, const int *__
   slotCell[q] = p >= 0 ? key[p] : -1;
 }
 
+#define SEGSORT_SMEM_LIMIT (200 * 1024)
+int apbInitBuildAttributes(apb_handle h) {
+  APB_CUDA(cudaFuncSetAttribute(kSegSort<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEGSORT_SMEM_LIMIT));
+  APB_CUDA(cudaFuncSetAttribute(kSegSort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEGSORT_SMEM_LIMIT));
+  return APB_OK;
+}
+
 static int segSort(apb_handle h, int mode, int64_t numSeg, int maxCount, const int *start, const int *count, int *perm) {
   if (maxCount <= 1 || numSeg == 0) return APB_OK;
   int P = 1;
   while (P < maxCount) P <<= 1;
   const size_t elem = mode == 1 ? 20 : 4;
   const size_t smem = static_cast<size_t>(P) * elem;
-  const size_t smemLimit = 200 * 1024;
+  const size_t smemLimit = SEGSORT_SMEM_LIMIT;
   int useGlobal = smem > smemLimit;
   int threads = P / 2;
   threads = std::max(32, std::min(1024, threads));
@@ -261,11 +268,9 @@ static int segSort(apb_handle h, int mode, int64_t numSeg, int maxCount, const i
   }
   const size_t dyn = useGlobal ? 0 : smem;
   if (mode == 1) {
-    if (dyn > 40 * 1024) APB_CUDA(cudaFuncSetAttribute(kSegSort<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
     ++h->launchCount, kSegSort<1><<<static_cast<unsigned>(numSeg), threads, dyn, h->stream>>>(start, count, perm, h->col[APB_COL_Z], h->id,
                                                                            useGlobal, gK1, gK2, gV);
   } else {
-    if (dyn > 40 * 1024) APB_CUDA(cudaFuncSetAttribute(kSegSort<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dyn)));
     ++h->launchCount, kSegSort<0><<<static_cast<unsigned>(numSeg), threads, dyn, h->stream>>>(start, count, perm, nullptr, nullptr,
                                                                            useGlobal, gK1, gK2, gV);
   }

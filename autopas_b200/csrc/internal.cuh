@@ -165,6 +165,7 @@ struct apb_handle_s {
   std::vector<LoopEvent> loopEvents;
   std::vector<void *> eventPool;
   long long launchCount = 0;                      // kernels launched through this handle
+  long long allocCount = 0;                       // device allocations made through this handle (growth events)
   bool deferSync = false;                          // apb_run_steps: do not block after every call
   apb_traversal_result *asyncResultDev = nullptr;  // apb_run_steps: where the reduced accumulators of this step go
   DevBuf loopResults;
@@ -213,6 +214,11 @@ int apbEnsure(apb_handle h, DevBuf &b, size_t bytes);
 // grow particle storage to at least `slots` slots, preserving [0, nslots)
 int apbReserveSlots(apb_handle h, int64_t slots);
 int apbEnsurePinned(apb_handle h, size_t bytes);
+void apbForgetHaloLinks(apb_handle h);
+// opt-in shared-memory sizes of every kernel that needs more than 48 KB, set once per handle (pruned.cu, build.cu)
+int apbInitKernelAttributes(apb_handle h);
+int apbInitPrunedAttributes(apb_handle h);
+int apbInitBuildAttributes(apb_handle h);
 // permute the whole storage: slot q of the new order takes old slot perm[q] (perm < 0: dummy); swaps double buffers
 int apbPermuteStorage(apb_handle h, const int *perm, int64_t newSlots);
 

@@ -582,10 +582,6 @@ int apbBuildPruned(apb_handle h) {
   o.maxCompact = maxCompactDev;
   o.totalEntries = reinterpret_cast<unsigned long long *>(scratch + 48);
   const bool uniform = M == 32;
-  if (smemMasks > 40 * 1024) {
-    APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemMasks)));
-    APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemMasks)));
-  }
   APB_CUDA(cudaMemsetAsync(warpRows, 0, sizeof(int) * (numWarps + 1), h->stream));
   if (uniform)
     ++h->launchCount, kPrunedMasks<true><<<numTiles, PR_TILE, smemMasks, h->stream>>>(a, stagedStart, staged, o);
@@ -615,10 +611,6 @@ int apbBuildPruned(apb_handle h) {
   const size_t smemFillBase = (static_cast<size_t>(maxStaged) * 12 + 15) & ~size_t(15);
   const int smemRowsPerWarp = smemFillBase + static_cast<size_t>(PR_WARPS) * maxRows * 256 <= 150 * 1024 ? maxRows : 0;
   const size_t smemFill = smemFillBase + static_cast<size_t>(PR_WARPS) * smemRowsPerWarp * 256 + 16;
-  if (smemFill > 40 * 1024) {
-    APB_CUDA(cudaFuncSetAttribute(kPrunedFill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemFill)));
-    APB_CUDA(cudaFuncSetAttribute(kPrunedFill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemFill)));
-  }
   if (uniform)
     ++h->launchCount, kPrunedFill<true><<<numTiles, PR_TILE, smemFill, h->stream>>>(
         a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp,
@@ -987,8 +979,6 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   a.partials = static_cast<LJStats *>(h->partials.p);
 #define PR_LAUNCH_CAP(MIXV, STATSV, DEADV, VIRV, CAPV)                                                               \
   do {                                                                                                               \
-    APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV, VIRV, CAPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  static_cast<int>(smem)));                                                         \
     ++h->launchCount, kLJPruned<MIXV, STATSV, DEADV, VIRV, CAPV><<<numTiles, PR_TILE, smem, h->stream>>>(a);         \
   } while (0)
 #define PR_LAUNCH(MIXV, STATSV, DEADV, VIRV)                                                                         \
@@ -1023,4 +1013,32 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   }
   if (part == 1) return APB_OK;  // the boundary half follows and finishes the statistics
   return apbFinishStats(h, numBlocks, stats, f, out);
+}
+
+// Opt-in shared-memory sizes, set once per handle (apb_create) instead of before every launch.
+int apbInitPrunedAttributes(apb_handle h) {
+  const int big = 200 * 1024 + 1024;
+  APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  APB_CUDA(cudaFuncSetAttribute(kPrunedFill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  APB_CUDA(cudaFuncSetAttribute(kPrunedFill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#define PR_ATTR(MIXV, STATSV, DEADV, VIRV)                                                                              \
+  APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV, VIRV, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                2048 * 28));                                                                            \
+  APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV, VIRV, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                4096 * 28))
+  PR_ATTR(false, false, false, false);
+  PR_ATTR(false, false, true, false);
+  PR_ATTR(false, true, false, false);
+  PR_ATTR(false, true, false, true);
+  PR_ATTR(false, true, true, false);
+  PR_ATTR(false, true, true, true);
+  PR_ATTR(true, false, false, false);
+  PR_ATTR(true, false, true, false);
+  PR_ATTR(true, true, false, false);
+  PR_ATTR(true, true, false, true);
+  PR_ATTR(true, true, true, false);
+  PR_ATTR(true, true, true, true);
+#undef PR_ATTR
+  return APB_OK;
 }

@@ -13,20 +13,26 @@ static std::string g_createError;
 // ------------------------------------------------------------------------------------------------------------------
 // memory helpers
 // ------------------------------------------------------------------------------------------------------------------
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with the release threshold lifted in
+// apb_create, so that growing a buffer never costs a device-wide synchronisation (cudaFree) or a trip to the driver's
+// page allocator once the pool is warm: the AutoTuner times every rebuild, the first ones included
+// (LogicHandler.h:1066-1141). A first allocation carries 25 % headroom: sizes that follow the particle configuration
+// (list rows, halo copies, staged sets) drift by a few per cent from rebuild to rebuild.
 int apbEnsure(apb_handle h, DevBuf &b, size_t bytes) {
   if (bytes <= b.cap) return APB_OK;
-  size_t want = std::max(bytes, b.cap + b.cap / 2);
+  size_t want = std::max(bytes + bytes / 4, b.cap + b.cap / 2);
   want = (want + 255) & ~size_t(255);
-  if (b.p) APB_CUDA(cudaFree(b.p));
-  b.p = nullptr;
-  b.cap = 0;
-  cudaError_t e = cudaMalloc(&b.p, want);
+  void *q = nullptr;
+  cudaError_t e = cudaMallocAsync(&q, want, h->stream);
   if (e == cudaErrorMemoryAllocation) {
     cudaGetLastError();
     return h->fail(APB_ERR_OUT_OF_MEMORY, "device allocation of " + std::to_string(want) + " bytes failed");
   }
   APB_CUDA(e);
+  if (b.p) APB_CUDA(cudaFreeAsync(b.p, h->stream));  // stream-ordered: earlier kernels may still read the old block
+  b.p = q;
   b.cap = want;
+  ++h->allocCount;
   return APB_OK;
 }
 
@@ -44,24 +50,22 @@ int apbEnsurePinned(apb_handle h, size_t bytes) {
 template <class T>
 static int growArray(apb_handle h, T *&p, int64_t oldN, int64_t newCap) {
   T *q = nullptr;
-  cudaError_t e = cudaMalloc(&q, sizeof(T) * newCap);
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&q), sizeof(T) * newCap, h->stream);
   if (e == cudaErrorMemoryAllocation) {
     cudaGetLastError();
     return h->fail(APB_ERR_OUT_OF_MEMORY, "device allocation of particle column failed");
   }
   APB_CUDA(e);
   if (p && oldN > 0) APB_CUDA(cudaMemcpyAsync(q, p, sizeof(T) * oldN, cudaMemcpyDeviceToDevice, h->stream));
-  if (p) {
-    APB_CUDA(cudaStreamSynchronize(h->stream));
-    APB_CUDA(cudaFree(p));
-  }
+  if (p) APB_CUDA(cudaFreeAsync(p, h->stream));
   p = q;
+  ++h->allocCount;
   return APB_OK;
 }
 
 int apbReserveSlots(apb_handle h, int64_t slots) {
   if (slots <= h->cap) return APB_OK;
-  int64_t newCap = std::max<int64_t>(slots, h->cap + h->cap / 2);
+  int64_t newCap = std::max<int64_t>(slots + slots / 4, h->cap + h->cap / 2);
   newCap = (newCap + 1023) & ~int64_t(1023);
   for (int c = 0; c < APB_NUM_COLUMNS; ++c) {
     if (!h->active[c]) continue;
@@ -75,6 +79,12 @@ int apbReserveSlots(apb_handle h, int64_t slots) {
   APB_CHECK(growArray(h, h->own, h->nslots, newCap));
   APB_CHECK(growArray(h, h->ownTmp, 0, newCap));
   h->cap = newCap;
+  return APB_OK;
+}
+
+int apbInitKernelAttributes(apb_handle h) {
+  APB_CHECK(apbInitBuildAttributes(h));
+  APB_CHECK(apbInitPrunedAttributes(h));
   return APB_OK;
 }
 
@@ -267,6 +277,26 @@ extern "C" int apb_create(const apb_config *config, apb_handle *out) {
     delete h;
     return APB_ERR_CUDA;
   }
+  {
+    // keep freed blocks in the pool instead of returning them to the driver at the next synchronisation
+    cudaMemPool_t pool = nullptr;
+    unsigned long long threshold = ~0ULL;
+    if (cudaDeviceGetDefaultMemPool(&pool, c.device) != cudaSuccess ||
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold) != cudaSuccess) {
+      g_createError = "apb_create: the device has no stream-ordered memory pool";
+      delete h;
+      return APB_ERR_CUDA;
+    }
+  }
+  {
+    // per-function attributes (opt-in shared memory sizes) are set once here, not per launch
+    int rc = apbInitKernelAttributes(h);
+    if (rc != APB_OK) {
+      g_createError = h->err;
+      apb_destroy(h);
+      return rc;
+    }
+  }
   for (int k = APB_COL_X; k <= APB_COL_FZ; ++k) h->active[k] = true;
   if (c.particle_kind == APB_PARTICLE_LJ || c.particle_kind == APB_PARTICLE_MULTISITE) {
     for (int k = APB_COL_OLDFX; k <= APB_COL_OLDFZ; ++k) h->active[k] = true;
@@ -389,6 +419,7 @@ extern "C" int apb_add_particles(apb_handle h, int64_t n, const double *x, const
   h->structureValid = false;
   h->prunedValid = false;
   h->countsValid = false;
+  apbForgetHaloLinks(h);
   return APB_OK;
 }
 
@@ -400,6 +431,35 @@ extern "C" int apb_delete_all_particles(apb_handle h) {
   h->prunedValid = false;
   h->countsValid = false;
   h->numClusters = h->numPairs = 0;
+  apbForgetHaloLinks(h);
+  return APB_OK;
+}
+
+// The recorded halo links (send / receive / image slot lists) describe copies made by the last generating
+// apb_exchange_halos. Whatever replaces the particle set behind their back - deleteAllParticles, particles or ownership
+// states supplied by the host - makes them meaningless: the next apb_exchange_halos must not take the refresh branch.
+void apbForgetHaloLinks(apb_handle h) {
+  h->haloLinksValid = false;
+  h->haloAllMode = false;
+  h->haloAllN = 0;
+  for (int d = 0; d < 3; ++d)
+    for (int s = 0; s < 2; ++s) h->link[d][s].nSend = h->link[d][s].nRecv = 0;
+}
+
+// ParticleContainerInterface::reserve(numParticles, numParticlesHaloEstimate) (containers/ParticleContainerInterface.h:95)
+extern "C" int apb_reserve(apb_handle h, int64_t numParticles, int64_t numParticlesHaloEstimate) {
+  APB_ENTRY(h);
+  if (numParticles < 0 || numParticlesHaloEstimate < 0) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_reserve: negative count");
+  int64_t slots = numParticles + numParticlesHaloEstimate;
+  // VerletClusterLists pads every tower to a multiple of the cluster size (ClusterTower.h:83-143)
+  if (h->cfg.container == APB_CONTAINER_VERLET_CLUSTER_LISTS) slots += slots / 8 + 1024;
+  return apbReserveSlots(h, slots);
+}
+
+extern "C" int apb_get_alloc_count(apb_handle h, int64_t *out_count) {
+  APB_ENTRY(h);
+  if (!out_count) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_get_alloc_count: null argument");
+  *out_count = h->allocCount;
   return APB_OK;
 }
 
@@ -627,6 +687,7 @@ extern "C" int apb_upload_ownership(apb_handle h, const int32_t *ownership) {
   APB_CUDA(cudaStreamSynchronize(h->stream));
   h->countsValid = false;
   h->ownDirty = true;
+  apbForgetHaloLinks(h);
   return APB_OK;
 }
 

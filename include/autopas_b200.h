@@ -165,6 +165,9 @@ const char *apb_last_error(apb_handle h);
  * APB_ERR_PARTICLE_OUTSIDE. */
 int apb_add_particles(apb_handle h, int64_t n, const double *x, const double *y, const double *z, const int64_t *ids,
                       const int32_t *types, int32_t ownership, int32_t check_box);
+/* ParticleContainerInterface::reserve(numParticles, numParticlesHaloEstimate) (containers/ParticleContainerInterface.h:95):
+ * sizes the device SoA once so that later appends / rebuilds do not have to grow it */
+int apb_reserve(apb_handle h, int64_t num_particles, int64_t num_particles_halo_estimate);
 /* ParticleContainerInterface::deleteAllParticles */
 int apb_delete_all_particles(apb_handle h);
 /* ParticleContainerInterface::deleteHaloParticles (LinkedCells.h:110): halo slots become dummies */
@@ -296,6 +299,9 @@ int apb_get_stream(apb_handle h, void **out_stream);
 /* ---- measurement ------------------------------------------------------------------------------------------------- */
 /* number of CUDA kernels launched through this handle so far (bench.py's gpu_launches) */
 int apb_get_launch_count(apb_handle h, int64_t *out_count);
+/* number of device allocations (buffer growth events) made through this handle so far: a rebuild of an unchanged
+ * system makes none (tests/test_gpu_dynamics.py) */
+int apb_get_alloc_count(apb_handle h, int64_t *out_count);
 /* CUDA-event timing of the phases of apb_run_steps on the handle's stream, the analogue of the reference's
  * rebuild / computeInteractions / remainder timers (LogicHandler.h:1083-1125).
  * out_ms[4] / out_counts[4]: 0 force kernels, 1 rebuild (migrate + halo generation + structure build),

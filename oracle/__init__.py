@@ -209,6 +209,70 @@ def ref_bench_lj(x, y, z, own, box_min, box_max, cutoff, skin, container="Verlet
             "threads": ref().ref_num_threads()}
 
 
+# ---- reference arm of bench.py: the reference's LJ kernels built like its own Release build (oracle/ref_bench.cpp) -------
+_refbench = None
+
+
+def _cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def refbench_path():
+    """The timing library for the highest x86-64 micro-architecture level this host runs (v4 = AVX-512, v3 = AVX2)."""
+    flags = _cpu_flags()
+    v4 = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags
+    order = ["v4", "v3"] if v4 else ["v3"]
+    for lvl in order:
+        path = os.path.join(_HERE, "_ref", f"libautopas_refbench_{lvl}.so")
+        if os.path.exists(path):
+            return path
+    return None
+
+
+def have_refbench():
+    return refbench_path() is not None
+
+
+def refbench():
+    global _refbench
+    if _refbench is None:
+        _refbench = ctypes.CDLL(refbench_path())
+        _refbench.refb_isa.restype = ctypes.c_char_p
+    return _refbench
+
+
+def refbench_lj(x, y, z, own, box_min, box_max, cutoff, skin, functor="LJFunctor", container="LinkedCells",
+                traversal="lc_c08", cluster_size=4, newton3=True, warmup=1, iters=10, rebuild_freq=10, threads=None):
+    """Time the unmodified reference's force step (OpenMP on `threads` host threads, default: every core this process
+    may run on - torchrun's OMP_NUM_THREADS=1 is ignored on purpose). Only bench.py's cpu_baseline / --impl reference
+    legs call this."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    own = _i64(own)
+    lib_ = refbench()
+    if threads is None:
+        threads = len(os.sched_getaffinity(0))
+    lib_.refb_set_num_threads(ctypes.c_int(int(threads)))
+    fun = {"LJFunctor": 0, "LJFunctorHWY": 1}[functor]
+    cont = {"LinkedCells": 0, "VerletClusterLists": 1}[container]
+    trav = {"lc_c08": 0, "lc_c18": 1, "vcl_cluster_iteration": 0, "vcl_c06": 1, "vcl_c01_balanced": 2}[traversal]
+    out = np.zeros(5)
+    rc = lib_.refb_bench_lj(ctypes.c_int64(len(x)), _p(x), _p(y), _p(z), _p(own), _p(_f64(box_min)), _p(_f64(box_max)),
+                            ctypes.c_double(cutoff), ctypes.c_double(skin), ctypes.c_int(fun), ctypes.c_int(cont),
+                            ctypes.c_int(trav), ctypes.c_int64(cluster_size), ctypes.c_int(1 if newton3 else 0),
+                            ctypes.c_int(warmup), ctypes.c_int(iters), ctypes.c_int(rebuild_freq), _p(out))
+    if rc != 0:
+        raise RuntimeError("reference bench run failed")
+    return {"rebuild_s": out[0], "compute_s": out[1], "num_rebuilds": int(out[2]), "upot": out[3], "virial": out[4],
+            "threads": lib_.refb_num_threads(), "isa": lib_.refb_isa().decode()}
+
+
 # ---- the unmodified reference (oracle/_ref) --------------------------------------------------------------------
 def ref_lj_linkedcells(x, y, z, types, own, box_min, box_max, cutoff, skin, csf=1.0, shift=False, mixing=False,
                        newton3=True, soa=False, traversal="lc_c08", eps=1.0, sigma=1.0):

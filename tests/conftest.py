@@ -12,6 +12,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _gpu_available():
+    """A CUDA device and the built product library: what every `gpu` test needs."""
+    try:
+        import ctypes
+
+        from autopas_b200 import capi
+        capi.load()
+        cudart = ctypes.CDLL("libcudart.so")
+        n = ctypes.c_int(0)
+        return cudart.cudaGetDeviceCount(ctypes.byref(n)) == 0 and n.value > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if any("gpu" in item.keywords for item in items) and not _gpu_available():
+        skip = pytest.mark.skip(reason="no CUDA device or libautopas_b200.so not built")
+        for item in items:
+            if "gpu" in item.keywords:
+                item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle_mod():
     import oracle

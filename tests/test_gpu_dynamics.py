@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle
-from autopas_b200 import GpuParticleContainer, GpuTraversal, LJFunctor
+from autopas_b200 import GpuParticleContainer, GpuTraversal, LJFunctor, capi
 from scenarios import grid_lattice, periodic_images
 
 pytestmark = pytest.mark.gpu
@@ -257,3 +257,75 @@ def test_force_step_by_id_equals_separate_calls():
         np.testing.assert_array_equal(a[0], b[0])
         assert a[1:] == b[1:]
     assert np.abs(out[0][-1][0]).max() > 0
+
+
+def test_rebuilds_after_motion_cost_the_same_and_allocate_nothing():
+    """LogicHandler times every rebuild, the first ones after particles start moving included (LogicHandler.h:1066-1141).
+    Three consecutive rebuild periods of a moving 125k-particle liquid: the rebuild phase of each must lie within 2x
+    of the others, and from the second period on no device buffer may grow (stream-ordered pool + headroom)."""
+    import ctypes
+    import time
+
+    rc, skin, dt = 2.5, 0.3, 0.002
+    pos, bmin, bmax = grid_lattice(50, 1.0581, jitter=0.1, seed=5)
+    pos = bmin + np.mod(pos - bmin, bmax - bmin)
+    n = len(pos)
+    rng = np.random.default_rng(1)
+    vel = rng.normal(0, 1, (n, 3))
+    c = GpuParticleContainer("gpuVerletClusterLists", bmin, bmax, rc, skin, clusterSize=32)
+    c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(n))
+    for d, name in enumerate(("VX", "VY", "VZ")):
+        c.uploadColumn(name, vel[:, d])
+    f = _functor(rc)
+    t = GpuTraversal("gpuvcl_pruned", f, False)
+    c.enableLoopTiming(True)
+    per_period, allocs = [], []
+    for period in range(4):
+        c.getLoopTiming()
+        a0 = c.getAllocCount()
+        c.runSteps(t, 10, 10 * period, dt, [1.0], 10, wantResults=False)
+        tm = c.getLoopTiming()
+        assert tm["rebuild"][1] == 1
+        per_period.append(tm["rebuild"][0])
+        allocs.append(c.getAllocCount() - a0)
+    c.close()
+    # period 0 builds everything for the first time (particles at rest in a fresh handle); 1..3 follow moving particles
+    moving = per_period[1:]
+    assert max(moving) <= 2.0 * min(moving), per_period
+    assert allocs[2] == 0 and allocs[3] == 0, allocs
+    assert per_period[0] <= 6.0 * min(moving), per_period  # no tens of milliseconds of allocator work up front either
+
+
+def test_handle_reuse_after_delete_all_regenerates_halos():
+    """deleteAllParticles followed by a refill and a rebuild must not refresh through the halo links of the old
+    particle set (stale slot lists would overwrite live particles): the next exchange generates halos again."""
+    rc, skin = 2.5, 0.3
+    c = GpuParticleContainer("gpuVerletClusterLists", [0, 0, 0], [0, 0, 0] + np.array([15.4, 15.4, 15.4]), rc, skin,
+                             clusterSize=32)
+    for seed, npd in ((1, 14), (2, 13)):
+        pos, bmin, bmax = grid_lattice(npd, 15.4 / npd, jitter=0.1, seed=seed)
+        bmin, bmax = np.zeros(3), np.full(3, 15.4)
+        pos = np.mod(pos - pos.min(axis=0) + 0.3, 15.4)
+        n = len(pos)
+        o, nhalo = _host_forces(pos, bmin, bmax, rc, skin)
+        c.deleteAllParticles()
+        c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(n))
+        f = _functor(rc)
+        t = GpuTraversal("gpuvcl_pruned", f, False)
+        if seed == 2:
+            # a rebuild without a generating exchange in between: the old links must already be gone
+            c.rebuildNeighborLists(t)
+            with pytest.raises(capi.ApbError, match="no halo links"):
+                c.exchangeHalos()  # structure valid + links of the OLD particle set would have been the refresh branch
+        c.migrate()
+        c.exchangeHalos()
+        assert c.getNumberOfParticles("halo") == nhalo
+        c.rebuildNeighborLists(t)
+        c.exchangeHalos()  # refresh branch: must leave positions untouched (nothing moved)
+        f.initTraversal()
+        c.computeInteractions(t)
+        f.endTraversal(False)
+        F = c.forcesById(n)
+        err = np.abs(F - o["f"][:n]).max(axis=1)
+        assert np.all(err <= 1e-12 * o["fscale"][:n] + 1e-300)
+    c.close()
