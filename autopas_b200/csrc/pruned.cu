@@ -31,6 +31,15 @@
 #ifndef PR_MINBLOCKS
 #define PR_MINBLOCKS (32 / PR_WARPS)  // 32 resident warps per SM: 64 registers per thread
 #endif
+#ifdef PR_ZDUP
+#define PR_MINBLOCKS_CAP2048 3
+#define PR_MINBLOCKS_CAP4096 1
+#define PR_BYTES_XYZ 32  // (x, y) + two z copies per staged particle
+#else
+#define PR_MINBLOCKS_CAP2048 PR_MINBLOCKS
+#define PR_MINBLOCKS_CAP4096 2
+#define PR_BYTES_XYZ 24
+#endif
 #define PR_CAND_MAX 8192  // candidate cluster ids gathered per tile before sort/unique
 
 struct PrunedArgs {
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
                                                        const int *__restrict__ staged, MaskOut o,
                                                        const int *__restrict__ warpRowStart,
                                                        unsigned short *__restrict__ lists, int *__restrict__ compactSlot,
-                                                       int smemRowsPerWarp, int *__restrict__ tileHalo) {
+                                                       int smemRowsPerWarp, int sched, int *__restrict__ tileHalo) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int tile = blockIdx.x;
   const int g0 = stagedStart[tile], nS = stagedStart[tile + 1] - g0;
@@ -410,15 +419,28 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   const int rows = o.warpRows[warpGlobal];
   if (first < 0 || rows == 0) return;
   // The warp's rows are assembled in shared memory (2-byte scattered writes) and copied out coalesced; directly in
-  // global memory only if a warp's rows exceed the shared-memory budget. Padding entries point at the sentinel slot of
-  // the lane's own bank class (16 sentinel slots follow the staged particles), so that padding causes no conflicts.
+  // global memory only if a warp's rows exceed the shared-memory budget. Padding entries point at one of the 16 sentinel
+  // slots that follow the staged particles (one per bank class).
+  //
+  // Order of a lane's entries (sched != 0). The force kernel gathers the partner of every lane from shared memory: an
+  // LDS.128 for (x, y) - a quarter-warp per wavefront, bank group = index mod 8 - and an LDS.64 for z - a half-warp per
+  // wavefront, bank pair = index mod 16. In list order the indices of the 32 lanes are unrelated and a row costs ~14
+  // wavefronts instead of 6 (tools/sim/bank_conflicts.py; ncu: LSU data pipe 86 % busy, the first limiter of
+  // kLJPruned). So each lane's list is laid out on a Latin square: at slot t lane l reads a partner of class
+  // (l + t) mod 16, i.e. the j-th entry of class k sits at slot ((k - l) mod 16) + 16 j. At every slot the 16 lanes of a
+  // half-warp then hit 16 different bank pairs, and the 8 lanes of a quarter 8 different bank groups: conflict-free by
+  // construction, with no communication between lanes while the list is built. An entry whose slot is beyond the warp's
+  // rows or already taken (a class with more entries than visits: about one entry in eight) goes to the lane's last free
+  // slot instead (open addressing from the end, where most lanes idle) and may collide there; the slots left over take
+  // the sentinel of the slot's own class. ~7.6 wavefronts per row in the model. Only the order inside a lane changes:
+  // the same pairs are evaluated.
   const int nC = o.numCompact[tile];
-  const int R = rows * 4, p = lane & 15;
+  const int R = rows * 4;
   unsigned short *gout = lists + static_cast<size_t>(warpRowStart[warpGlobal]) * 128;
   const bool viaSmem = rows <= smemRowsPerWarp;
-  unsigned short *block = viaSmem ? reinterpret_cast<unsigned short *>(smemRaw + ((static_cast<size_t>(nS) * 12 + 15) & ~size_t(15))) +
-                                        static_cast<size_t>(warp) * smemRowsPerWarp * 128
-                                  : gout;
+  const bool latin = viaSmem && sched;
+  unsigned char *blocks = smemRaw + ((static_cast<size_t>(nS) * 12 + 15) & ~size_t(15));
+  unsigned short *block = viaSmem ? reinterpret_cast<unsigned short *>(blocks) + static_cast<size_t>(warp) * smemRowsPerWarp * 128 : gout;
   unsigned short *out = block + lane * 4;
   const int64_t i = static_cast<int64_t>(first) + lane;
   const bool laneIn = lane < num;
@@ -426,7 +448,10 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   const bool active = laneIn && a.own[i] == APB_OWN_OWNED && !a.clIsHalo[A];
   const int li = static_cast<int>(i) & mask;
   const int e0 = active ? a.nbrStart[A] : 0, e1 = active ? a.nbrStart[A + 1] : -1;
-  int cnt = 0;
+  int cnt = 0, spill = R - 1;
+  unsigned long long C0 = 0ULL, C1 = 0ULL;  // entries placed so far per class, 8 bits each (classes 0-7, 8-15)
+  if (latin)
+    for (int r = 0; r < rows; ++r) *reinterpret_cast<uint2 *>(out + static_cast<size_t>(r) * 128) = make_uint2(~0u, ~0u);
   // software pipelined: the next entry's cluster id and mask are loaded while the current one is expanded
   int lon = e1 >= e0 ? o.entryLo[static_cast<size_t>(e0) + A] : 0;
   unsigned mn = e1 >= e0 ? o.masks[(static_cast<size_t>(e0) + A) * a.M + li] : 0u;
@@ -442,12 +467,49 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
     while (m) {
       const int k = __ffs(m) - 1;
       m &= m - 1;
-      out[static_cast<size_t>(cnt >> 2) * 128 + (cnt & 3)] = static_cast<unsigned short>((cb + __popc(u & ((1u << k) - 1u))) << 4);
+      const unsigned ci = cb + __popc(u & ((1u << k) - 1u));
+      if (latin) {
+        const unsigned cls = ci & 15u, sh = (cls & 7u) * 8u;
+        unsigned j;
+        if (cls & 8u) {
+          j = static_cast<unsigned>(C1 >> sh) & 0xFFu;
+          C1 += 1ULL << sh;
+        } else {
+          j = static_cast<unsigned>(C0 >> sh) & 0xFFu;
+          C0 += 1ULL << sh;
+        }
+        int t = static_cast<int>((cls - lane) & 15u) + 16 * static_cast<int>(j);
+        if (t >= R || out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] != 0xFFFFu) {
+          while (out[static_cast<size_t>(spill >> 2) * 128 + (spill & 3)] != 0xFFFFu) --spill;  // cnt <= R: one is free
+          t = spill--;
+        }
+        out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] = static_cast<unsigned short>(ci << 4);
+      } else {
+        out[static_cast<size_t>(cnt >> 2) * 128 + (cnt & 3)] = static_cast<unsigned short>(ci << 4);
+      }
       ++cnt;
     }
   }
-  for (int t = cnt; t < R; ++t)
-    out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] = static_cast<unsigned short>((nC + ((p - nC) & 15)) << 4);
+  if (latin) {
+    // empty slots: the sentinel of the slot's own class, four slots (one row) at a time
+    for (int r = 0; r < rows; ++r) {
+      uint2 *q = reinterpret_cast<uint2 *>(out + static_cast<size_t>(r) * 128);
+      uint2 v = *q;
+      if (((v.x & 0xFFFFu) == 0xFFFFu) | ((v.x >> 16) == 0xFFFFu) | ((v.y & 0xFFFFu) == 0xFFFFu) | ((v.y >> 16) == 0xFFFFu)) {
+        const unsigned s0 = (nC + ((lane + 4 * r - nC) & 15)) << 4, s1 = (nC + ((lane + 4 * r + 1 - nC) & 15)) << 4,
+                       s2 = (nC + ((lane + 4 * r + 2 - nC) & 15)) << 4, s3 = (nC + ((lane + 4 * r + 3 - nC) & 15)) << 4;
+        if ((v.x & 0xFFFFu) == 0xFFFFu) v.x = (v.x & 0xFFFF0000u) | s0;
+        if ((v.x >> 16) == 0xFFFFu) v.x = (v.x & 0xFFFFu) | (s1 << 16);
+        if ((v.y & 0xFFFFu) == 0xFFFFu) v.y = (v.y & 0xFFFF0000u) | s2;
+        if ((v.y >> 16) == 0xFFFFu) v.y = (v.y & 0xFFFFu) | (s3 << 16);
+        *q = v;
+      }
+    }
+  } else {
+    const int p = lane & 15;
+    for (int t = cnt; t < R; ++t)
+      out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] = static_cast<unsigned short>((nC + ((p - nC) & 15)) << 4);
+  }
   if (viaSmem) {
     __syncwarp();
     const uint4 *src = reinterpret_cast<const uint4 *>(block);
@@ -611,13 +673,20 @@ int apbBuildPruned(apb_handle h) {
   const size_t smemFillBase = (static_cast<size_t>(maxStaged) * 12 + 15) & ~size_t(15);
   const int smemRowsPerWarp = smemFillBase + static_cast<size_t>(PR_WARPS) * maxRows * 256 <= 150 * 1024 ? maxRows : 0;
   const size_t smemFill = smemFillBase + static_cast<size_t>(PR_WARPS) * smemRowsPerWarp * 256 + 16;
+  // Latin layout of the lists (kPrunedFill; lists assembled in shared memory only). Measured on B200 (C2, 1 M particles,
+  // profiles/r02_latin_lists.txt): shared-memory wavefronts of kLJPruned 40.3 M -> 28.1 M, LSU data pipe 86 % -> 69 %,
+  // FP64 pipe 53 % -> 60 %, kernel 0.197 -> 0.177 ms per step; but kPrunedFill pays for the placement (rebuild 1.44 ->
+  // 2.0 ms). At the reference's rebuild frequency of 10 that is a net loss (0.341 -> 0.378 ms per step), so the layout
+  // is opt-in: APB_LIST_SCHEDULE=1 (worth it from about 25 steps per rebuild).
+  static const bool schedEnv = getenv("APB_LIST_SCHEDULE") != nullptr && atoi(getenv("APB_LIST_SCHEDULE")) != 0;
+  const int sched = schedEnv;
   if (uniform)
     ++h->launchCount, kPrunedFill<true><<<numTiles, PR_TILE, smemFill, h->stream>>>(
-        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp,
+        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp, sched,
         static_cast<int *>(h->prTileHalo.p));
   else
     ++h->launchCount, kPrunedFill<false><<<numTiles, PR_TILE, smemFill, h->stream>>>(
-        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp,
+        a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp, sched,
         static_cast<int *>(h->prTileHalo.p));
   APB_CUDA(cudaGetLastError());
   // order[0 .. numTiles) and, behind it, the number of interior tiles
@@ -718,6 +787,27 @@ __device__ __forceinline__ void prAccumulate(const LJParams &p, int ti, const in
   }
 }
 
+// z of the staged particle behind list entry e16 (= index * 16).
+// Default layout: one z array behind the CAP (x, y) pairs, element index * 8.
+// PR_ZDUP (experiment): two interleaved copies, index c at ((c >> 3) * 16 + (c & 7)) * 8 and 64 bytes behind it; lanes
+// 0-7 of each half-warp read the first copy (banks 0-15), lanes 8-15 the second (banks 16-31), so the LDS.64 of a
+// half-warp is conflict-free whenever each quarter reads 8 different classes mod 8.
+template <int CAP>
+__device__ __forceinline__ double prLoadZ(const unsigned char *sxyz, unsigned e16) {
+#ifdef PR_ZDUP
+  return *reinterpret_cast<const double *>(sxyz + CAP * 16 + (threadIdx.x & 8u) * 8u + (e16 - ((e16 & 0x70u) >> 1)));
+#else
+  return *reinterpret_cast<const double *>(sxyz + CAP * 16 + (e16 >> 1));
+#endif
+}
+__device__ __forceinline__ int prZIndex(int e) {  // element index (in doubles, first copy) of staged particle e
+#ifdef PR_ZDUP
+  return ((e >> 3) << 4) + (e & 7);
+#else
+  return e;
+#endif
+}
+
 template <bool MIX, bool STATS, bool DEAD, bool VIR3, int CAP>
 __device__ __forceinline__ void prPair(const LJParams &p, double xi, double yi, double zi, int ti,
                                        const unsigned char *sxyz, const int *stype, unsigned e16, unsigned sentinel16,
@@ -726,7 +816,7 @@ __device__ __forceinline__ void prPair(const LJParams &p, double xi, double yi, 
   e16 = (((e16 >> 4) & ~15u) | (threadIdx.x & 15u)) << 4;  // timing experiment only: conflict-free gather
 #endif
   const double2 pxy = *reinterpret_cast<const double2 *>(sxyz + e16);
-  const double pz = *reinterpret_cast<const double *>(sxyz + CAP * 16 + (e16 >> 1));
+  const double pz = prLoadZ<CAP>(sxyz, e16);
   const double drx = xi - pxy.x, dry = yi - pxy.y, drz = zi - pz;
   const double dx2 = drx * drx;
   const double dr2 = fma(drz, drz, fma(dry, dry, dx2));
@@ -762,7 +852,7 @@ __device__ __forceinline__ void prPairExact(const LJParams &p, double xi, double
                                             const unsigned char *sxyz, const int *stype, unsigned e16,
                                             PairAcc<MIX, STATS, VIR3> &acc) {
   const double2 pxy = *reinterpret_cast<const double2 *>(sxyz + e16);
-  const double pz = *reinterpret_cast<const double *>(sxyz + CAP * 16 + (e16 >> 1));
+  const double pz = prLoadZ<CAP>(sxyz, e16);
   const double drx = xi - pxy.x, dry = yi - pxy.y, drz = zi - pz;
   const double dx2 = drx * drx;
   const double dr2 = fma(drz, drz, fma(dry, dry, dx2));
@@ -794,10 +884,10 @@ __device__ __forceinline__ void prCpAsync8(void *smemDst, const void *gmemSrc) {
 // CAP: staged particles (incl. the 16 sentinels) the shared-memory layout is compiled for: (x, y) pairs at 16 CAP bytes,
 // z behind them, types behind those - compile-time offsets keep the gather free of address arithmetic.
 template <bool MIX, bool STATS, bool DEAD, bool VIR3, int CAP>
-__global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS : 2) kLJPruned(PrunedForceArgs a) {
+__global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS_CAP2048 : PR_MINBLOCKS_CAP4096) kLJPruned(PrunedForceArgs a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   unsigned char *sxyz = smemRaw;
-  int *stype = reinterpret_cast<int *>(smemRaw + static_cast<size_t>(CAP) * 24);
+  int *stype = reinterpret_cast<int *>(smemRaw + static_cast<size_t>(CAP) * PR_BYTES_XYZ);
   int pos = blockIdx.x;
   if (a.part != 0) {
     const int nI = *a.numInterior;
@@ -850,7 +940,10 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS : 2) kLJPr
     if (slots[k] >= 0) {
       prCpAsync8(sxy + 2 * e, a.x + slots[k]);
       prCpAsync8(sxy + 2 * e + 1, a.y + slots[k]);
-      prCpAsync8(sz + e, a.z + slots[k]);
+      prCpAsync8(sz + prZIndex(e), a.z + slots[k]);
+#ifdef PR_ZDUP
+      prCpAsync8(sz + prZIndex(e) + 8, a.z + slots[k]);
+#endif
       if (MIX) stype[e] = a.type[slots[k]];
     }
   }
@@ -858,7 +951,10 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS : 2) kLJPr
     const int slot = __ldg(cs + e);
     prCpAsync8(sxy + 2 * e, a.x + slot);
     prCpAsync8(sxy + 2 * e + 1, a.y + slot);
-    prCpAsync8(sz + e, a.z + slot);
+    prCpAsync8(sz + prZIndex(e), a.z + slot);
+#ifdef PR_ZDUP
+    prCpAsync8(sz + prZIndex(e) + 8, a.z + slot);
+#endif
     if (MIX) stype[e] = a.type[slot];
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -866,7 +962,10 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS : 2) kLJPr
   if (threadIdx.x < 16) {  // sentinel slots for padding entries, one per bank class
     sxy[2 * (nP + threadIdx.x)] = PR_FAR;
     sxy[2 * (nP + threadIdx.x) + 1] = 0.;
-    sz[nP + threadIdx.x] = 0.;
+    sz[prZIndex(nP + threadIdx.x)] = 0.;
+#ifdef PR_ZDUP
+    sz[prZIndex(nP + threadIdx.x) + 8] = 0.;
+#endif
     if (MIX) stype[nP + threadIdx.x] = 0;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -965,7 +1064,7 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   a.p = p;
   // shared-memory layout compiled for 2048 or 4096 staged particles (4 or 2 CTAs per SM)
   const int cap = h->prunedMaxCompact + 16 <= 2048 ? 2048 : 4096;
-  const size_t smem = static_cast<size_t>(cap) * (mix ? 28 : 24);
+  const size_t smem = static_cast<size_t>(cap) * (mix ? PR_BYTES_XYZ + 4 : PR_BYTES_XYZ);
   // per-component virial only on request: LJFunctor exposes the sum alone (getVirial, LJFunctor.h:719)
   const bool vir3 = stats && !(f->flags & APB_FUNCTOR_VIRIAL_TRACE);
   const int sel = (mix ? 8 : 0) | (stats ? 4 : 0) | (h->ownDirty ? 2 : 0) | (vir3 ? 1 : 0);
@@ -1024,9 +1123,9 @@ int apbInitPrunedAttributes(apb_handle h) {
   APB_CUDA(cudaFuncSetAttribute(kPrunedFill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 #define PR_ATTR(MIXV, STATSV, DEADV, VIRV)                                                                              \
   APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV, VIRV, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                2048 * 28));                                                                            \
+                                2048 * (PR_BYTES_XYZ + 4)));                                                                            \
   APB_CUDA(cudaFuncSetAttribute(kLJPruned<MIXV, STATSV, DEADV, VIRV, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                4096 * 28))
+                                4096 * (PR_BYTES_XYZ + 4)))
   PR_ATTR(false, false, false, false);
   PR_ATTR(false, false, true, false);
   PR_ATTR(false, true, false, false);
