@@ -782,9 +782,9 @@ int apbCheckTraversal(apb_handle h, int traversal, int newton3) {
   if (!traversalMatchesContainer(h->cfg.container, traversal))
     return h->fail(APB_ERR_NOT_APPLICABLE, "traversal option is not compatible with this container "
                                            "(CompatibleTraversals.h: gpulc_* <-> gpuLinkedCells, gpuvcl_* <-> gpuVerletClusterLists)");
-  // CompatibleTraversals.h:142-151: cluster_iteration and c01_balanced support newton3 off only; so does gpuvcl_pruned
+  // CompatibleTraversals.h:142-151: cluster_iteration and c01_balanced support newton3 off only
   if (newton3 && (traversal == APB_TRAVERSAL_GPUVCL_CLUSTER_ITERATION ||
-                  traversal == APB_TRAVERSAL_GPUVCL_C01_BALANCED || traversal == APB_TRAVERSAL_GPUVCL_PRUNED))
+                  traversal == APB_TRAVERSAL_GPUVCL_C01_BALANCED))
     return h->fail(APB_ERR_NOT_APPLICABLE, "this traversal supports newton3 = off only");
   return APB_OK;
 }
@@ -793,8 +793,9 @@ extern "C" int apb_rebuild_neighbor_lists(apb_handle h, int32_t traversal, int32
   APB_ENTRY(h);
   APB_CHECK(apbCheckTraversal(h, traversal, newton3));
   if (h->cfg.container == APB_CONTAINER_LINKED_CELLS) return apbRebuildLinkedCells(h);
-  APB_CHECK(apbRebuildVCL(h, newton3));
-  if (traversal == APB_TRAVERSAL_GPUVCL_PRUNED) APB_CHECK(apbBuildPruned(h));
+  // gpuvcl_pruned refines the full (newton3 off) cluster-pair list in both newton3 modes
+  APB_CHECK(apbRebuildVCL(h, traversal == APB_TRAVERSAL_GPUVCL_PRUNED ? 0 : newton3));
+  if (traversal == APB_TRAVERSAL_GPUVCL_PRUNED) APB_CHECK(apbBuildPruned(h, newton3));
   return APB_OK;
 }
 

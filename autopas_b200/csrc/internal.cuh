@@ -93,6 +93,7 @@ struct apb_handle_s {
   DevBuf nbrCount, nbrStart, nbrList;
   // per-particle lists for APB_TRAVERSAL_GPUVCL_PRUNED (pruned.cu)
   bool prunedValid = false;
+  int prunedNewton3 = 0;    // which newton3 mode the per-particle lists were built for
   int prunedTiles = 0;
   int prunedMaxStaged = 0;  // clusters
   int prunedMaxCompact = 0; // particles staged by the force kernel (largest tile)
@@ -228,7 +229,7 @@ int apbExclusiveScan(apb_handle h, const int *in, int *out, int64_t n, long long
 // build.cu
 int apbRebuildLinkedCells(apb_handle h);
 int apbRebuildVCL(apb_handle h, int newton3);
-int apbBuildPruned(apb_handle h);
+int apbBuildPruned(apb_handle h, int newton3);
 void apbComputeLCGeom(const apb_config &cfg, LCGeom &g);
 int apbComputeStencil(apb_handle h);
 

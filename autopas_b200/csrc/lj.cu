@@ -400,7 +400,7 @@ int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f
     }                                                                                              \
   } while (0)
 
-int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bool mix, bool stats,
+int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bool mix, bool stats, bool n3,
                        apb_traversal_result *out);
 
 int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3, apb_traversal_result *out) {
@@ -410,7 +410,7 @@ int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3,
   const bool stats = f->flags & (APB_FUNCTOR_CALC_GLOBALS | APB_FUNCTOR_COUNT_FLOPS);
   const bool n3 = newton3 != 0;
   const int64_t n = h->nslots;
-  if (traversal == APB_TRAVERSAL_GPUVCL_PRUNED) return apbComputeLJPruned(h, f, p, mix, stats, out);
+  if (traversal == APB_TRAVERSAL_GPUVCL_PRUNED) return apbComputeLJPruned(h, f, p, mix, stats, n3, out);
   const int block = 128;
   const int grid = apbDivUp(n, block);
   if (n == 0) return apbFinishStats(h, 0, stats, f, out);
@@ -471,7 +471,9 @@ extern "C" int apb_compute_interactions(apb_handle h, int32_t traversal, const a
   if (!h->structureValid)
     return h->fail(APB_ERR_STATE, "apb_compute_interactions: particles were added / removed since the last "
                                   "apb_rebuild_neighbor_lists");
-  if (h->cfg.container == APB_CONTAINER_VERLET_CLUSTER_LISTS && h->builtNewton3 != (newton3 ? 1 : 0))
+  // (gpuvcl_pruned refines the newton3-off cluster-pair list in both modes and keeps track of its own lists)
+  if (h->cfg.container == APB_CONTAINER_VERLET_CLUSTER_LISTS &&
+      h->builtNewton3 != (traversal == APB_TRAVERSAL_GPUVCL_PRUNED ? 0 : (newton3 ? 1 : 0)))
     return h->fail(APB_ERR_STATE, "apb_compute_interactions: cluster-pair lists were built for the other newton3 mode "
                                   "(VerletClusterListsRebuilder.h:153-163: list contents depend on newton3)");
   switch (functor->kind) {

@@ -199,7 +199,10 @@ __device__ __forceinline__ int prLowerBound(const int *stg, int nS, int B) {
   return lo;
 }
 
-template <bool UNIFORM>
+// N3 (newton3 lists): every owned-owned pair is listed once, by the particle in the lower slot; pairs with a halo partner
+// stay with the owned particle (halo particles own no list and receive no force). The force kernel then applies the
+// reaction to the listed partner (LJFunctor::SoAFunctorPairImpl<true>, LJFunctor.h:387-559).
+template <bool UNIFORM, bool N3>
 __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int *__restrict__ stagedStart,
                                                         const int *__restrict__ staged, MaskOut o) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
       r = make_float4(1e30f, 0.f, 0.f, 0.f);  // padding dummies are nobody's partner (dr2 overflows to +inf)
     } else {
       r = make_float4(static_cast<float>(a.x[slot] - ox), static_cast<float>(a.y[slot] - oy),
-                      static_cast<float>(a.z[slot] - oz), 0.f);
+                      static_cast<float>(a.z[slot] - oz), (N3 && a.own[slot] == APB_OWN_HALO) ? 1.f : 0.f);
       ext = fmaxf(ext, fmaxf(fabsf(r.x), fmaxf(fabsf(r.y), fabsf(r.z))));
     }
     rel[e] = r;
@@ -306,6 +309,10 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
             }
           }
           if (e < e0) m &= ~(1u << lane);
+          if (N3) {
+            const unsigned halos = __ballot_sync(0xffffffffu, pk.w != 0.f);  // bit k: particle k of B is a halo copy
+            m &= halos | (B > A ? 0xffffffffu : (B == A ? (0xfffffffeu << lane) : 0u));
+          }
           if (!active) m = 0u;
           *mrow = m;
           if (lane == 0) o.entryLo[static_cast<size_t>(e) + 1 + A] = lo;
@@ -327,7 +334,8 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
         for (int k = 0; k < a.M; ++k) {
           const float4 pj = rb[k];
           const float dx = ri.x - pj.x, dy = ri.y - pj.y, dz = ri.z - pj.z;
-          if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) m |= 1u << k;
+          const bool mine = !N3 || pj.w != 0.f || B > A || (B == A && k > li);
+          if (mine && fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) m |= 1u << k;
         }
         if (e < e0) m &= ~(1u << li);
         o.masks[(static_cast<size_t>(e) + 1 + A) * a.M + li] = m;
@@ -543,9 +551,13 @@ __global__ void __launch_bounds__(1024) kPrunedTileOrder(int numTiles, const int
   if (threadIdx.x == 0) *numInterior = total;
 }
 
-int apbBuildPruned(apb_handle h) {
+int apbBuildPruned(apb_handle h, int newton3) {
+  // The per-particle lists are refined from the full (newton3 off) cluster-pair list in both modes; with newton3 the
+  // half that the lower slot owns is kept (kPrunedMasks<*, true>).
   if (!h->structureValid || h->builtNewton3 != 0)
-    return h->fail(APB_ERR_STATE, "gpuvcl_pruned needs cluster lists built with newton3 off");
+    return h->fail(APB_ERR_STATE, "gpuvcl_pruned needs the cluster-pair list of the newton3-off mode");
+  const bool n3 = newton3 != 0;
+  h->prunedNewton3 = n3 ? 1 : 0;
   const int M = h->cfg.cluster_size;
   int logM = 0;
   while ((1 << logM) < M) ++logM;
@@ -645,10 +657,14 @@ int apbBuildPruned(apb_handle h) {
   o.totalEntries = reinterpret_cast<unsigned long long *>(scratch + 48);
   const bool uniform = M == 32;
   APB_CUDA(cudaMemsetAsync(warpRows, 0, sizeof(int) * (numWarps + 1), h->stream));
-  if (uniform)
-    ++h->launchCount, kPrunedMasks<true><<<numTiles, PR_TILE, smemMasks, h->stream>>>(a, stagedStart, staged, o);
+  if (uniform && n3)
+    ++h->launchCount, kPrunedMasks<true, true><<<numTiles, PR_TILE, smemMasks, h->stream>>>(a, stagedStart, staged, o);
+  else if (uniform)
+    ++h->launchCount, kPrunedMasks<true, false><<<numTiles, PR_TILE, smemMasks, h->stream>>>(a, stagedStart, staged, o);
+  else if (n3)
+    ++h->launchCount, kPrunedMasks<false, true><<<numTiles, PR_TILE, smemMasks, h->stream>>>(a, stagedStart, staged, o);
   else
-    ++h->launchCount, kPrunedMasks<false><<<numTiles, PR_TILE, smemMasks, h->stream>>>(a, stagedStart, staged, o);
+    ++h->launchCount, kPrunedMasks<false, false><<<numTiles, PR_TILE, smemMasks, h->stream>>>(a, stagedStart, staged, o);
   APB_CUDA(cudaGetLastError());
   APB_CHECK(apbExclusiveScan(h, warpRows, warpStart, numWarps + 1, totals));
   long long totalRows = 0;
@@ -1033,11 +1049,144 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS_CAP2048 : 
 
 #undef PR_ROW
 
+// ---- newton3 variant ------------------------------------------------------------------------------------------------
+// Same tiles, staging and list format; the lists hold every owned-owned pair once (kPrunedMasks<*, true>). A hit adds
+// f to the lane's own particle in registers and -f to the partner through three RED.ADD.F64 on its force columns
+// (LJFunctor::SoAFunctorPairImpl<true>: LJFunctor.h:499-516); halo partners receive nothing. Globals carry the
+// reference's weight [i owned] + [j owned] (LJFunctor.h:525-527), i.e. 2 for an owned partner and 1 for a halo copy, so
+// they equal the newton3-off sums; every hit counts as a newton3 kernel call. Half the pair evaluations of kLJPruned,
+// but the scatter costs more than the arithmetic saves on this machine (REDs: ~1.3 cycles per lane and SM against 0.3
+// cycles per pair of FP64 work; measured in profiles/r02_newton3.txt) - the option exists so that the tuner can see it.
+template <bool MIX, bool STATS, int CAP>
+__global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? 3 : 1) kLJPrunedN3(PrunedForceArgs a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  unsigned char *sxyz = smemRaw;
+  int *sslot = reinterpret_cast<int *>(smemRaw + static_cast<size_t>(CAP) * PR_BYTES_XYZ);  // owned partner: slot, else -1
+  int *stype = sslot + CAP;
+  int pos = blockIdx.x;
+  if (a.part != 0) {
+    const int nI = *a.numInterior;
+    if (a.part == 1 ? pos >= nI : (pos += nI) >= a.numTiles) return;
+  }
+  const int tile = a.part != 0 ? a.tileOrder[pos] : pos;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warpGlobal = tile * PR_WARPS + warp;
+  const int nP = a.numCompact[tile];
+  if (nP == 0) {
+    if (STATS && threadIdx.x == 0) {
+      LJStats st;
+      ljStatsZero(st);
+      a.partials[pos] = st;
+    }
+    return;
+  }
+  const int first = a.chunkFirst[warpGlobal];
+  const int rows = first >= 0 ? a.warpRows[warpGlobal] : 0;
+  const uint2 *list = reinterpret_cast<const uint2 *>(a.lists) +
+                      (rows > 0 ? static_cast<size_t>(a.warpRowStart[warpGlobal]) * 32 + lane : lane);
+  const int *cs = a.compactSlot + (static_cast<size_t>(a.stagedStart[tile]) << a.logM);
+  double *sxy = reinterpret_cast<double *>(sxyz), *sz = reinterpret_cast<double *>(sxyz + CAP * 16);
+  for (int e = threadIdx.x; e < nP; e += PR_TILE) {
+    const int slot = __ldg(cs + e);
+    const int o = a.own[slot];
+    sxy[2 * e] = o == APB_OWN_DUMMY ? PR_FAR : a.x[slot];  // deleted since the list build: out of reach
+    sxy[2 * e + 1] = a.y[slot];
+    sz[prZIndex(e)] = a.z[slot];
+#ifdef PR_ZDUP
+    sz[prZIndex(e) + 8] = a.z[slot];
+#endif
+    sslot[e] = o == APB_OWN_OWNED ? slot : -1;
+    if (MIX) stype[e] = a.type[slot];
+  }
+  if (threadIdx.x < 16) {
+    sxy[2 * (nP + threadIdx.x)] = PR_FAR;
+    sxy[2 * (nP + threadIdx.x) + 1] = 0.;
+    sz[prZIndex(nP + threadIdx.x)] = 0.;
+#ifdef PR_ZDUP
+    sz[prZIndex(nP + threadIdx.x) + 8] = 0.;
+#endif
+    sslot[nP + threadIdx.x] = -1;
+    if (MIX) stype[nP + threadIdx.x] = 0;
+  }
+  const int64_t i = static_cast<int64_t>(first >= 0 ? first : 0) + lane;
+  const bool active = rows > 0 && lane < a.chunkNum[warpGlobal] && a.own[i] == APB_OWN_OWNED;
+  const double xi = active ? a.x[i] : 0.5 * PR_FAR, yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
+  const int ti = (MIX && active) ? a.type[i] : 0;
+  __syncthreads();
+  const unsigned sentinel16 = static_cast<unsigned>(nP) << 4;
+  double fx = 0., fy = 0., fz = 0.;
+  double upot = 0., vx = 0., vy = 0., vz = 0.;
+  unsigned dist = 0, hits = 0;
+  for (int r = 0; r < rows; ++r, list += 32) {
+    const uint2 q = __ldg(list);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const unsigned e16 = s == 0 ? (q.x & 0xFFFFu) : (s == 1 ? (q.x >> 16) : (s == 2 ? (q.y & 0xFFFFu) : (q.y >> 16)));
+      const double2 pxy = *reinterpret_cast<const double2 *>(sxyz + e16);
+      const double pz = prLoadZ<CAP>(sxyz, e16);
+      const double drx = xi - pxy.x, dry = yi - pxy.y, drz = zi - pz;
+      double dr2 = fma(drz, drz, fma(dry, dry, drx * drx));
+      const int band = __double2hiint(dr2) - a.p.cutHiLo;
+      bool hit = band < 0;
+      if (static_cast<unsigned>(band) <= 2u) {  // within a few ulp of the cutoff: decide like the reference (prPairExact)
+        dr2 = ljDist2(drx, dry, drz);
+        hit = __double_as_longlong(dr2) <= __double_as_longlong(a.p.cutoff2);
+      }
+      if (STATS) dist += e16 < sentinel16;
+      if (hit) {
+        double k1 = a.p.k1, k2 = a.p.k2, khalf = 0.5 * a.p.k1, shift6 = a.p.shift6;
+        if (MIX) {
+          const double2 *m = reinterpret_cast<const double2 *>(a.p.mix4) + 2 * (static_cast<size_t>(ti) * a.p.T + stype[e16 >> 4]);
+          const double2 k = __ldg(m), as = __ldg(m + 1);
+          k1 = k.x, k2 = k.y, khalf = as.x, shift6 = as.y;
+        }
+        const double inv = prRcp(dr2);
+        const double a2 = inv * inv;
+        const double b = a2 * inv;
+        const double fac = (a2 * a2) * fma(k1, b, k2);
+        const double px = drx * fac, py = dry * fac, pzf = drz * fac;
+        fx += px, fy += py, fz += pzf;
+        const int sj = sslot[e16 >> 4];
+        if (sj >= 0) {
+          atomicAdd(a.fx + sj, -px);
+          atomicAdd(a.fy + sj, -py);
+          atomicAdd(a.fz + sj, -pzf);
+        }
+        if (STATS) {
+          const double w = sj >= 0 ? 2. : 1.;
+          upot = fma(w, fma(b, fma(khalf, b, k2), shift6), upot);
+          vx = fma(w * drx, px, vx);
+          vy = fma(w * dry, py, vy);
+          vz = fma(w * drz, pzf, vz);
+          ++hits;
+        }
+      }
+    }
+  }
+  if (active) {
+    atomicAdd(a.fx + i, fx);
+    atomicAdd(a.fy + i, fy);
+    atomicAdd(a.fz + i, fz);
+  }
+  if (STATS) {
+    LJStats st;
+    ljStatsZero(st);
+    st.upot = upot;
+    st.vir[0] = vx;
+    st.vir[1] = vy;
+    st.vir[2] = vz;
+    st.dist = dist;
+    st.kN3 = hits;
+    st.gN3 = hits;
+    ljStatsBlockReduce(st, a.partials, pos);
+  }
+}
+
 int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f, apb_traversal_result *out);
 
-int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bool mix, bool stats,
+int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bool mix, bool stats, bool n3,
                        apb_traversal_result *out) {
-  if (!h->prunedValid) APB_CHECK(apbBuildPruned(h));
+  if (!h->prunedValid || h->prunedNewton3 != (n3 ? 1 : 0)) APB_CHECK(apbBuildPruned(h, n3 ? 1 : 0));
   const int numTiles = h->prunedTiles;
   if (numTiles == 0) return apbFinishStats(h, 0, stats, f, out);
   PrunedForceArgs a;
@@ -1076,6 +1225,24 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   const int numBlocks = numTiles;
   APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * numBlocks));
   a.partials = static_cast<LJStats *>(h->partials.p);
+  if (n3) {
+    const size_t smemN3 = static_cast<size_t>(cap) * (PR_BYTES_XYZ + (mix ? 8 : 4));
+#define PR_LAUNCH_N3(MIXV, STATSV)                                                                                      \
+  do {                                                                                                                  \
+    if (cap == 2048)                                                                                                    \
+      ++h->launchCount, kLJPrunedN3<MIXV, STATSV, 2048><<<numTiles, PR_TILE, smemN3, h->stream>>>(a);                   \
+    else                                                                                                                \
+      ++h->launchCount, kLJPrunedN3<MIXV, STATSV, 4096><<<numTiles, PR_TILE, smemN3, h->stream>>>(a);                   \
+  } while (0)
+    if (mix && stats) PR_LAUNCH_N3(true, true);
+    else if (mix) PR_LAUNCH_N3(true, false);
+    else if (stats) PR_LAUNCH_N3(false, true);
+    else PR_LAUNCH_N3(false, false);
+#undef PR_LAUNCH_N3
+    APB_CUDA(cudaGetLastError());
+    if (part == 1) return APB_OK;
+    return apbFinishStats(h, numBlocks, stats, f, out);
+  }
 #define PR_LAUNCH_CAP(MIXV, STATSV, DEADV, VIRV, CAPV)                                                               \
   do {                                                                                                               \
     ++h->launchCount, kLJPruned<MIXV, STATSV, DEADV, VIRV, CAPV><<<numTiles, PR_TILE, smem, h->stream>>>(a);         \
@@ -1117,8 +1284,10 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
 // Opt-in shared-memory sizes, set once per handle (apb_create) instead of before every launch.
 int apbInitPrunedAttributes(apb_handle h) {
   const int big = 200 * 1024 + 1024;
-  APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  APB_CUDA(cudaFuncSetAttribute(kPrunedMasks<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   APB_CUDA(cudaFuncSetAttribute(kPrunedFill<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   APB_CUDA(cudaFuncSetAttribute(kPrunedFill<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
 #define PR_ATTR(MIXV, STATSV, DEADV, VIRV)                                                                              \
@@ -1139,5 +1308,15 @@ int apbInitPrunedAttributes(apb_handle h) {
   PR_ATTR(true, true, true, false);
   PR_ATTR(true, true, true, true);
 #undef PR_ATTR
+#define PR_ATTR_N3(MIXV, STATSV)                                                                                       \
+  APB_CUDA(cudaFuncSetAttribute(kLJPrunedN3<MIXV, STATSV, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                2048 * (PR_BYTES_XYZ + 8)));                                                           \
+  APB_CUDA(cudaFuncSetAttribute(kLJPrunedN3<MIXV, STATSV, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                4096 * (PR_BYTES_XYZ + 8)))
+  PR_ATTR_N3(false, false);
+  PR_ATTR_N3(false, true);
+  PR_ATTR_N3(true, false);
+  PR_ATTR_N3(true, true);
+#undef PR_ATTR_N3
   return APB_OK;
 }

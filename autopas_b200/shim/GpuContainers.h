@@ -235,7 +235,7 @@ class GpuTraversal : public autopas::TraversalInterface, public GpuTraversalInte
   [[nodiscard]] bool isApplicableToDomain() const override {
     if (not functorHasGpuKernel()) return false;
     if (_useNewton3 and (_traversal == APB_TRAVERSAL_GPUVCL_CLUSTER_ITERATION or
-                         _traversal == APB_TRAVERSAL_GPUVCL_C01_BALANCED or _traversal == APB_TRAVERSAL_GPUVCL_PRUNED))
+                         _traversal == APB_TRAVERSAL_GPUVCL_C01_BALANCED))
       return false;
     return true;
   }

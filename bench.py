@@ -300,7 +300,7 @@ def measure(workload, n_per_dim, args, ctx, with_e2e=True):
     kernel_ms = force_ms / max(steps, 1)  # force phase per step (a split step launches the kernel twice)
     achieved_tf = flops_per_step / (kernel_ms * 1e-3) / 1e12
     peak_tf = ctx["fp64_peak"]()
-    kernel_name = {"gpuvcl_pruned": "kLJPruned", "gpuvcl_pruned_n3": "kLJPrunedN3"}.get(args.traversal, "kLJClusterPairs")
+    kernel_name = ("kLJPrunedN3" if args.newton3 else "kLJPruned") if args.traversal == "gpuvcl_pruned" else "kLJClusterPairs"
     # bound: the FP64 FMA pipe (north_star asks for the fraction of the B200 FP64 peak; the kernel is neither HBM- nor
     # tensor-bound: ~1.4 TB/s of DRAM traffic, and the path is not a contraction)
     n_local = c.getNumberOfParticles("owned")

@@ -48,8 +48,10 @@ enum apb_traversal {
   APB_TRAVERSAL_GPUVCL_CLUSTER_ITERATION = 2, /* VCLClusterIterationTraversal.h:60-66, newton3 off only */
   APB_TRAVERSAL_GPUVCL_C06 = 3,               /* VCLC06Traversal.h:86-150, newton3 on/off */
   APB_TRAVERSAL_GPUVCL_C01_BALANCED = 4,      /* VCLC01BalancedTraversal.h:60-90, newton3 off only */
-  APB_TRAVERSAL_GPUVCL_PRUNED = 5             /* B200-native: cluster-pair list refined to per-particle masks at
-                                                 rebuild (rc+skin test), newton3 off only; same forces/globals */
+  APB_TRAVERSAL_GPUVCL_PRUNED = 5             /* B200-native: cluster-pair list refined to per-particle lists at
+                                                 rebuild (rc+skin test); newton3 off (full lists, the fast mode) or on
+                                                 (each owned-owned pair once, reaction scattered with RED.ADD.F64);
+                                                 same forces / globals as the list-faithful traversals */
 };
 
 /* Which particle class the container stores (decides the SoA columns). */

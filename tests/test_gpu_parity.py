@@ -62,7 +62,7 @@ def check_forces(f_gpu, f_ref, fscale, own):
     ("gpuLinkedCells", "gpulc_c08", True), ("gpuLinkedCells", "gpulc_c08", False), ("gpuLinkedCells", "gpulc_c18", True),
     ("gpuVerletClusterLists", "gpuvcl_cluster_iteration", False), ("gpuVerletClusterLists", "gpuvcl_c06", True),
     ("gpuVerletClusterLists", "gpuvcl_c06", False), ("gpuVerletClusterLists", "gpuvcl_c01_balanced", False),
-    ("gpuVerletClusterLists", "gpuvcl_pruned", False)])
+    ("gpuVerletClusterLists", "gpuvcl_pruned", False), ("gpuVerletClusterLists", "gpuvcl_pruned", True)])
 def test_lj_golden_literal(cont, trav, n3):
     pos = np.array([[1.0, 1.0, 1.0], [1.1, 1.2, 1.3]])
     own = np.array([1, 1])
@@ -114,13 +114,35 @@ def test_gpu_matches_reference_fixture(fname):
     c.close()
 
 
+@pytest.mark.parametrize("fname", [f for f in _golden_files() if f.startswith("vcl")])
+@pytest.mark.parametrize("n3", [False, True])
+def test_pruned_matches_reference_fixture(fname, n3):
+    """gpuvcl_pruned (newton3 off and on) on the VerletClusterLists fixtures of the unmodified reference: forces, Upot
+    and virial of vcl_c06 / vcl_cluster_iteration are mode independent, so every fixture checks both modes."""
+    g = np.load(os.path.join(GOLDEN, fname))
+    cfg = {k: g[k].item() for k in ("cutoff", "skin", "shift", "mixing", "newton3", "cluster_size", "csf")}
+    M = int(cfg["cluster_size"])
+    if M & (M - 1) or M > 32:
+        pytest.skip("gpuvcl_pruned needs a power-of-two cluster size")
+    pos, own, types = g["pos"], g["own"], g["types"]
+    kw = dict(shift=bool(cfg["shift"]), mixing=bool(cfg["mixing"]), eps=g["eps"], sigma=g["sigma"])
+    o = oracle.lj_vcl(pos[:, 0], pos[:, 1], pos[:, 2], types, own, g["box_min"], g["box_max"], cfg["cutoff"], cfg["skin"], M,
+                      newton3=False, **kw)
+    c, f = run_gpu("gpuVerletClusterLists", "gpuvcl_pruned", pos, own, types, g["box_min"], g["box_max"], cfg["cutoff"],
+                   cfg["skin"], n3, M=M, **kw)
+    check_forces(c.forcesById(len(pos)), g["ref_f"], o["fscale"], own)
+    assert f.getPotentialEnergy() == pytest.approx(g["ref_upot"].item(), rel=1e-12)
+    assert f.getVirial() == pytest.approx(g["ref_virial"].item(), rel=1e-12)
+    c.close()
+
+
 # ---- every GPU configuration against the oracle on a fresh random scenario (TraversalComparison style) --------------
 CONFIGS = [("gpuLinkedCells", "gpulc_c08", n3, 0) for n3 in (True, False)] + \
           [("gpuLinkedCells", "gpulc_c18", n3, 0) for n3 in (True, False)] + \
           [("gpuVerletClusterLists", "gpuvcl_cluster_iteration", False, M) for M in (1, 2, 4, 8, 16, 32)] + \
           [("gpuVerletClusterLists", "gpuvcl_c06", n3, M) for n3 in (True, False) for M in (4, 32)] + \
           [("gpuVerletClusterLists", "gpuvcl_c01_balanced", False, 8)] + \
-          [("gpuVerletClusterLists", "gpuvcl_pruned", False, M) for M in (4, 8, 32)]
+          [("gpuVerletClusterLists", "gpuvcl_pruned", n3, M) for n3 in (False, True) for M in (4, 8, 32)]
 
 
 @pytest.mark.parametrize("cont,trav,n3,M", CONFIGS)
@@ -145,6 +167,11 @@ def test_gpu_matches_oracle(cont, trav, n3, M, n, nh, L):
     if cont == "gpuVerletClusterLists":
         ids, _, _ = c.downloadIds()
         np.testing.assert_array_equal(ids.reshape(-1, max(M, 1)), o["slot_particle"].reshape(-1, max(M, 1)))
+        if trav == "gpuvcl_pruned" and n3:
+            # gpuvcl_pruned refines the newton3-off cluster-pair list in both modes: that is the list it keeps
+            o = oracle.lj_vcl(pos[:, 0], pos[:, 1], pos[:, 2], types, own, bmin, bmax, 1.0, 0.1, M, newton3=False, **kw)
+            r = f._raw  # every in-cutoff pair once, counted as a newton3 kernel call (LJFunctor.h:518-531)
+            assert r.num_kernel_calls_no_n3 == 0 and r.num_global_calcs_n3 == r.num_kernel_calls_n3 > 0
         assert {tuple(p) for p in c.debugClusterPairs()} == {tuple(p) for p in o["pairs"]}
     else:
         ids, _, _ = c.downloadIds()
@@ -427,11 +454,18 @@ def test_pruned_cutoff_decision_is_bit_exact(cutoff):
     pos = np.vstack(parts)
     L = 8.0 * cutoff
     own = np.ones(len(pos), dtype=np.int64)
+    bf = oracle.lj_bruteforce(pos[:, 0], pos[:, 1], pos[:, 2], None, own, cutoff, shift=True)
     c, f = run_gpu("gpuVerletClusterLists", "gpuvcl_pruned", pos, own, None, [0, 0, 0], [L, L, L], cutoff, 0.2 * cutoff,
                    False, shift=True, M=32)
-    bf = oracle.lj_bruteforce(pos[:, 0], pos[:, 1], pos[:, 2], None, own, cutoff, shift=True)
     assert f._raw.num_kernel_calls_no_n3 == 2 * bf["res"].num_kernel_calls_n3  # newton3 off: both directions
     check_forces(c.forcesById(len(pos)), bf["f"], bf["fscale"], own)
+    c.close()
+    c, f = run_gpu("gpuVerletClusterLists", "gpuvcl_pruned", pos, own, None, [0, 0, 0], [L, L, L], cutoff, 0.2 * cutoff,
+                   True, shift=True, M=32)
+    assert f._raw.num_kernel_calls_n3 == bf["res"].num_kernel_calls_n3  # newton3: every pair once
+    check_forces(c.forcesById(len(pos)), bf["f"], bf["fscale"], own)
+    u, v = oracle.lj_end_traversal(bf["res"])
+    assert f.getPotentialEnergy() == pytest.approx(u, rel=1e-12) and f.getVirial() == pytest.approx(v, rel=1e-12)
     c.close()
 
 

@@ -1,5 +1,5 @@
 """Kernel experiment helper: times repeated force evaluations (no integration) of the C2 / C3 workload through the C ABI.
-usage: [APB_LIB_PATH=variant.so] python tools/force_only.py [cluster_size] [reps] [c2|c3] [n_per_dim]"""
+usage: [APB_LIB_PATH=variant.so] python tools/force_only.py [cluster_size] [reps] [c2|c3] [n_per_dim] [traversal] [n3]"""
 import sys, time, numpy as np
 sys.path.insert(0, '/root/repo')
 import bench
@@ -7,9 +7,9 @@ from autopas_b200 import GpuParticleContainer, GpuTraversal, LJFunctor
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 wl = sys.argv[3] if len(sys.argv) > 3 else "c2"
-npd = int(sys.argv[4]) if len(sys.argv) > 4 else (100 if wl == "c2" else 126)
+npd = int(sys.argv[4]) if len(sys.argv) > 4 and int(sys.argv[4]) > 0 else (100 if wl == "c2" else 126)
 trav = sys.argv[5] if len(sys.argv) > 5 else "gpuvcl_pruned"
-n3 = trav.endswith("_n3")
+n3 = len(sys.argv) > 6 and sys.argv[6] == "n3"
 skin = bench.C2["skin"] if wl == "c2" else bench.C3["skin"]
 pos, vel, bmin, bmax, gmin, gmax = bench.make_workload(wl, npd, 0, [1, 1, 1])
 n = len(pos)
@@ -38,5 +38,5 @@ for k in range(reps):
     f.endTraversal(n3)
 r = f._raw
 flops = 8 * r.num_dist_calls + 15 * r.num_kernel_calls_no_n3 + 18 * r.num_kernel_calls_n3 + 9 * r.num_global_calcs_no_n3 + 13 * r.num_global_calcs_n3
-print(f"{wl} n={n} M={M} {trav}: force call best {best*1e3:.4f} ms ({flops / best / 1e12:.2f} TFLOP/s), rebuild call {tb*1e3:.3f} ms, "
+print(f"{wl} n={n} M={M} {trav}{' newton3' if n3 else ''}: force call best {best*1e3:.4f} ms ({flops / best / 1e12:.2f} TFLOP/s), rebuild call {tb*1e3:.3f} ms, "
       f"upot {f.getPotentialEnergy():.9e} dist {r.num_dist_calls} hits {r.num_kernel_calls_no_n3 + r.num_kernel_calls_n3}")
