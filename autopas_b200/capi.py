@@ -152,6 +152,14 @@ SIGNATURES = {
     "apb_atm_num_flops": (ctypes.c_uint64, [ctypes.POINTER(TraversalResult)]),
     "apb_integrate_positions": (_i32, [_H, _f64, _vp, _i32, _vp]),
     "apb_integrate_velocities": (_i32, [_H, _f64, _vp, _i32]),
+    "apb_calc_temperature": (_i32, [_H, _vp, _i32, _vp, _vp]),
+    "apb_apply_thermostat": (_i32, [_H, _vp, _i32, _f64, _f64]),
+    "apb_set_thermostat": (_i32, [_H, _i32, _i32, _f64, _f64]),
+    "apb_set_dynamic_rebuild": (_i32, [_H, _i32]),
+    "apb_check_dynamic_rebuild": (_i32, [_H, ctypes.POINTER(_i32)]),
+    "apb_get_dynamic_rebuild_count": (_i32, [_H, ctypes.POINTER(_i64)]),
+    "apb_compute_remainder": (_i32, [_H, ctypes.POINTER(Functor), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     ctypes.POINTER(TraversalResult)]),
     "apb_comm_get_unique_id": (_i32, [_vp]),
     "apb_comm_init": (_i32, [_H, _i32, _i32, _vp]),
     "apb_set_decomposition": (_i32, [_H, _vp, _vp, _vp, _vp]),

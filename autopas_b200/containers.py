@@ -625,6 +625,51 @@ class GpuParticleContainer:
         m = _f64(np.atleast_1d(massOfType))
         self._check(self._lib.apb_integrate_velocities(self._h, float(dt), _ptr(m), len(m)))
 
+    # --- thermostat, dynamic-rebuild trigger, remainder traversal (LogicHandler / md-flexible pieces)
+    def calcTemperature(self, massOfType):
+        """Thermostat::calcTemperatureComponent: (temperature per type, particle count per type)."""
+        m = _f64(np.atleast_1d(massOfType))
+        t = np.zeros(len(m))
+        c = np.zeros(len(m), dtype=np.int64)
+        self._check(self._lib.apb_calc_temperature(self._h, _ptr(m), len(m), _ptr(t), _ptr(c)))
+        return t, c
+
+    def applyThermostat(self, massOfType, targetTemperature, deltaTemperature):
+        m = _f64(np.atleast_1d(massOfType))
+        self._check(self._lib.apb_apply_thermostat(self._h, _ptr(m), len(m), float(targetTemperature), float(deltaTemperature)))
+
+    def setThermostat(self, enable, interval=1, targetTemperature=0.0, deltaTemperature=0.0):
+        self._check(self._lib.apb_set_thermostat(self._h, 1 if enable else 0, int(interval), float(targetTemperature),
+                                                 float(deltaTemperature)))
+
+    def setDynamicRebuild(self, enable):
+        self._check(self._lib.apb_set_dynamic_rebuild(self._h, 1 if enable else 0))
+
+    def checkDynamicRebuild(self):
+        r = ctypes.c_int32()
+        self._check(self._lib.apb_check_dynamic_rebuild(self._h, ctypes.byref(r)))
+        return bool(r.value)
+
+    def getDynamicRebuildCount(self):
+        n = ctypes.c_int64()
+        self._check(self._lib.apb_get_dynamic_rebuild_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def computeRemainder(self, functor, x, y, z, ownership, types=None):
+        """RemainderPairwiseInteractionHandler::computeRemainderInteractions for buffered particles; returns their forces
+        (n, 3) and deposits the accumulators into the functor (in addition to what computeInteractions deposited)."""
+        x, y, z = _f64(x), _f64(y), _f64(z)
+        own = np.ascontiguousarray(ownership, dtype=np.int32)
+        ty = None if types is None else np.ascontiguousarray(types, dtype=np.int32)
+        n = len(x)
+        f = [np.zeros(n) for _ in range(3)]
+        cf = functor._c_functor()
+        raw = capi.TraversalResult()
+        self._check(self._lib.apb_compute_remainder(self._h, ctypes.byref(cf), n, _ptr(x), _ptr(y), _ptr(z), _ptr(ty),
+                                                    _ptr(own), _ptr(f[0]), _ptr(f[1]), _ptr(f[2]), ctypes.byref(raw)))
+        functor._deposit(raw)
+        return np.stack(f, axis=1), raw
+
     def commInit(self, nranks, rank, uniqueId=None):
         buf = None if uniqueId is None else np.frombuffer(bytes(uniqueId), dtype=np.uint8).copy()
         self._check(self._lib.apb_comm_init(self._h, int(nranks), int(rank), _ptr(buf)))

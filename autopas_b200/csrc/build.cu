@@ -792,11 +792,14 @@ int apbCheckTraversal(apb_handle h, int traversal, int newton3) {
 extern "C" int apb_rebuild_neighbor_lists(apb_handle h, int32_t traversal, int32_t newton3) {
   APB_ENTRY(h);
   APB_CHECK(apbCheckTraversal(h, traversal, newton3));
-  if (h->cfg.container == APB_CONTAINER_LINKED_CELLS) return apbRebuildLinkedCells(h);
+  if (h->cfg.container == APB_CONTAINER_LINKED_CELLS) {
+    APB_CHECK(apbRebuildLinkedCells(h));
+    return apbSnapshotRebuildPositions(h);
+  }
   // gpuvcl_pruned refines the full (newton3 off) cluster-pair list in both newton3 modes
   APB_CHECK(apbRebuildVCL(h, traversal == APB_TRAVERSAL_GPUVCL_PRUNED ? 0 : newton3));
   if (traversal == APB_TRAVERSAL_GPUVCL_PRUNED) APB_CHECK(apbBuildPruned(h, newton3));
-  return APB_OK;
+  return apbSnapshotRebuildPositions(h);
 }
 
 extern "C" int apb_get_geometry(apb_handle h, apb_geometry *out) {

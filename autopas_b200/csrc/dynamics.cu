@@ -123,6 +123,13 @@ extern "C" int apb_set_decomposition(apb_handle h, const double *globalMin, cons
   return APB_OK;
 }
 
+int apbAllReduce(apb_handle h, void *dev, int count, int isDouble, int isMax) {
+  if (h->nranks == 1) return APB_OK;
+  APB_NCCL(g_nccl.AllReduce(dev, dev, static_cast<size_t>(count), isDouble ? ncclFloat64 : ncclInt32, isMax ? ncclMax : ncclSum,
+                            static_cast<ncclComm_t>(h->comm), h->stream));
+  return APB_OK;
+}
+
 extern "C" int apb_allreduce_globals(apb_handle h, apb_traversal_result *inout) {
   APB_ENTRY(h);
   if (!inout) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_allreduce_globals: null argument");
@@ -1352,6 +1359,19 @@ int apbCheckTraversal(apb_handle h, int traversal, int newton3);
 // Simulation::simulate (examples/md-flexible/src/Simulation.cpp:230-351) for the built-in functors, without leaving the
 // device: positions -> (every rebuild_frequency steps: migrate, halo exchange, rebuild | else: halo refresh) -> forces
 // -> velocities. Work is enqueued asynchronously; the host only blocks on rebuild steps (it needs sizes) and at the end.
+// velocities of the finished step, thermostat (Simulation.cpp:313, 539-546: every thermostatInterval iterations, after
+// the velocity update), positions of the next step. Without a thermostat action the two integration halves run fused.
+static int finishStep(apb_handle h, const apb_loop_params *p, int s, int numSteps, int64_t it) {
+  const bool thermo = h->thermostatOn && it % h->thermostatInterval == 0;
+  if (!thermo)
+    return s + 1 < numSteps ? integrateVelocitiesPositions(h, p->dt, p->mass_of_type, p->num_types, p->global_force)
+                            : apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
+  APB_CHECK(apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types));
+  APB_CHECK(apb_apply_thermostat(h, p->mass_of_type, p->num_types, h->thermostatTarget, h->thermostatDelta));
+  if (s + 1 < numSteps) APB_CHECK(apb_integrate_positions(h, p->dt, p->mass_of_type, p->num_types, p->global_force));
+  return APB_OK;
+}
+
 extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb_loop_params *p, int32_t numSteps,
                              int64_t firstIteration, apb_traversal_result *outPerStep) {
   APB_ENTRY(h);
@@ -1383,7 +1403,20 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
       apbLoopTimingRecord(h, 3, false);
       if (rc != APB_OK) break;
     }
-    const bool rebuild = (it % p->rebuild_frequency == 0) || !h->structureValid;
+    // Rebuild cadence (LogicHandler::neighborListsAreValid, LogicHandler.h:987-997): by iteration number, or - with the
+    // dynamic trigger on - when rebuild_frequency steps have passed since the last rebuild or a particle has moved skin / 2
+    // (one 4-byte read-back per step: the host has to know before it enqueues the rest of the step).
+    bool rebuild = (h->dynamicRebuild ? h->stepsSinceRebuild >= p->rebuild_frequency : it % p->rebuild_frequency == 0) ||
+                   !h->structureValid;
+    if (!rebuild && h->dynamicRebuild) {
+      int32_t needed = 0;
+      rc = apb_check_dynamic_rebuild(h, &needed);
+      if (rc != APB_OK) break;
+      rebuild = needed != 0;
+      if (rebuild) ++h->dynamicRebuildCount;
+    }
+    if (rebuild) h->stepsSinceRebuild = 0;
+    ++h->stepsSinceRebuild;
     if (rebuild) {
       apbLoopTimingRecord(h, 1, true);
       const double t0 = now();
@@ -1429,8 +1462,7 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
       h->asyncResultDev = nullptr;
       if (rc != APB_OK) break;
       apbLoopTimingRecord(h, 3, true);
-      rc = s + 1 < numSteps ? integrateVelocitiesPositions(h, p->dt, p->mass_of_type, p->num_types, p->global_force)
-                            : apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
+      rc = finishStep(h, p, s, numSteps, it);
       apbLoopTimingRecord(h, 3, false);
       continue;
     } else {
@@ -1448,8 +1480,7 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
     h->asyncResultDev = nullptr;
     if (rc != APB_OK) break;
     apbLoopTimingRecord(h, 3, true);
-    rc = s + 1 < numSteps ? integrateVelocitiesPositions(h, p->dt, p->mass_of_type, p->num_types, p->global_force)
-                          : apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
+    rc = finishStep(h, p, s, numSteps, it);
     apbLoopTimingRecord(h, 3, false);
   }
   h->deferSync = false;

@@ -51,6 +51,25 @@ __device__ __forceinline__ void lcForEachPartner(const LCWalk &a, int64_t i, F &
   }
 }
 
+// Every non-dummy j > i of all stencil cells, halo cells included (newton3 triplets are owned by their lowest slot,
+// which may well be a halo copy).
+template <class F>
+__device__ __forceinline__ void lcForEachHigherSlot(const LCWalk &a, int64_t i, F &&f) {
+  const LCGeom &g = a.g;
+  const int c = a.slotCell[i];
+  const int cx = c % g.cellsPerDim[0], cy = (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+            cz = c / (g.cellsPerDim[0] * g.cellsPerDim[1]);
+  for (int s = 0; s < a.stencilN; ++s) {
+    const int ox = a.stencil[3 * s], oy = a.stencil[3 * s + 1], oz = a.stencil[3 * s + 2];
+    const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
+    if (nx < 0 || ny < 0 || nz < 0 || nx >= g.cellsPerDim[0] || ny >= g.cellsPerDim[1] || nz >= g.cellsPerDim[2]) continue;
+    const int c2 = c + (oz * g.cellsPerDim[1] + oy) * g.cellsPerDim[0] + ox;
+    const int j1 = a.cellStart[c2 + 1];
+    for (int j = max(a.cellStart[c2], static_cast<int>(i) + 1); j < j1; ++j)
+      if (a.own[j] != APB_OWN_DUMMY) f(j);
+  }
+}
+
 static LCWalk makeWalk(apb_handle h) {
   LCWalk w;
   w.g = h->lc;
@@ -239,7 +258,9 @@ static int computeSPH(apb_handle h, const apb_functor *f, int newton3, apb_trave
 // ---------------------------------------------------------------------------------------------------------------------
 // Axilrod-Teller-Muto (triwise). newton3 off: every particle i evaluates the triplets (i, j, k), j < k, of its own
 // neighbourhood and receives its force (the reference's lc_c01 calls the functor three times per triplet with rotated
-// roles, CellFunctor3B.h:267-273). Three kernels: neighbours of i within the cutoff (count, fill), then the triplets.
+// roles, CellFunctor3B.h:267-273). newton3 on: every triplet once, by its lowest slot, forces on all three
+// (CellFunctor3B.h:176-262 with newton3, AxilrodTellerMutoFunctor.h:240-290). Three kernels: neighbours of i within the
+// cutoff (count, fill; newton3: higher slots only), then the triplets.
 // ---------------------------------------------------------------------------------------------------------------------
 struct ATMArgs {
   LCWalk w;
@@ -256,19 +277,24 @@ struct ATMArgs {
   LJStats *partials;
 };
 
-template <bool FILL>
+// HALF (newton3): only partners in higher slots, so that thread i owns the triplets in which it is the lowest slot
+template <bool FILL, bool HALF>
 __global__ void __launch_bounds__(128) kATMNeighbors(ATMArgs a) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   int cnt = 0;
   if (i < a.w.n && a.w.own[i] != APB_OWN_DUMMY) {
     const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
-    lcForEachPartner<false>(a.w, i, [&](int j) {
+    auto visit = [&](int j) {
       const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
       if (dot3(drx, dry, drz, drx, dry, drz) <= a.cutoff2) {
         if (FILL) a.nbr[static_cast<size_t>(cnt) * a.w.n + i] = j;
         ++cnt;
       }
-    });
+    };
+    if (HALF)
+      lcForEachHigherSlot(a.w, i, visit);
+    else
+      lcForEachPartner<false>(a.w, i, visit);
   }
   if (!FILL) {
     if (i < a.w.n) a.nbrCount[i] = cnt;
@@ -342,6 +368,103 @@ __global__ void __launch_bounds__(128) kATMTriplets(ATMArgs a) {
   if (STATS) ljStatsBlockReduce(st, a.partials);
 }
 
+// newton3: every triplet once, by the thread of its lowest slot; forces on all three participants
+// (AxilrodTellerMutoFunctor.h:240-251: F_j from its own three directions, F_k = -(F_i + F_j)), the two partners through
+// RED.ADD.F64. Globals: 3 Upot and f_p * r_p for every owned participant (:269-290).
+template <bool MIX, bool STATS>
+__global__ void __launch_bounds__(128) kATMTripletsN3(ATMArgs a) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  LJStats st;
+  ljStatsZero(st);
+  if (i < a.w.n && a.w.own[i] != APB_OWN_DUMMY) {
+    const int cnt = a.nbrCount[i];
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+    const int ti = MIX ? a.type[i] : 0;
+    const bool ownedI = a.w.own[i] == APB_OWN_OWNED;
+    double Fx = 0., Fy = 0., Fz = 0.;
+    for (int p = 0; p < cnt; ++p) {
+      const int j = a.nbr[static_cast<size_t>(p) * a.w.n + i];
+      const double xj = a.x[j], yj = a.y[j], zj = a.z[j];
+      const double ijx = xj - xi, ijy = yj - yi, ijz = zj - zi;
+      const double d2ij = dot3(ijx, ijy, ijz, ijx, ijy, ijz);
+      const bool ownedJ = a.w.own[j] == APB_OWN_OWNED;
+      double Fjx = 0., Fjy = 0., Fjz = 0.;
+      for (int q = p + 1; q < cnt; ++q) {
+        const int k = a.nbr[static_cast<size_t>(q) * a.w.n + i];
+        const double xk = a.x[k], yk = a.y[k], zk = a.z[k];
+        const double jkx = xk - xj, jky = yk - yj, jkz = zk - zj;
+        const double d2jk = dot3(jkx, jky, jkz, jkx, jky, jkz);
+        if (STATS) ++st.dist;
+        if (d2jk > a.cutoff2) continue;
+        const double kix = xi - xk, kiy = yi - yk, kiz = zi - zk;
+        const double d2ki = dot3(kix, kiy, kiz, kix, kiy, kiz);
+        double nu = a.nu;
+        if (MIX) nu = __ldg(a.nuMix + (static_cast<size_t>(ti) * a.T + a.type[j]) * a.T + a.type[k]);
+        const double all2 = d2ij * d2jk * d2ki;
+        const double all5 = all2 * all2 * sqrt(all2);
+        const double factor = 3.0 * nu / all5;
+        const double IJdKI = dot3(ijx, ijy, ijz, kix, kiy, kiz);
+        const double IJdJK = dot3(ijx, ijy, ijz, jkx, jky, jkz);
+        const double JKdKI = dot3(jkx, jky, jkz, kix, kiy, kiz);
+        const double allDots = IJdKI * IJdJK * JKdKI;
+        const double cJK = IJdKI * (IJdJK - JKdKI);
+        const double cIJ = IJdJK * JKdKI - d2jk * d2ki + 5.0 * allDots / d2ij;
+        const double cKI = -IJdJK * JKdKI + d2ij * d2jk - 5.0 * allDots / d2ki;
+        const double fix = (jkx * cJK + ijx * cIJ + kix * cKI) * factor;
+        const double fiy = (jky * cJK + ijy * cIJ + kiy * cKI) * factor;
+        const double fiz = (jkz * cJK + ijz * cIJ + kiz * cKI) * factor;
+        // force on j (:241-247)
+        const double jKI = IJdJK * (JKdKI - IJdKI);
+        const double jIJ = -IJdKI * JKdKI + d2jk * d2ki - 5.0 * allDots / d2ij;
+        const double jJK = IJdKI * JKdKI - d2ij * d2ki + 5.0 * allDots / d2jk;
+        const double fjx = (kix * jKI + ijx * jIJ + jkx * jJK) * factor;
+        const double fjy = (kiy * jKI + ijy * jIJ + jky * jJK) * factor;
+        const double fjz = (kiz * jKI + ijz * jIJ + jkz * jJK) * factor;
+        const double fkx = (fix + fjx) * (-1.0), fky = (fiy + fjy) * (-1.0), fkz = (fiz + fjz) * (-1.0);
+        Fx += fix;
+        Fy += fiy;
+        Fz += fiz;
+        Fjx += fjx;
+        Fjy += fjy;
+        Fjz += fjz;
+        atomicAdd(a.fx + k, fkx);
+        atomicAdd(a.fy + k, fky);
+        atomicAdd(a.fz + k, fkz);
+        if (STATS) {
+          ++st.kN3;
+          ++st.gN3;
+          const double u3 = factor * (all2 - 3.0 * allDots);
+          if (ownedI) {
+            st.upot += u3;
+            st.vir[0] += fix * xi;
+            st.vir[1] += fiy * yi;
+            st.vir[2] += fiz * zi;
+          }
+          if (ownedJ) {
+            st.upot += u3;
+            st.vir[0] += fjx * xj;
+            st.vir[1] += fjy * yj;
+            st.vir[2] += fjz * zj;
+          }
+          if (a.w.own[k] == APB_OWN_OWNED) {
+            st.upot += u3;
+            st.vir[0] += fkx * xk;
+            st.vir[1] += fky * yk;
+            st.vir[2] += fkz * zk;
+          }
+        }
+      }
+      atomicAdd(a.fx + j, Fjx);
+      atomicAdd(a.fy + j, Fjy);
+      atomicAdd(a.fz + j, Fjz);
+    }
+    atomicAdd(a.fx + i, Fx);
+    atomicAdd(a.fy + i, Fy);
+    atomicAdd(a.fz + i, Fz);
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
 int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f, apb_traversal_result *out);
 
 static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
@@ -349,8 +472,6 @@ static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_trave
   // the reference offers triwise traversals for LinkedCells / DirectSum only (CompatibleTraversals.h:219-231)
   if (h->cfg.container != APB_CONTAINER_LINKED_CELLS)
     return h->fail(APB_ERR_NOT_APPLICABLE, "triwise functors run on gpuLinkedCells only");
-  if (newton3)
-    return h->fail(APB_ERR_NOT_APPLICABLE, "the GPU triwise traversal evaluates every particle's own triplets (newton3 off)");
   if (!(f->cutoff > 0.) || f->cutoff > h->cfg.cutoff)
     return h->fail(APB_ERR_INVALID_ARGUMENT, "functor cutoff must be in (0, container cutoff]");
   const bool mix = f->flags & APB_FUNCTOR_USE_MIXING;
@@ -389,7 +510,11 @@ static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_trave
   int *maxDev = reinterpret_cast<int *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 32);
   a.maxCount = maxDev;
   APB_CUDA(cudaMemsetAsync(maxDev, 0, 4, h->stream));
-  ++h->launchCount, kATMNeighbors<false><<<grid, block, 0, h->stream>>>(a);
+  ++h->launchCount;
+  if (newton3)
+    kATMNeighbors<false, true><<<grid, block, 0, h->stream>>>(a);
+  else
+    kATMNeighbors<false, false><<<grid, block, 0, h->stream>>>(a);
   APB_CUDA(cudaGetLastError());
   int cap = 0;
   APB_CUDA(cudaMemcpyAsync(&cap, maxDev, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -398,18 +523,26 @@ static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_trave
   APB_CHECK(apbEnsure(h, h->nbrList, sizeof(int) * static_cast<size_t>(std::max(cap, 1)) * n));
   a.nbr = static_cast<int *>(h->nbrList.p);
   if (cap > 0) {
-    ++h->launchCount, kATMNeighbors<true><<<grid, block, 0, h->stream>>>(a);
+    ++h->launchCount;
+    if (newton3)
+      kATMNeighbors<true, true><<<grid, block, 0, h->stream>>>(a);
+    else
+      kATMNeighbors<true, false><<<grid, block, 0, h->stream>>>(a);
     APB_CUDA(cudaGetLastError());
   }
   APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * grid));
   a.partials = static_cast<LJStats *>(h->partials.p);
   ++h->launchCount;
-  const int sel = (mix ? 2 : 0) | (stats ? 1 : 0);
+  const int sel = (newton3 ? 4 : 0) | (mix ? 2 : 0) | (stats ? 1 : 0);
   switch (sel) {
     case 0: kATMTriplets<false, false><<<grid, block, 0, h->stream>>>(a); break;
     case 1: kATMTriplets<false, true><<<grid, block, 0, h->stream>>>(a); break;
     case 2: kATMTriplets<true, false><<<grid, block, 0, h->stream>>>(a); break;
-    default: kATMTriplets<true, true><<<grid, block, 0, h->stream>>>(a); break;
+    case 3: kATMTriplets<true, true><<<grid, block, 0, h->stream>>>(a); break;
+    case 4: kATMTripletsN3<false, false><<<grid, block, 0, h->stream>>>(a); break;
+    case 5: kATMTripletsN3<false, true><<<grid, block, 0, h->stream>>>(a); break;
+    case 6: kATMTripletsN3<true, false><<<grid, block, 0, h->stream>>>(a); break;
+    default: kATMTripletsN3<true, true><<<grid, block, 0, h->stream>>>(a); break;
   }
   APB_CUDA(cudaGetLastError());
   return apbFinishStats(h, grid, stats, f, out);

@@ -171,6 +171,16 @@ struct apb_handle_s {
   apb_traversal_result *asyncResultDev = nullptr;  // apb_run_steps: where the reduced accumulators of this step go
   DevBuf loopResults;
 
+  // ---- loop control (control.cu): thermostat, dynamic-rebuild trigger, remainder staging ----
+  DevBuf thermoDev, rAtRebuild, remBuf;
+  bool thermostatOn = false;
+  int thermostatInterval = 1;
+  double thermostatTarget = 0., thermostatDelta = 0.;
+  bool dynamicRebuild = false, rAtRebuildValid = false;
+  int64_t rAtRebuildSlots = 0, rAtRebuildStride = 0;
+  long long dynamicRebuildCount = 0;  // rebuilds triggered by displacement (apb_run_steps)
+  int stepsSinceRebuild = 0;  // LogicHandler::_stepsSinceLastListRebuild (used when the dynamic trigger is on)
+
   int64_t numOwned = 0, numHalo = 0;  // refreshed lazily
   bool countsValid = false;
   // owned count as last counted; stays valid while nothing can add / remove owned particles, so that the single-rank
@@ -239,6 +249,11 @@ int apbLoopTimingRecord(apb_handle h, int phase, bool begin);
 // dynamics.cu
 int apbRemapHaloLinks(apb_handle h, const int *perm, int64_t nOld, int64_t nNew);
 void apbCommDestroy(apb_handle h);
+
+// control.cu
+int apbSnapshotRebuildPositions(apb_handle h);
+// dynamics.cu: in-place ncclAllReduce of `count` doubles / int32 on the handle's stream (sum or max); no-op for one rank
+int apbAllReduce(apb_handle h, void *dev, int count, int isDouble, int isMax);
 
 // lj.cu
 int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3, apb_traversal_result *out);

@@ -280,6 +280,36 @@ int apb_exchange_halos(apb_handle h);
 /* MPI_Reduce(SUM) of potential energy / virial in Simulation.cpp:319-322, as ncclAllReduce; no-op for one rank */
 int apb_allreduce_globals(apb_handle h, apb_traversal_result *inout);
 
+/* Velocity-scaling thermostat of examples/md-flexible/src/Thermostat.h on the device.
+ * apb_calc_temperature: Thermostat::calcTemperatureComponent (:66-150): per particle type T = sum(m v.v) / (3 N), k_B = 1,
+ * summed over the ranks; every particle counts once (owned only - the reference's iterator also visits halo copies).
+ * apb_apply_thermostat: Thermostat::apply (:228-275): per type the temperature moves by at most |delta| towards the
+ * target, velocities are scaled by sqrt(T_new / T_current). 1 .. 32 types.
+ * apb_set_thermostat: apb_run_steps applies it every `interval` iterations after the velocity update
+ * (Simulation::updateThermostat, Simulation.cpp:539-546). */
+int apb_calc_temperature(apb_handle h, const double *mass_of_type, int32_t num_types, double *out_temperature,
+                         int64_t *out_count);
+int apb_apply_thermostat(apb_handle h, const double *mass_of_type, int32_t num_types, double target_temperature,
+                         double delta_temperature);
+int apb_set_thermostat(apb_handle h, int32_t enable, int32_t interval, double target_temperature,
+                       double delta_temperature);
+/* Dynamic-rebuild trigger (AUTOPAS_ENABLE_DYNAMIC_CONTAINERS, src/autopas/LogicHandler.h:955-965, 1000-1016). Enabled:
+ * every rebuild records the positions (ParticleBase::resetRAtRebuild); apb_check_dynamic_rebuild reports 1 as soon as an
+ * owned particle is skin / 2 or more away from its recorded position (max over the ranks), and apb_run_steps rebuilds
+ * then, or rebuild_frequency steps after the last rebuild, whichever comes first (LogicHandler.h:987-997). */
+int apb_set_dynamic_rebuild(apb_handle h, int32_t enable);
+int apb_check_dynamic_rebuild(apb_handle h, int32_t *out_rebuild_needed);
+int apb_get_dynamic_rebuild_count(apb_handle h, int64_t *out_count); /* rebuilds apb_run_steps did because of it */
+/* RemainderPairwiseInteractionHandler::computeRemainderInteractions (src/autopas/remainder/
+ * RemainderPairwiseInteractionHandler.h:63-135) for LJFunctor: particles LogicHandler holds in its particle / halo
+ * buffers until the next rebuild (LogicHandler.h:339-391) interact with the container particles and with each other
+ * (all pairs with a buffered particle except halo-halo), each pair applied to both partners. Container forces are
+ * updated in place; fx, fy, fz receive the forces on the buffered particles from this call; ownership: 1 owned, 2 halo
+ * (0 = skip); types may be NULL. out_result: raw accumulators to add to those of apb_compute_interactions. */
+int apb_compute_remainder(apb_handle h, const apb_functor *functor, int64_t num_buffered, const double *x,
+                          const double *y, const double *z, const int32_t *types, const int32_t *ownership, double *fx,
+                          double *fy, double *fz, apb_traversal_result *out_result);
+
 typedef struct {
   double dt;                   /* deltaT */
   const double *mass_of_type;  /* ParticlePropertiesLibrary::getMolMass(typeId) */

@@ -369,12 +369,17 @@ def sph_density(pos, mass, smth, own):
     return rho, scale
 
 
-def sph_hydro(pos, vel, mass, smth, density, pressure, snd, own):
+def sph_hydro(pos, vel, mass, smth, density, pressure, snd, own, with_eng_scale=False):
+    """Returns (acc, engDot, vsigmax, scale of acc[, scale of engDot]): the scales are the sums of the magnitudes of the
+    per-pair terms, the yardstick for 1e-12 comparisons of sums whose terms cancel."""
     n = len(pos)
     cols = [_f64(pos[:, d]) for d in range(3)] + [_f64(vel[:, d]) for d in range(3)]
-    acc, eng, vsig, scale = np.zeros(3 * n), np.zeros(n), np.zeros(n), np.zeros(n)
+    acc, eng, vsig, scale, scale_e = np.zeros(3 * n), np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
     lib().orc_sph_hydro(ctypes.c_int64(n), *[_p(c) for c in cols], _p(_f64(mass)), _p(_f64(smth)), _p(_f64(density)),
-                        _p(_f64(pressure)), _p(_f64(snd)), _p(_i64(own)), None, _p(acc), _p(eng), _p(vsig), _p(scale))
+                        _p(_f64(pressure)), _p(_f64(snd)), _p(_i64(own)), None, _p(acc), _p(eng), _p(vsig), _p(scale),
+                        _p(scale_e))
+    if with_eng_scale:
+        return acc.reshape(n, 3), eng, vsig, scale, scale_e
     return acc.reshape(n, 3), eng, vsig, scale
 
 

@@ -78,9 +78,11 @@ void orc_sph_density(int64_t n, const double *x, const double *y, const double *
 void orc_sph_hydro(int64_t n, const double *x, const double *y, const double *z, const double *vx, const double *vy,
                    const double *vz, const double *mass, const double *smth, const double *density,
                    const double *pressure, const double *snd, const int64_t *own, const double *vsigmaxIn, double *acc,
-                   double *engDot, double *vsigmax, double *scale) {
+                   double *engDot, double *vsigmax, double *scale, double *scaleEng) {
+  /* scale / scaleEng: sums of the magnitudes of the per-pair terms of the acceleration / of engDot (the rounding error
+   * of a sum scales with those, not with the possibly cancelling result); scaleEng may be NULL */
   for (int64_t i = 0; i < n; ++i) {
-    double a[3] = {0., 0., 0.}, e = 0., vm = vsigmaxIn ? vsigmaxIn[i] : 0., sc = 0.;
+    double a[3] = {0., 0., 0.}, e = 0., vm = vsigmaxIn ? vsigmaxIn[i] : 0., sc = 0., sce = 0.;
     if (own[i] != 0) {
       for (int64_t j = 0; j < n; ++j) {
         if (j == i || own[j] == 0) continue;
@@ -106,6 +108,7 @@ void orc_sph_hydro(int64_t n, const double *x, const double *y, const double *z,
         }
         const double scale2i = mass[j] * (pressure[i] / (density[i] * density[i]) + 0.5 * AV);
         e += dot3(g, dv) * scale2i;
+        sce += (fabs(g[0] * dv[0]) + fabs(g[1] * dv[1]) + fabs(g[2] * dv[2])) * fabs(scale2i);
       }
     }
     acc[3 * i] = a[0];
@@ -114,6 +117,7 @@ void orc_sph_hydro(int64_t n, const double *x, const double *y, const double *z,
     engDot[i] = e;
     vsigmax[i] = vm;
     scale[i] = sc;
+    if (scaleEng) scaleEng[i] = sce;
   }
 }
 
