@@ -64,7 +64,7 @@ def _worker(rank, world, port, n_per_dim, result_dir):
     try:
         dims = bench.decomposition(world)
         assert dims == [2, 1, 1]
-        pos, vel, bmin, bmax, gmin, gmax = bench.make_workload(n_per_dim, rank, dims, seed=3)
+        pos, vel, bmin, bmax, gmin, gmax = bench.make_workload("c2", n_per_dim, rank, dims, seed=3)
         n = len(pos)
         # communicator id: rank 0 makes 128 bytes, everybody gets the same ones
         idbuf = torch.zeros(128, dtype=torch.uint8)

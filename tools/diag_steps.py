@@ -2,7 +2,7 @@ import sys, time, numpy as np
 sys.path.insert(0, '/root/repo')
 import bench
 from autopas_b200 import GpuParticleContainer, GpuTraversal, LJFunctor
-pos, vel, bmin, bmax, gmin, gmax = bench.make_workload(100, 0, [1,1,1])
+pos, vel, bmin, bmax, gmin, gmax = bench.make_workload("c2", 100, 0, [1,1,1])
 n = len(pos)
 c = GpuParticleContainer("gpuVerletClusterLists", bmin, bmax, 2.5, 0.3, clusterSize=32)
 c.addParticles(pos[:,0], pos[:,1], pos[:,2], np.arange(n))

@@ -45,7 +45,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dims = bench.decomposition(world)
     npd = 24
-    pos, vel, bmin, bmax, gmin, gmax = bench.make_workload(npd, rank, dims, seed=7)
+    pos, vel, bmin, bmax, gmin, gmax = bench.make_workload("c2", npd, rank, dims, seed=7)
     n = len(pos)
     c = GpuParticleContainer("gpuVerletClusterLists", bmin, bmax, RC, SKIN, clusterSize=32, device=local)
     idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -83,7 +83,7 @@ def main():
         # single-GPU run of the whole system
         allpos, allvel, allid = [], [], []
         for r in range(world):
-            p, v, *_ = bench.make_workload(npd, r, dims, seed=7)
+            p, v, *_ = bench.make_workload("c2", npd, r, dims, seed=7)
             allpos.append(p)
             allvel.append(v)
             allid.append(np.arange(len(p)) + r * len(p))
