@@ -37,6 +37,8 @@
 #include "autopas/utils/inBox.h"
 #include "autopas/utils/markParticleAsDeleted.h"
 #include "autopas_b200.h"
+#include "autopas/baseFunctors/TriwiseFunctor.h"
+#include "molecularDynamicsLibrary/AxilrodTellerMutoFunctor.h"
 #include "molecularDynamicsLibrary/LJFunctor.h"
 #include "molecularDynamicsLibrary/ParticlePropertiesLibrary.h"
 
@@ -208,6 +210,111 @@ class GpuLJFunctor
   bool _postProcessed = false;
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GpuATMFunctor
+// ---------------------------------------------------------------------------------------------------------------------
+/// autopas::TriwiseFunctor around mdLib::AxilrodTellerMutoFunctor (same template flags): CPU triwise traversals call the
+/// wrapped reference functor; the GPU traversal gpulc_c08 (kATMTriplets / kATMTripletsN3) deposits the raw accumulators
+/// and endTraversal applies the reference normalisation (AxilrodTellerMutoFunctor.h:360-386: Upot = sum / 9, virial
+/// not scaled).
+template <class Particle_T, bool useMixing = false, autopas::FunctorN3Modes useNewton3 = autopas::FunctorN3Modes::Both,
+          bool calculateGlobals = false, bool countFLOPs = false>
+class GpuATMFunctor
+    : public autopas::TriwiseFunctor<Particle_T, GpuATMFunctor<Particle_T, useMixing, useNewton3, calculateGlobals, countFLOPs>> {
+  using Self = GpuATMFunctor<Particle_T, useMixing, useNewton3, calculateGlobals, countFLOPs>;
+  using Cpu = mdLib::AxilrodTellerMutoFunctor<Particle_T, useMixing, useNewton3, calculateGlobals, countFLOPs>;
+
+ public:
+  static constexpr bool apbHasGpuKernel = true;
+
+  explicit GpuATMFunctor(double cutoff) requires(not useMixing)
+      : autopas::TriwiseFunctor<Particle_T, Self>(cutoff), _cpu(cutoff), _cutoff(cutoff) {}
+  GpuATMFunctor(double cutoff, ParticlePropertiesLibrary<double, size_t> &ppl) requires(useMixing)
+      : autopas::TriwiseFunctor<Particle_T, Self>(cutoff), _cpu(cutoff, ppl), _cutoff(cutoff), _ppl(&ppl) {}
+
+  std::string getName() final { return "GpuAxilrodTellerMutoFunctor"; }
+  bool isRelevantForTuning() final { return true; }
+  bool allowsNewton3() final { return _cpu.allowsNewton3(); }
+  bool allowsNonNewton3() final { return _cpu.allowsNonNewton3(); }
+  void AoSFunctor(Particle_T &i, Particle_T &j, Particle_T &k, bool newton3) final { _cpu.AoSFunctor(i, j, k, newton3); }
+  constexpr static auto getNeededAttr() { return Cpu::getNeededAttr(); }
+  constexpr static auto getNeededAttr(std::false_type) { return Cpu::getNeededAttr(std::false_type()); }
+  constexpr static auto getComputedAttr() { return Cpu::getComputedAttr(); }
+  constexpr static bool getMixing() { return useMixing; }
+  void setParticleProperties(double nu) {
+    _cpu.setParticleProperties(nu);
+    _nu = nu;
+  }
+  void initTraversal() final {
+    _cpu.initTraversal();
+    _gpuRaw = {};
+    _gpuUpot = _gpuVirial = 0.;
+    _postProcessed = false;
+  }
+  void endTraversal(bool newton3) final {
+    if (_postProcessed) {
+      autopas::utils::ExceptionHandler::exception(
+          "Already postprocessed, endTraversal(bool newton3) was called twice without calling initTraversal().");
+    }
+    _cpu.endTraversal(newton3);
+    if constexpr (calculateGlobals) apb_atm_end_traversal(&_gpuRaw, &_gpuUpot, &_gpuVirial);
+    _postProcessed = true;
+  }
+  double getPotentialEnergy() { return _cpu.getPotentialEnergy() + _gpuUpot; }
+  double getVirial() { return _cpu.getVirial() + _gpuVirial; }
+  [[nodiscard]] size_t getNumFLOPs() const override {
+    if constexpr (countFLOPs) return _cpu.getNumFLOPs() + apb_atm_num_flops(&_gpuRaw);
+    return std::numeric_limits<size_t>::max();
+  }
+  [[nodiscard]] double getHitRate() const override {
+    if constexpr (countFLOPs) {
+      if (_gpuRaw.num_dist_calls > 0)
+        return static_cast<double>(_gpuRaw.num_kernel_calls_n3 + _gpuRaw.num_kernel_calls_no_n3) /
+               static_cast<double>(_gpuRaw.num_dist_calls);
+      return _cpu.getHitRate();
+    }
+    return std::numeric_limits<double>::quiet_NaN();
+  }
+
+  FunctorDescriptor apbDescribe() {
+    FunctorDescriptor d;
+    d.functor.kind = APB_FUNCTOR_ATM;
+    d.functor.flags = (useMixing ? APB_FUNCTOR_USE_MIXING : 0) | (calculateGlobals ? APB_FUNCTOR_CALC_GLOBALS : 0) |
+                      (countFLOPs ? APB_FUNCTOR_COUNT_FLOPS : 0);
+    d.functor.cutoff = _cutoff;
+    d.functor.nu = _nu;
+    if constexpr (useMixing) {
+      // nu_ijk = cbrt(nu_i nu_j nu_k), row-major [T * T * T] (ParticlePropertiesLibrary.h:460-470)
+      const auto T = _ppl->getNumberRegisteredSiteTypes();
+      d.mixingTable.resize(T * T * T);
+      for (size_t i = 0; i < T; ++i)
+        for (size_t j = 0; j < T; ++j)
+          for (size_t k = 0; k < T; ++k) d.mixingTable[(i * T + j) * T + k] = _ppl->getMixingNu(i, j, k);
+      d.functor.num_types = static_cast<int32_t>(T);
+      d.functor.mixing_table = d.mixingTable.data();
+    }
+    return d;
+  }
+  void apbDeposit(const apb_traversal_result &raw) {
+    _gpuRaw.upot_sum += raw.upot_sum;
+    for (int d = 0; d < 3; ++d) _gpuRaw.virial_sum[d] += raw.virial_sum[d];
+    _gpuRaw.num_dist_calls += raw.num_dist_calls;
+    _gpuRaw.num_kernel_calls_n3 += raw.num_kernel_calls_n3;
+    _gpuRaw.num_kernel_calls_no_n3 += raw.num_kernel_calls_no_n3;
+    _gpuRaw.num_global_calcs_n3 += raw.num_global_calcs_n3;
+    _gpuRaw.num_global_calcs_no_n3 += raw.num_global_calcs_no_n3;
+  }
+
+ private:
+  Cpu _cpu;
+  double _cutoff;
+  ParticlePropertiesLibrary<double, size_t> *_ppl = nullptr;
+  double _nu = 0.;
+  apb_traversal_result _gpuRaw{};
+  double _gpuUpot = 0., _gpuVirial = 0.;
+  bool _postProcessed = false;
+};
+
 template <class F>
 concept HasGpuKernel = requires(F &f) {
   { f.apbDescribe() } -> std::same_as<FunctorDescriptor>;
@@ -301,10 +408,16 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     if (_h) apb_destroy(_h);
   }
 
-  /// With INTEGRATION.md applied: ContainerOption::gpuLinkedCells / gpuVerletClusterLists.
+  /// With the edits of INTEGRATION.md applied (tools/make_autopas_overlay.py, -DAUTOPAS_B200_INTEGRATED):
+  /// ContainerOption::gpuLinkedCells / gpuVerletClusterLists; against the unmodified tree the stock look-alikes.
   [[nodiscard]] autopas::ContainerOption getContainerType() const override {
+#ifdef AUTOPAS_B200_INTEGRATED
+    return _containerKind == APB_CONTAINER_LINKED_CELLS ? autopas::ContainerOption::gpuLinkedCells
+                                                        : autopas::ContainerOption::gpuVerletClusterLists;
+#else
     return _containerKind == APB_CONTAINER_LINKED_CELLS ? autopas::ContainerOption::linkedCells
                                                         : autopas::ContainerOption::verletClusterLists;
+#endif
   }
   void reserve(size_t, size_t) override {}
 

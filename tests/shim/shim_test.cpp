@@ -12,6 +12,7 @@
 
 #include "GpuContainers.h"
 #include "autopas/containers/linkedCells/LinkedCells.h"
+#include "autopas/containers/linkedCells/traversals/LCC01Traversal.h"
 #include "autopas/containers/linkedCells/traversals/LCC08Traversal.h"
 #include "molecularDynamicsLibrary/LJFunctor.h"
 #include "molecularDynamicsLibrary/MoleculeLJ.h"
@@ -160,6 +161,62 @@ static void compare(const Scenario &s, int gpuContainer, int gpuTraversal, unsig
   CHECK(c.getNumberOfParticles(autopas::IteratorBehavior::owned) == s.owned.size() - la.size() - deleted, "%s delete", name);
 }
 
+// Axilrod-Teller-Muto through the triwise interfaces: reference LinkedCells + lc_c01 (AoS, newton3 off - the reference's
+// own ground-truth configuration for three-body functors, TraversalComparison.cpp:216-220) against gpuLinkedCells +
+// gpulc_c08 with GpuATMFunctor, newton3 off and on.
+template <bool n3>
+static void compareATM(const Scenario &s0) {
+  Scenario s = s0;
+  s.cutoff = 1.6;  // ~17 neighbours, ~60 triplets per particle: keeps the O(N n^2) reference loop short
+  s.skin = 0.2;
+  autopas::LinkedCells<Molecule> ref(s.boxMin, s.boxMax, s.cutoff, s.skin, 1.0);
+  fill(ref, s);
+  using RefFunctor = mdLib::AxilrodTellerMutoFunctor<Molecule, false, autopas::FunctorN3Modes::Both, true, true>;
+  RefFunctor fr(s.cutoff);
+  fr.setParticleProperties(0.073);
+  const auto info = ref.getTraversalSelectorInfo();
+  autopas::LCC01Traversal<FMCell, RefFunctor, false> tr(info.cellsPerDim, fr, info.interactionLength, info.cellLength,
+                                                        autopas::DataLayoutOption::aos, false);
+  ref.rebuildNeighborLists(&tr);
+  fr.initTraversal();
+  ref.computeInteractions(&tr);
+  fr.endTraversal(false);
+  autopas_b200::GpuParticleContainer<Molecule> gpu(APB_CONTAINER_LINKED_CELLS, s.boxMin, s.boxMax, s.cutoff, s.skin, 1.0, 4);
+  autopas::ParticleContainerInterface<Molecule> &c = gpu;
+  fill(c, s);
+  using GpuFunctor = autopas_b200::GpuATMFunctor<Molecule, false, autopas::FunctorN3Modes::Both, true, true>;
+  GpuFunctor fg(s.cutoff);
+  fg.setParticleProperties(0.073);
+  autopas_b200::GpuTraversal<GpuFunctor> tg(APB_TRAVERSAL_GPULC_C08, fg, n3);
+  CHECK(tg.isApplicableToDomain(), "ATM gpulc_c08 applicable");
+  c.rebuildNeighborLists(&tg);
+  fg.initTraversal();
+  c.computeInteractions(&tg);
+  fg.endTraversal(n3);
+  const auto fRef = forcesOfOwned(ref);
+  const auto fGpu = forcesOfOwned(c);
+  double maxRel = 0., fmax = 0.;
+  for (const auto &[id, f] : fRef) fmax = std::max({fmax, std::fabs(f[0]), std::fabs(f[1]), std::fabs(f[2])});
+  for (const auto &[id, f] : fRef) {
+    const auto it = fGpu.find(id);
+    if (it == fGpu.end()) {
+      CHECK(false, "ATM id %zu missing", id);
+      continue;
+    }
+    for (int d = 0; d < 3; ++d) maxRel = std::max(maxRel, std::fabs(it->second[d] - f[d]) / fmax);
+  }
+  CHECK(maxRel <= 1e-12, "ATM force mismatch %.3e (relative to max |F| = %.3e)", maxRel, fmax);
+  const double u0 = fr.getPotentialEnergy(), u1 = fg.getPotentialEnergy();
+  CHECK(std::fabs(u1 - u0) <= 1e-12 * std::fabs(u0), "ATM Upot %.17g vs %.17g", u1, u0);
+  // the virial sums f_p * r_p with absolute positions (cancelling terms): yardstick = sum of |f_i| |r_i| over owned
+  double vscale = 0.;
+  for (auto it = ref.begin(autopas::IteratorBehavior::owned); it.isValid(); ++it)
+    for (int d = 0; d < 3; ++d) vscale += std::fabs(it->getF()[d] * it->getR()[d]);
+  CHECK(std::fabs(fg.getVirial() - fr.getVirial()) <= 1e-12 * vscale, "ATM virial %.17g vs %.17g", fg.getVirial(), fr.getVirial());
+  std::printf("%-44s newton3=%d  max |dF|/max|F| = %.2e  Upot %.12e  virial %.12e\n", "gpuLinkedCells/gpulc_c08 Axilrod-Teller", int(n3),
+              maxRel, u1, fg.getVirial());
+}
+
 int main() {
   autopas::utils::ExceptionHandler::setBehavior(autopas::utils::ExceptionBehavior::throwException);
   const Scenario s = makeScenario(42);
@@ -170,6 +227,8 @@ int main() {
     compare<false>(s, APB_CONTAINER_VERLET_CLUSTER_LISTS, APB_TRAVERSAL_GPUVCL_CLUSTER_ITERATION, 4,
                    "gpuVerletClusterLists/gpuvcl_cluster_iteration");
     compare<false>(s, APB_CONTAINER_VERLET_CLUSTER_LISTS, APB_TRAVERSAL_GPUVCL_PRUNED, 32, "gpuVerletClusterLists/gpuvcl_pruned");
+    compareATM<false>(s);
+    compareATM<true>(s);
     // wrong traversal type is rejected like the reference containers do
     autopas_b200::GpuParticleContainer<Molecule> gpu(APB_CONTAINER_LINKED_CELLS, s.boxMin, s.boxMax, s.cutoff, s.skin);
     using RefFunctor = mdLib::LJFunctor<Molecule>;

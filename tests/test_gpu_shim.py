@@ -20,3 +20,33 @@ def test_cpp_shim_matches_reference_through_autopas_interfaces():
     print(r.stderr)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "SHIM TEST PASSED" in r.stdout
+
+
+TUNER = os.path.join(ROOT, "oracle", "_ref", "autopas_tuner_driver")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(TUNER), reason="oracle/_ref/autopas_tuner_driver was not built (reference tree absent)")
+def test_autotuner_samples_cpu_and_gpu_configurations_side_by_side():
+    """A stock autopas::AutoPas<MoleculeLJ> (the reference's facade, LogicHandler and AutoTuner, compiled with the header
+    overlay of tools/make_autopas_overlay.py = the additive edits of INTEGRATION.md) whose search space holds
+    LinkedCells/lc_c08 next to gpuVerletClusterLists/gpuvcl_pruned and gpuLinkedCells/gpulc_c08, newton3 off and on:
+    the tuner must sample all six through AutoPas::computeInteractions (container switches included), every sample must
+    give the forces / Upot / virial of the CPU configuration, and the tuning phase must end with one of them chosen."""
+    import json
+    r = subprocess.run([TUNER, "24", "40"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    rep = json.loads(r.stdout)
+    its = rep["iterations"]
+    configs = {i["config"] for i in its}
+    assert rep["num_configs_sampled"] == 6 and len(configs) == 6, configs
+    assert {c.split("/")[0] for c in configs} == {"LinkedCells", "gpuVerletClusterLists", "gpuLinkedCells"}
+    assert {c.split("/")[1] for c in configs} == {"lc_c08", "gpuvcl_pruned", "gpulc_c08"}
+    for i in its:
+        if i["max_rel_force_dev"] >= 0:
+            assert i["max_rel_force_dev"] <= 1e-12, i
+        assert i["upot"] == pytest.approx(rep["ref_upot"], rel=1e-12), i
+        assert i["virial"] == pytest.approx(rep["ref_virial"], rel=1e-12), i
+    assert its[0]["tuning"] and not its[-1]["tuning"]  # 6 configurations x 3 samples, then the optimum runs
+    assert rep["chosen"] in configs and its[-1]["config"] == rep["chosen"]
+    print("tuner chose", rep["chosen"])
