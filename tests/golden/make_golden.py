@@ -51,5 +51,26 @@ def main():
         print(name, "upot", r["upot"], "flops", r["flops"])
 
 
+def c1_full_size():
+    """BASELINE configs[0] at full size (C1: 32^3 = 32 768 particles, spacing 1.1225, jittered, periodic images as halos,
+    cutoff 2.5, skin 0.2): forces, Upot, virial and cell indices of the unmodified reference, LinkedCells / lc_c08 / SoA /
+    newton3 with shift (the configuration the BASELINE names). Inputs are regenerated from the seed by the tests
+    (scenarios.grid_lattice / periodic_images), so only the reference's outputs are stored."""
+    from scenarios import grid_lattice, periodic_images
+    rc, skin = 2.5, 0.2
+    pos, bmin, bmax = grid_lattice(32, 1.1225, 0.1, 42)
+    pos = bmin + np.mod(pos - bmin, bmax - bmin)
+    hpos, _ = periodic_images(pos, bmin, bmax, rc + skin)
+    allpos = np.vstack([pos, hpos])
+    own = np.r_[np.ones(len(pos)), 2 * np.ones(len(hpos))].astype(np.int64)
+    r = oracle.ref_lj_linkedcells(allpos[:, 0], allpos[:, 1], allpos[:, 2], None, own, bmin, bmax, rc, skin, 1.0, shift=True,
+                                  newton3=True, soa=True)
+    np.savez_compressed(os.path.join(HERE, "c1_full_size.npz"), n=len(pos), num_halo=len(hpos), cutoff=rc, skin=skin,
+                        ref_f=r["f"][:len(pos)], ref_upot=r["upot"], ref_virial=r["virial"],
+                        ref_cell=r["cell"].astype(np.int32), pos_checksum=float(allpos.sum()))
+    print("c1_full_size upot", r["upot"], "virial", r["virial"])
+
+
 if __name__ == "__main__":
     main()
+    c1_full_size()

@@ -76,7 +76,7 @@ def test_lj_golden_literal(cont, trav, n3):
 
 # ---- fixtures generated from the unmodified reference ---------------------------------------------------------------
 def _golden_files():
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("fn_")) if os.path.isdir(GOLDEN) else []
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("fn_", "c1_"))) if os.path.isdir(GOLDEN) else []
 
 
 @pytest.mark.parametrize("fname", _golden_files())
@@ -360,15 +360,33 @@ def _periodic_system(n_per_dim, spacing, jitter, cutoff, skin, seed=42):
 
 @pytest.mark.parametrize("n_per_dim,spacing,cutoff,skin", [(32, 1.1225, 2.5, 0.2), (100, 1.0581, 2.5, 0.3)])
 def test_full_size_properties(n_per_dim, spacing, cutoff, skin):
-    """C1 (32^3) and C2 (100^3 = 1M): all containers / traversals give the same forces and globals; total force on a
-    periodic system vanishes; newton3 on/off agree; potential energy matches the lattice-sum scale."""
+    """C1 (32^3) and C2 (100^3 = 1M) at full size: every container / traversal against the CPU oracle (forces 1e-12 of
+    the per-particle sum of pair-force magnitudes, Upot and virial 1e-12), against the committed full-size fixture of
+    the unmodified reference (C1) and - when oracle/_ref travelled to the box - against the unmodified reference run
+    live on the same particles; plus the size-independent properties: total force of the periodic system vanishes,
+    newton3 on / off agree."""
     pos, hpos, hsrc, bmin, bmax = _periodic_system(n_per_dim, spacing, 0.1, cutoff, skin)
     n = len(pos)
+    allpos = np.vstack([pos, hpos])
+    allown = np.r_[np.ones(n), 2 * np.ones(len(hpos))].astype(np.int64)
+    o = oracle.lj_linkedcells(allpos[:, 0], allpos[:, 1], allpos[:, 2], None, allown, bmin, bmax, cutoff, skin, shift=True,
+                              newton3=True)
+    ou, ov = oracle.lj_end_traversal(o["res"])
+    refs = [("oracle", o["f"][:n], ou, ov)]
+    if n_per_dim == 32:
+        g = np.load(os.path.join(GOLDEN, "c1_full_size.npz"))
+        assert int(g["n"]) == n and int(g["num_halo"]) == len(hpos) and float(g["pos_checksum"]) == float(allpos.sum())
+        refs.append(("reference fixture", g["ref_f"], float(g["ref_upot"]), float(g["ref_virial"])))
+    if oracle.have_ref():
+        r = oracle.ref_lj_linkedcells(allpos[:, 0], allpos[:, 1], allpos[:, 2], None, allown, bmin, bmax, cutoff, skin, 1.0,
+                                      shift=True, newton3=True, soa=True)
+        refs.append(("reference live", r["f"][:n], r["upot"], r["virial"]))
     results = {}
     for cont, trav, n3, M in [("gpuLinkedCells", "gpulc_c08", False, 0), ("gpuLinkedCells", "gpulc_c18", True, 0),
                               ("gpuVerletClusterLists", "gpuvcl_cluster_iteration", False, 4),
                               ("gpuVerletClusterLists", "gpuvcl_c06", True, 32),
-                              ("gpuVerletClusterLists", "gpuvcl_pruned", False, 32)]:
+                              ("gpuVerletClusterLists", "gpuvcl_pruned", False, 32),
+                              ("gpuVerletClusterLists", "gpuvcl_pruned", True, 32)]:
         c = GpuParticleContainer(cont, bmin, bmax, cutoff, skin, clusterSize=max(M, 1))
         c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(n))
         c.addHaloParticles(hpos[:, 0], hpos[:, 1], hpos[:, 2], n + np.arange(len(hpos)))
@@ -382,6 +400,11 @@ def test_full_size_properties(n_per_dim, spacing, cutoff, skin):
         results[(cont, trav, n3)] = (F, f.getPotentialEnergy(), f.getVirial())
         assert c.getNumberOfParticles("owned") == n
         c.close()
+        for name, rf, ru, rv in refs:
+            err = np.abs(F - rf).max(axis=1)
+            assert np.all(err <= FTOL * o["fscale"][:n] + 1e-300), (cont, trav, n3, name, np.max(err / o["fscale"][:n]))
+            assert f.getPotentialEnergy() == pytest.approx(ru, rel=1e-12), (cont, trav, n3, name)
+            assert f.getVirial() == pytest.approx(rv, rel=1e-12), (cont, trav, n3, name)
     keys = list(results)
     F0, u0, v0 = results[keys[0]]
     fmax = np.abs(F0).max()
@@ -482,4 +505,76 @@ def test_gpu_flop_counter_literals(newton3):
     assert (r.num_global_calcs_n3, r.num_global_calcs_no_n3) == (kn3, knon3)
     assert f.getNumFLOPs() == 8 * dist + 18 * kn3 + 15 * knon3 + 13 * kn3 + 9 * knon3
     assert f.getHitRate() == pytest.approx((kn3 + knon3) / dist, abs=1e-14)
+    c.close()
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 400.0])
+def test_pruned_reciprocal_is_accurate_over_the_whole_range(scale):
+    """kLJPruned replaces the division 1 / dr2 by MUFU.RCP64H + one cubic refinement step (pruned.cu: prRcp). Pairs at
+    distances from 1e-3 cutoff up to the cutoff, in units that put dr2 between 1e-12 and 1e+5 (tiny and huge arguments
+    of the reciprocal): forces against the oracle's IEEE division, 1e-12 of the sum of pair-force magnitudes."""
+    rng = np.random.default_rng(int(scale * 1000) + 1)
+    cutoff = 2.5 * scale
+    n_c = 40
+    centres = rng.uniform(0.2, 0.8, (n_c, 3)) * 40 * cutoff
+    parts = [centres]
+    for r_rel in (1e-3, 3e-3, 0.03, 0.2, 0.5, 0.9, 0.999):
+        d = rng.normal(size=(n_c, 3))
+        d /= np.linalg.norm(d, axis=1)[:, None]
+        parts.append(centres + d * r_rel * cutoff)
+    pos = np.vstack(parts)
+    L = 40 * cutoff
+    own = np.ones(len(pos), dtype=np.int64)
+    # sigma = scale: the potential keeps its shape, only the units change
+    kw = dict(shift=True, mixing=True, eps=[1.0, 0.8], sigma=[scale, 0.9 * scale])
+    types = rng.integers(0, 2, len(pos)).astype(np.int64)
+    bf = oracle.lj_bruteforce(pos[:, 0], pos[:, 1], pos[:, 2], types, own, cutoff, **kw)
+    for n3 in (False, True):
+        c, f = run_gpu("gpuVerletClusterLists", "gpuvcl_pruned", pos, own, types, [0, 0, 0], [L, L, L], cutoff, 0.1 * cutoff,
+                       n3, M=32, **kw)
+        check_forces(c.forcesById(len(pos)), bf["f"], bf["fscale"], own)
+        u, v = oracle.lj_end_traversal(bf["res"])
+        assert f.getPotentialEnergy() == pytest.approx(u, rel=1e-12) and f.getVirial() == pytest.approx(v, rel=1e-12)
+        c.close()
+
+
+def test_pruned_capacity_limits_on_dense_blobs():
+    """Inhomogeneous systems (droplets): a blob whose tiles stay within the staging capacity of gpuvcl_pruned must give
+    the oracle's forces; one that exceeds it (more than 4080 particles referenced by one tile) must be rejected with
+    APB_ERR_NOT_APPLICABLE - the tuner then drops the configuration (TraversalSelector.h:353-356) - while the
+    list-faithful traversal of the same container still runs."""
+    rng = np.random.default_rng(8)
+    L, rc, skin = 12.0, 2.5, 0.3
+
+    def blob(n, radius):
+        d = rng.normal(size=(n, 3))
+        d *= (radius * rng.uniform(0, 1, n) ** (1 / 3) / np.linalg.norm(d, axis=1))[:, None]
+        gas = rng.uniform(0, L, (300, 3))
+        return np.vstack([d + L / 2, gas])
+
+    # (a) dense but within capacity: 2500 particles inside radius 2 (density 75: every particle sees ~2000 others)
+    pos = blob(2500, 2.0)
+    own = np.ones(len(pos), dtype=np.int64)
+    bf = oracle.lj_bruteforce(pos[:, 0], pos[:, 1], pos[:, 2], None, own, rc, shift=True)
+    c, f = run_gpu("gpuVerletClusterLists", "gpuvcl_pruned", pos, own, None, [0, 0, 0], [L, L, L], rc, skin, False, shift=True,
+                   M=32)
+    check_forces(c.forcesById(len(pos)), bf["f"], bf["fscale"], own)
+    assert f._raw.num_kernel_calls_no_n3 == 2 * bf["res"].num_kernel_calls_n3
+    c.close()
+    # (b) beyond capacity: 7000 particles inside radius 2.2
+    pos = blob(7000, 2.2)
+    own = np.ones(len(pos), dtype=np.int64)
+    c = GpuParticleContainer("gpuVerletClusterLists", [0, 0, 0], [L, L, L], rc, skin, clusterSize=32)
+    c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(len(pos)))
+    f = make_functor(rc, True, False, 1.0, 1.0)
+    with pytest.raises(ApbError) as e:
+        c.rebuildNeighborLists(GpuTraversal("gpuvcl_pruned", f, False))
+    assert e.value.code == capi.ERR_NOT_APPLICABLE
+    t = GpuTraversal("gpuvcl_c06", f, False)  # same handle, list-faithful traversal: still applicable
+    c.rebuildNeighborLists(t)
+    f.initTraversal()
+    c.computeInteractions(t)
+    f.endTraversal(False)
+    bf = oracle.lj_bruteforce(pos[:, 0], pos[:, 1], pos[:, 2], None, own, rc, shift=True)
+    check_forces(c.forcesById(len(pos)), bf["f"], bf["fscale"], own)
     c.close()

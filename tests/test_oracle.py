@@ -172,7 +172,7 @@ def test_traversals_agree_with_brute_force(container, newton3):
 def _golden_files():
     if not os.path.isdir(GOLDEN):
         return []
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("fn_"))
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("fn_", "c1_")))
 
 
 @pytest.mark.parametrize("fname", _golden_files())
@@ -302,3 +302,25 @@ def test_flop_counter_literals(newton3, shift):
     assert (r.num_global_calcs_n3, r.num_global_calcs_no_n3) == (kn3, knon3)
     expected = 8 * dist + 18 * kn3 + 15 * knon3 + (13 if shift else 12) * kn3 + (9 if shift else 8) * knon3
     assert oracle.lj_num_flops(r, shift) == expected
+
+
+def test_oracle_matches_full_size_reference_fixture_c1():
+    """The C restatement against the unmodified reference at BASELINE configs[0] size (32 768 particles + periodic
+    images): forces 1e-12 of the per-particle sum of pair-force magnitudes, Upot / virial 1e-12, cell indices exact."""
+    import os
+    from scenarios import grid_lattice, periodic_images
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c1_full_size.npz"))
+    rc, skin = float(g["cutoff"]), float(g["skin"])
+    pos, bmin, bmax = grid_lattice(32, 1.1225, 0.1, 42)
+    pos = bmin + np.mod(pos - bmin, bmax - bmin)
+    hpos, _ = periodic_images(pos, bmin, bmax, rc + skin)
+    allpos = np.vstack([pos, hpos])
+    assert float(allpos.sum()) == float(g["pos_checksum"])
+    own = np.r_[np.ones(len(pos)), 2 * np.ones(len(hpos))].astype(np.int64)
+    o = oracle.lj_linkedcells(allpos[:, 0], allpos[:, 1], allpos[:, 2], None, own, bmin, bmax, rc, skin, shift=True, newton3=True)
+    n = len(pos)
+    err = np.abs(o["f"][:n] - g["ref_f"]).max(axis=1)
+    assert np.all(err <= 1e-12 * o["fscale"][:n])
+    u, v = oracle.lj_end_traversal(o["res"])
+    assert u == pytest.approx(float(g["ref_upot"]), rel=1e-12) and v == pytest.approx(float(g["ref_virial"]), rel=1e-12)
+    np.testing.assert_array_equal(o["cell"], g["ref_cell"])
