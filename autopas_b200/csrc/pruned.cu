@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
   float4 *rel = reinterpret_cast<float4 *>(smemRaw);
   int *stg = reinterpret_cast<int *>(rel + nP);
   unsigned *used = reinterpret_cast<unsigned *>(stg + nS);
+  unsigned *haloBits = used + nS;  // UNIFORM: bit k = particle k of the staged cluster is a halo copy
   for (int t = threadIdx.x; t < nS; t += PR_TILE) {
     stg[t] = staged[g0 + t];
     used[t] = 0u;
@@ -234,14 +235,21 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
   for (int e = threadIdx.x; e < nP; e += PR_TILE) {
     const int64_t slot = (static_cast<int64_t>(stg[e >> a.logM]) << a.logM) + (e & mask);
     float4 r;
-    if (a.own[slot] == APB_OWN_DUMMY) {
-      r = make_float4(1e30f, 0.f, 0.f, 0.f);  // padding dummies are nobody's partner (dr2 overflows to +inf)
+    const int ownE = a.own[slot];
+    if (ownE == APB_OWN_DUMMY) {
+      // padding dummies are nobody's partner: dr2 overflows to +inf (UNIFORM: |r|^2 = +inf)
+      r = make_float4(1e30f, 0.f, 0.f, UNIFORM ? __int_as_float(0x7f800000) : 0.f);
     } else {
       r = make_float4(static_cast<float>(a.x[slot] - ox), static_cast<float>(a.y[slot] - oy),
-                      static_cast<float>(a.z[slot] - oz), (N3 && a.own[slot] == APB_OWN_HALO) ? 1.f : 0.f);
+                      static_cast<float>(a.z[slot] - oz), (N3 && ownE == APB_OWN_HALO) ? 1.f : 0.f);
       ext = fmaxf(ext, fmaxf(fabsf(r.x), fmaxf(fabsf(r.y), fabsf(r.z))));
+      if (UNIFORM) r.w = fmaf(r.z, r.z, fmaf(r.y, r.y, r.x * r.x));
     }
     rel[e] = r;
+    if (UNIFORM && N3) {  // M == 32: a warp loads one staged cluster per pass (nP is a multiple of 32)
+      const unsigned hb = __ballot_sync(0xffffffffu, ownE == APB_OWN_HALO);
+      if (lane == 0) haloBits[e >> 5] = hb;
+    }
   }
   for (int s = 16; s > 0; s >>= 1) ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, s));
   if (lane == 0) sRed[warp] = ext;
@@ -253,7 +261,11 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
   // squares add a few ulp: |dr2_f32 - dr2| <= 2 sqrt(3) il (3 ext 2^-24) + il^2 2^-22  ~  6.2e-7 il ext + 2.4e-7 il^2.
   // The threshold below carries more than twice that.
   const double il = sqrt(a.il2);
-  const float thr = __double2float_ru(a.il2 * (1.0 + 1e-6) + 1.5e-6 * il * static_cast<double>(ext));
+  // UNIFORM evaluates dr2 = |ri|^2 + |rj|^2 - 2 ri.rj with |rj|^2 precomputed (3 FFMA per test instead of 3 FADD + FMUL +
+  // 2 FFMA): the squares (<= 3 ext^2 each), the three FMA roundings (partial sums <= 9 ext^2) and thr - |ri|^2 add at
+  // most 48 ulp(ext^2) = 2.9e-6 ext^2 to the error of dr2; the threshold carries twice that on top.
+  const float thr = __double2float_ru(a.il2 * (1.0 + 1e-6) + 1.5e-6 * il * static_cast<double>(ext) +
+                                      (UNIFORM ? 6e-6 * static_cast<double>(ext) * static_cast<double>(ext) : 0.0));
   const float thrBox = thr * 1.00001f;
 
   const int first = a.chunkFirst[warpGlobal], num = a.chunkNum[warpGlobal];
@@ -269,6 +281,7 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
       if (!a.clIsHalo[A]) {
         const int loA = prLowerBound(stg, nS, A);
         const float4 ri = rel[(loA << 5) + lane];
+        const float nxi = -2.f * ri.x, nyi = -2.f * ri.y, nzi = -2.f * ri.z, thri = thr - ri.w;
         // fp32 bounding box of the active particles of A
         float bx0 = active ? ri.x : 3e38f, bx1 = active ? ri.x : -3e38f;
         float by0 = active ? ri.y : 3e38f, by1 = active ? ri.y : -3e38f;
@@ -283,9 +296,23 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
         }
         const int e0 = a.nbrStart[A], e1 = a.nbrStart[A + 1];
         unsigned *mrow = o.masks + (static_cast<size_t>(e0) + A) * 32 + lane;
+        // The partner clusters of A and their positions in the staged set are fetched 32 entries at a time, one per lane
+        // (one coalesced load and 32 binary searches side by side instead of a dependent global load and a serial search
+        // per entry), and handed out by shuffles.
+        const int nE = e1 - e0 + 1;  // entry 0 is A itself
+        int Bl = A, lol = 0;
         for (int e = e0 - 1; e < e1; ++e, mrow += 32) {
-          const int B = e < e0 ? A : a.nbrList[e];
-          const int lo = prLowerBound(stg, nS, B);
+          const int q = (e - (e0 - 1)) & 31;
+          if (q == 0) {
+            const int idx = e - (e0 - 1) + lane;
+            if (idx < nE) {
+              Bl = idx == 0 ? A : __ldg(a.nbrList + e0 + idx - 1);
+              lol = prLowerBound(stg, nS, Bl);
+              o.entryLo[static_cast<size_t>(e0) + A + idx] = lol;
+            }
+          }
+          const int B = __shfl_sync(0xffffffffu, Bl, q);
+          const int lo = __shfl_sync(0xffffffffu, lol, q);
           const float4 *rb = rel + (lo << 5);
           // candidate partners: lane k tests particle k of B against the box of A
           const float4 pk = rb[lane];
@@ -303,19 +330,17 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedMasks(PrunedArgs a, const int 
 #pragma unroll
               for (int k = 8 * g8; k < 8 * g8 + 8; ++k) {
                 const float4 pj = rb[k];
-                const float dx = ri.x - pj.x, dy = ri.y - pj.y, dz = ri.z - pj.z;
-                if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) m |= 1u << k;
+                if (fmaf(nxi, pj.x, fmaf(nyi, pj.y, fmaf(nzi, pj.z, pj.w))) <= thri) m |= 1u << k;
               }
             }
           }
           if (e < e0) m &= ~(1u << lane);
           if (N3) {
-            const unsigned halos = __ballot_sync(0xffffffffu, pk.w != 0.f);  // bit k: particle k of B is a halo copy
+            const unsigned halos = haloBits[lo];  // bit k: particle k of B is a halo copy
             m &= halos | (B > A ? 0xffffffffu : (B == A ? (0xfffffffeu << lane) : 0u));
           }
           if (!active) m = 0u;
           *mrow = m;
-          if (lane == 0) o.entryLo[static_cast<size_t>(e) + 1 + A] = lo;
           cnt += __popc(m);
           const unsigned wm = __reduce_or_sync(0xffffffffu, m);
           if (lane == 0 && wm) atomicOr(&used[lo], wm);
@@ -389,7 +414,8 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
                                                        const int *__restrict__ staged, MaskOut o,
                                                        const int *__restrict__ warpRowStart,
                                                        unsigned short *__restrict__ lists, int *__restrict__ compactSlot,
-                                                       int smemRowsPerWarp, int sched, int *__restrict__ tileHalo) {
+                                                       int smemRowsPerWarp, int sched, int *__restrict__ tileHalo,
+                                                       int sentBase) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int tile = blockIdx.x;
   const int g0 = stagedStart[tile], nS = stagedStart[tile + 1] - g0;
@@ -442,7 +468,6 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   // slot instead (open addressing from the end, where most lanes idle) and may collide there; the slots left over take
   // the sentinel of the slot's own class. ~7.6 wavefronts per row in the model. Only the order inside a lane changes:
   // the same pairs are evaluated.
-  const int nC = o.numCompact[tile];
   const int R = rows * 4;
   unsigned short *gout = lists + static_cast<size_t>(warpRowStart[warpGlobal]) * 128;
   const bool viaSmem = rows <= smemRowsPerWarp;
@@ -460,16 +485,24 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   unsigned long long C0 = 0ULL, C1 = 0ULL;  // entries placed so far per class, 8 bits each (classes 0-7, 8-15)
   if (latin)
     for (int r = 0; r < rows; ++r) *reinterpret_cast<uint2 *>(out + static_cast<size_t>(r) * 128) = make_uint2(~0u, ~0u);
-  // software pipelined: the next entry's cluster id and mask are loaded while the current one is expanded
-  int lon = e1 >= e0 ? o.entryLo[static_cast<size_t>(e0) + A] : 0;
-  unsigned mn = e1 >= e0 ? o.masks[(static_cast<size_t>(e0) + A) * a.M + li] : 0u;
-  for (int e = e0 - 1; e < e1; ++e) {
-    const int lo = lon;
-    unsigned m = mn;
-    if (e + 1 < e1) {
-      lon = o.entryLo[static_cast<size_t>(e) + 2 + A];
-      mn = o.masks[(static_cast<size_t>(e) + 2 + A) * a.M + li];
+  // masks and partner positions are fetched eight entries at a time (independent loads in flight together: the loop is
+  // bound by global-memory latency otherwise), then expanded one after the other
+  constexpr int PR_FILL_BATCH = 8;
+  const size_t rowBase = static_cast<size_t>(e0) + A;  // mask row of entry 0 (A itself)
+  const int nE = e1 - e0 + 1;                          // 0 for an inactive lane
+  for (int eb = 0; eb < nE; eb += PR_FILL_BATCH) {
+    unsigned mm[PR_FILL_BATCH];
+    int ll[PR_FILL_BATCH];
+#pragma unroll
+    for (int q = 0; q < PR_FILL_BATCH; ++q) {
+      const bool v = eb + q < nE;
+      mm[q] = v ? __ldg(o.masks + (rowBase + eb + q) * a.M + li) : 0u;
+      ll[q] = v ? __ldg(o.entryLo + rowBase + eb + q) : 0;
     }
+#pragma unroll
+    for (int q = 0; q < PR_FILL_BATCH; ++q) {
+    const int lo = ll[q];
+    unsigned m = mm[q];
     const unsigned u = used[lo];
     const int cb = cbase[lo];
     while (m) {
@@ -497,6 +530,7 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
       }
       ++cnt;
     }
+    }
   }
   if (latin) {
     // empty slots: the sentinel of the slot's own class, four slots (one row) at a time
@@ -504,8 +538,9 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
       uint2 *q = reinterpret_cast<uint2 *>(out + static_cast<size_t>(r) * 128);
       uint2 v = *q;
       if (((v.x & 0xFFFFu) == 0xFFFFu) | ((v.x >> 16) == 0xFFFFu) | ((v.y & 0xFFFFu) == 0xFFFFu) | ((v.y >> 16) == 0xFFFFu)) {
-        const unsigned s0 = (nC + ((lane + 4 * r - nC) & 15)) << 4, s1 = (nC + ((lane + 4 * r + 1 - nC) & 15)) << 4,
-                       s2 = (nC + ((lane + 4 * r + 2 - nC) & 15)) << 4, s3 = (nC + ((lane + 4 * r + 3 - nC) & 15)) << 4;
+        // (sentBase is a multiple of 16: sentinel sentBase + c has bank class c)
+        const unsigned s0 = (sentBase + ((lane + 4 * r) & 15)) << 4, s1 = (sentBase + ((lane + 4 * r + 1) & 15)) << 4,
+                       s2 = (sentBase + ((lane + 4 * r + 2) & 15)) << 4, s3 = (sentBase + ((lane + 4 * r + 3) & 15)) << 4;
         if ((v.x & 0xFFFFu) == 0xFFFFu) v.x = (v.x & 0xFFFF0000u) | s0;
         if ((v.x >> 16) == 0xFFFFu) v.x = (v.x & 0xFFFFu) | (s1 << 16);
         if ((v.y & 0xFFFFu) == 0xFFFFu) v.y = (v.y & 0xFFFF0000u) | s2;
@@ -516,7 +551,7 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   } else {
     const int p = lane & 15;
     for (int t = cnt; t < R; ++t)
-      out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] = static_cast<unsigned short>((nC + ((p - nC) & 15)) << 4);
+      out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] = static_cast<unsigned short>((sentBase + p) << 4);
   }
   if (viaSmem) {
     __syncwarp();
@@ -549,6 +584,60 @@ __global__ void __launch_bounds__(1024) kPrunedTileOrder(int numTiles, const int
     if (tileHalo[t] == 0) order[posI++] = t; else order[posB++] = t;
   }
   if (threadIdx.x == 0) *numInterior = total;
+}
+
+// Execution order of the warp-specialised force kernel: the non-empty interior tiles, then the non-empty boundary tiles,
+// each group in ascending tile order; empty tiles (bricks above a tower's height, halo towers) are left out.
+// order[pos] = tile, counts = {interior, interior + boundary}. One block.
+__global__ void __launch_bounds__(1024) kPrunedActiveOrder(int numTiles, const int *__restrict__ tileHalo,
+                                                          const int *__restrict__ numCompact, int *__restrict__ order,
+                                                          int *__restrict__ counts) {
+  __shared__ int sI[1024], sB[1024];
+  const int chunk = (numTiles + 1023) / 1024;
+  const int b = min(static_cast<int>(threadIdx.x) * chunk, numTiles), e = min(b + chunk, numTiles);
+  int cI = 0, cB = 0;
+  for (int t = b; t < e; ++t)
+    if (numCompact[t] > 0) (tileHalo[t] == 0 ? cI : cB) += 1;
+  sI[threadIdx.x] = cI;
+  sB[threadIdx.x] = cB;
+  __syncthreads();
+  for (int s = 1; s < 1024; s <<= 1) {
+    const int vI = threadIdx.x >= s ? sI[threadIdx.x - s] : 0, vB = threadIdx.x >= s ? sB[threadIdx.x - s] : 0;
+    __syncthreads();
+    sI[threadIdx.x] += vI;
+    sB[threadIdx.x] += vB;
+    __syncthreads();
+  }
+  const int totalI = sI[1023];
+  int posI = sI[threadIdx.x] - cI, posB = totalI + sB[threadIdx.x] - cB;
+  for (int t = b; t < e; ++t)
+    if (numCompact[t] > 0) {
+      if (tileHalo[t] == 0) order[posI++] = t; else order[posB++] = t;
+    }
+  if (threadIdx.x == 0) {
+    counts[0] = totalI;
+    counts[1] = totalI + sB[1023];
+  }
+}
+
+// Packed per-tile and per-warp tables in execution order: one 16-byte load each in the force kernel.
+__global__ void kPrunedPackMeta(int numTiles, const int *__restrict__ order, const int *__restrict__ counts,
+                                const int *__restrict__ stagedStart, const int *__restrict__ numCompact,
+                                const int *__restrict__ chunkFirst, const int *__restrict__ chunkNum,
+                                const int *__restrict__ warpRows, const int *__restrict__ warpRowStart,
+                                int4 *__restrict__ tileMeta, int4 *__restrict__ warpMeta) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pos = g / PR_WARPS, wi = g % PR_WARPS;
+  if (pos >= counts[1]) return;
+  const int tile = order[pos];
+  if (wi == 0) tileMeta[pos] = make_int4(stagedStart[tile + 1] - stagedStart[tile], stagedStart[tile], numCompact[tile], tile);
+  const int wg = tile * PR_WARPS + wi;
+  warpMeta[g] = make_int4(chunkFirst[wg], chunkNum[wg], warpRows[wg], warpRowStart[wg]);
+}
+__global__ void kPrunedPackTab(long long totalStaged, const int *__restrict__ staged, const unsigned *__restrict__ used,
+                               const int *__restrict__ cbase, int4 *__restrict__ tab) {
+  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g < totalStaged) tab[g] = make_int4(staged[g], static_cast<int>(used[g]), cbase[g], 0);
 }
 
 int apbBuildPruned(apb_handle h, int newton3) {
@@ -630,7 +719,7 @@ int apbBuildPruned(apb_handle h, int newton3) {
                                                               std::to_string(PR_CAND_MAX) +
                                                               " cluster-list entries; use a larger cluster size");
   const int maxStaged = hostMisc[0];
-  const size_t smemMasks = static_cast<size_t>(maxStaged) * M * 16 + static_cast<size_t>(maxStaged) * 8 + 16;
+  const size_t smemMasks = static_cast<size_t>(maxStaged) * M * 16 + static_cast<size_t>(maxStaged) * 12 + 16;
   if (smemMasks > 200 * 1024)
     return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile (" + std::to_string(maxStaged * M) +
                                                " particles) does not fit shared memory; use a larger cluster size");
@@ -681,6 +770,10 @@ int apbBuildPruned(apb_handle h, int newton3) {
     return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: staged tile (" + std::to_string(maxCompact) +
                                                " particles) does not fit shared memory");
   h->prunedMaxCompact = maxCompact;
+  // shared-memory layout of the force kernels: staged particles + 16 sentinel slots at the end (padding list entries
+  // point at them, so the lists are built for one layout)
+  h->prunedCap = maxCompact + 16 <= 1280 ? 1280 : (maxCompact + 16 <= 2048 ? 2048 : 4096);
+  const int sentBase = h->prunedCap - 16;
   h->prunedRows = totalRows;
   h->prunedEntries = totalEntries;
   APB_CHECK(apbEnsure(h, h->prLists, sizeof(unsigned short) * 128 * (totalRows + 8)));  // 8 rows of slack: unchecked prefetch
@@ -699,17 +792,34 @@ int apbBuildPruned(apb_handle h, int newton3) {
   if (uniform)
     ++h->launchCount, kPrunedFill<true><<<numTiles, PR_TILE, smemFill, h->stream>>>(
         a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp, sched,
-        static_cast<int *>(h->prTileHalo.p));
+        static_cast<int *>(h->prTileHalo.p), sentBase);
   else
     ++h->launchCount, kPrunedFill<false><<<numTiles, PR_TILE, smemFill, h->stream>>>(
         a, stagedStart, staged, o, warpStart, static_cast<unsigned short *>(h->prLists.p), static_cast<int *>(h->prCompactSlot.p), smemRowsPerWarp, sched,
-        static_cast<int *>(h->prTileHalo.p));
+        static_cast<int *>(h->prTileHalo.p), sentBase);
   APB_CUDA(cudaGetLastError());
   // order[0 .. numTiles) and, behind it, the number of interior tiles
   ++h->launchCount, kPrunedTileOrder<<<1, 1024, 0, h->stream>>>(numTiles, static_cast<const int *>(h->prTileHalo.p),
                                                                static_cast<int *>(h->prTileOrder.p),
                                                                static_cast<int *>(h->prTileOrder.p) + numTiles);
   APB_CUDA(cudaGetLastError());
+  // tables of the warp-specialised kernel: active tiles in execution order, packed table entries
+  APB_CHECK(apbEnsure(h, h->prActOrder, sizeof(int) * (numTiles + 2)));
+  APB_CHECK(apbEnsure(h, h->prTileMeta, sizeof(int4) * numTiles));
+  APB_CHECK(apbEnsure(h, h->prWarpMeta, sizeof(int4) * numWarps));
+  APB_CHECK(apbEnsure(h, h->prStageTab, sizeof(int4) * stagedAlloc));
+  {
+    int *actOrder = static_cast<int *>(h->prActOrder.p), *counts = actOrder + numTiles;
+    ++h->launchCount, kPrunedActiveOrder<<<1, 1024, 0, h->stream>>>(numTiles, static_cast<const int *>(h->prTileHalo.p),
+                                                                   static_cast<const int *>(h->prNumCompact.p), actOrder, counts);
+    ++h->launchCount, kPrunedPackMeta<<<apbDivUp(numWarps, 256), 256, 0, h->stream>>>(
+        numTiles, actOrder, counts, stagedStart, static_cast<const int *>(h->prNumCompact.p), a.chunkFirst, a.chunkNum,
+        warpRows, warpStart, static_cast<int4 *>(h->prTileMeta.p), static_cast<int4 *>(h->prWarpMeta.p));
+    ++h->launchCount, kPrunedPackTab<<<static_cast<unsigned>(apbDivUp(stagedAlloc, 256)), 256, 0, h->stream>>>(
+        totalStaged, staged, static_cast<const unsigned *>(h->prUsed.p), static_cast<const int *>(h->prCbase.p),
+        static_cast<int4 *>(h->prStageTab.p));
+    APB_CUDA(cudaGetLastError());
+  }
   if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   h->prunedValid = true;
   if (getenv("APB_DEBUG"))
@@ -734,6 +844,7 @@ struct PrunedForceArgs {
   // order[*numInterior .. numTiles). A CTA beyond its part's range exits at once. Partials are indexed by position.
   const int *tileOrder, *numInterior;
   int part, numTiles;
+  int sentBase;  // first of the 16 sentinel slots of the staged layout (prunedCap - 16)
 };
 
 // reciprocal from the hardware seed: MUFU.RCP64H (relative error ~2^-20, it reads the high word only) followed by one
@@ -912,7 +1023,16 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS_CAP2048 : 
   const int tile = a.part != 0 ? a.tileOrder[pos] : pos;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warpGlobal = tile * PR_WARPS + warp;
-  const int nP = a.numCompact[tile];
+  // Prologue, ordered so that independent global loads are in flight together: (0) the per-tile and per-warp table
+  // entries, loaded unconditionally and ahead of the empty-tile test (all valid for every warp of the grid) so that they
+  // travel together instead of one dependent round trip after the other, (1) this warp's list rows (prefetched four
+  // ahead in a register ring; the list buffer has slack behind its end, so the prefetch needs no bounds check), (2) the
+  // tile's slot table, (3) the staged positions as asynchronous 8-byte copies (LDGSTS, no register round trip), (4)
+  // this lane's own particle.
+  const int nP = __ldg(a.numCompact + tile);
+  const int first = __ldg(a.chunkFirst + warpGlobal), rowsRaw = __ldg(a.warpRows + warpGlobal);
+  const int rowStart = __ldg(a.warpRowStart + warpGlobal), chunkNum = __ldg(a.chunkNum + warpGlobal);
+  const int stagedStart = __ldg(a.stagedStart + tile);
   const bool addEntries = STATS && !DEAD && pos == 0 && threadIdx.x == 0;
   if (nP == 0) {  // empty tile (block-uniform)
     if (STATS && threadIdx.x == 0) {
@@ -923,20 +1043,14 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS_CAP2048 : 
     }
     return;
   }
-  // Prologue, ordered so that independent global loads are in flight together: (1) this warp's list rows (prefetched
-  // four ahead in a register ring; the list buffer has slack behind its end, so the prefetch needs no bounds check),
-  // (2) the tile's slot table, (3) the staged positions as asynchronous 8-byte copies (LDGSTS, no register round
-  // trip), (4) this lane's own particle.
-  const int first = a.chunkFirst[warpGlobal];
 #ifdef PR_EXP_NOLOOP
-  const int rows = first >= 0 ? min(a.warpRows[warpGlobal], PR_EXP_NOLOOP) : 0;  // timing experiment only
+  const int rows = first >= 0 ? min(rowsRaw, PR_EXP_NOLOOP) : 0;  // timing experiment only
 #else
-  const int rows = first >= 0 ? a.warpRows[warpGlobal] : 0;
+  const int rows = first >= 0 ? rowsRaw : 0;
 #endif
-  const uint2 *list = reinterpret_cast<const uint2 *>(a.lists) +
-                      (rows > 0 ? static_cast<size_t>(a.warpRowStart[warpGlobal]) * 32 + lane : lane);
+  const uint2 *list = reinterpret_cast<const uint2 *>(a.lists) + (rows > 0 ? static_cast<size_t>(rowStart) * 32 + lane : lane);
   uint2 q0 = __ldg(list), q1 = __ldg(list + 32), q2 = __ldg(list + 64), q3 = __ldg(list + 96);
-  const int *cs = a.compactSlot + (static_cast<size_t>(a.stagedStart[tile]) << a.logM);
+  const int *cs = a.compactSlot + (static_cast<size_t>(stagedStart) << a.logM);
   double *sxy = reinterpret_cast<double *>(sxyz), *sz = reinterpret_cast<double *>(sxyz + CAP * 16);
   constexpr int PR_STAGE_UNROLL = 8;
   int slots[PR_STAGE_UNROLL];
@@ -946,7 +1060,7 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS_CAP2048 : 
     slots[k] = e < nP ? __ldg(cs + e) : -1;
   }
   const int64_t i = static_cast<int64_t>(first >= 0 ? first : 0) + lane;
-  const bool active = rows > 0 && lane < a.chunkNum[warpGlobal] && a.own[i] == APB_OWN_OWNED;
+  const bool active = rows > 0 && lane < chunkNum && a.own[i] == APB_OWN_OWNED;
   // a slot without an owned particle (its rows hold padding only, unless it was deleted after the build) sits far away
   const double xi = active ? a.x[i] : 0.5 * PR_FAR, yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
   const int ti = (MIX && active) ? a.type[i] : 0;
@@ -974,15 +1088,15 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS_CAP2048 : 
     if (MIX) stype[e] = a.type[slot];
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  const unsigned sentinel16 = static_cast<unsigned>(nP) << 4;
+  const unsigned sentinel16 = static_cast<unsigned>(a.sentBase) << 4;
   if (threadIdx.x < 16) {  // sentinel slots for padding entries, one per bank class
-    sxy[2 * (nP + threadIdx.x)] = PR_FAR;
-    sxy[2 * (nP + threadIdx.x) + 1] = 0.;
-    sz[prZIndex(nP + threadIdx.x)] = 0.;
+    sxy[2 * (a.sentBase + threadIdx.x)] = PR_FAR;
+    sxy[2 * (a.sentBase + threadIdx.x) + 1] = 0.;
+    sz[prZIndex(a.sentBase + threadIdx.x)] = 0.;
 #ifdef PR_ZDUP
-    sz[prZIndex(nP + threadIdx.x) + 8] = 0.;
+    sz[prZIndex(a.sentBase + threadIdx.x) + 8] = 0.;
 #endif
-    if (MIX) stype[nP + threadIdx.x] = 0;
+    if (MIX) stype[a.sentBase + threadIdx.x] = 0;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -1032,18 +1146,315 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS_CAP2048 : 
     atomicAdd(a.fz + i, acc.fz);
   }
   if (STATS) {
-    LJStats st;
-    ljStatsZero(st);
-    // potentialEnergy6 = eps24 * (lj12 - lj6) + shift6 (LJFunctor.h:174); only owned particles carry lists: weight 1
-    // K1/2 sum b^2 + K2 sum b + hits shift6; the trace of the virial is K1 sum b^2 + K2 sum b
-    st.upot = MIX ? acc.upot : fma(0.5 * a.p.k1, acc.sb2, fma(a.p.k2, acc.sb, static_cast<double>(acc.hits) * a.p.shift6));
-    st.vir[0] = VIR3 ? acc.vx : (MIX ? acc.vt : fma(a.p.k1, acc.sb2, a.p.k2 * acc.sb));
-    st.vir[1] = VIR3 ? acc.vy : 0.;
-    st.vir[2] = VIR3 ? acc.vz : 0.;
-    st.dist = DEAD ? acc.dist : (addEntries ? a.totalEntries : 0ULL);
-    st.kNoN3 = acc.hits;
-    st.gNoN3 = acc.hits;
-    ljStatsBlockReduce(st, a.partials, pos);
+    // Block sums of the raw accumulators only (2 doubles + the hit count; 5 with the per-component virial) instead of the
+    // nine fields of LJStats: fixed butterfly order inside a warp, fixed order over the warps - reproducible run to run.
+    // potentialEnergy6 = eps24 * (lj12 - lj6) + shift6 (LJFunctor.h:174); only owned particles carry lists: weight 1.
+    // Non-mixing: Upot = K1/2 sum b^2 + K2 sum b + hits shift6; the trace of the virial is K1 sum b^2 + K2 sum b.
+    constexpr int NV = VIR3 ? 5 : 2;
+    __shared__ double sRedD[PR_WARPS][NV];
+    __shared__ unsigned sRedU[PR_WARPS][2];
+    double v[NV];
+    v[0] = MIX ? acc.upot : acc.sb2;
+    v[1] = MIX ? acc.vt : acc.sb;
+    if (VIR3) v[2] = acc.vx, v[3] = acc.vy, v[4] = acc.vz;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    const unsigned hitsW = __reduce_add_sync(0xffffffffu, acc.hits);
+    const unsigned distW = DEAD ? __reduce_add_sync(0xffffffffu, acc.dist) : 0u;
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) sRedD[warp][k] = v[k];
+      sRedU[warp][0] = hitsW;
+      sRedU[warp][1] = distW;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t[NV];
+      unsigned long long hits = 0ULL, dist = 0ULL;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) t[k] = 0.;
+#pragma unroll
+      for (int w = 0; w < PR_WARPS; ++w) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) t[k] += sRedD[w][k];
+        hits += sRedU[w][0];
+        dist += sRedU[w][1];
+      }
+      LJStats st;
+      ljStatsZero(st);
+      st.upot = MIX ? t[0] : fma(0.5 * a.p.k1, t[0], fma(a.p.k2, t[1], static_cast<double>(hits) * a.p.shift6));
+      st.vir[0] = VIR3 ? t[2] : (MIX ? t[1] : fma(a.p.k1, t[0], a.p.k2 * t[1]));
+      st.vir[1] = VIR3 ? t[3] : 0.;
+      st.vir[2] = VIR3 ? t[4] : 0.;
+      st.dist = DEAD ? dist : (addEntries ? a.totalEntries : 0ULL);
+      st.kNoN3 = hits;
+      st.gNoN3 = hits;
+      a.partials[pos] = st;
+    }
+  }
+}
+
+
+// ---- warp-specialised persistent variant --------------------------------------------------------------------------------
+// kLJPruned spends 20-45 % of its warp time in the per-tile prologue: three dependent rounds of global loads (tables ->
+// slot list -> positions) before the first pair, with nothing else for the CTA to do (ncu source view, C2 / C3). Here a
+// CTA is persistent (static round-robin over the non-empty tiles in execution order) and splits into one producer warp
+// and PR_WARPS consumer warps over a double-buffered staging area:
+//   producer: for tile k, waits until the consumers have released buffer k & 1 (mbarrier `empty`), expands the tile's
+//             stage table {cluster, referenced-particle mask, compact base} - itself prefetched one tile ahead into shared
+//             memory - into asynchronous 8-byte copies of the referenced positions, and lets the copies signal mbarrier
+//             `full` themselves (cp.async.mbarrier.arrive.noinc);
+//   consumers: keep this tile's list rows and own particle in registers, issue the loads for the NEXT tile (table entry
+//             two tiles ahead), wait on `full`, run the same pair loop as kLJPruned, add the forces and release the
+//             buffer. No CTA-wide barrier per tile; a consumer never waits for global memory unless the producer falls
+//             behind. The statistics stay in registers across all tiles of a warp and are reduced once per CTA.
+// The sentinels (padding partners) live in 16 fixed slots behind the largest staged tile (sentBase ...), written once.
+struct PrunedWSArgs {
+  PrunedForceArgs f;
+  const int4 *tileMeta;  // [active tiles, execution order] {staged clusters, first stage-table entry, staged particles, tile}
+  const int4 *warpMeta;  // [active tiles * PR_WARPS] {first slot, slot count, list rows, first list row}
+  const int4 *stageTab;  // per staged cluster {cluster, mask of referenced particles, compact index of its first one, 0}
+  const int *counts;     // [0] interior active tiles, [1] active tiles
+  int partialBase;
+  int tabCap;            // stage-table entries per shared-memory buffer
+};
+
+__device__ double prFarConst = PR_FAR;
+
+__device__ __forceinline__ unsigned prSmem(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void prMbarInit(unsigned long long *b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(prSmem(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void prMbarArrive(unsigned long long *b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(prSmem(b)) : "memory");
+}
+__device__ __forceinline__ void prMbarArriveOnCopies(unsigned long long *b) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(prSmem(b)) : "memory");
+}
+__device__ __forceinline__ void prMbarWait(unsigned long long *b, unsigned parity) {
+  unsigned ok = 0;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(prSmem(b)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1 << 24)) __trap();  // a lost arrival must not hang the device
+  } while (!ok);
+}
+__device__ __forceinline__ void prCpAsync16(void *smemDst, const void *gmemSrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(prSmem(smemDst)), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void prCpAsync4(void *smemDst, const void *gmemSrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(prSmem(smemDst)), "l"(gmemSrc) : "memory");
+}
+
+#define PR_WS_THREADS (PR_TILE + 32)
+
+template <bool MIX, bool STATS, bool DEAD, bool VIR3, int CAP>
+__global__ void __launch_bounds__(PR_WS_THREADS, CAP <= 1280 ? 3 : 2) kLJPrunedWS(PrunedWSArgs w) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  constexpr int BUF = CAP * PR_BYTES_XYZ + (MIX ? CAP * 4 : 0);
+  int4 *tab = reinterpret_cast<int4 *>(smemRaw + 2 * BUF);
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tab + 2 * w.tabCap);  // full[2], empty[2]
+  const PrunedForceArgs &a = w.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int begin = 0, end;
+  {
+    const int nI = __ldg(w.counts), nA = __ldg(w.counts + 1);
+    end = a.part == 1 ? nI : nA;
+    if (a.part == 2) begin = nI;
+  }
+  const int grid = gridDim.x;
+  int pos = begin + blockIdx.x;
+  if (threadIdx.x == 0) {
+    prMbarInit(mbar + 0, 32);
+    prMbarInit(mbar + 1, 32);
+    prMbarInit(mbar + 2, PR_WARPS);
+    prMbarInit(mbar + 3, PR_WARPS);
+  }
+  if (threadIdx.x < 32) {  // sentinel slots of both buffers, one per bank class
+    unsigned char *bufS = smemRaw + (threadIdx.x >> 4) * BUF;
+    const int e = a.sentBase + (threadIdx.x & 15);
+    reinterpret_cast<double *>(bufS)[2 * e] = PR_FAR;
+    reinterpret_cast<double *>(bufS)[2 * e + 1] = 0.;
+    reinterpret_cast<double *>(bufS + CAP * 16)[prZIndex(e)] = 0.;
+    if (MIX) reinterpret_cast<int *>(bufS + static_cast<size_t>(CAP) * PR_BYTES_XYZ)[e] = 0;
+  }
+  __syncthreads();
+  PairAcc<MIX, STATS, VIR3> acc;
+  if (warp == PR_WARPS) {
+    // ---- producer ----
+    if (pos < end) {
+      int4 metaCur = __ldg(w.tileMeta + pos);
+      int4 metaNxt = pos + grid < end ? __ldg(w.tileMeta + pos + grid) : make_int4(0, 0, 0, 0);
+      for (int t = lane; t < metaCur.x; t += 32) prCpAsync16(tab + t, w.stageTab + metaCur.y + t);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      for (int k = 0; pos < end; ++k, pos += grid) {
+        const int b = k & 1;
+        if (k == 0)
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else
+          asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's table has landed; the previous tile's positions may still fly
+        __syncwarp();
+        if (k >= 2) prMbarWait(mbar + 2 + b, ((k >> 1) - 1) & 1);
+        const int4 *tb = tab + b * w.tabCap;
+        {  // next tile's table
+          int4 *tn = tab + (b ^ 1) * w.tabCap;
+          for (int t = lane; t < metaNxt.x; t += 32) prCpAsync16(tn + t, w.stageTab + metaNxt.y + t);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        unsigned char *buf = smemRaw + b * BUF;
+        double *sxy = reinterpret_cast<double *>(buf), *sz = reinterpret_cast<double *>(buf + CAP * 16);
+        int *stype = reinterpret_cast<int *>(buf + static_cast<size_t>(CAP) * PR_BYTES_XYZ);
+        const int nSlots = metaCur.x << a.logM, mMask = a.M - 1;
+#pragma unroll 4
+        for (int idx = lane; idx < nSlots; idx += 32) {
+          const int kk = idx & mMask;
+          const int4 t = tb[idx >> a.logM];
+          if ((static_cast<unsigned>(t.y) >> kk) & 1u) {
+            const int e = t.z + __popc(static_cast<unsigned>(t.y) & ((1u << kk) - 1u));
+            const int64_t slot = (static_cast<int64_t>(t.x) << a.logM) + kk;
+            const double *srcX = a.x + slot;
+            if (DEAD && a.own[slot] == APB_OWN_DUMMY) srcX = &prFarConst;  // deleted since the list build: out of reach
+            prCpAsync8(sxy + 2 * e, srcX);
+            prCpAsync8(sxy + 2 * e + 1, a.y + slot);
+            prCpAsync8(sz + prZIndex(e), a.z + slot);
+            if (MIX) prCpAsync4(stype + e, a.type + slot);
+          }
+        }
+        prMbarArriveOnCopies(mbar + b);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        metaCur = metaNxt;
+        metaNxt = pos + 2 * grid < end ? __ldg(w.tileMeta + pos + 2 * grid) : make_int4(0, 0, 0, 0);
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+  } else if (pos < end) {
+    // ---- consumers ----
+    // warp table entry -> list rows (four in a register ring), own particle
+#define PR_WS_LOAD(META, ROWS, LIST, Q0, Q1, Q2, Q3, I, ACTIVE, XI, YI, ZI, TI)                                          \
+  do {                                                                                                                   \
+    ROWS = (META).x >= 0 ? (META).z : 0;                                                                                 \
+    LIST = reinterpret_cast<const uint2 *>(a.lists) + (ROWS > 0 ? static_cast<size_t>((META).w) * 32 + lane : lane);     \
+    Q0 = __ldg(LIST), Q1 = __ldg(LIST + 32), Q2 = __ldg(LIST + 64), Q3 = __ldg(LIST + 96);                               \
+    I = static_cast<int64_t>((META).x >= 0 ? (META).x : 0) + lane;                                                       \
+    ACTIVE = ROWS > 0 && lane < (META).y && a.own[I] == APB_OWN_OWNED;                                                   \
+    XI = ACTIVE ? a.x[I] : 0.5 * PR_FAR, YI = ACTIVE ? a.y[I] : 0., ZI = ACTIVE ? a.z[I] : 0.;                           \
+    TI = (MIX && ACTIVE) ? a.type[I] : 0;                                                                                \
+  } while (0)
+    int4 mNxt = pos + grid < end ? __ldg(w.warpMeta + static_cast<size_t>(pos + grid) * PR_WARPS + warp) : make_int4(-1, 0, 0, 0);
+    int rows, ti;
+    const uint2 *list;
+    uint2 q0, q1, q2, q3;
+    int64_t i;
+    bool active;
+    double xi, yi, zi;
+    {
+      const int4 mCur = __ldg(w.warpMeta + static_cast<size_t>(pos) * PR_WARPS + warp);
+      PR_WS_LOAD(mCur, rows, list, q0, q1, q2, q3, i, active, xi, yi, zi, ti);
+    }
+    const unsigned sentinel16 = static_cast<unsigned>(a.sentBase) << 4;
+    for (int k = 0; pos < end; ++k, pos += grid) {
+      const int b = k & 1;
+      // next tile: its list rows and own particle travel while this tile is evaluated
+      int rowsN, tiN;
+      const uint2 *listN;
+      uint2 n0, n1, n2, n3;
+      int64_t iN;
+      bool activeN;
+      double xN, yN, zN;
+      PR_WS_LOAD(mNxt, rowsN, listN, n0, n1, n2, n3, iN, activeN, xN, yN, zN, tiN);
+      mNxt = pos + 2 * grid < end ? __ldg(w.warpMeta + static_cast<size_t>(pos + 2 * grid) * PR_WARPS + warp) : make_int4(-1, 0, 0, 0);
+      const unsigned char *sxyz = smemRaw + b * BUF;
+      const int *stype = reinterpret_cast<const int *>(sxyz + static_cast<size_t>(CAP) * PR_BYTES_XYZ);
+      prMbarWait(mbar + b, (k >> 1) & 1);
+      int r = 0;
+      list += 128;
+      for (; r + 4 <= rows; r += 4, list += 128) {
+        PR_ROW(q0);
+        q0 = __ldg(list);
+        PR_ROW(q1);
+        q1 = __ldg(list + 32);
+        PR_ROW(q2);
+        q2 = __ldg(list + 64);
+        PR_ROW(q3);
+        q3 = __ldg(list + 96);
+      }
+      if (r < rows) {
+        PR_ROW(q0);
+        if (r + 1 < rows) {
+          PR_ROW(q1);
+          if (r + 2 < rows) PR_ROW(q2);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) prMbarArrive(mbar + 2 + b);  // this warp is done with the buffer
+      if (active) {
+        atomicAdd(a.fx + i, acc.fx);
+        atomicAdd(a.fy + i, acc.fy);
+        atomicAdd(a.fz + i, acc.fz);
+      }
+      acc.fx = acc.fy = acc.fz = 0.;
+      rows = rowsN, list = listN, q0 = n0, q1 = n1, q2 = n2, q3 = n3, i = iN, active = activeN, xi = xN, yi = yN, zi = zN, ti = tiN;
+    }
+#undef PR_WS_LOAD
+  }
+  if (STATS) {
+    constexpr int NV = VIR3 ? 5 : 2;
+    __shared__ double sRedD[PR_WARPS][NV];
+    __shared__ unsigned long long sRedU[PR_WARPS][2];
+    if (warp < PR_WARPS) {
+      double v[NV];
+      v[0] = MIX ? acc.upot : acc.sb2;
+      v[1] = MIX ? acc.vt : acc.sb;
+      if (VIR3) v[2] = acc.vx, v[3] = acc.vy, v[4] = acc.vz;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+      }
+      unsigned long long hitsW = acc.hits, distW = DEAD ? acc.dist : 0U;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        hitsW += __shfl_xor_sync(0xffffffffu, hitsW, o);
+        if (DEAD) distW += __shfl_xor_sync(0xffffffffu, distW, o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) sRedD[warp][q] = v[q];
+        sRedU[warp][0] = hitsW;
+        sRedU[warp][1] = distW;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t[NV];
+      unsigned long long hits = 0ULL, dist = 0ULL;
+#pragma unroll
+      for (int q = 0; q < NV; ++q) t[q] = 0.;
+#pragma unroll
+      for (int q2 = 0; q2 < PR_WARPS; ++q2) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) t[q] += sRedD[q2][q];
+        hits += sRedU[q2][0];
+        dist += sRedU[q2][1];
+      }
+      LJStats st;
+      ljStatsZero(st);
+      st.upot = MIX ? t[0] : fma(0.5 * a.p.k1, t[0], fma(a.p.k2, t[1], static_cast<double>(hits) * a.p.shift6));
+      st.vir[0] = VIR3 ? t[2] : (MIX ? t[1] : fma(a.p.k1, t[0], a.p.k2 * t[1]));
+      st.vir[1] = VIR3 ? t[3] : 0.;
+      st.vir[2] = VIR3 ? t[4] : 0.;
+      st.dist = DEAD ? dist : ((begin + static_cast<int>(blockIdx.x) == 0 && begin < end) ? a.totalEntries : 0ULL);
+      st.kNoN3 = hits;
+      st.gNoN3 = hits;
+      a.partials[w.partialBase + blockIdx.x] = st;
+    }
   }
 }
 
@@ -1099,21 +1510,21 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? 3 : 1) kLJPrunedN3(Prun
     if (MIX) stype[e] = a.type[slot];
   }
   if (threadIdx.x < 16) {
-    sxy[2 * (nP + threadIdx.x)] = PR_FAR;
-    sxy[2 * (nP + threadIdx.x) + 1] = 0.;
-    sz[prZIndex(nP + threadIdx.x)] = 0.;
+    sxy[2 * (a.sentBase + threadIdx.x)] = PR_FAR;
+    sxy[2 * (a.sentBase + threadIdx.x) + 1] = 0.;
+    sz[prZIndex(a.sentBase + threadIdx.x)] = 0.;
 #ifdef PR_ZDUP
-    sz[prZIndex(nP + threadIdx.x) + 8] = 0.;
+    sz[prZIndex(a.sentBase + threadIdx.x) + 8] = 0.;
 #endif
-    sslot[nP + threadIdx.x] = -1;
-    if (MIX) stype[nP + threadIdx.x] = 0;
+    sslot[a.sentBase + threadIdx.x] = -1;
+    if (MIX) stype[a.sentBase + threadIdx.x] = 0;
   }
   const int64_t i = static_cast<int64_t>(first >= 0 ? first : 0) + lane;
   const bool active = rows > 0 && lane < a.chunkNum[warpGlobal] && a.own[i] == APB_OWN_OWNED;
   const double xi = active ? a.x[i] : 0.5 * PR_FAR, yi = active ? a.y[i] : 0., zi = active ? a.z[i] : 0.;
   const int ti = (MIX && active) ? a.type[i] : 0;
   __syncthreads();
-  const unsigned sentinel16 = static_cast<unsigned>(nP) << 4;
+  const unsigned sentinel16 = static_cast<unsigned>(a.sentBase) << 4;
   double fx = 0., fy = 0., fz = 0.;
   double upot = 0., vx = 0., vy = 0., vz = 0.;
   unsigned dist = 0, hits = 0;
@@ -1212,7 +1623,8 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   a.totalEntries = h->prunedEntries;
   a.p = p;
   // shared-memory layout compiled for 2048 or 4096 staged particles (4 or 2 CTAs per SM)
-  const int cap = h->prunedMaxCompact + 16 <= 2048 ? 2048 : 4096;
+  const int cap = h->prunedCap <= 2048 ? 2048 : 4096;
+  a.sentBase = h->prunedCap - 16;
   const size_t smem = static_cast<size_t>(cap) * (mix ? PR_BYTES_XYZ + 4 : PR_BYTES_XYZ);
   // per-component virial only on request: LJFunctor exposes the sum alone (getVirial, LJFunctor.h:719)
   const bool vir3 = stats && !(f->flags & APB_FUNCTOR_VIRIAL_TRACE);
@@ -1225,6 +1637,64 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   const int numBlocks = numTiles;
   APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * numBlocks));
   a.partials = static_cast<LJStats *>(h->partials.p);
+  // Warp-specialised persistent kernel (default; APB_PRUNED_WS=0 keeps the one-tile-per-CTA kernel): newton3 off, staged
+  // tiles of at most 2032 particles.
+  static const bool wsEnv = getenv("APB_PRUNED_WS") == nullptr || atoi(getenv("APB_PRUNED_WS")) != 0;
+  if (!n3 && wsEnv && h->prunedCap <= 2048 && PR_WARPS == 8) {
+    PrunedWSArgs w;
+    w.tileMeta = static_cast<const int4 *>(h->prTileMeta.p);
+    w.warpMeta = static_cast<const int4 *>(h->prWarpMeta.p);
+    w.stageTab = static_cast<const int4 *>(h->prStageTab.p);
+    w.counts = static_cast<const int *>(h->prActOrder.p) + numTiles;
+    w.tabCap = (h->prunedMaxStaged + 3) & ~3;
+    // layout for 1280 staged particles: 3 CTAs per SM at 72 registers; for 2048: 2 CTAs at 96 (APB_PRUNED_WS_CAP overrides)
+    static const int capEnv = getenv("APB_PRUNED_WS_CAP") ? atoi(getenv("APB_PRUNED_WS_CAP")) : 0;
+    const int wcap = (capEnv == 2048 || h->prunedCap > 1280) ? 2048 : 1280;
+    const int ctasPerSM = wcap <= 1280 ? 3 : 2;
+    const int grid = std::max(1, std::min(numTiles, ctasPerSM * h->numSMs));
+    w.partialBase = part == 2 ? grid : 0;
+    APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * 2 * grid));
+    a.partials = static_cast<LJStats *>(h->partials.p);
+    w.f = a;
+    const size_t smemWS = 2 * static_cast<size_t>(wcap) * (mix ? PR_BYTES_XYZ + 4 : PR_BYTES_XYZ) + 2 * static_cast<size_t>(w.tabCap) * 16 + 64;
+#define PR_LAUNCH_WS_CAP(MIXV, STATSV, DEADV, VIRV, CAPV)                                                              \
+  do {                                                                                                                 \
+    ++h->launchCount, kLJPrunedWS<MIXV, STATSV, DEADV, VIRV, CAPV><<<grid, PR_WS_THREADS, smemWS, h->stream>>>(w);     \
+  } while (0)
+#define PR_LAUNCH_WS(MIXV, STATSV, DEADV, VIRV)                                                                        \
+  do {                                                                                                                 \
+    if (wcap == 1280)                                                                                                  \
+      PR_LAUNCH_WS_CAP(MIXV, STATSV, DEADV, VIRV, 1280);                                                               \
+    else                                                                                                               \
+      PR_LAUNCH_WS_CAP(MIXV, STATSV, DEADV, VIRV, 2048);                                                               \
+  } while (0)
+    switch (sel) {
+      case 0: PR_LAUNCH_WS(false, false, false, false); break;
+      case 2: PR_LAUNCH_WS(false, false, true, false); break;
+      case 4: PR_LAUNCH_WS(false, true, false, false); break;
+      case 5: PR_LAUNCH_WS(false, true, false, true); break;
+      case 6: PR_LAUNCH_WS(false, true, true, false); break;
+      case 7: PR_LAUNCH_WS(false, true, true, true); break;
+      case 8: PR_LAUNCH_WS(true, false, false, false); break;
+      case 10: PR_LAUNCH_WS(true, false, true, false); break;
+      case 12: PR_LAUNCH_WS(true, true, false, false); break;
+      case 13: PR_LAUNCH_WS(true, true, false, true); break;
+      case 14: PR_LAUNCH_WS(true, true, true, false); break;
+      default: PR_LAUNCH_WS(true, true, true, true); break;
+    }
+#undef PR_LAUNCH_WS
+#undef PR_LAUNCH_WS_CAP
+    {
+      const cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) {
+        h->poisoned = true;
+        return h->fail(APB_ERR_CUDA, std::string("kLJPrunedWS launch failed: ") + cudaGetErrorString(e) + " (grid " +
+                                         std::to_string(grid) + ", dynamic smem " + std::to_string(smemWS) + " B)");
+      }
+    }
+    if (part == 1) return APB_OK;  // the boundary half follows and finishes the statistics
+    return apbFinishStats(h, part == 2 ? 2 * grid : grid, stats, f, out);
+  }
   if (n3) {
     const size_t smemN3 = static_cast<size_t>(cap) * (PR_BYTES_XYZ + (mix ? 8 : 4));
 #define PR_LAUNCH_N3(MIXV, STATSV)                                                                                      \
@@ -1308,6 +1778,25 @@ int apbInitPrunedAttributes(apb_handle h) {
   PR_ATTR(true, true, true, false);
   PR_ATTR(true, true, true, true);
 #undef PR_ATTR
+#define PR_ATTR_WS(MIXV, STATSV, DEADV, VIRV)                                                                           \
+  APB_CUDA(cudaFuncSetAttribute(kLJPrunedWS<MIXV, STATSV, DEADV, VIRV, 1280>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                2 * 1280 * (PR_BYTES_XYZ + 4) + 16 * 1024));                                             \
+  APB_CUDA(cudaFuncSetAttribute(kLJPrunedWS<MIXV, STATSV, DEADV, VIRV, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                2 * 2048 * (PR_BYTES_XYZ + 4) + 16 * 1024))
+  PR_ATTR_WS(false, false, false, false);
+  PR_ATTR_WS(false, false, true, false);
+  PR_ATTR_WS(false, true, false, false);
+  PR_ATTR_WS(false, true, false, true);
+  PR_ATTR_WS(false, true, true, false);
+  PR_ATTR_WS(false, true, true, true);
+  PR_ATTR_WS(true, false, false, false);
+  PR_ATTR_WS(true, false, true, false);
+  PR_ATTR_WS(true, true, false, false);
+  PR_ATTR_WS(true, true, false, true);
+  PR_ATTR_WS(true, true, true, false);
+  PR_ATTR_WS(true, true, true, true);
+#undef PR_ATTR_WS
+  APB_CUDA(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, h->cfg.device));
 #define PR_ATTR_N3(MIXV, STATSV)                                                                                       \
   APB_CUDA(cudaFuncSetAttribute(kLJPrunedN3<MIXV, STATSV, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                 2048 * (PR_BYTES_XYZ + 8)));                                                           \
