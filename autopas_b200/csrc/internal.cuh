@@ -106,11 +106,7 @@ struct apb_handle_s {
   DevBuf prEntryLo;
   DevBuf prTileHalo, prTileOrder;  // per tile: stages a halo copy; tiles ordered interior first (+ the interior count)
   int prunedPart = 0;              // 0: whole traversal; 1 / 2: interior / boundary half of a split step (apb_run_steps)
-  // warp-specialised force kernel (kLJPrunedWS): non-empty tiles in execution order (interior first) with their packed
-  // tables, + [interior count, active count] behind the order
-  DevBuf prActOrder, prTileMeta, prWarpMeta, prStageTab;
   int prunedCap = 0;  // staged particles incl. the 16 sentinel slots the lists were built for (1280, 2048 or 4096)
-  int numSMs = 0;
   cudaEvent_t evSplit[2] = {nullptr, nullptr};
 
   // ---- reductions / results ----

@@ -472,24 +472,30 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
   unsigned short *gout = lists + static_cast<size_t>(warpRowStart[warpGlobal]) * 128;
   const bool viaSmem = rows <= smemRowsPerWarp;
   const bool latin = viaSmem && sched;
+  // Shared-memory assembly is lane-major: lane l owns the R consecutive 2-byte slots at l * stride (stride = an odd
+  // number of 8-byte rows, so that the transposing copy-out - lane l reads its row r, the warp writes 256 contiguous
+  // bytes - is free of bank conflicts). Appending an entry is then one STS and one pointer increment.
   unsigned char *blocks = smemRaw + ((static_cast<size_t>(nS) * 12 + 15) & ~size_t(15));
-  unsigned short *block = viaSmem ? reinterpret_cast<unsigned short *>(blocks) + static_cast<size_t>(warp) * smemRowsPerWarp * 128 : gout;
-  unsigned short *out = block + lane * 4;
+  const int strideRows = smemRowsPerWarp | 1;
+  unsigned short *mine = reinterpret_cast<unsigned short *>(blocks) +
+                         (static_cast<size_t>(warp) * 32 + lane) * strideRows * 4;  // viaSmem only
   const int64_t i = static_cast<int64_t>(first) + lane;
   const bool laneIn = lane < num;
   const int A = static_cast<int>((laneIn ? i : static_cast<int64_t>(first)) >> a.logM);
   const bool active = laneIn && a.own[i] == APB_OWN_OWNED && !a.clIsHalo[A];
   const int li = static_cast<int>(i) & mask;
   const int e0 = active ? a.nbrStart[A] : 0, e1 = active ? a.nbrStart[A + 1] : -1;
+  const unsigned sentMine = static_cast<unsigned>(sentBase + (lane & 15)) << 4;
   int cnt = 0, spill = R - 1;
-  unsigned long long C0 = 0ULL, C1 = 0ULL;  // entries placed so far per class, 8 bits each (classes 0-7, 8-15)
+  unsigned long long C0 = 0ULL, C1 = 0ULL;  // Latin: entries placed so far per class, 8 bits each (classes 0-7, 8-15)
   if (latin)
-    for (int r = 0; r < rows; ++r) *reinterpret_cast<uint2 *>(out + static_cast<size_t>(r) * 128) = make_uint2(~0u, ~0u);
+    for (int r = 0; r < rows; ++r) *reinterpret_cast<uint2 *>(mine + r * 4) = make_uint2(~0u, ~0u);
   // masks and partner positions are fetched eight entries at a time (independent loads in flight together: the loop is
   // bound by global-memory latency otherwise), then expanded one after the other
   constexpr int PR_FILL_BATCH = 8;
   const size_t rowBase = static_cast<size_t>(e0) + A;  // mask row of entry 0 (A itself)
   const int nE = e1 - e0 + 1;                          // 0 for an inactive lane
+  unsigned short *wp = mine;
   for (int eb = 0; eb < nE; eb += PR_FILL_BATCH) {
     unsigned mm[PR_FILL_BATCH];
     int ll[PR_FILL_BATCH];
@@ -501,63 +507,59 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedFill(PrunedArgs a, const int *
     }
 #pragma unroll
     for (int q = 0; q < PR_FILL_BATCH; ++q) {
-    const int lo = ll[q];
-    unsigned m = mm[q];
-    const unsigned u = used[lo];
-    const int cb = cbase[lo];
-    while (m) {
-      const int k = __ffs(m) - 1;
-      m &= m - 1;
-      const unsigned ci = cb + __popc(u & ((1u << k) - 1u));
-      if (latin) {
-        const unsigned cls = ci & 15u, sh = (cls & 7u) * 8u;
-        unsigned j;
-        if (cls & 8u) {
-          j = static_cast<unsigned>(C1 >> sh) & 0xFFu;
-          C1 += 1ULL << sh;
-        } else {
-          j = static_cast<unsigned>(C0 >> sh) & 0xFFu;
-          C0 += 1ULL << sh;
+      unsigned m = mm[q];
+      const unsigned u = used[ll[q]];
+      const unsigned cb16 = static_cast<unsigned>(cbase[ll[q]]) << 4;
+      if (viaSmem && !latin) {
+        // lowest set bit k of m: its rank among the referenced particles of the cluster is popc(u & bits below k), and
+        // the bits below k are ~m & (m - 1) - no bit index, no shift
+        while (m) {
+          const unsigned t = m - 1u;
+          *wp++ = static_cast<unsigned short>(cb16 + (static_cast<unsigned>(__popc(u & ~m & t)) << 4));
+          m &= t;
         }
-        int t = static_cast<int>((cls - lane) & 15u) + 16 * static_cast<int>(j);
-        if (t >= R || out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] != 0xFFFFu) {
-          while (out[static_cast<size_t>(spill >> 2) * 128 + (spill & 3)] != 0xFFFFu) --spill;  // cnt <= R: one is free
-          t = spill--;
-        }
-        out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] = static_cast<unsigned short>(ci << 4);
       } else {
-        out[static_cast<size_t>(cnt >> 2) * 128 + (cnt & 3)] = static_cast<unsigned short>(ci << 4);
+        while (m) {
+          const unsigned t = m - 1u;
+          const unsigned ci16 = cb16 + (static_cast<unsigned>(__popc(u & ~m & t)) << 4);
+          m &= t;
+          if (latin) {
+            const unsigned cls = (ci16 >> 4) & 15u, sh = (cls & 7u) * 8u;
+            unsigned j;
+            if (cls & 8u) {
+              j = static_cast<unsigned>(C1 >> sh) & 0xFFu;
+              C1 += 1ULL << sh;
+            } else {
+              j = static_cast<unsigned>(C0 >> sh) & 0xFFu;
+              C0 += 1ULL << sh;
+            }
+            int t2 = static_cast<int>((cls - lane) & 15u) + 16 * static_cast<int>(j);
+            if (t2 >= R || mine[t2] != 0xFFFFu) {
+              while (mine[spill] != 0xFFFFu) --spill;  // cnt <= R: one is free
+              t2 = spill--;
+            }
+            mine[t2] = static_cast<unsigned short>(ci16);
+          } else {
+            gout[static_cast<size_t>(cnt >> 2) * 128 + lane * 4 + (cnt & 3)] = static_cast<unsigned short>(ci16);
+          }
+          ++cnt;
+        }
       }
-      ++cnt;
-    }
     }
   }
+  if (viaSmem && !latin) cnt = static_cast<int>(wp - mine);
   if (latin) {
-    // empty slots: the sentinel of the slot's own class, four slots (one row) at a time
-    for (int r = 0; r < rows; ++r) {
-      uint2 *q = reinterpret_cast<uint2 *>(out + static_cast<size_t>(r) * 128);
-      uint2 v = *q;
-      if (((v.x & 0xFFFFu) == 0xFFFFu) | ((v.x >> 16) == 0xFFFFu) | ((v.y & 0xFFFFu) == 0xFFFFu) | ((v.y >> 16) == 0xFFFFu)) {
-        // (sentBase is a multiple of 16: sentinel sentBase + c has bank class c)
-        const unsigned s0 = (sentBase + ((lane + 4 * r) & 15)) << 4, s1 = (sentBase + ((lane + 4 * r + 1) & 15)) << 4,
-                       s2 = (sentBase + ((lane + 4 * r + 2) & 15)) << 4, s3 = (sentBase + ((lane + 4 * r + 3) & 15)) << 4;
-        if ((v.x & 0xFFFFu) == 0xFFFFu) v.x = (v.x & 0xFFFF0000u) | s0;
-        if ((v.x >> 16) == 0xFFFFu) v.x = (v.x & 0xFFFFu) | (s1 << 16);
-        if ((v.y & 0xFFFFu) == 0xFFFFu) v.y = (v.y & 0xFFFF0000u) | s2;
-        if ((v.y >> 16) == 0xFFFFu) v.y = (v.y & 0xFFFFu) | (s3 << 16);
-        *q = v;
-      }
-    }
+    // empty slots: the sentinel of the slot's own class (sentBase is a multiple of 16: sentinel sentBase + c has class c)
+    for (int t = 0; t < R; ++t)
+      if (mine[t] == 0xFFFFu) mine[t] = static_cast<unsigned short>((sentBase + ((lane + t) & 15)) << 4);
+  } else if (viaSmem) {
+    for (int t = cnt; t < R; ++t) mine[t] = static_cast<unsigned short>(sentMine);
   } else {
-    const int p = lane & 15;
-    for (int t = cnt; t < R; ++t)
-      out[static_cast<size_t>(t >> 2) * 128 + (t & 3)] = static_cast<unsigned short>((sentBase + p) << 4);
+    for (int t = cnt; t < R; ++t) gout[static_cast<size_t>(t >> 2) * 128 + lane * 4 + (t & 3)] = static_cast<unsigned short>(sentMine);
   }
   if (viaSmem) {
-    __syncwarp();
-    const uint4 *src = reinterpret_cast<const uint4 *>(block);
-    uint4 *dst = reinterpret_cast<uint4 *>(gout);
-    for (int q = lane; q < rows * 16; q += 32) dst[q] = src[q];
+    uint2 *dst = reinterpret_cast<uint2 *>(gout) + lane;
+    for (int r = 0; r < rows; ++r) dst[r * 32] = *reinterpret_cast<const uint2 *>(mine + r * 4);
   }
 }
 
@@ -584,60 +586,6 @@ __global__ void __launch_bounds__(1024) kPrunedTileOrder(int numTiles, const int
     if (tileHalo[t] == 0) order[posI++] = t; else order[posB++] = t;
   }
   if (threadIdx.x == 0) *numInterior = total;
-}
-
-// Execution order of the warp-specialised force kernel: the non-empty interior tiles, then the non-empty boundary tiles,
-// each group in ascending tile order; empty tiles (bricks above a tower's height, halo towers) are left out.
-// order[pos] = tile, counts = {interior, interior + boundary}. One block.
-__global__ void __launch_bounds__(1024) kPrunedActiveOrder(int numTiles, const int *__restrict__ tileHalo,
-                                                          const int *__restrict__ numCompact, int *__restrict__ order,
-                                                          int *__restrict__ counts) {
-  __shared__ int sI[1024], sB[1024];
-  const int chunk = (numTiles + 1023) / 1024;
-  const int b = min(static_cast<int>(threadIdx.x) * chunk, numTiles), e = min(b + chunk, numTiles);
-  int cI = 0, cB = 0;
-  for (int t = b; t < e; ++t)
-    if (numCompact[t] > 0) (tileHalo[t] == 0 ? cI : cB) += 1;
-  sI[threadIdx.x] = cI;
-  sB[threadIdx.x] = cB;
-  __syncthreads();
-  for (int s = 1; s < 1024; s <<= 1) {
-    const int vI = threadIdx.x >= s ? sI[threadIdx.x - s] : 0, vB = threadIdx.x >= s ? sB[threadIdx.x - s] : 0;
-    __syncthreads();
-    sI[threadIdx.x] += vI;
-    sB[threadIdx.x] += vB;
-    __syncthreads();
-  }
-  const int totalI = sI[1023];
-  int posI = sI[threadIdx.x] - cI, posB = totalI + sB[threadIdx.x] - cB;
-  for (int t = b; t < e; ++t)
-    if (numCompact[t] > 0) {
-      if (tileHalo[t] == 0) order[posI++] = t; else order[posB++] = t;
-    }
-  if (threadIdx.x == 0) {
-    counts[0] = totalI;
-    counts[1] = totalI + sB[1023];
-  }
-}
-
-// Packed per-tile and per-warp tables in execution order: one 16-byte load each in the force kernel.
-__global__ void kPrunedPackMeta(int numTiles, const int *__restrict__ order, const int *__restrict__ counts,
-                                const int *__restrict__ stagedStart, const int *__restrict__ numCompact,
-                                const int *__restrict__ chunkFirst, const int *__restrict__ chunkNum,
-                                const int *__restrict__ warpRows, const int *__restrict__ warpRowStart,
-                                int4 *__restrict__ tileMeta, int4 *__restrict__ warpMeta) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pos = g / PR_WARPS, wi = g % PR_WARPS;
-  if (pos >= counts[1]) return;
-  const int tile = order[pos];
-  if (wi == 0) tileMeta[pos] = make_int4(stagedStart[tile + 1] - stagedStart[tile], stagedStart[tile], numCompact[tile], tile);
-  const int wg = tile * PR_WARPS + wi;
-  warpMeta[g] = make_int4(chunkFirst[wg], chunkNum[wg], warpRows[wg], warpRowStart[wg]);
-}
-__global__ void kPrunedPackTab(long long totalStaged, const int *__restrict__ staged, const unsigned *__restrict__ used,
-                               const int *__restrict__ cbase, int4 *__restrict__ tab) {
-  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (g < totalStaged) tab[g] = make_int4(staged[g], static_cast<int>(used[g]), cbase[g], 0);
 }
 
 int apbBuildPruned(apb_handle h, int newton3) {
@@ -780,8 +728,8 @@ int apbBuildPruned(apb_handle h, int newton3) {
   // per-warp list blocks in shared memory if the longest list fits (256 B per row)
   const int maxRows = hostMisc[3];
   const size_t smemFillBase = (static_cast<size_t>(maxStaged) * 12 + 15) & ~size_t(15);
-  const int smemRowsPerWarp = smemFillBase + static_cast<size_t>(PR_WARPS) * maxRows * 256 <= 150 * 1024 ? maxRows : 0;
-  const size_t smemFill = smemFillBase + static_cast<size_t>(PR_WARPS) * smemRowsPerWarp * 256 + 16;
+  const int smemRowsPerWarp = smemFillBase + static_cast<size_t>(PR_WARPS) * (maxRows | 1) * 256 <= 150 * 1024 ? maxRows : 0;
+  const size_t smemFill = smemFillBase + static_cast<size_t>(PR_WARPS) * (smemRowsPerWarp | 1) * 256 + 16;
   // Latin layout of the lists (kPrunedFill; lists assembled in shared memory only). Measured on B200 (C2, 1 M particles,
   // profiles/r02_latin_lists.txt): shared-memory wavefronts of kLJPruned 40.3 M -> 28.1 M, LSU data pipe 86 % -> 69 %,
   // FP64 pipe 53 % -> 60 %, kernel 0.197 -> 0.177 ms per step; but kPrunedFill pays for the placement (rebuild 1.44 ->
@@ -803,23 +751,6 @@ int apbBuildPruned(apb_handle h, int newton3) {
                                                                static_cast<int *>(h->prTileOrder.p),
                                                                static_cast<int *>(h->prTileOrder.p) + numTiles);
   APB_CUDA(cudaGetLastError());
-  // tables of the warp-specialised kernel: active tiles in execution order, packed table entries
-  APB_CHECK(apbEnsure(h, h->prActOrder, sizeof(int) * (numTiles + 2)));
-  APB_CHECK(apbEnsure(h, h->prTileMeta, sizeof(int4) * numTiles));
-  APB_CHECK(apbEnsure(h, h->prWarpMeta, sizeof(int4) * numWarps));
-  APB_CHECK(apbEnsure(h, h->prStageTab, sizeof(int4) * stagedAlloc));
-  {
-    int *actOrder = static_cast<int *>(h->prActOrder.p), *counts = actOrder + numTiles;
-    ++h->launchCount, kPrunedActiveOrder<<<1, 1024, 0, h->stream>>>(numTiles, static_cast<const int *>(h->prTileHalo.p),
-                                                                   static_cast<const int *>(h->prNumCompact.p), actOrder, counts);
-    ++h->launchCount, kPrunedPackMeta<<<apbDivUp(numWarps, 256), 256, 0, h->stream>>>(
-        numTiles, actOrder, counts, stagedStart, static_cast<const int *>(h->prNumCompact.p), a.chunkFirst, a.chunkNum,
-        warpRows, warpStart, static_cast<int4 *>(h->prTileMeta.p), static_cast<int4 *>(h->prWarpMeta.p));
-    ++h->launchCount, kPrunedPackTab<<<static_cast<unsigned>(apbDivUp(stagedAlloc, 256)), 256, 0, h->stream>>>(
-        totalStaged, staged, static_cast<const unsigned *>(h->prUsed.p), static_cast<const int *>(h->prCbase.p),
-        static_cast<int4 *>(h->prStageTab.p));
-    APB_CUDA(cudaGetLastError());
-  }
   if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   h->prunedValid = true;
   if (getenv("APB_DEBUG"))
@@ -1198,266 +1129,6 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS_CAP2048 : 
 }
 
 
-// ---- warp-specialised persistent variant --------------------------------------------------------------------------------
-// kLJPruned spends 20-45 % of its warp time in the per-tile prologue: three dependent rounds of global loads (tables ->
-// slot list -> positions) before the first pair, with nothing else for the CTA to do (ncu source view, C2 / C3). Here a
-// CTA is persistent (static round-robin over the non-empty tiles in execution order) and splits into one producer warp
-// and PR_WARPS consumer warps over a double-buffered staging area:
-//   producer: for tile k, waits until the consumers have released buffer k & 1 (mbarrier `empty`), expands the tile's
-//             stage table {cluster, referenced-particle mask, compact base} - itself prefetched one tile ahead into shared
-//             memory - into asynchronous 8-byte copies of the referenced positions, and lets the copies signal mbarrier
-//             `full` themselves (cp.async.mbarrier.arrive.noinc);
-//   consumers: keep this tile's list rows and own particle in registers, issue the loads for the NEXT tile (table entry
-//             two tiles ahead), wait on `full`, run the same pair loop as kLJPruned, add the forces and release the
-//             buffer. No CTA-wide barrier per tile; a consumer never waits for global memory unless the producer falls
-//             behind. The statistics stay in registers across all tiles of a warp and are reduced once per CTA.
-// The sentinels (padding partners) live in 16 fixed slots behind the largest staged tile (sentBase ...), written once.
-struct PrunedWSArgs {
-  PrunedForceArgs f;
-  const int4 *tileMeta;  // [active tiles, execution order] {staged clusters, first stage-table entry, staged particles, tile}
-  const int4 *warpMeta;  // [active tiles * PR_WARPS] {first slot, slot count, list rows, first list row}
-  const int4 *stageTab;  // per staged cluster {cluster, mask of referenced particles, compact index of its first one, 0}
-  const int *counts;     // [0] interior active tiles, [1] active tiles
-  int partialBase;
-  int tabCap;            // stage-table entries per shared-memory buffer
-};
-
-__device__ double prFarConst = PR_FAR;
-
-__device__ __forceinline__ unsigned prSmem(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void prMbarInit(unsigned long long *b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(prSmem(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void prMbarArrive(unsigned long long *b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(prSmem(b)) : "memory");
-}
-__device__ __forceinline__ void prMbarArriveOnCopies(unsigned long long *b) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(prSmem(b)) : "memory");
-}
-__device__ __forceinline__ void prMbarWait(unsigned long long *b, unsigned parity) {
-  unsigned ok = 0;
-  int spins = 0;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(prSmem(b)), "r"(parity)
-        : "memory");
-    if (!ok && ++spins > (1 << 24)) __trap();  // a lost arrival must not hang the device
-  } while (!ok);
-}
-__device__ __forceinline__ void prCpAsync16(void *smemDst, const void *gmemSrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(prSmem(smemDst)), "l"(gmemSrc) : "memory");
-}
-__device__ __forceinline__ void prCpAsync4(void *smemDst, const void *gmemSrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(prSmem(smemDst)), "l"(gmemSrc) : "memory");
-}
-
-#define PR_WS_THREADS (PR_TILE + 32)
-
-template <bool MIX, bool STATS, bool DEAD, bool VIR3, int CAP>
-__global__ void __launch_bounds__(PR_WS_THREADS, CAP <= 1280 ? 3 : 2) kLJPrunedWS(PrunedWSArgs w) {
-  extern __shared__ __align__(16) unsigned char smemRaw[];
-  constexpr int BUF = CAP * PR_BYTES_XYZ + (MIX ? CAP * 4 : 0);
-  int4 *tab = reinterpret_cast<int4 *>(smemRaw + 2 * BUF);
-  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tab + 2 * w.tabCap);  // full[2], empty[2]
-  const PrunedForceArgs &a = w.f;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int begin = 0, end;
-  {
-    const int nI = __ldg(w.counts), nA = __ldg(w.counts + 1);
-    end = a.part == 1 ? nI : nA;
-    if (a.part == 2) begin = nI;
-  }
-  const int grid = gridDim.x;
-  int pos = begin + blockIdx.x;
-  if (threadIdx.x == 0) {
-    prMbarInit(mbar + 0, 32);
-    prMbarInit(mbar + 1, 32);
-    prMbarInit(mbar + 2, PR_WARPS);
-    prMbarInit(mbar + 3, PR_WARPS);
-  }
-  if (threadIdx.x < 32) {  // sentinel slots of both buffers, one per bank class
-    unsigned char *bufS = smemRaw + (threadIdx.x >> 4) * BUF;
-    const int e = a.sentBase + (threadIdx.x & 15);
-    reinterpret_cast<double *>(bufS)[2 * e] = PR_FAR;
-    reinterpret_cast<double *>(bufS)[2 * e + 1] = 0.;
-    reinterpret_cast<double *>(bufS + CAP * 16)[prZIndex(e)] = 0.;
-    if (MIX) reinterpret_cast<int *>(bufS + static_cast<size_t>(CAP) * PR_BYTES_XYZ)[e] = 0;
-  }
-  __syncthreads();
-  PairAcc<MIX, STATS, VIR3> acc;
-  if (warp == PR_WARPS) {
-    // ---- producer ----
-    if (pos < end) {
-      int4 metaCur = __ldg(w.tileMeta + pos);
-      int4 metaNxt = pos + grid < end ? __ldg(w.tileMeta + pos + grid) : make_int4(0, 0, 0, 0);
-      for (int t = lane; t < metaCur.x; t += 32) prCpAsync16(tab + t, w.stageTab + metaCur.y + t);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      for (int k = 0; pos < end; ++k, pos += grid) {
-        const int b = k & 1;
-        if (k == 0)
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-        else
-          asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's table has landed; the previous tile's positions may still fly
-        __syncwarp();
-        if (k >= 2) prMbarWait(mbar + 2 + b, ((k >> 1) - 1) & 1);
-        const int4 *tb = tab + b * w.tabCap;
-        {  // next tile's table
-          int4 *tn = tab + (b ^ 1) * w.tabCap;
-          for (int t = lane; t < metaNxt.x; t += 32) prCpAsync16(tn + t, w.stageTab + metaNxt.y + t);
-          asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        unsigned char *buf = smemRaw + b * BUF;
-        double *sxy = reinterpret_cast<double *>(buf), *sz = reinterpret_cast<double *>(buf + CAP * 16);
-        int *stype = reinterpret_cast<int *>(buf + static_cast<size_t>(CAP) * PR_BYTES_XYZ);
-        const int nSlots = metaCur.x << a.logM, mMask = a.M - 1;
-#pragma unroll 4
-        for (int idx = lane; idx < nSlots; idx += 32) {
-          const int kk = idx & mMask;
-          const int4 t = tb[idx >> a.logM];
-          if ((static_cast<unsigned>(t.y) >> kk) & 1u) {
-            const int e = t.z + __popc(static_cast<unsigned>(t.y) & ((1u << kk) - 1u));
-            const int64_t slot = (static_cast<int64_t>(t.x) << a.logM) + kk;
-            const double *srcX = a.x + slot;
-            if (DEAD && a.own[slot] == APB_OWN_DUMMY) srcX = &prFarConst;  // deleted since the list build: out of reach
-            prCpAsync8(sxy + 2 * e, srcX);
-            prCpAsync8(sxy + 2 * e + 1, a.y + slot);
-            prCpAsync8(sz + prZIndex(e), a.z + slot);
-            if (MIX) prCpAsync4(stype + e, a.type + slot);
-          }
-        }
-        prMbarArriveOnCopies(mbar + b);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        metaCur = metaNxt;
-        metaNxt = pos + 2 * grid < end ? __ldg(w.tileMeta + pos + 2 * grid) : make_int4(0, 0, 0, 0);
-      }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-    }
-  } else if (pos < end) {
-    // ---- consumers ----
-    // warp table entry -> list rows (four in a register ring), own particle
-#define PR_WS_LOAD(META, ROWS, LIST, Q0, Q1, Q2, Q3, I, ACTIVE, XI, YI, ZI, TI)                                          \
-  do {                                                                                                                   \
-    ROWS = (META).x >= 0 ? (META).z : 0;                                                                                 \
-    LIST = reinterpret_cast<const uint2 *>(a.lists) + (ROWS > 0 ? static_cast<size_t>((META).w) * 32 + lane : lane);     \
-    Q0 = __ldg(LIST), Q1 = __ldg(LIST + 32), Q2 = __ldg(LIST + 64), Q3 = __ldg(LIST + 96);                               \
-    I = static_cast<int64_t>((META).x >= 0 ? (META).x : 0) + lane;                                                       \
-    ACTIVE = ROWS > 0 && lane < (META).y && a.own[I] == APB_OWN_OWNED;                                                   \
-    XI = ACTIVE ? a.x[I] : 0.5 * PR_FAR, YI = ACTIVE ? a.y[I] : 0., ZI = ACTIVE ? a.z[I] : 0.;                           \
-    TI = (MIX && ACTIVE) ? a.type[I] : 0;                                                                                \
-  } while (0)
-    int4 mNxt = pos + grid < end ? __ldg(w.warpMeta + static_cast<size_t>(pos + grid) * PR_WARPS + warp) : make_int4(-1, 0, 0, 0);
-    int rows, ti;
-    const uint2 *list;
-    uint2 q0, q1, q2, q3;
-    int64_t i;
-    bool active;
-    double xi, yi, zi;
-    {
-      const int4 mCur = __ldg(w.warpMeta + static_cast<size_t>(pos) * PR_WARPS + warp);
-      PR_WS_LOAD(mCur, rows, list, q0, q1, q2, q3, i, active, xi, yi, zi, ti);
-    }
-    const unsigned sentinel16 = static_cast<unsigned>(a.sentBase) << 4;
-    for (int k = 0; pos < end; ++k, pos += grid) {
-      const int b = k & 1;
-      // next tile: its list rows and own particle travel while this tile is evaluated
-      int rowsN, tiN;
-      const uint2 *listN;
-      uint2 n0, n1, n2, n3;
-      int64_t iN;
-      bool activeN;
-      double xN, yN, zN;
-      PR_WS_LOAD(mNxt, rowsN, listN, n0, n1, n2, n3, iN, activeN, xN, yN, zN, tiN);
-      mNxt = pos + 2 * grid < end ? __ldg(w.warpMeta + static_cast<size_t>(pos + 2 * grid) * PR_WARPS + warp) : make_int4(-1, 0, 0, 0);
-      const unsigned char *sxyz = smemRaw + b * BUF;
-      const int *stype = reinterpret_cast<const int *>(sxyz + static_cast<size_t>(CAP) * PR_BYTES_XYZ);
-      prMbarWait(mbar + b, (k >> 1) & 1);
-      int r = 0;
-      list += 128;
-      for (; r + 4 <= rows; r += 4, list += 128) {
-        PR_ROW(q0);
-        q0 = __ldg(list);
-        PR_ROW(q1);
-        q1 = __ldg(list + 32);
-        PR_ROW(q2);
-        q2 = __ldg(list + 64);
-        PR_ROW(q3);
-        q3 = __ldg(list + 96);
-      }
-      if (r < rows) {
-        PR_ROW(q0);
-        if (r + 1 < rows) {
-          PR_ROW(q1);
-          if (r + 2 < rows) PR_ROW(q2);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) prMbarArrive(mbar + 2 + b);  // this warp is done with the buffer
-      if (active) {
-        atomicAdd(a.fx + i, acc.fx);
-        atomicAdd(a.fy + i, acc.fy);
-        atomicAdd(a.fz + i, acc.fz);
-      }
-      acc.fx = acc.fy = acc.fz = 0.;
-      rows = rowsN, list = listN, q0 = n0, q1 = n1, q2 = n2, q3 = n3, i = iN, active = activeN, xi = xN, yi = yN, zi = zN, ti = tiN;
-    }
-#undef PR_WS_LOAD
-  }
-  if (STATS) {
-    constexpr int NV = VIR3 ? 5 : 2;
-    __shared__ double sRedD[PR_WARPS][NV];
-    __shared__ unsigned long long sRedU[PR_WARPS][2];
-    if (warp < PR_WARPS) {
-      double v[NV];
-      v[0] = MIX ? acc.upot : acc.sb2;
-      v[1] = MIX ? acc.vt : acc.sb;
-      if (VIR3) v[2] = acc.vx, v[3] = acc.vy, v[4] = acc.vz;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int q = 0; q < NV; ++q) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
-      }
-      unsigned long long hitsW = acc.hits, distW = DEAD ? acc.dist : 0U;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        hitsW += __shfl_xor_sync(0xffffffffu, hitsW, o);
-        if (DEAD) distW += __shfl_xor_sync(0xffffffffu, distW, o);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < NV; ++q) sRedD[warp][q] = v[q];
-        sRedU[warp][0] = hitsW;
-        sRedU[warp][1] = distW;
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t[NV];
-      unsigned long long hits = 0ULL, dist = 0ULL;
-#pragma unroll
-      for (int q = 0; q < NV; ++q) t[q] = 0.;
-#pragma unroll
-      for (int q2 = 0; q2 < PR_WARPS; ++q2) {
-#pragma unroll
-        for (int q = 0; q < NV; ++q) t[q] += sRedD[q2][q];
-        hits += sRedU[q2][0];
-        dist += sRedU[q2][1];
-      }
-      LJStats st;
-      ljStatsZero(st);
-      st.upot = MIX ? t[0] : fma(0.5 * a.p.k1, t[0], fma(a.p.k2, t[1], static_cast<double>(hits) * a.p.shift6));
-      st.vir[0] = VIR3 ? t[2] : (MIX ? t[1] : fma(a.p.k1, t[0], a.p.k2 * t[1]));
-      st.vir[1] = VIR3 ? t[3] : 0.;
-      st.vir[2] = VIR3 ? t[4] : 0.;
-      st.dist = DEAD ? dist : ((begin + static_cast<int>(blockIdx.x) == 0 && begin < end) ? a.totalEntries : 0ULL);
-      st.kNoN3 = hits;
-      st.gNoN3 = hits;
-      a.partials[w.partialBase + blockIdx.x] = st;
-    }
-  }
-}
-
 #undef PR_ROW
 
 // ---- newton3 variant ------------------------------------------------------------------------------------------------
@@ -1637,64 +1308,6 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   const int numBlocks = numTiles;
   APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * numBlocks));
   a.partials = static_cast<LJStats *>(h->partials.p);
-  // Warp-specialised persistent kernel (default; APB_PRUNED_WS=0 keeps the one-tile-per-CTA kernel): newton3 off, staged
-  // tiles of at most 2032 particles.
-  static const bool wsEnv = getenv("APB_PRUNED_WS") == nullptr || atoi(getenv("APB_PRUNED_WS")) != 0;
-  if (!n3 && wsEnv && h->prunedCap <= 2048 && PR_WARPS == 8) {
-    PrunedWSArgs w;
-    w.tileMeta = static_cast<const int4 *>(h->prTileMeta.p);
-    w.warpMeta = static_cast<const int4 *>(h->prWarpMeta.p);
-    w.stageTab = static_cast<const int4 *>(h->prStageTab.p);
-    w.counts = static_cast<const int *>(h->prActOrder.p) + numTiles;
-    w.tabCap = (h->prunedMaxStaged + 3) & ~3;
-    // layout for 1280 staged particles: 3 CTAs per SM at 72 registers; for 2048: 2 CTAs at 96 (APB_PRUNED_WS_CAP overrides)
-    static const int capEnv = getenv("APB_PRUNED_WS_CAP") ? atoi(getenv("APB_PRUNED_WS_CAP")) : 0;
-    const int wcap = (capEnv == 2048 || h->prunedCap > 1280) ? 2048 : 1280;
-    const int ctasPerSM = wcap <= 1280 ? 3 : 2;
-    const int grid = std::max(1, std::min(numTiles, ctasPerSM * h->numSMs));
-    w.partialBase = part == 2 ? grid : 0;
-    APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * 2 * grid));
-    a.partials = static_cast<LJStats *>(h->partials.p);
-    w.f = a;
-    const size_t smemWS = 2 * static_cast<size_t>(wcap) * (mix ? PR_BYTES_XYZ + 4 : PR_BYTES_XYZ) + 2 * static_cast<size_t>(w.tabCap) * 16 + 64;
-#define PR_LAUNCH_WS_CAP(MIXV, STATSV, DEADV, VIRV, CAPV)                                                              \
-  do {                                                                                                                 \
-    ++h->launchCount, kLJPrunedWS<MIXV, STATSV, DEADV, VIRV, CAPV><<<grid, PR_WS_THREADS, smemWS, h->stream>>>(w);     \
-  } while (0)
-#define PR_LAUNCH_WS(MIXV, STATSV, DEADV, VIRV)                                                                        \
-  do {                                                                                                                 \
-    if (wcap == 1280)                                                                                                  \
-      PR_LAUNCH_WS_CAP(MIXV, STATSV, DEADV, VIRV, 1280);                                                               \
-    else                                                                                                               \
-      PR_LAUNCH_WS_CAP(MIXV, STATSV, DEADV, VIRV, 2048);                                                               \
-  } while (0)
-    switch (sel) {
-      case 0: PR_LAUNCH_WS(false, false, false, false); break;
-      case 2: PR_LAUNCH_WS(false, false, true, false); break;
-      case 4: PR_LAUNCH_WS(false, true, false, false); break;
-      case 5: PR_LAUNCH_WS(false, true, false, true); break;
-      case 6: PR_LAUNCH_WS(false, true, true, false); break;
-      case 7: PR_LAUNCH_WS(false, true, true, true); break;
-      case 8: PR_LAUNCH_WS(true, false, false, false); break;
-      case 10: PR_LAUNCH_WS(true, false, true, false); break;
-      case 12: PR_LAUNCH_WS(true, true, false, false); break;
-      case 13: PR_LAUNCH_WS(true, true, false, true); break;
-      case 14: PR_LAUNCH_WS(true, true, true, false); break;
-      default: PR_LAUNCH_WS(true, true, true, true); break;
-    }
-#undef PR_LAUNCH_WS
-#undef PR_LAUNCH_WS_CAP
-    {
-      const cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) {
-        h->poisoned = true;
-        return h->fail(APB_ERR_CUDA, std::string("kLJPrunedWS launch failed: ") + cudaGetErrorString(e) + " (grid " +
-                                         std::to_string(grid) + ", dynamic smem " + std::to_string(smemWS) + " B)");
-      }
-    }
-    if (part == 1) return APB_OK;  // the boundary half follows and finishes the statistics
-    return apbFinishStats(h, part == 2 ? 2 * grid : grid, stats, f, out);
-  }
   if (n3) {
     const size_t smemN3 = static_cast<size_t>(cap) * (PR_BYTES_XYZ + (mix ? 8 : 4));
 #define PR_LAUNCH_N3(MIXV, STATSV)                                                                                      \
@@ -1778,25 +1391,6 @@ int apbInitPrunedAttributes(apb_handle h) {
   PR_ATTR(true, true, true, false);
   PR_ATTR(true, true, true, true);
 #undef PR_ATTR
-#define PR_ATTR_WS(MIXV, STATSV, DEADV, VIRV)                                                                           \
-  APB_CUDA(cudaFuncSetAttribute(kLJPrunedWS<MIXV, STATSV, DEADV, VIRV, 1280>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                2 * 1280 * (PR_BYTES_XYZ + 4) + 16 * 1024));                                             \
-  APB_CUDA(cudaFuncSetAttribute(kLJPrunedWS<MIXV, STATSV, DEADV, VIRV, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                2 * 2048 * (PR_BYTES_XYZ + 4) + 16 * 1024))
-  PR_ATTR_WS(false, false, false, false);
-  PR_ATTR_WS(false, false, true, false);
-  PR_ATTR_WS(false, true, false, false);
-  PR_ATTR_WS(false, true, false, true);
-  PR_ATTR_WS(false, true, true, false);
-  PR_ATTR_WS(false, true, true, true);
-  PR_ATTR_WS(true, false, false, false);
-  PR_ATTR_WS(true, false, true, false);
-  PR_ATTR_WS(true, true, false, false);
-  PR_ATTR_WS(true, true, false, true);
-  PR_ATTR_WS(true, true, true, false);
-  PR_ATTR_WS(true, true, true, true);
-#undef PR_ATTR_WS
-  APB_CUDA(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, h->cfg.device));
 #define PR_ATTR_N3(MIXV, STATSV)                                                                                       \
   APB_CUDA(cudaFuncSetAttribute(kLJPrunedN3<MIXV, STATSV, 2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                 2048 * (PR_BYTES_XYZ + 8)));                                                           \

@@ -44,10 +44,118 @@
 
 namespace autopas_b200 {
 
+/// Which device particle kind (apb_particle_kind) and which SoA columns a particle class maps to: mdLib::MoleculeLJ
+/// (MoleculeLJ.h:39-70), mdLib::MultisiteMoleculeLJ (quaternion, torque) and sphLib::SPHParticle (SPHParticle.h: mass,
+/// smoothing length, density, pressure, sound speed, engDot, vSigMax; the force columns carry the acceleration).
+/// Attributes without a device column (angular velocity; SPH energy and dt) stay on the host, keyed by particle id.
+template <class P>
+struct ParticleColumns {
+  static constexpr bool sph = requires(const P &p) { p.getSmoothingLength(); };
+  static constexpr bool multisite = requires(const P &p) { p.getQuaternion(); };
+  static constexpr bool hasOldF = requires(const P &p) { p.getOldF(); };
+  static constexpr int kind = sph ? APB_PARTICLE_SPH : (multisite ? APB_PARTICLE_MULTISITE : APB_PARTICLE_LJ);
+  static constexpr int numHostOnly = sph ? 2 : (multisite ? 3 : 0);
+  static constexpr int maxColumns = 24;
+
+  /// device columns of this particle class; the first three are the position
+  static const std::vector<int> &ids() {
+    static const std::vector<int> v = [] {
+      std::vector<int> c{APB_COL_X, APB_COL_Y, APB_COL_Z, APB_COL_VX, APB_COL_VY, APB_COL_VZ, APB_COL_FX, APB_COL_FY, APB_COL_FZ};
+      if constexpr (hasOldF and not sph) c.insert(c.end(), {APB_COL_OLDFX, APB_COL_OLDFY, APB_COL_OLDFZ});
+      if constexpr (multisite) c.insert(c.end(), {APB_COL_Q0, APB_COL_Q1, APB_COL_Q2, APB_COL_Q3, APB_COL_TX, APB_COL_TY, APB_COL_TZ});
+      if constexpr (sph)
+        c.insert(c.end(), {APB_COL_MASS, APB_COL_SMTH, APB_COL_DENSITY, APB_COL_PRESSURE, APB_COL_SNDSPEED, APB_COL_ENGDOT, APB_COL_VSIGMAX});
+      return c;
+    }();
+    return v;
+  }
+  /// out[k] = value of column ids()[k]
+  static void gather(const P &p, double *out) {
+    int k = 0;
+    for (int d = 0; d < 3; ++d) out[k++] = p.getR()[d];
+    for (int d = 0; d < 3; ++d) out[k++] = p.getV()[d];
+    if constexpr (sph) {
+      for (int d = 0; d < 3; ++d) out[k++] = p.getAcceleration()[d];
+    } else {
+      for (int d = 0; d < 3; ++d) out[k++] = p.getF()[d];
+    }
+    if constexpr (hasOldF and not sph)
+      for (int d = 0; d < 3; ++d) out[k++] = p.getOldF()[d];
+    if constexpr (multisite) {
+      for (int d = 0; d < 4; ++d) out[k++] = p.getQuaternion()[d];
+      for (int d = 0; d < 3; ++d) out[k++] = p.getTorque()[d];
+    }
+    if constexpr (sph) {
+      out[k++] = p.getMass();
+      out[k++] = p.getSmoothingLength();
+      out[k++] = p.getDensity();
+      out[k++] = p.getPressure();
+      out[k++] = p.getSoundSpeed();
+      out[k++] = p.getEngDot();
+      out[k++] = p.getVSigMax();
+    }
+  }
+  static void scatter(P &p, const double *in) {
+    int k = 0;
+    p.setR({in[0], in[1], in[2]});
+    p.setV({in[3], in[4], in[5]});
+    if constexpr (sph) p.setAcceleration({in[6], in[7], in[8]});
+    else p.setF({in[6], in[7], in[8]});
+    k = 9;
+    if constexpr (hasOldF and not sph) {
+      p.setOldF({in[k], in[k + 1], in[k + 2]});
+      k += 3;
+    }
+    if constexpr (multisite) {
+      p.setQuaternion({in[k], in[k + 1], in[k + 2], in[k + 3]});
+      p.setTorque({in[k + 4], in[k + 5], in[k + 6]});
+      k += 7;
+    }
+    if constexpr (sph) {
+      p.setMass(in[k]);
+      p.setSmoothingLength(in[k + 1]);
+      p.setDensity(in[k + 2]);
+      p.setPressure(in[k + 3]);
+      p.setSoundSpeed(in[k + 4]);
+      p.setEngDot(in[k + 5]);
+      p.setVSigMax(in[k + 6]);
+    }
+  }
+  static std::array<double, 3> hostOnly(const P &p) {
+    if constexpr (sph) return {p.getEnergy(), p.getDt(), 0.};
+    else if constexpr (multisite) return p.getAngularVel();
+    else return {0., 0., 0.};
+  }
+  static void setHostOnly(P &p, const std::array<double, 3> &v) {
+    if constexpr (sph) {
+      p.setEnergy(v[0]);
+      p.setDt(v[1]);
+    } else if constexpr (multisite) {
+      p.setAngularVel(v);
+    }
+  }
+};
+
 /// Kernel descriptor handed from a GPU-capable functor to the container.
 struct FunctorDescriptor {
   apb_functor functor{};
   std::vector<double> mixingTable;  // keeps functor.mixing_table alive
+  std::vector<int32_t> siteStart, siteTypes;  // multi-site: keep functor.site_start / site_types alive
+  std::vector<double> sitePositions;          // and functor.site_positions
+  FunctorDescriptor() = default;
+  FunctorDescriptor(FunctorDescriptor &&o) noexcept { *this = std::move(o); }
+  FunctorDescriptor &operator=(FunctorDescriptor &&o) noexcept {
+    functor = o.functor;
+    mixingTable = std::move(o.mixingTable);
+    siteStart = std::move(o.siteStart);
+    siteTypes = std::move(o.siteTypes);
+    sitePositions = std::move(o.sitePositions);
+    if (functor.mixing_table) functor.mixing_table = mixingTable.data();
+    if (functor.site_start) functor.site_start = siteStart.data();
+    if (functor.site_types) functor.site_types = siteTypes.data();
+    if (functor.site_positions) functor.site_positions = sitePositions.data();
+    return *this;
+  }
 };
 
 /// Interface the container sees; implemented by GpuTraversal<Functor_T>.
