@@ -141,6 +141,7 @@ SIGNATURES = {
     "apb_reset_forces": (_i32, [_H, _f64, _f64, _f64]),
     "apb_update_container": (_i32, [_H, _i32, ctypes.POINTER(_i64)]),
     "apb_get_leavers": (_i32, [_H, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "apb_get_leaver_column": (_i32, [_H, _i32, _vp]),
     "apb_rebuild_neighbor_lists": (_i32, [_H, _i32, _i32]),
     "apb_get_geometry": (_i32, [_H, ctypes.POINTER(Geometry)]),
     "apb_compute_interactions": (_i32, [_H, _i32, ctypes.POINTER(Functor), _i32, ctypes.POINTER(TraversalResult)]),
@@ -164,6 +165,7 @@ SIGNATURES = {
     "apb_comm_init": (_i32, [_H, _i32, _i32, _vp]),
     "apb_set_decomposition": (_i32, [_H, _vp, _vp, _vp, _vp]),
     "apb_migrate": (_i32, [_H, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "apb_refresh_halo_columns": (_i32, [_H, _i32, _vp]),
     "apb_exchange_halos": (_i32, [_H]),
     "apb_allreduce_globals": (_i32, [_H, ctypes.POINTER(TraversalResult)]),
     "apb_run_steps": (_i32, [_H, ctypes.POINTER(Functor), _vp, _i32, _i64, _vp]),

@@ -584,8 +584,16 @@ class GpuParticleContainer:
         types = np.zeros(n, dtype=np.int32)
         if n:
             self._check(self._lib.apb_get_leavers(self._h, *[_ptr(c) for c in cols], _ptr(ids), _ptr(types)))
+        self._numLeavers = n
         return {"x": cols[0], "y": cols[1], "z": cols[2], "vx": cols[3], "vy": cols[4], "vz": cols[5], "id": ids,
                 "type": types}
+
+    def leaverColumn(self, name):
+        """Any other attribute of the particles the last updateContainer returned (they are whole copies in the
+        reference, LeavingParticleCollector.h:101-110), in the same order."""
+        out = np.zeros(getattr(self, "_numLeavers", 0))
+        self._check(self._lib.apb_get_leaver_column(self._h, capi.COL[name], _ptr(out)))
+        return out
 
     def rebuildNeighborLists(self, traversal):
         self._check(self._lib.apb_rebuild_neighbor_lists(self._h, capi.TRAVERSAL_NAMES[traversal.option],
@@ -687,6 +695,12 @@ class GpuParticleContainer:
 
     def exchangeHalos(self):
         self._check(self._lib.apb_exchange_halos(self._h))
+
+    def refreshHaloColumns(self, names):
+        """sph-mpi's updateHaloParticles between the density and the hydro-force pass: the halo copies recorded by the
+        last generating exchangeHalos() receive the owners' current values of the named columns."""
+        cols = np.ascontiguousarray([capi.COL[n] for n in names], dtype=np.int32)
+        self._check(self._lib.apb_refresh_halo_columns(self._h, len(cols), _ptr(cols)))
 
     def allreduceGlobals(self, raw):
         self._check(self._lib.apb_allreduce_globals(self._h, ctypes.byref(raw)))

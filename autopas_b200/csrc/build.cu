@@ -7,6 +7,8 @@
 // All kernels here are HBM-bound integer / compare work; decisions that must be bit-exact use explicit
 // round-to-nearest intrinsics so that no FMA contraction can change a `<=` outcome.
 #include <algorithm>
+#include <array>
+#include <vector>
 #include <cmath>
 
 #include "internal.cuh"
@@ -66,8 +68,21 @@ int apbComputeStencil(apb_handle h) {
                                                        std::to_string(APB_MAX_STENCIL) + " cells");
         }
       }
-  APB_CHECK(apbEnsure(h, h->stencilDev, sizeof(int) * 3 * APB_MAX_STENCIL));
+  // behind the list (self first): the same cells in (z, y, x) order, for the warp-cooperative walk (lc_warp.cuh), which
+  // merges cells adjacent in x into one slot range
+  std::vector<std::array<int, 3>> sorted(h->stencilN);
+  for (int s = 0; s < h->stencilN; ++s) sorted[s] = {h->stencil[s][2], h->stencil[s][1], h->stencil[s][0]};
+  std::sort(sorted.begin(), sorted.end());
+  std::vector<int> flat(3 * APB_MAX_STENCIL, 0);
+  for (int s = 0; s < h->stencilN; ++s) {
+    flat[3 * s] = sorted[s][2];
+    flat[3 * s + 1] = sorted[s][1];
+    flat[3 * s + 2] = sorted[s][0];
+  }
+  APB_CHECK(apbEnsure(h, h->stencilDev, sizeof(int) * 6 * APB_MAX_STENCIL));
   APB_CUDA(cudaMemcpy(h->stencilDev.p, h->stencil, sizeof(int) * 3 * h->stencilN, cudaMemcpyHostToDevice));
+  APB_CUDA(cudaMemcpy(static_cast<int *>(h->stencilDev.p) + 3 * APB_MAX_STENCIL, flat.data(), sizeof(int) * 3 * APB_MAX_STENCIL,
+                      cudaMemcpyHostToDevice));
   return APB_OK;
 }
 
@@ -430,6 +445,7 @@ int apbRebuildLinkedCells(apb_handle h) {
   if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   h->numCells = nc;
   h->structureValid = true;
+  ++h->structureVersion;
   h->countsValid = false;
   return APB_OK;
 }
@@ -762,6 +778,7 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   h->numPairs = numPairs;
   h->numCells = nt;
   h->structureValid = true;
+  ++h->structureVersion;
   h->builtNewton3 = newton3 ? 1 : 0;
   h->ownDirty = false;
   h->prunedValid = false;

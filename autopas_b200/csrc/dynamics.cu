@@ -816,7 +816,7 @@ static bool nearRel(double a, double b) {
 
 // One dimension of a generating exchange (halo generation or migration).
 // mode 0: halo generation (packed columns: x, y, z); mode 1: migration (all active columns).
-static int exchangeDim(apb_handle h, int d, int mode) {
+static int exchangeDim(apb_handle h, int d, int mode, int64_t *outSent = nullptr) {
   if (mode == 1) h->ownedKnown = false;  // migration between ranks changes the number of owned particles
   if (h->nranks > 1) APB_CHECK(ensureP2P(h));  // every rank passes here in the same order: the handle trade matches up
   const int64_t n = h->nslots;
@@ -882,6 +882,7 @@ static int exchangeDim(apb_handle h, int d, int mode) {
     APB_CUDA(cudaStreamSynchronize(h->stream));
     APB_CHECK(exchangeCounts(h, d, sendCount, recvCount));
   }
+  if (outSent) *outSent += sendCount[0] + sendCount[1];
   // packed columns
   int ncols = 0;
   int colIds[APB_NUM_COLUMNS];
@@ -1195,13 +1196,112 @@ __global__ void kWrapSelf(int64_t n, const int32_t *__restrict__ own, double *x,
   }
 }
 
+// ---- refresh of arbitrary columns of the halo copies ----------------------------------------------------------------
+// sph-mpi refreshes its halo particles between the density and the hydro-force pass (examples/sph-mpi/sph-main-mpi.cpp:
+// 373-414: updateHaloParticles -> density -> setPressure -> updateHaloParticles -> hydro force): the copies need the
+// owners' density and pressure. Here the halo copies recorded by the last generating apb_exchange_halos receive the
+// current values of the given columns from their source particles, dimension by dimension in the order of the
+// generating exchange (a copy of a copy - edge and corner halos - is fed by the already refreshed copy).
+struct ColumnSet {
+  int n;
+  double *p[APB_NUM_COLUMNS];
+};
+// one launch for both directions of a dimension (or for all images of a rank that is its own neighbour everywhere)
+__global__ void kCopyColumns(int64_t mA, int64_t mB, const int *__restrict__ srcA, const int *__restrict__ dstA,
+                             const int *__restrict__ srcB, const int *__restrict__ dstB, ColumnSet cs) {
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= mA + mB) return;
+  const bool second = q >= mA;
+  if (second) q -= mA;
+  const int s = second ? srcB[q] : srcA[q], t = second ? dstB[q] : dstA[q];
+  if (s < 0 || t < 0) return;  // dropped by the rebuild
+  for (int c = 0; c < cs.n; ++c) cs.p[c][t] = cs.p[c][s];
+}
+__global__ void kGatherColumns2(int64_t m0, int64_t m1, const int *__restrict__ idx0, const int *__restrict__ idx1,
+                                ColumnSet cs, double *out0, double *out1) {
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= m0 + m1) return;
+  const bool second = q >= m0;
+  if (second) q -= m0;
+  const int64_t m = second ? m1 : m0;
+  const int s = second ? idx1[q] : idx0[q];
+  double *out = second ? out1 : out0;
+  out[q] = s >= 0 ? 1. : 0.;  // validity of the source slot, then the columns
+  for (int c = 0; c < cs.n; ++c) out[(c + 1) * m + q] = s >= 0 ? cs.p[c][s] : 0.;
+}
+__global__ void kScatterColumns2(int64_t m0, int64_t m1, const int *__restrict__ slot0, const int *__restrict__ slot1,
+                                 const double *in0, const double *in1, ColumnSet cs) {
+  int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= m0 + m1) return;
+  const bool second = q >= m0;
+  if (second) q -= m0;
+  const int64_t m = second ? m1 : m0;
+  const int t = second ? slot1[q] : slot0[q];
+  const double *in = second ? in1 : in0;
+  if (t < 0 || in[q] == 0.) return;
+  for (int c = 0; c < cs.n; ++c) cs.p[c][t] = in[(c + 1) * m + q];
+}
+
+static int refreshHaloColumns(apb_handle h, const ColumnSet &cs) {
+  if (cs.n == 0) return APB_OK;
+  if (h->haloAllMode) {
+    if (h->haloAllN > 0) {
+      ++h->launchCount, kCopyColumns<<<apbDivUp(h->haloAllN, 256), 256, 0, h->stream>>>(
+          h->haloAllN, 0, static_cast<const int *>(h->haloAllSrc.p), static_cast<const int *>(h->haloAllDst.p), nullptr,
+          nullptr, cs);
+      APB_CUDA(cudaGetLastError());
+    }
+    return APB_OK;
+  }
+  for (int d = 0; d < 3; ++d) {
+    HaloLink &L0 = h->link[d][0], &L1 = h->link[d][1];
+    const int left = h->neighbor[d][0], right = h->neighbor[d][1];
+    if (h->nranks == 1 || (left == h->myRank && right == h->myRank)) {
+      if (L1.nSend != L0.nRecv || L0.nSend != L1.nRecv)
+        return h->fail(APB_ERR_STATE, "apb_refresh_halo_columns: inconsistent self-exchange links");
+      const int64_t m = L1.nSend + L0.nSend;
+      if (m > 0) {
+        ++h->launchCount, kCopyColumns<<<apbDivUp(m, 256), 256, 0, h->stream>>>(
+            L1.nSend, L0.nSend, static_cast<const int *>(L1.sendIdx.p), static_cast<const int *>(L0.recvSlot.p),
+            static_cast<const int *>(L0.sendIdx.p), static_cast<const int *>(L1.recvSlot.p), cs);
+        APB_CUDA(cudaGetLastError());
+      }
+      continue;
+    }
+    void *sendBuf[2], *recvBuf[2];
+    size_t sb[2], rb[2];
+    for (int s = 0; s < 2; ++s) {
+      sb[s] = sizeof(double) * (cs.n + 1) * h->link[d][s].nSend;
+      rb[s] = sizeof(double) * (cs.n + 1) * h->link[d][s].nRecv;
+      APB_CHECK(apbEnsure(h, h->xbuf[s], sb[s] + 256));
+      APB_CHECK(apbEnsure(h, h->xbuf[2 + s], rb[s] + 256));
+      sendBuf[s] = h->xbuf[s].p;
+      recvBuf[s] = h->xbuf[2 + s].p;
+    }
+    if (L0.nSend + L1.nSend > 0) {
+      ++h->launchCount, kGatherColumns2<<<apbDivUp(L0.nSend + L1.nSend, 256), 256, 0, h->stream>>>(
+          L0.nSend, L1.nSend, static_cast<const int *>(L0.sendIdx.p), static_cast<const int *>(L1.sendIdx.p), cs,
+          static_cast<double *>(sendBuf[0]), static_cast<double *>(sendBuf[1]));
+      APB_CUDA(cudaGetLastError());
+    }
+    APB_CHECK(exchangePayload(h, d, sendBuf, sb, recvBuf, rb));
+    if (L0.nRecv + L1.nRecv > 0) {
+      ++h->launchCount, kScatterColumns2<<<apbDivUp(L0.nRecv + L1.nRecv, 256), 256, 0, h->stream>>>(
+          L0.nRecv, L1.nRecv, static_cast<const int *>(L0.recvSlot.p), static_cast<const int *>(L1.recvSlot.p),
+          static_cast<const double *>(recvBuf[0]), static_cast<const double *>(recvBuf[1]), cs);
+      APB_CUDA(cudaGetLastError());
+    }
+  }
+  return APB_OK;
+}
+
 extern "C" int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num_received) {
   APB_ENTRY(h);
   APB_CHECK(ensureDecomposition(h));
   APB_CHECK(apb_delete_halo_particles(h));
   h->haloLinksValid = false;
   const int64_t before = h->nslots;
-  int64_t received = 0;
+  int64_t received = 0, sent = 0;
   int selfMask = 0;
   for (int d = 0; d < 3; ++d) {
     const bool self = h->periodic[d] && h->neighbor[d][0] == h->myRank && h->neighbor[d][1] == h->myRank &&
@@ -1211,7 +1311,7 @@ extern "C" int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num
       continue;
     }
     const int64_t n0 = h->nslots;
-    APB_CHECK(exchangeDim(h, d, 1));
+    APB_CHECK(exchangeDim(h, d, 1, &sent));
     received += h->nslots - n0;
   }
   // self dimensions last: arrivals of the exchanged dimensions are wrapped as well (the dimensions are independent)
@@ -1226,7 +1326,7 @@ extern "C" int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num
   // Sent particles and the old halos are dummies now. They are not compacted here: the rebuild that must follow drops
   // dummies while it sorts (VerletClusterLists.h:362-397 / LinkedCells.h:152-202 likewise delete dummies on rebuild).
   if (out_num_received) *out_num_received = received;
-  if (out_num_sent) *out_num_sent = received;  // single rank: identical; multi rank: local view of arrivals
+  if (out_num_sent) *out_num_sent = sent;  // particles this rank handed to its neighbours (all exchanged dimensions)
   h->structureValid = false;
   h->prunedValid = false;
   h->countsValid = false;
@@ -1246,6 +1346,7 @@ extern "C" int apb_exchange_halos(apb_handle h) {
       for (int s = 0; s < 2; ++s) h->link[d][s].nSend = h->link[d][s].nRecv = 0;
     h->haloAllMode = false;
     h->haloAllN = 0;
+    h->noHalos = false;  // halo copies are appended from here on: a round that fails midway must not hide them
     static const bool noOnePass = getenv("APB_NO_ONEPASS_HALO") != nullptr;
     h->countsValid = false;
     h->countsTrusted = false;
@@ -1261,6 +1362,16 @@ extern "C" int apb_exchange_halos(apb_handle h) {
     }
     h->haloLinksValid = true;
     h->noHalos = false;
+    if (h->cfg.particle_kind != APB_PARTICLE_LJ) {
+      // halo copies of SPH / multi-site particles need their attributes (mass, smoothing length, quaternion ...): the
+      // generating exchange carries positions, ids and types; the other active columns follow through the recorded links
+      ColumnSet cs;
+      cs.n = 0;
+      for (int c = APB_COL_VX; c < APB_NUM_COLUMNS; ++c)
+        if (h->active[c]) cs.p[cs.n++] = h->col[c];
+      APB_CHECK(refreshHaloColumns(h, cs));
+      if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+    }
     return APB_OK;
   }
   if (!h->haloLinksValid) return h->fail(APB_ERR_STATE, "apb_exchange_halos: no halo links recorded; call it once before the rebuild");
@@ -1347,6 +1458,29 @@ extern "C" int apb_exchange_halos(apb_handle h) {
       APB_CUDA(cudaGetLastError());
     }
   }
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+extern "C" int apb_refresh_halo_columns(apb_handle h, int32_t numColumns, const int32_t *columns) {
+  APB_ENTRY(h);
+  APB_CHECK(ensureDecomposition(h));
+  if (numColumns < 0 || numColumns > APB_NUM_COLUMNS || (numColumns > 0 && !columns))
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_refresh_halo_columns: bad column list");
+  if (!h->haloLinksValid)
+    return h->fail(APB_ERR_STATE, "apb_refresh_halo_columns: no halo links recorded; call apb_exchange_halos before the rebuild");
+  ColumnSet cs;
+  cs.n = 0;
+  for (int k = 0; k < numColumns; ++k) {
+    const int c = columns[k];
+    if (c < 0 || c >= APB_NUM_COLUMNS || !h->active[c])
+      return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_refresh_halo_columns: column not part of this particle kind");
+    if (c <= APB_COL_Z)
+      return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_refresh_halo_columns: positions are refreshed by apb_exchange_halos "
+                                               "(they are shifted at the periodic boundary)");
+    cs.p[cs.n++] = h->col[c];
+  }
+  APB_CHECK(refreshHaloColumns(h, cs));
   if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
   return APB_OK;
 }
@@ -1500,14 +1634,8 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
     h->poisoned = true;
     return h->fail(APB_ERR_STATE, "halo refresh: a neighbour rank did not publish its positions within ten seconds");
   }
-  if (outPerStep) {
-    for (int s = 0; s < numSteps; ++s) {
-      if (!(functor->flags & APB_FUNCTOR_CALC_GLOBALS)) {
-        outPerStep[s].upot_sum = 0.;
-        outPerStep[s].virial_sum[0] = outPerStep[s].virial_sum[1] = outPerStep[s].virial_sum[2] = 0.;
-      }
-    }
-  }
+  if (outPerStep)
+    for (int s = 0; s < numSteps; ++s) apbMaskResultByFlags(outPerStep[s], functor->flags);
   return APB_OK;
 }
 
@@ -1545,17 +1673,7 @@ extern "C" int apb_force_step_by_id(apb_handle h, int32_t traversal, const apb_f
   if (rc != APB_OK) return rc;
   if (lj) APB_CUDA(cudaMemcpyAsync(&host, dres, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
   APB_CHECK(apb_download_forces_by_id(h, idBegin, numIds, fx, fy, fz));  // synchronises
-  if (lj) {
-    if (!(functor->flags & APB_FUNCTOR_CALC_GLOBALS)) {
-      host.upot_sum = 0.;
-      host.virial_sum[0] = host.virial_sum[1] = host.virial_sum[2] = 0.;
-      host.num_global_calcs_n3 = host.num_global_calcs_no_n3 = 0;
-    }
-    if (!(functor->flags & APB_FUNCTOR_COUNT_FLOPS)) {
-      host.num_dist_calls = host.num_kernel_calls_n3 = host.num_kernel_calls_no_n3 = 0;
-      host.num_global_calcs_n3 = host.num_global_calcs_no_n3 = 0;
-    }
-  }
+  if (lj) apbMaskResultByFlags(host, functor->flags);
   if (out) *out = host;
   return APB_OK;
 }

@@ -10,6 +10,7 @@
 // separately (__dmul_rn / __dadd_rn), like the oracle built with -ffp-contract=off.
 #include "internal.cuh"
 #include "lj_device.cuh"
+#include "lc_warp.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------------
 // linked-cells pair walk shared by the kernels below
@@ -212,56 +213,268 @@ __global__ void __launch_bounds__(128) kSPHHydroLC(SPHArgs a) {
   }
 }
 
-static int computeSPH(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
-  if (h->cfg.particle_kind != APB_PARTICLE_SPH) return h->fail(APB_ERR_NOT_APPLICABLE, "SPH functors need SPHParticle storage");
-  if (h->cfg.container != APB_CONTAINER_LINKED_CELLS)
-    return h->fail(APB_ERR_NOT_APPLICABLE, "SPH functors run on gpuLinkedCells (gpulc_c08 / gpulc_c18)");
-  if (out) std::memset(out, 0, sizeof(*out));
-  const int64_t n = h->nslots;
-  if (n == 0) return APB_OK;
-  SPHArgs a;
-  a.w = makeWalk(h);
-  a.x = h->col[APB_COL_X];
-  a.y = h->col[APB_COL_Y];
-  a.z = h->col[APB_COL_Z];
-  a.vx = h->col[APB_COL_VX];
-  a.vy = h->col[APB_COL_VY];
-  a.vz = h->col[APB_COL_VZ];
-  a.mass = h->col[APB_COL_MASS];
-  a.smth = h->col[APB_COL_SMTH];
-  a.pressure = h->col[APB_COL_PRESSURE];
-  a.snd = h->col[APB_COL_SNDSPEED];
-  a.density = h->col[APB_COL_DENSITY];
-  a.ax = h->col[APB_COL_FX];
-  a.ay = h->col[APB_COL_FY];
-  a.az = h->col[APB_COL_FZ];
-  a.engDot = h->col[APB_COL_ENGDOT];
-  a.vsigmax = h->col[APB_COL_VSIGMAX];
-  const int block = 128, grid = apbDivUp(n, block);
-  ++h->launchCount;
-  if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
-    if (newton3)
-      kSPHDensityLC<true><<<grid, block, 0, h->stream>>>(a);
-    else
-      kSPHDensityLC<false><<<grid, block, 0, h->stream>>>(a);
-  } else {
-    if (newton3)
-      kSPHHydroLC<true><<<grid, block, 0, h->stream>>>(a);
-    else
-      kSPHHydroLC<false><<<grid, block, 0, h->stream>>>(a);
+// ---- one warp per particle slot (lc_warp.cuh) ---------------------------------------------------------------------------
+// The SPH pair arithmetic is heavy (three divisions and a square root in the hydro force) and only 10-15 % of the
+// candidates of the 27 stencil cells lie inside the kernel support: the lanes of a warp share the candidates of slot i,
+// the hits are compacted and evaluated on full rows of 32, the lane partial sums are reduced with shuffles.
+struct SPHWarpArgs {
+  SPHArgs s;
+  LCWarpGeom w;
+  double interactionLength2;
+};
+
+template <bool N3>
+__global__ void __launch_bounds__(LCW_WARPS * 32) kSPHDensityWarp(SPHWarpArgs wa) {
+  __shared__ int queues[LCW_WARPS][64];
+  const SPHArgs &a = wa.s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * LCW_WARPS + warp; i < a.w.n; i += static_cast<int64_t>(gridDim.x) * LCW_WARPS) {
+    if (a.w.own[i] == APB_OWN_DUMMY) continue;
+    const int c = a.w.slotCell[i];
+    const LCGeom &g = a.w.g;
+    const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+                                       c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
+    if (!canOwnI && !N3) continue;
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
+    // newton3: the pair also feeds rho_j with the partner's support, which may be the larger one
+    const double H = SPH_SUPPORT * hi;
+    const double reach2 = N3 ? wa.interactionLength2 : __dmul_rn(H, H);
+    double rho = 0.;
+    lcWarpWalk<N3>(
+        wa.w, i, c, !canOwnI, queues[warp],
+        [&](int j) {
+          if (j == i || a.w.own[j] == APB_OWN_DUMMY) return false;
+          const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+          return dot3(drx, dry, drz, drx, dry, drz) < reach2;
+        },
+        [&](int j) {
+          const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+          const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+          rho += __dmul_rn(a.mass[j], sphW(dr2, hi));
+          if (N3) {
+            const double d2 = __dmul_rn(mi, sphW(dr2, a.smth[j]));
+            if (d2 != 0.) atomicAdd(a.density + j, d2);
+          }
+        });
+    rho = lcWarpSum(rho);
+    if (lane == 0) {
+      if (N3)
+        atomicAdd(a.density + i, rho);
+      else
+        a.density[i] += rho;
+    }
   }
-  APB_CUDA(cudaGetLastError());
-  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
-  return APB_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Axilrod-Teller-Muto (triwise). newton3 off: every particle i evaluates the triplets (i, j, k), j < k, of its own
-// neighbourhood and receives its force (the reference's lc_c01 calls the functor three times per triplet with rotated
-// roles, CellFunctor3B.h:267-273). newton3 on: every triplet once, by its lowest slot, forces on all three
-// (CellFunctor3B.h:176-262 with newton3, AxilrodTellerMutoFunctor.h:240-290). Three kernels: neighbours of i within the
-// cutoff (count, fill; newton3: higher slots only), then the triplets.
-// ---------------------------------------------------------------------------------------------------------------------
+template <bool N3>
+__global__ void __launch_bounds__(LCW_WARPS * 32) kSPHHydroWarp(SPHWarpArgs wa) {
+  __shared__ int queues[LCW_WARPS][64];
+  const SPHArgs &a = wa.s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * LCW_WARPS + warp; i < a.w.n; i += static_cast<int64_t>(gridDim.x) * LCW_WARPS) {
+    if (a.w.own[i] == APB_OWN_DUMMY) continue;
+    const int c = a.w.slotCell[i];
+    const LCGeom &g = a.w.g;
+    const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+                                       c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
+    if (!canOwnI && !N3) continue;
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
+    const double vxi = a.vx[i], vyi = a.vy[i], vzi = a.vz[i];
+    const double rhoi = a.density[i], Pi = a.pressure[i], ci = a.snd[i];
+    const double cut = hi * SPH_SUPPORT;
+    const double cut2 = __dmul_rn(cut, cut);
+    const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
+    double accx = 0., accy = 0., accz = 0., eng = 0., vmax = 0.;
+    lcWarpWalk<N3>(
+        wa.w, i, c, !canOwnI, queues[warp],
+        [&](int j) {
+          if (j == i || a.w.own[j] == APB_OWN_DUMMY) return false;
+          const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+          return dot3(drx, dry, drz, drx, dry, drz) < cut2;
+        },
+        [&](int j) {
+          const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+          const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+          const double dvx = vxi - a.vx[j], dvy = vyi - a.vy[j], dvz = vzi - a.vz[j];
+          const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
+          const double drabs = sqrt(dr2);
+          const double wij = (dvdr < 0) ? dvdr / drabs : 0;
+          const double vsig = __dadd_rn(__dadd_rn(ci, a.snd[j]), -__dmul_rn(3.0, wij));
+          vmax = fmax(vmax, vsig);
+          const double rhoj = a.density[j], Pj = a.pressure[j], mj = a.mass[j];
+          const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
+          const double gi = sphGradWScale(drabs, hi), gj = sphGradWScale(drabs, a.smth[j]);
+          const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
+          const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
+          const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
+          const double PjOverRho2 = Pj / __dmul_rn(rhoj, rhoj);
+          const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
+          const double si = __dmul_rn(scale, mj);
+          accx -= __dmul_rn(gx, si);
+          accy -= __dmul_rn(gy, si);
+          accz -= __dmul_rn(gz, si);
+          const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
+          const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
+          eng += __dmul_rn(gdv, scale2i);
+          if (N3) {
+            atomicMaxPositive(a.vsigmax + j, vsig);
+            const double sj = __dmul_rn(scale, mi);
+            atomicAdd(a.ax + j, __dmul_rn(gx, sj));
+            atomicAdd(a.ay + j, __dmul_rn(gy, sj));
+            atomicAdd(a.az + j, __dmul_rn(gz, sj));
+            const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
+            atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
+          }
+        });
+    accx = lcWarpSum(accx);
+    accy = lcWarpSum(accy);
+    accz = lcWarpSum(accz);
+    eng = lcWarpSum(eng);
+    vmax = lcWarpMax(vmax);
+    if (lane == 0) {
+      if (N3) {
+        atomicAdd(a.ax + i, accx);
+        atomicAdd(a.ay + i, accy);
+        atomicAdd(a.az + i, accz);
+        atomicAdd(a.engDot + i, eng);
+        if (vmax > 0.) atomicMaxPositive(a.vsigmax + i, vmax);
+      } else {
+        a.ax[i] += accx;
+        a.ay[i] += accy;
+        a.az[i] += accz;
+        a.engDot[i] += eng;
+        a.vsigmax[i] = fmax(a.vsigmax[i], vmax);
+      }
+    }
+  }
+}
+
+// ---- one thread per slot, pair arithmetic deferred (lcDeferredWalk): the variant for systems that fill the GPU ---------
+template <bool N3>
+__global__ void __launch_bounds__(LCD_BLOCK) kSPHDensityDeferred(SPHWarpArgs wa) {
+  __shared__ int queue[LCD_DEPTH * LCD_BLOCK];
+  const SPHArgs &a = wa.s;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool live = i < a.w.n && a.w.own[i] != APB_OWN_DUMMY;
+  const int c = live ? a.w.slotCell[i] : 0;
+  const LCGeom &g = a.w.g;
+  const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+                                     c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
+  const bool part = live && (canOwnI || N3);
+  const int64_t ii = part ? i : 0;
+  const double xi = a.x[ii], yi = a.y[ii], zi = a.z[ii], hi = a.smth[ii], mi = a.mass[ii];
+  const double H = SPH_SUPPORT * hi;
+  const double reach2 = N3 ? wa.interactionLength2 : __dmul_rn(H, H);
+  double rho = 0.;
+  lcDeferredWalk<N3>(
+      g, wa.w.cellStart, wa.w.stencilSorted, wa.w.stencilN, part, i, c, !canOwnI, queue,
+      [&](int j) {
+        if (j == i || a.w.own[j] == APB_OWN_DUMMY) return false;
+        const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+        return dot3(drx, dry, drz, drx, dry, drz) < reach2;
+      },
+      [&](int j) {
+        const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+        const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+        rho += __dmul_rn(a.mass[j], sphW(dr2, hi));
+        if (N3) {
+          const double d2 = __dmul_rn(mi, sphW(dr2, a.smth[j]));
+          if (d2 != 0.) atomicAdd(a.density + j, d2);
+        }
+      });
+  if (part) {
+    if (N3)
+      atomicAdd(a.density + i, rho);
+    else
+      a.density[i] += rho;
+  }
+}
+
+template <bool N3>
+__global__ void __launch_bounds__(LCD_BLOCK) kSPHHydroDeferred(SPHWarpArgs wa) {
+  __shared__ int queue[LCD_DEPTH * LCD_BLOCK];
+  const SPHArgs &a = wa.s;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool live = i < a.w.n && a.w.own[i] != APB_OWN_DUMMY;
+  const int c = live ? a.w.slotCell[i] : 0;
+  const LCGeom &g = a.w.g;
+  const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+                                     c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
+  const bool part = live && (canOwnI || N3);
+  const int64_t ii = part ? i : 0;
+  const double xi = a.x[ii], yi = a.y[ii], zi = a.z[ii], hi = a.smth[ii], mi = a.mass[ii];
+  const double vxi = a.vx[ii], vyi = a.vy[ii], vzi = a.vz[ii];
+  const double rhoi = a.density[ii], Pi = a.pressure[ii], ci = a.snd[ii];
+  const double cut = hi * SPH_SUPPORT;
+  const double cut2 = __dmul_rn(cut, cut);
+  const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
+  double accx = 0., accy = 0., accz = 0., eng = 0., vmax = 0.;
+  lcDeferredWalk<N3>(
+      g, wa.w.cellStart, wa.w.stencilSorted, wa.w.stencilN, part, i, c, !canOwnI, queue,
+      [&](int j) {
+        if (j == i || a.w.own[j] == APB_OWN_DUMMY) return false;
+        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+        return dot3(drx, dry, drz, drx, dry, drz) < cut2;
+      },
+      [&](int j) {
+        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+        const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+        const double dvx = vxi - a.vx[j], dvy = vyi - a.vy[j], dvz = vzi - a.vz[j];
+        const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
+        const double drabs = sqrt(dr2);
+        const double wij = (dvdr < 0) ? dvdr / drabs : 0;
+        const double vsig = __dadd_rn(__dadd_rn(ci, a.snd[j]), -__dmul_rn(3.0, wij));
+        vmax = fmax(vmax, vsig);
+        const double rhoj = a.density[j], Pj = a.pressure[j], mj = a.mass[j];
+        const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
+        const double gi = sphGradWScale(drabs, hi), gj = sphGradWScale(drabs, a.smth[j]);
+        const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
+        const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
+        const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
+        const double PjOverRho2 = Pj / __dmul_rn(rhoj, rhoj);
+        const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
+        const double si = __dmul_rn(scale, mj);
+        accx -= __dmul_rn(gx, si);
+        accy -= __dmul_rn(gy, si);
+        accz -= __dmul_rn(gz, si);
+        const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
+        const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
+        eng += __dmul_rn(gdv, scale2i);
+        if (N3) {
+          atomicMaxPositive(a.vsigmax + j, vsig);
+          const double sj = __dmul_rn(scale, mi);
+          atomicAdd(a.ax + j, __dmul_rn(gx, sj));
+          atomicAdd(a.ay + j, __dmul_rn(gy, sj));
+          atomicAdd(a.az + j, __dmul_rn(gz, sj));
+          const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
+          atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
+        }
+      });
+  if (part) {
+    if (N3) {
+      atomicAdd(a.ax + i, accx);
+      atomicAdd(a.ay + i, accy);
+      atomicAdd(a.az + i, accz);
+      atomicAdd(a.engDot + i, eng);
+      if (vmax > 0.) atomicMaxPositive(a.vsigmax + i, vmax);
+    } else {
+      a.ax[i] += accx;
+      a.ay[i] += accy;
+      a.az[i] += accz;
+      a.engDot[i] += eng;
+      a.vsigmax[i] = fmax(a.vsigmax[i], vmax);
+    }
+  }
+}
+
+// ---- per-slot partner lists --------------------------------------------------------------------------------------------
+// The 27 stencil cells hold ~1000 candidates per particle at SPH densities, of which ~110 lie inside the kernel support;
+// walking them costs ~75 instructions per candidate whatever the kernel variant (measured, profiles/r02_lc_kernels.txt),
+// and the density and the hydro-force pass walk the same cells. gpuLinkedCells therefore keeps, per slot, the list of
+// partner slots within cutoff + skin (entry-major, coalesced across threads), built on first use after a rebuild and
+// valid for as long as the cells are (particles move less than skin / 2 between rebuilds: every pair within the cutoff
+// at traversal time is on the list - the guarantee a Verlet list gives, VerletListHelpers.h). The functor kernels test
+// the current distance of every listed pair and do the pair arithmetic in place.
 struct ATMArgs {
   LCWalk w;
   const double *x, *y, *z;
@@ -304,6 +517,257 @@ __global__ void __launch_bounds__(128) kATMNeighbors(ATMArgs a) {
   }
 }
 
+
+static int ensureLCLists(apb_handle h, bool half) {
+  if (h->lcListVersion == h->structureVersion && h->lcListHalf == (half ? 1 : 0)) return APB_OK;
+  const int64_t n = h->nslots;
+  ATMArgs a{};
+  a.w = makeWalk(h);
+  a.x = h->col[APB_COL_X];
+  a.y = h->col[APB_COL_Y];
+  a.z = h->col[APB_COL_Z];
+  const double il = h->cfg.cutoff + h->cfg.skin;
+  a.cutoff2 = il * il;
+  const int block = 128, grid = apbDivUp(n, block);
+  APB_CHECK(apbEnsure(h, h->nbrCount, sizeof(int) * (n + 1)));
+  a.nbrCount = static_cast<int *>(h->nbrCount.p);
+  int *maxDev = reinterpret_cast<int *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 32);
+  a.maxCount = maxDev;
+  APB_CUDA(cudaMemsetAsync(maxDev, 0, 4, h->stream));
+  ++h->launchCount;
+  if (half)
+    kATMNeighbors<false, true><<<grid, block, 0, h->stream>>>(a);
+  else
+    kATMNeighbors<false, false><<<grid, block, 0, h->stream>>>(a);
+  APB_CUDA(cudaGetLastError());
+  int cap = 0;
+  APB_CUDA(cudaMemcpyAsync(&cap, maxDev, 4, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  APB_CHECK(apbEnsure(h, h->nbrList, sizeof(int) * static_cast<size_t>(std::max(cap, 1)) * n));
+  a.nbr = static_cast<int *>(h->nbrList.p);
+  a.cap = cap;
+  if (cap > 0) {
+    ++h->launchCount;
+    if (half)
+      kATMNeighbors<true, true><<<grid, block, 0, h->stream>>>(a);
+    else
+      kATMNeighbors<true, false><<<grid, block, 0, h->stream>>>(a);
+    APB_CUDA(cudaGetLastError());
+  }
+  h->lcListVersion = h->structureVersion;
+  h->lcListHalf = half ? 1 : 0;
+  h->lcListCap = cap;
+  return APB_OK;
+}
+
+struct SPHListArgs {
+  SPHArgs s;
+  const int *nbrCount, *nbr;
+};
+
+template <bool N3>
+__global__ void __launch_bounds__(128) kSPHDensityList(SPHListArgs la) {
+  const SPHArgs &a = la.s;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= a.w.n || a.w.own[i] == APB_OWN_DUMMY) return;
+  const int cnt = la.nbrCount[i];
+  if (cnt == 0) return;
+  const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
+  double rho = 0.;
+  for (int p = 0; p < cnt; ++p) {
+    const int j = la.nbr[static_cast<size_t>(p) * a.w.n + i];
+    const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+    const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+    rho += __dmul_rn(a.mass[j], sphW(dr2, hi));
+    if (N3) {
+      const double d2 = __dmul_rn(mi, sphW(dr2, a.smth[j]));
+      if (d2 != 0.) atomicAdd(a.density + j, d2);
+    }
+  }
+  if (N3)
+    atomicAdd(a.density + i, rho);
+  else
+    a.density[i] += rho;
+}
+
+template <bool N3>
+__global__ void __launch_bounds__(128) kSPHHydroList(SPHListArgs la) {
+  const SPHArgs &a = la.s;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= a.w.n || a.w.own[i] == APB_OWN_DUMMY) return;
+  const int cnt = la.nbrCount[i];
+  if (cnt == 0) return;
+  const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
+  const double vxi = a.vx[i], vyi = a.vy[i], vzi = a.vz[i];
+  const double rhoi = a.density[i], Pi = a.pressure[i], ci = a.snd[i];
+  const double cut = hi * SPH_SUPPORT;
+  const double cut2 = __dmul_rn(cut, cut);
+  const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
+  double accx = 0., accy = 0., accz = 0., eng = 0., vmax = 0.;
+  for (int p = 0; p < cnt; ++p) {
+    const int j = la.nbr[static_cast<size_t>(p) * a.w.n + i];
+    const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+    const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+    if (dr2 >= cut2) continue;
+    const double dvx = vxi - a.vx[j], dvy = vyi - a.vy[j], dvz = vzi - a.vz[j];
+    const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
+    const double drabs = sqrt(dr2);
+    const double wij = (dvdr < 0) ? dvdr / drabs : 0;
+    const double vsig = __dadd_rn(__dadd_rn(ci, a.snd[j]), -__dmul_rn(3.0, wij));
+    vmax = fmax(vmax, vsig);
+    const double rhoj = a.density[j], Pj = a.pressure[j], mj = a.mass[j];
+    const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
+    const double gi = sphGradWScale(drabs, hi), gj = sphGradWScale(drabs, a.smth[j]);
+    const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
+    const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
+    const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
+    const double PjOverRho2 = Pj / __dmul_rn(rhoj, rhoj);
+    const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
+    const double si = __dmul_rn(scale, mj);
+    accx -= __dmul_rn(gx, si);
+    accy -= __dmul_rn(gy, si);
+    accz -= __dmul_rn(gz, si);
+    const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
+    const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
+    eng += __dmul_rn(gdv, scale2i);
+    if (N3) {
+      atomicMaxPositive(a.vsigmax + j, vsig);
+      const double sj = __dmul_rn(scale, mi);
+      atomicAdd(a.ax + j, __dmul_rn(gx, sj));
+      atomicAdd(a.ay + j, __dmul_rn(gy, sj));
+      atomicAdd(a.az + j, __dmul_rn(gz, sj));
+      const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
+      atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
+    }
+  }
+  if (N3) {
+    atomicAdd(a.ax + i, accx);
+    atomicAdd(a.ay + i, accy);
+    atomicAdd(a.az + i, accz);
+    atomicAdd(a.engDot + i, eng);
+    if (vmax > 0.) atomicMaxPositive(a.vsigmax + i, vmax);
+  } else {
+    a.ax[i] += accx;
+    a.ay[i] += accy;
+    a.az[i] += accz;
+    a.engDot[i] += eng;
+    a.vsigmax[i] = fmax(a.vsigmax[i], vmax);
+  }
+}
+
+static int computeSPH(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
+  if (h->cfg.particle_kind != APB_PARTICLE_SPH) return h->fail(APB_ERR_NOT_APPLICABLE, "SPH functors need SPHParticle storage");
+  if (h->cfg.container != APB_CONTAINER_LINKED_CELLS)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "SPH functors run on gpuLinkedCells (gpulc_c08 / gpulc_c18)");
+  if (out) std::memset(out, 0, sizeof(*out));
+  const int64_t n = h->nslots;
+  if (n == 0) return APB_OK;
+  SPHArgs a;
+  a.w = makeWalk(h);
+  a.x = h->col[APB_COL_X];
+  a.y = h->col[APB_COL_Y];
+  a.z = h->col[APB_COL_Z];
+  a.vx = h->col[APB_COL_VX];
+  a.vy = h->col[APB_COL_VY];
+  a.vz = h->col[APB_COL_VZ];
+  a.mass = h->col[APB_COL_MASS];
+  a.smth = h->col[APB_COL_SMTH];
+  a.pressure = h->col[APB_COL_PRESSURE];
+  a.snd = h->col[APB_COL_SNDSPEED];
+  a.density = h->col[APB_COL_DENSITY];
+  a.ax = h->col[APB_COL_FX];
+  a.ay = h->col[APB_COL_FY];
+  a.az = h->col[APB_COL_FZ];
+  a.engDot = h->col[APB_COL_ENGDOT];
+  a.vsigmax = h->col[APB_COL_VSIGMAX];
+  const int lcKernel = apbLCKernelVariant(n);  // 0 thread (round 1), 1 warp per slot, 2 deferred, 3 partner lists
+  if (lcKernel == 3) {
+    APB_CHECK(ensureLCLists(h, newton3 != 0));
+    SPHListArgs la;
+    la.s = a;
+    la.nbrCount = static_cast<const int *>(h->nbrCount.p);
+    la.nbr = static_cast<const int *>(h->nbrList.p);
+    const int lgrid = apbDivUp(n, 128);
+    ++h->launchCount;
+    if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
+      if (newton3)
+        kSPHDensityList<true><<<lgrid, 128, 0, h->stream>>>(la);
+      else
+        kSPHDensityList<false><<<lgrid, 128, 0, h->stream>>>(la);
+    } else {
+      if (newton3)
+        kSPHHydroList<true><<<lgrid, 128, 0, h->stream>>>(la);
+      else
+        kSPHHydroList<false><<<lgrid, 128, 0, h->stream>>>(la);
+    }
+    APB_CUDA(cudaGetLastError());
+    if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+    return APB_OK;
+  }
+  if (lcKernel != 0) {
+    SPHWarpArgs wa;
+    wa.s = a;
+    wa.w.g = h->lc;
+    wa.w.cellStart = a.w.cellStart;
+    wa.w.stencilSorted = a.w.stencil + 3 * APB_MAX_STENCIL;
+    wa.w.stencilN = h->stencilN;
+    const double il = h->cfg.cutoff + h->cfg.skin;
+    wa.interactionLength2 = il * il;
+    const int grid = static_cast<int>(std::min<int64_t>(apbDivUp(n, LCW_WARPS), 148 * 16));
+    ++h->launchCount;
+    if (lcKernel == 2) {
+      const int dgrid = apbDivUp(n, LCD_BLOCK);
+      if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
+        if (newton3)
+          kSPHDensityDeferred<true><<<dgrid, LCD_BLOCK, 0, h->stream>>>(wa);
+        else
+          kSPHDensityDeferred<false><<<dgrid, LCD_BLOCK, 0, h->stream>>>(wa);
+      } else {
+        if (newton3)
+          kSPHHydroDeferred<true><<<dgrid, LCD_BLOCK, 0, h->stream>>>(wa);
+        else
+          kSPHHydroDeferred<false><<<dgrid, LCD_BLOCK, 0, h->stream>>>(wa);
+      }
+    } else if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
+      if (newton3)
+        kSPHDensityWarp<true><<<grid, LCW_WARPS * 32, 0, h->stream>>>(wa);
+      else
+        kSPHDensityWarp<false><<<grid, LCW_WARPS * 32, 0, h->stream>>>(wa);
+    } else {
+      if (newton3)
+        kSPHHydroWarp<true><<<grid, LCW_WARPS * 32, 0, h->stream>>>(wa);
+      else
+        kSPHHydroWarp<false><<<grid, LCW_WARPS * 32, 0, h->stream>>>(wa);
+    }
+    APB_CUDA(cudaGetLastError());
+    if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+    return APB_OK;
+  }
+  const int block = 128, grid = apbDivUp(n, block);
+  ++h->launchCount;
+  if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
+    if (newton3)
+      kSPHDensityLC<true><<<grid, block, 0, h->stream>>>(a);
+    else
+      kSPHDensityLC<false><<<grid, block, 0, h->stream>>>(a);
+  } else {
+    if (newton3)
+      kSPHHydroLC<true><<<grid, block, 0, h->stream>>>(a);
+    else
+      kSPHHydroLC<false><<<grid, block, 0, h->stream>>>(a);
+  }
+  APB_CUDA(cudaGetLastError());
+  if (!h->deferSync) APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Axilrod-Teller-Muto (triwise). newton3 off: every particle i evaluates the triplets (i, j, k), j < k, of its own
+// neighbourhood and receives its force (the reference's lc_c01 calls the functor three times per triplet with rotated
+// roles, CellFunctor3B.h:267-273). newton3 on: every triplet once, by its lowest slot, forces on all three
+// (CellFunctor3B.h:176-262 with newton3, AxilrodTellerMutoFunctor.h:240-290). Three kernels: neighbours of i within the
+// cutoff (count, fill; newton3: higher slots only), then the triplets.
+// ---------------------------------------------------------------------------------------------------------------------
 template <bool MIX, bool STATS>
 __global__ void __launch_bounds__(128) kATMTriplets(ATMArgs a) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -465,6 +929,370 @@ __global__ void __launch_bounds__(128) kATMTripletsN3(ATMArgs a) {
   if (STATS) ljStatsBlockReduce(st, a.partials);
 }
 
+// ---- one warp per particle slot ----------------------------------------------------------------------------------------
+// kATMCountWarp: neighbours of slot i within the cutoff (newton3: in higher slots), warp-cooperative walk; feeds the
+// shared-memory capacity of kATMTripletsWarp. kATMTripletsWarp: the warp collects the neighbours of i into shared memory
+// (positions, slot, type), its lanes share the (j, k) pairs of the neighbour list, test |r_jk| <= cutoff, compact the
+// surviving triplets by ballot and evaluate them on full rows of 32 - a thread-per-particle loop executes the ~100 FP64
+// instructions of a triplet for every (j, k) pair of which only ~17 % pass. No neighbour list in global memory.
+// Triplet rules, globals and counters as in kATMTriplets / kATMTripletsN3.
+struct ATMWarpArgs {
+  ATMArgs a;
+  LCWarpGeom w;
+  int cap;  // neighbours per warp that fit in shared memory
+};
+
+template <bool HALF>
+__global__ void __launch_bounds__(LCW_WARPS * 32) kATMCountWarp(ATMWarpArgs wa) {
+  __shared__ int queues[LCW_WARPS][64];
+  const ATMArgs &a = wa.a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int most = 0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * LCW_WARPS + warp; i < a.w.n; i += static_cast<int64_t>(gridDim.x) * LCW_WARPS) {
+    int cnt = 0;
+    if (a.w.own[i] != APB_OWN_DUMMY) {
+      const int c = a.w.slotCell[i];
+      const LCGeom &g = a.w.g;
+      const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+                                         c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
+      if (HALF || canOwnI) {
+        const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+        cnt = lcWarpWalk<HALF>(
+            wa.w, i, c, false, queues[warp],
+            [&](int j) {
+              if (j == i || a.w.own[j] == APB_OWN_DUMMY) return false;
+              const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+              return dot3(drx, dry, drz, drx, dry, drz) <= a.cutoff2;
+            },
+            [](int) {});
+      }
+    }
+    if (lane == 0) a.nbrCount[i] = cnt;
+    most = max(most, cnt);
+  }
+  if (lane == 0 && most > 0) atomicMax(a.maxCount, most);
+}
+
+template <bool MIX, bool STATS, bool N3>
+__global__ void __launch_bounds__(LCW_WARPS * 32) kATMTripletsWarp(ATMWarpArgs wa) {
+  extern __shared__ __align__(16) unsigned char atmSmem[];
+  __shared__ int queues[LCW_WARPS][64];
+  const ATMArgs &a = wa.a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cap = wa.cap;
+  const unsigned below = (1u << lane) - 1u;
+  double *nx = reinterpret_cast<double *>(atmSmem) + static_cast<size_t>(warp) * 3 * cap, *ny = nx + cap, *nz = ny + cap;
+  int *nslot = reinterpret_cast<int *>(atmSmem + static_cast<size_t>(LCW_WARPS) * 24 * cap) + static_cast<size_t>(warp) * 2 * cap;
+  int *ntype = nslot + cap;
+  int *queue = queues[warp];
+  LJStats st;
+  ljStatsZero(st);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * LCW_WARPS + warp; i < a.w.n; i += static_cast<int64_t>(gridDim.x) * LCW_WARPS) {
+    const int ownI = a.w.own[i];
+    if (ownI == APB_OWN_DUMMY) continue;
+    const int cnt = a.nbrCount[i];
+    if (cnt < 2) continue;
+    const int c = a.w.slotCell[i];
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+    const int ti = MIX ? a.type[i] : 0;
+    const bool ownedI = ownI == APB_OWN_OWNED;
+    // ---- neighbours of i -> shared memory, in walk order
+    int filled = 0;
+    lcWarpWalk<N3>(
+        wa.w, i, c, false, queue,
+        [&](int j) {
+          if (j == i || a.w.own[j] == APB_OWN_DUMMY) return false;
+          const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+          return dot3(drx, dry, drz, drx, dry, drz) <= a.cutoff2;
+        },
+        [&](int j) {
+          const int e = filled + lane;
+          nx[e] = a.x[j];
+          ny[e] = a.y[j];
+          nz[e] = a.z[j];
+          nslot[e] = j;
+          if (MIX) ntype[e] = a.type[j];
+          filled += 32;
+        });
+    __syncwarp();
+    double Fx = 0., Fy = 0., Fz = 0.;
+    auto triplet = [&](int pq) {
+      const int p = pq >> 16, q = pq & 0xFFFF;
+      const double xj = nx[p], yj = ny[p], zj = nz[p], xk = nx[q], yk = ny[q], zk = nz[q];
+      const double ijx = xj - xi, ijy = yj - yi, ijz = zj - zi;
+      const double jkx = xk - xj, jky = yk - yj, jkz = zk - zj;
+      const double kix = xi - xk, kiy = yi - yk, kiz = zi - zk;
+      const double d2ij = dot3(ijx, ijy, ijz, ijx, ijy, ijz);
+      const double d2jk = dot3(jkx, jky, jkz, jkx, jky, jkz);
+      const double d2ki = dot3(kix, kiy, kiz, kix, kiy, kiz);
+      double nu = a.nu;
+      if (MIX) nu = __ldg(a.nuMix + (static_cast<size_t>(ti) * a.T + ntype[p]) * a.T + ntype[q]);
+      // AxilrodTellerMutoFunctor.h:217-251
+      const double all2 = d2ij * d2jk * d2ki;
+      const double all5 = all2 * all2 * sqrt(all2);
+      const double factor = 3.0 * nu / all5;
+      const double IJdKI = dot3(ijx, ijy, ijz, kix, kiy, kiz);
+      const double IJdJK = dot3(ijx, ijy, ijz, jkx, jky, jkz);
+      const double JKdKI = dot3(jkx, jky, jkz, kix, kiy, kiz);
+      const double allDots = IJdKI * IJdJK * JKdKI;
+      const double cJK = IJdKI * (IJdJK - JKdKI);
+      const double cIJ = IJdJK * JKdKI - d2jk * d2ki + 5.0 * allDots / d2ij;
+      const double cKI = -IJdJK * JKdKI + d2ij * d2jk - 5.0 * allDots / d2ki;
+      const double fix = (jkx * cJK + ijx * cIJ + kix * cKI) * factor;
+      const double fiy = (jky * cJK + ijy * cIJ + kiy * cKI) * factor;
+      const double fiz = (jkz * cJK + ijz * cIJ + kiz * cKI) * factor;
+      Fx += fix;
+      Fy += fiy;
+      Fz += fiz;
+      const double u3 = factor * (all2 - 3.0 * allDots);
+      if (N3) {
+        // force on j (:241-247), F_k = -(F_i + F_j)
+        const double jKI = IJdJK * (JKdKI - IJdKI);
+        const double jIJ = -IJdKI * JKdKI + d2jk * d2ki - 5.0 * allDots / d2ij;
+        const double jJK = IJdKI * JKdKI - d2ij * d2ki + 5.0 * allDots / d2jk;
+        const double fjx = (kix * jKI + ijx * jIJ + jkx * jJK) * factor;
+        const double fjy = (kiy * jKI + ijy * jIJ + jky * jJK) * factor;
+        const double fjz = (kiz * jKI + ijz * jIJ + jkz * jJK) * factor;
+        const double fkx = (fix + fjx) * (-1.0), fky = (fiy + fjy) * (-1.0), fkz = (fiz + fjz) * (-1.0);
+        const int j = nslot[p], k = nslot[q];
+        atomicAdd(a.fx + j, fjx);
+        atomicAdd(a.fy + j, fjy);
+        atomicAdd(a.fz + j, fjz);
+        atomicAdd(a.fx + k, fkx);
+        atomicAdd(a.fy + k, fky);
+        atomicAdd(a.fz + k, fkz);
+        if (STATS) {
+          ++st.kN3;
+          ++st.gN3;
+          if (ownedI) {
+            st.upot += u3;
+            st.vir[0] += fix * xi;
+            st.vir[1] += fiy * yi;
+            st.vir[2] += fiz * zi;
+          }
+          if (a.w.own[j] == APB_OWN_OWNED) {
+            st.upot += u3;
+            st.vir[0] += fjx * xj;
+            st.vir[1] += fjy * yj;
+            st.vir[2] += fjz * zj;
+          }
+          if (a.w.own[k] == APB_OWN_OWNED) {
+            st.upot += u3;
+            st.vir[0] += fkx * xk;
+            st.vir[1] += fky * yk;
+            st.vir[2] += fkz * zk;
+          }
+        }
+      } else if (STATS) {
+        ++st.kNoN3;
+        ++st.gNoN3;
+        if (ownedI) {
+          // potentialEnergy3 = factor (allDistsSquared - 3 allDotProducts); virial = f_i * r_i (:269-275)
+          st.upot += u3;
+          st.vir[0] += fix * xi;
+          st.vir[1] += fiy * yi;
+          st.vir[2] += fiz * zi;
+        }
+      }
+    };
+    // ---- (j, k) pairs of the list: lanes over k for every j; survivors compacted, evaluated on full rows
+    int qn = 0;
+    for (int p = 0; p + 1 < cnt; ++p) {
+      const double xj = nx[p], yj = ny[p], zj = nz[p];
+      for (int base = p + 1; base < cnt; base += 32) {
+        const int q = base + lane;
+        bool hit = false;
+        if (q < cnt) {
+          const double jkx = nx[q] - xj, jky = ny[q] - yj, jkz = nz[q] - zj;
+          hit = dot3(jkx, jky, jkz, jkx, jky, jkz) <= a.cutoff2;  // d2ij and d2ki are within the cutoff by construction
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) queue[qn + __popc(m & below)] = (p << 16) | q;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+          const int pq = queue[lane];
+          const int carry = lane < qn - 32 ? queue[32 + lane] : 0;
+          __syncwarp();
+          if (lane < qn - 32) queue[lane] = carry;
+          qn -= 32;
+          triplet(pq);
+          __syncwarp();
+        }
+      }
+    }
+    if (lane < qn) triplet(queue[lane]);
+    __syncwarp();
+    if (STATS && lane == 0) st.dist += static_cast<unsigned long long>(cnt) * (cnt - 1) / 2;
+    Fx = lcWarpSum(Fx);
+    Fy = lcWarpSum(Fy);
+    Fz = lcWarpSum(Fz);
+    if (lane == 0) {
+      if (N3) {
+        atomicAdd(a.fx + i, Fx);
+        atomicAdd(a.fy + i, Fy);
+        atomicAdd(a.fz + i, Fz);
+      } else {
+        a.fx[i] += Fx;
+        a.fy[i] += Fy;
+        a.fz[i] += Fz;
+      }
+    }
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
+// One thread per slot over the neighbour lists of kATMNeighbors with the triplet arithmetic deferred: a lane appends
+// the (j, k) pairs that pass |r_jk| <= cutoff to its private queue in shared memory and the warp drains the queues
+// together when the first one is full (see lcDeferredWalk, lc_warp.cuh) - the ~100 FP64 instructions of a triplet run
+// at the fill level of the queues instead of for every (j, k) pair. The variant for systems that fill the GPU.
+template <bool MIX, bool STATS, bool N3>
+__global__ void __launch_bounds__(LCD_BLOCK) kATMTripletsDeferred(ATMArgs a) {
+  __shared__ int queue[LCD_DEPTH * LCD_BLOCK];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  LJStats st;
+  ljStatsZero(st);
+  const int ownI = i < a.w.n ? a.w.own[i] : APB_OWN_DUMMY;
+  const int cnt = ownI != APB_OWN_DUMMY ? a.nbrCount[i] : 0;
+  const int64_t ii = ownI != APB_OWN_DUMMY ? i : 0;
+  const double xi = a.x[ii], yi = a.y[ii], zi = a.z[ii];
+  const int ti = MIX ? a.type[ii] : 0;
+  const bool ownedI = ownI == APB_OWN_OWNED;
+  double Fx = 0., Fy = 0., Fz = 0.;
+  auto triplet = [&](int pq) {
+    const int p = pq >> 16, q = pq & 0xFFFF;
+    const int j = a.nbr[static_cast<size_t>(p) * a.w.n + i], k = a.nbr[static_cast<size_t>(q) * a.w.n + i];
+    const double xj = a.x[j], yj = a.y[j], zj = a.z[j], xk = a.x[k], yk = a.y[k], zk = a.z[k];
+    const double ijx = xj - xi, ijy = yj - yi, ijz = zj - zi;
+    const double jkx = xk - xj, jky = yk - yj, jkz = zk - zj;
+    const double kix = xi - xk, kiy = yi - yk, kiz = zi - zk;
+    const double d2ij = dot3(ijx, ijy, ijz, ijx, ijy, ijz);
+    const double d2jk = dot3(jkx, jky, jkz, jkx, jky, jkz);
+    const double d2ki = dot3(kix, kiy, kiz, kix, kiy, kiz);
+    double nu = a.nu;
+    if (MIX) nu = __ldg(a.nuMix + (static_cast<size_t>(ti) * a.T + a.type[j]) * a.T + a.type[k]);
+    // AxilrodTellerMutoFunctor.h:217-251
+    const double all2 = d2ij * d2jk * d2ki;
+    const double all5 = all2 * all2 * sqrt(all2);
+    const double factor = 3.0 * nu / all5;
+    const double IJdKI = dot3(ijx, ijy, ijz, kix, kiy, kiz);
+    const double IJdJK = dot3(ijx, ijy, ijz, jkx, jky, jkz);
+    const double JKdKI = dot3(jkx, jky, jkz, kix, kiy, kiz);
+    const double allDots = IJdKI * IJdJK * JKdKI;
+    const double cJK = IJdKI * (IJdJK - JKdKI);
+    const double cIJ = IJdJK * JKdKI - d2jk * d2ki + 5.0 * allDots / d2ij;
+    const double cKI = -IJdJK * JKdKI + d2ij * d2jk - 5.0 * allDots / d2ki;
+    const double fix = (jkx * cJK + ijx * cIJ + kix * cKI) * factor;
+    const double fiy = (jky * cJK + ijy * cIJ + kiy * cKI) * factor;
+    const double fiz = (jkz * cJK + ijz * cIJ + kiz * cKI) * factor;
+    Fx += fix;
+    Fy += fiy;
+    Fz += fiz;
+    const double u3 = factor * (all2 - 3.0 * allDots);
+    if (N3) {
+      // force on j (:241-247), F_k = -(F_i + F_j)
+      const double jKI = IJdJK * (JKdKI - IJdKI);
+      const double jIJ = -IJdKI * JKdKI + d2jk * d2ki - 5.0 * allDots / d2ij;
+      const double jJK = IJdKI * JKdKI - d2ij * d2ki + 5.0 * allDots / d2jk;
+      const double fjx = (kix * jKI + ijx * jIJ + jkx * jJK) * factor;
+      const double fjy = (kiy * jKI + ijy * jIJ + jky * jJK) * factor;
+      const double fjz = (kiz * jKI + ijz * jIJ + jkz * jJK) * factor;
+      const double fkx = (fix + fjx) * (-1.0), fky = (fiy + fjy) * (-1.0), fkz = (fiz + fjz) * (-1.0);
+      atomicAdd(a.fx + j, fjx);
+      atomicAdd(a.fy + j, fjy);
+      atomicAdd(a.fz + j, fjz);
+      atomicAdd(a.fx + k, fkx);
+      atomicAdd(a.fy + k, fky);
+      atomicAdd(a.fz + k, fkz);
+      if (STATS) {
+        ++st.kN3;
+        ++st.gN3;
+        if (ownedI) {
+          st.upot += u3;
+          st.vir[0] += fix * xi;
+          st.vir[1] += fiy * yi;
+          st.vir[2] += fiz * zi;
+        }
+        if (a.w.own[j] == APB_OWN_OWNED) {
+          st.upot += u3;
+          st.vir[0] += fjx * xj;
+          st.vir[1] += fjy * yj;
+          st.vir[2] += fjz * zj;
+        }
+        if (a.w.own[k] == APB_OWN_OWNED) {
+          st.upot += u3;
+          st.vir[0] += fkx * xk;
+          st.vir[1] += fky * yk;
+          st.vir[2] += fkz * zk;
+        }
+      }
+    } else if (STATS) {
+      ++st.kNoN3;
+      ++st.gNoN3;
+      if (ownedI) {
+        // potentialEnergy3 = factor (allDistsSquared - 3 allDotProducts); virial = f_i * r_i (:269-275)
+        st.upot += u3;
+        st.vir[0] += fix * xi;
+        st.vir[1] += fiy * yi;
+        st.vir[2] += fiz * zi;
+      }
+    }
+  };
+  int *q = queue + threadIdx.x;
+  int p = -1, qq = 0, qn = 0;
+  double xj = 0., yj = 0., zj = 0.;
+  bool done = cnt < 2;
+  do {
+    int pq = -1;
+    if (!done) {
+      if (qq >= cnt || p < 0) {  // next j
+        ++p;
+        qq = p + 1;
+        if (qq >= cnt) {
+          done = true;
+        } else {
+          const int j = a.nbr[static_cast<size_t>(p) * a.w.n + i];
+          xj = a.x[j];
+          yj = a.y[j];
+          zj = a.z[j];
+        }
+      }
+      if (!done) {
+        const int k = a.nbr[static_cast<size_t>(qq) * a.w.n + i];
+        const double jkx = a.x[k] - xj, jky = a.y[k] - yj, jkz = a.z[k] - zj;
+        if (STATS) ++st.dist;
+        // d2ij and d2ki are within the cutoff by construction of the list
+        if (dot3(jkx, jky, jkz, jkx, jky, jkz) <= a.cutoff2) pq = (p << 16) | qq;
+        ++qq;
+      }
+    }
+    if (pq >= 0) {
+      q[qn * LCD_BLOCK] = pq;
+      ++qn;
+    }
+    if (__any_sync(0xffffffffu, qn == LCD_DEPTH)) {
+#pragma unroll 1
+      for (int t = 0; t < LCD_DEPTH; ++t)
+        if (t < qn) triplet(q[t * LCD_BLOCK]);
+      qn = 0;
+    }
+  } while (__any_sync(0xffffffffu, !done));
+#pragma unroll 1
+  for (int t = 0; t < LCD_DEPTH; ++t)
+    if (t < qn) triplet(q[t * LCD_BLOCK]);
+  if (cnt >= 2) {
+    if (N3) {
+      atomicAdd(a.fx + i, Fx);
+      atomicAdd(a.fy + i, Fy);
+      atomicAdd(a.fz + i, Fz);
+    } else {
+      a.fx[i] += Fx;
+      a.fy[i] += Fy;
+      a.fz[i] += Fz;
+    }
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
 int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f, apb_traversal_result *out);
 
 static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
@@ -503,6 +1331,7 @@ static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_trave
     a.T = f->num_types;
   }
   const int block = 128, grid = apbDivUp(n, block);
+  h->lcListVersion = -1;  // the buffers of the cached partner lists (ensureLCLists) are reused below
   APB_CHECK(apbEnsure(h, h->nbrCount, sizeof(int) * (n + 1)));
   a.nbrCount = static_cast<int *>(h->nbrCount.p);
   a.nbr = nullptr;
@@ -510,15 +1339,64 @@ static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_trave
   int *maxDev = reinterpret_cast<int *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 32);
   a.maxCount = maxDev;
   APB_CUDA(cudaMemsetAsync(maxDev, 0, 4, h->stream));
+  const int lcKernel = apbLCKernelVariant(n);  // 0 thread (round 1), 1 warp per slot, 2 thread with deferred triplets
+  const bool lcThreadKernel = lcKernel != 1;
+  ATMWarpArgs wa;
+  wa.w.g = h->lc;
+  wa.w.cellStart = a.w.cellStart;
+  wa.w.stencilSorted = a.w.stencil + 3 * APB_MAX_STENCIL;
+  wa.w.stencilN = h->stencilN;
+  const int wgrid = static_cast<int>(std::min<int64_t>(apbDivUp(n, LCW_WARPS), 148 * 16));
   ++h->launchCount;
-  if (newton3)
+  if (!lcThreadKernel) {
+    wa.a = a;
+    wa.cap = 0;
+    if (newton3)
+      kATMCountWarp<true><<<wgrid, LCW_WARPS * 32, 0, h->stream>>>(wa);
+    else
+      kATMCountWarp<false><<<wgrid, LCW_WARPS * 32, 0, h->stream>>>(wa);
+  } else if (newton3) {
     kATMNeighbors<false, true><<<grid, block, 0, h->stream>>>(a);
-  else
+  } else {
     kATMNeighbors<false, false><<<grid, block, 0, h->stream>>>(a);
+  }
   APB_CUDA(cudaGetLastError());
   int cap = 0;
   APB_CUDA(cudaMemcpyAsync(&cap, maxDev, 4, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
+  // the warp kernel keeps the neighbours of its 8 slots in shared memory (32 B each, rounded up to full rows of 32);
+  // beyond 640 neighbours per particle the list-based thread kernels below take over
+  const int capRows = (cap + 31) / 32 * 32;
+  if (!lcThreadKernel && capRows <= 640 && capRows < 65536) {
+    if (cap < 2) return apbFinishStats(h, 0, stats, f, out);
+    wa.a = a;
+    wa.cap = capRows;
+    APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * wgrid));
+    wa.a.partials = static_cast<LJStats *>(h->partials.p);
+    const size_t smem = static_cast<size_t>(LCW_WARPS) * 32 * capRows;
+    ++h->launchCount;
+    const int wsel = (newton3 ? 4 : 0) | (mix ? 2 : 0) | (stats ? 1 : 0);
+#define ATM_WARP_LAUNCH(MIXV, STATSV, N3V)                                                                           \
+  do {                                                                                                               \
+    if (smem > 48 * 1024)                                                                                            \
+      APB_CUDA(cudaFuncSetAttribute(kATMTripletsWarp<MIXV, STATSV, N3V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    static_cast<int>(smem)));                                                        \
+    kATMTripletsWarp<MIXV, STATSV, N3V><<<wgrid, LCW_WARPS * 32, smem, h->stream>>>(wa);                             \
+  } while (0)
+    switch (wsel) {
+      case 0: ATM_WARP_LAUNCH(false, false, false); break;
+      case 1: ATM_WARP_LAUNCH(false, true, false); break;
+      case 2: ATM_WARP_LAUNCH(true, false, false); break;
+      case 3: ATM_WARP_LAUNCH(true, true, false); break;
+      case 4: ATM_WARP_LAUNCH(false, false, true); break;
+      case 5: ATM_WARP_LAUNCH(false, true, true); break;
+      case 6: ATM_WARP_LAUNCH(true, false, true); break;
+      default: ATM_WARP_LAUNCH(true, true, true); break;
+    }
+    APB_CUDA(cudaGetLastError());
+    return apbFinishStats(h, wgrid, stats, f, out);
+  }
+  // (with counts from the warp kernel the fill pass below recounts: same candidates, same result)
   a.cap = cap;
   APB_CHECK(apbEnsure(h, h->nbrList, sizeof(int) * static_cast<size_t>(std::max(cap, 1)) * n));
   a.nbr = static_cast<int *>(h->nbrList.p);
@@ -534,6 +1412,20 @@ static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_trave
   a.partials = static_cast<LJStats *>(h->partials.p);
   ++h->launchCount;
   const int sel = (newton3 ? 4 : 0) | (mix ? 2 : 0) | (stats ? 1 : 0);
+  if (lcKernel != 0 && cap < 65536) {
+    switch (sel) {
+      case 0: kATMTripletsDeferred<false, false, false><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
+      case 1: kATMTripletsDeferred<false, true, false><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
+      case 2: kATMTripletsDeferred<true, false, false><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
+      case 3: kATMTripletsDeferred<true, true, false><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
+      case 4: kATMTripletsDeferred<false, false, true><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
+      case 5: kATMTripletsDeferred<false, true, true><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
+      case 6: kATMTripletsDeferred<true, false, true><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
+      default: kATMTripletsDeferred<true, true, true><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
+    }
+    APB_CUDA(cudaGetLastError());
+    return apbFinishStats(h, grid, stats, f, out);
+  }
   switch (sel) {
     case 0: kATMTriplets<false, false><<<grid, block, 0, h->stream>>>(a); break;
     case 1: kATMTriplets<false, true><<<grid, block, 0, h->stream>>>(a); break;

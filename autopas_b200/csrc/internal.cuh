@@ -80,6 +80,11 @@ struct apb_handle_s {
   VCLGeom vcl{};
   int64_t numCells = 0;  // cells or towers
   DevBuf key, rank, count, start, perm, slotCell, scanTmp, sortK1, sortK2, sortV;
+  // gpuLinkedCells: per-slot partner lists within cutoff + skin, built on first use after a rebuild (functors.cu)
+  long long structureVersion = 0, lcListVersion = -1;
+  int lcListHalf = -1, lcListCap = 0;
+  unsigned long long scanEpoch = 0;  // chained scan (apbExclusiveScan): entries of earlier scans read as not ready
+  int64_t scanTiles = 0;             // tiles the status array holds; the ticket counter sits behind them
   int stencilN = 0;  // LC neighbour-cell offsets (incl. self at index 0)
   int stencil[APB_MAX_STENCIL][3];
   DevBuf stencilDev;
@@ -120,7 +125,7 @@ struct apb_handle_s {
   int64_t numLeavers = 0;
   DevBuf leaverIdx;
   DevBuf idStage;  // 3 x numIds doubles: staging of the by-id transfers
-  std::vector<double> leaverCols[6];
+  std::vector<double> leaverCols[APB_NUM_COLUMNS];  // every active column of the leavers
   std::vector<int64_t> leaverIds;
   std::vector<int32_t> leaverTypes;
 
@@ -312,5 +317,31 @@ __host__ __device__ inline bool apbCellCanOwn(const LCGeom &g, int cx, int cy, i
   const int o = g.cellsPerInteractionLength;
   return cx >= o && cx < g.cellsPerDim[0] - o && cy >= o && cy < g.cellsPerDim[1] - o && cz >= o &&
          cz < g.cellsPerDim[2] - o;
+}
+// Accumulators a functor did not ask for read as zero, whichever entry point produced them (the statistics kernels run
+// if either flag is set): one rule for apb_compute_interactions, apb_force_step_by_id and apb_run_steps.
+inline void apbMaskResultByFlags(apb_traversal_result &r, int32_t flags) {
+  if (!(flags & APB_FUNCTOR_CALC_GLOBALS)) {
+    r.upot_sum = 0.;
+    r.virial_sum[0] = r.virial_sum[1] = r.virial_sum[2] = 0.;
+    r.num_global_calcs_n3 = r.num_global_calcs_no_n3 = 0;
+  }
+  if (!(flags & APB_FUNCTOR_COUNT_FLOPS)) {
+    r.num_dist_calls = r.num_kernel_calls_n3 = r.num_kernel_calls_no_n3 = 0;
+    r.num_global_calcs_n3 = r.num_global_calcs_no_n3 = 0;
+  }
+}
+
+// gpuLinkedCells kernels come in three variants (lc_warp.cuh): 0 = one thread per slot, pair arithmetic inline (round 1),
+// 1 = one warp per slot, 2 = one thread per slot with deferred pair arithmetic. Default: 1 below 16 384 slots (one thread
+// per slot cannot fill 148 SMs), 2 above. APB_LC_KERNEL=thread|warp|deferred overrides.
+inline int apbLCKernelVariant(int64_t numSlots) {
+  static const int forced = [] {
+    const char *e = getenv("APB_LC_KERNEL");
+    if (!e) return -1;
+    return e[0] == 't' ? 0 : (e[0] == 'w' ? 1 : (e[0] == 'l' ? 3 : 2));
+  }();
+  if (forced >= 0) return forced;
+  return numSlots < 16384 ? 1 : 2;
 }
 #endif

@@ -8,6 +8,7 @@
 // force in registers; with newton3 the reaction on j goes through fp64 atomics (RED.ADD.F64).
 #include "internal.cuh"
 #include "lj_device.cuh"
+#include "lc_warp.cuh"
 
 // ------------------------------------------------------------------------------------------------------------------
 // block reduction of per-thread statistics into one partial per block; final pass sums partials in fixed order
@@ -176,6 +177,171 @@ __global__ void __launch_bounds__(128) kLJLinkedCells(LCArgs a) {
         a.fy[i] += fya;
         a.fz[i] += fza;
       }
+    }
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
+// The same traversal with one warp per particle slot (lc_warp.cuh): the lanes share the candidates of the stencil cells,
+// hits are compacted and evaluated on full rows. Counters, ownership weights and the halo-cell rules are those of
+// kLJLinkedCells above. Forces of slot i are reduced over the lanes with shuffles; newton3 scatters -f to the partner
+// with one RED per component. The warps of a block take consecutive slots (same cell: the candidate loads hit in L1)
+// and stride over the slots.
+template <bool MIX, bool STATS, bool N3>
+__global__ void __launch_bounds__(LCW_WARPS * 32) kLJLinkedCellsWarp(LCArgs a, LCWarpGeom w) {
+  __shared__ int queues[LCW_WARPS][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  LJStats st;
+  ljStatsZero(st);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * LCW_WARPS + warp; i < a.n; i += static_cast<int64_t>(gridDim.x) * LCW_WARPS) {
+    const int ownI = a.own[i];
+    if (ownI == APB_OWN_DUMMY) continue;
+    const LCGeom &g = a.g;
+    const int c = a.slotCell[i];
+    const int cx = c % g.cellsPerDim[0], cy = (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+              cz = c / (g.cellsPerDim[0] * g.cellsPerDim[1]);
+    const bool canOwnI = apbCellCanOwn(g, cx, cy, cz);
+    if (!(canOwnI || N3 || a.processHaloCells)) continue;
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+    const int ti = MIX ? a.type[i] : 0;
+    const double wI = ownI == APB_OWN_OWNED ? 1. : 0.;
+    const int self0 = a.cellStart[c], self1 = a.cellStart[c + 1];
+    double fxa = 0., fya = 0., fza = 0.;
+    lcWarpWalk<N3>(
+        w, i, c, !canOwnI, queues[warp],
+        [&](int j) {
+          if (!N3 && j == i) return false;
+          if (a.own[j] == APB_OWN_DUMMY) return false;
+          const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+          const bool self = j >= self0 && j < self1;
+          // counters: a same-cell pair is one newton3 evaluation in the reference, whatever the newton3 flag
+          if (STATS && (!self || N3 || j > i)) ++st.dist;
+          return ljDist2(drx, dry, drz) <= a.p.cutoff2;
+        },
+        [&](int j) {
+          const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+          const double dr2 = ljDist2(drx, dry, drz);
+          double upot6;
+          const double fac = ljEval<MIX>(a.p, dr2, ti, MIX ? a.type[j] : 0, upot6);
+          const double fx = drx * fac, fy = dry * fac, fz = drz * fac;
+          fxa += fx;
+          fya += fy;
+          fza += fz;
+          if (N3) {
+            atomicAdd(&a.fx[j], -fx);
+            atomicAdd(&a.fy[j], -fy);
+            atomicAdd(&a.fz[j], -fz);
+          }
+          if (STATS) {
+            const double wJ = a.own[j] == APB_OWN_OWNED ? 1. : 0.;
+            const double wgt = N3 ? wI + wJ : wI;
+            st.upot += upot6 * wgt;
+            st.vir[0] += drx * fx * wgt;
+            st.vir[1] += dry * fy * wgt;
+            st.vir[2] += drz * fz * wgt;
+            const bool self = j >= self0 && j < self1;
+            if (!self || N3 || j > i) {
+              if (N3 || self) {
+                ++st.kN3;
+                ++st.gN3;
+              } else {
+                ++st.kNoN3;
+                ++st.gNoN3;
+              }
+            }
+          }
+        });
+    fxa = lcWarpSum(fxa);
+    fya = lcWarpSum(fya);
+    fza = lcWarpSum(fza);
+    if (lane == 0) {
+      if (N3) {
+        atomicAdd(&a.fx[i], fxa);
+        atomicAdd(&a.fy[i], fya);
+        atomicAdd(&a.fz[i], fza);
+      } else {
+        a.fx[i] += fxa;
+        a.fy[i] += fya;
+        a.fz[i] += fza;
+      }
+    }
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
+// One thread per slot with the pair arithmetic deferred through per-lane hit queues (lcDeferredWalk, lc_warp.cuh): the
+// variant for systems that fill the GPU. Same rules as above.
+template <bool MIX, bool STATS, bool N3>
+__global__ void __launch_bounds__(LCD_BLOCK) kLJLinkedCellsDeferred(LCArgs a) {
+  __shared__ int queue[LCD_DEPTH * LCD_BLOCK];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  LJStats st;
+  ljStatsZero(st);
+  const LCGeom &g = a.g;
+  const int ownI = i < a.n ? a.own[i] : APB_OWN_DUMMY;
+  const int c = ownI != APB_OWN_DUMMY ? a.slotCell[i] : 0;
+  const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
+                                     c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
+  const bool part = ownI != APB_OWN_DUMMY && (canOwnI || N3 || a.processHaloCells);
+  const int64_t ii = part ? i : 0;
+  const double xi = a.x[ii], yi = a.y[ii], zi = a.z[ii];
+  const int ti = MIX ? a.type[ii] : 0;
+  const double wI = ownI == APB_OWN_OWNED ? 1. : 0.;
+  const int self0 = a.cellStart[c], self1 = a.cellStart[c + 1];
+  double fxa = 0., fya = 0., fza = 0.;
+  lcDeferredWalk<N3>(
+      g, a.cellStart, a.stencil + 3 * APB_MAX_STENCIL, a.stencilN, part, i, c, !canOwnI, queue,
+      [&](int j) {
+        if (!N3 && j == i) return false;
+        if (a.own[j] == APB_OWN_DUMMY) return false;
+        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+        const bool self = j >= self0 && j < self1;
+        // counters: a same-cell pair is one newton3 evaluation in the reference, whatever the newton3 flag
+        if (STATS && (!self || N3 || j > i)) ++st.dist;
+        return ljDist2(drx, dry, drz) <= a.p.cutoff2;
+      },
+      [&](int j) {
+        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+        const double dr2 = ljDist2(drx, dry, drz);
+        double upot6;
+        const double fac = ljEval<MIX>(a.p, dr2, ti, MIX ? a.type[j] : 0, upot6);
+        const double fx = drx * fac, fy = dry * fac, fz = drz * fac;
+        fxa += fx;
+        fya += fy;
+        fza += fz;
+        if (N3) {
+          atomicAdd(&a.fx[j], -fx);
+          atomicAdd(&a.fy[j], -fy);
+          atomicAdd(&a.fz[j], -fz);
+        }
+        if (STATS) {
+          const double wJ = a.own[j] == APB_OWN_OWNED ? 1. : 0.;
+          const double wgt = N3 ? wI + wJ : wI;
+          st.upot += upot6 * wgt;
+          st.vir[0] += drx * fx * wgt;
+          st.vir[1] += dry * fy * wgt;
+          st.vir[2] += drz * fz * wgt;
+          const bool self = j >= self0 && j < self1;
+          if (!self || N3 || j > i) {
+            if (N3 || self) {
+              ++st.kN3;
+              ++st.gN3;
+            } else {
+              ++st.kNoN3;
+              ++st.gNoN3;
+            }
+          }
+        }
+      });
+  if (part) {
+    if (N3) {
+      atomicAdd(&a.fx[i], fxa);
+      atomicAdd(&a.fy[i], fya);
+      atomicAdd(&a.fz[i], fza);
+    } else {
+      a.fx[i] += fxa;
+      a.fy[i] += fya;
+      a.fz[i] += fza;
     }
   }
   if (STATS) ljStatsBlockReduce(st, a.partials);
@@ -372,15 +538,7 @@ int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f
     APB_CUDA(cudaMemcpyAsync(&host, h->result.p, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
   }
   APB_CUDA(cudaStreamSynchronize(h->stream));
-  if (!(f->flags & APB_FUNCTOR_CALC_GLOBALS)) {
-    host.upot_sum = 0.;
-    host.virial_sum[0] = host.virial_sum[1] = host.virial_sum[2] = 0.;
-    host.num_global_calcs_n3 = host.num_global_calcs_no_n3 = 0;
-  }
-  if (!(f->flags & APB_FUNCTOR_COUNT_FLOPS)) {
-    host.num_dist_calls = host.num_kernel_calls_n3 = host.num_kernel_calls_no_n3 = 0;
-    host.num_global_calcs_n3 = host.num_global_calcs_no_n3 = 0;
-  }
+  apbMaskResultByFlags(host, f->flags);
   if (out) *out = host;
   return APB_OK;
 }
@@ -412,8 +570,13 @@ int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3,
   const int64_t n = h->nslots;
   if (traversal == APB_TRAVERSAL_GPUVCL_PRUNED) return apbComputeLJPruned(h, f, p, mix, stats, n3, out);
   const int block = 128;
-  const int grid = apbDivUp(n, block);
+  int grid = apbDivUp(n, block);
   if (n == 0) return apbFinishStats(h, 0, stats, f, out);
+  // gpuLinkedCells kernel variant: one warp per slot while the system is too small to fill the GPU with one thread per
+  // slot, else one thread per slot with deferred pair arithmetic; APB_LC_KERNEL=thread|warp|deferred overrides (A/B runs)
+  const int lcKernel = apbLCKernelVariant(n);
+  if (h->cfg.container == APB_CONTAINER_LINKED_CELLS && lcKernel == 1)
+    grid = static_cast<int>(std::min<int64_t>(apbDivUp(n, LCW_WARPS), 148 * 16));
   APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * grid));
   if (h->cfg.container == APB_CONTAINER_LINKED_CELLS) {
     LCArgs a;
@@ -436,7 +599,19 @@ int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3,
     a.processHaloCells = (f->flags & APB_FUNCTOR_COUNT_FLOPS) ? 1 : 0;
     a.p = p;
     a.partials = static_cast<LJStats *>(h->partials.p);
-    LJ_DISPATCH(kLJLinkedCells, grid, block, a);
+    if (lcKernel == 0) {
+      LJ_DISPATCH(kLJLinkedCells, grid, block, a);
+    } else if (lcKernel == 2) {
+      LJ_DISPATCH(kLJLinkedCellsDeferred, grid, LCD_BLOCK, a);
+    } else {
+      LCWarpGeom w;
+      w.g = h->lc;
+      w.cellStart = a.cellStart;
+      w.stencilSorted = a.stencil + 3 * APB_MAX_STENCIL;
+      w.stencilN = h->stencilN;
+#define LJ_LCW_ARGS a, w
+      LJ_DISPATCH(kLJLinkedCellsWarp, grid, LCW_WARPS * 32, LJ_LCW_ARGS);
+    }
   } else {
     VCLArgs a;
     a.n = n;

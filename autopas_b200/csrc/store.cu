@@ -92,66 +92,35 @@ int apbInitKernelAttributes(apb_handle h) {
 // exclusive scan (int32), three-phase, recursive over block sums. HBM-bound: reads n, writes n (+ n/1024 sums).
 // ------------------------------------------------------------------------------------------------------------------
 #define SCAN_BLOCK 1024
-__global__ void __launch_bounds__(SCAN_BLOCK) kScanBlock(const int *__restrict__ in, int *__restrict__ out,
-                                                         int *__restrict__ blockSums, int64_t n) {
+// Exclusive scan in ONE launch for any length: chained tiles with decoupled look-back. A block takes the next tile by
+// ticket (atomicInc wraps to zero after the last tile, so the counter needs no reset), scans its 4096 elements with
+// coalesced 16-byte loads, publishes {epoch, flag, value} for its tile and walks back over its predecessors' entries
+// until it meets an inclusive prefix. Entries of earlier scans carry an older epoch and read as "not ready", so the
+// status array is never cleared. (Round 1 scanned up to 2^18 elements with one block - strided, uncoalesced, 43 us for
+// the 60 k clusters of a 2 M-particle container, nine times per rebuild - and longer arrays with four launches.)
+#define SCAN_TILE 4096
+__device__ __forceinline__ unsigned long long scanPack(unsigned long long epoch, unsigned flag, int value) {
+  return (epoch << 34) | (static_cast<unsigned long long>(flag) << 32) | static_cast<unsigned>(value);
+}
+__global__ void __launch_bounds__(1024) kScanChained(const int *__restrict__ in, int *__restrict__ out, int64_t n,
+                                                     long long *total, unsigned long long *status, unsigned *ticket,
+                                                     unsigned numTiles, unsigned long long epoch) {
   __shared__ int warpSums[32];
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * SCAN_BLOCK + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int v = i < n ? in[i] : 0;
-  int incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) warpSums[warp] = incl;
+  __shared__ unsigned sTile;
+  __shared__ int sPrefix;
+  if (threadIdx.x == 0) sTile = atomicInc(ticket, numTiles - 1);
   __syncthreads();
-  if (warp == 0) {
-    int w = warpSums[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += t;
-    }
-    warpSums[lane] = w;  // inclusive over warps
+  const unsigned tile = sTile;
+  const int64_t base = static_cast<int64_t>(tile) * SCAN_TILE + 4 * threadIdx.x;
+  int v[4] = {0, 0, 0, 0};
+  if (base + 3 < n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    const int4 q = *reinterpret_cast<const int4 *>(in + base);
+    v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+  } else {
+    for (int k = 0; k < 4; ++k)
+      if (base + k < n) v[k] = in[base + k];
   }
-  __syncthreads();
-  const int warpOffset = warp == 0 ? 0 : warpSums[warp - 1];
-  if (i < n) out[i] = warpOffset + incl - v;
-  if (threadIdx.x == SCAN_BLOCK - 1) blockSums[blockIdx.x] = warpOffset + incl;
-}
-
-__global__ void kScanAddOffsets(int *__restrict__ out, const int *__restrict__ blockOffsets, int64_t n) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * SCAN_BLOCK + threadIdx.x;
-  if (i < n) out[i] += blockOffsets[blockIdx.x];
-}
-
-__global__ void kScanTotal(const int *in, const int *out, int64_t n, long long *total) {
-  *total = n > 0 ? static_cast<long long>(out[n - 1]) + in[n - 1] : 0;
-}
-
-static int scanRec(apb_handle h, const int *in, int *out, int64_t n, int *scratch) {
-  const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  int *sums = scratch;
-  ++h->launchCount, kScanBlock<<<static_cast<unsigned>(nb), SCAN_BLOCK, 0, h->stream>>>(in, out, sums, n);
-  if (nb > 1) {
-    int *sumsScanned = scratch + nb;
-    APB_CHECK(scanRec(h, sums, sumsScanned, nb, scratch + 2 * nb));
-    ++h->launchCount, kScanAddOffsets<<<static_cast<unsigned>(nb), SCAN_BLOCK, 0, h->stream>>>(out, sumsScanned, n);
-  }
-  return APB_OK;
-}
-
-// Arrays of up to 2^18 elements (towers, tiles, warps, clusters of a 1 M-particle container) are scanned by ONE block
-// in one launch, total included: the rebuild chain is launch-latency bound on slow hosts, and the recursive version
-// costs four launches per scan.
-#define SCAN_SMALL_MAX (1 << 18)
-__global__ void __launch_bounds__(1024) kScanSmall(const int *__restrict__ in, int *__restrict__ out, int n, long long *total) {
-  __shared__ int warpSums[32];
-  const int chunk = (n + 1023) / 1024;
-  const int b = min(static_cast<int>(threadIdx.x) * chunk, n), e = min(b + chunk, n);
-  int sum = 0;
-  for (int i = b; i < e; ++i) sum += in[i];
+  const int sum = v[0] + v[1] + v[2] + v[3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = sum;
 #pragma unroll
@@ -171,27 +140,65 @@ __global__ void __launch_bounds__(1024) kScanSmall(const int *__restrict__ in, i
     warpSums[lane] = w;
   }
   __syncthreads();
-  int run = (warp == 0 ? 0 : warpSums[warp - 1]) + incl - sum;
-  for (int i = b; i < e; ++i) {
-    const int v = in[i];  // read before the write: in and out may alias
-    out[i] = run;
-    run += v;
+  if (threadIdx.x == 0) {
+    const int tileTotal = warpSums[31];
+    int prefix = 0;
+    volatile unsigned long long *st = status;
+    if (tile == 0) {
+      st[0] = scanPack(epoch, 2u, tileTotal);
+    } else {
+      st[tile] = scanPack(epoch, 1u, tileTotal);
+      __threadfence();
+      for (int t = static_cast<int>(tile) - 1;; --t) {
+        unsigned long long w;
+        do {
+          w = st[t];
+        } while ((w >> 34) != epoch || ((w >> 32) & 3u) == 0u);
+        prefix += static_cast<int>(static_cast<unsigned>(w));
+        if (((w >> 32) & 3u) == 2u) break;
+      }
+      st[tile] = scanPack(epoch, 2u, prefix + tileTotal);
+    }
+    sPrefix = prefix;
+    if (total && tile == numTiles - 1) *total = static_cast<long long>(prefix) + tileTotal;
   }
-  if (total && threadIdx.x == 1023) *total = warpSums[31];
+  __syncthreads();
+  int run = sPrefix + (warp == 0 ? 0 : warpSums[warp - 1]) + incl - sum;
+  if (base + 3 < n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    int4 q;
+    q.x = run;
+    q.y = run + v[0];
+    q.z = q.y + v[1];
+    q.w = q.z + v[2];
+    *reinterpret_cast<int4 *>(out + base) = q;
+  } else {
+    for (int k = 0; k < 4; ++k)
+      if (base + k < n) {
+        out[base + k] = run;
+        run += v[k];
+      }
+  }
 }
 
 int apbExclusiveScan(apb_handle h, const int *in, int *out, int64_t n, long long *totalDev) {
-  if (n > 0 && n <= SCAN_SMALL_MAX) {
-    ++h->launchCount, kScanSmall<<<1, 1024, 0, h->stream>>>(in, out, static_cast<int>(n), totalDev);
-    APB_CUDA(cudaGetLastError());
+  if (n <= 0) {
+    if (totalDev) APB_CUDA(cudaMemsetAsync(totalDev, 0, sizeof(long long), h->stream));
     return APB_OK;
   }
-  if (n > 0) {
-    const int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    APB_CHECK(apbEnsure(h, h->scanTmp, sizeof(int) * (4 * nb + 64)));
-    APB_CHECK(scanRec(h, in, out, n, static_cast<int *>(h->scanTmp.p)));
+  const int64_t numTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  const size_t need = sizeof(unsigned long long) * (numTiles + 2);
+  if (h->scanTmp.cap < need) {  // status array + ticket counter behind it; zero = an epoch no scan ever uses
+    const size_t before = h->scanTmp.cap;
+    APB_CHECK(apbEnsure(h, h->scanTmp, need + 4096));
+    (void)before;
+    APB_CUDA(cudaMemsetAsync(h->scanTmp.p, 0, h->scanTmp.cap, h->stream));
+    h->scanTiles = static_cast<int64_t>(h->scanTmp.cap / sizeof(unsigned long long)) - 1;
   }
-  if (totalDev) ++h->launchCount, kScanTotal<<<1, 1, 0, h->stream>>>(in, out, n, totalDev);
+  unsigned long long *status = static_cast<unsigned long long *>(h->scanTmp.p);
+  unsigned *ticket = reinterpret_cast<unsigned *>(status + h->scanTiles);
+  if (((++h->scanEpoch) & ((1ULL << 30) - 1)) == 0) ++h->scanEpoch;  // zero is the cleared state
+  ++h->launchCount, kScanChained<<<static_cast<unsigned>(numTiles), 1024, 0, h->stream>>>(
+      in, out, n, totalDev, status, ticket, static_cast<unsigned>(numTiles), h->scanEpoch & ((1ULL << 30) - 1));
   APB_CUDA(cudaGetLastError());
   return APB_OK;
 }
@@ -1014,23 +1021,32 @@ extern "C" int apb_update_container(apb_handle h, int32_t keep, int64_t *out_num
   const int64_t nl = hostTotals[0];
   h->numLeavers = nl;
   if (nl > 0) {
-    // the leavers' ownership was set to dummy above; their data is still in place. Gather and copy out.
-    APB_CHECK(apbEnsure(h, h->sortK1, sizeof(double) * nl));
+    // the leavers' ownership was set to dummy above; their data is still in place. Gather every active column, ids and
+    // types into one staging buffer and copy it out with one transfer.
+    int numActive = 0;
+    for (int k = 0; k < APB_NUM_COLUMNS; ++k) numActive += h->active[k] ? 1 : 0;
+    APB_CHECK(apbEnsure(h, h->sortK1, sizeof(double) * nl * (numActive + 2)));
     double *tmp = static_cast<double *>(h->sortK1.p);
-    for (int k = 0; k < 6; ++k) {
-      h->leaverCols[k].resize(nl);
-      ++h->launchCount, kGatherD<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->col[APB_COL_X + k], tmp);
-      APB_CUDA(cudaMemcpyAsync(h->leaverCols[k].data(), tmp, sizeof(double) * nl, cudaMemcpyDeviceToHost, h->stream));
-      APB_CUDA(cudaStreamSynchronize(h->stream));
-    }
+    std::vector<double> stage(static_cast<size_t>(nl) * (numActive + 2));
+    int q = 0;
+    for (int k = 0; k < APB_NUM_COLUMNS; ++k)
+      if (h->active[k])
+        ++h->launchCount, kGatherD<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->col[k], tmp + static_cast<size_t>(q++) * nl);
+    ++h->launchCount, kGatherI64<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->id, reinterpret_cast<int64_t *>(tmp + static_cast<size_t>(numActive) * nl));
+    ++h->launchCount, kGatherI32<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->type, reinterpret_cast<int32_t *>(tmp + static_cast<size_t>(numActive + 1) * nl));
+    APB_CUDA(cudaGetLastError());
+    APB_CUDA(cudaMemcpyAsync(stage.data(), tmp, sizeof(double) * stage.size(), cudaMemcpyDeviceToHost, h->stream));
+    APB_CUDA(cudaStreamSynchronize(h->stream));
+    q = 0;
+    for (int k = 0; k < APB_NUM_COLUMNS; ++k)
+      if (h->active[k]) {
+        h->leaverCols[k].assign(stage.begin() + static_cast<size_t>(q) * nl, stage.begin() + static_cast<size_t>(q + 1) * nl);
+        ++q;
+      }
     h->leaverIds.resize(nl);
     h->leaverTypes.resize(nl);
-    ++h->launchCount, kGatherI64<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->id, reinterpret_cast<int64_t *>(tmp));
-    APB_CUDA(cudaMemcpyAsync(h->leaverIds.data(), tmp, 8 * nl, cudaMemcpyDeviceToHost, h->stream));
-    APB_CUDA(cudaStreamSynchronize(h->stream));
-    ++h->launchCount, kGatherI32<<<apbDivUp(nl, 256), 256, 0, h->stream>>>(nl, leaverIdx, h->type, reinterpret_cast<int32_t *>(tmp));
-    APB_CUDA(cudaMemcpyAsync(h->leaverTypes.data(), tmp, 4 * nl, cudaMemcpyDeviceToHost, h->stream));
-    APB_CUDA(cudaStreamSynchronize(h->stream));
+    std::memcpy(h->leaverIds.data(), stage.data() + static_cast<size_t>(numActive) * nl, 8 * nl);
+    std::memcpy(h->leaverTypes.data(), stage.data() + static_cast<size_t>(numActive + 1) * nl, 4 * nl);
   }
   if (!keep) {
     // compact the kept (owned, in box) particles, preserving order
@@ -1063,6 +1079,15 @@ extern "C" int apb_get_leavers(apb_handle h, double *x, double *y, double *z, do
     if (dst[k] && nl > 0) std::memcpy(dst[k], h->leaverCols[k].data(), sizeof(double) * nl);
   if (ids && nl > 0) std::memcpy(ids, h->leaverIds.data(), 8 * nl);
   if (types && nl > 0) std::memcpy(types, h->leaverTypes.data(), 4 * nl);
+  return APB_OK;
+}
+
+extern "C" int apb_get_leaver_column(apb_handle h, int32_t column, double *dst) {
+  APB_ENTRY(h);
+  if (column < 0 || column >= APB_NUM_COLUMNS || !h->active[column])
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_get_leaver_column: column not part of this particle kind");
+  if (!dst) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_get_leaver_column: null destination");
+  if (h->numLeavers > 0) std::memcpy(dst, h->leaverCols[column].data(), sizeof(double) * h->numLeavers);
   return APB_OK;
 }
 

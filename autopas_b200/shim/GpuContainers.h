@@ -24,6 +24,7 @@
 #include <mutex>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "autopas/baseFunctors/PairwiseFunctor.h"
@@ -41,6 +42,15 @@
 #include "molecularDynamicsLibrary/AxilrodTellerMutoFunctor.h"
 #include "molecularDynamicsLibrary/LJFunctor.h"
 #include "molecularDynamicsLibrary/ParticlePropertiesLibrary.h"
+#if defined(MD_FLEXIBLE_MODE) && defined(MULTISITE) && MD_FLEXIBLE_MODE == MULTISITE
+#define AUTOPAS_B200_MULTISITE 1
+#include "molecularDynamicsLibrary/LJMultisiteFunctor.h"
+#endif
+#if __has_include("SPHLibrary/SPHCalcDensityFunctor.h")
+#define AUTOPAS_B200_SPH 1
+#include "SPHLibrary/SPHCalcDensityFunctor.h"
+#include "SPHLibrary/SPHCalcHydroForceFunctor.h"
+#endif
 
 namespace autopas_b200 {
 
@@ -334,6 +344,7 @@ class GpuATMFunctor
 
  public:
   static constexpr bool apbHasGpuKernel = true;
+  static constexpr bool apbLinkedCellsOnly = true;
 
   explicit GpuATMFunctor(double cutoff) requires(not useMixing)
       : autopas::TriwiseFunctor<Particle_T, Self>(cutoff), _cpu(cutoff), _cutoff(cutoff) {}
@@ -423,6 +434,200 @@ class GpuATMFunctor
   bool _postProcessed = false;
 };
 
+#ifdef AUTOPAS_B200_SPH
+// ---------------------------------------------------------------------------------------------------------------------
+// GpuSPHCalcDensityFunctor / GpuSPHCalcHydroForceFunctor
+// ---------------------------------------------------------------------------------------------------------------------
+/// Common part of the two SPH wrappers: the CPU interfaces forward to the wrapped reference functor `Cpu_T`
+/// (SPHCalcDensityFunctor.h:20 / SPHCalcHydroForceFunctor.h:19; no template flags, no globals, functor cutoff 0 - the
+/// kernel support 2.5 h is applied per pair); the GPU traversals gpulc_c08 / gpulc_c18 run kSPHDensityLC / kSPHHydroLC
+/// on gpuLinkedCells with SPHParticle storage and write density, or acceleration / engDot / vSigMax, on the device.
+template <class Particle_T, class Cpu_T, class Self_T, int apbKind>
+class GpuSPHFunctorBase : public autopas::PairwiseFunctor<Particle_T, Self_T> {
+  using SoAArraysType = typename Particle_T::SoAArraysType;
+
+ public:
+  static constexpr bool apbHasGpuKernel = true;
+  static constexpr bool apbLinkedCellsOnly = true;
+  GpuSPHFunctorBase() : autopas::PairwiseFunctor<Particle_T, Self_T>(0.) {}
+  bool isRelevantForTuning() final { return true; }
+  bool allowsNewton3() final { return true; }
+  bool allowsNonNewton3() final { return true; }
+  void AoSFunctor(Particle_T &i, Particle_T &j, bool newton3) final { _cpu.AoSFunctor(i, j, newton3); }
+  void SoAFunctorSingle(autopas::SoAView<SoAArraysType> soa, bool newton3) final { _cpu.SoAFunctorSingle(soa, newton3); }
+  void SoAFunctorPair(autopas::SoAView<SoAArraysType> soa1, autopas::SoAView<SoAArraysType> soa2, bool newton3) final {
+    _cpu.SoAFunctorPair(soa1, soa2, newton3);
+  }
+  void SoAFunctorVerlet(autopas::SoAView<SoAArraysType> soa, const size_t indexFirst,
+                        const std::vector<size_t, autopas::AlignedAllocator<size_t>> &neighborList, bool newton3) final {
+    _cpu.SoAFunctorVerlet(soa, indexFirst, neighborList, newton3);
+  }
+  constexpr static auto getNeededAttr() { return Cpu_T::getNeededAttr(); }
+  constexpr static auto getNeededAttr(std::false_type) { return Cpu_T::getNeededAttr(std::false_type()); }
+  constexpr static auto getComputedAttr() { return Cpu_T::getComputedAttr(); }
+
+  FunctorDescriptor apbDescribe() {
+    FunctorDescriptor d;
+    d.functor.kind = apbKind;
+    return d;
+  }
+  void apbDeposit(const apb_traversal_result &) {}  // no globals (SPHCalcDensityFunctor.h / SPHCalcHydroForceFunctor.h)
+
+ protected:
+  Cpu_T _cpu;
+};
+
+template <class Particle_T>
+class GpuSPHCalcDensityFunctor
+    : public GpuSPHFunctorBase<Particle_T, sphLib::SPHCalcDensityFunctor<Particle_T>, GpuSPHCalcDensityFunctor<Particle_T>,
+                               APB_FUNCTOR_SPH_DENSITY> {
+ public:
+  std::string getName() final { return "GpuSPHDensityFunctor"; }
+  /// SPHCalcDensityFunctor.h:65-72
+  static unsigned long getNumFlopsPerKernelCall() { return sphLib::SPHCalcDensityFunctor<Particle_T>::getNumFlopsPerKernelCall(); }
+};
+
+template <class Particle_T>
+class GpuSPHCalcHydroForceFunctor
+    : public GpuSPHFunctorBase<Particle_T, sphLib::SPHCalcHydroForceFunctor<Particle_T>,
+                               GpuSPHCalcHydroForceFunctor<Particle_T>, APB_FUNCTOR_SPH_HYDRO> {
+ public:
+  std::string getName() final { return "GpuSPHHydroForceFunctor"; }
+};
+#endif  // AUTOPAS_B200_SPH
+
+#ifdef AUTOPAS_B200_MULTISITE
+// ---------------------------------------------------------------------------------------------------------------------
+// GpuLJMultisiteFunctor
+// ---------------------------------------------------------------------------------------------------------------------
+/// autopas::PairwiseFunctor around mdLib::LJMultisiteFunctor (LJMultisiteFunctor.h:44-47, same template flags; the
+/// reference library offers it only in its MULTISITE build mode, so does this wrapper). GPU traversal: gpulc_c08 /
+/// gpulc_c18 on gpuLinkedCells with MultisiteMoleculeLJ storage (kLJMultisiteLC: forces and torques on the device).
+/// Site geometry and site types come from the ParticlePropertiesLibrary (getSitePositions / getSiteTypes, :186-196)
+/// when mixing is used, else from setParticleProperties (:629-640).
+template <class Particle_T, bool applyShift = false, bool useMixing = false,
+          autopas::FunctorN3Modes useNewton3 = autopas::FunctorN3Modes::Both, bool calculateGlobals = false,
+          bool relevantForTuning = true>
+class GpuLJMultisiteFunctor
+    : public autopas::PairwiseFunctor<Particle_T, GpuLJMultisiteFunctor<Particle_T, applyShift, useMixing, useNewton3,
+                                                                        calculateGlobals, relevantForTuning>> {
+  using Self = GpuLJMultisiteFunctor<Particle_T, applyShift, useMixing, useNewton3, calculateGlobals, relevantForTuning>;
+  using Cpu = mdLib::LJMultisiteFunctor<Particle_T, applyShift, useMixing, useNewton3, calculateGlobals, relevantForTuning>;
+  using SoAArraysType = typename Particle_T::SoAArraysType;
+
+ public:
+  static constexpr bool apbHasGpuKernel = true;
+  static constexpr bool apbLinkedCellsOnly = true;
+
+  explicit GpuLJMultisiteFunctor(double cutoff) requires(not useMixing)
+      : autopas::PairwiseFunctor<Particle_T, Self>(cutoff), _cpu(cutoff), _cutoff(cutoff) {}
+  GpuLJMultisiteFunctor(double cutoff, ParticlePropertiesLibrary<double, size_t> &ppl) requires(useMixing)
+      : autopas::PairwiseFunctor<Particle_T, Self>(cutoff), _cpu(cutoff, ppl), _cutoff(cutoff), _ppl(&ppl) {}
+
+  std::string getName() final { return "GpuLJMultisiteFunctor"; }
+  bool isRelevantForTuning() final { return relevantForTuning; }
+  bool allowsNewton3() final { return _cpu.allowsNewton3(); }
+  bool allowsNonNewton3() final { return _cpu.allowsNonNewton3(); }
+  void AoSFunctor(Particle_T &i, Particle_T &j, bool newton3) final { _cpu.AoSFunctor(i, j, newton3); }
+  void SoAFunctorSingle(autopas::SoAView<SoAArraysType> soa, bool newton3) final { _cpu.SoAFunctorSingle(soa, newton3); }
+  void SoAFunctorPair(autopas::SoAView<SoAArraysType> soa1, autopas::SoAView<SoAArraysType> soa2, bool newton3) final {
+    _cpu.SoAFunctorPair(soa1, soa2, newton3);
+  }
+  void SoAFunctorVerlet(autopas::SoAView<SoAArraysType> soa, const size_t indexFirst,
+                        const std::vector<size_t, autopas::AlignedAllocator<size_t>> &neighborList, bool newton3) final {
+    _cpu.SoAFunctorVerlet(soa, indexFirst, neighborList, newton3);
+  }
+  constexpr static auto getNeededAttr() { return Cpu::getNeededAttr(); }
+  constexpr static auto getNeededAttr(std::false_type) { return Cpu::getNeededAttr(std::false_type()); }
+  constexpr static auto getComputedAttr() { return Cpu::getComputedAttr(); }
+  constexpr static bool getMixing() { return useMixing; }
+
+  void setParticleProperties(double epsilon24, double sigmaSquared, std::vector<std::array<double, 3>> sitePositionsLJ) {
+    _cpu.setParticleProperties(epsilon24, sigmaSquared, sitePositionsLJ);
+    _epsilon24 = epsilon24;
+    _sigmaSquared = sigmaSquared;
+    _sitePositions = std::move(sitePositionsLJ);
+  }
+  void initTraversal() final {
+    _cpu.initTraversal();
+    _gpuRaw = {};
+    _gpuUpot = _gpuVirial = 0.;
+    _postProcessed = false;
+  }
+  /// same normalisation as LJFunctor (LJMultisiteFunctor.h:725-750)
+  void endTraversal(bool newton3) final {
+    if (_postProcessed) {
+      autopas::utils::ExceptionHandler::exception(
+          "Already postprocessed, endTraversal(bool newton3) was called twice without calling initTraversal().");
+    }
+    _cpu.endTraversal(newton3);
+    if constexpr (calculateGlobals) apb_lj_end_traversal(&_gpuRaw, &_gpuUpot, &_gpuVirial);
+    _postProcessed = true;
+  }
+  double getPotentialEnergy() { return _cpu.getPotentialEnergy() + _gpuUpot; }  // throws like the reference if misused
+  double getVirial() { return _cpu.getVirial() + _gpuVirial; }
+
+  FunctorDescriptor apbDescribe() {
+    FunctorDescriptor d;
+    d.functor.kind = APB_FUNCTOR_LJ_MULTISITE;
+    d.functor.flags = (applyShift ? APB_FUNCTOR_APPLY_SHIFT : 0) | APB_FUNCTOR_USE_MIXING |
+                      (calculateGlobals ? APB_FUNCTOR_CALC_GLOBALS : 0);
+    d.functor.cutoff = _cutoff;
+    d.siteStart.push_back(0);
+    if constexpr (useMixing) {
+      const auto T = _ppl->getNumberRegisteredSiteTypes();
+      d.mixingTable.resize(T * T * 3);
+      for (size_t i = 0; i < T; ++i)
+        for (size_t j = 0; j < T; ++j) {
+          d.mixingTable[3 * (i * T + j) + 0] = _ppl->getMixing24Epsilon(i, j);
+          d.mixingTable[3 * (i * T + j) + 1] = _ppl->getMixingSigmaSquared(i, j);
+          d.mixingTable[3 * (i * T + j) + 2] = applyShift ? _ppl->getMixingShift6(i, j) : 0.;
+        }
+      d.functor.num_types = static_cast<int32_t>(T);
+      const size_t numMolTypes = static_cast<size_t>(_ppl->getNumberRegisteredMolTypes());
+      for (size_t m = 0; m < numMolTypes; ++m) {
+        const auto pos = _ppl->getSitePositions(m);
+        const auto types = _ppl->getSiteTypes(m);
+        for (size_t k = 0; k < pos.size(); ++k) {
+          d.sitePositions.insert(d.sitePositions.end(), pos[k].begin(), pos[k].end());
+          d.siteTypes.push_back(static_cast<int32_t>(types[k]));
+        }
+        d.siteStart.push_back(static_cast<int32_t>(d.siteTypes.size()));
+      }
+    } else {
+      const double shift6 = applyShift ? ParticlePropertiesLibrary<double, size_t>::calcShift6(_epsilon24, _sigmaSquared, _cutoff * _cutoff) : 0.;
+      d.mixingTable = {_epsilon24, _sigmaSquared, shift6};
+      d.functor.num_types = 1;
+      for (const auto &p : _sitePositions) {
+        d.sitePositions.insert(d.sitePositions.end(), p.begin(), p.end());
+        d.siteTypes.push_back(0);
+      }
+      d.siteStart.push_back(static_cast<int32_t>(d.siteTypes.size()));
+    }
+    d.functor.mixing_table = d.mixingTable.data();
+    d.functor.num_mol_types = static_cast<int32_t>(d.siteStart.size() - 1);
+    d.functor.site_start = d.siteStart.data();
+    d.functor.site_positions = d.sitePositions.data();
+    d.functor.site_types = d.siteTypes.data();
+    return d;
+  }
+  void apbDeposit(const apb_traversal_result &raw) {
+    _gpuRaw.upot_sum += raw.upot_sum;
+    for (int d = 0; d < 3; ++d) _gpuRaw.virial_sum[d] += raw.virial_sum[d];
+  }
+
+ private:
+  Cpu _cpu;
+  double _cutoff;
+  ParticlePropertiesLibrary<double, size_t> *_ppl = nullptr;
+  double _epsilon24 = 0., _sigmaSquared = 0.;
+  std::vector<std::array<double, 3>> _sitePositions;
+  apb_traversal_result _gpuRaw{};
+  double _gpuUpot = 0., _gpuVirial = 0.;
+  bool _postProcessed = false;
+};
+#endif  // AUTOPAS_B200_MULTISITE
+
 template <class F>
 concept HasGpuKernel = requires(F &f) {
   { f.apbDescribe() } -> std::same_as<FunctorDescriptor>;
@@ -449,6 +654,9 @@ class GpuTraversal : public autopas::TraversalInterface, public GpuTraversalInte
   /// (CompatibleTraversals.h:142-151), makes the configuration inapplicable (TraversalSelector.h:353-356).
   [[nodiscard]] bool isApplicableToDomain() const override {
     if (not functorHasGpuKernel()) return false;
+    if constexpr (requires { Functor_T::apbLinkedCellsOnly; }) {  // kernels that exist for gpuLinkedCells only
+      if (_traversal != APB_TRAVERSAL_GPULC_C08 and _traversal != APB_TRAVERSAL_GPULC_C18) return false;
+    }
     if (_useNewton3 and (_traversal == APB_TRAVERSAL_GPUVCL_CLUSTER_ITERATION or
                          _traversal == APB_TRAVERSAL_GPUVCL_C01_BALANCED))
       return false;
@@ -484,6 +692,7 @@ class GpuTraversal : public autopas::TraversalInterface, public GpuTraversalInte
 template <class Particle_T>
 class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle_T> {
   using Base = autopas::ParticleContainerInterface<Particle_T>;
+  using Columns = ParticleColumns<Particle_T>;
   static constexpr size_t kChunk = 1024;  // mirror particles per iterator "cell" (threads stride over chunks)
 
  public:
@@ -506,7 +715,7 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     cfg.cell_size_factor = cellSizeFactor;
     cfg.cluster_size = static_cast<int32_t>(clusterSize);
     cfg.container = container;
-    cfg.particle_kind = APB_PARTICLE_LJ;
+    cfg.particle_kind = Columns::kind;
     cfg.device = device;
     if (apb_create(&cfg, &_h) != APB_OK) {
       autopas::utils::ExceptionHandler::exception("GpuParticleContainer: {}", apb_last_error(nullptr));
@@ -686,19 +895,29 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     _mirrorValid = false;
     std::vector<Particle_T> leavers(static_cast<size_t>(nl));
     if (nl > 0) {
-      std::vector<double> c[6];
-      for (auto &v : c) v.resize(nl);
+      // leavers are whole copies of the particles (LeavingParticleCollector.h:101-110): every column travels
+      const auto &colIds = Columns::ids();
+      const size_t nc = colIds.size();
+      std::vector<std::vector<double>> c(nc, std::vector<double>(static_cast<size_t>(nl)));
+      for (size_t k = 0; k < nc; ++k) check(apb_get_leaver_column(_h, colIds[k], c[k].data()));
       std::vector<int64_t> ids(nl);
       std::vector<int32_t> types(nl);
-      check(apb_get_leavers(_h, c[0].data(), c[1].data(), c[2].data(), c[3].data(), c[4].data(), c[5].data(), ids.data(),
-                            types.data()));
+      check(apb_get_leavers(_h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ids.data(), types.data()));
       for (int64_t i = 0; i < nl; ++i) {
         Particle_T p;
-        p.setR({c[0][i], c[1][i], c[2][i]});
-        p.setV({c[3][i], c[4][i], c[5][i]});
+        double row[Columns::maxColumns];
+        for (size_t k = 0; k < nc; ++k) row[k] = c[k][i];
+        Columns::scatter(p, row);
         p.setID(static_cast<size_t>(ids[i]));
         if constexpr (requires { p.setTypeId(size_t{}); }) p.setTypeId(static_cast<size_t>(types[i]));
         p.setOwnershipState(autopas::OwnershipState::owned);
+        if constexpr (Columns::numHostOnly > 0) {
+          const auto it = _hostOnly.find(p.getID());
+          if (it != _hostOnly.end()) {
+            Columns::setHostOnly(p, it->second);
+            _hostOnly.erase(it);
+          }
+        }
         leavers[i] = p;
       }
     }
@@ -777,33 +996,32 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     size_t total = 0;
     for (auto &v : _pending) total += v.size();
     if (total == 0) return;
+    const auto &colIds = Columns::ids();
+    const size_t nc = colIds.size();
     for (int pass = 0; pass < 2; ++pass) {  // owned first, then halo: two bulk calls
       const auto want = pass == 0 ? autopas::OwnershipState::owned : autopas::OwnershipState::halo;
-      std::vector<double> col[12];
+      std::vector<std::vector<double>> col(nc);
       std::vector<int64_t> ids;
       std::vector<int32_t> types;
+      double row[Columns::maxColumns];
       for (auto &v : _pending)
         for (auto &p : v) {
           if (p.getOwnershipState() != want) continue;
-          for (int d = 0; d < 3; ++d) {
-            col[d].push_back(p.getR()[d]);
-            col[3 + d].push_back(p.getV()[d]);
-            col[6 + d].push_back(p.getF()[d]);
-            if constexpr (requires { p.getOldF(); }) col[9 + d].push_back(p.getOldF()[d]);
-          }
+          Columns::gather(p, row);
+          for (size_t k = 0; k < nc; ++k) col[k].push_back(row[k]);
           ids.push_back(static_cast<int64_t>(p.getID()));
           if constexpr (requires { p.getTypeId(); }) types.push_back(static_cast<int32_t>(p.getTypeId()));
           else types.push_back(0);
+          if constexpr (Columns::numHostOnly > 0) _hostOnly[p.getID()] = Columns::hostOnly(p);
         }
       if (ids.empty()) continue;
       int64_t before = 0;
       check(apb_get_num_slots(_h, &before));
       check(apb_add_particles(_h, static_cast<int64_t>(ids.size()), col[0].data(), col[1].data(), col[2].data(), ids.data(),
                               types.data(), pass == 0 ? APB_OWN_OWNED_VALUE : APB_OWN_HALO_VALUE, 0));
-      // velocities / forces of the appended slots: columns are transferred whole, so patch them through the mirror path
-      _appendedExtra.push_back({static_cast<size_t>(before), std::move(col[3]), std::move(col[4]), std::move(col[5]),
-                                std::move(col[6]), std::move(col[7]), std::move(col[8]), std::move(col[9]),
-                                std::move(col[10]), std::move(col[11])});
+      // the other columns of the appended slots: columns are transferred whole, so patch them through the mirror path
+      col.erase(col.begin(), col.begin() + 3);
+      _appendedExtra.push_back({static_cast<size_t>(before), std::move(col)});
     }
     for (auto &v : _pending) v.clear();
     patchAppendedColumns();
@@ -811,29 +1029,23 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
   }
   struct Appended {
     size_t first;
-    std::vector<double> c[9];
-    Appended(size_t f, std::vector<double> &&a0, std::vector<double> &&a1, std::vector<double> &&a2,
-             std::vector<double> &&a3, std::vector<double> &&a4, std::vector<double> &&a5, std::vector<double> &&a6,
-             std::vector<double> &&a7, std::vector<double> &&a8)
-        : first(f), c{std::move(a0), std::move(a1), std::move(a2), std::move(a3), std::move(a4),
-                      std::move(a5), std::move(a6), std::move(a7), std::move(a8)} {}
+    std::vector<std::vector<double>> c;  // columns ids()[3 ...]
   };
   void patchAppendedColumns() {
     if (_appendedExtra.empty()) return;
     int64_t slots = 0;
     check(apb_get_num_slots(_h, &slots));
-    static constexpr int colId[9] = {APB_COL_VX, APB_COL_VY, APB_COL_VZ, APB_COL_FX, APB_COL_FY,
-                                     APB_COL_FZ, APB_COL_OLDFX, APB_COL_OLDFY, APB_COL_OLDFZ};
+    const auto &colIds = Columns::ids();
     std::vector<double> tmp(static_cast<size_t>(slots));
-    for (int k = 0; k < 9; ++k) {
+    for (size_t k = 3; k < colIds.size(); ++k) {
       bool any = false;
       for (auto &a : _appendedExtra)
-        for (double v : a.c[k]) any = any or v != 0.;
+        for (double v : a.c[k - 3]) any = any or v != 0.;
       if (not any) continue;  // appended slots are zero-initialised by the library
-      check(apb_download_column(_h, colId[k], tmp.data()));
+      check(apb_download_column(_h, colIds[k], tmp.data()));
       for (auto &a : _appendedExtra)
-        for (size_t i = 0; i < a.c[k].size(); ++i) tmp[a.first + i] = a.c[k][i];
-      check(apb_upload_column(_h, colId[k], tmp.data()));
+        for (size_t i = 0; i < a.c[k - 3].size(); ++i) tmp[a.first + i] = a.c[k - 3][i];
+      check(apb_upload_column(_h, colIds[k], tmp.data()));
     }
     _appendedExtra.clear();
   }
@@ -854,12 +1066,12 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     int64_t slots = 0;
     check(apb_get_num_slots(_h, &slots));
     const size_t n = static_cast<size_t>(slots);
-    std::vector<double> c[12];
-    static constexpr int colId[12] = {APB_COL_X, APB_COL_Y, APB_COL_Z, APB_COL_VX, APB_COL_VY, APB_COL_VZ,
-                                      APB_COL_FX, APB_COL_FY, APB_COL_FZ, APB_COL_OLDFX, APB_COL_OLDFY, APB_COL_OLDFZ};
-    for (int k = 0; k < 12; ++k) {
+    const auto &colIds = Columns::ids();
+    const size_t nc = colIds.size();
+    std::vector<std::vector<double>> c(nc);
+    for (size_t k = 0; k < nc; ++k) {
       c[k].resize(n);
-      if (n) check(apb_download_column(_h, colId[k], c[k].data()));
+      if (n) check(apb_download_column(_h, colIds[k], c[k].data()));
     }
     std::vector<int64_t> ids(n);
     std::vector<int32_t> types(n), own(n);
@@ -868,13 +1080,18 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     AUTOPAS_OPENMP(parallel for schedule(static))
     for (size_t i = 0; i < n; ++i) {
       Particle_T &p = _mirror[i];
-      p.setR({c[0][i], c[1][i], c[2][i]});
-      p.setV({c[3][i], c[4][i], c[5][i]});
-      p.setF({c[6][i], c[7][i], c[8][i]});
-      if constexpr (requires { p.setOldF(std::array<double, 3>{}); }) p.setOldF({c[9][i], c[10][i], c[11][i]});
+      double row[Columns::maxColumns];
+      for (size_t k = 0; k < nc; ++k) row[k] = c[k][i];
+      Columns::scatter(p, row);
       p.setID(static_cast<size_t>(ids[i]));
       if constexpr (requires { p.setTypeId(size_t{}); }) p.setTypeId(static_cast<size_t>(types[i]));
       p.setOwnershipState(static_cast<autopas::OwnershipState>(own[i]));
+      if constexpr (Columns::numHostOnly > 0) {
+        if (own[i] != 0) {
+          const auto it = _hostOnly.find(p.getID());
+          if (it != _hostOnly.end()) Columns::setHostOnly(p, it->second);
+        }
+      }
     }
     _mirrorValid = true;
     _mirrorDirty = false;
@@ -886,24 +1103,26 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     if (static_cast<size_t>(slots) != n) {
       autopas::utils::ExceptionHandler::exception("GpuParticleContainer: host mirror and device storage diverged");
     }
-    std::vector<double> c[12];
+    const auto &colIds = Columns::ids();
+    const size_t nc = colIds.size();
+    std::vector<std::vector<double>> c(nc);
     std::vector<int32_t> own(n);
     for (auto &v : c) v.resize(n);
     AUTOPAS_OPENMP(parallel for schedule(static))
     for (size_t i = 0; i < n; ++i) {
       const Particle_T &p = _mirror[i];
-      for (int d = 0; d < 3; ++d) {
-        c[d][i] = p.getR()[d];
-        c[3 + d][i] = p.getV()[d];
-        c[6 + d][i] = p.getF()[d];
-        if constexpr (requires { p.getOldF(); }) c[9 + d][i] = p.getOldF()[d];
-      }
+      double row[Columns::maxColumns];
+      Columns::gather(p, row);
+      for (size_t k = 0; k < nc; ++k) c[k][i] = row[k];
       own[i] = static_cast<int32_t>(p.getOwnershipState());
     }
-    static constexpr int colId[12] = {APB_COL_X, APB_COL_Y, APB_COL_Z, APB_COL_VX, APB_COL_VY, APB_COL_VZ,
-                                      APB_COL_FX, APB_COL_FY, APB_COL_FZ, APB_COL_OLDFX, APB_COL_OLDFY, APB_COL_OLDFZ};
+    if constexpr (Columns::numHostOnly > 0) {  // attributes without a device column follow the particle id
+      _hostOnly.clear();
+      for (size_t i = 0; i < n; ++i)
+        if (own[i] != 0) _hostOnly[_mirror[i].getID()] = Columns::hostOnly(_mirror[i]);
+    }
     if (n) {
-      for (int k = 0; k < 12; ++k) check(apb_upload_column(_h, colId[k], c[k].data()));
+      for (size_t k = 0; k < nc; ++k) check(apb_upload_column(_h, colIds[k], c[k].data()));
       check(apb_upload_ownership(_h, own.data()));
     }
     _mirrorDirty = false;
@@ -944,6 +1163,7 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
   int _containerKind;
   std::vector<std::vector<Particle_T>> _pending;
   std::vector<Appended> _appendedExtra;
+  std::unordered_map<size_t, std::array<double, 3>> _hostOnly;  // attributes without a device column, by particle id
   mutable std::vector<Particle_T> _mirror;
   mutable bool _mirrorValid = true;   // mirror == device (an empty container starts coherent)
   mutable bool _mirrorDirty = false;  // mirror was handed out mutable since the last upload

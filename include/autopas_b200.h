@@ -217,6 +217,9 @@ int apb_reset_forces(apb_handle h, double fx, double fy, double fz);
 int apb_update_container(apb_handle h, int32_t keep_neighbor_lists_valid, int64_t *out_num_leavers);
 int apb_get_leavers(apb_handle h, double *x, double *y, double *z, double *vx, double *vy, double *vz, int64_t *ids,
                     int32_t *types);
+/* any other column of the leavers of the last apb_update_container (the returned particles are whole copies,
+ * LeavingParticleCollector.h:101-110: forces, quaternion / torque, the SPH attributes), same order as apb_get_leavers */
+int apb_get_leaver_column(apb_handle h, int32_t column, double *dst);
 /* ParticleContainerInterface::rebuildNeighborLists(TraversalInterface*) (:158): LinkedCells re-binning
  * (counting sort) or VerletClusterLists tower/cluster/pair-list construction (VerletClusterLists.h:779-799). */
 int apb_rebuild_neighbor_lists(apb_handle h, int32_t traversal, int32_t newton3);
@@ -277,6 +280,12 @@ int apb_migrate(apb_handle h, int64_t *out_num_sent, int64_t *out_num_received);
  * (bulk updateHaloParticle), same three-phase order, fixed message sizes. A single fully periodic rank called after
  * apb_migrate generates (and later refreshes) all periodic images in one pass - the same set of halo copies. */
 int apb_exchange_halos(apb_handle h);
+/* Refresh of other columns of the halo copies from their source particles through the links the last generating
+ * apb_exchange_halos recorded: sph-mpi's updateHaloParticles between the density and the hydro-force pass
+ * (examples/sph-mpi/sph-main-mpi.cpp:271-315, 373-414: the copies need the owners' density and pressure). Positions are
+ * not accepted here (apb_exchange_halos shifts them at the periodic boundary). For SPHParticle / MultisiteMoleculeLJ
+ * storage the generating exchange itself copies every attribute column to the new halo copies. */
+int apb_refresh_halo_columns(apb_handle h, int32_t num_columns, const int32_t *columns);
 /* MPI_Reduce(SUM) of potential energy / virial in Simulation.cpp:319-322, as ncclAllReduce; no-op for one rank */
 int apb_allreduce_globals(apb_handle h, apb_traversal_result *inout);
 

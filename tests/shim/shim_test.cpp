@@ -16,6 +16,7 @@
 #include "autopas/containers/linkedCells/traversals/LCC08Traversal.h"
 #include "molecularDynamicsLibrary/LJFunctor.h"
 #include "molecularDynamicsLibrary/MoleculeLJ.h"
+#include "SPHLibrary/SPHParticle.h"
 
 using Molecule = mdLib::MoleculeLJ;
 using FMCell = autopas::FullParticleCell<Molecule>;
@@ -217,6 +218,140 @@ static void compareATM(const Scenario &s0) {
               maxRel, u1, fg.getVirial());
 }
 
+// SPH density and hydro-force functors behind the pairwise interfaces: reference LinkedCells<SPHParticle> + lc_c08 (AoS)
+// against gpuLinkedCells + gpulc_c08 / gpulc_c18 with GpuSPHCalcDensityFunctor / GpuSPHCalcHydroForceFunctor. The flow is
+// the one of examples/sph/main.cpp: density pass -> pressure set per particle through the container iterators -> hydro
+// force pass; density, acceleration, engDot and vSigMax are read back through the iterators. Newton3 evaluates a pair
+// once with the first particle's support radius, so that case uses one smoothing length for all particles.
+using SPH = sphLib::SPHParticle;
+using SPHCell = autopas::FullParticleCell<SPH>;
+template <bool n3>
+static void compareSPH(const Scenario &s0) {
+  const double smth = 1.0;  // support radius 2.5 h = the container cutoff
+  std::vector<SPH> owned, halo;
+  std::mt19937_64 rng(7);
+  std::uniform_real_distribution<double> u(0., 1.);
+  for (const auto &m : s0.owned)
+    owned.emplace_back(m.getR(), m.getV(), m.getID(), 0.8 + 0.4 * u(rng), n3 ? smth : smth * (0.9 + 0.1 * u(rng)), 1.0 + u(rng));
+  for (const auto &m : s0.halo) {
+    SPH p(m.getR(), std::array<double, 3>{0.1 * u(rng), 0.1 * u(rng), 0.1 * u(rng)}, m.getID(), 0.8 + 0.4 * u(rng),
+          n3 ? smth : smth * (0.9 + 0.1 * u(rng)), 1.0 + u(rng));
+    p.setOwnershipState(autopas::OwnershipState::halo);
+    halo.push_back(p);
+  }
+  for (auto &p : owned) {
+    p.setEnergy(1.0 + u(rng));
+    p.setDt(0.01 * u(rng));
+  }
+  const double cutoff = 2.5, skin = 0.3;
+  autopas::LinkedCells<SPH> ref(s0.boxMin, s0.boxMax, cutoff, skin, 1.0);
+  autopas_b200::GpuParticleContainer<SPH> gpu(APB_CONTAINER_LINKED_CELLS, s0.boxMin, s0.boxMax, cutoff, skin, 1.0, 4);
+  autopas::ParticleContainerInterface<SPH> &c = gpu;
+  for (const auto &p : owned) ref.addParticle(p), c.addParticle(p);
+  for (const auto &p : halo) ref.addHaloParticle(p), c.addHaloParticle(p);
+  const auto info = ref.getTraversalSelectorInfo();
+  // ---- density
+  sphLib::SPHCalcDensityFunctor<SPH> dr;
+  autopas::LCC08Traversal<SPHCell, sphLib::SPHCalcDensityFunctor<SPH>> tdr(info.cellsPerDim, dr, info.interactionLength,
+                                                                           info.cellLength, autopas::DataLayoutOption::aos, n3);
+  ref.rebuildNeighborLists(&tdr);
+  dr.initTraversal();
+  ref.computeInteractions(&tdr);
+  dr.endTraversal(n3);
+  autopas_b200::GpuSPHCalcDensityFunctor<SPH> dg;
+  autopas_b200::GpuTraversal<autopas_b200::GpuSPHCalcDensityFunctor<SPH>> tdg(APB_TRAVERSAL_GPULC_C08, dg, n3);
+  CHECK(tdg.isApplicableToDomain(), "SPH density gpulc_c08 applicable");
+  autopas_b200::GpuTraversal<autopas_b200::GpuSPHCalcDensityFunctor<SPH>> tdv(APB_TRAVERSAL_GPUVCL_PRUNED, dg, n3);
+  CHECK(!tdv.isApplicableToDomain(), "SPH functors have no kernel for the cluster-list traversals");
+  c.rebuildNeighborLists(&tdg);
+  dg.initTraversal();
+  c.computeInteractions(&tdg);
+  dg.endTraversal(n3);
+  std::map<size_t, double> rhoRef;
+  for (auto it = ref.begin(autopas::IteratorBehavior::owned); it.isValid(); ++it) rhoRef[it->getID()] = it->getDensity();
+  double maxRho = 0.;
+  size_t seen = 0;
+  for (auto it = c.begin(autopas::IteratorBehavior::owned); it.isValid(); ++it, ++seen)
+    maxRho = std::max(maxRho, std::fabs(it->getDensity() - rhoRef.at(it->getID())) / rhoRef.at(it->getID()));
+  CHECK(seen == owned.size(), "SPH iterator visits %zu of %zu owned", seen, owned.size());
+  CHECK(maxRho <= 1e-12, "SPH density mismatch %.3e", maxRho);
+  // ---- pressure and halo densities through the mutable iterators (write-through of the SPH columns), host-only
+  // attributes (energy, dt) survive the round trip
+  auto prepare = [](auto &cont) {
+    for (auto it = cont.begin(autopas::IteratorBehavior::ownedOrHalo); it.isValid(); ++it) {
+      if (it->isHalo()) it->setDensity(1.0 + 0.001 * static_cast<double>(it->getID() % 97));
+      it->setPressure(0.4 * it->getDensity() * (1.0 + 0.01 * static_cast<double>(it->getID() % 13)));
+    }
+  };
+  prepare(ref);
+  prepare(c);
+  // ---- hydro force
+  sphLib::SPHCalcHydroForceFunctor<SPH> hr;
+  autopas::LCC08Traversal<SPHCell, sphLib::SPHCalcHydroForceFunctor<SPH>> thr(info.cellsPerDim, hr, info.interactionLength,
+                                                                              info.cellLength, autopas::DataLayoutOption::aos, n3);
+  hr.initTraversal();
+  ref.computeInteractions(&thr);
+  hr.endTraversal(n3);
+  autopas_b200::GpuSPHCalcHydroForceFunctor<SPH> hg;
+  autopas_b200::GpuTraversal<autopas_b200::GpuSPHCalcHydroForceFunctor<SPH>> thg(APB_TRAVERSAL_GPULC_C18, hg, n3);
+  hg.initTraversal();
+  c.computeInteractions(&thg);
+  hg.endTraversal(n3);
+  struct Out {
+    std::array<double, 3> acc;
+    double engDot, vsig, energy, dt;
+  };
+  std::map<size_t, Out> outRef;
+  double amax = 0., emax = 0.;
+  for (auto it = ref.begin(autopas::IteratorBehavior::owned); it.isValid(); ++it) {
+    outRef[it->getID()] = {it->getAcceleration(), it->getEngDot(), it->getVSigMax(), it->getEnergy(), it->getDt()};
+    for (int d = 0; d < 3; ++d) amax = std::max(amax, std::fabs(it->getAcceleration()[d]));
+    emax = std::max(emax, std::fabs(it->getEngDot()));
+  }
+  double maxA = 0., maxE = 0., maxV = 0.;
+  bool hostOnlyKept = true;
+  for (auto it = c.begin(autopas::IteratorBehavior::owned); it.isValid(); ++it) {
+    const Out &o = outRef.at(it->getID());
+    for (int d = 0; d < 3; ++d) maxA = std::max(maxA, std::fabs(it->getAcceleration()[d] - o.acc[d]) / amax);
+    maxE = std::max(maxE, std::fabs(it->getEngDot() - o.engDot) / emax);
+    maxV = std::max(maxV, std::fabs(it->getVSigMax() - o.vsig) / std::fabs(o.vsig));
+    hostOnlyKept = hostOnlyKept and it->getEnergy() == o.energy and it->getDt() == o.dt;
+  }
+  CHECK(maxA <= 1e-12, "SPH acceleration mismatch %.3e (relative to max |a| = %.3e)", maxA, amax);
+  CHECK(maxE <= 1e-12, "SPH engDot mismatch %.3e (relative to max = %.3e)", maxE, emax);
+  CHECK(maxV <= 1e-14, "SPH vSigMax mismatch %.3e", maxV);
+  CHECK(hostOnlyKept, "SPH energy / dt (no device column) must survive the device round trip");
+  std::printf("%-44s newton3=%d  density %.2e  acceleration %.2e  engDot %.2e  vSigMax %.2e\n",
+              "gpuLinkedCells/gpulc_c08+c18 SPH", int(n3), maxRho, maxA, maxE, maxV);
+  // leavers are whole particles: SPH attributes and host-only attributes travel with them
+  for (auto *cont : {static_cast<autopas::ParticleContainerInterface<SPH> *>(&ref), &c})
+    for (auto it = cont->begin(autopas::IteratorBehavior::owned); it.isValid(); ++it)
+      if (it->getID() % 11 == 0) it->setR({it->getR()[0], it->getR()[1] - 1.7, it->getR()[2]});
+  auto leaveRef = ref.updateContainer(false);
+  auto leaveGpu = c.updateContainer(false);
+  std::map<size_t, SPH> la;
+  for (auto &p : leaveRef) la.emplace(p.getID(), p);
+  CHECK(leaveGpu.size() == la.size() and not la.empty(), "SPH leavers: %zu vs %zu", leaveGpu.size(), la.size());
+  for (auto &p : leaveGpu) {
+    const auto it = la.find(p.getID());
+    if (it == la.end()) {
+      CHECK(false, "SPH leaver %zu not a reference leaver", static_cast<size_t>(p.getID()));
+      continue;
+    }
+    const SPH &q = it->second;
+    const bool same[10] = {p.getR() == q.getR(), p.getV() == q.getV(), p.getMass() == q.getMass(),
+                           p.getSmoothingLength() == q.getSmoothingLength(),
+                           std::fabs(p.getPressure() - q.getPressure()) <= 1e-12 * q.getPressure(),  // set from the density
+                           p.getSoundSpeed() == q.getSoundSpeed(), p.getEnergy() == q.getEnergy(), p.getDt() == q.getDt(),
+                           std::fabs(p.getDensity() - q.getDensity()) <= 1e-12 * q.getDensity(),
+                           std::fabs(p.getEngDot() - q.getEngDot()) <= 1e-12 * emax};
+    bool all = true;
+    for (bool b : same) all = all and b;
+    CHECK(all, "SPH leaver %zu lost attributes (r v m h P c e dt rho engDot: %d %d %d %d %d %d %d %d %d %d)",
+          static_cast<size_t>(p.getID()), same[0], same[1], same[2], same[3], same[4], same[5], same[6], same[7], same[8], same[9]);
+  }
+}
+
 int main() {
   autopas::utils::ExceptionHandler::setBehavior(autopas::utils::ExceptionBehavior::throwException);
   const Scenario s = makeScenario(42);
@@ -229,6 +364,8 @@ int main() {
     compare<false>(s, APB_CONTAINER_VERLET_CLUSTER_LISTS, APB_TRAVERSAL_GPUVCL_PRUNED, 32, "gpuVerletClusterLists/gpuvcl_pruned");
     compareATM<false>(s);
     compareATM<true>(s);
+    compareSPH<false>(s);
+    compareSPH<true>(s);
     // wrong traversal type is rejected like the reference containers do
     autopas_b200::GpuParticleContainer<Molecule> gpu(APB_CONTAINER_LINKED_CELLS, s.boxMin, s.boxMax, s.cutoff, s.skin);
     using RefFunctor = mdLib::LJFunctor<Molecule>;

@@ -227,3 +227,62 @@ def test_multisite_matches_reference_fixture(n3):
     assert close(T[owned], g["ref_torque"][owned], o["scale"][owned])
     assert f.getPotentialEnergy() == pytest.approx(float(g["ref_upot"]), rel=1e-12)
     assert f.getVirial() == pytest.approx(float(g["ref_virial"]), rel=1e-12)
+
+
+# ---- SPH across a periodic boundary: generating halo exchange + column refresh ------------------------------------------
+def test_sph_periodic_halo_exchange_and_column_refresh():
+    """The sph-mpi flow (examples/sph-mpi/sph-main-mpi.cpp:373-414) on one periodic rank: updateHaloParticles -> density
+    -> pressure -> updateHaloParticles -> hydro force. The generating exchange must give the halo copies every attribute
+    of their owners, apb_refresh_halo_columns the owners' new density and pressure; results against the oracle with
+    host-built periodic images."""
+    from scenarios import grid_lattice, periodic_images
+    cutoff, skin = 1.0, 0.1
+    pos, bmin, bmax = grid_lattice(9, 0.35, jitter=0.07, seed=5)
+    L = bmax - bmin
+    pos = bmin + np.mod(pos - bmin, L)
+    n = len(pos)
+    rng = np.random.default_rng(6)
+    vel = rng.normal(0, 0.5, (n, 3))
+    mass, smth, snd = rng.uniform(0.8, 1.2, n), rng.uniform(0.30, 0.40, n), rng.uniform(1.0, 1.4, n)
+    c = GpuParticleContainer("gpuLinkedCells", bmin, bmax, cutoff, skin, particleKind=capi.PARTICLE_SPH)
+    c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(n))
+    upload_by_id(c, VX=vel[:, 0], VY=vel[:, 1], VZ=vel[:, 2], MASS=mass, SMTH=smth, SNDSPEED=snd)
+    c.exchangeHalos()  # generating: copies carry mass, smoothing length, velocity, sound speed
+    hpos, hsrc = periodic_images(pos, bmin, bmax, cutoff + skin)
+    assert c.getNumberOfParticles("halo") == len(hpos)
+    ids, _, own = c.downloadIds()
+    hal = own == 2
+    for name, ref in (("MASS", mass), ("SMTH", smth), ("SNDSPEED", snd), ("VX", vel[:, 0]), ("VZ", vel[:, 2])):
+        assert np.array_equal(c.downloadColumn(name)[hal], ref[ids[hal]]), name
+    c.rebuildNeighborLists(GpuTraversal("gpulc_c08", SPHCalcDensityFunctor(), False))
+    run(c, "gpulc_c08", SPHCalcDensityFunctor(), False)
+    ids, _, own = c.downloadIds()
+    owned, hal = own == 1, own == 2
+    rho = np.zeros(n)
+    rho[ids[owned]] = c.downloadColumn("DENSITY")[owned]
+    # oracle: owned + images, attributes of an image = attributes of its source
+    src = np.r_[np.arange(n), hsrc]
+    apos = np.vstack([pos, hpos])
+    aown = np.r_[np.ones(n), 2 * np.ones(len(hpos))].astype(np.int64)
+    o_rho, sc = oracle.sph_density(apos, mass[src], smth[src], aown)
+    assert close(rho, o_rho[:n], sc[:n])
+    pressure = 0.3 * rho * (1.0 + 0.1 * np.sin(np.arange(n)))
+    col = c.downloadColumn("PRESSURE")
+    col[owned] = pressure[ids[owned]]
+    c.uploadColumn("PRESSURE", col)
+    c.refreshHaloColumns(["DENSITY", "PRESSURE"])
+    assert np.array_equal(c.downloadColumn("DENSITY")[hal], rho[ids[hal]])
+    assert np.array_equal(c.downloadColumn("PRESSURE")[hal], pressure[ids[hal]])
+    with pytest.raises(ApbError):
+        c.refreshHaloColumns(["X"])  # positions go through exchangeHalos (periodic shift)
+    run(c, "gpulc_c18", SPHCalcHydroForceFunctor(), False)
+    acc = np.zeros((n, 3))
+    for d, k in enumerate(("FX", "FY", "FZ")):
+        acc[ids[owned], d] = c.downloadColumn(k)[owned]
+    eng = np.zeros(n)
+    eng[ids[owned]] = c.downloadColumn("ENGDOT")[owned]
+    o_acc, o_eng, _, sc, sce = oracle.sph_hydro(apos, vel[src], mass[src], smth[src], rho[src], pressure[src], snd[src], aown,
+                                                with_eng_scale=True)
+    assert close(acc, o_acc[:n], sc[:n])
+    assert close(eng, o_eng[:n], sce[:n])
+    c.close()

@@ -311,10 +311,17 @@ def test_update_container_returns_leavers(cont):
         movers = (sown == 1) & (x > 5.9)
         x[movers] += 0.15  # leaves through the +x face
         c.uploadColumn("X", x)
+        c.uploadColumn("FY", sid * 0.25)     # leavers are whole copies: any other column travels with them
+        c.uploadColumn("OLDFZ", sid * -0.5)
         expect = set(sid[movers & (x >= 6.0)].tolist())
         leavers = c.updateContainer(keep)
         assert set(leavers["id"].tolist()) == expect
         assert np.all(leavers["x"] >= 6.0)
+        assert np.array_equal(c.leaverColumn("X"), leavers["x"]) and np.array_equal(c.leaverColumn("VZ"), leavers["vz"])
+        assert np.array_equal(c.leaverColumn("FY"), leavers["id"] * 0.25)
+        assert np.array_equal(c.leaverColumn("OLDFZ"), leavers["id"] * -0.5)
+        with pytest.raises(ApbError):
+            c.leaverColumn("DENSITY")  # not a column of MoleculeLJ storage
         assert c.getNumberOfParticles("halo") == 0
         assert c.getNumberOfParticles("owned") == int(mo.sum()) - len(expect)
         if keep:

@@ -22,6 +22,21 @@ def test_cpp_shim_matches_reference_through_autopas_interfaces():
     assert "SHIM TEST PASSED" in r.stdout
 
 
+BIN_MS = os.path.join(ROOT, "oracle", "_ref", "shim_test_ms")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(BIN_MS), reason="oracle/_ref/shim_test_ms was not built (reference tree absent)")
+def test_cpp_shim_multisite_functor_matches_reference():
+    """GpuLJMultisiteFunctor around mdLib::LJMultisiteFunctor in the reference's MULTISITE build mode: forces, torques,
+    Upot and virial of gpuLinkedCells/gpulc_c08 (newton3) and gpulc_c18 against LinkedCells/lc_c08 at 1e-12."""
+    r = subprocess.run([BIN_MS], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    print(r.stderr)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "SHIM TEST PASSED" in r.stdout
+
+
 TUNER = os.path.join(ROOT, "oracle", "_ref", "autopas_tuner_driver")
 
 
