@@ -349,124 +349,6 @@ __global__ void __launch_bounds__(LCW_WARPS * 32) kSPHHydroWarp(SPHWarpArgs wa) 
   }
 }
 
-// ---- one thread per slot, pair arithmetic deferred (lcDeferredWalk): the variant for systems that fill the GPU ---------
-template <bool N3>
-__global__ void __launch_bounds__(LCD_BLOCK) kSPHDensityDeferred(SPHWarpArgs wa) {
-  __shared__ int queue[LCD_DEPTH * LCD_BLOCK];
-  const SPHArgs &a = wa.s;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool live = i < a.w.n && a.w.own[i] != APB_OWN_DUMMY;
-  const int c = live ? a.w.slotCell[i] : 0;
-  const LCGeom &g = a.w.g;
-  const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
-                                     c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
-  const bool part = live && (canOwnI || N3);
-  const int64_t ii = part ? i : 0;
-  const double xi = a.x[ii], yi = a.y[ii], zi = a.z[ii], hi = a.smth[ii], mi = a.mass[ii];
-  const double H = SPH_SUPPORT * hi;
-  const double reach2 = N3 ? wa.interactionLength2 : __dmul_rn(H, H);
-  double rho = 0.;
-  lcDeferredWalk<N3>(
-      g, wa.w.cellStart, wa.w.stencilSorted, wa.w.stencilN, part, i, c, !canOwnI, queue,
-      [&](int j) {
-        if (j == i || a.w.own[j] == APB_OWN_DUMMY) return false;
-        const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
-        return dot3(drx, dry, drz, drx, dry, drz) < reach2;
-      },
-      [&](int j) {
-        const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
-        const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
-        rho += __dmul_rn(a.mass[j], sphW(dr2, hi));
-        if (N3) {
-          const double d2 = __dmul_rn(mi, sphW(dr2, a.smth[j]));
-          if (d2 != 0.) atomicAdd(a.density + j, d2);
-        }
-      });
-  if (part) {
-    if (N3)
-      atomicAdd(a.density + i, rho);
-    else
-      a.density[i] += rho;
-  }
-}
-
-template <bool N3>
-__global__ void __launch_bounds__(LCD_BLOCK) kSPHHydroDeferred(SPHWarpArgs wa) {
-  __shared__ int queue[LCD_DEPTH * LCD_BLOCK];
-  const SPHArgs &a = wa.s;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool live = i < a.w.n && a.w.own[i] != APB_OWN_DUMMY;
-  const int c = live ? a.w.slotCell[i] : 0;
-  const LCGeom &g = a.w.g;
-  const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
-                                     c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
-  const bool part = live && (canOwnI || N3);
-  const int64_t ii = part ? i : 0;
-  const double xi = a.x[ii], yi = a.y[ii], zi = a.z[ii], hi = a.smth[ii], mi = a.mass[ii];
-  const double vxi = a.vx[ii], vyi = a.vy[ii], vzi = a.vz[ii];
-  const double rhoi = a.density[ii], Pi = a.pressure[ii], ci = a.snd[ii];
-  const double cut = hi * SPH_SUPPORT;
-  const double cut2 = __dmul_rn(cut, cut);
-  const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
-  double accx = 0., accy = 0., accz = 0., eng = 0., vmax = 0.;
-  lcDeferredWalk<N3>(
-      g, wa.w.cellStart, wa.w.stencilSorted, wa.w.stencilN, part, i, c, !canOwnI, queue,
-      [&](int j) {
-        if (j == i || a.w.own[j] == APB_OWN_DUMMY) return false;
-        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
-        return dot3(drx, dry, drz, drx, dry, drz) < cut2;
-      },
-      [&](int j) {
-        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
-        const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
-        const double dvx = vxi - a.vx[j], dvy = vyi - a.vy[j], dvz = vzi - a.vz[j];
-        const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
-        const double drabs = sqrt(dr2);
-        const double wij = (dvdr < 0) ? dvdr / drabs : 0;
-        const double vsig = __dadd_rn(__dadd_rn(ci, a.snd[j]), -__dmul_rn(3.0, wij));
-        vmax = fmax(vmax, vsig);
-        const double rhoj = a.density[j], Pj = a.pressure[j], mj = a.mass[j];
-        const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
-        const double gi = sphGradWScale(drabs, hi), gj = sphGradWScale(drabs, a.smth[j]);
-        const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
-        const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
-        const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
-        const double PjOverRho2 = Pj / __dmul_rn(rhoj, rhoj);
-        const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
-        const double si = __dmul_rn(scale, mj);
-        accx -= __dmul_rn(gx, si);
-        accy -= __dmul_rn(gy, si);
-        accz -= __dmul_rn(gz, si);
-        const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
-        const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
-        eng += __dmul_rn(gdv, scale2i);
-        if (N3) {
-          atomicMaxPositive(a.vsigmax + j, vsig);
-          const double sj = __dmul_rn(scale, mi);
-          atomicAdd(a.ax + j, __dmul_rn(gx, sj));
-          atomicAdd(a.ay + j, __dmul_rn(gy, sj));
-          atomicAdd(a.az + j, __dmul_rn(gz, sj));
-          const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
-          atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
-        }
-      });
-  if (part) {
-    if (N3) {
-      atomicAdd(a.ax + i, accx);
-      atomicAdd(a.ay + i, accy);
-      atomicAdd(a.az + i, accz);
-      atomicAdd(a.engDot + i, eng);
-      if (vmax > 0.) atomicMaxPositive(a.vsigmax + i, vmax);
-    } else {
-      a.ax[i] += accx;
-      a.ay[i] += accy;
-      a.az[i] += accz;
-      a.engDot[i] += eng;
-      a.vsigmax[i] = fmax(a.vsigmax[i], vmax);
-    }
-  }
-}
-
 // ---- per-slot partner lists --------------------------------------------------------------------------------------------
 // The 27 stencil cells hold ~1000 candidates per particle at SPH densities, of which ~110 lie inside the kernel support;
 // walking them costs ~75 instructions per candidate whatever the kernel variant (measured, profiles/r02_lc_kernels.txt),
@@ -563,7 +445,31 @@ static int ensureLCLists(apb_handle h, bool half) {
 struct SPHListArgs {
   SPHArgs s;
   const int *nbrCount, *nbr;
+  const double *pOverRho2, *gradWNorm;  // hydro force: per-particle factors, kSPHPrepareHydro
 };
+
+// Per-particle factors of the hydro-force pair term that the reference recomputes for every pair
+// (SPHCalcHydroForceFunctor.h:86-96: P_j / rho_j^2; SPHKernels.cpp gradW: 16 / pi / H_j^3): two of the nine divisions of
+// a pair. Same operations on the same operands, so the results are bit-identical to the per-pair evaluation.
+__global__ void kSPHPrepareHydro(int64_t n, const double *__restrict__ pressure, const double *__restrict__ density,
+                                 const double *__restrict__ smth, double *__restrict__ pOverRho2,
+                                 double *__restrict__ gradWNorm) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double rho = density[i], H = SPH_SUPPORT * smth[i];
+  pOverRho2[i] = pressure[i] / __dmul_rn(rho, rho);
+  gradWNorm[i] = 16.0 / SPH_PI / __dmul_rn(__dmul_rn(H, H), H);
+}
+// sphGradWScale with the normalisation 16 / pi / H^3 handed in
+__device__ __forceinline__ double sphGradWScaleNorm(double drabs, double h, double norm) {
+  const double H = SPH_SUPPORT * h;
+  const double s = drabs / H;
+  const double s1 = (1.0 - s < 0) ? 0 : 1.0 - s;
+  const double s2 = (0.5 - s < 0) ? 0 : 0.5 - s;
+  double r = __dadd_rn(__dmul_rn(-3.0, __dmul_rn(s1, s1)), __dmul_rn(12.0, __dmul_rn(s2, s2)));
+  r = __dmul_rn(r, norm);
+  return r / __dadd_rn(__dmul_rn(drabs, H), __dmul_rn(1.0e-6, h));
+}
 
 template <bool N3>
 __global__ void __launch_bounds__(128) kSPHDensityList(SPHListArgs la) {
@@ -603,6 +509,7 @@ __global__ void __launch_bounds__(128) kSPHHydroList(SPHListArgs la) {
   const double cut = hi * SPH_SUPPORT;
   const double cut2 = __dmul_rn(cut, cut);
   const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
+  const double normI = la.gradWNorm[i];
   double accx = 0., accy = 0., accz = 0., eng = 0., vmax = 0.;
   for (int p = 0; p < cnt; ++p) {
     const int j = la.nbr[static_cast<size_t>(p) * a.w.n + i];
@@ -615,13 +522,13 @@ __global__ void __launch_bounds__(128) kSPHHydroList(SPHListArgs la) {
     const double wij = (dvdr < 0) ? dvdr / drabs : 0;
     const double vsig = __dadd_rn(__dadd_rn(ci, a.snd[j]), -__dmul_rn(3.0, wij));
     vmax = fmax(vmax, vsig);
-    const double rhoj = a.density[j], Pj = a.pressure[j], mj = a.mass[j];
+    const double rhoj = a.density[j], mj = a.mass[j];
     const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
-    const double gi = sphGradWScale(drabs, hi), gj = sphGradWScale(drabs, a.smth[j]);
+    const double gi = sphGradWScaleNorm(drabs, hi, normI), gj = sphGradWScaleNorm(drabs, a.smth[j], la.gradWNorm[j]);
     const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
     const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
     const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
-    const double PjOverRho2 = Pj / __dmul_rn(rhoj, rhoj);
+    const double PjOverRho2 = la.pOverRho2[j];
     const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
     const double si = __dmul_rn(scale, mj);
     accx -= __dmul_rn(gx, si);
@@ -680,7 +587,7 @@ static int computeSPH(apb_handle h, const apb_functor *f, int newton3, apb_trave
   a.az = h->col[APB_COL_FZ];
   a.engDot = h->col[APB_COL_ENGDOT];
   a.vsigmax = h->col[APB_COL_VSIGMAX];
-  const int lcKernel = apbLCKernelVariant(n);  // 0 thread (round 1), 1 warp per slot, 2 deferred, 3 partner lists
+  const int lcKernel = apbLCKernelVariant(n, 3);  // 0 thread over the cells (round 1), 1 warp per slot, 3 partner lists
   if (lcKernel == 3) {
     APB_CHECK(ensureLCLists(h, newton3 != 0));
     SPHListArgs la;
@@ -688,6 +595,14 @@ static int computeSPH(apb_handle h, const apb_functor *f, int newton3, apb_trave
     la.nbrCount = static_cast<const int *>(h->nbrCount.p);
     la.nbr = static_cast<const int *>(h->nbrList.p);
     const int lgrid = apbDivUp(n, 128);
+    la.pOverRho2 = la.gradWNorm = nullptr;
+    if (f->kind == APB_FUNCTOR_SPH_HYDRO) {
+      APB_CHECK(apbEnsure(h, h->sortK2, sizeof(double) * 2 * n));  // scratch of the rebuild, free between rebuilds
+      double *tmp = static_cast<double *>(h->sortK2.p);
+      la.pOverRho2 = tmp;
+      la.gradWNorm = tmp + n;
+      ++h->launchCount, kSPHPrepareHydro<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, a.pressure, a.density, a.smth, tmp, tmp + n);
+    }
     ++h->launchCount;
     if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
       if (newton3)
@@ -715,20 +630,7 @@ static int computeSPH(apb_handle h, const apb_functor *f, int newton3, apb_trave
     wa.interactionLength2 = il * il;
     const int grid = static_cast<int>(std::min<int64_t>(apbDivUp(n, LCW_WARPS), 148 * 16));
     ++h->launchCount;
-    if (lcKernel == 2) {
-      const int dgrid = apbDivUp(n, LCD_BLOCK);
-      if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
-        if (newton3)
-          kSPHDensityDeferred<true><<<dgrid, LCD_BLOCK, 0, h->stream>>>(wa);
-        else
-          kSPHDensityDeferred<false><<<dgrid, LCD_BLOCK, 0, h->stream>>>(wa);
-      } else {
-        if (newton3)
-          kSPHHydroDeferred<true><<<dgrid, LCD_BLOCK, 0, h->stream>>>(wa);
-        else
-          kSPHHydroDeferred<false><<<dgrid, LCD_BLOCK, 0, h->stream>>>(wa);
-      }
-    } else if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
+    if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
       if (newton3)
         kSPHDensityWarp<true><<<grid, LCW_WARPS * 32, 0, h->stream>>>(wa);
       else
@@ -1141,158 +1043,6 @@ __global__ void __launch_bounds__(LCW_WARPS * 32) kATMTripletsWarp(ATMWarpArgs w
   if (STATS) ljStatsBlockReduce(st, a.partials);
 }
 
-// One thread per slot over the neighbour lists of kATMNeighbors with the triplet arithmetic deferred: a lane appends
-// the (j, k) pairs that pass |r_jk| <= cutoff to its private queue in shared memory and the warp drains the queues
-// together when the first one is full (see lcDeferredWalk, lc_warp.cuh) - the ~100 FP64 instructions of a triplet run
-// at the fill level of the queues instead of for every (j, k) pair. The variant for systems that fill the GPU.
-template <bool MIX, bool STATS, bool N3>
-__global__ void __launch_bounds__(LCD_BLOCK) kATMTripletsDeferred(ATMArgs a) {
-  __shared__ int queue[LCD_DEPTH * LCD_BLOCK];
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  LJStats st;
-  ljStatsZero(st);
-  const int ownI = i < a.w.n ? a.w.own[i] : APB_OWN_DUMMY;
-  const int cnt = ownI != APB_OWN_DUMMY ? a.nbrCount[i] : 0;
-  const int64_t ii = ownI != APB_OWN_DUMMY ? i : 0;
-  const double xi = a.x[ii], yi = a.y[ii], zi = a.z[ii];
-  const int ti = MIX ? a.type[ii] : 0;
-  const bool ownedI = ownI == APB_OWN_OWNED;
-  double Fx = 0., Fy = 0., Fz = 0.;
-  auto triplet = [&](int pq) {
-    const int p = pq >> 16, q = pq & 0xFFFF;
-    const int j = a.nbr[static_cast<size_t>(p) * a.w.n + i], k = a.nbr[static_cast<size_t>(q) * a.w.n + i];
-    const double xj = a.x[j], yj = a.y[j], zj = a.z[j], xk = a.x[k], yk = a.y[k], zk = a.z[k];
-    const double ijx = xj - xi, ijy = yj - yi, ijz = zj - zi;
-    const double jkx = xk - xj, jky = yk - yj, jkz = zk - zj;
-    const double kix = xi - xk, kiy = yi - yk, kiz = zi - zk;
-    const double d2ij = dot3(ijx, ijy, ijz, ijx, ijy, ijz);
-    const double d2jk = dot3(jkx, jky, jkz, jkx, jky, jkz);
-    const double d2ki = dot3(kix, kiy, kiz, kix, kiy, kiz);
-    double nu = a.nu;
-    if (MIX) nu = __ldg(a.nuMix + (static_cast<size_t>(ti) * a.T + a.type[j]) * a.T + a.type[k]);
-    // AxilrodTellerMutoFunctor.h:217-251
-    const double all2 = d2ij * d2jk * d2ki;
-    const double all5 = all2 * all2 * sqrt(all2);
-    const double factor = 3.0 * nu / all5;
-    const double IJdKI = dot3(ijx, ijy, ijz, kix, kiy, kiz);
-    const double IJdJK = dot3(ijx, ijy, ijz, jkx, jky, jkz);
-    const double JKdKI = dot3(jkx, jky, jkz, kix, kiy, kiz);
-    const double allDots = IJdKI * IJdJK * JKdKI;
-    const double cJK = IJdKI * (IJdJK - JKdKI);
-    const double cIJ = IJdJK * JKdKI - d2jk * d2ki + 5.0 * allDots / d2ij;
-    const double cKI = -IJdJK * JKdKI + d2ij * d2jk - 5.0 * allDots / d2ki;
-    const double fix = (jkx * cJK + ijx * cIJ + kix * cKI) * factor;
-    const double fiy = (jky * cJK + ijy * cIJ + kiy * cKI) * factor;
-    const double fiz = (jkz * cJK + ijz * cIJ + kiz * cKI) * factor;
-    Fx += fix;
-    Fy += fiy;
-    Fz += fiz;
-    const double u3 = factor * (all2 - 3.0 * allDots);
-    if (N3) {
-      // force on j (:241-247), F_k = -(F_i + F_j)
-      const double jKI = IJdJK * (JKdKI - IJdKI);
-      const double jIJ = -IJdKI * JKdKI + d2jk * d2ki - 5.0 * allDots / d2ij;
-      const double jJK = IJdKI * JKdKI - d2ij * d2ki + 5.0 * allDots / d2jk;
-      const double fjx = (kix * jKI + ijx * jIJ + jkx * jJK) * factor;
-      const double fjy = (kiy * jKI + ijy * jIJ + jky * jJK) * factor;
-      const double fjz = (kiz * jKI + ijz * jIJ + jkz * jJK) * factor;
-      const double fkx = (fix + fjx) * (-1.0), fky = (fiy + fjy) * (-1.0), fkz = (fiz + fjz) * (-1.0);
-      atomicAdd(a.fx + j, fjx);
-      atomicAdd(a.fy + j, fjy);
-      atomicAdd(a.fz + j, fjz);
-      atomicAdd(a.fx + k, fkx);
-      atomicAdd(a.fy + k, fky);
-      atomicAdd(a.fz + k, fkz);
-      if (STATS) {
-        ++st.kN3;
-        ++st.gN3;
-        if (ownedI) {
-          st.upot += u3;
-          st.vir[0] += fix * xi;
-          st.vir[1] += fiy * yi;
-          st.vir[2] += fiz * zi;
-        }
-        if (a.w.own[j] == APB_OWN_OWNED) {
-          st.upot += u3;
-          st.vir[0] += fjx * xj;
-          st.vir[1] += fjy * yj;
-          st.vir[2] += fjz * zj;
-        }
-        if (a.w.own[k] == APB_OWN_OWNED) {
-          st.upot += u3;
-          st.vir[0] += fkx * xk;
-          st.vir[1] += fky * yk;
-          st.vir[2] += fkz * zk;
-        }
-      }
-    } else if (STATS) {
-      ++st.kNoN3;
-      ++st.gNoN3;
-      if (ownedI) {
-        // potentialEnergy3 = factor (allDistsSquared - 3 allDotProducts); virial = f_i * r_i (:269-275)
-        st.upot += u3;
-        st.vir[0] += fix * xi;
-        st.vir[1] += fiy * yi;
-        st.vir[2] += fiz * zi;
-      }
-    }
-  };
-  int *q = queue + threadIdx.x;
-  int p = -1, qq = 0, qn = 0;
-  double xj = 0., yj = 0., zj = 0.;
-  bool done = cnt < 2;
-  do {
-    int pq = -1;
-    if (!done) {
-      if (qq >= cnt || p < 0) {  // next j
-        ++p;
-        qq = p + 1;
-        if (qq >= cnt) {
-          done = true;
-        } else {
-          const int j = a.nbr[static_cast<size_t>(p) * a.w.n + i];
-          xj = a.x[j];
-          yj = a.y[j];
-          zj = a.z[j];
-        }
-      }
-      if (!done) {
-        const int k = a.nbr[static_cast<size_t>(qq) * a.w.n + i];
-        const double jkx = a.x[k] - xj, jky = a.y[k] - yj, jkz = a.z[k] - zj;
-        if (STATS) ++st.dist;
-        // d2ij and d2ki are within the cutoff by construction of the list
-        if (dot3(jkx, jky, jkz, jkx, jky, jkz) <= a.cutoff2) pq = (p << 16) | qq;
-        ++qq;
-      }
-    }
-    if (pq >= 0) {
-      q[qn * LCD_BLOCK] = pq;
-      ++qn;
-    }
-    if (__any_sync(0xffffffffu, qn == LCD_DEPTH)) {
-#pragma unroll 1
-      for (int t = 0; t < LCD_DEPTH; ++t)
-        if (t < qn) triplet(q[t * LCD_BLOCK]);
-      qn = 0;
-    }
-  } while (__any_sync(0xffffffffu, !done));
-#pragma unroll 1
-  for (int t = 0; t < LCD_DEPTH; ++t)
-    if (t < qn) triplet(q[t * LCD_BLOCK]);
-  if (cnt >= 2) {
-    if (N3) {
-      atomicAdd(a.fx + i, Fx);
-      atomicAdd(a.fy + i, Fy);
-      atomicAdd(a.fz + i, Fz);
-    } else {
-      a.fx[i] += Fx;
-      a.fy[i] += Fy;
-      a.fz[i] += Fz;
-    }
-  }
-  if (STATS) ljStatsBlockReduce(st, a.partials);
-}
-
 int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f, apb_traversal_result *out);
 
 static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
@@ -1339,7 +1089,7 @@ static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_trave
   int *maxDev = reinterpret_cast<int *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 32);
   a.maxCount = maxDev;
   APB_CUDA(cudaMemsetAsync(maxDev, 0, 4, h->stream));
-  const int lcKernel = apbLCKernelVariant(n);  // 0 thread (round 1), 1 warp per slot, 2 thread with deferred triplets
+  const int lcKernel = apbLCKernelVariant(n, 0);  // 0 thread per slot over neighbour lists, 1 warp per slot
   const bool lcThreadKernel = lcKernel != 1;
   ATMWarpArgs wa;
   wa.w.g = h->lc;
@@ -1412,20 +1162,6 @@ static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_trave
   a.partials = static_cast<LJStats *>(h->partials.p);
   ++h->launchCount;
   const int sel = (newton3 ? 4 : 0) | (mix ? 2 : 0) | (stats ? 1 : 0);
-  if (lcKernel != 0 && cap < 65536) {
-    switch (sel) {
-      case 0: kATMTripletsDeferred<false, false, false><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
-      case 1: kATMTripletsDeferred<false, true, false><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
-      case 2: kATMTripletsDeferred<true, false, false><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
-      case 3: kATMTripletsDeferred<true, true, false><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
-      case 4: kATMTripletsDeferred<false, false, true><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
-      case 5: kATMTripletsDeferred<false, true, true><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
-      case 6: kATMTripletsDeferred<true, false, true><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
-      default: kATMTripletsDeferred<true, true, true><<<grid, LCD_BLOCK, 0, h->stream>>>(a); break;
-    }
-    APB_CUDA(cudaGetLastError());
-    return apbFinishStats(h, grid, stats, f, out);
-  }
   switch (sel) {
     case 0: kATMTriplets<false, false><<<grid, block, 0, h->stream>>>(a); break;
     case 1: kATMTriplets<false, true><<<grid, block, 0, h->stream>>>(a); break;

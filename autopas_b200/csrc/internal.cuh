@@ -332,16 +332,17 @@ inline void apbMaskResultByFlags(apb_traversal_result &r, int32_t flags) {
   }
 }
 
-// gpuLinkedCells kernels come in three variants (lc_warp.cuh): 0 = one thread per slot, pair arithmetic inline (round 1),
-// 1 = one warp per slot, 2 = one thread per slot with deferred pair arithmetic. Default: 1 below 16 384 slots (one thread
-// per slot cannot fill 148 SMs), 2 above. APB_LC_KERNEL=thread|warp|deferred overrides.
-inline int apbLCKernelVariant(int64_t numSlots) {
+// gpuLinkedCells kernel variants: 0 = one thread per slot walking the stencil cells (round 1), 1 = one warp per slot
+// (lc_warp.cuh), 3 = one thread per slot over cached partner lists (SPH functors). Default: 1 below 16 384 slots (one
+// thread per slot cannot fill 148 SMs), `large` above. APB_LC_KERNEL=thread|warp|list overrides (A/B runs; measured in
+// profiles/r02_lc_kernels.txt).
+inline int apbLCKernelVariant(int64_t numSlots, int large) {
   static const int forced = [] {
     const char *e = getenv("APB_LC_KERNEL");
     if (!e) return -1;
-    return e[0] == 't' ? 0 : (e[0] == 'w' ? 1 : (e[0] == 'l' ? 3 : 2));
+    return e[0] == 't' ? 0 : (e[0] == 'w' ? 1 : 3);
   }();
   if (forced >= 0) return forced;
-  return numSlots < 16384 ? 1 : 2;
+  return numSlots < 16384 ? 1 : large;
 }
 #endif

@@ -87,61 +87,3 @@ __device__ __forceinline__ double lcWarpMax(double v) {
 }
 
 #define LCW_WARPS 8  // warps (= particle slots in flight) per block
-
-// ---- one thread per particle slot, pair arithmetic deferred -----------------------------------------------------------
-// For systems that fill the GPU the cheapest candidate test is the one-thread-per-slot walk (every lane tests its own i
-// against its own j, no per-particle bookkeeping shared by a warp), but evaluating the pair inside that loop makes the
-// whole warp pay for it whenever a single lane hits - at hit rates of 7-15 % practically always. Here a lane only appends
-// its hits to a private queue in shared memory (entry-major: conflict-free); when the first lane of the warp has
-// LCD_DEPTH hits queued, all lanes drain their queues together, so the pair arithmetic runs at the fill level of the
-// queues (~70 %) instead of the hit rate. The walk is written as one convergent loop (every lane carries its own
-// stencil cursor) so that the warp votes are legal.
-#define LCD_DEPTH 16
-#define LCD_BLOCK 128
-
-// `part`: this thread takes part (a live slot whose cell rules allow it). HIGHER: partners in higher slots only.
-// queue: LCD_DEPTH * LCD_BLOCK ints of the block.
-template <bool HIGHER, class Cand, class Heavy>
-__device__ __forceinline__ void lcDeferredWalk(const LCGeom &g, const int *__restrict__ cellStart,
-                                               const int *__restrict__ stencil, int stencilN, bool part, int64_t i, int c,
-                                               bool filterHaloPairs, int *queue, Cand &&cand, Heavy &&heavy) {
-  const int cx = c % g.cellsPerDim[0], cy = (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
-            cz = c / (g.cellsPerDim[0] * g.cellsPerDim[1]);
-  int *q = queue + threadIdx.x;
-  int s = -1, j = 0, j1 = 0, qn = 0;
-  bool done = !part;
-  do {
-    int jj = -1;
-    if (!done) {
-      while (j >= j1) {
-        if (++s >= stencilN) {
-          done = true;
-          break;
-        }
-        const int ox = stencil[3 * s], oy = stencil[3 * s + 1], oz = stencil[3 * s + 2];
-        const int lin = (oz * g.cellsPerDim[1] + oy) * g.cellsPerDim[0] + ox;
-        if (HIGHER && lin < 0) continue;
-        const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
-        if (nx < 0 || ny < 0 || nz < 0 || nx >= g.cellsPerDim[0] || ny >= g.cellsPerDim[1] || nz >= g.cellsPerDim[2]) continue;
-        if (filterHaloPairs && !apbCellCanOwn(g, nx, ny, nz)) continue;
-        j = cellStart[c + lin];
-        j1 = cellStart[c + lin + 1];
-        if (HIGHER) j = max(j, static_cast<int>(i) + 1);
-      }
-      if (!done) jj = j++;
-    }
-    if (jj >= 0 && cand(jj)) {
-      q[qn * LCD_BLOCK] = jj;
-      ++qn;
-    }
-    if (__any_sync(0xffffffffu, qn == LCD_DEPTH)) {
-#pragma unroll 1
-      for (int k = 0; k < LCD_DEPTH; ++k)
-        if (k < qn) heavy(q[k * LCD_BLOCK]);
-      qn = 0;
-    }
-  } while (__any_sync(0xffffffffu, !done));
-#pragma unroll 1
-  for (int k = 0; k < LCD_DEPTH; ++k)
-    if (k < qn) heavy(q[k * LCD_BLOCK]);
-}

@@ -269,84 +269,6 @@ __global__ void __launch_bounds__(LCW_WARPS * 32) kLJLinkedCellsWarp(LCArgs a, L
   if (STATS) ljStatsBlockReduce(st, a.partials);
 }
 
-// One thread per slot with the pair arithmetic deferred through per-lane hit queues (lcDeferredWalk, lc_warp.cuh): the
-// variant for systems that fill the GPU. Same rules as above.
-template <bool MIX, bool STATS, bool N3>
-__global__ void __launch_bounds__(LCD_BLOCK) kLJLinkedCellsDeferred(LCArgs a) {
-  __shared__ int queue[LCD_DEPTH * LCD_BLOCK];
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  LJStats st;
-  ljStatsZero(st);
-  const LCGeom &g = a.g;
-  const int ownI = i < a.n ? a.own[i] : APB_OWN_DUMMY;
-  const int c = ownI != APB_OWN_DUMMY ? a.slotCell[i] : 0;
-  const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
-                                     c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
-  const bool part = ownI != APB_OWN_DUMMY && (canOwnI || N3 || a.processHaloCells);
-  const int64_t ii = part ? i : 0;
-  const double xi = a.x[ii], yi = a.y[ii], zi = a.z[ii];
-  const int ti = MIX ? a.type[ii] : 0;
-  const double wI = ownI == APB_OWN_OWNED ? 1. : 0.;
-  const int self0 = a.cellStart[c], self1 = a.cellStart[c + 1];
-  double fxa = 0., fya = 0., fza = 0.;
-  lcDeferredWalk<N3>(
-      g, a.cellStart, a.stencil + 3 * APB_MAX_STENCIL, a.stencilN, part, i, c, !canOwnI, queue,
-      [&](int j) {
-        if (!N3 && j == i) return false;
-        if (a.own[j] == APB_OWN_DUMMY) return false;
-        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
-        const bool self = j >= self0 && j < self1;
-        // counters: a same-cell pair is one newton3 evaluation in the reference, whatever the newton3 flag
-        if (STATS && (!self || N3 || j > i)) ++st.dist;
-        return ljDist2(drx, dry, drz) <= a.p.cutoff2;
-      },
-      [&](int j) {
-        const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
-        const double dr2 = ljDist2(drx, dry, drz);
-        double upot6;
-        const double fac = ljEval<MIX>(a.p, dr2, ti, MIX ? a.type[j] : 0, upot6);
-        const double fx = drx * fac, fy = dry * fac, fz = drz * fac;
-        fxa += fx;
-        fya += fy;
-        fza += fz;
-        if (N3) {
-          atomicAdd(&a.fx[j], -fx);
-          atomicAdd(&a.fy[j], -fy);
-          atomicAdd(&a.fz[j], -fz);
-        }
-        if (STATS) {
-          const double wJ = a.own[j] == APB_OWN_OWNED ? 1. : 0.;
-          const double wgt = N3 ? wI + wJ : wI;
-          st.upot += upot6 * wgt;
-          st.vir[0] += drx * fx * wgt;
-          st.vir[1] += dry * fy * wgt;
-          st.vir[2] += drz * fz * wgt;
-          const bool self = j >= self0 && j < self1;
-          if (!self || N3 || j > i) {
-            if (N3 || self) {
-              ++st.kN3;
-              ++st.gN3;
-            } else {
-              ++st.kNoN3;
-              ++st.gNoN3;
-            }
-          }
-        }
-      });
-  if (part) {
-    if (N3) {
-      atomicAdd(&a.fx[i], fxa);
-      atomicAdd(&a.fy[i], fya);
-      atomicAdd(&a.fz[i], fza);
-    } else {
-      a.fx[i] += fxa;
-      a.fy[i] += fya;
-      a.fz[i] += fza;
-    }
-  }
-  if (STATS) ljStatsBlockReduce(st, a.partials);
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // VerletClusterLists, list-faithful traversal: every listed cluster pair costs M x M distance evaluations
 // (VCLClusterFunctor.h:38-96). One thread per slot; the M lanes of a cluster walk the cluster's list together and read
@@ -573,8 +495,9 @@ int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3,
   int grid = apbDivUp(n, block);
   if (n == 0) return apbFinishStats(h, 0, stats, f, out);
   // gpuLinkedCells kernel variant: one warp per slot while the system is too small to fill the GPU with one thread per
-  // slot, else one thread per slot with deferred pair arithmetic; APB_LC_KERNEL=thread|warp|deferred overrides (A/B runs)
-  const int lcKernel = apbLCKernelVariant(n);
+  // slot (3x faster at 10 k slots), else one thread per slot; APB_LC_KERNEL=thread|warp overrides (A/B runs,
+  // profiles/r02_lc_kernels.txt)
+  const int lcKernel = apbLCKernelVariant(n, 0);
   if (h->cfg.container == APB_CONTAINER_LINKED_CELLS && lcKernel == 1)
     grid = static_cast<int>(std::min<int64_t>(apbDivUp(n, LCW_WARPS), 148 * 16));
   APB_CHECK(apbEnsure(h, h->partials, sizeof(LJStats) * grid));
@@ -599,10 +522,8 @@ int apbComputeLJ(apb_handle h, int traversal, const apb_functor *f, int newton3,
     a.processHaloCells = (f->flags & APB_FUNCTOR_COUNT_FLOPS) ? 1 : 0;
     a.p = p;
     a.partials = static_cast<LJStats *>(h->partials.p);
-    if (lcKernel == 0) {
+    if (lcKernel != 1) {
       LJ_DISPATCH(kLJLinkedCells, grid, block, a);
-    } else if (lcKernel == 2) {
-      LJ_DISPATCH(kLJLinkedCellsDeferred, grid, LCD_BLOCK, a);
     } else {
       LCWarpGeom w;
       w.g = h->lc;
