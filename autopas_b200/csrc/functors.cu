@@ -445,20 +445,29 @@ static int ensureLCLists(apb_handle h, bool half) {
 struct SPHListArgs {
   SPHArgs s;
   const int *nbrCount, *nbr;
-  const double *pOverRho2, *gradWNorm;  // hydro force: per-particle factors, kSPHPrepareHydro
+  // partner attributes packed per particle (kSPHPack): a pair reads 2 (density) or 6 (hydro force) 16-byte words from
+  // one to three 32-byte sectors instead of 4 / 11 doubles from as many columns - the list kernels are bound by the
+  // sectors their gathers touch, not by arithmetic
+  const double2 *pack;
 };
 
-// Per-particle factors of the hydro-force pair term that the reference recomputes for every pair
-// (SPHCalcHydroForceFunctor.h:86-96: P_j / rho_j^2; SPHKernels.cpp gradW: 16 / pi / H_j^3): two of the nine divisions of
-// a pair. Same operations on the same operands, so the results are bit-identical to the per-pair evaluation.
-__global__ void kSPHPrepareHydro(int64_t n, const double *__restrict__ pressure, const double *__restrict__ density,
-                                 const double *__restrict__ smth, double *__restrict__ pOverRho2,
-                                 double *__restrict__ gradWNorm) {
+// density: {x, y, z, m}. hydro force: {x, y, z, m, vx, vy, vz, c, rho, P / rho^2, h, 16 / pi / H^3}; the last two
+// per-particle factors are what the reference recomputes for every pair (SPHCalcHydroForceFunctor.h:86-96;
+// SPHKernels.cpp gradW) - same operations on the same operands, so bit-identical.
+template <bool HYDRO>
+__global__ void kSPHPack(int64_t n, SPHArgs a, double2 *__restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double rho = density[i], H = SPH_SUPPORT * smth[i];
-  pOverRho2[i] = pressure[i] / __dmul_rn(rho, rho);
-  gradWNorm[i] = 16.0 / SPH_PI / __dmul_rn(__dmul_rn(H, H), H);
+  double2 *o = out + static_cast<size_t>(i) * (HYDRO ? 6 : 2);
+  o[0] = make_double2(a.x[i], a.y[i]);
+  o[1] = make_double2(a.z[i], a.mass[i]);
+  if (HYDRO) {
+    const double rho = a.density[i], h = a.smth[i], H = SPH_SUPPORT * h;
+    o[2] = make_double2(a.vx[i], a.vy[i]);
+    o[3] = make_double2(a.vz[i], a.snd[i]);
+    o[4] = make_double2(rho, a.pressure[i] / __dmul_rn(rho, rho));
+    o[5] = make_double2(h, 16.0 / SPH_PI / __dmul_rn(__dmul_rn(H, H), H));
+  }
 }
 // sphGradWScale with the normalisation 16 / pi / H^3 handed in
 __device__ __forceinline__ double sphGradWScaleNorm(double drabs, double h, double norm) {
@@ -482,9 +491,10 @@ __global__ void __launch_bounds__(128) kSPHDensityList(SPHListArgs la) {
   double rho = 0.;
   for (int p = 0; p < cnt; ++p) {
     const int j = la.nbr[static_cast<size_t>(p) * a.w.n + i];
-    const double drx = a.x[j] - xi, dry = a.y[j] - yi, drz = a.z[j] - zi;
+    const double2 q0 = __ldg(la.pack + 2 * static_cast<size_t>(j)), q1 = __ldg(la.pack + 2 * static_cast<size_t>(j) + 1);
+    const double drx = q0.x - xi, dry = q0.y - yi, drz = q1.x - zi;
     const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
-    rho += __dmul_rn(a.mass[j], sphW(dr2, hi));
+    rho += __dmul_rn(q1.y, sphW(dr2, hi));
     if (N3) {
       const double d2 = __dmul_rn(mi, sphW(dr2, a.smth[j]));
       if (d2 != 0.) atomicAdd(a.density + j, d2);
@@ -509,26 +519,28 @@ __global__ void __launch_bounds__(128) kSPHHydroList(SPHListArgs la) {
   const double cut = hi * SPH_SUPPORT;
   const double cut2 = __dmul_rn(cut, cut);
   const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
-  const double normI = la.gradWNorm[i];
+  const double normI = la.pack[6 * static_cast<size_t>(i) + 5].y;
   double accx = 0., accy = 0., accz = 0., eng = 0., vmax = 0.;
   for (int p = 0; p < cnt; ++p) {
     const int j = la.nbr[static_cast<size_t>(p) * a.w.n + i];
-    const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+    const double2 *pj = la.pack + 6 * static_cast<size_t>(j);
+    const double2 q0 = __ldg(pj), q1 = __ldg(pj + 1);
+    const double drx = xi - q0.x, dry = yi - q0.y, drz = zi - q1.x;
     const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
     if (dr2 >= cut2) continue;
-    const double dvx = vxi - a.vx[j], dvy = vyi - a.vy[j], dvz = vzi - a.vz[j];
+    const double2 q2 = __ldg(pj + 2), q3 = __ldg(pj + 3), q4 = __ldg(pj + 4), q5 = __ldg(pj + 5);
+    const double mj = q1.y, cj = q3.y, rhoj = q4.x, PjOverRho2 = q4.y, hj = q5.x, normJ = q5.y;
+    const double dvx = vxi - q2.x, dvy = vyi - q2.y, dvz = vzi - q3.x;
     const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
     const double drabs = sqrt(dr2);
     const double wij = (dvdr < 0) ? dvdr / drabs : 0;
-    const double vsig = __dadd_rn(__dadd_rn(ci, a.snd[j]), -__dmul_rn(3.0, wij));
+    const double vsig = __dadd_rn(__dadd_rn(ci, cj), -__dmul_rn(3.0, wij));
     vmax = fmax(vmax, vsig);
-    const double rhoj = a.density[j], mj = a.mass[j];
     const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
-    const double gi = sphGradWScaleNorm(drabs, hi, normI), gj = sphGradWScaleNorm(drabs, a.smth[j], la.gradWNorm[j]);
+    const double gi = sphGradWScaleNorm(drabs, hi, normI), gj = sphGradWScaleNorm(drabs, hj, normJ);
     const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
     const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
     const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
-    const double PjOverRho2 = la.pOverRho2[j];
     const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
     const double si = __dmul_rn(scale, mj);
     accx -= __dmul_rn(gx, si);
@@ -595,14 +607,14 @@ static int computeSPH(apb_handle h, const apb_functor *f, int newton3, apb_trave
     la.nbrCount = static_cast<const int *>(h->nbrCount.p);
     la.nbr = static_cast<const int *>(h->nbrList.p);
     const int lgrid = apbDivUp(n, 128);
-    la.pOverRho2 = la.gradWNorm = nullptr;
-    if (f->kind == APB_FUNCTOR_SPH_HYDRO) {
-      APB_CHECK(apbEnsure(h, h->sortK2, sizeof(double) * 2 * n));  // scratch of the rebuild, free between rebuilds
-      double *tmp = static_cast<double *>(h->sortK2.p);
-      la.pOverRho2 = tmp;
-      la.gradWNorm = tmp + n;
-      ++h->launchCount, kSPHPrepareHydro<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, a.pressure, a.density, a.smth, tmp, tmp + n);
-    }
+    const bool hydro = f->kind == APB_FUNCTOR_SPH_HYDRO;
+    APB_CHECK(apbEnsure(h, h->sortK2, sizeof(double2) * (hydro ? 6 : 2) * n));  // scratch of the rebuild, free between rebuilds
+    la.pack = static_cast<const double2 *>(h->sortK2.p);
+    ++h->launchCount;
+    if (hydro)
+      kSPHPack<true><<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, a, static_cast<double2 *>(h->sortK2.p));
+    else
+      kSPHPack<false><<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, a, static_cast<double2 *>(h->sortK2.p));
     ++h->launchCount;
     if (f->kind == APB_FUNCTOR_SPH_DENSITY) {
       if (newton3)
