@@ -480,6 +480,14 @@ __device__ __forceinline__ double sphGradWScaleNorm(double drabs, double h, doub
   return r / __dadd_rn(__dmul_rn(drabs, H), __dmul_rn(1.0e-6, h));
 }
 
+// The list kernels are bound by the latency of the partner gathers (ncu: long-scoreboard stalls dominate), so the
+// entries are taken SPH_LIST_BATCH at a time: all indices, then all packed partner words, are in flight together before
+// the first pair is evaluated.
+#define SPH_LIST_BATCH 4
+#ifndef SPH_HYDRO_BATCH
+#define SPH_HYDRO_BATCH 2  // 12 registers per entry in flight: 4 entries cost a third of the resident warps
+#endif
+
 template <bool N3>
 __global__ void __launch_bounds__(128) kSPHDensityList(SPHListArgs la) {
   const SPHArgs &a = la.s;
@@ -489,15 +497,27 @@ __global__ void __launch_bounds__(128) kSPHDensityList(SPHListArgs la) {
   if (cnt == 0) return;
   const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
   double rho = 0.;
-  for (int p = 0; p < cnt; ++p) {
-    const int j = la.nbr[static_cast<size_t>(p) * a.w.n + i];
-    const double2 q0 = __ldg(la.pack + 2 * static_cast<size_t>(j)), q1 = __ldg(la.pack + 2 * static_cast<size_t>(j) + 1);
-    const double drx = q0.x - xi, dry = q0.y - yi, drz = q1.x - zi;
-    const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
-    rho += __dmul_rn(q1.y, sphW(dr2, hi));
-    if (N3) {
-      const double d2 = __dmul_rn(mi, sphW(dr2, a.smth[j]));
-      if (d2 != 0.) atomicAdd(a.density + j, d2);
+  for (int p0 = 0; p0 < cnt; p0 += SPH_LIST_BATCH) {
+    int j[SPH_LIST_BATCH];
+    double2 q0[SPH_LIST_BATCH], q1[SPH_LIST_BATCH];
+#pragma unroll
+    for (int b = 0; b < SPH_LIST_BATCH; ++b) j[b] = p0 + b < cnt ? la.nbr[static_cast<size_t>(p0 + b) * a.w.n + i] : -1;
+#pragma unroll
+    for (int b = 0; b < SPH_LIST_BATCH; ++b) {
+      const size_t e = 2 * static_cast<size_t>(max(j[b], 0));
+      q0[b] = __ldg(la.pack + e);
+      q1[b] = __ldg(la.pack + e + 1);
+    }
+#pragma unroll
+    for (int b = 0; b < SPH_LIST_BATCH; ++b) {
+      if (j[b] < 0) continue;
+      const double drx = q0[b].x - xi, dry = q0[b].y - yi, drz = q1[b].x - zi;
+      const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+      rho += __dmul_rn(q1[b].y, sphW(dr2, hi));
+      if (N3) {
+        const double d2 = __dmul_rn(mi, sphW(dr2, a.smth[j[b]]));
+        if (d2 != 0.) atomicAdd(a.density + j[b], d2);
+      }
     }
   }
   if (N3)
@@ -521,42 +541,54 @@ __global__ void __launch_bounds__(128) kSPHHydroList(SPHListArgs la) {
   const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
   const double normI = la.pack[6 * static_cast<size_t>(i) + 5].y;
   double accx = 0., accy = 0., accz = 0., eng = 0., vmax = 0.;
-  for (int p = 0; p < cnt; ++p) {
-    const int j = la.nbr[static_cast<size_t>(p) * a.w.n + i];
-    const double2 *pj = la.pack + 6 * static_cast<size_t>(j);
-    const double2 q0 = __ldg(pj), q1 = __ldg(pj + 1);
-    const double drx = xi - q0.x, dry = yi - q0.y, drz = zi - q1.x;
-    const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
-    if (dr2 >= cut2) continue;
-    const double2 q2 = __ldg(pj + 2), q3 = __ldg(pj + 3), q4 = __ldg(pj + 4), q5 = __ldg(pj + 5);
-    const double mj = q1.y, cj = q3.y, rhoj = q4.x, PjOverRho2 = q4.y, hj = q5.x, normJ = q5.y;
-    const double dvx = vxi - q2.x, dvy = vyi - q2.y, dvz = vzi - q3.x;
-    const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
-    const double drabs = sqrt(dr2);
-    const double wij = (dvdr < 0) ? dvdr / drabs : 0;
-    const double vsig = __dadd_rn(__dadd_rn(ci, cj), -__dmul_rn(3.0, wij));
-    vmax = fmax(vmax, vsig);
-    const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
-    const double gi = sphGradWScaleNorm(drabs, hi, normI), gj = sphGradWScaleNorm(drabs, hj, normJ);
-    const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
-    const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
-    const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
-    const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
-    const double si = __dmul_rn(scale, mj);
-    accx -= __dmul_rn(gx, si);
-    accy -= __dmul_rn(gy, si);
-    accz -= __dmul_rn(gz, si);
-    const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
-    const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
-    eng += __dmul_rn(gdv, scale2i);
-    if (N3) {
-      atomicMaxPositive(a.vsigmax + j, vsig);
-      const double sj = __dmul_rn(scale, mi);
-      atomicAdd(a.ax + j, __dmul_rn(gx, sj));
-      atomicAdd(a.ay + j, __dmul_rn(gy, sj));
-      atomicAdd(a.az + j, __dmul_rn(gz, sj));
-      const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
-      atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
+  for (int p0 = 0; p0 < cnt; p0 += SPH_HYDRO_BATCH) {
+    int jb[SPH_HYDRO_BATCH];
+    double2 w[SPH_HYDRO_BATCH][6];
+#pragma unroll
+    for (int b = 0; b < SPH_HYDRO_BATCH; ++b) jb[b] = p0 + b < cnt ? la.nbr[static_cast<size_t>(p0 + b) * a.w.n + i] : -1;
+#pragma unroll
+    for (int b = 0; b < SPH_HYDRO_BATCH; ++b) {
+      const double2 *pj = la.pack + 6 * static_cast<size_t>(max(jb[b], 0));
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w[b][k] = __ldg(pj + k);
+    }
+#pragma unroll
+    for (int b = 0; b < SPH_HYDRO_BATCH; ++b) {
+      const int j = jb[b];
+      if (j < 0) continue;
+      const double2 q0 = w[b][0], q1 = w[b][1], q2 = w[b][2], q3 = w[b][3], q4 = w[b][4], q5 = w[b][5];
+      const double drx = xi - q0.x, dry = yi - q0.y, drz = zi - q1.x;
+      const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
+      if (dr2 >= cut2) continue;
+      const double mj = q1.y, cj = q3.y, rhoj = q4.x, PjOverRho2 = q4.y, hj = q5.x, normJ = q5.y;
+      const double dvx = vxi - q2.x, dvy = vyi - q2.y, dvz = vzi - q3.x;
+      const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
+      const double drabs = sqrt(dr2);
+      const double wij = (dvdr < 0) ? dvdr / drabs : 0;
+      const double vsig = __dadd_rn(__dadd_rn(ci, cj), -__dmul_rn(3.0, wij));
+      vmax = fmax(vmax, vsig);
+      const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
+      const double gi = sphGradWScaleNorm(drabs, hi, normI), gj = sphGradWScaleNorm(drabs, hj, normJ);
+      const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
+      const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
+      const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
+      const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
+      const double si = __dmul_rn(scale, mj);
+      accx -= __dmul_rn(gx, si);
+      accy -= __dmul_rn(gy, si);
+      accz -= __dmul_rn(gz, si);
+      const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
+      const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
+      eng += __dmul_rn(gdv, scale2i);
+      if (N3) {
+        atomicMaxPositive(a.vsigmax + j, vsig);
+        const double sj = __dmul_rn(scale, mi);
+        atomicAdd(a.ax + j, __dmul_rn(gx, sj));
+        atomicAdd(a.ay + j, __dmul_rn(gy, sj));
+        atomicAdd(a.az + j, __dmul_rn(gz, sj));
+        const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
+        atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
+      }
     }
   }
   if (N3) {
