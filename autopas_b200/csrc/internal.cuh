@@ -109,6 +109,7 @@ struct apb_handle_s {
   DevBuf prNumStaged, prStagedStart, prStaged, prWarpLen, prWarpStart, prLists, prTileFirst, prTileNum, prTileWarp;
   DevBuf prMasks, prUsed, prCbase, prNumCompact, prCompactSlot;
   DevBuf prEntryLo;
+  DevBuf prStageEarly;  // fixed-stride rows of staged sets written by the counting pass (kPrunedStage<false>)
   DevBuf prTileHalo, prTileOrder;  // per tile: stages a halo copy; tiles ordered interior first (+ the interior count)
   int prunedPart = 0;              // 0: whole traversal; 1 / 2: interior / boundary half of a split step (apb_run_steps)
   int prunedCap = 0;  // staged particles incl. the 16 sentinel slots the lists were built for (1280, 2048 or 4096)

@@ -54,10 +54,15 @@ struct PrunedArgs {
 
 // ---- stage sets ----------------------------------------------------------------------------------------------------
 // One CTA per tile: gather {own clusters} U {listed neighbours of its non-halo clusters}, sort, unique.
+// The counting pass (FILL = false) also keeps its result in a fixed-stride scratch row of the tile when it fits
+// (`early`, `earlyStride`): the sets then only have to be compacted into their final place (kPrunedStageCompact) instead
+// of being gathered, sorted and made unique a second time. A tile that does not fit raises overflow[7] and the FILL
+// pass runs as before.
 template <bool FILL>
 __global__ void __launch_bounds__(PR_TILE) kPrunedStage(PrunedArgs a, int *__restrict__ numStaged,
                                                         const int *__restrict__ stagedStart, int *__restrict__ staged,
-                                                        int *__restrict__ maxStaged, int *__restrict__ overflow) {
+                                                        int *__restrict__ maxStaged, int *__restrict__ overflow,
+                                                        int *__restrict__ early, int earlyStride) {
   __shared__ int cand[PR_CAND_MAX];
   __shared__ int nCand;
   __shared__ int chunkCount[PR_TILE];
@@ -135,12 +140,27 @@ __global__ void __launch_bounds__(PR_TILE) kPrunedStage(PrunedArgs a, int *__res
     if (threadIdx.x == 0) {
       numStaged[tile] = total;
       atomicMax(maxStaged, total);
+      if (early && total > earlyStride) atomicExch(overflow + 7, 1);  // (flag word at scratch + 64)
+    }
+    if (early && total <= earlyStride) {
+      int pos = tile * earlyStride + chunkCount[threadIdx.x] - cnt;
+      for (int t = b; t < e; ++t)
+        if (t == 0 || cand[t] != cand[t - 1]) early[pos++] = cand[t];
     }
   } else {
     int pos = stagedStart[tile] + chunkCount[threadIdx.x] - cnt;
     for (int t = b; t < e; ++t)
       if (t == 0 || cand[t] != cand[t - 1]) staged[pos++] = cand[t];
   }
+}
+
+// fixed-stride rows of the counting pass -> the compact sets; one warp per tile
+__global__ void kPrunedStageCompact(int numTiles, const int *__restrict__ numStaged, const int *__restrict__ stagedStart,
+                                    const int *__restrict__ early, int earlyStride, int *__restrict__ staged) {
+  const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (tile >= numTiles) return;
+  const int n = numStaged[tile], dst = stagedStart[tile];
+  for (int t = lane; t < n; t += 32) staged[dst + t] = early[static_cast<size_t>(tile) * earlyStride + t];
 }
 
 // ---- tile table ----------------------------------------------------------------------------------------------------
@@ -653,15 +673,24 @@ int apbBuildPruned(apb_handle h, int newton3) {
   long long *totals = reinterpret_cast<long long *>(scratch);
   int *maxStagedDev = reinterpret_cast<int *>(scratch + 32), *overflowDev = reinterpret_cast<int *>(scratch + 36);
   int *maxCompactDev = reinterpret_cast<int *>(scratch + 40);
-  APB_CUDA(cudaMemsetAsync(scratch + 32, 0, 24, h->stream));
+  APB_CUDA(cudaMemsetAsync(scratch + 32, 0, 36, h->stream));  // ... + the early-overflow word at scratch + 64
   APB_CUDA(cudaMemsetAsync(numStaged, 0, sizeof(int) * (numTiles + 1), h->stream));
-  ++h->launchCount, kPrunedStage<false><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, nullptr, nullptr, maxStagedDev, overflowDev);
+  // scratch rows for the sets found by the counting pass: as many clusters as a staged tile can hold (4096 particles)
+  const int earlyStride = 4096 >> logM;
+  int *early = nullptr;
+  if (static_cast<size_t>(numTiles) * earlyStride * sizeof(int) <= (size_t(1) << 30)) {
+    APB_CHECK(apbEnsure(h, h->prStageEarly, sizeof(int) * static_cast<size_t>(numTiles) * earlyStride));
+    early = static_cast<int *>(h->prStageEarly.p);
+  }
+  ++h->launchCount, kPrunedStage<false><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, nullptr, nullptr, maxStagedDev, overflowDev, early, earlyStride);
   APB_CUDA(cudaGetLastError());
   APB_CHECK(apbExclusiveScan(h, numStaged, stagedStart, numTiles + 1, totals));
   long long totalStaged = 0;
   int hostMisc[4] = {0, 0, 0, 0};
   APB_CUDA(cudaMemcpyAsync(&totalStaged, totals, 8, cudaMemcpyDeviceToHost, h->stream));
-  APB_CUDA(cudaMemcpyAsync(hostMisc, scratch + 32, 8, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaMemcpyAsync(hostMisc, scratch + 32, 8, cudaMemcpyDeviceToHost, h->stream));  // {largest set, overflow}
+  int earlyOverflow = 0;
+  APB_CUDA(cudaMemcpyAsync(&earlyOverflow, scratch + 64, 4, cudaMemcpyDeviceToHost, h->stream));
   APB_CUDA(cudaStreamSynchronize(h->stream));
   if (hostMisc[1]) return h->fail(APB_ERR_NOT_APPLICABLE, "gpuvcl_pruned: a tile interacts with more than " +
                                                               std::to_string(PR_CAND_MAX) +
@@ -680,7 +709,11 @@ int apbBuildPruned(apb_handle h, int newton3) {
   APB_CHECK(apbEnsure(h, h->prCompactSlot, sizeof(int) * stagedAlloc * M));
   APB_CHECK(apbEnsure(h, h->prMasks, sizeof(unsigned) * static_cast<size_t>(h->numPairs + h->numClusters + 1) * M));
   int *staged = static_cast<int *>(h->prStaged.p);
-  ++h->launchCount, kPrunedStage<true><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, stagedStart, staged, maxStagedDev, overflowDev);
+  if (early && !earlyOverflow)
+    ++h->launchCount, kPrunedStageCompact<<<apbDivUp(static_cast<int64_t>(numTiles) * 32, 256), 256, 0, h->stream>>>(
+        numTiles, numStaged, stagedStart, early, earlyStride, staged);
+  else
+    ++h->launchCount, kPrunedStage<true><<<numTiles, PR_TILE, 0, h->stream>>>(a, numStaged, stagedStart, staged, maxStagedDev, overflowDev, nullptr, 0);
   APB_CUDA(cudaGetLastError());
   MaskOut o;
   o.masks = static_cast<unsigned *>(h->prMasks.p);

@@ -357,7 +357,7 @@ extern "C" int apb_destroy(apb_handle h) {
   DevBuf *ctrl[] = {&h->thermoDev, &h->rAtRebuild, &h->remBuf};
   for (DevBuf *b : ctrl)
     if (b->p) cudaFree(b->p);
-  DevBuf *more[] = {&h->prTileFirst, &h->prTileNum, &h->prTileWarp, &h->loopResults, &h->invPerm, &h->xbuf[0], &h->xbuf[1], &h->xbuf[2], &h->xbuf[3], &h->massDev};
+  DevBuf *more[] = {&h->prStageEarly, &h->prTileFirst, &h->prTileNum, &h->prTileWarp, &h->loopResults, &h->invPerm, &h->xbuf[0], &h->xbuf[1], &h->xbuf[2], &h->xbuf[3], &h->massDev};
   for (DevBuf *b : more)
     if (b->p) cudaFree(b->p);
   for (int d = 0; d < 3; ++d)

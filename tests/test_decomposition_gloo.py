@@ -95,6 +95,7 @@ def _worker(rank, world, port, n_per_dim, result_dir):
         L = gmax - gmin
         P = np.concatenate([pos, (np.arange(n) + rank * n)[:, None].astype(float)], axis=1)  # x, y, z, id
         own = np.ones(n, dtype=np.int64)
+        links = []  # per dimension: (send slots to the left, to the right, receive slots from the left, from the right)
         for d in range(3):
             left, right = _select(P[:, :3], own, d, bmin[d], bmax[d])
             at_min, at_max = abs(bmin[d] - gmin[d]) < 1e-9, abs(bmax[d] - gmax[d]) < 1e-9
@@ -105,9 +106,22 @@ def _worker(rank, world, port, n_per_dim, result_dir):
                 to_right[:, d] -= L[d]
             from_right = _exchange(rank, world, to_left, nb[2 * d], nb[2 * d + 1])   # what my right neighbour sent left
             from_left = _exchange(rank, world, to_right, nb[2 * d + 1], nb[2 * d])
+            first = len(P)
+            links.append((np.flatnonzero(left), np.flatnonzero(right), np.arange(first, first + len(from_left)),
+                          np.arange(first + len(from_left), first + len(from_left) + len(from_right))))
             P = np.concatenate([P, from_left, from_right])
             own = np.concatenate([own, np.full(len(from_left) + len(from_right), 2)])
         halos = P[own == 2]
+        # ---- apb_refresh_halo_columns (dynamics.cu: refreshHaloColumns): a column that changed on the owners reaches
+        # every copy through the recorded links, dimension by dimension (copies of copies are fed by the refreshed copy)
+        col = np.where(own == 1, np.cos(P[:, 3]) + 2.0, np.nan)  # new owner values by id; copies stale (NaN)
+        for d in range(3):
+            sl, sr, rl, rr = links[d]
+            pack = lambda idx: np.stack([col[idx]] * 4, axis=1)  # noqa: E731  (4 doubles per entry, like _exchange expects)
+            col[rr] = _exchange(rank, world, pack(sl), nb[2 * d], nb[2 * d + 1])[:, 0]
+            col[rl] = _exchange(rank, world, pack(sr), nb[2 * d + 1], nb[2 * d])[:, 0]
+        assert not np.isnan(col).any()
+        np.testing.assert_array_equal(col, np.cos(P[:, 3]) + 2.0)  # every copy carries its owner's value
         # ---- brute force: every periodic image of every particle of the global system inside my halo shell ----
         allpos = [torch.zeros((n, 3), dtype=torch.float64) for _ in range(world)]
         dist.all_gather(allpos, torch.from_numpy(np.ascontiguousarray(pos)))
