@@ -859,7 +859,9 @@ static int exchangeDim(apb_handle h, int d, int mode, int64_t *outSent = nullptr
   const bool remote = h->nranks > 1 && !(left == h->myRank && right == h->myRank);
   if (remote && h->p2pState == 1 && per && h->p2pPeer[d][0] && h->p2pPeer[d][1]) {
     // counts through the peer arenas: no NCCL round and one host read-back (send and receive counts together)
-    const long long seq = static_cast<long long>(++h->p2pCountSeq);
+    // sequence number and slot parity per dimension: consecutive exchanges of a dimension alternate between its two count
+    // slots whatever the number of exchanging dimensions (a rank may run one exchange ahead of its neighbour)
+    const long long seq = static_cast<long long>(++h->p2pCountSeq[d]);
     const int parity = static_cast<int>(seq & 1);
     const int to0 = left == right ? 0 : 1, to1 = left == right ? 1 : 0;  // same matching as the payload (see the refresh)
     ++h->launchCount, kPushCounts<<<1, 1, 0, h->stream>>>(totals, p2pCountSlot(h->p2pPeer[d][0], h->p2pCap, d, to0, parity),

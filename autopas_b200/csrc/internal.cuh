@@ -148,7 +148,7 @@ struct apb_handle_s {
   size_t p2pCap = 0;                       // doubles per region
   void *p2pPeer[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};  // neighbour arenas (mapped)
   std::vector<std::pair<int, void *>> p2pOpened;  // rank -> mapped base (one mapping per distinct neighbour)
-  unsigned long long p2pSeq = 0, p2pCountSeq = 0;
+  unsigned long long p2pSeq = 0, p2pCountSeq[3] = {0, 0, 0};
   int p2pState = 0;                        // 0 not set up yet, 1 ready, -1 not applicable
   int *p2pCounters = nullptr;              // 3 block counters (last-block-signals pattern)
   bool haloLinksValid = false;

@@ -675,8 +675,9 @@ int apbBuildPruned(apb_handle h, int newton3) {
   int *maxCompactDev = reinterpret_cast<int *>(scratch + 40);
   APB_CUDA(cudaMemsetAsync(scratch + 32, 0, 36, h->stream));  // ... + the early-overflow word at scratch + 64
   APB_CUDA(cudaMemsetAsync(numStaged, 0, sizeof(int) * (numTiles + 1), h->stream));
-  // scratch rows for the sets found by the counting pass: as many clusters as a staged tile can hold (4096 particles)
-  const int earlyStride = 4096 >> logM;
+  // scratch rows for the sets found by the counting pass: as many clusters as kPrunedMasks can stage in shared memory
+  // (a larger set fails below anyway)
+  const int earlyStride = static_cast<int>(200 * 1024 / (static_cast<size_t>(M) * 16 + 12)) + 1;
   int *early = nullptr;
   if (static_cast<size_t>(numTiles) * earlyStride * sizeof(int) <= (size_t(1) << 30)) {
     APB_CHECK(apbEnsure(h, h->prStageEarly, sizeof(int) * static_cast<size_t>(numTiles) * earlyStride));
