@@ -20,6 +20,7 @@ PARTICLE_LJ, PARTICLE_MULTISITE, PARTICLE_SPH = 0, 1, 2
 FUNCTOR_LJ, FUNCTOR_LJ_MULTISITE, FUNCTOR_ATM, FUNCTOR_SPH_DENSITY, FUNCTOR_SPH_HYDRO = range(5)
 FLAG_APPLY_SHIFT, FLAG_USE_MIXING, FLAG_CALC_GLOBALS, FLAG_COUNT_FLOPS, FLAG_VIRIAL_TRACE = 1, 2, 4, 8, 16
 OWN_DUMMY, OWN_OWNED, OWN_HALO = 0, 1, 2
+WIRE_RECORD_BYTES = 120  # md-flexible's MPI record of a MoleculeLJ (ParticleSerializationTools.cpp:66)
 
 COLUMNS = ["X", "Y", "Z", "VX", "VY", "VZ", "FX", "FY", "FZ", "OLDFX", "OLDFY", "OLDFZ", "Q0", "Q1", "Q2", "Q3", "TX",
            "TY", "TZ", "MASS", "SMTH", "DENSITY", "PRESSURE", "SNDSPEED", "ENGDOT", "VSIGMAX"]
@@ -142,6 +143,8 @@ SIGNATURES = {
     "apb_update_container": (_i32, [_H, _i32, ctypes.POINTER(_i64)]),
     "apb_get_leavers": (_i32, [_H, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "apb_get_leaver_column": (_i32, [_H, _i32, _vp]),
+    "apb_serialize_particles": (_i32, [_H, _i32, _vp, _i64, _vp]),
+    "apb_deserialize_particles": (_i32, [_H, _vp, _i64]),
     "apb_rebuild_neighbor_lists": (_i32, [_H, _i32, _i32]),
     "apb_get_geometry": (_i32, [_H, ctypes.POINTER(Geometry)]),
     "apb_compute_interactions": (_i32, [_H, _i32, ctypes.POINTER(Functor), _i32, ctypes.POINTER(TraversalResult)]),

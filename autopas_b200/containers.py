@@ -588,6 +588,23 @@ class GpuParticleContainer:
         return {"x": cols[0], "y": cols[1], "z": cols[2], "vx": cols[3], "vy": cols[4], "vz": cols[5], "id": ids,
                 "type": types}
 
+    def serializeParticles(self, behavior="ownedOrHalo"):
+        """ParticleSerializationTools::serializeParticle for every owned and / or halo particle, in storage order: a uint8
+        array of 120-byte records (md-flexible's MPI wire format)."""
+        mask = {"owned": 1, "halo": 2, "ownedOrHalo": 3}[behavior]
+        cap = self.numSlots()
+        buf = np.zeros(cap * capi.WIRE_RECORD_BYTES, dtype=np.uint8)
+        n = ctypes.c_int64()
+        self._check(self._lib.apb_serialize_particles(self._h, mask, _ptr(buf), cap, ctypes.byref(n)))
+        return buf[: n.value * capi.WIRE_RECORD_BYTES]
+
+    def deserializeParticles(self, data):
+        """ParticleSerializationTools::deserializeParticles + addParticle / addHaloParticle by the record's ownership."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        if len(data) % capi.WIRE_RECORD_BYTES:
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "wire data is not a whole number of 120-byte records")
+        self._check(self._lib.apb_deserialize_particles(self._h, _ptr(data), len(data) // capi.WIRE_RECORD_BYTES))
+
     def leaverColumn(self, name):
         """Any other attribute of the particles the last updateContainer returned (they are whole copies in the
         reference, LeavingParticleCollector.h:101-110), in the same order."""

@@ -433,6 +433,135 @@ extern "C" int apb_add_particles(apb_handle h, int64_t n, const double *x, const
   return APB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// md-flexible's MPI wire format (examples/md-flexible/src/ParticleSerializationTools.cpp:43-146): one record of
+// AttributesSize = 120 bytes per MoleculeLJ, the attributes memcpy'd in this order (:43-58), each 8 bytes wide -
+// id (size_t), posX posY posZ, velocityX..Z, forceX..Z, oldForceX..Z (double), typeId (size_t), ownershipState (int64_t,
+// OwnershipState.h:20-29). Lets a hybrid run hand device-resident particles to md-flexible's MPI exchange between nodes
+// (RegularGridDecomposition.cpp: sendParticles / receiveParticles) and take its messages back.
+// One thread per (record, word): the 15-word records are written / read with fully coalesced 8-byte accesses.
+// ------------------------------------------------------------------------------------------------------------------
+#define APB_WIRE_WORDS 15
+struct WireColumns {
+  const double *c[12];  // x y z vx vy vz fx fy fz oldFx oldFy oldFz
+  double *w[12];
+};
+__global__ void kWireSelect(int64_t n, const int32_t *__restrict__ own, int mask, int *__restrict__ flag) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int o = own[i];
+  flag[i] = (o == APB_OWN_OWNED && (mask & 1)) || (o == APB_OWN_HALO && (mask & 2));
+}
+__global__ void kWirePack(int64_t n, const int *__restrict__ flag, const int *__restrict__ pos, WireColumns cols,
+                          const int64_t *__restrict__ id, const int32_t *__restrict__ type, const int32_t *__restrict__ own,
+                          unsigned long long *__restrict__ out) {
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t i = g / APB_WIRE_WORDS;
+  const int w = static_cast<int>(g % APB_WIRE_WORDS);
+  if (i >= n || !flag[i]) return;
+  unsigned long long v;
+  if (w == 0)
+    v = static_cast<unsigned long long>(id[i]);
+  else if (w <= 12)
+    v = static_cast<unsigned long long>(__double_as_longlong(cols.c[w - 1][i]));
+  else if (w == 13)
+    v = static_cast<unsigned long long>(type[i]);
+  else
+    v = static_cast<unsigned long long>(static_cast<long long>(own[i]));
+  out[static_cast<size_t>(pos[i]) * APB_WIRE_WORDS + w] = v;
+}
+__global__ void kWireUnpack(int64_t m, int64_t first, const unsigned long long *__restrict__ in, WireColumns cols,
+                            int64_t *__restrict__ id, int32_t *__restrict__ type, int32_t *__restrict__ own, int *bad) {
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t r = g / APB_WIRE_WORDS;
+  const int w = static_cast<int>(g % APB_WIRE_WORDS);
+  if (r >= m) return;
+  const unsigned long long v = in[g];
+  const int64_t t = first + r;
+  if (w == 0)
+    id[t] = static_cast<int64_t>(v);
+  else if (w <= 12)
+    cols.w[w - 1][t] = __longlong_as_double(static_cast<long long>(v));
+  else if (w == 13)
+    type[t] = static_cast<int32_t>(v);
+  else {
+    const long long o = static_cast<long long>(v);
+    if (o != APB_OWN_OWNED && o != APB_OWN_HALO) atomicExch(bad, 1);  // a dummy has no business on the wire
+    own[t] = o == APB_OWN_HALO ? APB_OWN_HALO : APB_OWN_OWNED;
+  }
+}
+
+static int wireColumns(apb_handle h, WireColumns &wc) {
+  if (h->cfg.particle_kind != APB_PARTICLE_LJ)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "the 120-byte wire record is the one of MoleculeLJ (single-site mode)");
+  for (int k = 0; k < 12; ++k) wc.c[k] = wc.w[k] = h->col[APB_COL_X + k];
+  return APB_OK;
+}
+
+extern "C" int apb_serialize_particles(apb_handle h, int32_t ownershipMask, void *dst, int64_t capacityRecords,
+                                       int64_t *outNum) {
+  APB_ENTRY(h);
+  if (outNum) *outNum = 0;
+  if (!(ownershipMask & 3) || capacityRecords < 0 || (capacityRecords > 0 && !dst))
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_serialize_particles: bad argument");
+  WireColumns wc;
+  APB_CHECK(wireColumns(h, wc));
+  const int64_t n = h->nslots;
+  if (n == 0) return APB_OK;
+  APB_CHECK(apbEnsure(h, h->key, sizeof(int) * n));
+  APB_CHECK(apbEnsure(h, h->rank, sizeof(int) * (n + 1)));
+  int *flag = static_cast<int *>(h->key.p), *pos = static_cast<int *>(h->rank.p);
+  long long *totals = reinterpret_cast<long long *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result));
+  ++h->launchCount, kWireSelect<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->own, ownershipMask, flag);
+  APB_CHECK(apbExclusiveScan(h, flag, pos, n, totals));
+  long long m = 0;
+  APB_CUDA(cudaMemcpyAsync(&m, totals, 8, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (outNum) *outNum = m;
+  if (m > capacityRecords)
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_serialize_particles: " + std::to_string(m) + " records do not fit the buffer");
+  if (m == 0) return APB_OK;
+  APB_CHECK(apbEnsure(h, h->sortK1, static_cast<size_t>(m) * APB_WIRE_WORDS * 8));
+  unsigned long long *out = static_cast<unsigned long long *>(h->sortK1.p);
+  // (kWirePack reads `flag` after the scan wrote `pos`: the scan is out of place)
+  ++h->launchCount, kWirePack<<<apbDivUp(n * APB_WIRE_WORDS, 256), 256, 0, h->stream>>>(n, flag, pos, wc, h->id, h->type, h->own, out);
+  APB_CUDA(cudaGetLastError());
+  APB_CUDA(cudaMemcpyAsync(dst, out, static_cast<size_t>(m) * APB_WIRE_WORDS * 8, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  return APB_OK;
+}
+
+extern "C" int apb_deserialize_particles(apb_handle h, const void *src, int64_t numRecords) {
+  APB_ENTRY(h);
+  if (numRecords < 0 || (numRecords > 0 && !src)) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_deserialize_particles: bad argument");
+  WireColumns wc;
+  APB_CHECK(wireColumns(h, wc));
+  if (numRecords == 0) return APB_OK;
+  h->ownedKnown = false;
+  h->ownedInsideBox = false;
+  h->noHalos = false;
+  const int64_t first = h->nslots;
+  APB_CHECK(apbReserveSlots(h, first + numRecords));
+  APB_CHECK(wireColumns(h, wc));  // the columns may have moved
+  APB_CHECK(apbEnsure(h, h->sortK1, static_cast<size_t>(numRecords) * APB_WIRE_WORDS * 8));
+  int *bad = reinterpret_cast<int *>(static_cast<char *>(h->result.p) + sizeof(apb_traversal_result) + 32);
+  APB_CUDA(cudaMemsetAsync(bad, 0, 4, h->stream));
+  APB_CUDA(cudaMemcpyAsync(h->sortK1.p, src, static_cast<size_t>(numRecords) * APB_WIRE_WORDS * 8, cudaMemcpyHostToDevice, h->stream));
+  ++h->launchCount, kWireUnpack<<<apbDivUp(numRecords * APB_WIRE_WORDS, 256), 256, 0, h->stream>>>(
+      numRecords, first, static_cast<const unsigned long long *>(h->sortK1.p), wc, h->id, h->type, h->own, bad);
+  APB_CUDA(cudaGetLastError());
+  int hostBad = 0;
+  APB_CUDA(cudaMemcpyAsync(&hostBad, bad, 4, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (hostBad) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_deserialize_particles: a record is neither owned nor halo");
+  h->nslots = first + numRecords;
+  h->structureValid = false;
+  h->prunedValid = false;
+  h->countsValid = false;
+  apbForgetHaloLinks(h);
+  return APB_OK;
+}
+
 extern "C" int apb_delete_all_particles(apb_handle h) {
   APB_ENTRY(h);
   h->ownedKnown = false;  // the number of owned particles may change

@@ -785,6 +785,7 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
   void deleteAllParticles() override {
     for (auto &v : _pending) v.clear();
     check(apb_delete_all_particles(_h));
+    _hostOnly.clear();
     _mirror.clear();
     _mirrorValid = true;
     _mirrorDirty = false;
@@ -1012,7 +1013,9 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
           ids.push_back(static_cast<int64_t>(p.getID()));
           if constexpr (requires { p.getTypeId(); }) types.push_back(static_cast<int32_t>(p.getTypeId()));
           else types.push_back(0);
-          if constexpr (Columns::numHostOnly > 0) _hostOnly[p.getID()] = Columns::hostOnly(p);
+          // (owned particles only: a halo copy shares the id of its owner and must not overwrite the owner's values)
+          if constexpr (Columns::numHostOnly > 0)
+            if (pass == 0) _hostOnly[p.getID()] = Columns::hostOnly(p);
         }
       if (ids.empty()) continue;
       int64_t before = 0;
@@ -1087,7 +1090,7 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
       if constexpr (requires { p.setTypeId(size_t{}); }) p.setTypeId(static_cast<size_t>(types[i]));
       p.setOwnershipState(static_cast<autopas::OwnershipState>(own[i]));
       if constexpr (Columns::numHostOnly > 0) {
-        if (own[i] != 0) {
+        if (own[i] == APB_OWN_OWNED_VALUE) {
           const auto it = _hostOnly.find(p.getID());
           if (it != _hostOnly.end()) Columns::setHostOnly(p, it->second);
         }
@@ -1119,7 +1122,7 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     if constexpr (Columns::numHostOnly > 0) {  // attributes without a device column follow the particle id
       _hostOnly.clear();
       for (size_t i = 0; i < n; ++i)
-        if (own[i] != 0) _hostOnly[_mirror[i].getID()] = Columns::hostOnly(_mirror[i]);
+        if (own[i] == APB_OWN_OWNED_VALUE) _hostOnly[_mirror[i].getID()] = Columns::hostOnly(_mirror[i]);
     }
     if (n) {
       for (size_t k = 0; k < nc; ++k) check(apb_upload_column(_h, colIds[k], c[k].data()));

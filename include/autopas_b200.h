@@ -210,6 +210,17 @@ int apb_force_step_by_id(apb_handle h, int32_t traversal, const apb_functor *fun
 /* set force columns to a constant (TimeDiscretization.cpp:16-68 resets f to globalForce) */
 int apb_reset_forces(apb_handle h, double fx, double fy, double fz);
 
+/* ---- wire format ------------------------------------------------------------------------------------------------ */
+/* md-flexible's MPI particle record (examples/md-flexible/src/ParticleSerializationTools.cpp:43-146: serializeParticle /
+ * deserializeParticles, AttributesSize = 120 bytes for MoleculeLJ): id, position, velocity, force, oldForce, typeId,
+ * ownershipState, 8 bytes each, memcpy'd in that order. apb_serialize_particles writes the records of the owned and / or
+ * halo particles (ownership_mask bit 0 / bit 1) in storage order into a host buffer; apb_deserialize_particles appends
+ * the particles of such a buffer with all their attributes (ParticleContainerInterface::addParticle / addHaloParticle
+ * by the record's ownership state). Single-site particles only. */
+#define APB_WIRE_RECORD_BYTES 120
+int apb_serialize_particles(apb_handle h, int32_t ownership_mask, void *dst, int64_t capacity_records, int64_t *out_num);
+int apb_deserialize_particles(apb_handle h, const void *src, int64_t num_records);
+
 /* ---- container maintenance ------------------------------------------------------------------------------------- */
 /* ParticleContainerInterface::updateContainer(bool keepNeighborListsValid) (:297);
  * keep != 0: LeavingParticleCollector::collectParticlesAndMarkNonOwnedAsDummy (LeavingParticleCollector.h:85-118);

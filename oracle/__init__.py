@@ -460,3 +460,62 @@ def ref_multisite(pos, quat, mol_type, own, box_min, box_max, cutoff, skin, shif
     if rc != 0:
         raise RuntimeError("reference multisite run failed")
     return {"f": f.reshape(n, 3), "torque": tq.reshape(n, 3), "upot": g[0], "virial": g[1]}
+
+
+# ---- md-flexible's MPI wire format -------------------------------------------------------------------------------------
+WIRE_RECORD_BYTES = 120
+_REF_WIRE = os.path.join(_HERE, "_ref", "libautopas_ref_wire.so")
+_WIRE_DTYPE = np.dtype([("id", "<u8"), ("r", "<f8", 3), ("v", "<f8", 3), ("f", "<f8", 3), ("oldf", "<f8", 3), ("type", "<u8"),
+                        ("own", "<i8")])
+
+
+def wire_serialize(ids, r, v, f, oldf, types, own):
+    """Restatement of ParticleSerializationTools::serializeParticle for MoleculeLJ
+    (examples/md-flexible/src/ParticleSerializationTools.cpp:43-58, 76-82, 104-114): the attributes id, posX..Z, velocityX..Z,
+    forceX..Z, oldForceX..Z, typeId, ownershipState are memcpy'd back to back, 8 bytes each = 120 bytes per particle
+    (AttributesSize, :66). Returns a uint8 array."""
+    n = len(ids)
+    rec = np.zeros(n, dtype=_WIRE_DTYPE)
+    assert _WIRE_DTYPE.itemsize == WIRE_RECORD_BYTES
+    rec["id"], rec["type"], rec["own"] = ids, types, own
+    rec["r"], rec["v"], rec["f"], rec["oldf"] = r, v, f, oldf
+    return rec.view(np.uint8).reshape(-1).copy()
+
+
+def wire_deserialize(data):
+    """ParticleSerializationTools::deserializeParticles (:132-141): a dict of arrays."""
+    rec = np.ascontiguousarray(data, dtype=np.uint8).view(_WIRE_DTYPE)
+    return {"id": rec["id"].astype(np.int64), "r": rec["r"].copy(), "v": rec["v"].copy(), "f": rec["f"].copy(),
+            "oldf": rec["oldf"].copy(), "type": rec["type"].astype(np.int64), "own": rec["own"].copy()}
+
+
+def have_ref_wire():
+    return os.path.exists(_REF_WIRE)
+
+
+def ref_wire_serialize(ids, r, v, f, oldf, types, own):
+    """The unmodified reference (oracle/_ref/libautopas_ref_wire.so) on the same particles."""
+    lib_ = ctypes.CDLL(_REF_WIRE)
+    lib_.ref_wire_serialize.restype = ctypes.c_int64
+    n = len(ids)
+    cols = [_f64(a[:, d]) for a in (r, v, f, oldf) for d in range(3)]
+    ptrs = (ctypes.c_void_p * 12)(*[c.ctypes.data for c in cols])
+    out = np.zeros(n * WIRE_RECORD_BYTES, dtype=np.uint8)
+    ids_, types_, own_ = _i64(ids), _i64(types), _i64(own)
+    nb = lib_.ref_wire_serialize(ctypes.c_int64(n), ptrs, _p(ids_), _p(types_), _p(own_), _p(out))
+    assert nb == n * WIRE_RECORD_BYTES
+    return out
+
+
+def ref_wire_deserialize(data):
+    lib_ = ctypes.CDLL(_REF_WIRE)
+    lib_.ref_wire_deserialize.restype = ctypes.c_int64
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    n = len(data) // WIRE_RECORD_BYTES
+    cols = [np.zeros(n) for _ in range(12)]
+    ptrs = (ctypes.c_void_p * 12)(*[c.ctypes.data for c in cols])
+    ids, types, own = (np.zeros(n, dtype=np.int64) for _ in range(3))
+    m = lib_.ref_wire_deserialize(ctypes.c_int64(len(data)), _p(data), ptrs, _p(ids), _p(types), _p(own))
+    assert m == n
+    c = np.stack(cols, axis=1)
+    return {"id": ids, "r": c[:, 0:3], "v": c[:, 3:6], "f": c[:, 6:9], "oldf": c[:, 9:12], "type": types, "own": own}

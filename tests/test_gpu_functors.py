@@ -286,3 +286,34 @@ def test_sph_periodic_halo_exchange_and_column_refresh():
     assert close(acc, o_acc[:n], sc[:n])
     assert close(eng, o_eng[:n], sce[:n])
     c.close()
+
+
+def test_sph_leavers_carry_their_attributes_and_refresh_needs_links():
+    """updateContainer returns whole particles (LeavingParticleCollector.h:101-110): for SPHParticle storage the leavers'
+    mass / smoothing length / density ... come back through apb_get_leaver_column; apb_refresh_halo_columns without a
+    generating halo exchange is a state error."""
+    s = sph_scenario(seed=9)
+    n = len(s["pos"])
+    owned = s["own"] == 1
+    c = GpuParticleContainer("gpuLinkedCells", s["box_min"], s["box_max"], s["cutoff"], s["skin"], particleKind=capi.PARTICLE_SPH)
+    ids = np.arange(n)
+    c.addParticles(s["pos"][owned, 0], s["pos"][owned, 1], s["pos"][owned, 2], ids[owned])
+    with pytest.raises(ApbError):
+        c.refreshHaloColumns(["DENSITY"])
+    upload_by_id(c, MASS=s["mass"], SMTH=s["smth"], DENSITY=s["mass"] * 3.0, ENGDOT=s["smth"] - 1.0)
+    sid, _, _ = c.downloadIds()
+    x = c.downloadColumn("X")
+    movers = x > s["box_max"][0] - 0.2
+    assert movers.any()
+    x[movers] += 0.25
+    c.uploadColumn("X", x)
+    leavers = c.updateContainer(False)
+    assert set(leavers["id"].tolist()) == set(sid[movers].tolist())
+    lid = leavers["id"]
+    assert np.array_equal(c.leaverColumn("MASS"), s["mass"][lid])
+    assert np.array_equal(c.leaverColumn("SMTH"), s["smth"][lid])
+    assert np.array_equal(c.leaverColumn("DENSITY"), s["mass"][lid] * 3.0)
+    assert np.array_equal(c.leaverColumn("ENGDOT"), s["smth"][lid] - 1.0)
+    with pytest.raises(ApbError):
+        c.leaverColumn("OLDFX")  # SPHParticle has no oldF
+    c.close()
