@@ -1,6 +1,6 @@
 """Golden bytes of md-flexible's MPI wire format: seeded particles serialised by the UNMODIFIED reference
 (oracle/_ref/libautopas_ref_wire.so = examples/md-flexible/src/ParticleSerializationTools.cpp compiled where it lies).
-Run in the build container:  python tests/golden/make_golden_wire.py  ->  tests/golden/wire_format.npz"""
+Run in the build container:  python tests/golden/make_golden_wire.py  ->  tests/golden/fn_wire_format.npz"""
 import os
 import sys
 
@@ -28,6 +28,6 @@ if __name__ == "__main__":
     data = oracle.ref_wire_serialize(*p)
     back = oracle.ref_wire_deserialize(data)
     assert np.array_equal(back["id"], p[0]) and np.array_equal(back["r"], p[1]) and np.array_equal(back["own"], p[6])
-    np.savez(os.path.join(os.path.dirname(os.path.abspath(__file__)), "wire_format.npz"), ids=p[0], r=p[1], v=p[2], f=p[3],
+    np.savez(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fn_wire_format.npz"), ids=p[0], r=p[1], v=p[2], f=p[3],
              oldf=p[4], types=p[5], own=p[6], ref_bytes=data)
-    print("wire_format.npz:", len(data), "bytes")
+    print("fn_wire_format.npz:", len(data), "bytes")

@@ -1,6 +1,6 @@
 """md-flexible's MPI wire format (examples/md-flexible/src/ParticleSerializationTools.cpp:43-146).
 CPU: the oracle restatement against bytes produced by the unmodified reference (committed fixture
-tests/golden/wire_format.npz, and live when oracle/_ref travelled). GPU: apb_serialize_particles /
+tests/golden/fn_wire_format.npz, and live when oracle/_ref travelled). GPU: apb_serialize_particles /
 apb_deserialize_particles byte for byte against the oracle, round trip, full-size property."""
 import os
 
@@ -10,7 +10,7 @@ import pytest
 import oracle
 from autopas_b200 import ApbError, GpuParticleContainer, capi
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wire_format.npz")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fn_wire_format.npz")
 
 
 def _golden():
