@@ -359,32 +359,37 @@ __global__ void kScatterPermBins(int64_t n, int ZB, const int *__restrict__ key,
   if (k >= 0) perm[start[k / ZB] + binOff[k] + rank[i]] = static_cast<int>(i);
 }
 
-// one warp per (tower, z bin): rank of every member among the members by (z, id, slot); permOut receives the sorted bin
+// BIN_G lanes per (tower, z bin) - a bin holds about a dozen particles, so two bins share a warp: rank of every member
+// among the members by (z, id, slot); permOut receives the sorted bin. The loops run for the larger of the two bins (the
+// shuffles need the whole warp); a lane without a member contributes nothing.
+#define BIN_G 16
 __global__ void kBinSort(int numBins, int ZB, const int *__restrict__ start, const int *__restrict__ binOff,
                          const int *__restrict__ binCount, const int *__restrict__ permIn, int *__restrict__ permOut,
                          const double *__restrict__ z, const int64_t *__restrict__ id) {
-  const int bin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (bin >= numBins) return;
-  const int cnt = binCount[bin];
-  if (cnt == 0) return;
-  const int b0 = start[bin / ZB] + binOff[bin];
-  for (int ci = 0; ci < cnt; ci += 32) {
+  const int bin = (blockIdx.x * blockDim.x + threadIdx.x) / BIN_G, lane = threadIdx.x & (BIN_G - 1);
+  const int cnt = bin < numBins ? binCount[bin] : 0;
+  int cntMax = cnt;
+  for (int w = BIN_G; w < 32; w <<= 1) cntMax = max(cntMax, __shfl_xor_sync(0xffffffffu, cntMax, w));
+  if (cntMax == 0) return;  // warp-uniform
+  const int b0 = cnt > 0 ? start[bin / ZB] + binOff[bin] : 0;
+  for (int ci = 0; ci < cntMax; ci += BIN_G) {
     const bool mine = ci + lane < cnt;
     const int p = mine ? permIn[b0 + ci + lane] : 0;
     const double zi = mine ? z[p] : 0.;
     const long long idi = mine ? id[p] : 0;
     int r = 0;
-    for (int cj = 0; cj < cnt; cj += 32) {
+    for (int cj = 0; cj < cntMax; cj += BIN_G) {
       const bool have = cj + lane < cnt;
       const int pj = have ? (cj == ci ? p : permIn[b0 + cj + lane]) : 0;
       const double zj = have ? (cj == ci ? zi : z[pj]) : 0.;
       const long long idj = have ? (cj == ci ? idi : id[pj]) : 0;
-      const int m = min(32, cnt - cj);
-      for (int k = 0; k < m; ++k) {
-        const double zk = __shfl_sync(0xffffffffu, zj, k);
-        const long long idk = __shfl_sync(0xffffffffu, idj, k);
-        const int pk = __shfl_sync(0xffffffffu, pj, k);
-        r += zk < zi || (zk == zi && (idk < idi || (idk == idi && pk < p)));
+      const int m = min(BIN_G, cnt - cj);  // members of this group's bin in the chunk (<= 0: none)
+#pragma unroll 4
+      for (int k = 0; k < BIN_G; ++k) {
+        const double zk = __shfl_sync(0xffffffffu, zj, k, BIN_G);
+        const long long idk = __shfl_sync(0xffffffffu, idj, k, BIN_G);
+        const int pk = __shfl_sync(0xffffffffu, pj, k, BIN_G);
+        r += k < m && (zk < zi || (zk == zi && (idk < idi || (idk == idi && pk < p))));
       }
     }
     if (mine) permOut[b0 + r] = p;
@@ -476,38 +481,43 @@ __global__ void kSlotTower(int numTowers, const int *__restrict__ start, const i
   for (int k = threadIdx.x; k < np; k += blockDim.x) slotTower[s0 + k] = t;
 }
 
-// One thread per cluster: bounding box over the ACTUAL members. The reference computes the box while the padding
-// dummies sit on the last actual particle (ClusterTower.h:170-180), which gives the same box: z from first / last
-// member (sorted), x and y as min / max (Cluster.h:135-149).
-__global__ void kClusterBoxes(int64_t numClusters, int M, const double *__restrict__ x, const double *__restrict__ y,
-                              const double *__restrict__ z, const int32_t *__restrict__ own,
+// M lanes per cluster (32 / M clusters per warp): bounding box over the ACTUAL members. The reference computes the box
+// while the padding dummies sit on the last actual particle (ClusterTower.h:170-180), which gives the same box: z from
+// first / last member (sorted), x and y as min / max (Cluster.h:135-149). Every lane reads one slot (coalesced) and the
+// group reduces with shuffles; one thread per cluster walked its 32 slots serially (0.64 ms at 16 M particles).
+__global__ void kClusterBoxes(int64_t numClusters, int M, int logM, const double *__restrict__ x,
+                              const double *__restrict__ y, const double *__restrict__ z, const int32_t *__restrict__ own,
                               const int *__restrict__ slotTower, double *__restrict__ bmin, double *__restrict__ bmax,
                               int *__restrict__ hasOwned, int *__restrict__ clTower) {
-  const int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (c >= numClusters) return;
-  const int64_t s0 = c * M;
-  double lx = x[s0], ly = y[s0], lz = z[s0];
-  double hx = lx, hy = ly, hz = lz;
-  int ownedAny = own[s0] == APB_OWN_OWNED;
-  for (int k = 1; k < M; ++k) {
-    const int o = own[s0 + k];
-    if (o == APB_OWN_DUMMY) break;  // dummies only trail
-    const double px = x[s0 + k], py = y[s0 + k];
-    lx = fmin(lx, px);
-    hx = fmax(hx, px);
-    ly = fmin(ly, py);
-    hy = fmax(hy, py);
-    hz = z[s0 + k];
-    ownedAny |= o == APB_OWN_OWNED;
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // slot
+  const int64_t c = s >> logM;
+  const int k = static_cast<int>(s) & (M - 1);
+  const bool in = c < numClusters;
+  const int o = in ? own[s] : APB_OWN_DUMMY;
+  const bool live = o != APB_OWN_DUMMY;  // dummies only trail; slot 0 of a cluster is always a particle
+  double lx = live ? x[s] : 1e308, hx = live ? x[s] : -1e308;
+  double ly = live ? y[s] : 1e308, hy = live ? y[s] : -1e308;
+  double lz = live ? z[s] : 1e308, hz = live ? z[s] : -1e308;  // z-sorted: min = first, max = last live member
+  int ownedAny = o == APB_OWN_OWNED;
+  for (int w = 1; w < M; w <<= 1) {
+    lx = fmin(lx, __shfl_xor_sync(0xffffffffu, lx, w));
+    hx = fmax(hx, __shfl_xor_sync(0xffffffffu, hx, w));
+    ly = fmin(ly, __shfl_xor_sync(0xffffffffu, ly, w));
+    hy = fmax(hy, __shfl_xor_sync(0xffffffffu, hy, w));
+    lz = fmin(lz, __shfl_xor_sync(0xffffffffu, lz, w));
+    hz = fmax(hz, __shfl_xor_sync(0xffffffffu, hz, w));
+    ownedAny |= __shfl_xor_sync(0xffffffffu, ownedAny, w);
   }
-  bmin[c] = lx;
-  bmin[numClusters + c] = ly;
-  bmin[2 * numClusters + c] = lz;
-  bmax[c] = hx;
-  bmax[numClusters + c] = hy;
-  bmax[2 * numClusters + c] = hz;
-  hasOwned[c] = ownedAny;
-  clTower[c] = slotTower[s0];
+  if (in && k == 0) {
+    bmin[c] = lx;
+    bmin[numClusters + c] = ly;
+    bmin[2 * numClusters + c] = lz;
+    bmax[c] = hx;
+    bmax[numClusters + c] = hy;
+    bmax[2 * numClusters + c] = hz;
+    hasOwned[c] = ownedAny;
+    clTower[c] = slotTower[s];
+  }
 }
 
 // ClusterTower::generateClusters (ClusterTower.h:109-141): [firstOwnedCluster, firstTailHaloCluster)
@@ -700,7 +710,7 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   if (total > 0) APB_CUDA(cudaMemsetAsync(perm, 0xFF, sizeof(int) * total, h->stream));
   if (n > 0 && total > 0) {
     ++h->launchCount, kScatterPermBins<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, ZB, key, rank, start, binOff, permUnsorted);
-    ++h->launchCount, kBinSort<<<apbDivUp(numBins * 32, 256), 256, 0, h->stream>>>(static_cast<int>(numBins), ZB, start, binOff, binCount,
+    ++h->launchCount, kBinSort<<<apbDivUp(numBins * BIN_G, 256), 256, 0, h->stream>>>(static_cast<int>(numBins), ZB, start, binOff, binCount,
                                                                       permUnsorted, perm, h->col[APB_COL_Z], h->id);
     APB_CUDA(cudaGetLastError());
   }
@@ -735,8 +745,10 @@ int apbRebuildVCL(apb_handle h, int newton3) {
   APB_CHECK(apbEnsure(h, h->nbrCount, sizeof(int) * (ncAlloc + 1)));
   APB_CHECK(apbEnsure(h, h->nbrStart, sizeof(int) * (ncAlloc + 1)));
   if (numClusters > 0) {
-    ++h->launchCount, kClusterBoxes<<<apbDivUp(numClusters, 128), 128, 0, h->stream>>>(
-        numClusters, M, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own, slotTower,
+    int logM = 0;
+    while ((1 << logM) < M) ++logM;
+    ++h->launchCount, kClusterBoxes<<<apbDivUp(numClusters * M, 256), 256, 0, h->stream>>>(
+        numClusters, M, logM, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own, slotTower,
         static_cast<double *>(h->clBoxMin.p), static_cast<double *>(h->clBoxMax.p), static_cast<int *>(h->clHasOwned.p),
         static_cast<int *>(h->clTower.p));
     APB_CUDA(cudaGetLastError());
