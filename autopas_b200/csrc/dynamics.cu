@@ -198,6 +198,9 @@ __global__ void kIntegrateVelocities(int64_t n, const int32_t *__restrict__ own,
 
 // calculateVelocities of step s followed by calculatePositionsAndResetForces of step s + 1 in one pass over the
 // particles (same arithmetic, expression by expression, as the two kernels above): 24 instead of 30 column passes.
+// RESET = false: the force column is not reset here because the next force kernel stores instead of adding (kLJPruned,
+// PrunedForceArgs::overwrite): 21 column passes.
+template <bool RESET>
 __global__ void kIntegrateVelocitiesPositions(int64_t n, const int32_t *__restrict__ own, const int32_t *__restrict__ type,
                                               const double *__restrict__ massOfType, int numTypes, double dt, double gx,
                                               double gy, double gz, double *x, double *y, double *z, double *vx, double *vy,
@@ -216,9 +219,11 @@ __global__ void kIntegrateVelocitiesPositions(int64_t n, const int32_t *__restri
   ofx[i] = Fx;
   ofy[i] = Fy;
   ofz[i] = Fz;
-  fx[i] = gx;
-  fy[i] = gy;
-  fz[i] = gz;
+  if (RESET) {
+    fx[i] = gx;
+    fy[i] = gy;
+    fz[i] = gz;
+  }
   x[i] += Vx * dt + Fx * sx;
   y[i] += Vy * dt + Fy * sx;
   z[i] += Vz * dt + Fz * sx;
@@ -257,18 +262,26 @@ extern "C" int apb_integrate_positions(apb_handle h, double dt, const double *ma
 
 // velocities of the finished step + positions of the next one (apb_run_steps between two steps)
 static int integrateVelocitiesPositions(apb_handle h, double dt, const double *massOfType, int32_t numTypes,
-                                        const double *globalForce) {
+                                        const double *globalForce, bool resetForces = true) {
   if (!h->active[APB_COL_OLDFX]) return h->fail(APB_ERR_NOT_APPLICABLE, "particle kind has no oldF columns");
   APB_CHECK(uploadMasses(h, massOfType, numTypes));
   h->ownedInsideBox = false;
   if (h->nslots == 0) return APB_OK;
   const double g[3] = {globalForce ? globalForce[0] : 0., globalForce ? globalForce[1] : 0.,
                        globalForce ? globalForce[2] : 0.};
-  ++h->launchCount, kIntegrateVelocitiesPositions<<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(
-      h->nslots, h->own, h->type, static_cast<const double *>(h->massDev.p), numTypes, dt, g[0], g[1], g[2],
-      h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->col[APB_COL_VX], h->col[APB_COL_VY], h->col[APB_COL_VZ],
-      h->col[APB_COL_FX], h->col[APB_COL_FY], h->col[APB_COL_FZ], h->col[APB_COL_OLDFX], h->col[APB_COL_OLDFY],
-      h->col[APB_COL_OLDFZ]);
+  ++h->launchCount;
+  if (resetForces)
+    kIntegrateVelocitiesPositions<true><<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(
+        h->nslots, h->own, h->type, static_cast<const double *>(h->massDev.p), numTypes, dt, g[0], g[1], g[2],
+        h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->col[APB_COL_VX], h->col[APB_COL_VY], h->col[APB_COL_VZ],
+        h->col[APB_COL_FX], h->col[APB_COL_FY], h->col[APB_COL_FZ], h->col[APB_COL_OLDFX], h->col[APB_COL_OLDFY],
+        h->col[APB_COL_OLDFZ]);
+  else
+    kIntegrateVelocitiesPositions<false><<<apbDivUp(h->nslots, 256), 256, 0, h->stream>>>(
+        h->nslots, h->own, h->type, static_cast<const double *>(h->massDev.p), numTypes, dt, g[0], g[1], g[2],
+        h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->col[APB_COL_VX], h->col[APB_COL_VY], h->col[APB_COL_VZ],
+        h->col[APB_COL_FX], h->col[APB_COL_FY], h->col[APB_COL_FZ], h->col[APB_COL_OLDFX], h->col[APB_COL_OLDFY],
+        h->col[APB_COL_OLDFZ]);
   APB_CUDA(cudaGetLastError());
   return APB_OK;
 }
@@ -1500,7 +1513,8 @@ int apbCheckTraversal(apb_handle h, int traversal, int newton3);
 static int finishStep(apb_handle h, const apb_loop_params *p, int s, int numSteps, int64_t it) {
   const bool thermo = h->thermostatOn && it % h->thermostatInterval == 0;
   if (!thermo)
-    return s + 1 < numSteps ? integrateVelocitiesPositions(h, p->dt, p->mass_of_type, p->num_types, p->global_force)
+    return s + 1 < numSteps ? integrateVelocitiesPositions(h, p->dt, p->mass_of_type, p->num_types, p->global_force,
+                                                           !h->forceOverwrite)
                             : apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types);
   APB_CHECK(apb_integrate_velocities(h, p->dt, p->mass_of_type, p->num_types));
   APB_CHECK(apb_apply_thermostat(h, p->mass_of_type, p->num_types, h->thermostatTarget, h->thermostatDelta));
@@ -1519,6 +1533,13 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
   apb_traversal_result *dres = static_cast<apb_traversal_result *>(h->loopResults.p);
   int rc = APB_OK;
   h->deferSync = true;
+  // Inside this loop every force evaluation is preceded by a reset of the force column to the global force. With
+  // gpuvcl_pruned (newton3 off: one writer per owned particle, every owned particle written) the kernel stores
+  // global force + pair sum instead and the fused integrator skips the reset.
+  static const bool noOverwrite = getenv("APB_NO_FORCE_OVERWRITE") != nullptr;
+  h->forceOverwrite = !noOverwrite && p->traversal == APB_TRAVERSAL_GPUVCL_PRUNED && !p->newton3 &&
+                      functor->kind == APB_FUNCTOR_LJ && h->cfg.particle_kind == APB_PARTICLE_LJ;
+  for (int d = 0; d < 3; ++d) h->forceG[d] = p->global_force ? p->global_force[d] : 0.;
   // APB_DEBUG_TIMING: host wall time spent inside each phase call (where the host blocks on count read-backs / peers)
   static const bool dbgTiming = getenv("APB_DEBUG_TIMING") != nullptr;
   // Overlapped halo refresh (interior / boundary split of the force step). The two partial force launches cost about
@@ -1621,6 +1642,7 @@ extern "C" int apb_run_steps(apb_handle h, const apb_functor *functor, const apb
   }
   h->deferSync = false;
   h->asyncResultDev = nullptr;
+  h->forceOverwrite = false;
   if (rc != APB_OK) return rc;
   if (dbgTiming)
     fprintf(stderr, "[apb] rank %d run_steps(%d): host ms in migrate %.3f, halo build %.3f, rebuild %.3f, halo refresh %.3f\n",

@@ -459,7 +459,10 @@ __global__ void kSPHPack(int64_t n, SPHArgs a, double2 *__restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double2 *o = out + static_cast<size_t>(i) * (HYDRO ? 6 : 2);
-  o[0] = make_double2(a.x[i], a.y[i]);
+  // a slot that became a dummy after the lists were built (updateContainer with keepNeighborListsValid, deleteParticle)
+  // is still listed: it is packed out of everybody's reach, like the reference functors skip dummies
+  const double x = a.w.own[i] == APB_OWN_DUMMY ? 1e300 : a.x[i];
+  o[0] = make_double2(x, a.y[i]);
   o[1] = make_double2(a.z[i], a.mass[i]);
   if (HYDRO) {
     const double rho = a.density[i], h = a.smth[i], H = SPH_SUPPORT * h;

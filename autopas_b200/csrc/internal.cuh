@@ -111,6 +111,9 @@ struct apb_handle_s {
   DevBuf prEntryLo;
   DevBuf prStageEarly;  // fixed-stride rows of staged sets written by the counting pass (kPrunedStage<false>)
   DevBuf prTileHalo, prTileOrder;  // per tile: stages a halo copy; tiles ordered interior first (+ the interior count)
+  // apb_run_steps with gpuvcl_pruned (newton3 off): kLJPruned stores global force + pair sum, the integrator skips its reset
+  bool forceOverwrite = false;
+  double forceG[3] = {0., 0., 0.};
   int prunedPart = 0;              // 0: whole traversal; 1 / 2: interior / boundary half of a split step (apb_run_steps)
   int prunedCap = 0;  // staged particles incl. the 16 sentinel slots the lists were built for (1280, 2048 or 4096)
   cudaEvent_t evSplit[2] = {nullptr, nullptr};

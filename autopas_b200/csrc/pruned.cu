@@ -810,6 +810,10 @@ struct PrunedForceArgs {
   const int *tileOrder, *numInterior;
   int part, numTiles;
   int sentBase;  // first of the 16 sentinel slots of the staged layout (prunedCap - 16)
+  // apb_run_steps: the force of an owned particle is stored as global force + pair sum instead of being added to a
+  // column the integrator reset beforehand (one column pass less on each side; same value bit for bit)
+  int overwrite;
+  double gx, gy, gz;
 };
 
 // reciprocal from the hardware seed: MUFU.RCP64H (relative error ~2^-20, it reads the high word only) followed by one
@@ -1105,10 +1109,16 @@ __global__ void __launch_bounds__(PR_TILE, CAP <= 2048 ? PR_MINBLOCKS_CAP2048 : 
     }
   }
   if (active) {
-    // single writer per slot: fire-and-forget RED.ADD.F64 instead of a load / add / store round trip
-    atomicAdd(a.fx + i, acc.fx);
-    atomicAdd(a.fy + i, acc.fy);
-    atomicAdd(a.fz + i, acc.fz);
+    if (a.overwrite) {
+      a.fx[i] = a.gx + acc.fx;
+      a.fy[i] = a.gy + acc.fy;
+      a.fz[i] = a.gz + acc.fz;
+    } else {
+      // single writer per slot: fire-and-forget RED.ADD.F64 instead of a load / add / store round trip
+      atomicAdd(a.fx + i, acc.fx);
+      atomicAdd(a.fy + i, acc.fy);
+      atomicAdd(a.fz + i, acc.fz);
+    }
   }
   if (STATS) {
     // Block sums of the raw accumulators only (2 doubles + the hit count; 5 with the per-component virial) instead of the
@@ -1317,6 +1327,10 @@ int apbComputeLJPruned(apb_handle h, const apb_functor *f, const LJParams &p, bo
   a.fx = h->col[APB_COL_FX];
   a.fy = h->col[APB_COL_FY];
   a.fz = h->col[APB_COL_FZ];
+  a.overwrite = (h->forceOverwrite && !n3) ? 1 : 0;
+  a.gx = h->forceG[0];
+  a.gy = h->forceG[1];
+  a.gz = h->forceG[2];
   a.type = h->type;
   a.own = h->own;
   a.stagedStart = static_cast<const int *>(h->prStagedStart.p);

@@ -271,8 +271,10 @@ def measure(workload, n_per_dim, args, ctx, with_e2e=True):
     c.getLoopTiming()
     sampler = ClockSampler(local_rank if rank == 0 else None)  # one nvidia-smi poller per job, not per rank
     launches0, allocs0 = c.getLaunchCount(), c.getAllocCount()
-    barrier()
+    # the poller is spawned BEFORE the barrier: forking nvidia-smi takes rank 0 several milliseconds, and a rank that starts
+    # late stalls its neighbours inside their timed region (their exchanges wait for it)
     sampler.start()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()
@@ -422,6 +424,8 @@ def main():
                          "liquid per GPU, weak scaling")
     ap.add_argument("--n-per-dim", type=int, default=0, help="lattice points per dimension (c2: per rank; c3: in total)")
     ap.add_argument("--no-c2", action="store_true", help="skip the additional c2 measurement of the default run")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the C1 / C4 / C5 functor timings the default one-GPU run appends under 'other_configs'")
     ap.add_argument("--cluster-size", type=int, default=32)
     ap.add_argument("--traversal", default="gpuvcl_pruned")
     ap.add_argument("--newton3", type=int, default=0)
@@ -555,6 +559,15 @@ def main():
                           "warmup": q["warmup"], "ms_per_step": q["ms_per_step"],
                           "config": config_of("c2", C2["n_per_dim"], q), "roofline": rl2, "e2e": q.get("e2e"),
                           "gpu_launches": q["gpu_launches"], "clocks": q["clocks"], "upot_last": q["upot_last"]}
+        if world == 1 and not args.no_other_configs and args.workload == "c3" and not args.no_c2:
+            # BASELINE configs[0], [3], [4] (parity-test configurations, not bench lines) timed on the same box, so that
+            # the driver-run record carries them: tools/bench_functors.py through the same C ABI
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_functors
+                line["other_configs"] = bench_functors.c1(False) + bench_functors.c4(False) + bench_functors.c5(False)
+            except Exception as exc:  # never lose the headline line over the side measurements
+                line["other_configs"] = {"error": repr(exc)}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -317,3 +317,43 @@ def test_sph_leavers_carry_their_attributes_and_refresh_needs_links():
     with pytest.raises(ApbError):
         c.leaverColumn("OLDFX")  # SPHParticle has no oldF
     c.close()
+
+
+def test_sph_partner_lists_skip_particles_deleted_since_the_rebuild():
+    """updateContainer(keepNeighborListsValid=true) marks leavers as dummies without a rebuild
+    (LeavingParticleCollector.h:85-118): the cached partner lists of gpuLinkedCells still name them, the functor must not see
+    them (SPHCalcDensityFunctor.h:46: dummies are skipped)."""
+    rng = np.random.default_rng(3)
+    npd, d = 24, 0.35  # 13 824 particles... below 16 384 slots the warp kernel would run: force the list kernels
+    if os.environ.get("APB_LC_KERNEL", "list")[0] != "l":
+        pytest.skip("another kernel variant is forced")
+    npd = 28  # 21 952 particles: the partner-list kernels are the default
+    g = (np.arange(npd) + 0.5) * d
+    pos = np.stack([a.ravel() for a in np.meshgrid(g, g, g, indexing="ij")], axis=1) + rng.uniform(-0.06, 0.06, (npd ** 3, 3))
+    n = len(pos)
+    L = npd * d
+    mass, smth = rng.uniform(0.8, 1.2, n), rng.uniform(0.30, 0.40, n)
+    c = GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [L, L, L], 1.0, 0.2, particleKind=capi.PARTICLE_SPH)
+    c.addParticles(pos[:, 0], pos[:, 1], pos[:, 2], np.arange(n))
+    upload_by_id(c, MASS=mass, SMTH=smth)
+    c.rebuildNeighborLists(GpuTraversal("gpulc_c08", SPHCalcDensityFunctor(), False))
+    run(c, "gpulc_c08", SPHCalcDensityFunctor(), False)  # builds the lists
+    ids, _, own = c.downloadIds()
+    x = c.downloadColumn("X")
+    leave = (own == 1) & (x > L - 0.3) & (ids % 3 == 0)
+    assert leave.sum() > 20
+    x[leave] += 0.4  # out of the box: leavers
+    c.uploadColumn("X", x)
+    leavers = c.updateContainer(True)
+    assert set(leavers["id"].tolist()) == set(ids[leave].tolist())
+    c.uploadColumn("DENSITY", np.zeros(c.numSlots()))
+    run(c, "gpulc_c08", SPHCalcDensityFunctor(), False)
+    ids2, _, own2 = c.downloadIds()
+    rho = np.zeros(n)
+    m = own2 == 1
+    rho[ids2[m]] = c.downloadColumn("DENSITY")[m]
+    keep = np.ones(n, dtype=bool)
+    keep[ids[leave]] = False
+    o_rho, sc = oracle.sph_density(pos[keep], mass[keep], smth[keep], np.ones(keep.sum(), dtype=np.int64))
+    assert close(rho[keep], o_rho, sc)
+    c.close()

@@ -63,6 +63,7 @@ def container(pos, L, cutoff, skin, kind):
 
 
 def c1(small):
+    out = []
     npd = 16 if small else 32
     pos, L = lattice(npd, 1.1225, 0.0, 1)
     for n3 in (True, False):
@@ -78,10 +79,11 @@ def c1(small):
             c.computeInteractions(t)
             f.endTraversal(n3)
         s = timed(call, 10)
-        print(json.dumps({"config": "C1 LJ gpuLinkedCells/gpulc_c08", "newton3": n3, "particles": n, "halo": nh,
-                          "ms_per_call": s * 1e3, "MFUPs_per_s": n / s * 1e-6, "flops_reference_model": f.getNumFLOPs(),
-                          "TFLOP_per_s": f.getNumFLOPs() / s * 1e-12, "hit_rate": f.getHitRate()}), flush=True)
+        out.append({"config": "C1 LJ gpuLinkedCells/gpulc_c08", "newton3": n3, "particles": n, "halo": nh,
+                    "ms_per_call": s * 1e3, "MFUPs_per_s": n / s * 1e-6, "flops_reference_model": f.getNumFLOPs(),
+                    "TFLOP_per_s": f.getNumFLOPs() / s * 1e-12, "hit_rate": f.getHitRate()})
         c.close()
+    return out
 
 
 def c4(small):
@@ -99,11 +101,11 @@ def c4(small):
         c.computeInteractions(t)
         f.endTraversal(False)
     s = timed(call, 3)
-    print(json.dumps({"config": "C4 AxilrodTellerMuto gpuLinkedCells/gpulc_c08", "newton3": False, "particles": n, "halo": nh,
-                      "ms_per_call": s * 1e3, "MFUPs_per_s": n / s * 1e-6,
-                      "kernel_calls_per_particle": f._raw.num_kernel_calls_no_n3 / n,
-                      "flops_reference_model": f.getNumFLOPs(), "TFLOP_per_s": f.getNumFLOPs() / s * 1e-12}), flush=True)
+    out = [{"config": "C4 AxilrodTellerMuto gpuLinkedCells/gpulc_c08", "newton3": False, "particles": n, "halo": nh,
+            "ms_per_call": s * 1e3, "MFUPs_per_s": n / s * 1e-6, "kernel_calls_per_particle": f._raw.num_kernel_calls_no_n3 / n,
+            "flops_reference_model": f.getNumFLOPs(), "TFLOP_per_s": f.getNumFLOPs() / s * 1e-12}]
     c.close()
+    return out
 
 
 def c5(small):
@@ -143,15 +145,16 @@ def c5(small):
         c.computeInteractions(th)
         hyd.endTraversal(False)
     sh = timed(call_h, 3)
-    for name, s in (("density", sd), ("hydro force", sh)):
-        print(json.dumps({"config": f"C5 SPH {name} gpuLinkedCells/gpulc_c08", "newton3": False, "particles": n, "halo": nh,
-                          "ms_per_call": s * 1e3, "MFUPs_per_s": n / s * 1e-6,
-                          "ms_first_density_call_after_rebuild": first * 1e3}), flush=True)
+    out = [{"config": f"C5 SPH {name} gpuLinkedCells/gpulc_c08", "newton3": False, "particles": n, "halo": nh,
+            "ms_per_call": s * 1e3, "MFUPs_per_s": n / s * 1e-6, "ms_first_density_call_after_rebuild": first * 1e3}
+           for name, s in (("density", sd), ("hydro force", sh))]
     c.close()
+    return out
 
 
 if __name__ == "__main__":
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "c4", "c5"]
     small = "--small" in sys.argv
     for w in which:
-        {"c1": c1, "c4": c4, "c5": c5}[w](small)
+        for line in {"c1": c1, "c4": c4, "c5": c5}[w](small):
+            print(json.dumps(line), flush=True)
