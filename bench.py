@@ -179,6 +179,48 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def other_configs_cpu_reference(lines, bf):
+    """cpu_baseline leg for the side measurements: the unmodified reference (oracle/_ref/libautopas_ref.so: LinkedCells,
+    lc_c08 for SPH / lc_c01 for the three-body functor, AoS, newton3 off, OpenMP on all host cores) on the inputs of
+    tools/bench_functors.py C4 / C5, traversal time only. Skipped when oracle/_ref did not travel."""
+    import oracle
+    if not oracle.have_ref():
+        return
+    cores = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    what = f"unmodified reference, LinkedCells, AoS, newton3 off, OpenMP {cores} threads, traversal only"
+    try:
+        oracle.ref_set_timing_reps(1)
+        pos, L = bf.lattice(64, 1.2, 0.1, 4)
+        halo = bf.images(pos, L, 2.7)
+        allpos = np.vstack([pos, halo])
+        own = np.r_[np.ones(len(pos)), 2 * np.ones(len(halo))].astype(np.int64)
+        oracle.ref_atm(allpos, None, own, [0, 0, 0], [L, L, L], 2.5, 0.2, nu=0.073)
+        ref_ms = {"C4": oracle.ref_last_compute_seconds() * 1e3}
+        d = 0.4
+        h = 1.2 * d
+        cutoff = 2.5 * h
+        pos, L = bf.lattice(128, d, 0.05, 5)
+        halo = bf.images(pos, L, 1.1 * cutoff)
+        allpos = np.vstack([pos, halo])
+        n = len(allpos)
+        own = np.r_[np.ones(len(pos)), 2 * np.ones(len(halo))].astype(np.int64)
+        rng = np.random.default_rng(0)
+        vel = rng.normal(0, 0.1, (n, 3))
+        args_ = (allpos, vel, np.full(n, d ** 3), np.full(n, h), np.full(n, 1.0), np.full(n, 1.0), np.full(n, 1.2), own,
+                 [0, 0, 0], [L, L, L], cutoff, 0.1 * cutoff)
+        oracle.ref_sph(*args_, 0, False)
+        ref_ms["C5 SPH density"] = oracle.ref_last_compute_seconds() * 1e3
+        oracle.ref_sph(*args_, 1, False)
+        ref_ms["C5 SPH hydro"] = oracle.ref_last_compute_seconds() * 1e3
+        for ln in lines:
+            for key, ms in ref_ms.items():
+                if ln["config"].startswith(key):
+                    ln["cpu_reference"] = {"ms_per_call": ms, "cores": cores, "kind": "reference", "sample": what}
+    except Exception as exc:  # the side measurement must not cost the headline line
+        lines.append({"cpu_reference_error": repr(exc)})
+
+
 def reference_arm(workload, iters, warmup, n_per_dim=0):
     """The unmodified reference (oracle/_ref, built like its own Release build: -O3, the host's vector ISA) on every host
     core this process may use, on a bounded sample of the workload: a periodic sub-box of the same lattice with its
@@ -566,6 +608,8 @@ def main():
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import bench_functors
                 line["other_configs"] = bench_functors.c1(False) + bench_functors.c4(False) + bench_functors.c5(False)
+                if not args.no_cpu_baseline:
+                    other_configs_cpu_reference(line["other_configs"], bench_functors)
             except Exception as exc:  # never lose the headline line over the side measurements
                 line["other_configs"] = {"error": repr(exc)}
         print(json.dumps(line), file=json_out, flush=True)

@@ -519,3 +519,15 @@ def ref_wire_deserialize(data):
     assert m == n
     c = np.stack(cols, axis=1)
     return {"id": ids, "r": c[:, 0:3], "v": c[:, 3:6], "f": c[:, 6:9], "oldf": c[:, 9:12], "type": types, "own": own}
+
+
+def ref_set_timing_reps(reps):
+    """The extra-functor drivers (ref_sph, ref_atm) time their traversal; with reps > 1 they repeat it (outputs then only
+    serve timing)."""
+    ref().ref_set_timing_reps(ctypes.c_int(int(reps)))
+
+
+def ref_last_compute_seconds():
+    f = ref().ref_last_compute_seconds
+    f.restype = ctypes.c_double
+    return float(f())

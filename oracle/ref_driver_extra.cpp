@@ -4,7 +4,9 @@
 // sphLib::SPHCalcDensityFunctor / SPHCalcHydroForceFunctor and mdLib::AxilrodTellerMutoFunctor, run through the
 // reference's own LinkedCells container and traversals (lc_c08 AoS for pairwise, lc_c01 AoS newton3-off for triwise =
 // the reference configurations of TraversalComparison.cpp:210-220). Part of oracle/_ref/libautopas_ref.so.
+#include <algorithm>
 #include <array>
+#include <chrono>
 #include <cstdint>
 #include <vector>
 
@@ -25,7 +27,25 @@ using Molecule = mdLib::MoleculeLJ;
 using FMCell = autopas::FullParticleCell<Molecule>;
 }  // namespace
 
+namespace {
+// timing of the traversal alone (tools/bench_functors.py reports the reference's CPU time next to the GPU kernels): with
+// more than one repetition the outputs are accumulated that many times and are only good for timing
+int g_timingReps = 1;
+double g_lastComputeSeconds = 0.;
+template <class Container, class Traversal>
+void timedCompute(Container &c, Traversal *t) {
+  g_lastComputeSeconds = 1e300;
+  for (int r = 0; r < g_timingReps; ++r) {
+    const auto t0 = std::chrono::steady_clock::now();
+    c.computeInteractions(t);
+    g_lastComputeSeconds = std::min(g_lastComputeSeconds, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  }
+}
+}  // namespace
+
 extern "C" {
+void ref_set_timing_reps(int reps) { g_timingReps = reps < 1 ? 1 : reps; }
+double ref_last_compute_seconds() { return g_lastComputeSeconds; }
 // which: 0 density, 1 hydro force. out (by id): density[n] | acc[3n], engDot[n], vsigmax[n]
 int ref_sph(int64_t n, const double *x, const double *y, const double *z, const double *vx, const double *vy,
             const double *vz, const double *mass, const double *smth, const double *density, const double *pressure,
@@ -52,7 +72,7 @@ int ref_sph(int64_t n, const double *x, const double *y, const double *z, const 
                                                        autopas::DataLayoutOption::aos, newton3 != 0);
       c.rebuildNeighborLists(&t);
       f.initTraversal();
-      c.computeInteractions(&t);
+      timedCompute(c, &t);
       f.endTraversal(newton3 != 0);
     } else {
       sphLib::SPHCalcHydroForceFunctor<SPHP> f;
@@ -60,7 +80,7 @@ int ref_sph(int64_t n, const double *x, const double *y, const double *z, const 
                                                        autopas::DataLayoutOption::aos, newton3 != 0);
       c.rebuildNeighborLists(&t);
       f.initTraversal();
-      c.computeInteractions(&t);
+      timedCompute(c, &t);
       f.endTraversal(newton3 != 0);
     }
     for (auto it = c.begin(autopas::IteratorBehavior::ownedOrHalo); it.isValid(); ++it) {
@@ -101,7 +121,7 @@ int ref_atm(int64_t n, const double *x, const double *y, const double *z, const 
           info.cellsPerDim, functor, info.interactionLength, info.cellLength, autopas::DataLayoutOption::aos, false);
       c.rebuildNeighborLists(&t);
       functor.initTraversal();
-      c.computeInteractions(&t);
+      timedCompute(c, &t);
       functor.endTraversal(false);
       globals[0] = functor.getPotentialEnergy();
       globals[1] = functor.getVirial();
