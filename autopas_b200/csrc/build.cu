@@ -376,20 +376,38 @@ __global__ void kBinSort(int numBins, int ZB, const int *__restrict__ start, con
     const bool mine = ci + lane < cnt;
     const int p = mine ? permIn[b0 + ci + lane] : 0;
     const double zi = mine ? z[p] : 0.;
-    const long long idi = mine ? id[p] : 0;
+    // Fast pass: rank by z alone (two shuffles and one comparison per member) and note whether any two members of the
+    // bin share their z. Only then - a lattice at rest; practically never once the particles move - the full
+    // (z, id, slot) comparison below decides, as ClusterTower's sort with the canonical tie-break does.
     int r = 0;
+    bool tie = false;
     for (int cj = 0; cj < cntMax; cj += BIN_G) {
       const bool have = cj + lane < cnt;
-      const int pj = have ? (cj == ci ? p : permIn[b0 + cj + lane]) : 0;
-      const double zj = have ? (cj == ci ? zi : z[pj]) : 0.;
-      const long long idj = have ? (cj == ci ? idi : id[pj]) : 0;
-      const int m = min(BIN_G, cnt - cj);  // members of this group's bin in the chunk (<= 0: none)
+      const double zj = have ? (cj == ci ? zi : z[permIn[b0 + cj + lane]]) : 0.;
+      const int m = min(BIN_G, cnt - cj);
 #pragma unroll 4
       for (int k = 0; k < BIN_G; ++k) {
         const double zk = __shfl_sync(0xffffffffu, zj, k, BIN_G);
-        const long long idk = __shfl_sync(0xffffffffu, idj, k, BIN_G);
-        const int pk = __shfl_sync(0xffffffffu, pj, k, BIN_G);
-        r += k < m && (zk < zi || (zk == zi && (idk < idi || (idk == idi && pk < p))));
+        r += k < m && zk < zi;
+        tie |= mine && k < m && zk == zi && !(cj == ci && k == lane);
+      }
+    }
+    if (__any_sync(0xffffffffu, tie)) {
+      const long long idi = mine ? id[p] : 0;
+      r = 0;
+      for (int cj = 0; cj < cntMax; cj += BIN_G) {
+        const bool have = cj + lane < cnt;
+        const int pj = have ? (cj == ci ? p : permIn[b0 + cj + lane]) : 0;
+        const double zj = have ? (cj == ci ? zi : z[pj]) : 0.;
+        const long long idj = have ? (cj == ci ? idi : id[pj]) : 0;
+        const int m = min(BIN_G, cnt - cj);  // members of this group's bin in the chunk (<= 0: none)
+#pragma unroll 4
+        for (int k = 0; k < BIN_G; ++k) {
+          const double zk = __shfl_sync(0xffffffffu, zj, k, BIN_G);
+          const long long idk = __shfl_sync(0xffffffffu, idj, k, BIN_G);
+          const int pk = __shfl_sync(0xffffffffu, pj, k, BIN_G);
+          r += k < m && (zk < zi || (zk == zi && (idk < idi || (idk == idi && pk < p))));
+        }
       }
     }
     if (mine) permOut[b0 + r] = p;
