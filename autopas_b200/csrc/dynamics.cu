@@ -199,7 +199,9 @@ __global__ void kIntegrateVelocities(int64_t n, const int32_t *__restrict__ own,
 // calculateVelocities of step s followed by calculatePositionsAndResetForces of step s + 1 in one pass over the
 // particles (same arithmetic, expression by expression, as the two kernels above): 24 instead of 30 column passes.
 // RESET = false: the force column is not reset here because the next force kernel stores instead of adding (kLJPruned,
-// PrunedForceArgs::overwrite): 21 column passes.
+// PrunedForceArgs::overwrite), and oldForce = force is not copied: the caller swaps the two column pointers (the forces
+// just used become the old forces; the column that held the old forces is overwritten by the next force kernel - for
+// owned particles; halo copies carry zeros in both, dummies are nobody's business). 18 column passes.
 template <bool RESET>
 __global__ void kIntegrateVelocitiesPositions(int64_t n, const int32_t *__restrict__ own, const int32_t *__restrict__ type,
                                               const double *__restrict__ massOfType, int numTypes, double dt, double gx,
@@ -216,9 +218,11 @@ __global__ void kIntegrateVelocitiesPositions(int64_t n, const int32_t *__restri
   vx[i] = Vx;
   vy[i] = Vy;
   vz[i] = Vz;
-  ofx[i] = Fx;
-  ofy[i] = Fy;
-  ofz[i] = Fz;
+  if (RESET) {  // (without the reset the host swaps the force and oldForce columns instead of copying one into the other)
+    ofx[i] = Fx;
+    ofy[i] = Fy;
+    ofz[i] = Fz;
+  }
   if (RESET) {
     fx[i] = gx;
     fy[i] = gy;
@@ -283,6 +287,8 @@ static int integrateVelocitiesPositions(apb_handle h, double dt, const double *m
         h->col[APB_COL_FX], h->col[APB_COL_FY], h->col[APB_COL_FZ], h->col[APB_COL_OLDFX], h->col[APB_COL_OLDFY],
         h->col[APB_COL_OLDFZ]);
   APB_CUDA(cudaGetLastError());
+  if (!resetForces)
+    for (int d = 0; d < 3; ++d) std::swap(h->col[APB_COL_FX + d], h->col[APB_COL_OLDFX + d]);
   return APB_OK;
 }
 
