@@ -1093,6 +1093,166 @@ __global__ void __launch_bounds__(LCW_WARPS * 32) kATMTripletsWarp(ATMWarpArgs w
   if (STATS) ljStatsBlockReduce(st, a.partials);
 }
 
+// Two passes per thread over the neighbour list of its slot (kATMNeighbors). Pass 1 tests every (j, k) pair of the list
+// for |r_jk| <= cutoff and records the survivors as one 64-bit mask per j in shared memory; pass 2 walks the set bits.
+// kATMTriplets / kATMTripletsN3 evaluate the ~100 FP64 instructions of the triplet inside the (j, k) loop, where the
+// whole warp pays for them whenever one lane's pair survives (28 % of the pairs do, so practically always); here a lane
+// only runs the triplet arithmetic for its own survivors and the warp is done when its busiest lane is (lanes of a warp
+// are slots of the same cell: their counts differ by ~20 %). Pass 2 is software-pipelined: the partner slots and positions
+// of the next surviving triplet are loaded before the current one is evaluated (measured without it: long-scoreboard
+// stalls of 7.6 per issue at 30 % resident warps, profiles/r02_lc_kernels.txt). Needs at most 64 neighbours per slot.
+template <bool MIX, bool STATS, bool N3>
+__global__ void __launch_bounds__(128) kATMTripletsMasked(ATMArgs a) {
+  extern __shared__ unsigned long long atmMasks[];  // [cap][128]
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  LJStats st;
+  ljStatsZero(st);
+  const int ownI = i < a.w.n ? a.w.own[i] : APB_OWN_DUMMY;
+  const int cnt = ownI != APB_OWN_DUMMY ? a.nbrCount[i] : 0;
+  if (cnt >= 2) {
+    const double xi = a.x[i], yi = a.y[i], zi = a.z[i];
+    const int ti = MIX ? a.type[i] : 0;
+    const bool ownedI = ownI == APB_OWN_OWNED;
+    unsigned long long *mine = atmMasks + threadIdx.x;
+    // ---- pass 1: which (j, k) pairs are within the cutoff of each other (d2ij and d2ki are, by construction of the list)
+    for (int p = 0; p + 1 < cnt; ++p) {
+      const int j = a.nbr[static_cast<size_t>(p) * a.w.n + i];
+      const double xj = a.x[j], yj = a.y[j], zj = a.z[j];
+      unsigned long long m = 0ULL;
+#pragma unroll 4
+      for (int q = p + 1; q < cnt; ++q) {
+        const int k = a.nbr[static_cast<size_t>(q) * a.w.n + i];
+        const double jkx = a.x[k] - xj, jky = a.y[k] - yj, jkz = a.z[k] - zj;
+        if (dot3(jkx, jky, jkz, jkx, jky, jkz) <= a.cutoff2) m |= 1ULL << q;
+      }
+      mine[p * 128] = m;
+    }
+    if (STATS) st.dist += static_cast<unsigned long long>(cnt) * (cnt - 1) / 2;
+    double Fx = 0., Fy = 0., Fz = 0.;
+    auto triplet = [&](int j, int k, double xj, double yj, double zj, double xk, double yk, double zk) {
+      const double ijx = xj - xi, ijy = yj - yi, ijz = zj - zi;
+      const double jkx = xk - xj, jky = yk - yj, jkz = zk - zj;
+      const double kix = xi - xk, kiy = yi - yk, kiz = zi - zk;
+      const double d2ij = dot3(ijx, ijy, ijz, ijx, ijy, ijz);
+      const double d2jk = dot3(jkx, jky, jkz, jkx, jky, jkz);
+      const double d2ki = dot3(kix, kiy, kiz, kix, kiy, kiz);
+      double nu = a.nu;
+      if (MIX) nu = __ldg(a.nuMix + (static_cast<size_t>(ti) * a.T + a.type[j]) * a.T + a.type[k]);
+      // AxilrodTellerMutoFunctor.h:217-251
+      const double all2 = d2ij * d2jk * d2ki;
+      const double all5 = all2 * all2 * sqrt(all2);
+      const double factor = 3.0 * nu / all5;
+      const double IJdKI = dot3(ijx, ijy, ijz, kix, kiy, kiz);
+      const double IJdJK = dot3(ijx, ijy, ijz, jkx, jky, jkz);
+      const double JKdKI = dot3(jkx, jky, jkz, kix, kiy, kiz);
+      const double allDots = IJdKI * IJdJK * JKdKI;
+      const double cJK = IJdKI * (IJdJK - JKdKI);
+      const double cIJ = IJdJK * JKdKI - d2jk * d2ki + 5.0 * allDots / d2ij;
+      const double cKI = -IJdJK * JKdKI + d2ij * d2jk - 5.0 * allDots / d2ki;
+      const double fix = (jkx * cJK + ijx * cIJ + kix * cKI) * factor;
+      const double fiy = (jky * cJK + ijy * cIJ + kiy * cKI) * factor;
+      const double fiz = (jkz * cJK + ijz * cIJ + kiz * cKI) * factor;
+      Fx += fix;
+      Fy += fiy;
+      Fz += fiz;
+      const double u3 = factor * (all2 - 3.0 * allDots);
+      if (N3) {
+        // force on j (:241-247), F_k = -(F_i + F_j)
+        const double jKI = IJdJK * (JKdKI - IJdKI);
+        const double jIJ = -IJdKI * JKdKI + d2jk * d2ki - 5.0 * allDots / d2ij;
+        const double jJK = IJdKI * JKdKI - d2ij * d2ki + 5.0 * allDots / d2jk;
+        const double fjx = (kix * jKI + ijx * jIJ + jkx * jJK) * factor;
+        const double fjy = (kiy * jKI + ijy * jIJ + jky * jJK) * factor;
+        const double fjz = (kiz * jKI + ijz * jIJ + jkz * jJK) * factor;
+        const double fkx = (fix + fjx) * (-1.0), fky = (fiy + fjy) * (-1.0), fkz = (fiz + fjz) * (-1.0);
+        atomicAdd(a.fx + j, fjx);
+        atomicAdd(a.fy + j, fjy);
+        atomicAdd(a.fz + j, fjz);
+        atomicAdd(a.fx + k, fkx);
+        atomicAdd(a.fy + k, fky);
+        atomicAdd(a.fz + k, fkz);
+        if (STATS) {
+          ++st.kN3;
+          ++st.gN3;
+          if (ownedI) {
+            st.upot += u3;
+            st.vir[0] += fix * xi;
+            st.vir[1] += fiy * yi;
+            st.vir[2] += fiz * zi;
+          }
+          if (a.w.own[j] == APB_OWN_OWNED) {
+            st.upot += u3;
+            st.vir[0] += fjx * xj;
+            st.vir[1] += fjy * yj;
+            st.vir[2] += fjz * zj;
+          }
+          if (a.w.own[k] == APB_OWN_OWNED) {
+            st.upot += u3;
+            st.vir[0] += fkx * xk;
+            st.vir[1] += fky * yk;
+            st.vir[2] += fkz * zk;
+          }
+        }
+      } else if (STATS) {
+        ++st.kNoN3;
+        ++st.gNoN3;
+        if (ownedI) {
+          // potentialEnergy3 = factor (allDistsSquared - 3 allDotProducts); virial = f_i * r_i (:269-275)
+          st.upot += u3;
+          st.vir[0] += fix * xi;
+          st.vir[1] += fiy * yi;
+          st.vir[2] += fiz * zi;
+        }
+      }
+    };
+    // ---- pass 2: the surviving triplets of this slot, one after the other; the loads of triplet t + 1 are in flight
+    // while triplet t is evaluated
+    int p = 0;
+    unsigned long long m = mine[0];
+    auto nextPair = [&](int &pp, int &qq) {
+      while (m == 0ULL && ++p + 1 < cnt) m = mine[p * 128];
+      if (m == 0ULL) return false;
+      pp = p;
+      qq = __ffsll(static_cast<long long>(m)) - 1;
+      m &= m - 1ULL;
+      return true;
+    };
+    int pc = 0, qc = 0;
+    bool have = nextPair(pc, qc);
+    int j = 0, k = 0;
+    double xj = 0., yj = 0., zj = 0., xk = 0., yk = 0., zk = 0.;
+    if (have) {
+      j = a.nbr[static_cast<size_t>(pc) * a.w.n + i];
+      k = a.nbr[static_cast<size_t>(qc) * a.w.n + i];
+      xj = a.x[j], yj = a.y[j], zj = a.z[j], xk = a.x[k], yk = a.y[k], zk = a.z[k];
+    }
+    while (have) {
+      int pn = 0, qn = 0, jn = 0, kn = 0;
+      double xjn = 0., yjn = 0., zjn = 0., xkn = 0., ykn = 0., zkn = 0.;
+      const bool haveNext = nextPair(pn, qn);
+      if (haveNext) {
+        jn = a.nbr[static_cast<size_t>(pn) * a.w.n + i];
+        kn = a.nbr[static_cast<size_t>(qn) * a.w.n + i];
+        xjn = a.x[jn], yjn = a.y[jn], zjn = a.z[jn], xkn = a.x[kn], ykn = a.y[kn], zkn = a.z[kn];
+      }
+      triplet(j, k, xj, yj, zj, xk, yk, zk);
+      have = haveNext;
+      j = jn, k = kn;
+      xj = xjn, yj = yjn, zj = zjn, xk = xkn, yk = ykn, zk = zkn;
+    }
+    if (N3) {
+      atomicAdd(a.fx + i, Fx);
+      atomicAdd(a.fy + i, Fy);
+      atomicAdd(a.fz + i, Fz);
+    } else {
+      a.fx[i] += Fx;
+      a.fy[i] += Fy;
+      a.fz[i] += Fz;
+    }
+  }
+  if (STATS) ljStatsBlockReduce(st, a.partials);
+}
+
 int apbFinishStats(apb_handle h, int numBlocks, bool stats, const apb_functor *f, apb_traversal_result *out);
 
 static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
@@ -1212,6 +1372,29 @@ static int computeATM(apb_handle h, const apb_functor *f, int newton3, apb_trave
   a.partials = static_cast<LJStats *>(h->partials.p);
   ++h->launchCount;
   const int sel = (newton3 ? 4 : 0) | (mix ? 2 : 0) | (stats ? 1 : 0);
+  static const bool atmInline = getenv("APB_ATM_INLINE") != nullptr;  // A/B switch: triplet arithmetic inside the pair loop
+  if (cap <= 64 && !atmInline) {
+    const size_t smem = sizeof(unsigned long long) * 128 * static_cast<size_t>(std::max(cap, 1));
+#define ATM_MASKED_LAUNCH(MIXV, STATSV, N3V)                                                                             \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024)                                                                                              \
+      APB_CUDA(cudaFuncSetAttribute(kATMTripletsMasked<MIXV, STATSV, N3V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    static_cast<int>(smem)));                                                          \
+    kATMTripletsMasked<MIXV, STATSV, N3V><<<grid, block, smem, h->stream>>>(a);                                        \
+  } while (0)
+    switch (sel) {
+      case 0: ATM_MASKED_LAUNCH(false, false, false); break;
+      case 1: ATM_MASKED_LAUNCH(false, true, false); break;
+      case 2: ATM_MASKED_LAUNCH(true, false, false); break;
+      case 3: ATM_MASKED_LAUNCH(true, true, false); break;
+      case 4: ATM_MASKED_LAUNCH(false, false, true); break;
+      case 5: ATM_MASKED_LAUNCH(false, true, true); break;
+      case 6: ATM_MASKED_LAUNCH(true, false, true); break;
+      default: ATM_MASKED_LAUNCH(true, true, true); break;
+    }
+    APB_CUDA(cudaGetLastError());
+    return apbFinishStats(h, grid, stats, f, out);
+  }
   switch (sel) {
     case 0: kATMTriplets<false, false><<<grid, block, 0, h->stream>>>(a); break;
     case 1: kATMTriplets<false, true><<<grid, block, 0, h->stream>>>(a); break;
