@@ -150,67 +150,113 @@ __device__ __forceinline__ void atomicMaxPositive(double *addr, double v) {
   atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
 }
 
-// SPHCalcHydroForceFunctor::AoSFunctor (:45-108)
+// gradW(dr, h) scale with the normalisation 16 / pi / H^3 handed in (a per-particle factor; the list kernels precompute it,
+// the others evaluate it here - the same operations on the same operands as sphGradWScale)
+__device__ __forceinline__ double sphGradWNorm(double h) {
+  const double H = SPH_SUPPORT * h;
+  return 16.0 / SPH_PI / __dmul_rn(__dmul_rn(H, H), H);
+}
+__device__ __forceinline__ double sphGradWScaleNorm(double drabs, double h, double norm) {
+  const double H = SPH_SUPPORT * h;
+  const double s = drabs / H;
+  const double s1 = (1.0 - s < 0) ? 0 : 1.0 - s;
+  const double s2 = (0.5 - s < 0) ? 0 : 0.5 - s;
+  double r = __dadd_rn(__dmul_rn(-3.0, __dmul_rn(s1, s1)), __dmul_rn(12.0, __dmul_rn(s2, s2)));
+  r = __dmul_rn(r, norm);
+  return r / __dadd_rn(__dmul_rn(drabs, H), __dmul_rn(1.0e-6, h));
+}
+
+// One pair of the hydro-force functor seen from particle i (SPHCalcHydroForceFunctor::AoSFunctor, :45-108), shared by
+// the three kernel variants; the caller has already decided that the pair is inside i's support (dr2 < cut2).
+struct SPHHydroI {
+  double x, y, z, vx, vy, vz, h, m, rho, pOverRho2, c, norm;
+};
+struct SPHHydroSum {
+  double ax = 0., ay = 0., az = 0., eng = 0., vmax = 0.;
+};
+template <bool N3>
+__device__ __forceinline__ void sphHydroPair(const SPHArgs &a, const SPHHydroI &I, int j, double drx, double dry, double drz,
+                                             double dr2, double vxj, double vyj, double vzj, double mj, double cj,
+                                             double rhoj, double PjOverRho2, double hj, double normJ, SPHHydroSum &acc) {
+  const double dvx = I.vx - vxj, dvy = I.vy - vyj, dvz = I.vz - vzj;
+  const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
+  const double drabs = sqrt(dr2);
+  const double wij = (dvdr < 0) ? dvdr / drabs : 0;
+  const double vsig = __dadd_rn(__dadd_rn(I.c, cj), -__dmul_rn(3.0, wij));
+  acc.vmax = fmax(acc.vmax, vsig);
+  const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(I.rho, rhoj));
+  // gradW_ij = (gradW(dr, h_i) + gradW(dr, h_j)) * 0.5, component by component
+  const double gi = sphGradWScaleNorm(drabs, I.h, I.norm), gj = sphGradWScaleNorm(drabs, hj, normJ);
+  const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
+  const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
+  const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
+  const double scale = __dadd_rn(__dadd_rn(I.pOverRho2, PjOverRho2), AV);
+  const double si = __dmul_rn(scale, mj);
+  acc.ax -= __dmul_rn(gx, si);
+  acc.ay -= __dmul_rn(gy, si);
+  acc.az -= __dmul_rn(gz, si);
+  const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
+  const double scale2i = __dmul_rn(mj, __dadd_rn(I.pOverRho2, __dmul_rn(0.5, AV)));
+  acc.eng += __dmul_rn(gdv, scale2i);
+  if (N3) {
+    atomicMaxPositive(a.vsigmax + j, vsig);
+    const double sj = __dmul_rn(scale, I.m);
+    atomicAdd(a.ax + j, __dmul_rn(gx, sj));
+    atomicAdd(a.ay + j, __dmul_rn(gy, sj));
+    atomicAdd(a.az + j, __dmul_rn(gz, sj));
+    const double scale2j = __dmul_rn(I.m, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
+    atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
+  }
+}
+__device__ __forceinline__ SPHHydroI sphHydroLoadI(const SPHArgs &a, int64_t i) {
+  SPHHydroI I;
+  I.x = a.x[i], I.y = a.y[i], I.z = a.z[i], I.vx = a.vx[i], I.vy = a.vy[i], I.vz = a.vz[i];
+  I.h = a.smth[i], I.m = a.mass[i], I.rho = a.density[i], I.c = a.snd[i];
+  I.pOverRho2 = a.pressure[i] / __dmul_rn(I.rho, I.rho);
+  I.norm = sphGradWNorm(I.h);
+  return I;
+}
+// partner j from the particle columns (cell-walk and warp kernels)
+template <bool N3>
+__device__ __forceinline__ void sphHydroPairFromColumns(const SPHArgs &a, const SPHHydroI &I, int j, double drx, double dry,
+                                                        double drz, double dr2, SPHHydroSum &acc) {
+  const double rhoj = a.density[j], hj = a.smth[j];
+  sphHydroPair<N3>(a, I, j, drx, dry, drz, dr2, a.vx[j], a.vy[j], a.vz[j], a.mass[j], a.snd[j], rhoj,
+                   a.pressure[j] / __dmul_rn(rhoj, rhoj), hj, sphGradWNorm(hj), acc);
+}
+template <bool N3>
+__device__ __forceinline__ void sphHydroStore(const SPHArgs &a, int64_t i, const SPHHydroSum &acc) {
+  if (N3) {
+    atomicAdd(a.ax + i, acc.ax);
+    atomicAdd(a.ay + i, acc.ay);
+    atomicAdd(a.az + i, acc.az);
+    atomicAdd(a.engDot + i, acc.eng);
+    if (acc.vmax > 0.) atomicMaxPositive(a.vsigmax + i, acc.vmax);
+  } else {
+    a.ax[i] += acc.ax;
+    a.ay[i] += acc.ay;
+    a.az[i] += acc.az;
+    a.engDot[i] += acc.eng;
+    a.vsigmax[i] = fmax(a.vsigmax[i], acc.vmax);
+  }
+}
+
+// SPHCalcHydroForceFunctor::AoSFunctor (:45-108), one thread per slot walking the stencil cells (round 1; APB_LC_KERNEL=thread)
 template <bool N3>
 __global__ void __launch_bounds__(128) kSPHHydroLC(SPHArgs a) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= a.w.n || a.w.own[i] == APB_OWN_DUMMY) return;
-  const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
-  const double vxi = a.vx[i], vyi = a.vy[i], vzi = a.vz[i];
-  const double rhoi = a.density[i], Pi = a.pressure[i], ci = a.snd[i];
-  const double cut = hi * SPH_SUPPORT;
+  const SPHHydroI I = sphHydroLoadI(a, i);
+  const double cut = I.h * SPH_SUPPORT;
   const double cut2 = __dmul_rn(cut, cut);
-  const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
-  double accx = 0., accy = 0., accz = 0., eng = 0., vmax = a.vsigmax[i];
+  SPHHydroSum acc;
   lcForEachPartner<N3>(a.w, i, [&](int j) {
-    const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+    const double drx = I.x - a.x[j], dry = I.y - a.y[j], drz = I.z - a.z[j];
     const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
     if (dr2 >= cut2) return;
-    const double dvx = vxi - a.vx[j], dvy = vyi - a.vy[j], dvz = vzi - a.vz[j];
-    const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
-    const double drabs = sqrt(dr2);
-    const double wij = (dvdr < 0) ? dvdr / drabs : 0;
-    const double vsig = __dadd_rn(__dadd_rn(ci, a.snd[j]), -__dmul_rn(3.0, wij));
-    vmax = fmax(vmax, vsig);
-    const double rhoj = a.density[j], Pj = a.pressure[j], mj = a.mass[j];
-    const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
-    // gradW_ij = (gradW(dr, h_i) + gradW(dr, h_j)) * 0.5, component by component
-    const double gi = sphGradWScale(drabs, hi), gj = sphGradWScale(drabs, a.smth[j]);
-    const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
-    const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
-    const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
-    const double PjOverRho2 = Pj / __dmul_rn(rhoj, rhoj);
-    const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
-    const double si = __dmul_rn(scale, mj);
-    accx -= __dmul_rn(gx, si);
-    accy -= __dmul_rn(gy, si);
-    accz -= __dmul_rn(gz, si);
-    const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
-    const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
-    eng += __dmul_rn(gdv, scale2i);
-    if (N3) {
-      atomicMaxPositive(a.vsigmax + j, vsig);
-      const double sj = __dmul_rn(scale, mi);
-      atomicAdd(a.ax + j, __dmul_rn(gx, sj));
-      atomicAdd(a.ay + j, __dmul_rn(gy, sj));
-      atomicAdd(a.az + j, __dmul_rn(gz, sj));
-      const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
-      atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
-    }
+    sphHydroPairFromColumns<N3>(a, I, j, drx, dry, drz, dr2, acc);
   });
-  if (N3) {
-    atomicAdd(a.ax + i, accx);
-    atomicAdd(a.ay + i, accy);
-    atomicAdd(a.az + i, accz);
-    atomicAdd(a.engDot + i, eng);
-    atomicMaxPositive(a.vsigmax + i, vmax);
-  } else {
-    a.ax[i] += accx;
-    a.ay[i] += accy;
-    a.az[i] += accz;
-    a.engDot[i] += eng;
-    a.vsigmax[i] = vmax;
-  }
+  sphHydroStore<N3>(a, i, acc);
 }
 
 // ---- one warp per particle slot (lc_warp.cuh) ---------------------------------------------------------------------------
@@ -278,74 +324,27 @@ __global__ void __launch_bounds__(LCW_WARPS * 32) kSPHHydroWarp(SPHWarpArgs wa) 
     const bool canOwnI = apbCellCanOwn(g, c % g.cellsPerDim[0], (c / g.cellsPerDim[0]) % g.cellsPerDim[1],
                                        c / (g.cellsPerDim[0] * g.cellsPerDim[1]));
     if (!canOwnI && !N3) continue;
-    const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
-    const double vxi = a.vx[i], vyi = a.vy[i], vzi = a.vz[i];
-    const double rhoi = a.density[i], Pi = a.pressure[i], ci = a.snd[i];
-    const double cut = hi * SPH_SUPPORT;
+    const SPHHydroI I = sphHydroLoadI(a, i);
+    const double cut = I.h * SPH_SUPPORT;
     const double cut2 = __dmul_rn(cut, cut);
-    const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
-    double accx = 0., accy = 0., accz = 0., eng = 0., vmax = 0.;
+    SPHHydroSum acc;
     lcWarpWalk<N3>(
         wa.w, i, c, !canOwnI, queues[warp],
         [&](int j) {
           if (j == i || a.w.own[j] == APB_OWN_DUMMY) return false;
-          const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
+          const double drx = I.x - a.x[j], dry = I.y - a.y[j], drz = I.z - a.z[j];
           return dot3(drx, dry, drz, drx, dry, drz) < cut2;
         },
         [&](int j) {
-          const double drx = xi - a.x[j], dry = yi - a.y[j], drz = zi - a.z[j];
-          const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
-          const double dvx = vxi - a.vx[j], dvy = vyi - a.vy[j], dvz = vzi - a.vz[j];
-          const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
-          const double drabs = sqrt(dr2);
-          const double wij = (dvdr < 0) ? dvdr / drabs : 0;
-          const double vsig = __dadd_rn(__dadd_rn(ci, a.snd[j]), -__dmul_rn(3.0, wij));
-          vmax = fmax(vmax, vsig);
-          const double rhoj = a.density[j], Pj = a.pressure[j], mj = a.mass[j];
-          const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
-          const double gi = sphGradWScale(drabs, hi), gj = sphGradWScale(drabs, a.smth[j]);
-          const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
-          const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
-          const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
-          const double PjOverRho2 = Pj / __dmul_rn(rhoj, rhoj);
-          const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
-          const double si = __dmul_rn(scale, mj);
-          accx -= __dmul_rn(gx, si);
-          accy -= __dmul_rn(gy, si);
-          accz -= __dmul_rn(gz, si);
-          const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
-          const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
-          eng += __dmul_rn(gdv, scale2i);
-          if (N3) {
-            atomicMaxPositive(a.vsigmax + j, vsig);
-            const double sj = __dmul_rn(scale, mi);
-            atomicAdd(a.ax + j, __dmul_rn(gx, sj));
-            atomicAdd(a.ay + j, __dmul_rn(gy, sj));
-            atomicAdd(a.az + j, __dmul_rn(gz, sj));
-            const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
-            atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
-          }
+          const double drx = I.x - a.x[j], dry = I.y - a.y[j], drz = I.z - a.z[j];
+          sphHydroPairFromColumns<N3>(a, I, j, drx, dry, drz, dot3(drx, dry, drz, drx, dry, drz), acc);
         });
-    accx = lcWarpSum(accx);
-    accy = lcWarpSum(accy);
-    accz = lcWarpSum(accz);
-    eng = lcWarpSum(eng);
-    vmax = lcWarpMax(vmax);
-    if (lane == 0) {
-      if (N3) {
-        atomicAdd(a.ax + i, accx);
-        atomicAdd(a.ay + i, accy);
-        atomicAdd(a.az + i, accz);
-        atomicAdd(a.engDot + i, eng);
-        if (vmax > 0.) atomicMaxPositive(a.vsigmax + i, vmax);
-      } else {
-        a.ax[i] += accx;
-        a.ay[i] += accy;
-        a.az[i] += accz;
-        a.engDot[i] += eng;
-        a.vsigmax[i] = fmax(a.vsigmax[i], vmax);
-      }
-    }
+    acc.ax = lcWarpSum(acc.ax);
+    acc.ay = lcWarpSum(acc.ay);
+    acc.az = lcWarpSum(acc.az);
+    acc.eng = lcWarpSum(acc.eng);
+    acc.vmax = lcWarpMax(acc.vmax);
+    if (lane == 0) sphHydroStore<N3>(a, i, acc);
   }
 }
 
@@ -465,22 +464,12 @@ __global__ void kSPHPack(int64_t n, SPHArgs a, double2 *__restrict__ out) {
   o[0] = make_double2(x, a.y[i]);
   o[1] = make_double2(a.z[i], a.mass[i]);
   if (HYDRO) {
-    const double rho = a.density[i], h = a.smth[i], H = SPH_SUPPORT * h;
+    const double rho = a.density[i], h = a.smth[i];
     o[2] = make_double2(a.vx[i], a.vy[i]);
     o[3] = make_double2(a.vz[i], a.snd[i]);
     o[4] = make_double2(rho, a.pressure[i] / __dmul_rn(rho, rho));
-    o[5] = make_double2(h, 16.0 / SPH_PI / __dmul_rn(__dmul_rn(H, H), H));
+    o[5] = make_double2(h, sphGradWNorm(h));
   }
-}
-// sphGradWScale with the normalisation 16 / pi / H^3 handed in
-__device__ __forceinline__ double sphGradWScaleNorm(double drabs, double h, double norm) {
-  const double H = SPH_SUPPORT * h;
-  const double s = drabs / H;
-  const double s1 = (1.0 - s < 0) ? 0 : 1.0 - s;
-  const double s2 = (0.5 - s < 0) ? 0 : 0.5 - s;
-  double r = __dadd_rn(__dmul_rn(-3.0, __dmul_rn(s1, s1)), __dmul_rn(12.0, __dmul_rn(s2, s2)));
-  r = __dmul_rn(r, norm);
-  return r / __dadd_rn(__dmul_rn(drabs, H), __dmul_rn(1.0e-6, h));
 }
 
 // The list kernels are bound by the latency of the partner gathers (ncu: long-scoreboard stalls dominate), so the
@@ -539,14 +528,10 @@ __global__ void __launch_bounds__(128, SPH_HYDRO_MINBLOCKS) kSPHHydroList(SPHLis
   if (i >= a.w.n || a.w.own[i] == APB_OWN_DUMMY) return;
   const int cnt = la.nbrCount[i];
   if (cnt == 0) return;
-  const double xi = a.x[i], yi = a.y[i], zi = a.z[i], hi = a.smth[i], mi = a.mass[i];
-  const double vxi = a.vx[i], vyi = a.vy[i], vzi = a.vz[i];
-  const double rhoi = a.density[i], Pi = a.pressure[i], ci = a.snd[i];
-  const double cut = hi * SPH_SUPPORT;
+  const SPHHydroI I = sphHydroLoadI(a, i);
+  const double cut = I.h * SPH_SUPPORT;
   const double cut2 = __dmul_rn(cut, cut);
-  const double PiOverRho2 = Pi / __dmul_rn(rhoi, rhoi);
-  const double normI = la.pack[6 * static_cast<size_t>(i) + 5].y;
-  double accx = 0., accy = 0., accz = 0., eng = 0., vmax = 0.;
+  SPHHydroSum acc;
   for (int p0 = 0; p0 < cnt; p0 += SPH_HYDRO_BATCH) {
     int jb[SPH_HYDRO_BATCH];
     double2 w[SPH_HYDRO_BATCH][6];
@@ -562,54 +547,15 @@ __global__ void __launch_bounds__(128, SPH_HYDRO_MINBLOCKS) kSPHHydroList(SPHLis
     for (int b = 0; b < SPH_HYDRO_BATCH; ++b) {
       const int j = jb[b];
       if (j < 0) continue;
-      const double2 q0 = w[b][0], q1 = w[b][1], q2 = w[b][2], q3 = w[b][3], q4 = w[b][4], q5 = w[b][5];
-      const double drx = xi - q0.x, dry = yi - q0.y, drz = zi - q1.x;
+      // packed partner: {x, y} {z, m} {vx, vy} {vz, c} {rho, P / rho^2} {h, 16 / pi / H^3}
+      const double drx = I.x - w[b][0].x, dry = I.y - w[b][0].y, drz = I.z - w[b][1].x;
       const double dr2 = dot3(drx, dry, drz, drx, dry, drz);
       if (dr2 >= cut2) continue;
-      const double mj = q1.y, cj = q3.y, rhoj = q4.x, PjOverRho2 = q4.y, hj = q5.x, normJ = q5.y;
-      const double dvx = vxi - q2.x, dvy = vyi - q2.y, dvz = vzi - q3.x;
-      const double dvdr = dot3(dvx, dvy, dvz, drx, dry, drz);
-      const double drabs = sqrt(dr2);
-      const double wij = (dvdr < 0) ? dvdr / drabs : 0;
-      const double vsig = __dadd_rn(__dadd_rn(ci, cj), -__dmul_rn(3.0, wij));
-      vmax = fmax(vmax, vsig);
-      const double AV = __dmul_rn(__dmul_rn(-0.5, vsig), wij) / __dmul_rn(0.5, __dadd_rn(rhoi, rhoj));
-      const double gi = sphGradWScaleNorm(drabs, hi, normI), gj = sphGradWScaleNorm(drabs, hj, normJ);
-      const double gx = __dmul_rn(__dadd_rn(__dmul_rn(drx, gi), __dmul_rn(drx, gj)), 0.5);
-      const double gy = __dmul_rn(__dadd_rn(__dmul_rn(dry, gi), __dmul_rn(dry, gj)), 0.5);
-      const double gz = __dmul_rn(__dadd_rn(__dmul_rn(drz, gi), __dmul_rn(drz, gj)), 0.5);
-      const double scale = __dadd_rn(__dadd_rn(PiOverRho2, PjOverRho2), AV);
-      const double si = __dmul_rn(scale, mj);
-      accx -= __dmul_rn(gx, si);
-      accy -= __dmul_rn(gy, si);
-      accz -= __dmul_rn(gz, si);
-      const double gdv = dot3(gx, gy, gz, dvx, dvy, dvz);
-      const double scale2i = __dmul_rn(mj, __dadd_rn(PiOverRho2, __dmul_rn(0.5, AV)));
-      eng += __dmul_rn(gdv, scale2i);
-      if (N3) {
-        atomicMaxPositive(a.vsigmax + j, vsig);
-        const double sj = __dmul_rn(scale, mi);
-        atomicAdd(a.ax + j, __dmul_rn(gx, sj));
-        atomicAdd(a.ay + j, __dmul_rn(gy, sj));
-        atomicAdd(a.az + j, __dmul_rn(gz, sj));
-        const double scale2j = __dmul_rn(mi, __dadd_rn(PjOverRho2, __dmul_rn(0.5, AV)));
-        atomicAdd(a.engDot + j, __dmul_rn(gdv, scale2j));
-      }
+      sphHydroPair<N3>(a, I, j, drx, dry, drz, dr2, w[b][2].x, w[b][2].y, w[b][3].x, w[b][1].y, w[b][3].y, w[b][4].x,
+                       w[b][4].y, w[b][5].x, w[b][5].y, acc);
     }
   }
-  if (N3) {
-    atomicAdd(a.ax + i, accx);
-    atomicAdd(a.ay + i, accy);
-    atomicAdd(a.az + i, accz);
-    atomicAdd(a.engDot + i, eng);
-    if (vmax > 0.) atomicMaxPositive(a.vsigmax + i, vmax);
-  } else {
-    a.ax[i] += accx;
-    a.ay[i] += accy;
-    a.az[i] += accz;
-    a.engDot[i] += eng;
-    a.vsigmax[i] = fmax(a.vsigmax[i], vmax);
-  }
+  sphHydroStore<N3>(a, i, acc);
 }
 
 static int computeSPH(apb_handle h, const apb_functor *f, int newton3, apb_traversal_result *out) {
