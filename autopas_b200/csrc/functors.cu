@@ -827,6 +827,90 @@ __global__ void __launch_bounds__(128) kATMTripletsN3(ATMArgs a) {
   if (STATS) ljStatsBlockReduce(st, a.partials);
 }
 
+// One triplet (i, j, k) of the Axilrod-Teller-Muto functor from the thread that owns i
+// (AxilrodTellerMutoFunctor.h:217-290): force on i into (Fx, Fy, Fz); newton3: forces on j and k through RED.ADD.F64
+// (F_k = -(F_i + F_j)); globals 3 Upot and f_p * r_p for every owned participant (:269-290). Shared by the
+// warp-per-slot and the two-pass kernel.
+template <bool MIX, bool STATS, bool N3>
+__device__ __forceinline__ void atmTriplet(const ATMArgs &a, double xi, double yi, double zi, int ti, bool ownedI, int j, int k,
+                                           double xj, double yj, double zj, double xk, double yk, double zk, double &Fx,
+                                           double &Fy, double &Fz, LJStats &st) {
+  const double ijx = xj - xi, ijy = yj - yi, ijz = zj - zi;
+  const double jkx = xk - xj, jky = yk - yj, jkz = zk - zj;
+  const double kix = xi - xk, kiy = yi - yk, kiz = zi - zk;
+  const double d2ij = dot3(ijx, ijy, ijz, ijx, ijy, ijz);
+  const double d2jk = dot3(jkx, jky, jkz, jkx, jky, jkz);
+  const double d2ki = dot3(kix, kiy, kiz, kix, kiy, kiz);
+  double nu = a.nu;
+  if (MIX) nu = __ldg(a.nuMix + (static_cast<size_t>(ti) * a.T + a.type[j]) * a.T + a.type[k]);
+  // AxilrodTellerMutoFunctor.h:217-251
+  const double all2 = d2ij * d2jk * d2ki;
+  const double all5 = all2 * all2 * sqrt(all2);
+  const double factor = 3.0 * nu / all5;
+  const double IJdKI = dot3(ijx, ijy, ijz, kix, kiy, kiz);
+  const double IJdJK = dot3(ijx, ijy, ijz, jkx, jky, jkz);
+  const double JKdKI = dot3(jkx, jky, jkz, kix, kiy, kiz);
+  const double allDots = IJdKI * IJdJK * JKdKI;
+  const double cJK = IJdKI * (IJdJK - JKdKI);
+  const double cIJ = IJdJK * JKdKI - d2jk * d2ki + 5.0 * allDots / d2ij;
+  const double cKI = -IJdJK * JKdKI + d2ij * d2jk - 5.0 * allDots / d2ki;
+  const double fix = (jkx * cJK + ijx * cIJ + kix * cKI) * factor;
+  const double fiy = (jky * cJK + ijy * cIJ + kiy * cKI) * factor;
+  const double fiz = (jkz * cJK + ijz * cIJ + kiz * cKI) * factor;
+  Fx += fix;
+  Fy += fiy;
+  Fz += fiz;
+  const double u3 = factor * (all2 - 3.0 * allDots);
+  if (N3) {
+    // force on j (:241-247), F_k = -(F_i + F_j)
+    const double jKI = IJdJK * (JKdKI - IJdKI);
+    const double jIJ = -IJdKI * JKdKI + d2jk * d2ki - 5.0 * allDots / d2ij;
+    const double jJK = IJdKI * JKdKI - d2ij * d2ki + 5.0 * allDots / d2jk;
+    const double fjx = (kix * jKI + ijx * jIJ + jkx * jJK) * factor;
+    const double fjy = (kiy * jKI + ijy * jIJ + jky * jJK) * factor;
+    const double fjz = (kiz * jKI + ijz * jIJ + jkz * jJK) * factor;
+    const double fkx = (fix + fjx) * (-1.0), fky = (fiy + fjy) * (-1.0), fkz = (fiz + fjz) * (-1.0);
+    atomicAdd(a.fx + j, fjx);
+    atomicAdd(a.fy + j, fjy);
+    atomicAdd(a.fz + j, fjz);
+    atomicAdd(a.fx + k, fkx);
+    atomicAdd(a.fy + k, fky);
+    atomicAdd(a.fz + k, fkz);
+    if (STATS) {
+      ++st.kN3;
+      ++st.gN3;
+      if (ownedI) {
+        st.upot += u3;
+        st.vir[0] += fix * xi;
+        st.vir[1] += fiy * yi;
+        st.vir[2] += fiz * zi;
+      }
+      if (a.w.own[j] == APB_OWN_OWNED) {
+        st.upot += u3;
+        st.vir[0] += fjx * xj;
+        st.vir[1] += fjy * yj;
+        st.vir[2] += fjz * zj;
+      }
+      if (a.w.own[k] == APB_OWN_OWNED) {
+        st.upot += u3;
+        st.vir[0] += fkx * xk;
+        st.vir[1] += fky * yk;
+        st.vir[2] += fkz * zk;
+      }
+    }
+  } else if (STATS) {
+    ++st.kNoN3;
+    ++st.gNoN3;
+    if (ownedI) {
+      // potentialEnergy3 = factor (allDistsSquared - 3 allDotProducts); virial = f_i * r_i (:269-275)
+      st.upot += u3;
+      st.vir[0] += fix * xi;
+      st.vir[1] += fiy * yi;
+      st.vir[2] += fiz * zi;
+    }
+  }
+}
+
 // ---- one warp per particle slot ----------------------------------------------------------------------------------------
 // kATMCountWarp: neighbours of slot i within the cutoff (newton3: in higher slots), warp-cooperative walk; feeds the
 // shared-memory capacity of kATMTripletsWarp. kATMTripletsWarp: the warp collects the neighbours of i into shared memory
@@ -880,7 +964,6 @@ __global__ void __launch_bounds__(LCW_WARPS * 32) kATMTripletsWarp(ATMWarpArgs w
   const unsigned below = (1u << lane) - 1u;
   double *nx = reinterpret_cast<double *>(atmSmem) + static_cast<size_t>(warp) * 3 * cap, *ny = nx + cap, *nz = ny + cap;
   int *nslot = reinterpret_cast<int *>(atmSmem + static_cast<size_t>(LCW_WARPS) * 24 * cap) + static_cast<size_t>(warp) * 2 * cap;
-  int *ntype = nslot + cap;
   int *queue = queues[warp];
   LJStats st;
   ljStatsZero(st);
@@ -908,89 +991,15 @@ __global__ void __launch_bounds__(LCW_WARPS * 32) kATMTripletsWarp(ATMWarpArgs w
           ny[e] = a.y[j];
           nz[e] = a.z[j];
           nslot[e] = j;
-          if (MIX) ntype[e] = a.type[j];
           filled += 32;
         });
     __syncwarp();
     double Fx = 0., Fy = 0., Fz = 0.;
     auto triplet = [&](int pq) {
       const int p = pq >> 16, q = pq & 0xFFFF;
-      const double xj = nx[p], yj = ny[p], zj = nz[p], xk = nx[q], yk = ny[q], zk = nz[q];
-      const double ijx = xj - xi, ijy = yj - yi, ijz = zj - zi;
-      const double jkx = xk - xj, jky = yk - yj, jkz = zk - zj;
-      const double kix = xi - xk, kiy = yi - yk, kiz = zi - zk;
-      const double d2ij = dot3(ijx, ijy, ijz, ijx, ijy, ijz);
-      const double d2jk = dot3(jkx, jky, jkz, jkx, jky, jkz);
-      const double d2ki = dot3(kix, kiy, kiz, kix, kiy, kiz);
-      double nu = a.nu;
-      if (MIX) nu = __ldg(a.nuMix + (static_cast<size_t>(ti) * a.T + ntype[p]) * a.T + ntype[q]);
-      // AxilrodTellerMutoFunctor.h:217-251
-      const double all2 = d2ij * d2jk * d2ki;
-      const double all5 = all2 * all2 * sqrt(all2);
-      const double factor = 3.0 * nu / all5;
-      const double IJdKI = dot3(ijx, ijy, ijz, kix, kiy, kiz);
-      const double IJdJK = dot3(ijx, ijy, ijz, jkx, jky, jkz);
-      const double JKdKI = dot3(jkx, jky, jkz, kix, kiy, kiz);
-      const double allDots = IJdKI * IJdJK * JKdKI;
-      const double cJK = IJdKI * (IJdJK - JKdKI);
-      const double cIJ = IJdJK * JKdKI - d2jk * d2ki + 5.0 * allDots / d2ij;
-      const double cKI = -IJdJK * JKdKI + d2ij * d2jk - 5.0 * allDots / d2ki;
-      const double fix = (jkx * cJK + ijx * cIJ + kix * cKI) * factor;
-      const double fiy = (jky * cJK + ijy * cIJ + kiy * cKI) * factor;
-      const double fiz = (jkz * cJK + ijz * cIJ + kiz * cKI) * factor;
-      Fx += fix;
-      Fy += fiy;
-      Fz += fiz;
-      const double u3 = factor * (all2 - 3.0 * allDots);
-      if (N3) {
-        // force on j (:241-247), F_k = -(F_i + F_j)
-        const double jKI = IJdJK * (JKdKI - IJdKI);
-        const double jIJ = -IJdKI * JKdKI + d2jk * d2ki - 5.0 * allDots / d2ij;
-        const double jJK = IJdKI * JKdKI - d2ij * d2ki + 5.0 * allDots / d2jk;
-        const double fjx = (kix * jKI + ijx * jIJ + jkx * jJK) * factor;
-        const double fjy = (kiy * jKI + ijy * jIJ + jky * jJK) * factor;
-        const double fjz = (kiz * jKI + ijz * jIJ + jkz * jJK) * factor;
-        const double fkx = (fix + fjx) * (-1.0), fky = (fiy + fjy) * (-1.0), fkz = (fiz + fjz) * (-1.0);
-        const int j = nslot[p], k = nslot[q];
-        atomicAdd(a.fx + j, fjx);
-        atomicAdd(a.fy + j, fjy);
-        atomicAdd(a.fz + j, fjz);
-        atomicAdd(a.fx + k, fkx);
-        atomicAdd(a.fy + k, fky);
-        atomicAdd(a.fz + k, fkz);
-        if (STATS) {
-          ++st.kN3;
-          ++st.gN3;
-          if (ownedI) {
-            st.upot += u3;
-            st.vir[0] += fix * xi;
-            st.vir[1] += fiy * yi;
-            st.vir[2] += fiz * zi;
-          }
-          if (a.w.own[j] == APB_OWN_OWNED) {
-            st.upot += u3;
-            st.vir[0] += fjx * xj;
-            st.vir[1] += fjy * yj;
-            st.vir[2] += fjz * zj;
-          }
-          if (a.w.own[k] == APB_OWN_OWNED) {
-            st.upot += u3;
-            st.vir[0] += fkx * xk;
-            st.vir[1] += fky * yk;
-            st.vir[2] += fkz * zk;
-          }
-        }
-      } else if (STATS) {
-        ++st.kNoN3;
-        ++st.gNoN3;
-        if (ownedI) {
-          // potentialEnergy3 = factor (allDistsSquared - 3 allDotProducts); virial = f_i * r_i (:269-275)
-          st.upot += u3;
-          st.vir[0] += fix * xi;
-          st.vir[1] += fiy * yi;
-          st.vir[2] += fiz * zi;
-        }
-      }
+      // (mixing reads the partner types through their slots)
+      atmTriplet<MIX, STATS, N3>(a, xi, yi, zi, ti, ownedI, nslot[p], nslot[q], nx[p], ny[p], nz[p], nx[q], ny[q], nz[q], Fx, Fy,
+                                 Fz, st);
     };
     // ---- (j, k) pairs of the list: lanes over k for every j; survivors compacted, evaluated on full rows
     int qn = 0;
@@ -1076,80 +1085,7 @@ __global__ void __launch_bounds__(128) kATMTripletsMasked(ATMArgs a) {
     if (STATS) st.dist += static_cast<unsigned long long>(cnt) * (cnt - 1) / 2;
     double Fx = 0., Fy = 0., Fz = 0.;
     auto triplet = [&](int j, int k, double xj, double yj, double zj, double xk, double yk, double zk) {
-      const double ijx = xj - xi, ijy = yj - yi, ijz = zj - zi;
-      const double jkx = xk - xj, jky = yk - yj, jkz = zk - zj;
-      const double kix = xi - xk, kiy = yi - yk, kiz = zi - zk;
-      const double d2ij = dot3(ijx, ijy, ijz, ijx, ijy, ijz);
-      const double d2jk = dot3(jkx, jky, jkz, jkx, jky, jkz);
-      const double d2ki = dot3(kix, kiy, kiz, kix, kiy, kiz);
-      double nu = a.nu;
-      if (MIX) nu = __ldg(a.nuMix + (static_cast<size_t>(ti) * a.T + a.type[j]) * a.T + a.type[k]);
-      // AxilrodTellerMutoFunctor.h:217-251
-      const double all2 = d2ij * d2jk * d2ki;
-      const double all5 = all2 * all2 * sqrt(all2);
-      const double factor = 3.0 * nu / all5;
-      const double IJdKI = dot3(ijx, ijy, ijz, kix, kiy, kiz);
-      const double IJdJK = dot3(ijx, ijy, ijz, jkx, jky, jkz);
-      const double JKdKI = dot3(jkx, jky, jkz, kix, kiy, kiz);
-      const double allDots = IJdKI * IJdJK * JKdKI;
-      const double cJK = IJdKI * (IJdJK - JKdKI);
-      const double cIJ = IJdJK * JKdKI - d2jk * d2ki + 5.0 * allDots / d2ij;
-      const double cKI = -IJdJK * JKdKI + d2ij * d2jk - 5.0 * allDots / d2ki;
-      const double fix = (jkx * cJK + ijx * cIJ + kix * cKI) * factor;
-      const double fiy = (jky * cJK + ijy * cIJ + kiy * cKI) * factor;
-      const double fiz = (jkz * cJK + ijz * cIJ + kiz * cKI) * factor;
-      Fx += fix;
-      Fy += fiy;
-      Fz += fiz;
-      const double u3 = factor * (all2 - 3.0 * allDots);
-      if (N3) {
-        // force on j (:241-247), F_k = -(F_i + F_j)
-        const double jKI = IJdJK * (JKdKI - IJdKI);
-        const double jIJ = -IJdKI * JKdKI + d2jk * d2ki - 5.0 * allDots / d2ij;
-        const double jJK = IJdKI * JKdKI - d2ij * d2ki + 5.0 * allDots / d2jk;
-        const double fjx = (kix * jKI + ijx * jIJ + jkx * jJK) * factor;
-        const double fjy = (kiy * jKI + ijy * jIJ + jky * jJK) * factor;
-        const double fjz = (kiz * jKI + ijz * jIJ + jkz * jJK) * factor;
-        const double fkx = (fix + fjx) * (-1.0), fky = (fiy + fjy) * (-1.0), fkz = (fiz + fjz) * (-1.0);
-        atomicAdd(a.fx + j, fjx);
-        atomicAdd(a.fy + j, fjy);
-        atomicAdd(a.fz + j, fjz);
-        atomicAdd(a.fx + k, fkx);
-        atomicAdd(a.fy + k, fky);
-        atomicAdd(a.fz + k, fkz);
-        if (STATS) {
-          ++st.kN3;
-          ++st.gN3;
-          if (ownedI) {
-            st.upot += u3;
-            st.vir[0] += fix * xi;
-            st.vir[1] += fiy * yi;
-            st.vir[2] += fiz * zi;
-          }
-          if (a.w.own[j] == APB_OWN_OWNED) {
-            st.upot += u3;
-            st.vir[0] += fjx * xj;
-            st.vir[1] += fjy * yj;
-            st.vir[2] += fjz * zj;
-          }
-          if (a.w.own[k] == APB_OWN_OWNED) {
-            st.upot += u3;
-            st.vir[0] += fkx * xk;
-            st.vir[1] += fky * yk;
-            st.vir[2] += fkz * zk;
-          }
-        }
-      } else if (STATS) {
-        ++st.kNoN3;
-        ++st.gNoN3;
-        if (ownedI) {
-          // potentialEnergy3 = factor (allDistsSquared - 3 allDotProducts); virial = f_i * r_i (:269-275)
-          st.upot += u3;
-          st.vir[0] += fix * xi;
-          st.vir[1] += fiy * yi;
-          st.vir[2] += fiz * zi;
-        }
-      }
+      atmTriplet<MIX, STATS, N3>(a, xi, yi, zi, ti, ownedI, j, k, xj, yj, zj, xk, yk, zk, Fx, Fy, Fz, st);
     };
     // ---- pass 2: the surviving triplets of this slot, one after the other; the loads of triplet t + 1 are in flight
     // while triplet t is evaluated
