@@ -6,7 +6,7 @@ This package is the Python host mirror used by tests and benchmarks; ``shim/`` h
 from . import capi
 from .capi import ApbError
 from .containers import (AxilrodTellerMutoFunctor, GpuParticleContainer, GpuTraversal, LJFunctor, LJMultisiteFunctor,
-                         ParticlePropertiesLibrary, SPHCalcDensityFunctor, SPHCalcHydroForceFunctor)
+                         ParallelVtkWriter, ParticlePropertiesLibrary, SPHCalcDensityFunctor, SPHCalcHydroForceFunctor)
 
 __all__ = ["capi", "ApbError", "GpuParticleContainer", "GpuTraversal", "LJFunctor", "ParticlePropertiesLibrary",
-           "SPHCalcDensityFunctor", "SPHCalcHydroForceFunctor", "AxilrodTellerMutoFunctor", "LJMultisiteFunctor"]
+           "SPHCalcDensityFunctor", "SPHCalcHydroForceFunctor", "AxilrodTellerMutoFunctor", "LJMultisiteFunctor", "ParallelVtkWriter"]

@@ -605,6 +605,15 @@ class GpuParticleContainer:
             raise ApbError(capi.ERR_INVALID_ARGUMENT, "wire data is not a whole number of 120-byte records")
         self._check(self._lib.apb_deserialize_particles(self._h, _ptr(data), len(data) // capi.WIRE_RECORD_BYTES))
 
+    def vtkParticleRecord(self):
+        """ParallelVtkWriter::recordParticleStates (examples/md-flexible/src/ParallelVtkWriter.cpp:55-201): the bytes of
+        this rank's `.vtu` piece, formatted on the device from the SoA columns (uint8 array)."""
+        n = ctypes.c_int64()
+        self._check(self._lib.apb_vtk_particle_record(self._h, None, 0, ctypes.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        self._check(self._lib.apb_vtk_particle_record(self._h, _ptr(buf), n.value, ctypes.byref(n)))
+        return buf[: n.value]
+
     def leaverColumn(self, name):
         """Any other attribute of the particles the last updateContainer returned (they are whole copies in the
         reference, LeavingParticleCollector.h:101-110), in the same order."""
@@ -778,3 +787,37 @@ class GpuParticleContainer:
         out = np.zeros((max(g.num_cluster_pairs, 1), 2), dtype=np.int64)
         self._check(self._lib.apb_debug_cluster_pairs(self._h, _ptr(out)))
         return out[:g.num_cluster_pairs]
+
+
+class ParallelVtkWriter:
+    """md-flexible's checkpoint writer (examples/md-flexible/src/ParallelVtkWriter.h:21-37) over the device-side record:
+    same constructor arguments, same folders and file names (`<folder>/<session>/<session>_Particles_<iteration>.pvtu`,
+    `<folder>/<session>/data/<session>_Particles_<rank>_<iteration>.vtu`, ParallelVtkWriter.cpp:285-296, 437-441), so that
+    md-flexible's `--checkpoint` loader (MDFlexConfig.cpp:91-180) reads what it wrote."""
+
+    def __init__(self, sessionName, outputFolder, maximumNumberOfDigitsInIteration, rank=0, numberOfRanks=1):
+        import os
+        self._session, self._digits, self._rank, self._ranks = sessionName, int(maximumNumberOfDigitsInIteration), int(rank), int(numberOfRanks)
+        self._sessionFolder = os.path.join(outputFolder, sessionName) + "/"
+        self._dataFolder = self._sessionFolder + "data/"
+        if self._rank == 0:
+            os.makedirs(self._dataFolder, exist_ok=True)
+
+    def pvtuRecord(self, currentIteration):
+        lib = capi.load()
+        n = ctypes.c_int64()
+        args = (self._session.encode(), self._ranks, int(currentIteration), self._digits)
+        if lib.apb_vtk_pvtu_record(*args, None, 0, ctypes.byref(n)) != capi.APB_OK:
+            raise ApbError(capi.ERR_INVALID_ARGUMENT, "apb_vtk_pvtu_record: bad argument")
+        buf = np.zeros(n.value, dtype=np.uint8)
+        lib.apb_vtk_pvtu_record(*args, _ptr(buf), n.value, ctypes.byref(n))
+        return buf
+
+    def recordParticleStates(self, currentIteration, container):
+        """Writes the `.pvtu` index (rank 0) and this rank's `.vtu` piece; returns the piece's path."""
+        it = str(int(currentIteration)).zfill(self._digits)
+        if self._rank == 0:
+            self.pvtuRecord(currentIteration).tofile(f"{self._sessionFolder}{self._session}_Particles_{it}.pvtu")
+        path = f"{self._dataFolder}{self._session}_Particles_{self._rank}_{it}.vtu"
+        container.vtkParticleRecord().tofile(path)
+        return path

@@ -183,6 +183,9 @@ struct apb_handle_s {
 
   // ---- loop control (control.cu): thermostat, dynamic-rebuild trigger, remainder staging ----
   DevBuf thermoDev, rAtRebuild, remBuf;
+  // checkpoint record (vtk.cu): control words, libm tables, owned flags + row index, row lengths + offsets, the text
+  DevBuf vtkCtl, vtkTables, vtkFlag, vtkLen, vtkOut;
+  bool vtkTablesReady = false;
   bool thermostatOn = false;
   int thermostatInterval = 1;
   double thermostatTarget = 0., thermostatDelta = 0.;

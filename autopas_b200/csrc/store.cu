@@ -354,7 +354,7 @@ extern "C" int apb_destroy(apb_handle h) {
                     &h->prNumCompact, &h->prCompactSlot, &h->haloAllSrc, &h->haloAllDst, &h->haloAllCode, &h->prEntryLo, &h->partials2};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
-  DevBuf *ctrl[] = {&h->thermoDev, &h->rAtRebuild, &h->remBuf};
+  DevBuf *ctrl[] = {&h->thermoDev, &h->rAtRebuild, &h->remBuf, &h->vtkCtl, &h->vtkTables, &h->vtkFlag, &h->vtkLen, &h->vtkOut};
   for (DevBuf *b : ctrl)
     if (b->p) cudaFree(b->p);
   DevBuf *more[] = {&h->prStageEarly, &h->prTileFirst, &h->prTileNum, &h->prTileWarp, &h->loopResults, &h->invPerm, &h->xbuf[0], &h->xbuf[1], &h->xbuf[2], &h->xbuf[3], &h->massDev};

@@ -965,6 +965,18 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
       reduceLambda(*it, result);
   }
 
+  /// md-flexible's checkpoint piece of this rank, formatted on the device (ParallelVtkWriter::recordParticleStates,
+  /// examples/md-flexible/src/ParallelVtkWriter.cpp:55-201): the bytes the reference writer puts into
+  /// "<session>_Particles_<rank>_<iteration>.vtu" when it walks this container's owned particles.
+  [[nodiscard]] std::string vtkParticleRecord() {
+    syncToDevice();
+    int64_t bytes = 0;
+    check(apb_vtk_particle_record(_h, nullptr, 0, &bytes));
+    std::string record(static_cast<size_t>(bytes), '\0');
+    check(apb_vtk_particle_record(_h, record.data(), bytes, &bytes));
+    return record;
+  }
+
   /// the C handle, for device-resident extensions (apb_run_steps, apb_exchange_halos, ...)
   [[nodiscard]] apb_handle handle() {
     syncToDevice();

@@ -220,6 +220,18 @@ int apb_reset_forces(apb_handle h, double fx, double fy, double fz);
 #define APB_WIRE_RECORD_BYTES 120
 int apb_serialize_particles(apb_handle h, int32_t ownership_mask, void *dst, int64_t capacity_records, int64_t *out_num);
 int apb_deserialize_particles(apb_handle h, const void *src, int64_t num_records);
+/* md-flexible's VTK checkpoint (examples/md-flexible/src/ParallelVtkWriter.cpp:55-201 recordParticleStates): the bytes of
+ * one rank's "<session>_Particles_<rank>_<iteration>.vtu" piece - velocities, forces, typeIds, ids, positions of the owned
+ * particles as ASCII rows in storage order, doubles as a default std::ostream prints them ("%.6g"), positions next to
+ * the upper box corner with the raised precision of writeWithDynamicPrecision (:130-157) - formatted on the device from
+ * the SoA columns and copied into `dst` (host). dst == NULL: only the size is returned through out_bytes. Where the
+ * reference throws (a position identical to the border up to 15 digits) the call fails with
+ * APB_ERR_INVALID_ARGUMENT. Single-site particles only. md-flexible's loader (MDFlexConfig.cpp:91-180) reads the file. */
+int apb_vtk_particle_record(apb_handle h, void *dst, int64_t capacity_bytes, int64_t *out_bytes);
+/* The "<session>_Particles_<iteration>.pvtu" index rank 0 writes next to the pieces (ParallelVtkWriter.cpp:308-356,
+ * file names as generateFilename :437-441 builds them); host text, no handle. */
+int apb_vtk_pvtu_record(const char *session_name, int32_t num_ranks, uint64_t iteration, int32_t digits, char *dst,
+                        int64_t capacity_bytes, int64_t *out_bytes);
 
 /* ---- container maintenance ------------------------------------------------------------------------------------- */
 /* ParticleContainerInterface::updateContainer(bool keepNeighborListsValid) (:297);

@@ -521,6 +521,78 @@ def ref_wire_deserialize(data):
     return {"id": ids, "r": c[:, 0:3], "v": c[:, 3:6], "f": c[:, 6:9], "oldf": c[:, 9:12], "type": types, "own": own}
 
 
+# ---- md-flexible's VTK checkpoint record --------------------------------------------------------------------------------
+_REF_VTK = os.path.join(_HERE, "_ref", "vtk_ref_writer")
+
+
+def vtk_particle_record(ids, r, v, f, types, box_max):
+    """oracle/vtk_oracle.c: the bytes of one rank's `<session>_Particles_<rank>_<iteration>.vtu` piece for the particles
+    in the given order (ParallelVtkWriter.cpp:55-201). Raises ValueError where the reference would throw."""
+    fn = lib().vtk_oracle_particle_record
+    fn.restype = ctypes.c_int64
+    n = len(ids)
+    r_, v_, f_, ids_, types_, bm = _f64(r).reshape(-1), _f64(v).reshape(-1), _f64(f).reshape(-1), _i64(ids), _i64(types), _f64(box_max)
+    args = (ctypes.c_int64(n), _p(r_), _p(v_), _p(f_), _p(ids_), _p(types_), _p(bm))
+    need = fn(*args, None, ctypes.c_int64(0))
+    if need < 0:
+        raise ValueError("a position cannot be told from the box border within 15 digits")
+    out = np.zeros(need, dtype=np.uint8)
+    got = fn(*args, _p(out), ctypes.c_int64(need))
+    assert got == need
+    return out
+
+
+def vtk_position_precision(position, border):
+    fn = lib().vtk_oracle_position_precision
+    fn.restype = ctypes.c_int
+    return fn(ctypes.c_double(position), ctypes.c_double(border))
+
+
+def vtk_pvtu_record(session, num_ranks, iteration, digits):
+    """The `.pvtu` index of rank 0 (ParallelVtkWriter.cpp:308-356)."""
+    fn = lib().vtk_oracle_pvtu_record
+    fn.restype = ctypes.c_int64
+    args = (session.encode(), ctypes.c_int(num_ranks), ctypes.c_uint64(iteration), ctypes.c_int(digits))
+    need = fn(*args, None, ctypes.c_int64(0))
+    out = np.zeros(need, dtype=np.uint8)
+    fn(*args, _p(out), ctypes.c_int64(need))
+    return out
+
+
+def have_ref_vtk():
+    return os.path.exists(_REF_VTK)
+
+
+def ref_vtk_records(ids, r, v, f, types, box_min, box_max, session="ref", iteration=7, digits=6):
+    """The unmodified ParallelVtkWriter (oracle/_ref/vtk_ref_writer, oracle/ref_driver_vtk.cpp) on a stock
+    AutoPas<MoleculeLJ> holding these particles -> (bytes of the .vtu piece, bytes of the .pvtu index). The piece lists
+    the particles in the iteration order of the reference's container; its `ids` array tells which."""
+    import tempfile
+    n = len(ids)
+    rec = np.zeros(n, dtype=[("r", "<f8", 3), ("v", "<f8", 3), ("f", "<f8", 3), ("id", "<i8"), ("type", "<i8")])
+    rec["r"], rec["v"], rec["f"], rec["id"], rec["type"] = r, v, f, ids, types
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "in.bin"), "wb") as fh:
+            fh.write(np.int64(n).tobytes())
+            fh.write(_f64(box_min).tobytes())
+            fh.write(_f64(box_max).tobytes())
+            fh.write(rec.tobytes())
+        os.makedirs(os.path.join(d, "out"))
+        subprocess.run([_REF_VTK, os.path.join(d, "in.bin"), os.path.join(d, "out"), session, str(iteration), str(digits)],
+                       check=True, stdout=subprocess.DEVNULL, cwd=d)
+        it = str(iteration).zfill(digits)
+        piece = np.fromfile(os.path.join(d, "out", session, "data", f"{session}_Particles_0_{it}.vtu"), dtype=np.uint8)
+        index = np.fromfile(os.path.join(d, "out", session, f"{session}_Particles_{it}.pvtu"), dtype=np.uint8)
+    return piece, index
+
+
+def vtk_parse_ids(piece):
+    """The `ids` DataArray of a .vtu piece as the checkpoint loader reads it (MDFlexConfig.cpp:158-160)."""
+    text = bytes(piece).decode()
+    body = text.split('Name="ids"', 1)[1].split(">\n", 1)[1].split("</DataArray>", 1)[0]
+    return np.array([int(t) for t in body.split()], dtype=np.int64)
+
+
 def ref_set_timing_reps(reps):
     """The extra-functor drivers (ref_sph, ref_atm) time their traversal; with reps > 1 they repeat it (outputs then only
     serve timing)."""

@@ -1,0 +1,73 @@
+// TEST INFRASTRUCTURE ONLY — never linked into or called from the product path.
+//
+// Runs the UNMODIFIED md-flexible checkpoint writer (examples/md-flexible/src/ParallelVtkWriter.cpp, compiled where it
+// lies, single-site mode) on a stock autopas::AutoPas<MoleculeLJ> filled with the particles of a binary input file, so
+// that the bytes of its "<session>_Particles_<rank>_<iteration>.vtu" piece and of the ".pvtu" index can pin the oracle
+// restatement (oracle/vtk_oracle.c) and, through it, apb_vtk_particle_record.
+//
+//   vtk_ref_writer <input.bin> <output folder> <session name> <iteration> <digits>
+//
+// input.bin: int64 n, double boxMin[3], boxMax[3], then n records of {double r[3], v[3], f[3]; int64 id, type}.
+// ParallelVtkWriter::recordParticleStates is private (the public recordTimestep also wants a RegularGridDecomposition,
+// i.e. md-flexible's whole YAML configuration); the access specifier is lifted for this translation unit only - the
+// writer's source is untouched.
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include <sys/stat.h>
+
+#include <array>
+#include <sstream>
+#include <string>
+#include <unordered_set>
+
+#include "autopas/AutoPasImpl.h"
+#include "autopas/tuning/Configuration.h"
+#include "src/TypeDefinitions.h"
+#include "src/domainDecomposition/RegularGridDecomposition.h"
+// everything ParallelVtkWriter.h includes has been seen (and is guarded): the macro only reaches the writer's class
+#define private public
+#include "ParallelVtkWriter.h"
+#undef private
+
+template class autopas::AutoPas<ParticleType>;
+
+int main(int argc, char **argv) {
+  if (argc < 6) {
+    std::fprintf(stderr, "usage: %s input.bin folder session iteration digits\n", argv[0]);
+    return 2;
+  }
+  std::FILE *in = std::fopen(argv[1], "rb");
+  if (!in) return 3;
+  int64_t n = 0;
+  double box[6];
+  if (std::fread(&n, 8, 1, in) != 1 || std::fread(box, 8, 6, in) != 6) return 4;
+  struct Rec {
+    double r[3], v[3], f[3];
+    int64_t id, type;
+  };
+  std::vector<Rec> recs(static_cast<size_t>(n));
+  if (n > 0 && std::fread(recs.data(), sizeof(Rec), recs.size(), in) != recs.size()) return 5;
+  std::fclose(in);
+
+  autopas::AutoPas<ParticleType> autoPas;
+  autoPas.setBoxMin({box[0], box[1], box[2]});
+  autoPas.setBoxMax({box[3], box[4], box[5]});
+  autoPas.setCutoff(1.0);
+  autoPas.setVerletSkin(0.2);
+  autoPas.setAllowedContainers({autopas::ContainerOption::linkedCells});
+  autoPas.setAllowedTraversals({autopas::TraversalOption::lc_c08});
+  autoPas.setOutputSuffix("apb_vtk_ref");
+  autoPas.init();
+  for (const auto &q : recs) {
+    ParticleType p({q.r[0], q.r[1], q.r[2]}, {q.v[0], q.v[1], q.v[2]}, static_cast<unsigned long>(q.id),
+                   static_cast<unsigned long>(q.type));
+    p.setF({q.f[0], q.f[1], q.f[2]});
+    autoPas.addParticle(p);
+  }
+  ParallelVtkWriter writer(argv[3], argv[2], std::atoi(argv[5]));
+  writer.recordParticleStates(static_cast<size_t>(std::atoll(argv[4])), autoPas);
+  std::printf("%zu\n", autoPas.getNumberOfParticles(autopas::IteratorBehavior::owned));
+  return 0;
+}

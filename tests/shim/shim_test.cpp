@@ -6,6 +6,8 @@
 // LinkedCells, csf 1, lc_c08, AoS, newton3 (:210-214).
 #include <cmath>
 #include <cstdio>
+#include <iomanip>
+#include <sstream>
 #include <map>
 #include <random>
 #include <set>
@@ -352,6 +354,71 @@ static void compareSPH(const Scenario &s0) {
   }
 }
 
+// The checkpoint piece formatted on the device against the reference writer's own statements
+// (examples/md-flexible/src/ParallelVtkWriter.cpp:79-166) run over the same container's iterators: same particle order,
+// same std::ostream formatting, same libm in writeWithDynamicPrecision.
+static void compareVtk(const Scenario &s) {
+  autopas_b200::GpuParticleContainer<Molecule> gpu(APB_CONTAINER_VERLET_CLUSTER_LISTS, s.boxMin, s.boxMax, s.cutoff, s.skin, 4);
+  fill(gpu, s);
+  size_t k = 0;
+  for (auto it = gpu.begin(autopas::IteratorBehavior::owned); it.isValid(); ++it, ++k) {
+    it->setF({1e3 * std::sin(double(k)), -1e-7 * k, k % 7 == 0 ? 0. : 1e9 / (k + 1.)});
+    if (k % 50 == 0) {  // next to the upper corner: raised precision
+      auto r = it->getR();
+      r[k % 3] = s.boxMax[k % 3] - std::pow(10., -1. - double(k % 11));
+      it->setR(r);
+    }
+  }
+  std::ostringstream want;
+  const auto n = gpu.getNumberOfParticles(autopas::IteratorBehavior::owned);
+  want << "<?xml version=\"1.0\" encoding=\"UTF-8\" standalone=\"no\" ?>\n";
+  want << "<VTKFile byte_order=\"LittleEndian\" type=\"UnstructuredGrid\" version=\"0.1\">\n";
+  want << "  <UnstructuredGrid>\n";
+  want << "    <Piece NumberOfCells=\"0\" NumberOfPoints=\"" << n << "\">\n";
+  want << "      <PointData>\n";
+  want << "        <DataArray Name=\"velocities\" NumberOfComponents=\"3\" format=\"ascii\" type=\"Float32\">\n";
+  for (auto p = gpu.begin(autopas::IteratorBehavior::owned); p.isValid(); ++p)
+    want << "        " << p->getV()[0] << " " << p->getV()[1] << " " << p->getV()[2] << "\n";
+  want << "        </DataArray>\n";
+  want << "        <DataArray Name=\"forces\" NumberOfComponents=\"3\" format=\"ascii\" type=\"Float32\">\n";
+  for (auto p = gpu.begin(autopas::IteratorBehavior::owned); p.isValid(); ++p)
+    want << "        " << p->getF()[0] << " " << p->getF()[1] << " " << p->getF()[2] << "\n";
+  want << "        </DataArray>\n";
+  want << "        <DataArray Name=\"typeIds\" NumberOfComponents=\"1\" format=\"ascii\" type=\"Int32\">\n";
+  for (auto p = gpu.begin(autopas::IteratorBehavior::owned); p.isValid(); ++p) want << "        " << p->getTypeId() << "\n";
+  want << "        </DataArray>\n";
+  want << "        <DataArray Name=\"ids\" NumberOfComponents=\"1\" format=\"ascii\" type=\"Int32\">\n";
+  for (auto p = gpu.begin(autopas::IteratorBehavior::owned); p.isValid(); ++p) want << "        " << p->getID() << "\n";
+  want << "        </DataArray>\n";
+  want << "      </PointData>\n      <CellData/>\n      <Points>\n";
+  want << "        <DataArray Name=\"positions\" NumberOfComponents=\"3\" format=\"ascii\" type=\"Float32\">\n";
+  const auto boxMax = gpu.getBoxMax();
+  for (auto p = gpu.begin(autopas::IteratorBehavior::owned); p.isValid(); ++p) {
+    const auto dynamic = [&](double position, double border) {
+      const auto initial = want.precision();
+      if (border - position < 0.1)
+        while (autopas::utils::Math::isNearAbs(autopas::utils::Math::roundFloating(position, want.precision()), border,
+                                               std::pow(10, -want.precision())))
+          want << std::setprecision(want.precision() + 1);
+      want << position << std::setprecision(initial);
+    };
+    want << "        ";
+    dynamic(p->getR()[0], boxMax[0]);
+    want << " ";
+    dynamic(p->getR()[1], boxMax[1]);
+    want << " ";
+    dynamic(p->getR()[2], boxMax[2]);
+    want << "\n";
+  }
+  want << "        </DataArray>\n      </Points>\n      <Cells>\n";
+  want << "        <DataArray Name=\"types\" NumberOfComponents=\"0\" format=\"ascii\" type=\"Float32\"/>\n";
+  want << "      </Cells>\n    </Piece>\n  </UnstructuredGrid>\n</VTKFile>\n";
+  const std::string got = gpu.vtkParticleRecord();
+  CHECK(got == want.str(), "device-side VTK record differs from the reference writer's statements (%zu vs %zu bytes)", got.size(),
+        want.str().size());
+  std::printf("vtk record: %zu particles, %zu bytes, %s\n", size_t(n), got.size(), got == want.str() ? "identical" : "DIFFERENT");
+}
+
 int main() {
   autopas::utils::ExceptionHandler::setBehavior(autopas::utils::ExceptionBehavior::throwException);
   const Scenario s = makeScenario(42);
@@ -366,6 +433,7 @@ int main() {
     compareATM<true>(s);
     compareSPH<false>(s);
     compareSPH<true>(s);
+    compareVtk(s);
     // wrong traversal type is rejected like the reference containers do
     autopas_b200::GpuParticleContainer<Molecule> gpu(APB_CONTAINER_LINKED_CELLS, s.boxMin, s.boxMax, s.cutoff, s.skin);
     using RefFunctor = mdLib::LJFunctor<Molecule>;

@@ -1,0 +1,224 @@
+"""md-flexible's VTK checkpoint record (examples/md-flexible/src/ParallelVtkWriter.cpp:55-201, :308-356).
+CPU: the oracle restatement (oracle/vtk_oracle.c) against bytes written by the unmodified reference writer (committed
+fixture tests/golden/fn_vtk.npz, and live when oracle/_ref travelled); the product's decimal formatter
+(autopas_b200/csrc/vtk_format.cuh, compiled for the host by this test) against the C library's printf.
+GPU: apb_vtk_particle_record byte for byte against the oracle and the fixture, error paths, full-size record."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from autopas_b200 import ApbError, GpuParticleContainer, ParallelVtkWriter, capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden", "fn_vtk.npz")
+
+
+def _golden():
+    g = np.load(GOLDEN)
+    return g
+
+
+def _in_order_of(piece, ids):
+    """row order of a piece (its `ids` array) as indices into `ids`"""
+    where = {int(i): k for k, i in enumerate(ids)}
+    return np.array([where[int(i)] for i in oracle.vtk_parse_ids(piece)])
+
+
+def test_oracle_vtk_record_matches_reference_bytes():
+    g = _golden()
+    o = _in_order_of(g["ref_piece"], g["ids"])  # iteration order of the reference's LinkedCells
+    assert sorted(o) == list(range(len(g["ids"])))
+    mine = oracle.vtk_particle_record(g["ids"][o], g["r"][o], g["v"][o], g["f"][o], g["types"][o], g["box_max"])
+    assert np.array_equal(mine, g["ref_piece"])
+    text = bytes(mine).decode()
+    assert "9.9999999999999 " in text and " inf -inf nan\n" in text and "e-310" in text  # raised precision, specials, denormals
+    assert np.array_equal(oracle.vtk_pvtu_record(str(g["session"]), 1, int(g["iteration"]), int(g["digits"])), g["ref_pvtu"])
+
+
+@pytest.mark.skipif(not oracle.have_ref_vtk(), reason="oracle/_ref/vtk_ref_writer not built (reference tree absent)")
+def test_oracle_vtk_record_matches_reference_live():
+    rng = np.random.default_rng(9)
+    n = 3000
+    lo, hi = np.array([-3.0, 0.0, 100.0]), np.array([12.5, 1000.0, 104.0])
+    r = lo + rng.uniform(0, 1, (n, 3)) * (hi - lo)
+    for d in range(3):
+        r[d * 200:(d + 1) * 200, d] = hi[d] - 10.0 ** -rng.uniform(1, 12, 200)
+    v = rng.normal(size=(n, 3)) * 10.0 ** rng.integers(-12, 12, (n, 3))
+    f = rng.normal(size=(n, 3)) * 10.0 ** rng.integers(-6, 15, (n, 3))
+    ids, types = rng.permutation(7 * n)[:n].astype(np.int64), rng.integers(0, 5, n).astype(np.int64)
+    piece, index = oracle.ref_vtk_records(ids, r, v, f, types, lo, hi, "live", 123456, 4)
+    o = _in_order_of(piece, ids)
+    assert np.array_equal(oracle.vtk_particle_record(ids[o], r[o], v[o], f[o], types[o], hi), piece)
+    assert np.array_equal(oracle.vtk_pvtu_record("live", 1, 123456, 4), index)  # iteration wider than the digits
+
+
+@pytest.fixture(scope="module")
+def host_formatter(tmp_path_factory):
+    """vtk_format.cuh compiled for the host (tests/vtk/vtk_format_host.cpp): the same functions the kernels call."""
+    so = str(tmp_path_factory.mktemp("vtkfmt") / "libvtkfmt.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-x", "c++",
+                    "-I" + os.path.join(HERE, "..", "autopas_b200", "csrc"), "-o", so, os.path.join(HERE, "vtk", "vtk_format_host.cpp")],
+                   check=True)
+    lib = ctypes.CDLL(so)
+    lib.check_random.restype = ctypes.c_int64
+    lib.position_precision.argtypes = [ctypes.c_double, ctypes.c_double]
+    lib.fmt_g.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_char_p]
+    lib.fmt_u64.argtypes = [ctypes.c_uint64, ctypes.c_char_p]
+    return lib
+
+
+def test_formatter_equals_printf(host_formatter):
+    """Every precision the writer can use (6 ... 15, plus 1, 3, 16, 17) on random bit patterns (all exponents,
+    denormals), MD-like magnitudes, exact decimal ties and the neighbourhood of powers of ten."""
+    msg = ctypes.create_string_buffer(256)
+    for mode, count in ((0, 200_000), (1, 200_000), (2, 200_000), (3, 100_000)):
+        bad = host_formatter.check_random(ctypes.c_uint64(1000 + mode), ctypes.c_int64(count), mode, msg)
+        assert bad == 0, msg.value.decode()
+    buf = ctypes.create_string_buffer(64)
+    for v, want in ((0.0, "0"), (-0.0, "-0"), (float("inf"), "inf"), (float("-inf"), "-inf"), (0.5, "0.5"), (1e-5, "1e-05"),
+                    (123456.5, "123456"), (123457.5, "123458"), (999999.5, "1e+06"), (0.0001, "0.0001"), (5e-324, "4.94066e-324"),
+                    (1.7976931348623157e308, "1.79769e+308"), (100.0, "100"), (2.5e-5, "2.5e-05")):
+        n = host_formatter.fmt_g(v, 6, buf)
+        assert buf.raw[:n].decode() == want == "%g" % v, (v, buf.raw[:n])
+    for v in (0, 7, 10, 4294967296, 2 ** 64 - 1):
+        n = host_formatter.fmt_u64(v, buf)
+        assert buf.raw[:n].decode() == str(v)
+
+
+def test_position_precision_equals_oracle(host_formatter):
+    """writeWithDynamicPrecision's precision choice (ParallelVtkWriter.cpp:130-157) incl. the cases where it throws."""
+    rng = np.random.default_rng(0)
+    seen = set()
+    for it in range(40_000):
+        border = float(rng.choice([10.0, 100.0, 7.5, 1.0, 1000.0, 37.8, 0.3, 1e-3, 12345.678, 1e6, 378.0]))
+        kind = it % 4
+        if kind == 0:
+            pos = border - 10.0 ** (-rng.uniform(0, 17))
+        elif kind == 1:
+            pos = border - rng.integers(1, 300) * np.spacing(border)
+        elif kind == 2:
+            pos = rng.uniform(-border, border)
+        else:
+            pos = border * (1 - 10.0 ** (-rng.integers(1, 16)))
+        want = oracle.vtk_position_precision(pos, border)
+        assert host_formatter.position_precision(pos, border) == want, (pos.hex(), border)
+        seen.add(want)
+    assert seen == {-1, *range(6, 16)}
+
+
+def test_pvtu_record_through_the_c_abi():
+    """host text only (no device): equal to the reference's index file"""
+    g = _golden()
+    w = ParallelVtkWriter.__new__(ParallelVtkWriter)
+    w._session, w._digits, w._rank, w._ranks = str(g["session"]), int(g["digits"]), 0, 1
+    assert np.array_equal(w.pvtuRecord(int(g["iteration"])), g["ref_pvtu"])
+    w._ranks, w._digits = 3, 2
+    assert np.array_equal(w.pvtuRecord(12345), oracle.vtk_pvtu_record(str(g["session"]), 3, 12345, 2))
+
+
+def _fill(c, ids, r, v, f, types):
+    c.addParticles(r[:, 0], r[:, 1], r[:, 2], ids, types.astype(np.int32))
+    sid, _, _ = c.downloadIds()
+    where = {int(i): k for k, i in enumerate(ids)}
+    order = np.array([where[int(i)] for i in sid])
+    for name, a in (("V", v), ("F", f)):
+        for d, ax in enumerate("XYZ"):
+            c.uploadColumn(name + ax, a[order, d])
+    return order
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("container", ["gpuLinkedCells", "gpuVerletClusterLists"])
+def test_gpu_vtk_record_is_byte_exact(container, tmp_path):
+    g = _golden()
+    ids, r, v, f, types = g["ids"], g["r"], g["v"], g["f"], g["types"]
+    c = GpuParticleContainer(container, g["box_min"], g["box_max"], 1.0, 0.2, clusterSize=4)
+    order = _fill(c, ids, r, v, f, types)
+    want = oracle.vtk_particle_record(ids[order], r[order], v[order], f[order], types[order], g["box_max"])
+    got = c.vtkParticleRecord()
+    assert len(got) == len(want) and np.array_equal(got, want), bytes(got[:400])
+    # the same rows as the reference's file, whatever order its container iterates in
+    rows = lambda piece, name: sorted(bytes(piece).decode().split(f'Name="{name}"', 1)[1].split(">\n", 1)[1].split("        </DataArray>", 1)[0].splitlines())  # noqa: E731
+    for name in ("velocities", "forces", "typeIds", "ids", "positions"):
+        assert rows(got, name) == rows(g["ref_piece"], name), name
+    # halo copies and deleted particles are not part of the record (IteratorBehavior::owned)
+    c.addHaloParticles(np.array([-0.5]), np.array([0.0]), np.array([1.0]), np.array([999999], dtype=np.int64))
+    assert np.array_equal(c.vtkParticleRecord(), want)
+    # after a rebuild the rows follow the new storage order
+    if container == "gpuVerletClusterLists":
+        from autopas_b200 import GpuTraversal, LJFunctor
+        fn = LJFunctor(1.0)
+        fn.setParticleProperties(1.0, 1.0)
+        c.rebuildNeighborLists(GpuTraversal("gpuvcl_cluster_iteration", fn, False))
+        sid, _, sown = c.downloadIds()
+        where = {int(i): k for k, i in enumerate(ids)}
+        o2 = np.array([where[int(i)] for i, s in zip(sid, sown) if s == 1])
+        assert np.array_equal(c.vtkParticleRecord(), oracle.vtk_particle_record(ids[o2], r[o2], v[o2], f[o2], types[o2], g["box_max"]))
+    # files through the writer mirror: names as the reference's loader expects them (MDFlexConfig.cpp:91-120)
+    w = ParallelVtkWriter("sess", str(tmp_path), 6)
+    path = w.recordParticleStates(42, c)
+    assert path.endswith("/sess/data/sess_Particles_0_000042.vtu") and os.path.getsize(path) == len(c.vtkParticleRecord())
+    assert np.array_equal(np.fromfile(str(tmp_path / "sess" / "sess_Particles_000042.pvtu"), dtype=np.uint8),
+                          oracle.vtk_pvtu_record("sess", 1, 42, 6))
+    c.close()
+
+
+@pytest.mark.gpu
+def test_gpu_vtk_record_error_paths_and_empty_container():
+    box = [10.0, 10.0, 10.0]
+    c = GpuParticleContainer("gpuLinkedCells", [0, 0, 0], box, 1.0, 0.2)
+    assert np.array_equal(c.vtkParticleRecord(), oracle.vtk_particle_record(np.zeros(0, np.int64), np.zeros((0, 3)), np.zeros((0, 3)),
+                                                                          np.zeros((0, 3)), np.zeros(0, np.int64), box))
+    c.addParticles(np.array([5.0, np.nextafter(10.0, 0.0)]), np.array([5.0, 5.0]), np.array([5.0, 5.0]), np.array([1, 2], dtype=np.int64))
+    with pytest.raises(ValueError):
+        oracle.vtk_particle_record(np.array([2]), np.array([[np.nextafter(10.0, 0.0), 5.0, 5.0]]), np.zeros((1, 3)), np.zeros((1, 3)),
+                                   np.array([0]), box)
+    with pytest.raises(ApbError, match="15 digits"):  # the reference throws std::runtime_error (ParallelVtkWriter.cpp:141-149)
+        c.vtkParticleRecord()
+    c.deleteAllParticles()
+    c.addParticles(np.array([5.0]), np.array([5.0]), np.array([5.0]), np.array([1], dtype=np.int64))
+    n = ctypes.c_int64()
+    lib = capi.load()
+    assert lib.apb_vtk_particle_record(c._h, None, 0, ctypes.byref(n)) == capi.APB_OK and n.value > 800
+    small = np.zeros(100, dtype=np.uint8)
+    assert lib.apb_vtk_particle_record(c._h, small.ctypes.data_as(ctypes.c_void_p), 100, ctypes.byref(n)) == capi.ERR_INVALID_ARGUMENT
+    c.close()
+    s = GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [4, 4, 4], 1.0, 0.1, particleKind=capi.PARTICLE_SPH)
+    with pytest.raises(ApbError):
+        s.vtkParticleRecord()  # md-flexible's record is MoleculeLJ's
+    s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_vtk_record_full_size():
+    """1 M particles of a liquid box (positions incl. the band below the upper corner, velocities and forces over many
+    decades): the record equals the oracle's for the same columns in storage order, and reads back like md-flexible's
+    loader reads it (MDFlexConfig.cpp:122-165: counts, ids, values within the printed precision)."""
+    rng = np.random.default_rng(21)
+    n, L = 1_000_000, 100.0
+    ids = rng.permutation(n).astype(np.int64)
+    r = rng.uniform(0, L, (n, 3))
+    r[:5000, 0] = L - 10.0 ** -rng.uniform(1, 12, 5000)
+    c = GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [L, L, L], 2.5, 0.3)
+    c.addParticles(r[:, 0], r[:, 1], r[:, 2], ids, rng.integers(0, 3, n).astype(np.int32))
+    for k in ("VX", "VY", "VZ", "FX", "FY", "FZ"):
+        c.uploadColumn(k, rng.normal(size=n) * 10.0 ** rng.integers(-6, 7, n))
+    got = c.vtkParticleRecord()
+    sid, stype, _ = c.downloadIds()
+    col = lambda *names: np.stack([c.downloadColumn(k) for k in names], axis=1)  # noqa: E731
+    R, V, F = col("X", "Y", "Z"), col("VX", "VY", "VZ"), col("FX", "FY", "FZ")
+    want = oracle.vtk_particle_record(sid, R, V, F, stype, [L, L, L])
+    assert len(got) == len(want) and np.array_equal(got, want)
+    text = bytes(got).decode()
+    assert f'NumberOfPoints="{n}"' in text
+    payload = lambda name: text.split(f'Name="{name}"', 1)[1].split(">\n", 1)[1].split("</DataArray>", 1)[0]  # noqa: E731
+    assert np.array_equal(np.array(payload("ids").split(), dtype=np.int64), sid)
+    back = np.array(payload("positions").split(), dtype=np.float64).reshape(n, 3)
+    assert np.all(np.abs(back - R) <= 5.1e-6 * np.maximum(np.abs(R), 1e-300)) and np.all(back < L)  # no position rounds onto the border
+    vb = np.array(payload("velocities").split(), dtype=np.float64).reshape(n, 3)
+    assert np.all(np.abs(vb - V) <= 5.1e-6 * np.abs(V))
+    c.close()
