@@ -614,6 +614,12 @@ class GpuParticleContainer:
         self._check(self._lib.apb_vtk_particle_record(self._h, _ptr(buf), n.value, ctypes.byref(n)))
         return buf[: n.value]
 
+    def writeVtkParticleRecord(self, path):
+        """The same record written to `path` (device -> pinned pieces -> file); returns the number of bytes."""
+        n = ctypes.c_int64()
+        self._check(self._lib.apb_vtk_write_particle_record(self._h, str(path).encode(), ctypes.byref(n)))
+        return n.value
+
     def leaverColumn(self, name):
         """Any other attribute of the particles the last updateContainer returned (they are whole copies in the
         reference, LeavingParticleCollector.h:101-110), in the same order."""
@@ -819,5 +825,5 @@ class ParallelVtkWriter:
         if self._rank == 0:
             self.pvtuRecord(currentIteration).tofile(f"{self._sessionFolder}{self._session}_Particles_{it}.pvtu")
         path = f"{self._dataFolder}{self._session}_Particles_{self._rank}_{it}.vtu"
-        container.vtkParticleRecord().tofile(path)
+        container.writeVtkParticleRecord(path)
         return path

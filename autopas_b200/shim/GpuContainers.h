@@ -977,6 +977,14 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     return record;
   }
 
+  /// the same record into a file, as the reference writer leaves it (ParallelVtkWriter.cpp:61-70, 200); returns the bytes
+  size_t writeVtkParticleRecord(const std::string &path) {
+    syncToDevice();
+    int64_t bytes = 0;
+    check(apb_vtk_write_particle_record(_h, path.c_str(), &bytes));
+    return static_cast<size_t>(bytes);
+  }
+
   /// the C handle, for device-resident extensions (apb_run_steps, apb_exchange_halos, ...)
   [[nodiscard]] apb_handle handle() {
     syncToDevice();

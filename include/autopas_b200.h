@@ -228,6 +228,10 @@ int apb_deserialize_particles(apb_handle h, const void *src, int64_t num_records
  * reference throws (a position identical to the border up to 15 digits) the call fails with
  * APB_ERR_INVALID_ARGUMENT. Single-site particles only. md-flexible's loader (MDFlexConfig.cpp:91-180) reads the file. */
 int apb_vtk_particle_record(apb_handle h, void *dst, int64_t capacity_bytes, int64_t *out_bytes);
+/* The same record written to `path` like the reference does (ParallelVtkWriter.cpp:61-70, 200): device -> pinned host
+ * pieces -> fwrite, the copy of one piece overlapping the write of the previous one. A file that cannot be opened fails
+ * with the reference's message. */
+int apb_vtk_write_particle_record(apb_handle h, const char *path, int64_t *out_bytes);
 /* The "<session>_Particles_<iteration>.pvtu" index rank 0 writes next to the pieces (ParallelVtkWriter.cpp:308-356,
  * file names as generateFilename :437-441 builds them); host text, no handle. */
 int apb_vtk_pvtu_record(const char *session_name, int32_t num_ranks, uint64_t iteration, int32_t digits, char *dst,

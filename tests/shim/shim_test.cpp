@@ -6,7 +6,9 @@
 // LinkedCells, csf 1, lc_c08, AoS, newton3 (:210-214).
 #include <cmath>
 #include <cstdio>
+#include <fstream>
 #include <iomanip>
+#include <iterator>
 #include <sstream>
 #include <map>
 #include <random>
@@ -416,6 +418,13 @@ static void compareVtk(const Scenario &s) {
   const std::string got = gpu.vtkParticleRecord();
   CHECK(got == want.str(), "device-side VTK record differs from the reference writer's statements (%zu vs %zu bytes)", got.size(),
         want.str().size());
+  const std::string path = "/tmp/apb_shim_test_Particles_0_000001.vtu";
+  const size_t written = gpu.writeVtkParticleRecord(path);
+  std::ifstream back(path, std::ios::binary);
+  const std::string fileText((std::istreambuf_iterator<char>(back)), std::istreambuf_iterator<char>());
+  CHECK(written == got.size() && fileText == got, "the file written from the device differs from the record (%zu vs %zu bytes)",
+        fileText.size(), got.size());
+  std::remove(path.c_str());
   std::printf("vtk record: %zu particles, %zu bytes, %s\n", size_t(n), got.size(), got == want.str() ? "identical" : "DIFFERENT");
 }
 

@@ -20,6 +20,7 @@ def test_cpp_shim_matches_reference_through_autopas_interfaces():
     print(r.stderr)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "SHIM TEST PASSED" in r.stdout
+    assert "vtk record:" in r.stdout and "identical" in r.stdout  # device-side checkpoint == the reference writer's statements
 
 
 BIN_MS = os.path.join(ROOT, "oracle", "_ref", "shim_test_ms")

@@ -161,7 +161,10 @@ def test_gpu_vtk_record_is_byte_exact(container, tmp_path):
     # files through the writer mirror: names as the reference's loader expects them (MDFlexConfig.cpp:91-120)
     w = ParallelVtkWriter("sess", str(tmp_path), 6)
     path = w.recordParticleStates(42, c)
-    assert path.endswith("/sess/data/sess_Particles_0_000042.vtu") and os.path.getsize(path) == len(c.vtkParticleRecord())
+    assert path.endswith("/sess/data/sess_Particles_0_000042.vtu")
+    assert np.array_equal(np.fromfile(path, dtype=np.uint8), c.vtkParticleRecord())  # device -> pinned pieces -> file
+    with pytest.raises(ApbError, match="Failed to open file"):  # the reference's std::runtime_error (ParallelVtkWriter.cpp:68-70)
+        c.writeVtkParticleRecord(str(tmp_path / "no" / "such" / "folder" / "x.vtu"))
     assert np.array_equal(np.fromfile(str(tmp_path / "sess" / "sess_Particles_000042.pvtu"), dtype=np.uint8),
                           oracle.vtk_pvtu_record("sess", 1, 42, 6))
     c.close()
@@ -194,7 +197,7 @@ def test_gpu_vtk_record_error_paths_and_empty_container():
 
 
 @pytest.mark.gpu
-def test_gpu_vtk_record_full_size():
+def test_gpu_vtk_record_full_size(tmp_path):
     """1 M particles of a liquid box (positions incl. the band below the upper corner, velocities and forces over many
     decades): the record equals the oracle's for the same columns in storage order, and reads back like md-flexible's
     loader reads it (MDFlexConfig.cpp:122-165: counts, ids, values within the printed precision)."""
@@ -213,6 +216,8 @@ def test_gpu_vtk_record_full_size():
     R, V, F = col("X", "Y", "Z"), col("VX", "VY", "VZ"), col("FX", "FY", "FZ")
     want = oracle.vtk_particle_record(sid, R, V, F, stype, [L, L, L])
     assert len(got) == len(want) and np.array_equal(got, want)
+    path = str(tmp_path / "full.vtu")  # 128 MB: several 32 MB pieces through the two pinned buffers
+    assert c.writeVtkParticleRecord(path) == len(want) and np.array_equal(np.fromfile(path, dtype=np.uint8), want)
     text = bytes(got).decode()
     assert f'NumberOfPoints="{n}"' in text
     payload = lambda name: text.split(f'Name="{name}"', 1)[1].split(">\n", 1)[1].split("</DataArray>", 1)[0]  # noqa: E731
