@@ -9,8 +9,10 @@
 // device -> host copy (apb_vtk_particle_record) or through pinned buffers into a file (apb_vtk_write_particle_record). Rows follow the storage order (the order the container's iterators visit), like the reference's.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "internal.cuh"
 #include "vtk_format.cuh"
@@ -85,24 +87,24 @@ __global__ void __launch_bounds__(128) kVtkMeasure(int64_t n, int64_t m, const i
   len[section * m + rowOf[slot]] = l;
 }
 
-struct VtkBase {
-  long long at[kSections];  // byte offset of the first row of each data array in the record
-};
-
 // The rows of a warp's owned slots are consecutive in the record (row index and byte offset are exclusive scans over the
-// slots), so the warp formats them into shared memory at their relative offsets and stores the whole stretch (~1 KB) with
+// slots; a chunk of rows starts where the previous one ends), so the warp formats them into shared memory at their relative offsets and stores the whole stretch (~1 KB) with
 // aligned 16-byte stores; per-thread byte stores wrote 1.76 x the record's bytes to DRAM (partial sectors, ncu).
 __global__ void __launch_bounds__(128) kVtkWrite(int64_t n, int64_t m, const int *__restrict__ flag,
                                                  const int *__restrict__ rowOf, VtkCols c,
                                                  const ApbVtkTables *__restrict__ t, const int *__restrict__ off,
-                                                 VtkBase base, char *__restrict__ out) {
+                                                 const long long *__restrict__ base, int numChunks, int chunkRows,
+                                                 char *__restrict__ out) {
   __shared__ __align__(16) char stage[4][32 * kRowMax + 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t slot = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int section = static_cast<int>(blockIdx.y);
   const bool active = slot < n && flag[slot];
   long long myOff = 0;
-  if (active) myOff = base.at[section] + off[section * m + rowOf[slot]];
+  if (active) {  // byte offsets are 32-bit within a chunk of rows; base[] holds where each chunk of each data array starts
+    const int row = rowOf[slot];
+    myOff = base[section * numChunks + row / chunkRows] + off[section * m + row];
+  }
   const unsigned owners = __ballot_sync(0xffffffffu, active);
   if (owners == 0u) return;
   const long long warpOff = __shfl_sync(0xffffffffu, myOff, __ffs(owners) - 1);
@@ -168,16 +170,23 @@ std::string scaffold(int s, long long numParticles) {
 
 }  // namespace
 
+// Rows per scan: the byte offsets of a data array are 32-bit exclusive scans of the row lengths, so the rows are scanned
+// in chunks of 2^24 (at most 1.6 GB of text each) whose starting offsets are added up in 64 bits on the host.
+static long long vtkChunkRows() {
+  static const long long rows = [] {
+    const char *e = std::getenv("APB_VTK_CHUNK_ROWS");  // tests: exercise the chunked path on small containers
+    const long long v = e ? std::atoll(e) : 0;
+    return v > 0 ? v : (1ll << 24);
+  }();
+  return rows;
+}
+
 // Measures the record (measuring pass and scans) and, if it has at most `writeUpTo` bytes, formats it into h->vtkOut.
 static int vtkBuild(apb_handle h, long long writeUpTo, long long *totalOut) {
   if (h->cfg.particle_kind != APB_PARTICLE_LJ)
     return h->fail(APB_ERR_NOT_APPLICABLE, "the checkpoint record is the one of MoleculeLJ (md-flexible's single-site mode)");
   const int64_t n = h->nslots;
-  // control words: [0..4] bytes of the rows of each data array, [5] owned particles, then the error flag
-  APB_CHECK(apbEnsure(h, h->vtkCtl, 64));
-  long long *totals = static_cast<long long *>(h->vtkCtl.p);
-  int *bad = reinterpret_cast<int *>(totals + 6);
-  APB_CUDA(cudaMemsetAsync(h->vtkCtl.p, 0, 64, h->stream));
+  if (n > 0x7fffffffLL) return h->fail(APB_ERR_NOT_APPLICABLE, "apb_vtk_particle_record: more than 2^31 slots");
   if (!h->vtkTablesReady) {
     static const ApbVtkTables *hostTables = [] {
       auto *t = new ApbVtkTables;
@@ -191,16 +200,23 @@ static int vtkBuild(apb_handle h, long long writeUpTo, long long *totalOut) {
   long long m = 0;
   int *flag = nullptr, *rowOf = nullptr;
   if (n > 0) {
+    APB_CHECK(apbEnsure(h, h->vtkCtl, 64));
     APB_CHECK(apbEnsure(h, h->vtkFlag, sizeof(int) * n * 2));
     flag = static_cast<int *>(h->vtkFlag.p);
     rowOf = flag + n;
     ++h->launchCount, kVtkSelect<<<apbDivUp(n, 256), 256, 0, h->stream>>>(n, h->own, flag);
-    APB_CHECK(apbExclusiveScan(h, flag, rowOf, n, totals + 5));
-    APB_CUDA(cudaMemcpyAsync(&m, totals + 5, 8, cudaMemcpyDeviceToHost, h->stream));
+    APB_CHECK(apbExclusiveScan(h, flag, rowOf, n, static_cast<long long *>(h->vtkCtl.p)));
+    APB_CUDA(cudaMemcpyAsync(&m, h->vtkCtl.p, 8, cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaStreamSynchronize(h->stream));
   }
-  if (m * kRowMax > 0x7fffffffLL)
-    return h->fail(APB_ERR_NOT_APPLICABLE, "apb_vtk_particle_record: more than 2^31 bytes per data array (" + std::to_string(m) + " particles)");
+  const long long chunkRows = vtkChunkRows();
+  const long long numChunks = std::max(1ll, (m + chunkRows - 1) / chunkRows);
+  // control words: [0] error flag, then per (data array, chunk) the bytes of its rows, then where it starts in the record
+  APB_CHECK(apbEnsure(h, h->vtkCtl, 8 * static_cast<size_t>(1 + 2 * kSections * numChunks)));
+  long long *ctl = static_cast<long long *>(h->vtkCtl.p);
+  int *bad = reinterpret_cast<int *>(ctl);
+  long long *chunkBytes = ctl + 1, *chunkBase = chunkBytes + kSections * numChunks;
+  APB_CUDA(cudaMemsetAsync(ctl, 0, 8 * static_cast<size_t>(1 + 2 * kSections * numChunks), h->stream));
   VtkCols c;
   for (int d = 0; d < 3; ++d) {
     c.r[d] = h->col[APB_COL_X + d];
@@ -211,7 +227,7 @@ static int vtkBuild(apb_handle h, long long writeUpTo, long long *totalOut) {
   c.id = h->id;
   c.type = h->type;
   const ApbVtkTables *tables = static_cast<const ApbVtkTables *>(h->vtkTables.p);
-  long long sectionBytes[kSections] = {0, 0, 0, 0, 0};
+  std::vector<long long> bytesHost(static_cast<size_t>(kSections * numChunks), 0), baseHost(static_cast<size_t>(kSections * numChunks), 0);
   int *len = nullptr, *off = nullptr;
   if (m > 0) {
     APB_CHECK(apbEnsure(h, h->vtkLen, sizeof(int) * m * kSections * 2));
@@ -219,9 +235,13 @@ static int vtkBuild(apb_handle h, long long writeUpTo, long long *totalOut) {
     off = len + m * kSections;
     ++h->launchCount, kVtkMeasure<<<dim3(static_cast<unsigned>(apbDivUp(n, 128)), kSections), 128, 0, h->stream>>>(n, m, flag, rowOf, c, tables, len, bad);
     APB_CUDA(cudaGetLastError());
-    for (int s = 0; s < kSections; ++s) APB_CHECK(apbExclusiveScan(h, len + s * m, off + s * m, m, totals + s));
+    for (int s = 0; s < kSections; ++s)
+      for (long long k = 0; k < numChunks; ++k) {
+        const long long first = s * m + k * chunkRows;
+        APB_CHECK(apbExclusiveScan(h, len + first, off + first, std::min(chunkRows, m - k * chunkRows), chunkBytes + s * numChunks + k));
+      }
     int hostBad = 0;
-    APB_CUDA(cudaMemcpyAsync(sectionBytes, totals, 8 * kSections, cudaMemcpyDeviceToHost, h->stream));
+    APB_CUDA(cudaMemcpyAsync(bytesHost.data(), chunkBytes, 8 * bytesHost.size(), cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaMemcpyAsync(&hostBad, bad, 4, cudaMemcpyDeviceToHost, h->stream));
     APB_CUDA(cudaStreamSynchronize(h->stream));
     if (hostBad)  // the reference throws std::runtime_error here (ParallelVtkWriter.cpp:141-149)
@@ -229,29 +249,31 @@ static int vtkBuild(apb_handle h, long long writeUpTo, long long *totalOut) {
                      "ParallelVtkWriter::writeWithDynamicPrecision(): a position is identical to the box border up to 15 digits of precision");
   }
   std::string text[kSections + 1];
-  VtkBase base;
+  long long textAt[kSections + 1];
   long long total = 0;
   for (int s = 0; s <= kSections; ++s) {
     text[s] = scaffold(s, m);
+    textAt[s] = total;
     total += static_cast<long long>(text[s].size());
-    if (s < kSections) {
-      base.at[s] = total;
-      total += sectionBytes[s];
-    }
+    if (s < kSections)
+      for (long long k = 0; k < numChunks; ++k) {
+        baseHost[s * numChunks + k] = total;
+        total += bytesHost[s * numChunks + k];
+      }
   }
   *totalOut = total;
   if (total > writeUpTo) return APB_OK;
   APB_CHECK(apbEnsure(h, h->vtkOut, static_cast<size_t>(total)));
   char *out = static_cast<char *>(h->vtkOut.p);
-  long long at = 0;
-  for (int s = 0; s <= kSections; ++s) {
-    APB_CUDA(cudaMemcpyAsync(out + at, text[s].data(), text[s].size(), cudaMemcpyHostToDevice, h->stream));
-    at += static_cast<long long>(text[s].size()) + (s < kSections ? sectionBytes[s] : 0);
-  }
+  for (int s = 0; s <= kSections; ++s)
+    APB_CUDA(cudaMemcpyAsync(out + textAt[s], text[s].data(), text[s].size(), cudaMemcpyHostToDevice, h->stream));
   if (m > 0) {
-    ++h->launchCount, kVtkWrite<<<dim3(static_cast<unsigned>(apbDivUp(n, 128)), kSections), 128, 0, h->stream>>>(n, m, flag, rowOf, c, tables, off, base, out);
+    APB_CUDA(cudaMemcpyAsync(chunkBase, baseHost.data(), 8 * baseHost.size(), cudaMemcpyHostToDevice, h->stream));
+    ++h->launchCount, kVtkWrite<<<dim3(static_cast<unsigned>(apbDivUp(n, 128)), kSections), 128, 0, h->stream>>>(
+        n, m, flag, rowOf, c, tables, off, chunkBase, static_cast<int>(numChunks), static_cast<int>(std::min<long long>(chunkRows, 0x7fffffffLL)), out);
     APB_CUDA(cudaGetLastError());
   }
+  // (the host strings and vectors above are pageable: cudaMemcpyAsync has staged them before it returned)
   return APB_OK;
 }
 

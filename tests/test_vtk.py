@@ -6,11 +6,13 @@ GPU: apb_vtk_particle_record byte for byte against the oracle and the fixture, e
 import ctypes
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
 
-import oracle
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # (when run as the chunked child process)
+import oracle  # noqa: E402
 from autopas_b200 import ApbError, GpuParticleContainer, ParallelVtkWriter, capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -170,6 +172,44 @@ def test_gpu_vtk_record_is_byte_exact(container, tmp_path):
     c.close()
 
 
+def _chunked_record_equals_oracle():
+    """run in a child process with APB_VTK_CHUNK_ROWS set (the library reads it once)"""
+    g = _golden()
+    ids, r, v, f, types = g["ids"], g["r"], g["v"], g["f"], g["types"]
+    c = GpuParticleContainer("gpuLinkedCells", g["box_min"], g["box_max"], 1.0, 0.2)
+    order = _fill(c, ids, r, v, f, types)
+    want = oracle.vtk_particle_record(ids[order], r[order], v[order], f[order], types[order], g["box_max"])
+    assert np.array_equal(c.vtkParticleRecord(), want)
+    c.close()
+    rng = np.random.default_rng(4)
+    n, L = 50_000, 40.0
+    R = rng.uniform(0, L, (n, 3))
+    c = GpuParticleContainer("gpuVerletClusterLists", [0, 0, 0], [L, L, L], 2.5, 0.3, clusterSize=32)
+    c.addParticles(R[:, 0], R[:, 1], R[:, 2], np.arange(n, dtype=np.int64))
+    c.addHaloParticles(np.array([-1.0, L + 1.0]), np.array([1.0, 2.0]), np.array([1.0, 2.0]), np.array([n, n + 1], dtype=np.int64))
+    for k in ("VX", "VY", "VZ", "FX", "FY", "FZ"):
+        c.uploadColumn(k, rng.normal(size=c.numSlots()) * 10.0 ** rng.integers(-6, 7, c.numSlots()))
+    sid, stype, sown = c.downloadIds()
+    o = sown == 1
+    col = lambda *names: np.stack([c.downloadColumn(k) for k in names], axis=1)[o]  # noqa: E731
+    want = oracle.vtk_particle_record(sid[o], col("X", "Y", "Z"), col("VX", "VY", "VZ"), col("FX", "FY", "FZ"), stype[o], [L, L, L])
+    assert np.array_equal(c.vtkParticleRecord(), want)
+    c.close()
+    print("chunked record OK")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk_rows", [97, 4096])
+def test_gpu_vtk_record_in_chunks_of_rows(chunk_rows):
+    """Byte offsets are 32-bit within a chunk of rows (2^24 by default, so that a data array may exceed 2 GB): with small
+    chunks the fixture and a 50 000-particle container (several chunks per data array, chunk borders inside a warp's
+    stretch of rows) give the same bytes."""
+    env = dict(os.environ, APB_VTK_CHUNK_ROWS=str(chunk_rows))
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--chunked"], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(HERE))
+    assert r.returncode == 0 and "chunked record OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 @pytest.mark.gpu
 def test_gpu_vtk_record_error_paths_and_empty_container():
     box = [10.0, 10.0, 10.0]
@@ -227,3 +267,7 @@ def test_gpu_vtk_record_full_size(tmp_path):
     vb = np.array(payload("velocities").split(), dtype=np.float64).reshape(n, 3)
     assert np.all(np.abs(vb - V) <= 5.1e-6 * np.abs(V))
     c.close()
+
+
+if __name__ == "__main__" and "--chunked" in sys.argv:
+    _chunked_record_equals_oracle()
