@@ -6,7 +6,9 @@ This package is the Python host mirror used by tests and benchmarks; ``shim/`` h
 from . import capi
 from .capi import ApbError
 from .containers import (AxilrodTellerMutoFunctor, GpuParticleContainer, GpuTraversal, LJFunctor, LJMultisiteFunctor,
-                         ParallelVtkWriter, ParticlePropertiesLibrary, SPHCalcDensityFunctor, SPHCalcHydroForceFunctor)
+                         ParallelVtkWriter, ParticlePropertiesLibrary, SPHCalcDensityFunctor, SPHCalcHydroForceFunctor,
+                         checkpointPieces, loadParticlesFromCheckpoint)
 
 __all__ = ["capi", "ApbError", "GpuParticleContainer", "GpuTraversal", "LJFunctor", "ParticlePropertiesLibrary",
-           "SPHCalcDensityFunctor", "SPHCalcHydroForceFunctor", "AxilrodTellerMutoFunctor", "LJMultisiteFunctor", "ParallelVtkWriter"]
+           "SPHCalcDensityFunctor", "SPHCalcHydroForceFunctor", "AxilrodTellerMutoFunctor", "LJMultisiteFunctor",
+           "ParallelVtkWriter", "checkpointPieces", "loadParticlesFromCheckpoint"]

@@ -147,6 +147,7 @@ SIGNATURES = {
     "apb_deserialize_particles": (_i32, [_H, _vp, _i64]),
     "apb_vtk_particle_record": (_i32, [_H, _vp, _i64, _vp]),
     "apb_vtk_write_particle_record": (_i32, [_H, ctypes.c_char_p, _vp]),
+    "apb_vtk_load_particle_record": (_i32, [_H, _vp, _i64, _i32, _vp]),
     "apb_vtk_pvtu_record": (_i32, [ctypes.c_char_p, _i32, ctypes.c_uint64, _i32, _vp, _i64, _vp]),
     "apb_rebuild_neighbor_lists": (_i32, [_H, _i32, _i32]),
     "apb_get_geometry": (_i32, [_H, ctypes.POINTER(Geometry)]),

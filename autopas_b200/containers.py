@@ -620,6 +620,15 @@ class GpuParticleContainer:
         self._check(self._lib.apb_vtk_write_particle_record(self._h, str(path).encode(), ctypes.byref(n)))
         return n.value
 
+    def loadVtkParticleRecord(self, data, checkInBox=True):
+        """loadParticlesFromRankRecord (examples/md-flexible/src/configuration/MDFlexConfig.cpp:91-180) + addParticle: the
+        particles of a `.vtu` piece (uint8 array / bytes) appended as owned particles, parsed on the device; returns
+        their number."""
+        data = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, dtype=np.uint8)
+        n = ctypes.c_int64()
+        self._check(self._lib.apb_vtk_load_particle_record(self._h, _ptr(data), len(data), 1 if checkInBox else 0, ctypes.byref(n)))
+        return n.value
+
     def leaverColumn(self, name):
         """Any other attribute of the particles the last updateContainer returned (they are whole copies in the
         reference, LeavingParticleCollector.h:101-110), in the same order."""
@@ -827,3 +836,25 @@ class ParallelVtkWriter:
         path = f"{self._dataFolder}{self._session}_Particles_{self._rank}_{it}.vtu"
         container.writeVtkParticleRecord(path)
         return path
+
+
+def checkpointPieces(filename):
+    """The piece files a `.pvtu` checkpoint refers to, named as md-flexible's loader reconstructs them
+    (getNumPiecesInCheckpoint + loadParticlesFromRankRecord, MDFlexConfig.cpp:67-117): one per word "Piece" in the index,
+    `<folder>/data/<scenario>_<rank>_<iteration>.vtu` with scenario / iteration split at the last '_' of the file name."""
+    import os
+    import re
+    with open(filename) as f:
+        numPieces = len([w for w in re.split(r"[ /.,?!\"'<>=:;\n\t\r]", f.read()) if w == "Piece"])
+    folder, base = os.path.split(str(filename))
+    scenario, rest = base.rsplit("_", 1)
+    iteration = rest.rsplit(".", 1)[0]
+    return [os.path.join(folder, "data", f"{scenario}_{rank}_{iteration}.vtu") for rank in range(numPieces)]
+
+
+def loadParticlesFromCheckpoint(filename, rank, numRanks, container, checkInBox=True):
+    """MDFlexConfig::loadParticlesFromCheckpoint (MDFlexConfig.cpp:648-671) into a GPU container: with as many ranks as
+    pieces every rank loads its own piece, otherwise rank 0 loads all of them. Returns the number of particles added."""
+    pieces = checkpointPieces(filename)
+    mine = [pieces[rank]] if numRanks == len(pieces) else (pieces if rank == 0 else [])
+    return sum(container.loadVtkParticleRecord(np.fromfile(p, dtype=np.uint8), checkInBox) for p in mine)

@@ -371,3 +371,221 @@ extern "C" int apb_vtk_pvtu_record(const char *sessionName, int32_t numRanks, ui
   std::memcpy(dst, t.data(), t.size());
   return APB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Reading a piece back (loadParticlesFromRankRecord, examples/md-flexible/src/configuration/MDFlexConfig.cpp:91-180):
+// NumberOfPoints, then for "velocities", "forces", "typeIds", "ids", "positions" in this order: skip to the end of the
+// line that names the array and read NumberOfPoints x {3, 3, 1, 1, 3} whitespace-separated values with operator>>.
+// The text is copied to the device once; the host only looks at the XML tags (their positions come from a kernel that
+// lists every '<' - the payload has none). Per data array: threads count the tokens that start in their 128-byte
+// segment, a scan numbers them, and a second walk converts token t into component t % k of particle t / k with the
+// exact decimal -> binary conversion of vtk_format.cuh.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kSegment = 128;   // bytes of text per thread
+constexpr int kTokenMax = 72;   // longest token converted (40 digits, sign, point, exponent)
+constexpr int kTagCap = 256;    // '<' characters expected in a piece: 25
+
+__device__ __forceinline__ bool vtkIsSpace(char ch) {  // std::isspace in the "C" locale, what operator>> skips
+  return ch == ' ' || ch == '\n' || ch == '\t' || ch == '\r' || ch == '\v' || ch == '\f';
+}
+
+__global__ void kVtkFindTags(const char *__restrict__ text, long long numBytes, int *__restrict__ count,
+                             long long *__restrict__ where) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= numBytes || text[i] != '<') return;
+  const int k = atomicAdd(count, 1);
+  if (k < kTagCap) where[k] = i;
+}
+
+// tokens that START in segment g of the payload [begin, end)
+__global__ void kVtkCountTokens(const char *__restrict__ text, long long begin, long long end, int *__restrict__ count) {
+  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long a = begin + g * kSegment;
+  if (a >= end) return;
+  const long long b = min(a + kSegment, end);
+  bool prevSpace = a == begin ? true : vtkIsSpace(text[a - 1]);
+  int c = 0;
+  for (long long i = a; i < b; ++i) {
+    const bool sp = vtkIsSpace(text[i]);
+    c += prevSpace && !sp;
+    prevSpace = sp;
+  }
+  count[g] = c;
+}
+
+struct VtkLoadTarget {
+  double *d[3];      // columns receiving components 0 .. 2 (doubles), or
+  int64_t *id;       // ids (k == 1), or
+  int32_t *type;     // type ids (k == 1)
+  int k;             // values per particle
+  long long first;   // slot of particle 0
+  long long numParticles;
+};
+
+__global__ void kVtkParseTokens(const char *__restrict__ text, long long begin, long long end, const int *__restrict__ base,
+                                VtkLoadTarget t, int *__restrict__ bad) {
+  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long a = begin + g * kSegment;
+  if (a >= end) return;
+  const long long b = min(a + kSegment, end);
+  bool prevSpace = a == begin ? true : vtkIsSpace(text[a - 1]);
+  long long token = base[g];
+  for (long long i = a; i < b; ++i) {
+    const bool sp = vtkIsSpace(text[i]);
+    if (prevSpace && !sp) {
+      const long long particle = token / t.k;
+      const int comp = static_cast<int>(token % t.k);
+      ++token;
+      if (particle < t.numParticles) {  // the reference reads NumberOfPoints x k values and stops
+        char tok[kTokenMax];
+        int len = 0;
+        for (long long j = i; j < end && !vtkIsSpace(text[j]); ++j) {
+          if (len == kTokenMax) {
+            len = -1;
+            break;
+          }
+          tok[len++] = text[j];
+        }
+        int status = len < 0 ? 1 : 0;
+        if (!status) {
+          if (t.id) t.id[t.first + particle] = static_cast<int64_t>(apbParseU64(tok, len, status));
+          else if (t.type) t.type[t.first + particle] = static_cast<int32_t>(apbParseU64(tok, len, status));
+          else t.d[comp][t.first + particle] = apbParseDouble(tok, len, status);
+        }
+        if (status) atomicOr(bad, 1);
+      }
+    }
+    prevSpace = sp;
+  }
+}
+
+__global__ void kVtkFinishLoaded(long long first, long long n, const double *__restrict__ x, const double *__restrict__ y,
+                                 const double *__restrict__ z, int32_t *__restrict__ own, double lox, double loy, double loz,
+                                 double hix, double hiy, double hiz, int checkBox, int *__restrict__ bad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  own[first + i] = APB_OWN_OWNED;
+  if (checkBox) {  // utils::inBox is half-open [lo, hi) (utils/inBox.h:26-36)
+    const double px = x[first + i], py = y[first + i], pz = z[first + i];
+    if (!(px >= lox && px < hix && py >= loy && py < hiy && pz >= loz && pz < hiz)) atomicOr(bad, 2);
+  }
+}
+
+// position just behind the first `word` at or after `from` in [text, text + n); -1 if absent
+long long findBehind(const char *text, long long n, long long from, const std::string &word) {
+  if (from < 0 || from >= n) return -1;
+  const void *p = memmem(text + from, static_cast<size_t>(n - from), word.data(), word.size());
+  return p ? static_cast<const char *>(p) - text + static_cast<long long>(word.size()) : -1;
+}
+
+}  // namespace
+
+extern "C" int apb_vtk_load_particle_record(apb_handle h, const void *src, int64_t numBytes, int32_t checkBox, int64_t *outNum) {
+  APB_ENTRY(h);
+  if (outNum) *outNum = 0;
+  if (!src || numBytes <= 0) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_vtk_load_particle_record: empty record");
+  if (h->cfg.particle_kind != APB_PARTICLE_LJ)
+    return h->fail(APB_ERR_NOT_APPLICABLE, "the checkpoint record is the one of MoleculeLJ (md-flexible's single-site mode)");
+  const char *host = static_cast<const char *>(src);
+  // the text on the device, and where its tags are
+  APB_CHECK(apbEnsure(h, h->vtkOut, static_cast<size_t>(numBytes)));
+  APB_CHECK(apbEnsure(h, h->vtkCtl, 64 + 8 * kTagCap));
+  char *text = static_cast<char *>(h->vtkOut.p);
+  int *ctl = static_cast<int *>(h->vtkCtl.p);  // [0] number of '<', [1] error flags; positions from byte 64 on
+  long long *whereDev = reinterpret_cast<long long *>(static_cast<char *>(h->vtkCtl.p) + 64);
+  APB_CUDA(cudaMemsetAsync(ctl, 0, 64, h->stream));
+  APB_CUDA(cudaMemcpyAsync(text, host, static_cast<size_t>(numBytes), cudaMemcpyHostToDevice, h->stream));
+  ++h->launchCount, kVtkFindTags<<<apbDivUp(numBytes, 256), 256, 0, h->stream>>>(text, numBytes, ctl, whereDev);
+  APB_CUDA(cudaGetLastError());
+  int numTags = 0;
+  APB_CUDA(cudaMemcpyAsync(&numTags, ctl, 4, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  if (numTags <= 0 || numTags > kTagCap) return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_vtk_load_particle_record: not a .vtu piece of md-flexible");
+  std::vector<long long> tags(static_cast<size_t>(numTags));
+  APB_CUDA(cudaMemcpyAsync(tags.data(), whereDev, 8 * tags.size(), cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  std::sort(tags.begin(), tags.end());
+  // NumberOfPoints="N" (MDFlexConfig.cpp:121-130); the words are looked for where the tags are, not in the payload
+  const long long headEnd = std::min<long long>(numBytes, 4096);
+  long long at = findBehind(host, headEnd, 0, "NumberOfPoints");
+  if (at >= 0) at = findBehind(host, headEnd, at, "\"");
+  long long numParticles = 0;
+  for (; at >= 0 && at < headEnd && host[at] >= '0' && host[at] <= '9'; ++at) numParticles = numParticles * 10 + (host[at] - '0');
+  if (numParticles <= 0)
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "Could not determine the number of particles in the checkpoint file");
+  if (h->nslots + numParticles > 0x7fffffffLL) return h->fail(APB_ERR_NOT_APPLICABLE, "apb_vtk_load_particle_record: more than 2^31 slots");
+  // payload of every data array: from behind the line that names it to the next tag
+  const char *names[kSections] = {"velocities", "forces", "typeIds", "ids", "positions"};
+  long long payloadBegin[kSections], payloadEnd[kSections];
+  size_t tagIndex = 0;
+  for (int s = 0; s < kSections; ++s) {
+    long long found = -1;
+    for (; tagIndex < tags.size() && found < 0; ++tagIndex) {
+      const long long tagEnd = tagIndex + 1 < tags.size() ? tags[tagIndex + 1] : numBytes;
+      const long long limit = std::min(tagEnd, tags[tagIndex] + 256);
+      const long long behind = findBehind(host, limit, tags[tagIndex], std::string("\"") + names[s] + "\"");
+      if (behind >= 0) found = findBehind(host, tagEnd, behind, "\n");
+    }
+    if (found < 0 || tagIndex >= tags.size())
+      return h->fail(APB_ERR_INVALID_ARGUMENT, std::string("apb_vtk_load_particle_record: data array \"") + names[s] + "\" not found");
+    payloadBegin[s] = found;
+    payloadEnd[s] = tags[tagIndex];  // the closing </DataArray>
+    if (payloadEnd[s] - payloadBegin[s] > 0x7fffffffLL)  // (token numbers are 32-bit scans)
+      return h->fail(APB_ERR_NOT_APPLICABLE, "apb_vtk_load_particle_record: a data array of more than 2^31 bytes");
+  }
+  // append the particles
+  h->ownedKnown = false;
+  h->ownedInsideBox = false;
+  const int64_t first = h->nslots;
+  APB_CHECK(apbReserveSlots(h, first + numParticles));
+  for (int c = APB_COL_X; c < APB_NUM_COLUMNS; ++c)
+    if (h->active[c]) APB_CUDA(cudaMemsetAsync(h->col[c] + first, 0, sizeof(double) * numParticles, h->stream));
+  APB_CUDA(cudaMemsetAsync(h->id + first, 0, sizeof(int64_t) * numParticles, h->stream));
+  APB_CUDA(cudaMemsetAsync(h->type + first, 0, sizeof(int32_t) * numParticles, h->stream));
+  int *bad = ctl + 1;
+  long long *tokenTotal = reinterpret_cast<long long *>(ctl + 2);
+  long long tokensHost[kSections] = {0, 0, 0, 0, 0};
+  for (int s = 0; s < kSections; ++s) {
+    const long long bytes = payloadEnd[s] - payloadBegin[s];
+    const long long segments = (bytes + kSegment - 1) / kSegment;
+    if (segments <= 0) continue;
+    APB_CHECK(apbEnsure(h, h->vtkLen, sizeof(int) * segments * 2));
+    int *count = static_cast<int *>(h->vtkLen.p), *base = count + segments;
+    ++h->launchCount, kVtkCountTokens<<<apbDivUp(segments, 128), 128, 0, h->stream>>>(text, payloadBegin[s], payloadEnd[s], count);
+    APB_CUDA(cudaGetLastError());
+    APB_CHECK(apbExclusiveScan(h, count, base, segments, tokenTotal));
+    APB_CUDA(cudaMemcpyAsync(&tokensHost[s], tokenTotal, 8, cudaMemcpyDeviceToHost, h->stream));
+    VtkLoadTarget t{};
+    t.k = (s == 2 || s == 3) ? 1 : 3;
+    t.first = first;
+    t.numParticles = numParticles;
+    const int colBase = s == 0 ? APB_COL_VX : s == 1 ? APB_COL_FX : APB_COL_X;
+    for (int d = 0; d < 3; ++d) t.d[d] = h->col[colBase + d];
+    t.id = s == 3 ? h->id : nullptr;
+    t.type = s == 2 ? h->type : nullptr;
+    ++h->launchCount, kVtkParseTokens<<<apbDivUp(segments, 128), 128, 0, h->stream>>>(text, payloadBegin[s], payloadEnd[s], base, t, bad);
+    APB_CUDA(cudaGetLastError());
+  }
+  ++h->launchCount, kVtkFinishLoaded<<<apbDivUp(numParticles, 256), 256, 0, h->stream>>>(
+      first, numParticles, h->col[APB_COL_X], h->col[APB_COL_Y], h->col[APB_COL_Z], h->own, h->cfg.box_min[0], h->cfg.box_min[1],
+      h->cfg.box_min[2], h->cfg.box_max[0], h->cfg.box_max[1], h->cfg.box_max[2], checkBox, bad);
+  APB_CUDA(cudaGetLastError());
+  int hostBad = 0;
+  APB_CUDA(cudaMemcpyAsync(&hostBad, bad, 4, cudaMemcpyDeviceToHost, h->stream));
+  APB_CUDA(cudaStreamSynchronize(h->stream));
+  for (int s = 0; s < kSections; ++s)
+    if (tokensHost[s] < numParticles * ((s == 2 || s == 3) ? 1 : 3))
+      return h->fail(APB_ERR_INVALID_ARGUMENT, std::string("apb_vtk_load_particle_record: data array \"") + names[s] + "\" holds fewer values than NumberOfPoints asks for");
+  if (hostBad & 1)
+    return h->fail(APB_ERR_INVALID_ARGUMENT, "apb_vtk_load_particle_record: a value is not a decimal number (the reference's stream extraction fails on it)");
+  if (hostBad & 2) return h->fail(APB_ERR_PARTICLE_OUTSIDE, "apb_vtk_load_particle_record: a particle of the checkpoint is outside the container box");
+  h->nslots = first + numParticles;
+  h->structureValid = false;
+  h->prunedValid = false;
+  h->countsValid = false;
+  apbForgetHaloLinks(h);
+  if (outNum) *outNum = numParticles;
+  return APB_OK;
+}

@@ -4,7 +4,8 @@
 //
 // "%.{P}g" needs the first P significant decimal digits of the binary value, correctly rounded (glibc rounds the exact
 // value, ties to even). A double is m * 2^e with a 53-bit m, so the scaled value m * 2^e * 10^k, k = P - 1 - floor(log10 v),
-// is computed exactly in a small multi-word integer (at most 37 words of 32 bits for the whole double range): powers of
+// is computed exactly in a small multi-word integer (at most 37 words of 32 bits for the whole double range; the
+// reading direction below needs up to 46): powers of
 // ten enter by multiplications / divisions with 10^9, powers of two by shifts, and what falls off the low end decides
 // the rounding (above / exactly / below one half). No floating-point arithmetic is involved, so host and device agree
 // by construction; tests/test_vtk.py compiles this header for the host and compares it with printf over tens of
@@ -20,7 +21,7 @@
 #define APB_HD static inline
 #endif
 
-#define APB_VTK_BIG_WORDS 40
+#define APB_VTK_BIG_WORDS 48
 
 struct ApbBig {
   uint32_t w[APB_VTK_BIG_WORDS];  // little endian
@@ -326,6 +327,150 @@ APB_HD int apbVtkPositionPrecision(const ApbVtkTables &t, double position, doubl
     }
   }
   return precision;
+}
+
+// ---- the reading direction: decimal text -> double, as `stream >> value` (strtod) converts it -------------------------
+// md-flexible's loader reads the checkpoint with operator>> (MDFlexConfig.cpp:31-46 readPayload), i.e. the correctly
+// rounded double of the decimal string. value = D * 10^E with the digits D collected exactly (up to 40 significant
+// digits); E >= 0: the product is an integer; E < 0: floor(D 2^s / 10^-E) with s chosen so that the quotient keeps more
+// than 64 bits, remainders of the divisions are sticky. The top 53 bits (fewer for subnormal results) are rounded to
+// nearest / even on what lies below. status: 0 fine, 1 not a decimal number this function supports (inf / nan / hex,
+// more than 40 significant digits, stray characters).
+APB_HD void apbBigAddSmall(ApbBig &b, uint32_t c) {
+  uint64_t carry = c;
+  for (int i = 0; i < b.n && carry; ++i) {
+    const uint64_t t = static_cast<uint64_t>(b.w[i]) + carry;
+    b.w[i] = static_cast<uint32_t>(t);
+    carry = t >> 32;
+  }
+  if (carry) b.w[b.n++] = static_cast<uint32_t>(carry);
+}
+APB_HD int apbBigBitLength(const ApbBig &b) {
+  const uint32_t top = b.w[b.n - 1];
+  if (top == 0) return 0;  // (only the value zero has a zero top word)
+  return 32 * (b.n - 1) + 64 - apbCountLeadingZeros64(static_cast<uint64_t>(top));
+}
+APB_HD double apbBitsToDouble(uint64_t bits) {
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(static_cast<long long>(bits));
+#else
+  double v;
+  __builtin_memcpy(&v, &bits, 8);
+  return v;
+#endif
+}
+
+APB_HD double apbParseDouble(const char *s, int len, int &status) {
+  status = 0;
+  int i = 0;
+  uint64_t sign = 0;
+  if (i < len && (s[i] == '+' || s[i] == '-')) {
+    if (s[i] == '-') sign = 1ull << 63;
+    ++i;
+  }
+  ApbBig big;
+  apbBigSet(big, 0);
+  int nd = 0;          // significant digits collected
+  long long E = 0;     // decimal exponent of the collected integer
+  bool any = false, seenPoint = false;
+  for (; i < len; ++i) {
+    const char ch = s[i];
+    if (ch >= '0' && ch <= '9') {
+      any = true;
+      if (seenPoint) --E;
+      if (nd == 0 && ch == '0') continue;  // leading zeros
+      if (nd >= 40) {
+        status = 1;
+        return 0.;
+      }
+      apbBigMulSmall(big, 10u);
+      apbBigAddSmall(big, static_cast<uint32_t>(ch - '0'));
+      ++nd;
+    } else if (ch == '.' && !seenPoint) {
+      seenPoint = true;
+    } else {
+      break;
+    }
+  }
+  if (!any) {
+    status = 1;
+    return 0.;
+  }
+  if (i < len && (s[i] == 'e' || s[i] == 'E')) {
+    ++i;
+    bool negExp = false;
+    if (i < len && (s[i] == '+' || s[i] == '-')) {
+      negExp = s[i] == '-';
+      ++i;
+    }
+    long long ex = 0;
+    bool anyExp = false;
+    for (; i < len && s[i] >= '0' && s[i] <= '9'; ++i) {
+      anyExp = true;
+      if (ex < 100000) ex = ex * 10 + (s[i] - '0');
+    }
+    if (!anyExp) {
+      status = 1;
+      return 0.;
+    }
+    E += negExp ? -ex : ex;
+  }
+  if (i != len) {
+    status = 1;
+    return 0.;
+  }
+  if (nd == 0) return apbBitsToDouble(sign);  // +-0
+  // 10^(nd - 1 + E) <= value < 10^(nd + E)
+  if (nd - 1 + E >= 309) return apbBitsToDouble(sign | 0x7ff0000000000000ull);
+  if (nd + E < -324) return apbBitsToDouble(sign);  // below half of the smallest subnormal (2.47e-324)
+  int s2 = 0;
+  bool sticky = false;
+  if (E >= 0) {
+    long long kk = E;
+    for (; kk >= 9; kk -= 9) apbBigMulSmall(big, 1000000000u);
+    if (kk) apbBigMulSmall(big, static_cast<uint32_t>(apbPow10u64(static_cast<int>(kk))));
+  } else {
+    long long k = -E;
+    s2 = 66 + static_cast<int>((k * 3402) >> 10) + 1 - apbBigBitLength(big);  // 3402 / 1024 > log2(10)
+    if (s2 < 0) s2 = 0;
+    apbBigShl(big, s2);
+    for (; k > 9; k -= 9) sticky |= apbBigDivSmall(big, 1000000000u) != 0;
+    sticky |= apbBigDivSmall(big, static_cast<uint32_t>(apbPow10u64(static_cast<int>(k)))) != 0;
+  }
+  const int nb = apbBigBitLength(big);
+  int e2 = nb - 1 - s2;  // value in [2^e2, 2^(e2 + 1))
+  if (e2 > 1023) return apbBitsToDouble(sign | 0x7ff0000000000000ull);
+  int keep = 53;
+  if (e2 < -1022) keep = 53 - (-1022 - e2);
+  if (keep < 0) return apbBitsToDouble(sign);
+  const int shift = nb - keep;
+  uint64_t mant;
+  if (shift <= 0) {
+    mant = apbBigShr64(big, 0) << (-shift);  // exact (nb < 53 happens only for integers)
+  } else {
+    mant = keep ? apbBigShr64(big, shift) : 0ull;
+    if (keep < 64 && keep > 0) mant &= (1ull << keep) - 1ull;  // (apbBigShr64 returns 64 bits)
+    const bool rbit = apbBigBit(big, shift - 1) != 0;
+    const bool below = sticky || apbBigAnyBelow(big, shift - 1);
+    if (rbit && (below || (mant & 1ull))) ++mant;
+  }
+  if (keep < 53) return apbBitsToDouble(sign | mant);  // subnormal (a carry into bit 52 is the smallest normal)
+  if (mant == (1ull << 53)) {
+    mant >>= 1;
+    if (++e2 > 1023) return apbBitsToDouble(sign | 0x7ff0000000000000ull);
+  }
+  return apbBitsToDouble(sign | (static_cast<uint64_t>(e2 + 1023) << 52) | (mant & ((1ull << 52) - 1ull)));
+}
+
+// decimal digits -> unsigned long (`stream >> size_t`); status 1: not a number of at most 19 digits
+APB_HD uint64_t apbParseU64(const char *s, int len, int &status) {
+  status = (len <= 0 || len > 19) ? 1 : 0;
+  uint64_t v = 0;
+  for (int i = 0; i < len && !status; ++i) {
+    if (s[i] < '0' || s[i] > '9') status = 1;
+    v = v * 10u + static_cast<uint64_t>(s[i] - '0');
+  }
+  return v;
 }
 
 // Host side: the two tables from this process's libm (the one the reference's writer would call on this machine).

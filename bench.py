@@ -612,6 +612,11 @@ def main():
                     other_configs_cpu_reference(line["other_configs"], bench_functors)
             except Exception as exc:  # never lose the headline line over the side measurements
                 line["other_configs"] = {"error": repr(exc)}
+            try:  # md-flexible's checkpoint of a 4 M-particle box written from the device SoA
+                import bench_vtk
+                line["checkpoint"] = bench_vtk.record_timing(4_000_000)
+            except Exception as exc:
+                line["checkpoint"] = {"error": repr(exc)}
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()

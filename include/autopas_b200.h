@@ -236,6 +236,14 @@ int apb_vtk_write_particle_record(apb_handle h, const char *path, int64_t *out_b
  * file names as generateFilename :437-441 builds them); host text, no handle. */
 int apb_vtk_pvtu_record(const char *session_name, int32_t num_ranks, uint64_t iteration, int32_t digits, char *dst,
                         int64_t capacity_bytes, int64_t *out_bytes);
+/* The way back: md-flexible's checkpoint loader for one piece (loadParticlesFromRankRecord,
+ * examples/md-flexible/src/configuration/MDFlexConfig.cpp:91-180). `src` (host) holds the bytes of a ".vtu" piece;
+ * NumberOfPoints particles are appended as owned particles with velocities, forces, typeIds, ids and positions converted
+ * on the device exactly like `stream >> value` converts them (correctly rounded), oldForce = 0. check_box != 0: a particle
+ * outside [box_min, box_max) fails with APB_ERR_PARTICLE_OUTSIDE (AutoPas::addParticle throws there) and nothing is
+ * added. A value that is not a decimal number ("inf", "nan": the reference's extraction fails on them too) or a missing
+ * data array fails with APB_ERR_INVALID_ARGUMENT. Single-site particles only. */
+int apb_vtk_load_particle_record(apb_handle h, const void *src, int64_t num_bytes, int32_t check_box, int64_t *out_num);
 
 /* ---- container maintenance ------------------------------------------------------------------------------------- */
 /* ParticleContainerInterface::updateContainer(bool keepNeighborListsValid) (:297);

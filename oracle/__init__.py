@@ -586,6 +586,46 @@ def ref_vtk_records(ids, r, v, f, types, box_min, box_max, session="ref", iterat
     return piece, index
 
 
+def vtk_load_particle_record(piece):
+    """Restatement of md-flexible's checkpoint loader for one piece (loadParticlesFromRankRecord,
+    examples/md-flexible/src/configuration/MDFlexConfig.cpp:91-180): NumberOfPoints, then for velocities, forces, typeIds,
+    ids, positions: go behind the word (findWord :54-65), skip the rest of that line, read NumberOfPoints x {3, 3, 1, 1, 3}
+    whitespace-separated values with operator>> (= strtod / strtoul: float() and int() round the same way).
+    Returns dict(ids, r, v, f, types). Pinned by particles of the unmodified loader: tests/golden/fn_vtk_load.npz, live."""
+    text = bytes(piece).decode()
+    at = text.index("NumberOfPoints")
+    at = text.index('"', at) + 1
+    n = int(text[at:text.index('"', at)])
+    if n == 0:
+        raise ValueError("Could not determine the number of particles in the checkpoint file")
+    out = {}
+    for word, key, k, conv in (("velocities", "v", 3, float), ("forces", "f", 3, float), ("typeIds", "types", 1, int),
+                               ("ids", "ids", 1, int), ("positions", "r", 3, float)):
+        at = text.index('"' + word + '"', at)  # (findWord compares whole words between separators; '"' is one)
+        at = text.index("\n", at) + 1
+        end = text.index("<", at)
+        tokens = text[at:end].split()[: n * k]
+        if len(tokens) < n * k:
+            raise ValueError(f"data array {word} holds fewer values than NumberOfPoints asks for")
+        a = np.array([conv(t) for t in tokens], dtype=np.float64 if conv is float else np.int64)
+        out[key] = a.reshape(n, 3) if k == 3 else a
+    return out
+
+
+def ref_vtk_load(pvtu_path, rank=0, num_ranks=1):
+    """The unmodified loader (MDFlexConfig::loadParticlesFromCheckpoint through oracle/_ref/vtk_ref_writer --load) on a
+    checkpoint on disk -> dict(ids, r, v, f, types) in the order it produced the particles."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "particles.bin")
+        subprocess.run([_REF_VTK, "--load", str(pvtu_path), str(rank), str(num_ranks), out], check=True, stdout=subprocess.DEVNULL)
+        raw = np.fromfile(out, dtype=np.uint8)
+    n = int(raw[:8].view(np.int64)[0])
+    rec = raw[8:].view(np.dtype([("r", "<f8", 3), ("v", "<f8", 3), ("f", "<f8", 3), ("id", "<i8"), ("type", "<i8")]))
+    assert len(rec) == n
+    return {"ids": rec["id"].copy(), "r": rec["r"].copy(), "v": rec["v"].copy(), "f": rec["f"].copy(), "types": rec["type"].copy()}
+
+
 def vtk_parse_ids(piece):
     """The `ids` DataArray of a .vtu piece as the checkpoint loader reads it (MDFlexConfig.cpp:158-160)."""
     text = bytes(piece).decode()

@@ -6,6 +6,12 @@
 // restatement (oracle/vtk_oracle.c) and, through it, apb_vtk_particle_record.
 //
 //   vtk_ref_writer <input.bin> <output folder> <session name> <iteration> <digits>
+//   vtk_ref_writer --load <checkpoint.pvtu> <rank> <number of ranks> <output.bin>
+//
+// The second form runs the UNMODIFIED checkpoint loader, MDFlexConfig::loadParticlesFromCheckpoint
+// (examples/md-flexible/src/configuration/MDFlexConfig.cpp:91-180, 648-671, compiled where it lies; yaml-cpp's headers
+// come from the reference's own libs/ archive, its parser objects are never linked because nothing here parses YAML) on
+// a default-constructed configuration and dumps the particles it produced: int64 n, then n records as below.
 //
 // input.bin: int64 n, double boxMin[3], boxMax[3], then n records of {double r[3], v[3], f[3]; int64 id, type}.
 // ParallelVtkWriter::recordParticleStates is private (the public recordTimestep also wants a RegularGridDecomposition,
@@ -25,6 +31,7 @@
 #include "autopas/AutoPasImpl.h"
 #include "autopas/tuning/Configuration.h"
 #include "src/TypeDefinitions.h"
+#include "src/configuration/MDFlexConfig.h"
 #include "src/domainDecomposition/RegularGridDecomposition.h"
 // everything ParallelVtkWriter.h includes has been seen (and is guarded): the macro only reaches the writer's class
 #define private public
@@ -33,7 +40,32 @@
 
 template class autopas::AutoPas<ParticleType>;
 
+struct OutRec {
+  double r[3], v[3], f[3];
+  int64_t id, type;
+};
+
+static int loadMode(int argc, char **argv) {
+  if (argc < 6) return 2;
+  MDFlexConfig config;
+  config.checkpointfile.value = argv[2];
+  config.loadParticlesFromCheckpoint(static_cast<size_t>(std::atoll(argv[3])), static_cast<size_t>(std::atoll(argv[4])));
+  std::FILE *out = std::fopen(argv[5], "wb");
+  if (!out) return 3;
+  const int64_t n = static_cast<int64_t>(config.particles.size());
+  std::fwrite(&n, 8, 1, out);
+  for (const auto &p : config.particles) {
+    OutRec q{{p.getR()[0], p.getR()[1], p.getR()[2]}, {p.getV()[0], p.getV()[1], p.getV()[2]}, {p.getF()[0], p.getF()[1], p.getF()[2]},
+             static_cast<int64_t>(p.getID()), static_cast<int64_t>(p.getTypeId())};
+    std::fwrite(&q, sizeof q, 1, out);
+  }
+  std::fclose(out);
+  std::printf("%lld\n", static_cast<long long>(n));
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc > 1 && std::string(argv[1]) == "--load") return loadMode(argc, argv);
   if (argc < 6) {
     std::fprintf(stderr, "usage: %s input.bin folder session iteration digits\n", argv[0]);
     return 2;

@@ -57,3 +57,19 @@ if __name__ == "__main__":
                         box_min=BOX_MIN, box_max=BOX_MAX, ref_piece=piece, ref_pvtu=index, session=np.array("fixture"),
                         iteration=np.int64(42), digits=np.int64(6))
     print("fn_vtk.npz:", len(piece), "bytes in the piece,", len(index), "in the index")
+    # The loader's fixture: the same particles without the inf / nan row (the reference's own loader cannot read those
+    # back: operator>> fails on them), written by the reference writer and read by the unmodified reference loader.
+    import tempfile
+    f2 = f.copy()
+    f2[0] = [1.5e300, -2.5e-300, 4.9e-324]
+    piece2, index2 = oracle.ref_vtk_records(ids, r, v, f2, types, BOX_MIN, BOX_MAX, "fixture", 42, 6)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "fixture", "data"))
+        piece2.tofile(os.path.join(d, "fixture", "data", "fixture_Particles_0_000042.vtu"))
+        index2.tofile(os.path.join(d, "fixture", "fixture_Particles_000042.pvtu"))
+        back = oracle.ref_vtk_load(os.path.join(d, "fixture", "fixture_Particles_000042.pvtu"))
+    assert np.array_equal(back["ids"], oracle.vtk_parse_ids(piece2))
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fn_vtk_load.npz"), piece=piece2, pvtu=index2,
+                        box_min=BOX_MIN, box_max=BOX_MAX, ref_ids=back["ids"], ref_r=back["r"], ref_v=back["v"], ref_f=back["f"],
+                        ref_types=back["types"])
+    print("fn_vtk_load.npz:", len(piece2), "bytes,", len(back["ids"]), "particles from the reference loader")

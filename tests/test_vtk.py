@@ -112,6 +112,73 @@ def test_position_precision_equals_oracle(host_formatter):
     assert seen == {-1, *range(6, 16)}
 
 
+GOLDEN_LOAD = os.path.join(HERE, "golden", "fn_vtk_load.npz")
+
+
+def _same_bits(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def test_oracle_vtk_loader_matches_reference_particles():
+    """oracle.vtk_load_particle_record == the particles the UNMODIFIED loader (MDFlexConfig::loadParticlesFromCheckpoint)
+    made of a piece written by the unmodified writer: bit patterns of every value (denormals, 1e300, raised precision)."""
+    g = np.load(GOLDEN_LOAD)
+    o = oracle.vtk_load_particle_record(g["piece"])
+    for mine, ref in (("ids", "ref_ids"), ("types", "ref_types"), ("r", "ref_r"), ("v", "ref_v"), ("f", "ref_f")):
+        assert _same_bits(o[mine], g[ref]), mine
+    assert 2 ** 40 + 5 in o["ids"] and np.any(np.abs(o["v"]) < 1e-308) and np.any(np.abs(o["v"]) > 1e299)
+
+
+@pytest.mark.skipif(not oracle.have_ref_vtk(), reason="oracle/_ref/vtk_ref_writer not built (reference tree absent)")
+def test_oracle_vtk_loader_matches_reference_live(tmp_path):
+    """a checkpoint of two pieces: piece names, piece count and particles as the unmodified loader sees them"""
+    rng = np.random.default_rng(12)
+    pieces = []
+    os.makedirs(tmp_path / "run" / "data")
+    for rank in range(2):
+        n = 400 + 100 * rank
+        ids = (rng.permutation(5 * n)[:n] + 10_000 * rank).astype(np.int64)
+        lo, hi = np.array([10.0 * rank, 0.0, 0.0]), np.array([10.0 * rank + 10.0, 8.0, 12.0])
+        r = lo + rng.uniform(0, 1, (n, 3)) * (hi - lo)
+        r[:30, 0] = hi[0] - 10.0 ** -rng.uniform(1, 12, 30)
+        v = rng.normal(size=(n, 3)) * 10.0 ** rng.integers(-12, 12, (n, 3))
+        f = rng.normal(size=(n, 3)) * 10.0 ** rng.integers(-6, 15, (n, 3))
+        piece, _ = oracle.ref_vtk_records(ids, r, v, f, rng.integers(0, 3, n), lo, hi, "run", 1200, 5)
+        piece.tofile(str(tmp_path / "run" / "data" / f"run_Particles_{rank}_01200.vtu"))
+        pieces.append(piece)
+    index = tmp_path / "run" / "run_Particles_01200.pvtu"
+    oracle.vtk_pvtu_record("run", 2, 1200, 5).tofile(str(index))
+    from autopas_b200 import checkpointPieces
+    assert checkpointPieces(str(index)) == [str(tmp_path / "run" / "data" / f"run_Particles_{k}_01200.vtu") for k in range(2)]
+    for rank in range(2):  # as many ranks as pieces: every rank reads its own
+        ref = oracle.ref_vtk_load(index, rank, 2)
+        mine = oracle.vtk_load_particle_record(pieces[rank])
+        assert all(_same_bits(mine[k], ref[k]) for k in ("ids", "types", "r", "v", "f"))
+    ref = oracle.ref_vtk_load(index, 0, 1)  # one rank, two pieces: rank 0 reads both
+    both = [oracle.vtk_load_particle_record(p) for p in pieces]
+    assert all(_same_bits(np.concatenate([b[k] for b in both]), ref[k]) for k in ("ids", "types", "r", "v", "f"))
+
+
+def test_parser_equals_strtod(host_formatter):
+    """apbParseDouble (the loader's decimal -> binary conversion) against the C library on printed doubles of every
+    precision, random digit strings up to 40 digits with exponents over the whole range, exact ties and the borders of
+    the subnormal / overflow ranges; malformed tokens are reported."""
+    host_formatter.check_parse.restype = ctypes.c_int64
+    host_formatter.parse_double.restype = ctypes.c_double
+    msg = ctypes.create_string_buffer(256)
+    for mode, count in ((0, 100_000), (1, 600_000), (2, 150_000)):
+        assert host_formatter.check_parse(ctypes.c_uint64(2000 + mode), ctypes.c_int64(count), mode, msg) == 0, msg.value.decode()
+    status = ctypes.c_int()
+    for text, want in (("0", 0.0), ("-0", -0.0), ("1e-400", 0.0), ("1e400", float("inf")), ("-1e400", float("-inf")), ("4.94066e-324", 5e-324),
+                       ("2.4703282292062327e-324", 0.0), ("2.4703282292062328e-324", 5e-324), (".5", 0.5), ("5.", 5.0), ("+1E+2", 100.0)):
+        got = host_formatter.parse_double(text.encode(), len(text), ctypes.byref(status))
+        assert status.value == 0 and got == want and np.signbit(got) == np.signbit(want), text
+    for text in ("inf", "nan", "-inf", "", "-", "1e", "1e+", "0x10", "1.2.3", "12a", "1" * 41, "."):
+        host_formatter.parse_double(text.encode(), len(text), ctypes.byref(status))
+        assert status.value == 1, text
+
+
 def test_pvtu_record_through_the_c_abi():
     """host text only (no device): equal to the reference's index file"""
     g = _golden()
@@ -267,6 +334,85 @@ def test_gpu_vtk_record_full_size(tmp_path):
     vb = np.array(payload("velocities").split(), dtype=np.float64).reshape(n, 3)
     assert np.all(np.abs(vb - V) <= 5.1e-6 * np.abs(V))
     c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("container", ["gpuLinkedCells", "gpuVerletClusterLists"])
+def test_gpu_vtk_loader_equals_reference_loader(container, tmp_path):
+    """the reference's piece -> device: every attribute has the bits the unmodified reference loader produced; written
+    again it is the same file (up to the row order of the reference's container, which the loader keeps)"""
+    g = np.load(GOLDEN_LOAD)
+    c = GpuParticleContainer(container, g["box_min"], g["box_max"], 1.0, 0.2, clusterSize=4)
+    assert c.loadVtkParticleRecord(g["piece"]) == len(g["ref_ids"]) == c.getNumberOfParticles("owned")
+    sid, stype, sown = c.downloadIds()
+    col = lambda *names: np.stack([c.downloadColumn(k) for k in names], axis=1)  # noqa: E731
+    assert np.array_equal(sid, g["ref_ids"]) and np.array_equal(stype, g["ref_types"]) and np.all(sown == 1)
+    assert _same_bits(col("X", "Y", "Z"), g["ref_r"]) and _same_bits(col("VX", "VY", "VZ"), g["ref_v"]) and _same_bits(col("FX", "FY", "FZ"), g["ref_f"])
+    assert not np.any(col("OLDFX", "OLDFY", "OLDFZ"))
+    assert np.array_equal(c.vtkParticleRecord(), g["piece"])  # write(load(reference file)) == reference file
+    # a second piece appends; through the file-name logic of the loader
+    w = ParallelVtkWriter("again", str(tmp_path), 3)
+    w.recordParticleStates(7, c)
+    d = GpuParticleContainer(container, g["box_min"], g["box_max"], 1.0, 0.2, clusterSize=4)
+    from autopas_b200 import loadParticlesFromCheckpoint
+    assert loadParticlesFromCheckpoint(str(tmp_path / "again" / "again_Particles_007.pvtu"), 0, 1, d) == len(sid)
+    assert np.array_equal(d.vtkParticleRecord(), g["piece"])
+    c.close()
+    d.close()
+
+
+@pytest.mark.gpu
+def test_gpu_vtk_loader_error_paths():
+    g = np.load(GOLDEN_LOAD)
+    text = bytes(g["piece"])
+    small = GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [5, 5, 5], 1.0, 0.2)
+    with pytest.raises(ApbError) as e:  # AutoPas::addParticle throws for a particle outside the box
+        small.loadVtkParticleRecord(g["piece"])
+    assert e.value.code == capi.ERR_PARTICLE_OUTSIDE and small.getNumberOfParticles("owned") == 0
+    assert small.loadVtkParticleRecord(g["piece"], checkInBox=False) == len(g["ref_ids"])
+    small.close()
+    c = GpuParticleContainer("gpuLinkedCells", g["box_min"], g["box_max"], 1.0, 0.2)
+    with pytest.raises(ApbError, match="not a decimal number"):  # the fixture of the writer test holds "inf -inf nan"
+        c.loadVtkParticleRecord(_golden()["ref_piece"])
+    with pytest.raises(ApbError, match="fewer values"):
+        c.loadVtkParticleRecord(text.replace(b'NumberOfPoints="600"', b'NumberOfPoints="601"'))
+    with pytest.raises(ApbError, match="not found"):
+        c.loadVtkParticleRecord(text.replace(b'"forces"', b'"farces"'))
+    with pytest.raises(ApbError, match="number of particles"):
+        c.loadVtkParticleRecord(text.replace(b'NumberOfPoints="600"', b'NumberOfPoints="0"'))
+    with pytest.raises(ApbError):
+        c.loadVtkParticleRecord(b"hello")
+    assert c.getNumberOfParticles("owned") == 0
+    # values spread over lines differently, extra blanks, more values than needed: operator>> does not care
+    loose = text.replace(b"\n        ", b" \t\n  ", 50)
+    assert c.loadVtkParticleRecord(loose) == 600
+    sid, _, _ = c.downloadIds()
+    assert np.array_equal(sid, g["ref_ids"])
+    c.close()
+
+
+@pytest.mark.gpu
+def test_gpu_vtk_round_trip_full_size():
+    """1 M particles: write -> load into an empty container -> write gives the same bytes, and every loaded value is the
+    correctly rounded double of its text (the oracle's float() of the same tokens)."""
+    rng = np.random.default_rng(33)
+    n, L = 1_000_000, 100.0
+    c = GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [L, L, L], 2.5, 0.3)
+    c.addParticles(rng.uniform(0, L, n), rng.uniform(0, L, n), rng.uniform(0, L, n), rng.permutation(n).astype(np.int64),
+                   rng.integers(0, 3, n).astype(np.int32))
+    for k in ("VX", "VY", "VZ", "FX", "FY", "FZ"):
+        c.uploadColumn(k, rng.normal(size=n) * 10.0 ** rng.integers(-6, 7, n))
+    piece = c.vtkParticleRecord()
+    d = GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [L, L, L], 2.5, 0.3)
+    assert d.loadVtkParticleRecord(piece) == n
+    assert np.array_equal(d.vtkParticleRecord(), piece)
+    want = oracle.vtk_load_particle_record(piece)
+    sid, stype, _ = d.downloadIds()
+    col = lambda *names: np.stack([d.downloadColumn(k) for k in names], axis=1)  # noqa: E731
+    assert np.array_equal(sid, want["ids"]) and np.array_equal(stype, want["types"])
+    assert _same_bits(col("X", "Y", "Z"), want["r"]) and _same_bits(col("VX", "VY", "VZ"), want["v"]) and _same_bits(col("FX", "FY", "FZ"), want["f"])
+    c.close()
+    d.close()
 
 
 if __name__ == "__main__" and "--chunked" in sys.argv:
