@@ -16,7 +16,8 @@ from autopas_b200 import GpuParticleContainer, capi  # noqa: E402
 def record_timing(n):
     """A liquid-density box of n particles with normally distributed velocities and forces."""
     rng = np.random.default_rng(3)
-    L = (n / 0.8442) ** (1 / 3)
+    # (a whole-number box edge: writeWithDynamicPrecision only protects positions that round exactly onto the border)
+    L = float(np.ceil((n / 0.8442) ** (1 / 3)))
     c = GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [L, L, L], 2.5, 0.3)
     try:
         c.addParticles(rng.uniform(0, L, n), rng.uniform(0, L, n), rng.uniform(0, L, n), np.arange(n, dtype=np.int64))
