@@ -6,7 +6,9 @@
 // every owned slot formats its own rows with the exact decimal conversion of vtk_format.cuh, twice: a measuring pass
 // gives the row lengths, one exclusive scan per data array turns them into byte offsets, and the writing pass puts the
 // text where it belongs; the XML scaffolding between the arrays comes from the host. The finished record leaves in one
-// device -> host copy (apb_vtk_particle_record) or through pinned buffers into a file (apb_vtk_write_particle_record). Rows follow the storage order (the order the container's iterators visit), like the reference's.
+// device -> host copy (apb_vtk_particle_record) or through pinned buffers into a file (apb_vtk_write_particle_record).
+// Rows follow the storage order (the order the container's iterators visit), like the reference's. The second half of
+// the file reads such a piece back (apb_vtk_load_particle_record).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
