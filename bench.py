@@ -179,6 +179,29 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def checkpoint_cpu_reference(n=250_000):
+    """cpu_baseline leg for the checkpoint entry: the UNMODIFIED md-flexible writer and loader (oracle/_ref/vtk_ref_writer:
+    ParallelVtkWriter::recordParticleStates and MDFlexConfig::loadParticlesFromCheckpoint, single-threaded like in
+    md-flexible) on a bounded sample of the same kind of box; seconds of the writer / loader alone, scaled to a million
+    particles. None when oracle/_ref did not travel."""
+    import tempfile
+    import oracle
+    if not oracle.have_ref_vtk():
+        return None
+    rng = np.random.default_rng(3)
+    L = float(np.ceil((n / 0.8442) ** (1 / 3)))
+    piece, index = oracle.ref_vtk_records(np.arange(n), rng.uniform(0, L, (n, 3)), rng.normal(size=(n, 3)), rng.normal(size=(n, 3)),
+                                          np.zeros(n, dtype=np.int64), [0, 0, 0], [L, L, L], "bench", 0, 6)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "bench", "data"))
+        piece.tofile(os.path.join(d, "bench", "data", "bench_Particles_0_000000.vtu"))
+        index.tofile(os.path.join(d, "bench", "bench_Particles_000000.pvtu"))
+        oracle.ref_vtk_load(os.path.join(d, "bench", "bench_Particles_000000.pvtu"))
+    return {"kind": "reference", "cores": 1, "sample": f"{n} particles, unmodified ParallelVtkWriter / MDFlexConfig loader",
+            "ms_write_per_million_particles": oracle.ref_vtk_seconds["write"] * 1e3 * 1e6 / n,
+            "ms_load_per_million_particles": oracle.ref_vtk_seconds["load"] * 1e3 * 1e6 / n}
+
+
 def other_configs_cpu_reference(lines, bf):
     """cpu_baseline leg for the side measurements: the unmodified reference (oracle/_ref/libautopas_ref.so: LinkedCells,
     lc_c08 for SPH / lc_c01 for the three-body functor, AoS, newton3 off, OpenMP on all host cores) on the inputs of
@@ -615,6 +638,11 @@ def main():
             try:  # md-flexible's checkpoint of a 4 M-particle box written from the device SoA
                 import bench_vtk
                 line["checkpoint"] = bench_vtk.record_timing(4_000_000)
+                if not args.no_cpu_baseline:
+                    try:
+                        line["checkpoint"]["cpu_reference"] = checkpoint_cpu_reference()
+                    except Exception as exc:
+                        line["checkpoint"]["cpu_reference"] = {"error": repr(exc)}
             except Exception as exc:
                 line["checkpoint"] = {"error": repr(exc)}
         print(json.dumps(line), file=json_out, flush=True)

@@ -563,6 +563,9 @@ def have_ref_vtk():
     return os.path.exists(_REF_VTK)
 
 
+ref_vtk_seconds = {}  # seconds the unmodified writer / loader took in the last ref_vtk_records / ref_vtk_load call
+
+
 def ref_vtk_records(ids, r, v, f, types, box_min, box_max, session="ref", iteration=7, digits=6):
     """The unmodified ParallelVtkWriter (oracle/_ref/vtk_ref_writer, oracle/ref_driver_vtk.cpp) on a stock
     AutoPas<MoleculeLJ> holding these particles -> (bytes of the .vtu piece, bytes of the .pvtu index). The piece lists
@@ -578,8 +581,9 @@ def ref_vtk_records(ids, r, v, f, types, box_min, box_max, session="ref", iterat
             fh.write(_f64(box_max).tobytes())
             fh.write(rec.tobytes())
         os.makedirs(os.path.join(d, "out"))
-        subprocess.run([_REF_VTK, os.path.join(d, "in.bin"), os.path.join(d, "out"), session, str(iteration), str(digits)],
-                       check=True, stdout=subprocess.DEVNULL, cwd=d)
+        done = subprocess.run([_REF_VTK, os.path.join(d, "in.bin"), os.path.join(d, "out"), session, str(iteration), str(digits)],
+                              check=True, capture_output=True, text=True, cwd=d)
+        ref_vtk_seconds["write"] = float(done.stdout.split()[1])  # the writer alone, without filling the container
         it = str(iteration).zfill(digits)
         piece = np.fromfile(os.path.join(d, "out", session, "data", f"{session}_Particles_0_{it}.vtu"), dtype=np.uint8)
         index = np.fromfile(os.path.join(d, "out", session, f"{session}_Particles_{it}.pvtu"), dtype=np.uint8)
@@ -618,7 +622,8 @@ def ref_vtk_load(pvtu_path, rank=0, num_ranks=1):
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         out = os.path.join(d, "particles.bin")
-        subprocess.run([_REF_VTK, "--load", str(pvtu_path), str(rank), str(num_ranks), out], check=True, stdout=subprocess.DEVNULL)
+        done = subprocess.run([_REF_VTK, "--load", str(pvtu_path), str(rank), str(num_ranks), out], check=True, capture_output=True, text=True)
+        ref_vtk_seconds["load"] = float(done.stdout.split()[1])
         raw = np.fromfile(out, dtype=np.uint8)
     n = int(raw[:8].view(np.int64)[0])
     rec = raw[8:].view(np.dtype([("r", "<f8", 3), ("v", "<f8", 3), ("f", "<f8", 3), ("id", "<i8"), ("type", "<i8")]))

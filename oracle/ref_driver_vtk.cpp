@@ -17,6 +17,7 @@
 // ParallelVtkWriter::recordParticleStates is private (the public recordTimestep also wants a RegularGridDecomposition,
 // i.e. md-flexible's whole YAML configuration); the access specifier is lifted for this translation unit only - the
 // writer's source is untouched.
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <vector>
@@ -49,7 +50,9 @@ static int loadMode(int argc, char **argv) {
   if (argc < 6) return 2;
   MDFlexConfig config;
   config.checkpointfile.value = argv[2];
+  const auto t0 = std::chrono::steady_clock::now();
   config.loadParticlesFromCheckpoint(static_cast<size_t>(std::atoll(argv[3])), static_cast<size_t>(std::atoll(argv[4])));
+  const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   std::FILE *out = std::fopen(argv[5], "wb");
   if (!out) return 3;
   const int64_t n = static_cast<int64_t>(config.particles.size());
@@ -60,7 +63,7 @@ static int loadMode(int argc, char **argv) {
     std::fwrite(&q, sizeof q, 1, out);
   }
   std::fclose(out);
-  std::printf("%lld\n", static_cast<long long>(n));
+  std::printf("%lld %.6f\n", static_cast<long long>(n), seconds);
   return 0;
 }
 
@@ -99,7 +102,10 @@ int main(int argc, char **argv) {
     autoPas.addParticle(p);
   }
   ParallelVtkWriter writer(argv[3], argv[2], std::atoi(argv[5]));
+  const auto t0 = std::chrono::steady_clock::now();
   writer.recordParticleStates(static_cast<size_t>(std::atoll(argv[4])), autoPas);
-  std::printf("%zu\n", autoPas.getNumberOfParticles(autopas::IteratorBehavior::owned));
+  const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  // particles, seconds the writer took (bench.py quotes it next to the device-side record)
+  std::printf("%zu %.6f\n", autoPas.getNumberOfParticles(autopas::IteratorBehavior::owned), seconds);
   return 0;
 }
