@@ -815,8 +815,9 @@ class ParallelVtkWriter:
         self._session, self._digits, self._rank, self._ranks = sessionName, int(maximumNumberOfDigitsInIteration), int(rank), int(numberOfRanks)
         self._sessionFolder = os.path.join(outputFolder, sessionName) + "/"
         self._dataFolder = self._sessionFolder + "data/"
-        if self._rank == 0:
-            os.makedirs(self._dataFolder, exist_ok=True)
+        # (the reference lets rank 0 create the folders and broadcasts their names, ParallelVtkWriter.cpp:22-41; without
+        # that synchronisation point every rank makes sure they exist)
+        os.makedirs(self._dataFolder, exist_ok=True)
 
     def pvtuRecord(self, currentIteration):
         lib = capi.load()
