@@ -179,6 +179,35 @@ def test_parser_equals_strtod(host_formatter):
         assert status.value == 1, text
 
 
+def test_checkpoint_piece_selection_follows_the_reference(tmp_path):
+    """MDFlexConfig::loadParticlesFromCheckpoint (MDFlexConfig.cpp:648-671): with as many ranks as pieces each rank
+    loads its own piece, otherwise rank 0 loads all and the others none; piece names are rebuilt from the index's own
+    name (:93-117), not from its Piece entries. Host logic only (a recording stand-in for the container)."""
+    from autopas_b200 import checkpointPieces, loadParticlesFromCheckpoint
+    os.makedirs(tmp_path / "out" / "spinodal_run" / "data")
+    index = tmp_path / "out" / "spinodal_run" / "spinodal_run_Particles_0250000.pvtu"
+    oracle.vtk_pvtu_record("spinodal_run", 4, 250000, 7).tofile(str(index))
+    names = [str(tmp_path / "out" / "spinodal_run" / "data" / f"spinodal_run_Particles_{k}_0250000.vtu") for k in range(4)]
+    assert checkpointPieces(str(index)) == names
+    for k, name in enumerate(names):
+        np.frombuffer(f"piece {k}".encode(), dtype=np.uint8).tofile(name)
+
+    class Recorder:
+        def __init__(self):
+            self.seen = []
+
+        def loadVtkParticleRecord(self, data, checkInBox=True):
+            self.seen.append(bytes(data).decode())
+            return 10
+
+    for rank in range(4):
+        rec = Recorder()
+        assert loadParticlesFromCheckpoint(str(index), rank, 4, rec) == 10 and rec.seen == [f"piece {rank}"]
+    for rank, want in ((0, [f"piece {k}" for k in range(4)]), (1, [])):
+        rec = Recorder()
+        assert loadParticlesFromCheckpoint(str(index), rank, 2, rec) == 10 * len(want) and rec.seen == want
+
+
 def test_pvtu_record_through_the_c_abi():
     """host text only (no device): equal to the reference's index file"""
     g = _golden()
