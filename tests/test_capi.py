@@ -88,6 +88,13 @@ def test_no_cpu_fallback():
         GpuParticleContainer("gpuLinkedCells", [0, 0, 0], [10, 10, 10], 1.0, 0.2)
     assert e.value.code == capi.ERR_CUDA
     assert "no CPU fallback" in str(e.value)
+    # without a handle there is nothing to compute with: the checkpoint entry points refuse as well (only the .pvtu
+    # index, plain host text, needs no device)
+    import ctypes
+    lib, n = capi.load(), ctypes.c_int64()
+    assert lib.apb_vtk_particle_record(None, None, 0, ctypes.byref(n)) == capi.ERR_INVALID_ARGUMENT
+    assert lib.apb_vtk_write_particle_record(None, b"/tmp/never.vtu", ctypes.byref(n)) == capi.ERR_INVALID_ARGUMENT
+    assert lib.apb_vtk_load_particle_record(None, b"<", 1, 1, ctypes.byref(n)) == capi.ERR_INVALID_ARGUMENT
 
 
 def test_invalid_configs_are_rejected_before_touching_the_device():
