@@ -985,6 +985,17 @@ class GpuParticleContainer : public autopas::ParticleContainerInterface<Particle
     return static_cast<size_t>(bytes);
   }
 
+  /// md-flexible's checkpoint loader for one piece (loadParticlesFromRankRecord + addParticle,
+  /// examples/md-flexible/src/configuration/MDFlexConfig.cpp:91-180): the particles of the piece's bytes are parsed on the
+  /// device and appended as owned particles; returns their number. A particle outside the box throws like addParticle.
+  size_t loadVtkParticleRecord(const std::string &pieceBytes, bool checkInBox = true) {
+    syncToDevice();
+    int64_t added = 0;
+    check(apb_vtk_load_particle_record(_h, pieceBytes.data(), static_cast<int64_t>(pieceBytes.size()), checkInBox ? 1 : 0, &added));
+    _mirrorValid = false;
+    return static_cast<size_t>(added);
+  }
+
   /// the C handle, for device-resident extensions (apb_run_steps, apb_exchange_halos, ...)
   [[nodiscard]] apb_handle handle() {
     syncToDevice();
